@@ -1,0 +1,91 @@
+// Internal context of libflvis_b200 (not part of the ABI).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+#include "../../include/flvis_b200.h"
+
+struct LevelGeom {
+  int w, h, pitch;   // pitch in bytes (multiple of 128)
+  size_t off;        // byte offset of the level inside one stream's pyramid block
+};
+
+struct PyrGeom {
+  int nlev;
+  LevelGeom lv[FLV_MAX_LEVELS];
+  size_t stream_stride;  // bytes per stream per slot
+};
+
+struct flv_ctx {
+  int device;
+  int S;         // max streams
+  int w, h;
+  int max_pts;
+  PyrGeom geom;
+  uint8_t* pyr[FLV_NUM_SLOTS];   // each S * geom.stream_stride bytes
+  cudaStream_t stream;
+  bool own_stream;
+  long long launches;
+  char err[512];
+
+  // staging for FLV_MEM_HOST calls (pinned host + device mirrors)
+  void* h_stage; size_t h_stage_bytes;
+  void* d_stage; size_t d_stage_bytes;
+
+  // LK
+  int* d_npts;                    // [S]
+  // GFTT
+  int gftt_cap;                   // max corners out
+  int cand_cap;                   // max NMS candidates per stream
+  float* d_eig;                   // [S][h][w]
+  int* d_eigmax;                  // [S] float bits (non-negative) via atomicMax
+  unsigned long long* d_cand;     // [S][cand_cap] key = val_bits<<32 | addr
+  int* d_ncand;                   // [S]
+  unsigned long long* d_sorted;   // [S][cand_cap] keys re-ordered by cell
+  float* d_corners;               // [S][gftt_cap][2]
+  int* d_ncorners;                // [S]
+  int* d_flags;                   // [S] overflow flags
+  int max_cells;
+  // FeatureDEM
+  double* d_exist;                // [S][max_pts][2]
+  int* d_nexist;                  // [S]
+  float* d_newxy;                 // [S][max_pts][2]
+  int* d_nnew;                    // [S]
+  // BA
+  int ba_max_poses, ba_max_lms, ba_max_edges;
+  void* ba_ws;                    // device workspace
+  size_t ba_ws_bytes;
+};
+
+#define FLV_CUDA(ctx, call)                                                            \
+  do {                                                                                 \
+    cudaError_t e__ = (call);                                                          \
+    if (e__ != cudaSuccess) {                                                          \
+      snprintf((ctx)->err, sizeof((ctx)->err), "%s:%d %s: %s", __FILE__, __LINE__, #call, \
+               cudaGetErrorString(e__));                                               \
+      return FLV_ERR_CUDA;                                                             \
+    }                                                                                  \
+  } while (0)
+
+#define FLV_FAIL(ctx, code, ...)                          \
+  do {                                                    \
+    snprintf((ctx)->err, sizeof((ctx)->err), __VA_ARGS__); \
+    return (code);                                        \
+  } while (0)
+
+// staging helpers (capi.cu)
+int flv_stage_reserve(flv_ctx* ctx, size_t bytes);
+
+// kernel launchers (one per .cu)
+int flv_launch_pyramid(flv_ctx* ctx, int slot, int n_streams);
+int flv_launch_lk(flv_ctx* ctx, int src_slot, int dst_slot, int n_streams, const int* d_npts,
+                  const float* d_prev, const float* d_init, float* d_next, uint8_t* d_status,
+                  float* d_err, int nlev_used, int max_iter, double eps2, double min_eig_thr);
+int flv_launch_gftt(flv_ctx* ctx, int slot, int n_streams, int max_corners, double quality,
+                    double min_distance);
+int flv_launch_region(flv_ctx* ctx, int slot, int n_streams, const flv_feature_params* prm,
+                      int redetect);
+int flv_gftt_init(flv_ctx* ctx);
+size_t flv_mindist_smem(int cand_cap, int max_cells);
+int flv_ba_free(flv_ctx* ctx);

@@ -1,0 +1,167 @@
+/*
+ * flvis_b200 -- C ABI of the Blackwell-native FLVIS hot path (libflvis_b200.so).
+ *
+ * The reference (HKPolyU-UAV/FLVIS) has no FFI around its hot path: the heavy calls are C++
+ * member functions that call OpenCV / g2o in-process.  Each entry point below names the
+ * reference call it replaces (paths relative to the reference tree).  The C++ host classes
+ * in flvis_b200/host/ (same names and argument meaning as the reference's) forward to these.
+ *
+ * Conventions
+ *   - every function returns FLV_OK (0) or a negative flv_status; nothing throws or aborts;
+ *   - one flv_ctx per GPU; it owns `max_streams` independent stream slots (one camera
+ *     sequence each) that are processed by ONE launch per stage (batched);
+ *   - `mem` says where the caller's arrays live: FLV_MEM_HOST (the library stages them
+ *     through pinned buffers and synchronises before returning) or FLV_MEM_DEVICE (device
+ *     pointers on ctx's device, work is enqueued on the ctx stream, no synchronisation);
+ *   - per-stream arrays are laid out [stream][max_pts] with the ctx's `max_pts` stride;
+ *   - images are 8-bit single channel, row-major.
+ */
+#ifndef FLVIS_B200_H
+#define FLVIS_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct flv_ctx flv_ctx;
+
+typedef enum {
+  FLV_OK = 0,
+  FLV_ERR_INVALID = -1,   /* bad argument */
+  FLV_ERR_CUDA = -2,      /* CUDA runtime error (see flv_last_error) */
+  FLV_ERR_NOMEM = -3,
+  FLV_ERR_UNSUPPORTED = -4, /* parameter combination the kernels do not implement */
+  FLV_ERR_OVERFLOW = -5   /* a device-side capacity was exceeded (candidate list, window) */
+} flv_status;
+
+typedef enum { FLV_MEM_HOST = 0, FLV_MEM_DEVICE = 1 } flv_memspace;
+
+#define FLV_MAX_LEVELS 4      /* 31x31 window: every FLVIS image size gives 4 pyramid levels */
+#define FLV_NUM_SLOTS 4       /* image/pyramid slots per stream (prev0, cur0, cur1, spare) */
+#define FLV_NUM_REGIONS 16    /* FeatureDEM's 4x4 grid, feature_dem.cpp:38-53 */
+
+/* ---- context ---------------------------------------------------------------------------- */
+int flv_create(flv_ctx** out, int device, int max_streams, int img_w, int img_h, int max_pts);
+void flv_destroy(flv_ctx* ctx);
+/* Enqueue all work on `cuda_stream` (a cudaStream_t, e.g. torch's current stream). NULL = own stream. */
+int flv_set_stream(flv_ctx* ctx, void* cuda_stream);
+int flv_sync(flv_ctx* ctx);
+const char* flv_last_error(flv_ctx* ctx);
+const char* flv_version(void);
+/* Number of kernels this context has launched since creation (bench.py's gpu_launches). */
+long long flv_launch_count(flv_ctx* ctx);
+/* Geometry of pyramid level `level` (0 = full image): returns width/height/pitch/offset. */
+int flv_level_info(flv_ctx* ctx, int level, int* w, int* h, int* pitch, size_t* offset);
+int flv_num_levels(flv_ctx* ctx);
+
+/* ---- images + pyramid (K1) ---------------------------------------------------------------
+ * Replaces the image hand-over of F2FTracking::image_feed (src/frontend/f2f_tracking.cpp:59-145)
+ * and cv::buildOpticalFlowPyramid inside cv::calcOpticalFlowPyrLK (called at
+ * src/processing/lkorb_tracking.cpp:64-73, src/processing/camera_frame.cpp:124-128).
+ * `imgs` holds n_streams images back to back: image s starts at imgs + s*img_stride_bytes,
+ * rows are row_stride_bytes apart.  Level 0 of slot `slot` is overwritten. */
+int flv_upload_images(flv_ctx* ctx, int slot, int n_streams, const uint8_t* imgs,
+                      size_t row_stride_bytes, size_t img_stride_bytes, flv_memspace mem);
+/* pyrDown chain (5x5 Gaussian, (s+128)>>8, REFLECT_101) for levels 1..L-1 of `slot`. */
+int flv_build_pyramid(flv_ctx* ctx, int slot, int n_streams);
+/* Copy pyramid level `level` of (slot, stream) out as a tight w*h image (tests / debugging). */
+int flv_download_level(flv_ctx* ctx, int slot, int stream, int level, uint8_t* out, flv_memspace mem);
+
+/* ---- pyramidal Lucas-Kanade (K2 frame->frame, K3 left->right) ------------------------------
+ * Replaces cv::calcOpticalFlowPyrLK(prev, next, prevPts, nextPts, status, err, Size(31,31),
+ * maxLevel, TermCriteria(COUNT+EPS, 30, 1e-3), OPTFLOW_USE_INITIAL_FLOW) at
+ * src/processing/lkorb_tracking.cpp:64-73 (maxLevel 10) and src/processing/camera_frame.cpp:124-128
+ * (maxLevel 5).  Pyramids of both slots must have been built.  init_xy is the initial flow
+ * (USE_INITIAL_FLOW); next_xy may alias init_xy.  win must be 31. */
+typedef struct {
+  int win;          /* 31 */
+  int max_level;    /* levels used = min(max_level, built levels-1)+1 */
+  int max_iter;     /* 30 */
+  double eps;       /* 1e-3 (squared internally, like OpenCV) */
+  double min_eig_threshold; /* 1e-4 */
+} flv_lk_params;
+int flv_lk_track(flv_ctx* ctx, int src_slot, int dst_slot, int n_streams, const int* n_pts,
+                 const float* prev_xy, const float* init_xy, float* next_xy, uint8_t* status,
+                 float* err, const flv_lk_params* prm, flv_memspace mem);
+
+/* ---- Shi-Tomasi corners (K4) ---------------------------------------------------------------
+ * Replaces cv::goodFeaturesToTrack(img, corners, maxCorners, quality, minDistance[, mask=255])
+ * at src/processing/feature_dem.cpp:160 and :221 (blockSize 3, Sobel 3, no Harris).
+ * Output: xy_out[s][i] integer-valued float coordinates in response-descending order,
+ * n_out[s] corners (<= max_corners <= ctx max_corner capacity). */
+int flv_gftt(flv_ctx* ctx, int slot, int n_streams, int max_corners, double quality,
+             double min_distance, float* xy_out, int* n_out, int out_stride_pts, flv_memspace mem);
+/* The f32 min-eigenvalue response map of (slot, stream) computed by the last flv_gftt (tests). */
+int flv_download_eig(flv_ctx* ctx, int stream, float* out, flv_memspace mem);
+/* Capacity of the corner output (max value of max_corners). */
+int flv_gftt_capacity(flv_ctx* ctx);
+
+/* ---- FeatureDEM region selection (K5) ------------------------------------------------------
+ * Replaces FeatureDEM::detect (src/processing/feature_dem.cpp:215-266) and
+ * FeatureDEM::redetect (:124-213) including calHarrisR (:59-88) and fillIntoRegion (:92-121);
+ * runs flv_gftt internally (2*gftt_num corners for detect, gftt_num for redetect).
+ * existing_xy: [s][max_pts][2] f64 (redetect only; the reference passes vector<Vec2>).
+ * new_xy: [s][max_pts][2] f32, n_new[s]; ordered region 0..15, within region by acceptance. */
+typedef struct {
+  int max_region_feature_num;  /* feature_para1 */
+  int min_region_feature_num;  /* feature_para2 (parsed, unused by the reference) */
+  int boundary_dis;            /* floor(feature_para3/2) */
+  int gftt_num;                /* feature_para4 */
+  double gftt_ql;              /* feature_para5 */
+  int gftt_dis;                /* feature_para6 */
+} flv_feature_params;
+int flv_feature_detect(flv_ctx* ctx, int slot, int n_streams, const flv_feature_params* prm,
+                       float* new_xy, int* n_new, flv_memspace mem);
+int flv_feature_redetect(flv_ctx* ctx, int slot, int n_streams, const flv_feature_params* prm,
+                         const double* existing_xy, const int* n_existing, float* new_xy,
+                         int* n_new, flv_memspace mem);
+
+/* ---- local bundle adjustment (K7-K10) and pose-only BA ---------------------------------------
+ * Replaces the g2o calls of LocalMapNodeletClass::frame_callback
+ * (src/backend/vo_localmap.cpp:292-319: initializeOptimization(); optimize(12); chi2>3 edge
+ * cull; initializeOptimization(); optimize(8)) -- BlockSolver_6_3 + LM + Huber(1) +
+ * EdgeSE3ProjectXYZ -- and of OptimizeInFrame::optimize (src/processing/optimize_in_frame.cpp:10-90).
+ * One problem per stream; the whole Levenberg-Marquardt loop runs on the device.
+ * Poses are g2o SE3Quat order: [qx qy qz qw tx ty tz] of T_c_w. */
+typedef struct {
+  int n_poses;        /* P  (slots 0..P-1) */
+  int n_landmarks;    /* L */
+  int n_edges;        /* E */
+  int fixed_pose;     /* index of the fixed pose vertex, -1 = none */
+  int fix_landmarks;  /* 1 = pose-only BA (all points fixed, optimize_in_frame.cpp:41) */
+  double fx, fy, cx, cy;
+} flv_ba_problem;
+typedef struct {
+  int iters1;         /* 12 (local map) / 2 (pose only) */
+  int iters2;         /* 8 / 2 */
+  double huber_delta; /* 1.0 */
+  double cull_chi2;   /* 3.0 */
+  int min_edges_after_cull; /* 0 (local map) / 10 (pose only: fail if fewer) */
+} flv_ba_params;
+typedef struct {
+  int iterations_run; /* total LM iterations executed (both phases) */
+  int n_culled;       /* edges removed by the chi2 cull */
+  int ok;             /* 0 if the solve failed / too few edges */
+  int reserved;
+  double chi2_initial, chi2_after1, chi2_final; /* robustified active chi2 */
+  double lambda_final;
+} flv_ba_stats;
+/* Arrays are per stream with fixed strides given at flv_ba_reserve:
+ *   poses [s][max_poses][7], landmarks [s][max_lms][3], edge_pose/edge_lm [s][max_edges] (indices
+ *   into the stream's pose / landmark arrays), edge_uv [s][max_edges][2],
+ *   edge_active [s][max_edges] (in: 0 = already culled; out: 0 for edges culled by this call).
+ * Vertex ordering inside the solver follows g2o: poses by index, landmarks by index, edges in
+ * array order (the host keeps them in g2o id / insertion order). */
+int flv_ba_reserve(flv_ctx* ctx, int max_poses, int max_landmarks, int max_edges);
+int flv_ba_optimize(flv_ctx* ctx, int n_streams, const flv_ba_problem* problems,
+                    const flv_ba_params* prm, double* poses, double* landmarks,
+                    const int* edge_pose, const int* edge_lm, const double* edge_uv,
+                    uint8_t* edge_active, flv_ba_stats* stats, flv_memspace mem);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FLVIS_B200_H */
