@@ -16,7 +16,7 @@ NUM_SLOTS = 4
 SYMBOLS = [
     "flv_create", "flv_destroy", "flv_set_stream", "flv_sync", "flv_last_error", "flv_version",
     "flv_launch_count", "flv_level_info", "flv_num_levels", "flv_upload_images", "flv_build_pyramid",
-    "flv_download_level", "flv_lk_track", "flv_gftt", "flv_download_eig", "flv_gftt_capacity",
+    "flv_download_level", "flv_lk_track", "flv_select_tracked", "flv_gftt", "flv_download_eig", "flv_gftt_capacity",
     "flv_feature_detect", "flv_feature_redetect", "flv_ba_reserve", "flv_ba_optimize",
 ]
 
@@ -75,6 +75,7 @@ def load_library(path=LIB_PATH):
     lib.flv_download_level.argtypes = [vp, C.c_int, C.c_int, C.c_int, vp, C.c_int]
     lib.flv_lk_track.argtypes = [vp, C.c_int, C.c_int, C.c_int, vp, vp, vp, vp, vp, vp,
                                  C.POINTER(LKParams), C.c_int]
+    lib.flv_select_tracked.argtypes = [vp, C.c_int, vp, vp, vp, vp, vp, vp, vp]
     lib.flv_gftt.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double, vp, vp, C.c_int, C.c_int]
     lib.flv_download_eig.argtypes = [vp, C.c_int, vp, C.c_int]
     lib.flv_feature_detect.argtypes = [vp, C.c_int, C.c_int, C.POINTER(FeatureParams), vp, vp, C.c_int]
@@ -214,6 +215,11 @@ class Context:
                                         C.c_void_p(d_prev), C.c_void_p(d_init), C.c_void_p(d_next),
                                         C.c_void_p(d_status), C.c_void_p(d_err), C.byref(prm), MEM_DEVICE))
 
+    def select_tracked_dev(self, n_streams, d_npts, d_prev, d_next, d_status, d_keep, d_out, d_out64):
+        self._chk(self.lib.flv_select_tracked(self.h, n_streams, C.c_void_p(d_npts), C.c_void_p(d_prev),
+                                              C.c_void_p(d_next), C.c_void_p(d_status), C.c_void_p(d_keep),
+                                              C.c_void_p(d_out), C.c_void_p(d_out64)))
+
     # -- GFTT / FeatureDEM
     def gftt(self, slot, n_streams, max_corners, quality, min_distance):
         xy = np.zeros((n_streams, max_corners, 2), np.float32)
@@ -230,6 +236,10 @@ class Context:
         out = np.empty((self.hh, self.w), np.float32)
         self._chk(self.lib.flv_download_eig(self.h, stream, _ptr(out), MEM_HOST))
         return out
+
+    def feature_detect_dev(self, slot, n_streams, fp, d_xy, d_n):
+        self._chk(self.lib.flv_feature_detect(self.h, slot, n_streams, C.byref(fp), C.c_void_p(d_xy), C.c_void_p(d_n),
+                                              MEM_DEVICE))
 
     def feature_detect(self, slot, n_streams, fp):
         xy = np.zeros((n_streams, self.max_pts, 2), np.float32)

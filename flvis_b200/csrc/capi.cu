@@ -220,6 +220,14 @@ int flv_lk_track(flv_ctx* ctx, int src_slot, int dst_slot, int n_streams, const 
   return FLV_OK;
 }
 
+int flv_select_tracked(flv_ctx* ctx, int n_streams, const int* n_pts, const float* prev_xy,
+                       const float* next_xy, const uint8_t* status, uint8_t* keep, float* out_xy,
+                       double* out_xy_f64) {
+  if (!ctx || !n_pts || !prev_xy || !next_xy || !status || n_streams < 1 || n_streams > ctx->S)
+    return FLV_ERR_INVALID;
+  return flv_launch_select(ctx, n_streams, n_pts, prev_xy, next_xy, status, keep, out_xy, out_xy_f64);
+}
+
 static int check_flags(flv_ctx* ctx, int n_streams) {
   // host-memory calls synchronise anyway: surface device-side capacity overflows as an error
   int* hf = (int*)ctx->h_stage;

@@ -86,6 +86,8 @@ int flv_launch_gftt(flv_ctx* ctx, int slot, int n_streams, int max_corners, doub
                     double min_distance);
 int flv_launch_region(flv_ctx* ctx, int slot, int n_streams, const flv_feature_params* prm,
                       int redetect);
+int flv_launch_select(flv_ctx* ctx, int n_streams, const int* d_npts, const float* prev, const float* next,
+                      const uint8_t* status, uint8_t* keep, float* out, double* out64);
 int flv_gftt_init(flv_ctx* ctx);
 size_t flv_mindist_smem(int cand_cap, int max_cells);
 int flv_ba_free(flv_ctx* ctx);

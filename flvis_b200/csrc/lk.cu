@@ -217,7 +217,32 @@ lk_track_kernel(const uint8_t* __restrict__ pyrI, const uint8_t* __restrict__ py
   }
 }
 
+__global__ void select_tracked_kernel(const int* __restrict__ npts, const float2* __restrict__ prev,
+                                      const float2* __restrict__ next, const uint8_t* __restrict__ status,
+                                      uint8_t* __restrict__ keep, float2* __restrict__ out,
+                                      double2* __restrict__ out64, int max_pts, int w, int h) {
+  const int s = blockIdx.y, i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= npts[s]) return;
+  const size_t k = (size_t)s * max_pts + i;
+  const float2 n = next[k], p = prev[k];
+  const bool ok = status[k] == 1 && n.x > 0.f && n.y > 0.f && n.x < (float)(w - 1) && n.y < (float)(h - 1);
+  const float2 o = ok ? n : p;
+  if (keep) keep[k] = ok ? 1 : 0;
+  if (out) out[k] = o;
+  if (out64) out64[k] = make_double2((double)o.x, (double)o.y);
+}
+
 }  // namespace
+
+int flv_launch_select(flv_ctx* ctx, int n_streams, const int* d_npts, const float* prev, const float* next,
+                      const uint8_t* status, uint8_t* keep, float* out, double* out64) {
+  dim3 grid((ctx->max_pts + 127) / 128, n_streams);
+  select_tracked_kernel<<<grid, 128, 0, ctx->stream>>>(d_npts, (const float2*)prev, (const float2*)next, status, keep,
+                                                       (float2*)out, (double2*)out64, ctx->max_pts, ctx->w, ctx->h);
+  ctx->launches++;
+  FLV_CUDA(ctx, cudaGetLastError());
+  return FLV_OK;
+}
 
 int flv_launch_lk(flv_ctx* ctx, int src_slot, int dst_slot, int n_streams, const int* d_npts,
                   const float* d_prev, const float* d_init, float* d_next, uint8_t* d_status,

@@ -1,0 +1,144 @@
+"""Batched device-resident frame loop used by bench.py and the multi-GPU driver.
+
+Order of stages per stereo frame = the order F2FTracking::image_feed runs them
+(/root/reference/src/frontend/f2f_tracking.cpp:187-355): LK frame->frame (:227) -> redetect (:291) ->
+depthInnovation's left->right LK (:326 -> camera_frame.cpp:124-128); every KF_EVERY-th frame of a stream
+is a keyframe and triggers that stream's local BA (vo_localmap.cpp:292-319).  All S streams share one
+launch per stage.  torch is plumbing here: device buffers, pinned host buffers, events.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import capi
+
+
+def make_ba_batch(n_streams, window, seed=0, n_landmarks=1500, obs_per_frame=480):
+    """Synthetic local-BA windows (ba_demo pattern, SURVEY.md 8(d) C1: W=10, E=4800, L~1500)."""
+    from . import ba_synth
+    return ba_synth.make_batch(n_streams, window, n_landmarks, obs_per_frame, seed)
+
+
+def cpu_ba_solve(batch, s):
+    """One local-BA solve of stream s with the CPU oracle port (bench cpu_baseline leg only)."""
+    from oracle import ba_ref
+    p = batch.problem(s)
+    ba_ref.optimize(p.copy(), 12, 8)
+
+
+class FrontendBench:
+    def __init__(self, n_streams, w, h, max_pts, npts, feature_para, device_index, ba_window=10, kf_every=5, seed=0):
+        import torch
+        self.torch = torch
+        self.S, self.w, self.h, self.max_pts, self.npts = n_streams, w, h, max_pts, npts
+        self.dev = torch.device("cuda", device_index)
+        self.ctx = capi.Context(n_streams, w, h, max_pts, device=device_index)
+        self.ctx.set_stream(torch.cuda.current_stream(self.dev).cuda_stream)
+        self.fp = capi.FeatureParams(int(feature_para[0]), int(feature_para[1]), int(feature_para[2] // 2),
+                                     int(feature_para[3]), float(feature_para[4]), int(feature_para[5]))
+        S, M = n_streams, max_pts
+        z = lambda *shape, dtype: torch.zeros(*shape, dtype=dtype, device=self.dev)
+        self.d_npts = z(S, dtype=torch.int32)
+        self.d_pts = z(S, M, 2, dtype=torch.float32)        # current feature positions in prev0
+        self.d_next = z(S, M, 2, dtype=torch.float32)
+        self.d_status = z(S, M, dtype=torch.uint8)
+        self.d_err = z(S, M, dtype=torch.float32)
+        self.d_keep = z(S, M, dtype=torch.uint8)
+        self.d_cur = z(S, M, 2, dtype=torch.float32)        # positions in cur0 after the keep rule
+        self.d_cur64 = z(S, M, 2, dtype=torch.float64)
+        self.d_right = z(S, M, 2, dtype=torch.float32)
+        self.d_rstatus = z(S, M, dtype=torch.uint8)
+        self.d_rerr = z(S, M, dtype=torch.float32)
+        self.d_new = z(S, M, 2, dtype=torch.float32)
+        self.d_nnew = z(S, dtype=torch.int32)
+        # pinned result buffers for the e2e mode
+        pin = lambda *shape, dtype: torch.zeros(*shape, dtype=dtype).pin_memory()
+        self.h_cur = pin(S, M, 2, dtype=torch.float32); self.h_keep = pin(S, M, dtype=torch.uint8)
+        self.h_right = pin(S, M, 2, dtype=torch.float32); self.h_rstatus = pin(S, M, dtype=torch.uint8)
+        self.h_new = pin(S, M, 2, dtype=torch.float32); self.h_nnew = pin(S, dtype=torch.int32)
+        self.slots = [0, 1, 2]          # prev0, cur0, cur1
+        self.kf_every = kf_every
+        self.collect_lk = False
+        self.lk_events = []
+        self.lk_ms = 0.0
+        self.has_ba = False
+        self.ba = None
+        try:
+            from . import ba_synth
+            self.ba = ba_synth.DeviceBatch(self.ctx, make_ba_batch(n_streams, ba_window, seed=seed), self.dev)
+            self.has_ba = True
+        except ImportError:
+            self.ba = None
+        self.h2d_bytes_per_step = 2 * S * w * h + (self.ba.h2d_bytes_per_step(kf_every) if self.has_ba else 0)
+        self.d2h_bytes_per_step = (S * M * (8 + 1) * 2 + S * M * 8 + S * 4 +
+                                   (self.ba.d2h_bytes_per_step(kf_every) if self.has_ba else 0))
+
+    # frame pool -------------------------------------------------------------------------------
+    def load_pool(self, f0, f1):
+        torch = self.torch
+        self.n_pool = f0.shape[0]
+        self.h_pool0 = torch.from_numpy(f0).pin_memory()
+        self.h_pool1 = torch.from_numpy(f1).pin_memory()
+        self.d_pool0 = self.h_pool0.to(self.dev)
+        self.d_pool1 = self.h_pool1.to(self.dev)
+
+    def reset(self):
+        """Frame 0: upload, pyramid, FeatureDEM::detect => the tracked set (init_frame, f2f_tracking.cpp:402-453)."""
+        ctx, S = self.ctx, self.S
+        prev0 = self.slots[0]
+        ctx.upload_dev(prev0, S, self.d_pool0[0].data_ptr())
+        ctx.build_pyramid(prev0, S)
+        ctx.feature_detect_dev(prev0, S, self.fp, self.d_pts.data_ptr(), self.d_npts.data_ptr())
+        self.torch.cuda.synchronize()
+
+    def _lk(self, src, dst, d_prev, d_init, d_out, d_st, d_err, max_level):
+        if self.collect_lk:
+            e0 = self.torch.cuda.Event(enable_timing=True); e1 = self.torch.cuda.Event(enable_timing=True)
+            e0.record()
+        self.ctx.lk_track_dev(src, dst, self.S, self.d_npts.data_ptr(), d_prev.data_ptr(), d_init.data_ptr(),
+                              d_out.data_ptr(), d_st.data_ptr(), d_err.data_ptr(), max_level=max_level)
+        if self.collect_lk:
+            e1.record()
+            self.lk_events.append((e0, e1))
+
+    def finish_lk_timing(self):
+        self.torch.cuda.synchronize()
+        ms = sum(a.elapsed_time(b) for a, b in self.lk_events)
+        n = len(self.lk_events)
+        self.lk_events = []
+        self.collect_lk = False
+        return ms, n
+
+    def step(self, i, mode):
+        ctx, S = self.ctx, self.S
+        prev0, cur0, cur1 = self.slots
+        k = (i + 1) % self.n_pool
+        if mode == "host":
+            ctx.upload_host_async(cur0, S, self.h_pool0[k].data_ptr())
+            ctx.upload_host_async(cur1, S, self.h_pool1[k].data_ptr())
+        else:
+            ctx.upload_dev(cur0, S, self.d_pool0[k].data_ptr())
+            ctx.upload_dev(cur1, S, self.d_pool1[k].data_ptr())
+        ctx.build_pyramid(cur0, S)
+        ctx.build_pyramid(cur1, S)
+        # frame -> frame LK (lkorb_tracking.cpp:64-73) + keep rule (:98-119)
+        self._lk(prev0, cur0, self.d_pts, self.d_pts, self.d_next, self.d_status, self.d_err, 10)
+        ctx.select_tracked_dev(S, self.d_npts.data_ptr(), self.d_pts.data_ptr(), self.d_next.data_ptr(),
+                               self.d_status.data_ptr(), self.d_keep.data_ptr(), self.d_cur.data_ptr(),
+                               self.d_cur64.data_ptr())
+        # redetect on cur0 against the surviving features (f2f_tracking.cpp:291 -> feature_dem.cpp:124)
+        ctx.feature_redetect_dev(cur0, S, self.fp, self.d_cur64.data_ptr(), self.d_npts.data_ptr(),
+                                 self.d_new.data_ptr(), self.d_nnew.data_ptr())
+        # left -> right LK (camera_frame.cpp:124-128, maxLevel 5), initial flow = cam0 position
+        self._lk(cur0, cur1, self.d_cur, self.d_cur, self.d_right, self.d_rstatus, self.d_rerr, 5)
+        if self.has_ba:
+            self.ba.step(i, mode, self.kf_every)
+        if mode == "host":
+            nb = True
+            self.h_cur.copy_(self.d_cur, non_blocking=nb); self.h_keep.copy_(self.d_keep, non_blocking=nb)
+            self.h_right.copy_(self.d_right, non_blocking=nb); self.h_rstatus.copy_(self.d_rstatus, non_blocking=nb)
+            self.h_new.copy_(self.d_new, non_blocking=nb); self.h_nnew.copy_(self.d_nnew, non_blocking=nb)
+            self.torch.cuda.current_stream(self.dev).synchronize()      # the caller consumes the results every frame
+        # the tracked set of the next frame lives in cur0
+        self.d_pts, self.d_cur = self.d_cur, self.d_pts
+        self.slots = [cur0, prev0, cur1]

@@ -87,6 +87,14 @@ int flv_lk_track(flv_ctx* ctx, int src_slot, int dst_slot, int n_streams, const 
                  const float* prev_xy, const float* init_xy, float* next_xy, uint8_t* status,
                  float* err, const flv_lk_params* prm, flv_memspace mem);
 
+/* Keep rule of LKORBTracking::tracking (src/processing/lkorb_tracking.cpp:98-119): a tracked point survives
+ * iff status==1 && 0<x<w-1 && 0<y<h-1.  keep[s][i] = 1/0; out_xy[s][i] = next if kept else prev (f32) and the
+ * same as f64 in out_xy_f64 (the Vec2 list FeatureDEM::redetect takes); either output may be NULL.
+ * Device pointers only (FLV_MEM_DEVICE); this is glue for device-resident pipelines. */
+int flv_select_tracked(flv_ctx* ctx, int n_streams, const int* n_pts, const float* prev_xy,
+                       const float* next_xy, const uint8_t* status, uint8_t* keep, float* out_xy,
+                       double* out_xy_f64);
+
 /* ---- Shi-Tomasi corners (K4) ---------------------------------------------------------------
  * Replaces cv::goodFeaturesToTrack(img, corners, maxCorners, quality, minDistance[, mask=255])
  * at src/processing/feature_dem.cpp:160 and :221 (blockSize 3, Sobel 3, no Harris).
