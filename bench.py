@@ -140,10 +140,10 @@ def run_ours(args):
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         bench.lk_ms = 0.0
         bench.collect_lk = True
-        ev0.record()
+        ev0.record(bench.stream)
         for i in range(steps):
             bench.step(warmup + i, mode)
-        ev1.record()
+        ev1.record(bench.stream)
         barrier()
         ms = ev0.elapsed_time(ev1)
         lk_ms, lk_calls = bench.finish_lk_timing()

@@ -33,7 +33,9 @@ class FrontendBench:
         self.S, self.w, self.h, self.max_pts, self.npts = n_streams, w, h, max_pts, npts
         self.dev = torch.device("cuda", device_index)
         self.ctx = capi.Context(n_streams, w, h, max_pts, device=device_index)
-        self.ctx.set_stream(torch.cuda.current_stream(self.dev).cuda_stream)
+        # a dedicated (non-default) torch stream: the library launches on it and all events are recorded on it
+        self.stream = torch.cuda.Stream(self.dev)
+        self.ctx.set_stream(self.stream.cuda_stream)
         self.fp = capi.FeatureParams(int(feature_para[0]), int(feature_para[1]), int(feature_para[2] // 2),
                                      int(feature_para[3]), float(feature_para[4]), int(feature_para[5]))
         S, M = n_streams, max_pts
@@ -85,6 +87,7 @@ class FrontendBench:
     def reset(self):
         """Frame 0: upload, pyramid, FeatureDEM::detect => the tracked set (init_frame, f2f_tracking.cpp:402-453)."""
         ctx, S = self.ctx, self.S
+        self.torch.cuda.synchronize()
         prev0 = self.slots[0]
         ctx.upload_dev(prev0, S, self.d_pool0[0].data_ptr())
         ctx.build_pyramid(prev0, S)
@@ -94,11 +97,11 @@ class FrontendBench:
     def _lk(self, src, dst, d_prev, d_init, d_out, d_st, d_err, max_level):
         if self.collect_lk:
             e0 = self.torch.cuda.Event(enable_timing=True); e1 = self.torch.cuda.Event(enable_timing=True)
-            e0.record()
+            e0.record(self.stream)
         self.ctx.lk_track_dev(src, dst, self.S, self.d_npts.data_ptr(), d_prev.data_ptr(), d_init.data_ptr(),
                               d_out.data_ptr(), d_st.data_ptr(), d_err.data_ptr(), max_level=max_level)
         if self.collect_lk:
-            e1.record()
+            e1.record(self.stream)
             self.lk_events.append((e0, e1))
 
     def finish_lk_timing(self):
@@ -110,6 +113,10 @@ class FrontendBench:
         return ms, n
 
     def step(self, i, mode):
+        with self.torch.cuda.stream(self.stream):
+            self._step(i, mode)
+
+    def _step(self, i, mode):
         ctx, S = self.ctx, self.S
         prev0, cur0, cur1 = self.slots
         k = (i + 1) % self.n_pool
@@ -138,7 +145,7 @@ class FrontendBench:
             self.h_cur.copy_(self.d_cur, non_blocking=nb); self.h_keep.copy_(self.d_keep, non_blocking=nb)
             self.h_right.copy_(self.d_right, non_blocking=nb); self.h_rstatus.copy_(self.d_rstatus, non_blocking=nb)
             self.h_new.copy_(self.d_new, non_blocking=nb); self.h_nnew.copy_(self.d_nnew, non_blocking=nb)
-            self.torch.cuda.current_stream(self.dev).synchronize()      # the caller consumes the results every frame
+            self.stream.synchronize()      # the caller consumes the results every frame
         # the tracked set of the next frame lives in cur0
         self.d_pts, self.d_cur = self.d_cur, self.d_pts
         self.slots = [cur0, prev0, cur1]
