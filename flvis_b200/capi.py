@@ -17,7 +17,8 @@ SYMBOLS = [
     "flv_create", "flv_destroy", "flv_set_stream", "flv_sync", "flv_last_error", "flv_version",
     "flv_launch_count", "flv_level_info", "flv_num_levels", "flv_upload_images", "flv_build_pyramid",
     "flv_download_level", "flv_lk_track", "flv_select_tracked", "flv_gftt", "flv_download_eig", "flv_gftt_capacity",
-    "flv_feature_detect", "flv_feature_redetect", "flv_ba_reserve", "flv_ba_optimize",
+    "flv_feature_detect", "flv_feature_redetect", "flv_ba_reserve", "flv_ba_optimize", "flv_gftt_keep_response",
+    "flv_ba_profile",
 ]
 
 
@@ -68,6 +69,8 @@ def load_library(path=LIB_PATH):
     lib.flv_launch_count.argtypes = [vp]
     lib.flv_num_levels.argtypes = [vp]
     lib.flv_gftt_capacity.argtypes = [vp]
+    lib.flv_gftt_keep_response.argtypes = [vp, C.c_int]
+    lib.flv_ba_profile.argtypes = [vp, C.c_int, vp]
     lib.flv_level_info.argtypes = [vp, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int),
                                    C.POINTER(C.c_size_t)]
     lib.flv_upload_images.argtypes = [vp, C.c_int, C.c_int, vp, C.c_size_t, C.c_size_t, C.c_int]
@@ -231,6 +234,14 @@ class Context:
     def gftt_dev(self, slot, n_streams, max_corners, quality, min_distance, d_xy, d_n, stride_pts):
         self._chk(self.lib.flv_gftt(self.h, slot, n_streams, max_corners, quality, min_distance, C.c_void_p(d_xy),
                                     C.c_void_p(d_n), stride_pts, MEM_DEVICE))
+
+    def keep_response(self, enable=True):
+        self._chk(self.lib.flv_gftt_keep_response(self.h, 1 if enable else 0))
+
+    def ba_profile(self, stream):
+        out = np.zeros(8, np.int64)
+        self._chk(self.lib.flv_ba_profile(self.h, stream, _ptr(out)))
+        return out
 
     def download_eig(self, stream):
         out = np.empty((self.hh, self.w), np.float32)

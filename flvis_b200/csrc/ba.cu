@@ -42,6 +42,7 @@ struct BAArgs {
   flv_ba_stats* stats;
   int max_poses, max_lms, max_edges;
   unsigned char* ws; size_t ws_stride;
+  long long* prof;   // [S][8] cycle counters or nullptr
 };
 
 // ---- SE3 helpers (g2o SE3Quat semantics, quaternion stored x,y,z,w) ----------------------------
@@ -182,7 +183,12 @@ struct Sh {   // fixed-size shared state
   int pcount[BA_MAX_POSES];
   int queue[BA_WARPS][64];
   int np, fail, nact;
+  long long prof[8], tlast;   // cycle counters: 0 chi2, 1 build, 2 schur, 3 cholesky, 4 substitution, 5 update, 6 setup
 };
+
+__device__ __forceinline__ void mark(Sh& sh, int slot) {
+  if (threadIdx.x == 0) { const long long now = clock64(); sh.prof[slot] += now - sh.tlast; sh.tlast = now; }
+}
 
 struct Ws {   // per-stream global workspace views
   double *pbk, *lbk, *W, *Hll, *bl, *Dinv, *xl;
@@ -409,6 +415,7 @@ __device__ void solve_system(const flv_ba_problem& pb, double lambda, double* S,
   }
   if (tid == 0) sh.fail = 0;
   __syncthreads();
+  mark(sh, 2);
   // dense Cholesky S = L L^T (lower part, in place), right-looking, whole CTA
   for (int j = 0; j < n; ++j) {
     if (tid == 0) {
@@ -427,6 +434,7 @@ __device__ void solve_system(const flv_ba_problem& pb, double lambda, double* S,
     }
     __syncthreads();
   }
+  mark(sh, 3);
   // forward / backward substitution by one warp (n <= 144)
   if (warp == 0) {
     for (int i = 0; i < n; ++i) {
@@ -445,6 +453,7 @@ __device__ void solve_system(const flv_ba_problem& pb, double lambda, double* S,
     }
   }
   __syncthreads();
+  mark(sh, 4);
 }
 
 // state update (sparse_optimizer.cpp:433-446) incl. landmark back-substitution (block_solver.hpp:422-444).
@@ -525,11 +534,13 @@ __global__ void __launch_bounds__(BA_THREADS, 1) ba_kernel(BAArgs a) {
     if (tid == 0) { st.ok = 0; st.reserved = 1; a.stats[s] = st; }
     return;
   }
+  if (tid == 0) { for (int i = 0; i < 8; ++i) sh.prof[i] = 0; sh.tlast = clock64(); }
   st.chi2_initial = robust_chi2(pb, cam, poses, lms, ep, el, uv, act, delta, sh.red);
   double lambda = 0;
   for (int phase = 0; phase < 2; ++phase) {
     const int iters = phase == 0 ? a.prm.iters1 : a.prm.iters2;
     setup_active(pb, ep, el, act, ws, sh);
+    mark(sh, 6);
     if (sh.np > BA_MAX_FREE) { st.ok = 0; st.reserved = 2; break; }
     const int n = 6 * sh.np;
     double* S = dyn;
@@ -537,7 +548,9 @@ __global__ void __launch_bounds__(BA_THREADS, 1) ba_kernel(BAArgs a) {
     double ni = 2;
     for (int it = 0; it < iters; ++it) {
       double currentChi = robust_chi2(pb, cam, poses, lms, ep, el, uv, act, delta, sh.red);
+      mark(sh, 0);
       build_system(pb, cam, poses, lms, uv, delta, ws, sh);
+      mark(sh, 1);
       if (it == 0) {
         double md = 0;
         if (tid < sh.np) {
@@ -559,7 +572,9 @@ __global__ void __launch_bounds__(BA_THREADS, 1) ba_kernel(BAArgs a) {
         if (ok2) {
           scale = apply_update(pb, lambda, poses, lms, ws, sh);
           __syncthreads();
+          mark(sh, 5);
           tempChi = robust_chi2(pb, cam, poses, lms, ep, el, uv, act, delta, sh.red);
+          mark(sh, 0);
         } else {
           tempChi = 1.7976931348623157e308;
         }
@@ -598,7 +613,10 @@ __global__ void __launch_bounds__(BA_THREADS, 1) ba_kernel(BAArgs a) {
   }
   st.chi2_final = robust_chi2(pb, cam, poses, lms, ep, el, uv, act, delta, sh.red);
   st.lambda_final = lambda;
-  if (tid == 0) a.stats[s] = st;
+  if (tid == 0) {
+    a.stats[s] = st;
+    if (a.prof) for (int i = 0; i < 8; ++i) a.prof[8 * s + i] = sh.prof[i];
+  }
 }
 
 size_t ws_stride_bytes(int max_poses, int max_lms, int max_edges) {
@@ -626,7 +644,7 @@ int flv_ba_reserve(flv_ctx* ctx, int max_poses, int max_landmarks, int max_edges
   flv_ba_free(ctx);
   size_t stride = ws_stride_bytes(max_poses, max_landmarks, max_edges);
   // tail: device copies of problems / stats / staging are carved after the per-stream blocks
-  size_t total = stride * ctx->S + (size_t)ctx->S * (sizeof(flv_ba_problem) + sizeof(flv_ba_stats)) + 512;
+  size_t total = stride * ctx->S + (size_t)ctx->S * (sizeof(flv_ba_problem) + sizeof(flv_ba_stats) + 64) + 512;
   FLV_CUDA(ctx, cudaMalloc(&ctx->ba_ws, total));
   ctx->ba_ws_bytes = total;
   ctx->ba_max_poses = max_poses; ctx->ba_max_lms = max_landmarks; ctx->ba_max_edges = max_edges;
@@ -649,6 +667,7 @@ int flv_ba_optimize(flv_ctx* ctx, int n_streams, const flv_ba_problem* problems,
   flv_ba_problem* d_prob = (flv_ba_problem*)tail;
   flv_ba_stats* d_stats = (flv_ba_stats*)(tail + (size_t)ctx->S * sizeof(flv_ba_problem));
   BAArgs a;
+  a.prof = (long long*)(tail + (size_t)ctx->S * (sizeof(flv_ba_problem) + sizeof(flv_ba_stats)));
   a.prm = *prm; a.max_poses = MP; a.max_lms = ML; a.max_edges = ME;
   a.ws = (unsigned char*)ctx->ba_ws; a.ws_stride = stride;
   const int nfree = MP < BA_MAX_FREE ? MP : BA_MAX_FREE;
@@ -693,6 +712,17 @@ int flv_ba_optimize(flv_ctx* ctx, int n_streams, const flv_ba_problem* problems,
     if (stats[s].reserved)
       FLV_FAIL(ctx, FLV_ERR_UNSUPPORTED, "stream %d: %s", s,
                stats[s].reserved == 1 ? "pose count outside [1,32]" : "more than 24 free poses (reduced system > 144)");
+  return FLV_OK;
+}
+
+/* debug: cycle counters of the last flv_ba_optimize for `stream` (8 values, see Sh::prof) */
+int flv_ba_profile(flv_ctx* ctx, int stream, long long* out8) {
+  if (!ctx || !ctx->ba_ws || !out8 || stream < 0 || stream >= ctx->S) return FLV_ERR_INVALID;
+  const size_t stride = ws_stride_bytes(ctx->ba_max_poses, ctx->ba_max_lms, ctx->ba_max_edges);
+  unsigned char* tail = (unsigned char*)ctx->ba_ws + stride * ctx->S;
+  long long* d = (long long*)(tail + (size_t)ctx->S * (sizeof(flv_ba_problem) + sizeof(flv_ba_stats)));
+  FLV_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  FLV_CUDA(ctx, cudaMemcpy(out8, d + 8 * stream, 64, cudaMemcpyDeviceToHost));
   return FLV_OK;
 }
 

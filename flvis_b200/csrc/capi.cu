@@ -79,6 +79,9 @@ int flv_create(flv_ctx** out, int device, int max_streams, int img_w, int img_h,
   rc |= dev_alloc(ctx, &ctx->d_cand, S * ctx->cand_cap);
   rc |= dev_alloc(ctx, &ctx->d_ncand, S);
   rc |= dev_alloc(ctx, &ctx->d_sorted, S * ctx->cand_cap);
+  rc |= dev_alloc(ctx, &ctx->d_items, S * ctx->cand_cap);
+  rc |= dev_alloc(ctx, &ctx->d_state, S * ctx->cand_cap);
+  rc |= dev_alloc(ctx, &ctx->d_need_full, S);
   rc |= dev_alloc(ctx, &ctx->d_corners, S * ctx->gftt_cap * 2);
   rc |= dev_alloc(ctx, &ctx->d_ncorners, S);
   rc |= dev_alloc(ctx, &ctx->d_flags, S);
@@ -100,7 +103,7 @@ void flv_destroy(flv_ctx* ctx) {
   cudaDeviceSynchronize();
   for (int i = 0; i < FLV_NUM_SLOTS; ++i) cudaFree(ctx->pyr[i]);
   cudaFree(ctx->d_npts); cudaFree(ctx->d_eig); cudaFree(ctx->d_eigmax); cudaFree(ctx->d_cand);
-  cudaFree(ctx->d_ncand); cudaFree(ctx->d_sorted); cudaFree(ctx->d_corners); cudaFree(ctx->d_ncorners);
+  cudaFree(ctx->d_ncand); cudaFree(ctx->d_sorted); cudaFree(ctx->d_items); cudaFree(ctx->d_state); cudaFree(ctx->d_need_full); cudaFree(ctx->d_corners); cudaFree(ctx->d_ncorners);
   cudaFree(ctx->d_flags); cudaFree(ctx->d_exist); cudaFree(ctx->d_nexist); cudaFree(ctx->d_newxy);
   cudaFree(ctx->d_nnew);
   flv_ba_free(ctx);
@@ -131,6 +134,11 @@ const char* flv_last_error(flv_ctx* ctx) { return ctx ? ctx->err : "null context
 long long flv_launch_count(flv_ctx* ctx) { return ctx ? ctx->launches : 0; }
 int flv_num_levels(flv_ctx* ctx) { return ctx ? ctx->geom.nlev : 0; }
 int flv_gftt_capacity(flv_ctx* ctx) { return ctx ? ctx->gftt_cap : 0; }
+int flv_gftt_keep_response(flv_ctx* ctx, int enable) {
+  if (!ctx) return FLV_ERR_INVALID;
+  ctx->keep_eig = enable ? 1 : 0;
+  return FLV_OK;
+}
 
 int flv_level_info(flv_ctx* ctx, int level, int* w, int* h, int* pitch, size_t* offset) {
   if (!ctx || level < 0 || level >= ctx->geom.nlev) return FLV_ERR_INVALID;
@@ -260,6 +268,7 @@ int flv_gftt(flv_ctx* ctx, int slot, int n_streams, int max_corners, double qual
 
 int flv_download_eig(flv_ctx* ctx, int stream, float* out, flv_memspace mem) {
   if (!ctx || !out || stream < 0 || stream >= ctx->S) return FLV_ERR_INVALID;
+  if (!ctx->keep_eig) FLV_FAIL(ctx, FLV_ERR_INVALID, "response map not kept: call flv_gftt_keep_response(ctx, 1) first");
   FLV_CUDA(ctx, cudaMemcpyAsync(out, ctx->d_eig + (size_t)stream * ctx->w * ctx->h, (size_t)ctx->w * ctx->h * 4,
                                 mem == FLV_MEM_HOST ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice,
                                 ctx->stream));

@@ -42,7 +42,11 @@ struct flv_ctx {
   int* d_eigmax;                  // [S] float bits (non-negative) via atomicMax
   unsigned long long* d_cand;     // [S][cand_cap] key = val_bits<<32 | addr
   int* d_ncand;                   // [S]
-  unsigned long long* d_sorted;   // [S][cand_cap] keys re-ordered by cell
+  unsigned long long* d_sorted;   // [S][cand_cap] slow path: keys sorted by priority
+  int* d_items;                   // [S][cand_cap] slow path: ranks grouped by cell
+  unsigned char* d_state;         // [S][cand_cap] slow path: greedy state
+  int* d_need_full;               // [S] fast path could not decide -> slow path runs
+  int keep_eig;                   // debug: also write the f32 response map
   float* d_corners;               // [S][gftt_cap][2]
   int* d_ncorners;                // [S]
   int* d_flags;                   // [S] overflow flags

@@ -3,14 +3,18 @@
 // Reference call sites: src/processing/feature_dem.cpp:160 (redetect) and :221 (detect).
 // Bit-level contract: oracle/gftt_ref.py (pinned to cv2 4.13.0 by tests/golden/gftt_*.npz).
 //
-//   mineig_kernel   u8 image -> f32 min-eigenvalue map + per-stream max   (HBM: read w*h, write 4*w*h)
-//   nms_kernel      threshold q*max, 3x3 non-max test, emit (value,y,x) keys
-//   mindist_kernel  one CTA per stream: bin keys into d x d cells, decide OpenCV's sequential greedy
-//                   "accept if no stronger accepted corner within d" as a parallel fixed point
-//                   (a corner's fate depends only on stronger corners, so iterating "reject if a
-//                   stronger neighbour is accepted / accept if all stronger neighbours are rejected"
-//                   reproduces the sequential result exactly), then bitonic-sort the accepted keys
-//                   and keep the strongest N.
+//   corner_response_kernel  one warp per 26-column x 32-row strip marches down the image with the
+//       I / covariance / box-sum / eigenvalue rows in registers (neighbours by warp shuffle, no shared
+//       memory): min-eigenvalue response, 3x3 non-max test and candidate emission fused, the response
+//       map is never written (only when the debug flag asks for it).  HBM traffic = the u8 image once.
+//   mindist_fast_kernel     one CTA per stream: threshold q*max, take the strongest <= 8192 candidates
+//       (a prefix of the priority order, cut at a value-histogram bin), sort them in shared memory,
+//       and decide OpenCV's sequential greedy "accept if no stronger accepted corner within d" as a
+//       parallel fixed point (a corner's fate depends only on stronger corners, so iterating "reject
+//       if a stronger neighbour is accepted / accept once all stronger neighbours are rejected"
+//       reproduces the sequential result exactly).  If the prefix yields fewer than N corners and
+//       candidates were left out, the stream is flagged and
+//   mindist_full_kernel     redoes it over all candidates out of global memory (rare slow path).
 //
 // Float contract of the response map (found by probing cv2, see oracle/gftt_ref.py header): explicit
 // __fmaf_rn where OpenCV's AVX2 body contracts, plain mul/add in its scalar tail (x >= w - w%32).
@@ -24,141 +28,131 @@ __device__ __forceinline__ int reflect101(int i, int n) {
   i = i < 0 ? -i : i;
   return i >= n ? 2 * n - 2 - i : i;
 }
+__device__ __forceinline__ int clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
 
 // ------------------------------------------------------------------------------------------------
-constexpr int ETW = 64, ETH = 16;            // output tile
-constexpr int ITW = ETW + 4, ITH = ETH + 4;  // image tile (halo 2)
-constexpr int CTW = ETW + 2, CTH = ETH + 2;  // covariance tile (halo 1)
+constexpr int CS_ROWS = 32;   // output rows per strip
+constexpr int CS_COLS = 26;   // output columns per warp (32 lanes - 3 halo lanes each side)
+constexpr int CS_WARPS = 4;
 
-__global__ void __launch_bounds__(256)
-mineig_kernel(const uint8_t* __restrict__ img_base, size_t stream_stride, int pitch, int w, int h,
-              float* __restrict__ eig_base, int* __restrict__ eigmax) {
-  __shared__ uint8_t It[ITH][ITW + 4];
-  __shared__ float cxx[CTH][CTW + 1], cxy[CTH][CTW + 1], cyy[CTH][CTW + 1];
-  __shared__ int smax[8];
-  const int s = blockIdx.z;
+struct Row3 { int l, c, r; };
+
+__global__ void __launch_bounds__(CS_WARPS * 32)
+corner_response_kernel(const uint8_t* __restrict__ img_base, size_t stream_stride, int pitch, int w, int h,
+                       int nsx, int nsy, float* __restrict__ eig_out, int* __restrict__ eigmax, double quality,
+                       unsigned long long* __restrict__ cand_base, int* __restrict__ ncand, int cand_cap) {
+  const int lane = threadIdx.x & 31;
+  const int strip = blockIdx.x * CS_WARPS + (threadIdx.x >> 5);
+  if (strip >= nsx * nsy) return;
+  const int s = blockIdx.y;
+  const int sx = strip % nsx, sy = strip / nsx;
   const uint8_t* img = img_base + (size_t)s * stream_stride;
-  float* eig = eig_base + (size_t)s * w * h;
-  const int x0 = blockIdx.x * ETW, y0 = blockIdx.y * ETH;
-  const int tid = threadIdx.x;
-  for (int i = tid; i < ITH * ITW; i += 256) {
-    int r = i / ITW, c = i - r * ITW;
-    int y = reflect101(y0 - 2 + r, h), x = reflect101(x0 - 2 + c, w);
-    // tiles hanging far over the right/bottom edge can reflect twice; clamp keeps loads in range
-    y = min(max(y, 0), h - 1); x = min(max(x, 0), w - 1);
-    It[r][c] = img[(size_t)y * pitch + x];
-  }
-  __syncthreads();
+  const int x = sx * CS_COLS - 3 + lane;
+  const int y0 = sy * CS_ROWS;
+  const bool in_x = x >= 0 && x < w;
+  const int xl = clampi(reflect101(x, w), 0, w - 1);      // column this lane loads
+  const bool left_from_up = (x - 1 < 0);                  // reflect101(-1) = 1  -> neighbour value sits in lane+1
+  const bool right_from_down = (x + 1 > w - 1);           // reflect101(w) = w-2 -> neighbour value sits in lane-1
   const float k1 = (float)(1.0 / (4 * 3 * 255.0));
   const float k0 = 2.f * k1;
-  const int body = w - (w & 31);
-  for (int i = tid; i < CTH * CTW; i += 256) {
-    int r = i / CTW, c = i - r * CTW;
-    int px = x0 - 1 + c, py = y0 - 1 + r;
+  const bool body = x < w - (w & 31);
+  const bool out_lane = lane >= 3 && lane < 3 + CS_COLS && in_x;
+  const float pre_thr = (float)((double)__int_as_float(*(volatile int*)&eigmax[s]) * quality);
+  float* eig_s = eig_out ? eig_out + (size_t)s * w * h : nullptr;
+  unsigned long long* cand = cand_base + (size_t)s * cand_cap;
+
+  auto load_row = [&](int r) -> Row3 {
+    const int yy = clampi(reflect101(r, h), 0, h - 1);
+    const int c = img[(size_t)yy * pitch + xl];
+    const int up = __shfl_down_sync(FULL, c, 1), dn = __shfl_up_sync(FULL, c, 1);
+    Row3 o;
+    o.c = c;
+    o.l = left_from_up ? up : dn;
+    o.r = right_from_down ? dn : up;
+    return o;
+  };
+
+  Row3 Ia, Ib = load_row(y0 - 3), Ic = load_row(y0 - 2);
+  double Rm[3] = {0, 0, 0}, R0[3] = {0, 0, 0}, Rp[3] = {0, 0, 0};
+  float Ea = 0.f, Eb = 0.f, m3a = 0.f, m3b = 0.f, nb = 0.f;   // eig rows y-2 (a), y-1 (b); nb = max(left,right) of row b
+  float best = 0.f;
+  for (int r = y0 - 2; r <= y0 + CS_ROWS + 1; ++r) {
+    Ia = Ib; Ib = Ic; Ic = load_row(r + 1);
+    // covariance of row r at this lane's column (only inside the image)
     float vxx = 0.f, vxy = 0.f, vyy = 0.f;
-    if (px <= w && py <= h) {
-      // covariance at the REFLECTED coordinate (boxFilter border), computed there from scratch
-      int qx = reflect101(px, w), qy = reflect101(py, h);
-      int cxm = reflect101(qx - 1, w) - (x0 - 2), cx0 = qx - (x0 - 2), cxp = reflect101(qx + 1, w) - (x0 - 2);
-      int rym = reflect101(qy - 1, h) - (y0 - 2), ry0 = qy - (y0 - 2), ryp = reflect101(qy + 1, h) - (y0 - 2);
-      int a_m = It[rym][cxm], a_0 = It[rym][cx0], a_p = It[rym][cxp];
-      int b_m = It[ry0][cxm], b_0 = It[ry0][cx0], b_p = It[ry0][cxp];
-      int c_m = It[ryp][cxm], c_0 = It[ryp][cx0], c_p = It[ryp][cxp];
-      // Dx: rows of [-1 0 1] (exact), columns k1*[1 2 1] as fma(k1, r(y-1)+r(y+1), k0*r(y))
-      float dx = __fmaf_rn(k1, (float)((a_p - a_m) + (c_p - c_m)), __fmul_rn(k0, (float)(b_p - b_m)));
-      // Dy: rows smoothed with k1*[1 2 1] (FMA body / plain tail), then row difference
+    if (r >= 0 && r < h && in_x) {
+      const float dx = __fmaf_rn(k1, (float)((Ia.r - Ia.l) + (Ic.r - Ic.l)), __fmul_rn(k0, (float)(Ib.r - Ib.l)));
       float sa, sc;
-      if (qx < body) {
-        sa = __fmaf_rn(k1, (float)a_p, __fmaf_rn(k0, (float)a_0, __fmul_rn(k1, (float)a_m)));
-        sc = __fmaf_rn(k1, (float)c_p, __fmaf_rn(k0, (float)c_0, __fmul_rn(k1, (float)c_m)));
+      if (body) {
+        sa = __fmaf_rn(k1, (float)Ia.r, __fmaf_rn(k0, (float)Ia.c, __fmul_rn(k1, (float)Ia.l)));
+        sc = __fmaf_rn(k1, (float)Ic.r, __fmaf_rn(k0, (float)Ic.c, __fmul_rn(k1, (float)Ic.l)));
       } else {
-        sa = __fadd_rn(__fadd_rn(__fmul_rn(k1, (float)a_m), __fmul_rn(k0, (float)a_0)), __fmul_rn(k1, (float)a_p));
-        sc = __fadd_rn(__fadd_rn(__fmul_rn(k1, (float)c_m), __fmul_rn(k0, (float)c_0)), __fmul_rn(k1, (float)c_p));
+        sa = __fadd_rn(__fadd_rn(__fmul_rn(k1, (float)Ia.l), __fmul_rn(k0, (float)Ia.c)), __fmul_rn(k1, (float)Ia.r));
+        sc = __fadd_rn(__fadd_rn(__fmul_rn(k1, (float)Ic.l), __fmul_rn(k0, (float)Ic.c)), __fmul_rn(k1, (float)Ic.r));
       }
-      float dy = __fsub_rn(sc, sa);
+      const float dy = __fsub_rn(sc, sa);
       vxx = __fmul_rn(dx, dx); vxy = __fmul_rn(dx, dy); vyy = __fmul_rn(dy, dy);
     }
-    cxx[r][c] = vxx; cxy[r][c] = vxy; cyy[r][c] = vyy;
-  }
-  __syncthreads();
-  float best = -1.f;
-  for (int i = tid; i < ETH * ETW; i += 256) {
-    int r = i / ETW, c = i - r * ETW;
-    int x = x0 + c, y = y0 + r;
-    if (x < w && y < h) {
-      double sxx = 0, sxy = 0, syy = 0;
+    // horizontal 3-sum (column reflection = take the other neighbour twice); exact in double
+    Rm[0] = R0[0]; Rm[1] = R0[1]; Rm[2] = R0[2];
+    R0[0] = Rp[0]; R0[1] = Rp[1]; R0[2] = Rp[2];
+    {
+      const float v[3] = {vxx, vxy, vyy};
 #pragma unroll
-      for (int dr = 0; dr < 3; ++dr)
-#pragma unroll
-        for (int dc = 0; dc < 3; ++dc) {
-          sxx += (double)cxx[r + dr][c + dc];
-          sxy += (double)cxy[r + dr][c + dc];
-          syy += (double)cyy[r + dr][c + dc];
-        }
-      float a = __fmul_rn((float)sxx, 0.5f), b = (float)sxy, cc = __fmul_rn((float)syy, 0.5f);
-      float t = __fsub_rn(a, cc);
-      float e = __fsub_rn(__fadd_rn(a, cc), __fsqrt_rn(__fadd_rn(__fmul_rn(t, t), __fmul_rn(b, b))));
-      eig[(size_t)y * w + x] = e;
-      best = fmaxf(best, e);
+      for (int k = 0; k < 3; ++k) {
+        const float up = __shfl_down_sync(FULL, v[k], 1), dn = __shfl_up_sync(FULL, v[k], 1);
+        const float lf = left_from_up ? up : dn, rt = right_from_down ? dn : up;
+        Rp[k] = (double)lf + (double)v[k] + (double)rt;
+      }
     }
+    // eigenvalue of row y = r-1 (rows y-1, y, y+1 of R are Rm, R0, Rp; row reflection at the image border)
+    const int y = r - 1;
+    float e = 0.f;
+    if (y >= 0 && y < h) {
+      const bool top = (y == 0), bot = (y == h - 1);
+      double sxx = R0[0] + (top ? Rp[0] : Rm[0]) + (bot ? Rm[0] : Rp[0]);
+      double sxy = R0[1] + (top ? Rp[1] : Rm[1]) + (bot ? Rm[1] : Rp[1]);
+      double syy = R0[2] + (top ? Rp[2] : Rm[2]) + (bot ? Rm[2] : Rp[2]);
+      const float a = __fmul_rn((float)sxx, 0.5f), b = (float)sxy, c = __fmul_rn((float)syy, 0.5f);
+      const float t = __fsub_rn(a, c);
+      e = __fsub_rn(__fadd_rn(a, c), __fsqrt_rn(__fadd_rn(__fmul_rn(t, t), __fmul_rn(b, b))));
+      if (out_lane && y >= y0 && y < y0 + CS_ROWS) {
+        best = fmaxf(best, e);
+        if (eig_s) eig_s[(size_t)y * w + x] = e;
+      }
+    }
+    const float el = __shfl_up_sync(FULL, e, 1), er = __shfl_down_sync(FULL, e, 1);
+    const float nc = fmaxf(el, er);
+    const float m3c = fmaxf(nc, e);
+    // non-max test of row yy = y-1 (its neighbours are rows a, c and its own left/right)
+    const int yy = y - 1;
+    const bool is = out_lane && yy >= y0 && yy < y0 + CS_ROWS && yy >= 1 && yy < h - 1 && x >= 1 && x < w - 1 &&
+                    Eb > pre_thr && Eb > 0.f && Eb >= m3a && Eb >= m3c && Eb >= nb;
+    const unsigned mask = __ballot_sync(FULL, is);
+    if (mask) {
+      int base = 0;
+      if (lane == 0) base = atomicAdd(&ncand[s], __popc(mask));
+      base = __shfl_sync(FULL, base, 0);
+      if (is) {
+        const int pos = base + __popc(mask & ((1u << lane) - 1));
+        if (pos < cand_cap)
+          cand[pos] = ((unsigned long long)__float_as_uint(Eb) << 32) | ((unsigned)yy << 16) | (unsigned)x;
+      }
+    }
+    Ea = Eb; m3a = m3b; Eb = e; m3b = m3c; nb = nc;
+    (void)Ea;
   }
-  // block max -> atomicMax on the int view (valid ordering for non-negative floats; negatives lose)
-  int bi = __float_as_int(fmaxf(best, 0.f));
+  int bi = __float_as_int(best);
   bi = __reduce_max_sync(FULL, bi);
-  if ((tid & 31) == 0) smax[tid >> 5] = bi;
-  __syncthreads();
-  if (tid < 8) {
-    int v = smax[tid];
-    v = max(v, __shfl_xor_sync(0xffu, v, 4));
-    v = max(v, __shfl_xor_sync(0xffu, v, 2));
-    v = max(v, __shfl_xor_sync(0xffu, v, 1));
-    if (tid == 0) atomicMax(&eigmax[s], v);
-  }
-}
-
-// ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256)
-nms_kernel(const float* __restrict__ eig_base, int w, int h, const int* __restrict__ eigmax,
-           double quality, unsigned long long* __restrict__ cand_base, int* __restrict__ ncand,
-           int cand_cap) {
-  const int s = blockIdx.z;
-  const float* eig = eig_base + (size_t)s * w * h;
-  const int x = blockIdx.x * 32 + (threadIdx.x & 31);
-  const int y = blockIdx.y * 8 + (threadIdx.x >> 5);
-  const float thr = (float)((double)__int_as_float(eigmax[s]) * quality);
-  bool is = false;
-  float c = 0.f;
-  if (x >= 1 && x < w - 1 && y >= 1 && y < h - 1) {
-    c = eig[(size_t)y * w + x];
-    if (c > thr) {
-      const float* p = eig + (size_t)(y - 1) * w + x;
-      float m = fmaxf(fmaxf(p[-1], p[0]), p[1]);
-      p += w; m = fmaxf(m, fmaxf(p[-1], p[1]));
-      p += w; m = fmaxf(m, fmaxf(fmaxf(p[-1], p[0]), p[1]));
-      is = c >= m;
-    }
-  }
-  unsigned mask = __ballot_sync(FULL, is);
-  if (mask) {
-    int lane = threadIdx.x & 31;
-    int base = 0;
-    if (lane == 0) base = atomicAdd(&ncand[s], __popc(mask));
-    base = __shfl_sync(FULL, base, 0);
-    if (is) {
-      int pos = base + __popc(mask & ((1u << lane) - 1));
-      if (pos < cand_cap)
-        cand_base[(size_t)s * cand_cap + pos] =
-            ((unsigned long long)__float_as_uint(c) << 32) | ((unsigned)y << 16) | (unsigned)x;
-    }
-  }
+  if (lane == 0 && bi > 0) atomicMax(&eigmax[s], bi);
 }
 
 // ------------------------------------------------------------------------------------------------
 constexpr int MD_THREADS = 1024;
-constexpr int ACC_CAP = 8192;   // accepted corners that can be sorted (packing bound of d >= 8 on 1241x376)
+constexpr int SEL_CAP = 8192;    // candidates handled by the shared-memory fast path
+constexpr int HBINS = 4096;      // histogram over float bits [30:19]
 
 __device__ __forceinline__ int block_exclusive_scan(int v, int* warp_sums, int* total) {
-  // v: per-thread value; returns exclusive prefix over the block (MD_THREADS threads)
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   int inc = v;
 #pragma unroll
@@ -166,6 +160,7 @@ __device__ __forceinline__ int block_exclusive_scan(int v, int* warp_sums, int* 
     int t = __shfl_up_sync(FULL, inc, o);
     if (lane >= o) inc += t;
   }
+  __syncthreads();
   if (lane == 31) warp_sums[wid] = inc;
   __syncthreads();
   if (wid == 0) {
@@ -183,140 +178,243 @@ __device__ __forceinline__ int block_exclusive_scan(int v, int* warp_sums, int* 
   return warp_sums[wid] + inc - v;
 }
 
-__global__ void __launch_bounds__(MD_THREADS, 1)
-mindist_kernel(const unsigned long long* __restrict__ cand_base, const int* __restrict__ ncand,
-               int cand_cap, unsigned long long* __restrict__ sorted_base, int w, int h,
-               double min_distance, int max_corners, float* __restrict__ corners_base,
-               int* __restrict__ ncorners, int corner_stride, int* __restrict__ flags,
-               int max_cells) {
-  extern __shared__ unsigned char smem_raw[];
-  // layout: acc keys [ACC_CAP] u64 | cell start [max_cells+1] int | cell count [max_cells] int | state [cand_cap] u8
-  unsigned long long* acc = (unsigned long long*)smem_raw;
-  int* cstart = (int*)(acc + ACC_CAP);
-  int* ccount = cstart + (max_cells + 1);
-  unsigned char* state = (unsigned char*)(ccount + max_cells);
-  __shared__ int warp_sums[32];
-  __shared__ int sh_total, sh_nacc;
-
-  const int s = blockIdx.x;
+// Greedy min-distance selection over `n` keys sorted in DESCENDING priority order (index == rank).
+// keys: shared or global; cstart/ccount: ints [ncell+1]/[ncell]; items: ranks grouped by cell; state: u8[n].
+template <typename ItemT>
+__device__ void greedy_fixed_point(const unsigned long long* keys, int n, int cell, int gw, int gh, double d2,
+                                   int* cstart, int* ccount, ItemT* items, unsigned char* state, int* warp_sums,
+                                   int* sh_total) {
   const int tid = threadIdx.x;
-  const unsigned long long* cand = cand_base + (size_t)s * cand_cap;
-  unsigned long long* skey = sorted_base + (size_t)s * cand_cap;
-  int n = ncand[s];
-  if (n > cand_cap) { n = cand_cap; if (tid == 0) atomicOr(&flags[s], 1); }
-  float* corners = corners_base + (size_t)s * corner_stride * 2;
-
-  if (tid == 0) sh_nacc = 0;
-  const bool use_dist = min_distance >= 1.0;
-  if (use_dist) {
-    const int cell = (int)rint(min_distance);
-    const int gw = (w + cell - 1) / cell, gh = (h + cell - 1) / cell;
-    const int ncell = gw * gh;
-    const double d2 = min_distance * min_distance;
-    for (int i = tid; i < ncell; i += MD_THREADS) ccount[i] = 0;
-    __syncthreads();
-    for (int i = tid; i < n; i += MD_THREADS) {
-      unsigned lo = (unsigned)cand[i];
-      int x = lo & 0xffff, y = lo >> 16;
-      atomicAdd(&ccount[(y / cell) * gw + x / cell], 1);
-    }
-    __syncthreads();
-    // exclusive scan of ccount -> cstart (each thread owns a contiguous chunk of cells)
-    const int per = (ncell + MD_THREADS - 1) / MD_THREADS;
-    int local = 0;
-    for (int k = 0; k < per; ++k) { int c = tid * per + k; if (c < ncell) local += ccount[c]; }
-    int ex = block_exclusive_scan(local, warp_sums, &sh_total);
-    for (int k = 0; k < per; ++k) {
-      int c = tid * per + k;
-      if (c < ncell) { cstart[c] = ex; ex += ccount[c]; ccount[c] = 0; }
-    }
-    if (tid == 0) cstart[ncell] = n;
-    __syncthreads();
-    for (int i = tid; i < n; i += MD_THREADS) {
-      unsigned long long k = cand[i];
-      unsigned lo = (unsigned)k;
-      int x = lo & 0xffff, y = lo >> 16;
-      int c = (y / cell) * gw + x / cell;
-      int pos = cstart[c] + atomicAdd(&ccount[c], 1);
-      skey[pos] = k;
-      state[pos] = 0;
-    }
-    __syncthreads();
-    // fixed-point iteration of the greedy rule
-    for (;;) {
-      int pending = 0;
-      for (int i = tid; i < n; i += MD_THREADS) {
-        if (state[i] != 0) continue;
-        const unsigned long long ki = skey[i];
-        const unsigned lo = (unsigned)ki;
-        const int x = lo & 0xffff, y = lo >> 16;
-        const int xc = x / cell, yc = y / cell;
-        const int x1 = max(0, xc - 1), x2 = min(gw - 1, xc + 1);
-        const int y1 = max(0, yc - 1), y2 = min(gh - 1, yc + 1);
-        int verdict = 1;   // 1 accept, 2 reject, 0 wait
-        for (int yy = y1; yy <= y2 && verdict != 2; ++yy) {
-          const int jb = cstart[yy * gw + x1], je = cstart[yy * gw + x2 + 1];
-          for (int j = jb; j < je; ++j) {
-            const unsigned long long kj = skey[j];
-            if (kj <= ki) continue;
-            const unsigned lj = (unsigned)kj;
-            const int dx = x - (int)(lj & 0xffff), dy = y - (int)(lj >> 16);
-            if ((double)(dx * dx + dy * dy) < d2) {
-              const int sj = ((volatile unsigned char*)state)[j];
-              if (sj == 1) { verdict = 2; break; }
-              if (sj == 0) verdict = 0;
-            }
-          }
-        }
-        if (verdict == 0) pending = 1;
-        else ((volatile unsigned char*)state)[i] = (unsigned char)verdict;
-      }
-      if (!__syncthreads_or(pending)) break;
-    }
-    // gather accepted keys
-    for (int i = tid; i < n; i += MD_THREADS) {
-      if (state[i] == 1) {
-        int p = atomicAdd(&sh_nacc, 1);
-        if (p < ACC_CAP) acc[p] = skey[i];
-      }
-    }
-  } else {
-    __syncthreads();
-    for (int i = tid; i < n; i += MD_THREADS) {
-      int p = atomicAdd(&sh_nacc, 1);
-      if (p < ACC_CAP) acc[p] = cand[i];
-    }
+  const int ncell = gw * gh;
+  for (int i = tid; i < ncell; i += MD_THREADS) ccount[i] = 0;
+  __syncthreads();
+  for (int i = tid; i < n; i += MD_THREADS) {
+    const unsigned lo = (unsigned)keys[i];
+    atomicAdd(&ccount[((lo >> 16) / cell) * gw + (lo & 0xffff) / cell], 1);
   }
   __syncthreads();
-  int nacc = sh_nacc;
-  if (nacc > ACC_CAP) { nacc = ACC_CAP; if (tid == 0) atomicOr(&flags[s], 2); }
-  int np2 = 1;
-  while (np2 < nacc) np2 <<= 1;
-  for (int i = nacc + tid; i < np2; i += MD_THREADS) acc[i] = 0ull;
+  const int per = (ncell + MD_THREADS - 1) / MD_THREADS;
+  int local = 0;
+  for (int k = 0; k < per; ++k) { const int c = tid * per + k; if (c < ncell) local += ccount[c]; }
+  int ex = block_exclusive_scan(local, warp_sums, sh_total);
+  for (int k = 0; k < per; ++k) {
+    const int c = tid * per + k;
+    if (c < ncell) { cstart[c] = ex; ex += ccount[c]; ccount[c] = 0; }
+  }
+  if (tid == 0) cstart[ncell] = n;
   __syncthreads();
-  // bitonic sort, descending
+  for (int i = tid; i < n; i += MD_THREADS) {
+    const unsigned lo = (unsigned)keys[i];
+    const int c = ((lo >> 16) / cell) * gw + (lo & 0xffff) / cell;
+    items[cstart[c] + atomicAdd(&ccount[c], 1)] = (ItemT)i;
+    state[i] = 0;
+  }
+  __syncthreads();
+  volatile unsigned char* vstate = state;
+  for (;;) {
+    int pending = 0;
+    for (int i = tid; i < n; i += MD_THREADS) {
+      if (vstate[i] != 0) continue;
+      const unsigned lo = (unsigned)keys[i];
+      const int x = lo & 0xffff, y = lo >> 16;
+      const int xc = x / cell, yc = y / cell;
+      const int x1 = max(0, xc - 1), x2 = min(gw - 1, xc + 1);
+      const int y1 = max(0, yc - 1), y2 = min(gh - 1, yc + 1);
+      int verdict = 1;   // 1 accept, 2 reject, 0 wait
+      for (int yy = y1; yy <= y2 && verdict != 2; ++yy) {
+        const int jb = cstart[yy * gw + x1], je = cstart[yy * gw + x2 + 1];
+        for (int j = jb; j < je; ++j) {
+          const int rj = (int)items[j];
+          if (rj >= i) continue;                    // only stronger corners (smaller rank) matter
+          const unsigned lj = (unsigned)keys[rj];
+          const int dx = x - (int)(lj & 0xffff), dy = y - (int)(lj >> 16);
+          if ((double)(dx * dx + dy * dy) < d2) {
+            const int sj = vstate[rj];
+            if (sj == 1) { verdict = 2; break; }
+            if (sj == 0) verdict = 0;
+          }
+        }
+      }
+      if (verdict == 0) pending = 1;
+      else vstate[i] = (unsigned char)verdict;
+    }
+    if (!__syncthreads_or(pending)) break;
+  }
+}
+
+// bitonic sort of np2 (power of two) u64 keys, descending
+__device__ void bitonic_desc(unsigned long long* a, int np2) {
   for (int k = 2; k <= np2; k <<= 1) {
     for (int j = k >> 1; j > 0; j >>= 1) {
-      for (int i = tid; i < np2; i += MD_THREADS) {
-        int l = i ^ j;
+      for (int i = threadIdx.x; i < np2; i += MD_THREADS) {
+        const int l = i ^ j;
         if (l > i) {
-          unsigned long long a = acc[i], b = acc[l];
-          bool desc = (i & k) == 0;
-          if (desc ? (a < b) : (a > b)) { acc[i] = b; acc[l] = a; }
+          const unsigned long long x = a[i], y = a[l];
+          const bool desc = (i & k) == 0;
+          if (desc ? (x < y) : (x > y)) { a[i] = y; a[l] = x; }
         }
       }
       __syncthreads();
     }
   }
-  int nout = nacc;
-  if (max_corners > 0 && nout > max_corners) nout = max_corners;
-  if (nout > corner_stride) nout = corner_stride;
-  for (int i = tid; i < nout; i += MD_THREADS) {
-    unsigned lo = (unsigned)acc[i];
-    corners[2 * i] = (float)(lo & 0xffff);
-    corners[2 * i + 1] = (float)(lo >> 16);
+}
+
+// write the first `max_corners` accepted keys (rank order) as corners; returns count via ncorners
+__device__ void emit_accepted(const unsigned long long* keys, const unsigned char* state, int n, bool all,
+                              int max_corners, float* corners, int corner_stride, int* ncorners_s, int* warp_sums,
+                              int* sh_total) {
+  const int tid = threadIdx.x;
+  const int per = (n + MD_THREADS - 1) / MD_THREADS;
+  int local = 0;
+  for (int k = 0; k < per; ++k) { const int i = tid * per + k; if (i < n && (all || state[i] == 1)) ++local; }
+  int pos = block_exclusive_scan(local, warp_sums, sh_total);
+  int limit = max_corners < corner_stride ? max_corners : corner_stride;
+  for (int k = 0; k < per; ++k) {
+    const int i = tid * per + k;
+    if (i < n && (all || state[i] == 1)) {
+      if (pos < limit) {
+        const unsigned lo = (unsigned)keys[i];
+        corners[2 * pos] = (float)(lo & 0xffff);
+        corners[2 * pos + 1] = (float)(lo >> 16);
+      }
+      ++pos;
+    }
   }
-  if (tid == 0) ncorners[s] = nout;
+  if (tid == 0) *ncorners_s = *sh_total < limit ? *sh_total : limit;
+}
+
+__global__ void __launch_bounds__(MD_THREADS, 1)
+mindist_fast_kernel(const unsigned long long* __restrict__ cand_base, const int* __restrict__ ncand, int cand_cap,
+                    const int* __restrict__ eigmax, double quality, int w, int h, double min_distance,
+                    int max_corners, float* __restrict__ corners_base, int* __restrict__ ncorners,
+                    int corner_stride, int* __restrict__ flags, int* __restrict__ need_full, int max_cells) {
+  extern __shared__ unsigned char smem_raw[];
+  // layout: keys [SEL_CAP] u64 | cstart [max_cells+1] | ccount/hist [max(max_cells,HBINS)] | items u16 [SEL_CAP] | state [SEL_CAP]
+  unsigned long long* keys = (unsigned long long*)smem_raw;
+  int* cstart = (int*)(keys + SEL_CAP);
+  int* ccount = cstart + (max_cells + 1);
+  const int cc_len = max_cells > HBINS ? max_cells : HBINS;
+  unsigned short* items = (unsigned short*)(ccount + cc_len);
+  unsigned char* state = (unsigned char*)(items + SEL_CAP);
+  __shared__ int warp_sums[32];
+  __shared__ int sh_total, sh_nsel, sh_cut, sh_npass;
+
+  const int s = blockIdx.x, tid = threadIdx.x;
+  const unsigned long long* cand = cand_base + (size_t)s * cand_cap;
+  int n = ncand[s];
+  if (n > cand_cap) { n = cand_cap; if (tid == 0) atomicOr(&flags[s], 1); }
+  float* corners = corners_base + (size_t)s * corner_stride * 2;
+  const float thr = (float)((double)__int_as_float(eigmax[s]) * quality);
+  if (tid == 0) { need_full[s] = 0; sh_nsel = 0; sh_npass = 0; }
+  // 1. histogram of the candidates that pass the quality threshold
+  int* hist = ccount;
+  for (int i = tid; i < HBINS; i += MD_THREADS) hist[i] = 0;
+  __syncthreads();
+  for (int i = tid; i < n; i += MD_THREADS) {
+    const unsigned vb = (unsigned)(cand[i] >> 32);
+    if (__uint_as_float(vb) > thr) atomicAdd(&hist[(vb >> 19) & (HBINS - 1)], 1);
+  }
+  __syncthreads();
+  // 2. lowest bin `cut` such that everything in bins >= cut fits the fast path (suffix sums by one warp)
+  if (tid < 32) {
+    int run = 0, cut = HBINS, npass = 0;
+    for (int b0 = HBINS - 32; b0 >= 0; b0 -= 32) {
+      const int v = hist[b0 + tid];
+      int suf = v;                                        // inclusive suffix sum within the 32-bin chunk
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_down_sync(FULL, suf, o);
+        if (tid + o < 32) suf += t;
+      }
+      const bool fits = run + suf <= SEL_CAP;
+      const unsigned fm = __ballot_sync(FULL, fits);
+      if (cut == b0 + 32) {                               // still contiguous from the top
+        // lanes that fit form a suffix of the chunk (suffix sums are monotone)
+        const int nfit = __popc(fm);
+        if (nfit > 0) cut = b0 + 32 - nfit;
+      }
+      run += __shfl_sync(FULL, suf, 0);
+      npass = run;
+    }
+    if (tid == 0) { sh_cut = cut; sh_npass = npass; }
+  }
+  __syncthreads();
+  const int cut = sh_cut, npass = sh_npass;
+  // 3. gather the selected prefix into shared memory
+  for (int i = tid; i < n; i += MD_THREADS) {
+    const unsigned long long k = cand[i];
+    const unsigned vb = (unsigned)(k >> 32);
+    if (__uint_as_float(vb) > thr && (int)((vb >> 19) & (HBINS - 1)) >= cut) {
+      const int p = atomicAdd(&sh_nsel, 1);
+      if (p < SEL_CAP) keys[p] = k;
+    }
+  }
+  __syncthreads();
+  const int nsel = sh_nsel < SEL_CAP ? sh_nsel : SEL_CAP;
+  int np2 = 1;
+  while (np2 < nsel) np2 <<= 1;
+  for (int i = nsel + tid; i < np2; i += MD_THREADS) keys[i] = 0ull;
+  __syncthreads();
+  bitonic_desc(keys, np2);
+  const bool complete = nsel == npass;
+  if (min_distance >= 1.0) {
+    const int cell = (int)rint(min_distance);
+    const int gw = (w + cell - 1) / cell, gh = (h + cell - 1) / cell;
+    greedy_fixed_point<unsigned short>(keys, nsel, cell, gw, gh, min_distance * min_distance, cstart, ccount, items,
+                                       state, warp_sums, &sh_total);
+    emit_accepted(keys, state, nsel, false, max_corners, corners, corner_stride, &ncorners[s], warp_sums, &sh_total);
+  } else {
+    emit_accepted(keys, state, nsel, true, max_corners, corners, corner_stride, &ncorners[s], warp_sums, &sh_total);
+  }
+  __syncthreads();
+  if (tid == 0 && !complete && sh_total < max_corners) need_full[s] = 1;   // prefix too short: slow path decides
+}
+
+// slow path: all passing candidates, keys sorted in global memory by a shared-memory-free odd route:
+// (1) compact passing keys into `sorted`, (2) bitonic sort in global memory, (3) greedy with global state.
+__global__ void __launch_bounds__(MD_THREADS, 1)
+mindist_full_kernel(const unsigned long long* __restrict__ cand_base, const int* __restrict__ ncand, int cand_cap,
+                    unsigned long long* __restrict__ sorted_base, int* __restrict__ items_base,
+                    unsigned char* __restrict__ state_base, const int* __restrict__ eigmax, double quality, int w,
+                    int h, double min_distance, int max_corners, float* __restrict__ corners_base,
+                    int* __restrict__ ncorners, int corner_stride, const int* __restrict__ need_full, int max_cells) {
+  extern __shared__ unsigned char smem_raw[];
+  const int s = blockIdx.x, tid = threadIdx.x;
+  if (!need_full[s]) return;
+  int* cstart = (int*)smem_raw;
+  int* ccount = cstart + (max_cells + 1);
+  __shared__ int warp_sums[32];
+  __shared__ int sh_total, sh_n;
+  const unsigned long long* cand = cand_base + (size_t)s * cand_cap;
+  unsigned long long* keys = sorted_base + (size_t)s * cand_cap;
+  int* items = items_base + (size_t)s * cand_cap;
+  unsigned char* state = state_base + (size_t)s * cand_cap;
+  int n = ncand[s];
+  if (n > cand_cap) n = cand_cap;
+  const float thr = (float)((double)__int_as_float(eigmax[s]) * quality);
+  if (tid == 0) sh_n = 0;
+  __syncthreads();
+  for (int i = tid; i < n; i += MD_THREADS) {
+    const unsigned long long k = cand[i];
+    if (__uint_as_float((unsigned)(k >> 32)) > thr) keys[atomicAdd(&sh_n, 1)] = k;
+  }
+  __syncthreads();
+  const int m = sh_n;
+  int np2 = 1;
+  while (np2 < m) np2 <<= 1;                     // np2 <= cand_cap (power of two by construction)
+  for (int i = m + tid; i < np2; i += MD_THREADS) keys[i] = 0ull;
+  __syncthreads();
+  bitonic_desc(keys, np2);
+  float* corners = corners_base + (size_t)s * corner_stride * 2;
+  if (min_distance >= 1.0) {
+    const int cell = (int)rint(min_distance);
+    const int gw = (w + cell - 1) / cell, gh = (h + cell - 1) / cell;
+    greedy_fixed_point<int>(keys, m, cell, gw, gh, min_distance * min_distance, cstart, ccount, items, state,
+                            warp_sums, &sh_total);
+    emit_accepted(keys, state, m, false, max_corners, corners, corner_stride, &ncorners[s], warp_sums, &sh_total);
+  } else {
+    emit_accepted(keys, state, m, true, max_corners, corners, corner_stride, &ncorners[s], warp_sums, &sh_total);
+  }
 }
 
 __global__ void gftt_reset_kernel(int* eigmax, int* ncand, int n) {
@@ -324,11 +422,13 @@ __global__ void gftt_reset_kernel(int* eigmax, int* ncand, int n) {
   if (i < n) { eigmax[i] = 0; ncand[i] = 0; }
 }
 
-}  // namespace
-
-size_t flv_mindist_smem(int cand_cap, int max_cells) {
-  return (size_t)ACC_CAP * 8 + (size_t)(2 * max_cells + 1) * 4 + (size_t)cand_cap;
+size_t fast_smem(int max_cells) {
+  const int cc_len = max_cells > HBINS ? max_cells : HBINS;
+  return (size_t)SEL_CAP * 8 + (size_t)(max_cells + 1 + cc_len) * 4 + (size_t)SEL_CAP * 2 + SEL_CAP;
 }
+size_t full_smem(int max_cells) { return (size_t)(2 * max_cells + 1) * 4; }
+
+}  // namespace
 
 int flv_launch_gftt(flv_ctx* ctx, int slot, int n_streams, int max_corners, double quality,
                     double min_distance) {
@@ -343,16 +443,17 @@ int flv_launch_gftt(flv_ctx* ctx, int slot, int n_streams, int max_corners, doub
   if (max_corners > ctx->gftt_cap || max_corners <= 0)
     FLV_FAIL(ctx, FLV_ERR_INVALID, "max_corners %d outside (0, %d]", max_corners, ctx->gftt_cap);
   gftt_reset_kernel<<<(n_streams + 127) / 128, 128, 0, ctx->stream>>>(ctx->d_eigmax, ctx->d_ncand, n_streams);
-  dim3 g1((w + ETW - 1) / ETW, (h + ETH - 1) / ETH, n_streams);
-  mineig_kernel<<<g1, 256, 0, ctx->stream>>>(ctx->pyr[slot] + ctx->geom.lv[0].off, ctx->geom.stream_stride,
-                                             ctx->geom.lv[0].pitch, w, h, ctx->d_eig, ctx->d_eigmax);
-  dim3 g2((w + 31) / 32, (h + 7) / 8, n_streams);
-  nms_kernel<<<g2, 256, 0, ctx->stream>>>(ctx->d_eig, w, h, ctx->d_eigmax, quality, ctx->d_cand,
-                                          ctx->d_ncand, ctx->cand_cap);
-  size_t smem = flv_mindist_smem(ctx->cand_cap, ctx->max_cells);
-  mindist_kernel<<<n_streams, MD_THREADS, smem, ctx->stream>>>(
-      ctx->d_cand, ctx->d_ncand, ctx->cand_cap, ctx->d_sorted, w, h,
-      min_distance, max_corners, ctx->d_corners, ctx->d_ncorners, ctx->gftt_cap, ctx->d_flags,
+  const int nsx = (w + CS_COLS - 1) / CS_COLS, nsy = (h + CS_ROWS - 1) / CS_ROWS;
+  dim3 g1((nsx * nsy + CS_WARPS - 1) / CS_WARPS, n_streams);
+  corner_response_kernel<<<g1, CS_WARPS * 32, 0, ctx->stream>>>(
+      ctx->pyr[slot] + ctx->geom.lv[0].off, ctx->geom.stream_stride, ctx->geom.lv[0].pitch, w, h, nsx, nsy,
+      ctx->keep_eig ? ctx->d_eig : nullptr, ctx->d_eigmax, quality, ctx->d_cand, ctx->d_ncand, ctx->cand_cap);
+  mindist_fast_kernel<<<n_streams, MD_THREADS, fast_smem(ctx->max_cells), ctx->stream>>>(
+      ctx->d_cand, ctx->d_ncand, ctx->cand_cap, ctx->d_eigmax, quality, w, h, min_distance, max_corners,
+      ctx->d_corners, ctx->d_ncorners, ctx->gftt_cap, ctx->d_flags, ctx->d_need_full, ctx->max_cells);
+  mindist_full_kernel<<<n_streams, MD_THREADS, full_smem(ctx->max_cells), ctx->stream>>>(
+      ctx->d_cand, ctx->d_ncand, ctx->cand_cap, ctx->d_sorted, ctx->d_items, ctx->d_state, ctx->d_eigmax, quality,
+      w, h, min_distance, max_corners, ctx->d_corners, ctx->d_ncorners, ctx->gftt_cap, ctx->d_need_full,
       ctx->max_cells);
   ctx->launches += 4;
   FLV_CUDA(ctx, cudaGetLastError());
@@ -360,7 +461,9 @@ int flv_launch_gftt(flv_ctx* ctx, int slot, int n_streams, int max_corners, doub
 }
 
 int flv_gftt_init(flv_ctx* ctx) {
-  size_t smem = flv_mindist_smem(ctx->cand_cap, ctx->max_cells);
-  FLV_CUDA(ctx, cudaFuncSetAttribute(mindist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  FLV_CUDA(ctx, cudaFuncSetAttribute(mindist_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)fast_smem(ctx->max_cells)));
+  FLV_CUDA(ctx, cudaFuncSetAttribute(mindist_full_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)full_smem(ctx->max_cells)));
   return FLV_OK;
 }

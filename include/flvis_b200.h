@@ -102,7 +102,9 @@ int flv_select_tracked(flv_ctx* ctx, int n_streams, const int* n_pts, const floa
  * n_out[s] corners (<= max_corners <= ctx max_corner capacity). */
 int flv_gftt(flv_ctx* ctx, int slot, int n_streams, int max_corners, double quality,
              double min_distance, float* xy_out, int* n_out, int out_stride_pts, flv_memspace mem);
-/* The f32 min-eigenvalue response map of (slot, stream) computed by the last flv_gftt (tests). */
+/* Debug: the fused kernel normally never writes the response map; enable=1 makes flv_gftt also store it so
+ * flv_download_eig can return the f32 min-eigenvalue map of `stream` from the last flv_gftt (tests). */
+int flv_gftt_keep_response(flv_ctx* ctx, int enable);
 int flv_download_eig(flv_ctx* ctx, int stream, float* out, flv_memspace mem);
 /* Capacity of the corner output (max value of max_corners). */
 int flv_gftt_capacity(flv_ctx* ctx);
@@ -168,6 +170,10 @@ int flv_ba_optimize(flv_ctx* ctx, int n_streams, const flv_ba_problem* problems,
                     const flv_ba_params* prm, double* poses, double* landmarks,
                     const int* edge_pose, const int* edge_lm, const double* edge_uv,
                     uint8_t* edge_active, flv_ba_stats* stats, flv_memspace mem);
+
+/* Debug: SM cycle counters of the last flv_ba_optimize for `stream`:
+ * out8 = {chi2, build, schur, cholesky, substitution, update, setup, unused}. Synchronises. */
+int flv_ba_profile(flv_ctx* ctx, int stream, long long* out8);
 
 #ifdef __cplusplus
 }

@@ -98,6 +98,7 @@ def test_gftt_bit_exact(name):
     h, w = img.shape
     ctx = _ctx(1, w, h)
     ctx.upload(0, img)
+    ctx.keep_response(True)
     N, q, d = int(g["N"]), float(g["q"]), float(g["d"])
     c = ctx.gftt(0, 1, N, q, d)[0]
     eig = ctx.download_eig(0)

@@ -1,0 +1,22 @@
+"""Per-phase SM cycle counters of the BA kernel on an EuRoC-sized window (debug aid; run on the GPU box)."""
+import sys, os, time
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+from flvis_b200 import capi, ba_synth
+
+W = int(sys.argv[1]) if len(sys.argv) > 1 else 10
+S = int(sys.argv[2]) if len(sys.argv) > 2 else 1
+probs = [ba_synth.make_problem(window=W, n_landmarks=1500 if W <= 10 else 2000, obs_per_frame=480, seed=2 + s) for s in range(S)]
+batch = ba_synth.Batch(probs)
+ctx = capi.Context(S, 752, 480)
+for rep in range(2):
+    t = time.perf_counter()
+    poses, lms, active, stats = ba_synth.solve_batch_host(ctx, batch)
+    dt = time.perf_counter() - t
+names = ["chi2", "build", "schur", "cholesky", "subst", "update", "setup", "-"]
+pr = ctx.ba_profile(0)
+tot = pr.sum()
+print(f"W={W} S={S} E={len(probs[0].ep)} L={len(probs[0].lms)} iters={stats[0].iterations_run} culled={stats[0].n_culled} "
+      f"host wall {dt*1e3:.2f} ms, kernel cycles {tot} (~{tot/1.9e6:.2f} ms @1.9GHz)")
+for n, v in zip(names, pr):
+    print(f"  {n:9s} {v:12d} cycles {100.0*v/max(tot,1):5.1f}%")
