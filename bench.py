@@ -135,6 +135,7 @@ def run_ours(args):
         bench.reset()
         for i in range(warmup):
             bench.step(i, mode)
+        bench.join()
         barrier()
         launches0 = bench.ctx.launches
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -143,6 +144,7 @@ def run_ours(args):
         ev0.record(bench.stream)
         for i in range(steps):
             bench.step(warmup + i, mode)
+        bench.join()                       # the timed region ends when the asynchronous BA streams have drained too
         ev1.record(bench.stream)
         barrier()
         ms = ev0.elapsed_time(ev1)

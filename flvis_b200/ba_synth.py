@@ -148,12 +148,14 @@ class DeviceBatch:
         self.d0 = {k: v.to(dev) for k, v in self.h0.items()}            # pristine inputs (HBM-resident)
         self.prm = capi.BAParams(12, 8, 1.0, 3.0, 0)
         self.groups = None
+        self.streams = None          # one CUDA stream per keyframe phase: the local-map thread analogue
 
     def _groups(self, kf_every):
         if self.groups is None:
             torch = self.torch
             self.groups = []
             nstat = C.sizeof(capi.BAStats)
+            slot0 = 0
             for r in range(kf_every):
                 sel = [s for s in range(self.S) if (r + s) % kf_every == 0]
                 if not sel:
@@ -162,7 +164,7 @@ class DeviceBatch:
                 idx = torch.tensor(sel, device=self.dev)
                 cp = (capi.BAProblem * len(sel))(*[self.b.cprob[s] for s in sel])
                 h_prob = torch.frombuffer(bytearray(bytes(cp)), dtype=torch.uint8).pin_memory()
-                g = {"sel": sel, "d_prob": h_prob.to(self.dev),
+                g = {"sel": sel, "d_prob": h_prob.to(self.dev), "prm": capi.BAParams(12, 8, 1.0, 3.0, 0, slot0),
                      "w": {k: self.d0[k][idx].contiguous() for k in self.d0},
                      "src": {k: self.d0[k][idx].contiguous() for k in self.d0},
                      "hsrc": {k: self.h0[k][torch.tensor(sel)].contiguous().pin_memory() for k in self.h0},
@@ -170,6 +172,7 @@ class DeviceBatch:
                      "h_stats": torch.zeros(len(sel) * nstat, dtype=torch.uint8).pin_memory(),
                      "h_poses": torch.zeros(len(sel), self.b.MP, 7, dtype=torch.float64).pin_memory(),
                      "h_lms": torch.zeros(len(sel), self.b.ML, 3, dtype=torch.float64).pin_memory()}
+                slot0 += len(sel)      # concurrent launches of different phases use disjoint workspace slots
                 self.groups.append(g)
         return self.groups
 
@@ -186,13 +189,31 @@ class DeviceBatch:
         g = self._groups(kf_every)[i % kf_every]
         if g is None:
             return
+        torch = self.torch
+        if self.streams is None:
+            self.streams = [torch.cuda.Stream(self.dev) for _ in range(kf_every)]
+        st = self.streams[i % kf_every]
+        # like FLVIS's local-map nodelet, the BA of a keyframe runs concurrently with the tracking of the following
+        # frames: its own stream, nothing in the frame loop waits for it (the reference's feedback path is dead code)
+        with torch.cuda.stream(st):
+            self.ctx.set_ba_stream(st.cuda_stream, True)
+            self._solve(g, mode)
+            self.ctx.set_ba_stream(0, False)
+
+    def join(self, main_stream):
+        """Make `main_stream` wait for all outstanding BA work (end of a timed region)."""
+        if self.streams:
+            for st in self.streams:
+                main_stream.wait_stream(st)
+
+    def _solve(self, g, mode):
         w = g["w"]
         src = g["hsrc"] if mode == "host" else g["src"]
         for k in w:                                               # (re)load the windows: H2D in e2e mode, D2D otherwise
             w[k].copy_(src[k], non_blocking=True)
         n = len(g["sel"])
         self.ctx._chk(self.ctx.lib.flv_ba_optimize(
-            self.ctx.h, n, C.cast(C.c_void_p(g["d_prob"].data_ptr()), C.POINTER(capi.BAProblem)), C.byref(self.prm),
+            self.ctx.h, n, C.cast(C.c_void_p(g["d_prob"].data_ptr()), C.POINTER(capi.BAProblem)), C.byref(g["prm"]),
             C.c_void_p(w["poses"].data_ptr()), C.c_void_p(w["lms"].data_ptr()), C.c_void_p(w["ep"].data_ptr()),
             C.c_void_p(w["el"].data_ptr()), C.c_void_p(w["uv"].data_ptr()), C.c_void_p(w["active"].data_ptr()),
             C.cast(C.c_void_p(g["d_stats"].data_ptr()), C.POINTER(capi.BAStats)), capi.MEM_DEVICE))

@@ -18,7 +18,7 @@ SYMBOLS = [
     "flv_launch_count", "flv_level_info", "flv_num_levels", "flv_upload_images", "flv_build_pyramid",
     "flv_download_level", "flv_lk_track", "flv_select_tracked", "flv_gftt", "flv_download_eig", "flv_gftt_capacity",
     "flv_feature_detect", "flv_feature_redetect", "flv_ba_reserve", "flv_ba_optimize", "flv_gftt_keep_response",
-    "flv_ba_profile",
+    "flv_ba_profile", "flv_set_ba_stream",
 ]
 
 
@@ -41,7 +41,7 @@ class BAProblem(C.Structure):
 
 class BAParams(C.Structure):
     _fields_ = [("iters1", C.c_int), ("iters2", C.c_int), ("huber_delta", C.c_double),
-                ("cull_chi2", C.c_double), ("min_edges_after_cull", C.c_int)]
+                ("cull_chi2", C.c_double), ("min_edges_after_cull", C.c_int), ("ws_slot0", C.c_int)]
 
 
 class BAStats(C.Structure):
@@ -71,6 +71,7 @@ def load_library(path=LIB_PATH):
     lib.flv_gftt_capacity.argtypes = [vp]
     lib.flv_gftt_keep_response.argtypes = [vp, C.c_int]
     lib.flv_ba_profile.argtypes = [vp, C.c_int, vp]
+    lib.flv_set_ba_stream.argtypes = [vp, vp, C.c_int]
     lib.flv_level_info.argtypes = [vp, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int),
                                    C.POINTER(C.c_size_t)]
     lib.flv_upload_images.argtypes = [vp, C.c_int, C.c_int, vp, C.c_size_t, C.c_size_t, C.c_int]
@@ -237,6 +238,9 @@ class Context:
 
     def keep_response(self, enable=True):
         self._chk(self.lib.flv_gftt_keep_response(self.h, 1 if enable else 0))
+
+    def set_ba_stream(self, cuda_stream_ptr, enable=True):
+        self._chk(self.lib.flv_set_ba_stream(self.h, C.c_void_p(cuda_stream_ptr), 1 if enable else 0))
 
     def ba_profile(self, stream):
         out = np.zeros(8, np.int64)

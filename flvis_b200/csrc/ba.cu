@@ -119,29 +119,31 @@ __device__ void pose_oplus(double* pose, const double* u) {   // pose <- exp(u) 
 
 struct Cam { double fx, fy, cx, cy; };
 
-// residual r (2), optional A = d r / d point (2x3), B = d r / d pose (2x6)
+// residual r (2), optional A = d r / d point (2x3), B = d r / d pose (2x6).  One fp64 division per edge:
+// the reference's x/z, y/z, 1/z, x*y/z^2 ... are evaluated with iz = 1/z (differences ~1 ulp, tolerance-checked).
 template <bool JAC>
 __device__ __forceinline__ void edge_eval(const double* pose, const double* X, const double* uv, const Cam& c,
                                           double* r, double* A, double* B) {
   double Xc[3];
   q_rotate(pose, X, Xc);
   const double x = Xc[0] + pose[4], y = Xc[1] + pose[5], z = Xc[2] + pose[6];
-  r[0] = uv[0] - (x / z * c.fx + c.cx);
-  r[1] = uv[1] - (y / z * c.fy + c.cy);
+  const double iz = 1.0 / z;
+  const double xz = x * iz, yz = y * iz;
+  r[0] = uv[0] - (xz * c.fx + c.cx);
+  r[1] = uv[1] - (yz * c.fy + c.cy);
   if (JAC) {
-    const double z2 = z * z;
     double R[9];
     q_to_R(pose, R);
-    const double t02 = -x / z * c.fx, t12 = -y / z * c.fy, iz = -1. / z;
+    const double t02 = -xz * c.fx, t12 = -yz * c.fy, miz = -iz;
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
-      A[k] = iz * (c.fx * R[k] + t02 * R[6 + k]);
-      A[3 + k] = iz * (c.fy * R[3 + k] + t12 * R[6 + k]);
+      A[k] = miz * (c.fx * R[k] + t02 * R[6 + k]);
+      A[3 + k] = miz * (c.fy * R[3 + k] + t12 * R[6 + k]);
     }
-    B[0] = x * y / z2 * c.fx; B[1] = -(1 + (x * x / z2)) * c.fx; B[2] = y / z * c.fx;
-    B[3] = -1. / z * c.fx; B[4] = 0; B[5] = x / z2 * c.fx;
-    B[6] = (1 + y * y / z2) * c.fy; B[7] = -x * y / z2 * c.fy; B[8] = -x / z * c.fy;
-    B[9] = 0; B[10] = -1. / z * c.fy; B[11] = y / z2 * c.fy;
+    B[0] = xz * yz * c.fx; B[1] = -(1 + xz * xz) * c.fx; B[2] = yz * c.fx;
+    B[3] = miz * c.fx; B[4] = 0; B[5] = xz * iz * c.fx;
+    B[6] = (1 + yz * yz) * c.fy; B[7] = -xz * yz * c.fy; B[8] = -xz * c.fy;
+    B[9] = 0; B[10] = miz * c.fy; B[11] = yz * iz * c.fy;
   }
 }
 
@@ -173,16 +175,21 @@ __device__ double block_max(double v, double* red) {
   return t;
 }
 
+constexpr int BA_MAX_PAIRS = BA_MAX_FREE * (BA_MAX_FREE + 1) / 2;   // 300
+
 struct Sh {   // fixed-size shared state
   double red[BA_WARPS];
   double Hd[BA_MAX_FREE][21];
+  double part[2 * BA_MAX_FREE][27];     // pose-pass partial sums (two halves per pose)
   double bp[6 * BA_MAX_FREE];
   double x[6 * BA_MAX_FREE];
+  double piv;
   int pidx[BA_MAX_POSES];
   int pose_of[BA_MAX_FREE];
   int pcount[BA_MAX_POSES];
-  int queue[BA_WARPS][64];
-  int np, fail, nact;
+  int pstart[BA_MAX_POSES + 1];
+  int pair_off[BA_MAX_PAIRS + 1];
+  int np, fail, nact, overflow;
   long long prof[8], tlast;   // cycle counters: 0 chi2, 1 build, 2 schur, 3 cholesky, 4 substitution, 5 update, 6 setup
 };
 
@@ -191,12 +198,18 @@ __device__ __forceinline__ void mark(Sh& sh, int slot) {
 }
 
 struct Ws {   // per-stream global workspace views
-  double *pbk, *lbk, *W, *Hll, *bl, *Dinv, *xl;
-  int *eidx; unsigned* lmask;
+  double *pbk, *lbk, *W, *Bw, *g, *Hll, *bl, *Dinv, *xl;
+  int *eidx; unsigned* lmask; int* plist; int* pairs; int pair_cap;
 };
 
 __device__ __forceinline__ int sym21(int i, int j) {   // index into upper-triangular 6x6 (i<=j)
   return i * 6 - (i * (i - 1)) / 2 + (j - i);
+}
+__device__ __forceinline__ void pair_of(int blk, int np, int& a, int& b) {
+  a = 0;
+  int rem = blk;
+  while (rem >= np - a) { rem -= np - a; ++a; }
+  b = a + rem;
 }
 
 __device__ double robust_chi2(const flv_ba_problem& pb, const Cam& cam, const double* poses, const double* lms,
@@ -214,12 +227,14 @@ __device__ double robust_chi2(const flv_ba_problem& pb, const Cam& cam, const do
   return block_sum(acc, red);
 }
 
-// active sets + lookup tables (sparse_optimizer.cpp:168-272 semantics)
+// active sets + lookup tables (sparse_optimizer.cpp:168-272 semantics); built once per optimize() call:
+//   eidx[p][l], lmask[l]; per-pose edge lists (landmark order); per pose-pair member lists (landmark order).
 __device__ void setup_active(const flv_ba_problem& pb, const int* ep, const int* el, const uint8_t* act, Ws& ws, Sh& sh) {
-  const int P = pb.n_poses, L = pb.n_landmarks, E = pb.n_edges, tid = threadIdx.x;
+  const int P = pb.n_poses, L = pb.n_landmarks, E = pb.n_edges, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   for (int i = tid; i < P * L; i += BA_THREADS) ws.eidx[i] = -1;
   for (int i = tid; i < L; i += BA_THREADS) ws.lmask[i] = 0u;
   if (tid < BA_MAX_POSES) sh.pcount[tid] = 0;
+  if (tid == 0) sh.overflow = 0;
   __syncthreads();
   for (int e = tid; e < E; e += BA_THREADS) {
     if (!act[e]) continue;
@@ -232,25 +247,77 @@ __device__ void setup_active(const flv_ba_problem& pb, const int* ep, const int*
   if (tid == 0) {
     int np = 0, nact = 0;
     for (int p = 0; p < P; ++p) {
+      sh.pstart[p] = nact;
       nact += sh.pcount[p];
       if (p != pb.fixed_pose && sh.pcount[p] > 0) { sh.pidx[p] = np; sh.pose_of[np] = p; ++np; }
       else sh.pidx[p] = -1;
     }
+    sh.pstart[P] = nact;
     sh.np = np; sh.nact = nact;
+  }
+  __syncthreads();
+  // per-pose edge lists in landmark order (deterministic): warp per pose, ballot compaction
+  for (int p = warp; p < P; p += BA_WARPS) {
+    int base = sh.pstart[p];
+    for (int l0 = 0; l0 < L; l0 += 32) {
+      const int l = l0 + lane;
+      const int e = l < L ? ws.eidx[p * L + l] : -1;
+      const unsigned bal = __ballot_sync(FULL, e >= 0);
+      if (e >= 0) ws.plist[base + __popc(bal & ((1u << lane) - 1))] = e;
+      base += __popc(bal);
+    }
+  }
+  if (pb.fix_landmarks || sh.np > BA_MAX_FREE) { __syncthreads(); return; }
+  // pose-pair member lists: count, prefix, fill (two scans over lmask)
+  const int np = sh.np, nblk = np * (np + 1) / 2;
+  for (int blk = warp; blk < nblk; blk += BA_WARPS) {
+    int a, b; pair_of(blk, np, a, b);
+    const unsigned need = (1u << sh.pose_of[a]) | (1u << sh.pose_of[b]);
+    int cnt = 0;
+    for (int l0 = 0; l0 < L; l0 += 32) {
+      const int l = l0 + lane;
+      cnt += __popc(__ballot_sync(FULL, l < L && (ws.lmask[l] & need) == need));
+    }
+    if (lane == 0) sh.pair_off[blk + 1] = cnt;
+  }
+  __syncthreads();
+  if (tid == 0) {
+    sh.pair_off[0] = 0;
+    for (int i = 0; i < nblk; ++i) sh.pair_off[i + 1] += sh.pair_off[i];
+    if (sh.pair_off[nblk] > ws.pair_cap) sh.overflow = 1;
+  }
+  __syncthreads();
+  if (sh.overflow) return;
+  for (int blk = warp; blk < nblk; blk += BA_WARPS) {
+    int a, b; pair_of(blk, np, a, b);
+    const int pa = sh.pose_of[a], pb_ = sh.pose_of[b];
+    const unsigned need = (1u << pa) | (1u << pb_);
+    int base = sh.pair_off[blk];
+    for (int l0 = 0; l0 < L; l0 += 32) {
+      const int l = l0 + lane;
+      const bool mem = l < L && (ws.lmask[l] & need) == need;
+      const unsigned bal = __ballot_sync(FULL, mem);
+      if (mem) {
+        int* it = ws.pairs + 3 * (size_t)(base + __popc(bal & ((1u << lane) - 1)));
+        it[0] = ws.eidx[pa * L + l]; it[1] = ws.eidx[pb_ * L + l]; it[2] = l;
+      }
+      base += __popc(bal);
+    }
   }
   __syncthreads();
 }
 
 __device__ void build_system(const flv_ba_problem& pb, const Cam& cam, const double* poses, const double* lms,
-                             const double* uv, double delta, Ws& ws, Sh& sh) {
-  const int P = pb.n_poses, L = pb.n_landmarks, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+                             const int* el, const double* uv, double delta, Ws& ws, Sh& sh) {
+  const int L = pb.n_landmarks, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const double d2 = delta * delta;
   if (!pb.fix_landmarks) {
+    // thread per landmark: Hll, bl, and per edge W = rho' B^T A, Bw = sqrt(rho') B, g = -sqrt(rho') r
     for (int l = tid; l < L; l += BA_THREADS) {
       unsigned m = ws.lmask[l];
       if (!m) continue;
       double H[6] = {0, 0, 0, 0, 0, 0}, b[3] = {0, 0, 0};
-      const double* X = lms + 3 * l;
+      const double X[3] = {lms[3 * l], lms[3 * l + 1], lms[3 * l + 2]};
       while (m) {
         const int p = __ffs(m) - 1; m &= m - 1;
         const int e = ws.eidx[p * L + l];
@@ -270,6 +337,11 @@ __device__ void build_system(const flv_ba_problem& pb, const Cam& cam, const dou
           for (int i = 0; i < 6; ++i)
 #pragma unroll
             for (int j = 0; j < 3; ++j) W[3 * i + j] = rho1 * (B[i] * A[j] + B[6 + i] * A[3 + j]);
+          const double sr = sqrt(rho1);
+          double* Bw = ws.Bw + 12 * (size_t)e;
+#pragma unroll
+          for (int i = 0; i < 12; ++i) Bw[i] = sr * B[i];
+          ws.g[2 * (size_t)e] = -sr * r[0]; ws.g[2 * (size_t)e + 1] = -sr * r[1];
         }
       }
 #pragma unroll
@@ -277,41 +349,60 @@ __device__ void build_system(const flv_ba_problem& pb, const Cam& cam, const dou
 #pragma unroll
       for (int i = 0; i < 3; ++i) ws.bl[3 * (size_t)l + i] = b[i];
     }
+    __syncthreads();
   }
-  // pose diagonal blocks: warp per free pose, lanes stride over the landmarks it observes
-  for (int pi = warp; pi < sh.np; pi += BA_WARPS) {
-    const int p = sh.pose_of[pi];
+  // pose diagonal blocks: task = (free pose, half of its edge list); lanes stride over the list
+  for (int task = warp; task < 2 * sh.np; task += BA_WARPS) {
+    const int pi = task >> 1, p = sh.pose_of[pi];
+    const int b0 = sh.pstart[p], cnt = sh.pstart[p + 1] - b0;
+    const int mid = (cnt + 1) >> 1;
+    const int lo = (task & 1) ? mid : 0, hi = (task & 1) ? cnt : mid;
     double H[21], b[6];
 #pragma unroll
     for (int i = 0; i < 21; ++i) H[i] = 0;
 #pragma unroll
     for (int i = 0; i < 6; ++i) b[i] = 0;
-    for (int l = lane; l < L; l += 32) {
-      const int e = ws.eidx[p * L + l];
-      if (e < 0) continue;
-      double r[2], A[6], B[12];
-      edge_eval<true>(poses + 7 * p, lms + 3 * l, uv + 2 * e, cam, r, A, B);
-      const double c = r[0] * r[0] + r[1] * r[1];
-      const double rho1 = (c <= d2) ? 1.0 : delta / sqrt(c);
-      const double o0 = -r[0] * rho1, o1 = -r[1] * rho1;
-      int k = 0;
+    for (int k = lo + lane; k < hi; k += 32) {
+      const int e = ws.plist[b0 + k];
+      double B[12], g0, g1;
+      if (pb.fix_landmarks) {
+        double r[2], A[6];
+        edge_eval<true>(poses + 7 * p, lms + 3 * el[e], uv + 2 * e, cam, r, A, B);
+        const double c = r[0] * r[0] + r[1] * r[1];
+        const double sr = (c <= d2) ? 1.0 : sqrt(delta / sqrt(c));
+#pragma unroll
+        for (int i = 0; i < 12; ++i) B[i] *= sr;
+        g0 = -sr * r[0]; g1 = -sr * r[1];
+      } else {
+        const double* Bw = ws.Bw + 12 * (size_t)e;
+#pragma unroll
+        for (int i = 0; i < 12; ++i) B[i] = Bw[i];
+        g0 = ws.g[2 * (size_t)e]; g1 = ws.g[2 * (size_t)e + 1];
+      }
+      int k2 = 0;
 #pragma unroll
       for (int i = 0; i < 6; ++i) {
-        b[i] += B[i] * o0 + B[6 + i] * o1;
+        b[i] += B[i] * g0 + B[6 + i] * g1;
 #pragma unroll
-        for (int j = i; j < 6; ++j) H[k++] += rho1 * (B[i] * B[j] + B[6 + i] * B[6 + j]);
+        for (int j = i; j < 6; ++j) H[k2++] += B[i] * B[j] + B[6 + i] * B[6 + j];
       }
     }
 #pragma unroll
-    for (int i = 0; i < 21; ++i) { const double v = warp_sum(H[i]); if (lane == 0) sh.Hd[pi][i] = v; }
+    for (int i = 0; i < 21; ++i) { const double v = warp_sum(H[i]); if (lane == 0) sh.part[task][i] = v; }
 #pragma unroll
-    for (int i = 0; i < 6; ++i) { const double v = warp_sum(b[i]); if (lane == 0) sh.bp[6 * pi + i] = v; }
+    for (int i = 0; i < 6; ++i) { const double v = warp_sum(b[i]); if (lane == 0) sh.part[task][21 + i] = v; }
+  }
+  __syncthreads();
+  for (int i = tid; i < sh.np * 27; i += BA_THREADS) {
+    const int pi = i / 27, k = i - 27 * pi;
+    const double v = sh.part[2 * pi][k] + sh.part[2 * pi + 1][k];
+    if (k < 21) sh.Hd[pi][k] = v; else sh.bp[6 * pi + k - 21] = v;
   }
   __syncthreads();
 }
 
-// Schur complement into S (n x n, shared), bs (n); returns via sh.fail the Cholesky status; x in sh.x
-__device__ void solve_system(const flv_ba_problem& pb, double lambda, double* S, double* bs, Ws& ws, Sh& sh) {
+// (H + lambda I) x = b through the Schur complement: S (n x ld, shared, lower triangle used), y, x in shared
+__device__ void solve_system(const flv_ba_problem& pb, double lambda, double* S, double* y, int ld, Ws& ws, Sh& sh) {
   const int L = pb.n_landmarks, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int np = sh.np, n = 6 * np;
   if (!pb.fix_landmarks) {
@@ -333,61 +424,35 @@ __device__ void solve_system(const flv_ba_problem& pb, double lambda, double* S,
   }
   const int nblk = np * (np + 1) / 2;
   for (int blk = warp; blk < nblk; blk += BA_WARPS) {
-    // blk -> (a,b), a <= b
-    int a = 0, rem = blk;
-    while (rem >= np - a) { rem -= np - a; ++a; }
-    const int b = a + rem;
-    const int pa = sh.pose_of[a], pb_ = sh.pose_of[b];
+    int a, b; pair_of(blk, np, a, b);
     double acc[36], cf[6];
 #pragma unroll
     for (int i = 0; i < 36; ++i) acc[i] = 0;
 #pragma unroll
     for (int i = 0; i < 6; ++i) cf[i] = 0;
     if (!pb.fix_landmarks) {
-      const unsigned need = (1u << pa) | (1u << pb_);
-      int* q = sh.queue[warp];
-      int qn = 0;
-      auto process = [&](int take) {
-        if (lane < take) {
-          const int l = q[lane];
-          const double* Wa = ws.W + 18 * (size_t)ws.eidx[pa * L + l];
-          const double* Wb = ws.W + 18 * (size_t)ws.eidx[pb_ * L + l];
-          const double* Di = ws.Dinv + 6 * (size_t)l;
-          const double d0 = Di[0], d1 = Di[1], d2 = Di[2], d3 = Di[3], d4 = Di[4], d5 = Di[5];
-          double wb[18];
+      const int i0 = sh.pair_off[blk], i1 = sh.pair_off[blk + 1];
+      for (int k = i0 + lane; k < i1; k += 32) {
+        const int* it = ws.pairs + 3 * (size_t)k;
+        const double* Wa = ws.W + 18 * (size_t)it[0];
+        const double* Wb = ws.W + 18 * (size_t)it[1];
+        const int l = it[2];
+        const double* Di = ws.Dinv + 6 * (size_t)l;
+        const double d0 = Di[0], d1 = Di[1], d2 = Di[2], d3 = Di[3], d4 = Di[4], d5 = Di[5];
+        double wb[18];
 #pragma unroll
-          for (int i = 0; i < 18; ++i) wb[i] = Wb[i];
-          const double* db = ws.xl + 3 * (size_t)l;
+        for (int i = 0; i < 18; ++i) wb[i] = Wb[i];
+        const double* db = ws.xl + 3 * (size_t)l;
+        const double db0 = db[0], db1 = db[1], db2 = db[2];
 #pragma unroll
-          for (int i = 0; i < 6; ++i) {
-            const double w0 = Wa[3 * i], w1 = Wa[3 * i + 1], w2 = Wa[3 * i + 2];
-            const double y0 = w0 * d0 + w1 * d1 + w2 * d2, y1 = w0 * d1 + w1 * d3 + w2 * d4, y2 = w0 * d2 + w1 * d4 + w2 * d5;
+        for (int i = 0; i < 6; ++i) {
+          const double w0 = Wa[3 * i], w1 = Wa[3 * i + 1], w2 = Wa[3 * i + 2];
+          const double y0 = w0 * d0 + w1 * d1 + w2 * d2, y1 = w0 * d1 + w1 * d3 + w2 * d4, y2 = w0 * d2 + w1 * d4 + w2 * d5;
 #pragma unroll
-            for (int j = 0; j < 6; ++j) acc[6 * i + j] += y0 * wb[3 * j] + y1 * wb[3 * j + 1] + y2 * wb[3 * j + 2];
-            if (a == b) cf[i] += w0 * db[0] + w1 * db[1] + w2 * db[2];
-          }
-        }
-      };
-      for (int l0 = 0; l0 < L; l0 += 32) {
-        const int l = l0 + lane;
-        const bool mem = l < L && (ws.lmask[l] & need) == need;
-        const unsigned bal = __ballot_sync(FULL, mem);
-        if (mem) q[qn + __popc(bal & ((1u << lane) - 1))] = l;
-        qn += __popc(bal);
-        __syncwarp();
-        if (qn >= 32) {
-          process(32);
-          const int left = qn - 32;
-          int keepv = 0;
-          if (lane < left) keepv = q[32 + lane];
-          __syncwarp();
-          if (lane < left) q[lane] = keepv;
-          qn = left;
-          __syncwarp();
+          for (int j = 0; j < 6; ++j) acc[6 * i + j] += y0 * wb[3 * j] + y1 * wb[3 * j + 1] + y2 * wb[3 * j + 2];
+          if (a == b) cf[i] += w0 * db0 + w1 * db1 + w2 * db2;
         }
       }
-      if (qn > 0) process(qn);
-      __syncwarp();
     }
 #pragma unroll
     for (int i = 0; i < 36; ++i) acc[i] = warp_sum(acc[i]);
@@ -395,64 +460,67 @@ __device__ void solve_system(const flv_ba_problem& pb, double lambda, double* S,
 #pragma unroll
       for (int i = 0; i < 6; ++i) cf[i] = warp_sum(cf[i]);
     }
-    if (lane == 0) {
+    // S block (b,a) of the lower triangle = -(acc)^T (+ Hpp + lambda on the diagonal block); lanes 0..35 write
+    if (lane < 32) {
 #pragma unroll
       for (int i = 0; i < 6; ++i)
 #pragma unroll
         for (int j = 0; j < 6; ++j) {
-          double v = -acc[6 * i + j];
-          if (a == b) {
-            v += sh.Hd[a][i <= j ? sym21(i, j) : sym21(j, i)];
-            if (i == j) v += lambda;
+          if (((6 * i + j) & 31) == lane) {
+            double v = -acc[6 * i + j];
+            if (a == b) {
+              v += sh.Hd[a][i <= j ? sym21(i, j) : sym21(j, i)];
+              if (i == j) v += lambda;
+            }
+            S[(6 * b + j) * ld + 6 * a + i] = v;          // row index from pose b >= a: lower triangle
+            if (a == b) S[(6 * a + i) * ld + 6 * b + j] = v;
           }
-          S[(6 * a + i) * n + 6 * b + j] = v;
-          if (a != b) S[(6 * b + j) * n + 6 * a + i] = v;
         }
-      if (a == b)
-#pragma unroll
-        for (int i = 0; i < 6; ++i) bs[6 * a + i] = sh.bp[6 * a + i] - cf[i];
+      if (a == b && lane < 6) y[6 * a + lane] = sh.bp[6 * a + lane] - cf[lane];
     }
   }
   if (tid == 0) sh.fail = 0;
   __syncthreads();
   mark(sh, 2);
-  // dense Cholesky S = L L^T (lower part, in place), right-looking, whole CTA
+  // left-looking Cholesky on the augmented matrix [S ; y^T]: row n is the right-hand side, so the forward
+  // substitution comes for free.  T threads per row split each dot product.
+  int T = 1;
+  while ((n + 1) * (T << 1) <= BA_THREADS && T < 32) T <<= 1;
+  const int row = tid / T, t = tid - row * T;
   for (int j = 0; j < n; ++j) {
-    if (tid == 0) {
-      const double d = S[j * n + j];
-      if (!(d > 0)) sh.fail = 1;
-      S[j * n + j] = sqrt(d > 0 ? d : 1.0);
+    double sres = 0;
+    const bool mine = row >= j && row <= n;
+    const double* Li = row < n ? S + row * ld : y;         // row n: y holds b (entries < j already y_k)
+    double acc = 0;
+    if (mine) {
+      const double* Lj = S + j * ld;
+      for (int k = t; k < j; k += T) acc += Li[k] * Lj[k];
+    }
+    for (int o = T >> 1; o > 0; o >>= 1) acc += __shfl_xor_sync(FULL, acc, o);   // whole warp, uniform
+    if (mine) {
+      sres = Li[j] - acc;
+      if (row == j && t == 0) sh.piv = sres;
     }
     __syncthreads();
-    const double dj = S[j * n + j];
-    for (int i = j + 1 + tid; i < n; i += BA_THREADS) S[i * n + j] /= dj;
-    __syncthreads();
-    const int m = n - j - 1;
-    for (int t = tid; t < m * m; t += BA_THREADS) {
-      const int r = j + 1 + t / m, c = j + 1 + t % m;
-      if (c <= r) S[r * n + c] -= S[r * n + j] * S[c * n + j];
+    const double d = sh.piv;
+    if (!(d > 0)) { if (tid == 0) sh.fail = 1; }
+    const double sd = sqrt(d > 0 ? d : 1.0);
+    if (mine && t == 0) {
+      if (row == j) S[j * ld + j] = sd;
+      else if (row < n) S[row * ld + j] = sres / sd;
+      else y[j] = sres / sd;
     }
     __syncthreads();
   }
   mark(sh, 3);
-  // forward / backward substitution by one warp (n <= 144)
-  if (warp == 0) {
-    for (int i = 0; i < n; ++i) {
-      double s = 0;
-      for (int k = lane; k < i; k += 32) s += S[i * n + k] * sh.x[k];
-      s = warp_sum(s);
-      if (lane == 0) sh.x[i] = (bs[i] - s) / S[i * n + i];
-      __syncwarp();
-    }
-    for (int i = n - 1; i >= 0; --i) {
-      double s = 0;
-      for (int k = i + 1 + lane; k < n; k += 32) s += S[k * n + i] * sh.x[k];
-      s = warp_sum(s);
-      if (lane == 0) sh.x[i] = (sh.x[i] - s) / S[i * n + i];
-      __syncwarp();
-    }
+  // back substitution x = L^-T y, column oriented
+  for (int j = n - 1; j >= 0; --j) {
+    const double xj = y[j] / S[j * ld + j];
+    __syncthreads();
+    if (tid < j) y[tid] -= S[j * ld + tid] * xj;
+    if (tid == j) sh.x[j] = xj;
+    __syncthreads();
   }
-  __syncthreads();
   mark(sh, 4);
 }
 
@@ -499,6 +567,10 @@ __device__ void restore_state(const flv_ba_problem& pb, double* poses, double* l
   __syncthreads();
 }
 
+__host__ __device__ inline size_t pair_capacity(int max_poses, int max_edges) {
+  return (size_t)max_edges * ((max_poses + 2) / 2);
+}
+
 __global__ void __launch_bounds__(BA_THREADS, 1) ba_kernel(BAArgs a) {
   extern __shared__ double dyn[];
   __shared__ Sh sh;
@@ -519,12 +591,17 @@ __global__ void __launch_bounds__(BA_THREADS, 1) ba_kernel(BAArgs a) {
     ws.pbk = d; d += 7 * a.max_poses;
     ws.lbk = d; d += 3 * a.max_lms;
     ws.W = d; d += 18 * (size_t)a.max_edges;
+    ws.Bw = d; d += 12 * (size_t)a.max_edges;
+    ws.g = d; d += 2 * (size_t)a.max_edges;
     ws.Hll = d; d += 6 * a.max_lms;
     ws.bl = d; d += 3 * a.max_lms;
     ws.Dinv = d; d += 6 * a.max_lms;
     ws.xl = d; d += 3 * a.max_lms;
     ws.eidx = (int*)d;
     ws.lmask = (unsigned*)(ws.eidx + (size_t)a.max_poses * a.max_lms);
+    ws.plist = (int*)(ws.lmask + a.max_lms);
+    ws.pairs = ws.plist + a.max_edges;
+    ws.pair_cap = (int)pair_capacity(a.max_poses, a.max_edges);
   }
   const double delta = a.prm.huber_delta;
   flv_ba_stats st;
@@ -542,14 +619,15 @@ __global__ void __launch_bounds__(BA_THREADS, 1) ba_kernel(BAArgs a) {
     setup_active(pb, ep, el, act, ws, sh);
     mark(sh, 6);
     if (sh.np > BA_MAX_FREE) { st.ok = 0; st.reserved = 2; break; }
-    const int n = 6 * sh.np;
+    if (sh.overflow) { st.ok = 0; st.reserved = 3; break; }
+    const int n = 6 * sh.np, ld = n + 1;
     double* S = dyn;
-    double* bs = dyn + (size_t)n * n;
+    double* y = dyn + (size_t)n * ld;
     double ni = 2;
     for (int it = 0; it < iters; ++it) {
       double currentChi = robust_chi2(pb, cam, poses, lms, ep, el, uv, act, delta, sh.red);
       mark(sh, 0);
-      build_system(pb, cam, poses, lms, uv, delta, ws, sh);
+      build_system(pb, cam, poses, lms, el, uv, delta, ws, sh);
       mark(sh, 1);
       if (it == 0) {
         double md = 0;
@@ -566,7 +644,7 @@ __global__ void __launch_bounds__(BA_THREADS, 1) ba_kernel(BAArgs a) {
       double rho = 0;
       int qmax = 0;
       do {
-        solve_system(pb, lambda, S, bs, ws, sh);
+        solve_system(pb, lambda, S, y, ld, ws, sh);
         const int ok2 = !sh.fail;
         double scale = 0, tempChi;
         if (ok2) {
@@ -620,10 +698,16 @@ __global__ void __launch_bounds__(BA_THREADS, 1) ba_kernel(BAArgs a) {
 }
 
 size_t ws_stride_bytes(int max_poses, int max_lms, int max_edges) {
-  size_t d = 7 * (size_t)max_poses + 3 * (size_t)max_lms + 18 * (size_t)max_edges + 6 * (size_t)max_lms +
+  size_t d = 7 * (size_t)max_poses + 3 * (size_t)max_lms + (18 + 12 + 2) * (size_t)max_edges + 6 * (size_t)max_lms +
              3 * (size_t)max_lms + 6 * (size_t)max_lms + 3 * (size_t)max_lms;
-  size_t b = d * 8 + ((size_t)max_poses * max_lms + max_lms) * 4;
+  size_t ints = (size_t)max_poses * max_lms + max_lms + max_edges + 3 * pair_capacity(max_poses, max_edges);
+  size_t b = d * 8 + ints * 4;
   return (b + 255) & ~(size_t)255;
+}
+
+size_t ba_dyn_smem(int nfree) {
+  const size_t n = 6 * (size_t)nfree;
+  return (n * (n + 1) + n + 8) * 8;
 }
 
 }  // namespace
@@ -649,7 +733,7 @@ int flv_ba_reserve(flv_ctx* ctx, int max_poses, int max_landmarks, int max_edges
   ctx->ba_ws_bytes = total;
   ctx->ba_max_poses = max_poses; ctx->ba_max_lms = max_landmarks; ctx->ba_max_edges = max_edges;
   int nfree = max_poses < BA_MAX_FREE ? max_poses : BA_MAX_FREE;
-  size_t smem = ((size_t)36 * nfree * nfree + 6 * nfree) * 8;
+  size_t smem = ba_dyn_smem(nfree);
   FLV_CUDA(ctx, cudaFuncSetAttribute(ba_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   return FLV_OK;
 }
@@ -664,19 +748,22 @@ int flv_ba_optimize(flv_ctx* ctx, int n_streams, const flv_ba_problem* problems,
   const int MP = ctx->ba_max_poses, ML = ctx->ba_max_lms, ME = ctx->ba_max_edges;
   const size_t stride = ws_stride_bytes(MP, ML, ME);
   unsigned char* tail = (unsigned char*)ctx->ba_ws + stride * ctx->S;
-  flv_ba_problem* d_prob = (flv_ba_problem*)tail;
-  flv_ba_stats* d_stats = (flv_ba_stats*)(tail + (size_t)ctx->S * sizeof(flv_ba_problem));
+  const int slot0 = prm->ws_slot0;
+  if (slot0 < 0 || slot0 + n_streams > ctx->S) FLV_FAIL(ctx, FLV_ERR_INVALID, "ws_slot0 %d + %d streams exceeds %d slots", slot0, n_streams, ctx->S);
+  flv_ba_problem* d_prob = (flv_ba_problem*)tail + slot0;
+  flv_ba_stats* d_stats = (flv_ba_stats*)(tail + (size_t)ctx->S * sizeof(flv_ba_problem)) + slot0;
   BAArgs a;
-  a.prof = (long long*)(tail + (size_t)ctx->S * (sizeof(flv_ba_problem) + sizeof(flv_ba_stats)));
+  a.prof = (long long*)(tail + (size_t)ctx->S * (sizeof(flv_ba_problem) + sizeof(flv_ba_stats))) + 8 * slot0;
   a.prm = *prm; a.max_poses = MP; a.max_lms = ML; a.max_edges = ME;
-  a.ws = (unsigned char*)ctx->ba_ws; a.ws_stride = stride;
+  a.ws = (unsigned char*)ctx->ba_ws + stride * slot0; a.ws_stride = stride;
   const int nfree = MP < BA_MAX_FREE ? MP : BA_MAX_FREE;
-  const size_t smem = ((size_t)36 * nfree * nfree + 6 * nfree) * 8;
+  const size_t smem = ba_dyn_smem(nfree);
   const size_t S = n_streams;
+  cudaStream_t stream = ctx->ba_stream_set ? ctx->ba_stream : ctx->stream;
   if (mem == FLV_MEM_DEVICE) {
     a.problems = problems; a.poses = poses; a.lms = landmarks; a.ep = edge_pose; a.el = edge_lm; a.uv = edge_uv;
     a.active = edge_active; a.stats = stats;
-    ba_kernel<<<n_streams, BA_THREADS, smem, ctx->stream>>>(a);
+    ba_kernel<<<n_streams, BA_THREADS, smem, stream>>>(a);
     ctx->launches++;
     FLV_CUDA(ctx, cudaGetLastError());
     return FLV_OK;
@@ -696,22 +783,29 @@ int flv_ba_optimize(flv_ctx* ctx, int n_streams, const flv_ba_problem* problems,
   char* hs = (char*)ctx->h_stage; char* ds = (char*)ctx->d_stage;
   memcpy(hs + o_pose, poses, b_pose); memcpy(hs + o_lm, landmarks, b_lm); memcpy(hs + o_uv, edge_uv, b_uv);
   memcpy(hs + o_ep, edge_pose, b_i); memcpy(hs + o_el, edge_lm, b_i); memcpy(hs + o_act, edge_active, b_a);
-  FLV_CUDA(ctx, cudaMemcpyAsync(ds, hs, total, cudaMemcpyHostToDevice, ctx->stream));
-  FLV_CUDA(ctx, cudaMemcpyAsync(d_prob, problems, S * sizeof(flv_ba_problem), cudaMemcpyHostToDevice, ctx->stream));
+  FLV_CUDA(ctx, cudaMemcpyAsync(ds, hs, total, cudaMemcpyHostToDevice, stream));
+  FLV_CUDA(ctx, cudaMemcpyAsync(d_prob, problems, S * sizeof(flv_ba_problem), cudaMemcpyHostToDevice, stream));
   a.problems = d_prob; a.poses = (double*)(ds + o_pose); a.lms = (double*)(ds + o_lm); a.uv = (const double*)(ds + o_uv);
   a.ep = (const int*)(ds + o_ep); a.el = (const int*)(ds + o_el); a.active = (uint8_t*)(ds + o_act); a.stats = d_stats;
-  ba_kernel<<<n_streams, BA_THREADS, smem, ctx->stream>>>(a);
+  ba_kernel<<<n_streams, BA_THREADS, smem, stream>>>(a);
   ctx->launches++;
   FLV_CUDA(ctx, cudaGetLastError());
-  FLV_CUDA(ctx, cudaMemcpyAsync(hs + o_pose, ds + o_pose, b_pose + b_lm, cudaMemcpyDeviceToHost, ctx->stream));
-  FLV_CUDA(ctx, cudaMemcpyAsync(hs + o_act, ds + o_act, b_a, cudaMemcpyDeviceToHost, ctx->stream));
-  FLV_CUDA(ctx, cudaMemcpyAsync(stats, d_stats, S * sizeof(flv_ba_stats), cudaMemcpyDeviceToHost, ctx->stream));
-  FLV_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  FLV_CUDA(ctx, cudaMemcpyAsync(hs + o_pose, ds + o_pose, b_pose + b_lm, cudaMemcpyDeviceToHost, stream));
+  FLV_CUDA(ctx, cudaMemcpyAsync(hs + o_act, ds + o_act, b_a, cudaMemcpyDeviceToHost, stream));
+  FLV_CUDA(ctx, cudaMemcpyAsync(stats, d_stats, S * sizeof(flv_ba_stats), cudaMemcpyDeviceToHost, stream));
+  FLV_CUDA(ctx, cudaStreamSynchronize(stream));
   memcpy(poses, hs + o_pose, b_pose); memcpy(landmarks, hs + o_lm, b_lm); memcpy(edge_active, hs + o_act, b_a);
   for (int s = 0; s < n_streams; ++s)
     if (stats[s].reserved)
       FLV_FAIL(ctx, FLV_ERR_UNSUPPORTED, "stream %d: %s", s,
-               stats[s].reserved == 1 ? "pose count outside [1,32]" : "more than 24 free poses (reduced system > 144)");
+               stats[s].reserved == 1 ? "pose count outside [1,32]" : stats[s].reserved == 2 ? "more than 24 free poses (reduced system > 144)" : "pose-pair list capacity exceeded");
+  return FLV_OK;
+}
+
+int flv_set_ba_stream(flv_ctx* ctx, void* cuda_stream, int enable) {
+  if (!ctx) return FLV_ERR_INVALID;
+  ctx->ba_stream = (cudaStream_t)cuda_stream;
+  ctx->ba_stream_set = enable ? 1 : 0;
   return FLV_OK;
 }
 
@@ -721,7 +815,7 @@ int flv_ba_profile(flv_ctx* ctx, int stream, long long* out8) {
   const size_t stride = ws_stride_bytes(ctx->ba_max_poses, ctx->ba_max_lms, ctx->ba_max_edges);
   unsigned char* tail = (unsigned char*)ctx->ba_ws + stride * ctx->S;
   long long* d = (long long*)(tail + (size_t)ctx->S * (sizeof(flv_ba_problem) + sizeof(flv_ba_stats)));
-  FLV_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  FLV_CUDA(ctx, cudaDeviceSynchronize());
   FLV_CUDA(ctx, cudaMemcpy(out8, d + 8 * stream, 64, cudaMemcpyDeviceToHost));
   return FLV_OK;
 }

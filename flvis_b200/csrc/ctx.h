@@ -59,6 +59,8 @@ struct flv_ctx {
   // BA
   int ba_max_poses, ba_max_lms, ba_max_edges;
   void* ba_ws;                    // device workspace
+  cudaStream_t ba_stream;         // optional separate stream for flv_ba_optimize (local-map thread analogue)
+  int ba_stream_set;
   size_t ba_ws_bytes;
 };
 

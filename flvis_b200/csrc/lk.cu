@@ -16,6 +16,7 @@
 // 1-2 sectors per request).  Border handling is index reflection (BORDER_REFLECT_101 for
 // intensities, zero derivative outside the image) instead of OpenCV's padded copies, so the
 // kernel reads exactly the pyramid bytes (2P + 29N algorithmic bytes per call).
+#include <stdlib.h>
 #include "ctx.h"
 
 namespace {
@@ -55,8 +56,38 @@ __device__ __forceinline__ void bilinear_weights(float a, float b, int& w00, int
   w11 = (1 << WB) - w00 - w01 - w10;
 }
 
-template <int WARPS>
-__global__ void __launch_bounds__(WARPS * 32)
+// One pass over the 31x31 window at integer origin (inx, iny) of image J with bilinear weights w**:
+//   diff(r,c) = DESCALE(bilinear(J), 9) - Ival(r,c)   -- the rounding constant and -Ival<<9 are pre-folded in tIc
+//   ERR = false: o1 += diff*Ix, o2 += diff*Iy (tXY packs Iy<<16 | Ix&0xffff);  ERR = true: o1 += |diff|.
+// INTERIOR = the whole 32x32 tap footprint lies inside the image: rows are walked with a pointer, no reflection.
+template <bool INTERIOR, bool ERR>
+__device__ __forceinline__ void window_pass(const uint8_t* __restrict__ J, int pitch, int w, int h, int inx, int iny,
+                                            int lane, int w00, int w01, int w10, int w11, const int (&tIc)[WIN],
+                                            const int (&tXY)[WIN], bool live, int& o1, int& o2) {
+  const uint8_t* p = J + (size_t)(INTERIOR ? iny : 0) * pitch + (INTERIOR ? inx + lane : 0);
+  const int xj = INTERIOR ? 0 : reflect101(inx + lane, w);
+  int q = INTERIOR ? (int)p[0] : (int)J[(size_t)reflect101(iny, h) * pitch + xj];
+  int qr = __shfl_down_sync(FULL, q, 1);
+#pragma unroll
+  for (int r = 1; r <= WIN; ++r) {
+    if (INTERIOR) p += pitch;
+    const int v = INTERIOR ? (int)p[0] : (int)J[(size_t)reflect101(iny + r, h) * pitch + xj];
+    const int vr = __shfl_down_sync(FULL, v, 1);
+    const int diff = (q * w00 + qr * w01 + v * w10 + vr * w11 + tIc[r - 1]) >> (WB - 5);
+    if (ERR) {
+      const int d = live ? diff : 0;
+      o1 += d < 0 ? -d : d;
+    } else {
+      const int xy = tXY[r - 1];
+      o1 += diff * (int)(short)(xy & 0xffff);
+      o2 += diff * (xy >> 16);
+    }
+    q = v; qr = vr;
+  }
+}
+
+template <int WARPS, int MINB>
+__global__ void __launch_bounds__(WARPS * 32, MINB)
 lk_track_kernel(const uint8_t* __restrict__ pyrI, const uint8_t* __restrict__ pyrJ, LKGeom g,
                 const int* __restrict__ npts, const float* __restrict__ prev_xy,
                 const float* __restrict__ init_xy, float* __restrict__ next_xy,
@@ -96,7 +127,7 @@ lk_track_kernel(const uint8_t* __restrict__ pyrI, const uint8_t* __restrict__ py
     bilinear_weights(px - (float)ipx, py - (float)ipy, w00, w01, w10, w11);
 
     // ---- template patch: Ival (5 guard bits), Ix, Iy (Scharr, int16 range) -------------------
-    int tI[WIN], tX[WIN], tY[WIN];
+    int tIc[WIN], tXY[WIN];   // tIc = (1<<8) - (Ival<<9); tXY = Iy<<16 | Ix&0xffff
     int a11 = 0, a12 = 0, a22 = 0;
     {
       const int x = ipx + lane;
@@ -128,7 +159,8 @@ lk_track_kernel(const uint8_t* __restrict__ pyrI, const uint8_t* __restrict__ py
           int ix = (qX * w00 + qXr * w01 + vX * w10 + vXr * w11 + (1 << (WB - 1))) >> WB;
           int iy = (qY * w00 + qYr * w01 + vY * w10 + vYr * w11 + (1 << (WB - 1))) >> WB;
           iv = live ? iv : 0; ix = live ? ix : 0; iy = live ? iy : 0;
-          tI[k - 1] = iv; tX[k - 1] = ix; tY[k - 1] = iy;
+          tIc[k - 1] = (1 << (WB - 5 - 1)) - (iv << (WB - 5));
+          tXY[k - 1] = (iy << 16) | (ix & 0xffff);
           a11 += ix * ix; a12 += ix * iy; a22 += iy * iy;
         }
         qI = vI; qX = vX; qY = vY; qIr = vIr; qXr = vXr; qYr = vYr;
@@ -157,20 +189,11 @@ lk_track_kernel(const uint8_t* __restrict__ pyrI, const uint8_t* __restrict__ py
         break;
       }
       bilinear_weights(cx - (float)inx, cy - (float)iny, w00, w01, w10, w11);
-      const int xj = reflect101(inx + lane, w);
       int b1 = 0, b2 = 0;
-      int q = J[(size_t)reflect101(iny, h) * pitch + xj];
-      int qr = __shfl_down_sync(FULL, q, 1);
-#pragma unroll
-      for (int r = 1; r <= WIN; ++r) {
-        const int v = J[(size_t)reflect101(iny + r, h) * pitch + xj];
-        const int vr = __shfl_down_sync(FULL, v, 1);
-        const int jv = (q * w00 + qr * w01 + v * w10 + vr * w11 + (1 << (WB - 5 - 1))) >> (WB - 5);
-        const int diff = jv - tI[r - 1];
-        b1 += diff * tX[r - 1];
-        b2 += diff * tY[r - 1];
-        q = v; qr = vr;
-      }
+      if (inx >= 0 && inx + WIN < w && iny >= 0 && iny + WIN < h)
+        window_pass<true, false>(J, pitch, w, h, inx, iny, lane, w00, w01, w10, w11, tIc, tXY, live, b1, b2);
+      else
+        window_pass<false, false>(J, pitch, w, h, inx, iny, lane, w00, w01, w10, w11, tIc, tXY, live, b1, b2);
       const float fb1 = __ll2float_rn(warp_sum_exact(b1)) * FLT_SCALE;
       const float fb2 = __ll2float_rn(warp_sum_exact(b2)) * FLT_SCALE;
       const float dx = (A12 * fb2 - A22 * fb1) * D;
@@ -192,19 +215,11 @@ lk_track_kernel(const uint8_t* __restrict__ pyrI, const uint8_t* __restrict__ py
         st = 0;
       } else {
         bilinear_weights(qx - (float)inx, qy - (float)iny, w00, w01, w10, w11);
-        const int xj = reflect101(inx + lane, w);
-        int e = 0;
-        int q = J[(size_t)reflect101(iny, h) * pitch + xj];
-        int qr = __shfl_down_sync(FULL, q, 1);
-#pragma unroll
-        for (int r = 1; r <= WIN; ++r) {
-          const int v = J[(size_t)reflect101(iny + r, h) * pitch + xj];
-          const int vr = __shfl_down_sync(FULL, v, 1);
-          const int jv = (q * w00 + qr * w01 + v * w10 + vr * w11 + (1 << (WB - 5 - 1))) >> (WB - 5);
-          const int diff = live ? (jv - tI[r - 1]) : 0;
-          e += diff < 0 ? -diff : diff;
-          q = v; qr = vr;
-        }
+        int e = 0, unused = 0;
+        if (inx >= 0 && inx + WIN < w && iny >= 0 && iny + WIN < h)
+          window_pass<true, true>(J, pitch, w, h, inx, iny, lane, w00, w01, w10, w11, tIc, tXY, live, e, unused);
+        else
+          window_pass<false, true>(J, pitch, w, h, inx, iny, lane, w00, w01, w10, w11, tIc, tXY, live, e, unused);
         er = __ll2float_rn(warp_sum_exact(e)) * err_scale;
       }
     }
@@ -257,9 +272,16 @@ int flv_launch_lk(flv_ctx* ctx, int src_slot, int dst_slot, int n_streams, const
   constexpr int WARPS = 4;
   dim3 grid((ctx->max_pts + WARPS - 1) / WARPS, n_streams);
   const float err_scale = (float)(1.0 / (32 * WIN * WIN));
-  lk_track_kernel<WARPS><<<grid, WARPS * 32, 0, ctx->stream>>>(
-      ctx->pyr[src_slot], ctx->pyr[dst_slot], g, d_npts, d_prev, d_init, d_next, d_status, d_err,
-      ctx->max_pts, nlev_used, max_iter, eps2, min_eig_thr, err_scale);
+  // two register budgets of the same kernel: 168 regs / 12 warps per SM (no spills) or 128 regs / 16 warps per SM
+  static const int variant = getenv("FLV_LK_VARIANT") ? atoi(getenv("FLV_LK_VARIANT")) : 3;
+  if (variant == 4)
+    lk_track_kernel<WARPS, 4><<<grid, WARPS * 32, 0, ctx->stream>>>(
+        ctx->pyr[src_slot], ctx->pyr[dst_slot], g, d_npts, d_prev, d_init, d_next, d_status, d_err,
+        ctx->max_pts, nlev_used, max_iter, eps2, min_eig_thr, err_scale);
+  else
+    lk_track_kernel<WARPS, 3><<<grid, WARPS * 32, 0, ctx->stream>>>(
+        ctx->pyr[src_slot], ctx->pyr[dst_slot], g, d_npts, d_prev, d_init, d_next, d_status, d_err,
+        ctx->max_pts, nlev_used, max_iter, eps2, min_eig_thr, err_scale);
   ctx->launches++;
   FLV_CUDA(ctx, cudaGetLastError());
   return FLV_OK;

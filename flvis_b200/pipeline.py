@@ -112,6 +112,10 @@ class FrontendBench:
         self.collect_lk = False
         return ms, n
 
+    def join(self):
+        if self.has_ba:
+            self.ba.join(self.stream)
+
     def step(self, i, mode):
         with self.torch.cuda.stream(self.stream):
             self._step(i, mode)

@@ -150,6 +150,8 @@ typedef struct {
   double huber_delta; /* 1.0 */
   double cull_chi2;   /* 3.0 */
   int min_edges_after_cull; /* 0 (local map) / 10 (pose only: fail if fewer) */
+  int ws_slot0;       /* workspace slot of the first problem of this call: 0 unless several calls are in flight
+                         concurrently on different streams (then give them disjoint [ws_slot0, ws_slot0+n) ranges) */
 } flv_ba_params;
 typedef struct {
   int iterations_run; /* total LM iterations executed (both phases) */
@@ -170,6 +172,11 @@ int flv_ba_optimize(flv_ctx* ctx, int n_streams, const flv_ba_problem* problems,
                     const flv_ba_params* prm, double* poses, double* landmarks,
                     const int* edge_pose, const int* edge_lm, const double* edge_uv,
                     uint8_t* edge_active, flv_ba_stats* stats, flv_memspace mem);
+
+/* Run subsequent flv_ba_optimize calls on `cuda_stream` instead of the context stream (enable=1), the analogue of
+ * FLVIS's separate local-map thread: the BA of keyframe k overlaps the tracking of the following frames.
+ * enable=0 reverts to the context stream.  The caller orders the streams (events) as it needs. */
+int flv_set_ba_stream(flv_ctx* ctx, void* cuda_stream, int enable);
 
 /* Debug: SM cycle counters of the last flv_ba_optimize for `stream`:
  * out8 = {chi2, build, schur, cholesky, substitution, update, setup, unused}. Synchronises. */
