@@ -109,6 +109,7 @@ void flv_destroy(flv_ctx* ctx) {
   flv_ba_free(ctx);
   if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
   if (ctx->d_stage) cudaFree(ctx->d_stage);
+  if (ctx->d_img_stage) cudaFree(ctx->d_img_stage);
   if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
 }
@@ -152,18 +153,27 @@ int flv_upload_images(flv_ctx* ctx, int slot, int n_streams, const uint8_t* imgs
   if (!ctx || !imgs || slot < 0 || slot >= FLV_NUM_SLOTS || n_streams < 1 || n_streams > ctx->S ||
       row_stride_bytes < (size_t)ctx->w)
     return FLV_ERR_INVALID;
-  const LevelGeom& L0 = ctx->geom.lv[0];
-  cudaMemcpyKind kind = mem == FLV_MEM_HOST ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice;
-  if (img_stride_bytes == row_stride_bytes * (size_t)ctx->h) {
-    // one 2D copy: rows of all streams are equally spaced on the source side only if the
-    // destination is too -- it is not (stream_stride != pitch*h in general), so go per stream
+  if (mem == FLV_MEM_DEVICE) return flv_launch_unpack(ctx, slot, n_streams, imgs, row_stride_bytes, img_stride_bytes);
+  // host images: one (2D) H2D copy of all streams into a tight device staging area, then one unpack launch.
+  const size_t w = ctx->w, h = ctx->h, bytes = (size_t)n_streams * w * h;
+  if (bytes > ctx->img_stage_bytes) {
+    if (ctx->d_img_stage) cudaFree(ctx->d_img_stage);
+    ctx->d_img_stage = nullptr; ctx->img_stage_bytes = 0;
+    FLV_CUDA(ctx, cudaMalloc(&ctx->d_img_stage, (size_t)ctx->S * w * h));
+    ctx->img_stage_bytes = (size_t)ctx->S * w * h;
   }
-  for (int s = 0; s < n_streams; ++s) {
-    FLV_CUDA(ctx, cudaMemcpy2DAsync(ctx->pyr[slot] + (size_t)s * ctx->geom.stream_stride + L0.off,
-                                    L0.pitch, imgs + (size_t)s * img_stride_bytes, row_stride_bytes,
-                                    ctx->w, ctx->h, kind, ctx->stream));
+  uint8_t* st = (uint8_t*)ctx->d_img_stage;
+  if (row_stride_bytes == w && img_stride_bytes == w * h) {
+    FLV_CUDA(ctx, cudaMemcpyAsync(st, imgs, bytes, cudaMemcpyHostToDevice, ctx->stream));
+  } else if (img_stride_bytes == row_stride_bytes * h) {
+    FLV_CUDA(ctx, cudaMemcpy2DAsync(st, w, imgs, row_stride_bytes, w, h * (size_t)n_streams, cudaMemcpyHostToDevice,
+                                    ctx->stream));
+  } else {
+    for (int s = 0; s < n_streams; ++s)
+      FLV_CUDA(ctx, cudaMemcpy2DAsync(st + (size_t)s * w * h, w, imgs + (size_t)s * img_stride_bytes, row_stride_bytes,
+                                      w, h, cudaMemcpyHostToDevice, ctx->stream));
   }
-  return FLV_OK;
+  return flv_launch_unpack(ctx, slot, n_streams, st, w, w * h);
 }
 
 int flv_build_pyramid(flv_ctx* ctx, int slot, int n_streams) {

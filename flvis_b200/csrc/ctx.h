@@ -32,6 +32,7 @@ struct flv_ctx {
   // staging for FLV_MEM_HOST calls (pinned host + device mirrors)
   void* h_stage; size_t h_stage_bytes;
   void* d_stage; size_t d_stage_bytes;
+  void* d_img_stage; size_t img_stage_bytes;   // tight [S][h][w] landing area of host image uploads
 
   // LK
   int* d_npts;                    // [S]
@@ -85,6 +86,7 @@ int flv_stage_reserve(flv_ctx* ctx, size_t bytes);
 
 // kernel launchers (one per .cu)
 int flv_launch_pyramid(flv_ctx* ctx, int slot, int n_streams);
+int flv_launch_unpack(flv_ctx* ctx, int slot, int n_streams, const uint8_t* d_src, size_t row_stride, size_t img_stride);
 int flv_launch_lk(flv_ctx* ctx, int src_slot, int dst_slot, int n_streams, const int* d_npts,
                   const float* d_prev, const float* d_init, float* d_next, uint8_t* d_status,
                   float* d_err, int nlev_used, int max_iter, double eps2, double min_eig_thr);

@@ -1,3 +1,4 @@
+// A/B baseline (first version of the tracker kept for kernel comparisons; FLV_LK_VARIANT=1).
 // K2/K3 -- pyramidal Lucas-Kanade tracker, one warp per (stream, point), all levels in one launch.
 //
 // Reference: cv::calcOpticalFlowPyrLK as called at src/processing/lkorb_tracking.cpp:64-73
@@ -16,7 +17,6 @@
 // 1-2 sectors per request).  Border handling is index reflection (BORDER_REFLECT_101 for
 // intensities, zero derivative outside the image) instead of OpenCV's padded copies, so the
 // kernel reads exactly the pyramid bytes (2P + 29N algorithmic bytes per call).
-#include <stdlib.h>
 #include "ctx.h"
 
 namespace {
@@ -56,39 +56,9 @@ __device__ __forceinline__ void bilinear_weights(float a, float b, int& w00, int
   w11 = (1 << WB) - w00 - w01 - w10;
 }
 
-// One pass over the 31x31 window at integer origin (inx, iny) of image J with bilinear weights w**:
-//   diff(r,c) = DESCALE(bilinear(J), 9) - Ival(r,c)   -- the rounding constant and -Ival<<9 are pre-folded in tIc
-//   ERR = false: o1 += diff*Ix, o2 += diff*Iy (tXY packs Iy<<16 | Ix&0xffff);  ERR = true: o1 += |diff|.
-// INTERIOR = the whole 32x32 tap footprint lies inside the image: rows are walked with a pointer, no reflection.
-template <bool INTERIOR, bool ERR>
-__device__ __forceinline__ void window_pass(const uint8_t* __restrict__ J, int pitch, int w, int h, int inx, int iny,
-                                            int lane, int w00, int w01, int w10, int w11, const int (&tIc)[WIN],
-                                            const int (&tXY)[WIN], bool live, int& o1, int& o2) {
-  const uint8_t* p = J + (size_t)(INTERIOR ? iny : 0) * pitch + (INTERIOR ? inx + lane : 0);
-  const int xj = INTERIOR ? 0 : reflect101(inx + lane, w);
-  int q = INTERIOR ? (int)p[0] : (int)J[(size_t)reflect101(iny, h) * pitch + xj];
-  int qr = __shfl_down_sync(FULL, q, 1);
-#pragma unroll
-  for (int r = 1; r <= WIN; ++r) {
-    // independent address per row (no serial pointer chain): the 32 row loads issue back to back
-    const int v = INTERIOR ? (int)p[r * pitch] : (int)J[(size_t)reflect101(iny + r, h) * pitch + xj];
-    const int vr = __shfl_down_sync(FULL, v, 1);
-    const int diff = (q * w00 + qr * w01 + v * w10 + vr * w11 + tIc[r - 1]) >> (WB - 5);
-    if (ERR) {
-      const int d = live ? diff : 0;
-      o1 += d < 0 ? -d : d;
-    } else {
-      const int xy = tXY[r - 1];
-      o1 += diff * (int)(short)(xy & 0xffff);
-      o2 += diff * (xy >> 16);
-    }
-    q = v; qr = vr;
-  }
-}
-
-template <int WARPS, int MINB>
-__global__ void __launch_bounds__(WARPS * 32, MINB)
-lk_track_kernel(const uint8_t* __restrict__ pyrI, const uint8_t* __restrict__ pyrJ, LKGeom g,
+template <int WARPS>
+__global__ void __launch_bounds__(WARPS * 32)
+lk_track_kernel_v1(const uint8_t* __restrict__ pyrI, const uint8_t* __restrict__ pyrJ, LKGeom g,
                 const int* __restrict__ npts, const float* __restrict__ prev_xy,
                 const float* __restrict__ init_xy, float* __restrict__ next_xy,
                 uint8_t* __restrict__ status, float* __restrict__ err, int max_pts, int nlev_used,
@@ -109,7 +79,6 @@ lk_track_kernel(const uint8_t* __restrict__ pyrI, const uint8_t* __restrict__ py
   const float FLT_SCALE = 1.f / (float)(1 << 20);
   const bool live = lane < WIN;
 
-#pragma unroll 1
   for (int level = nlev_used - 1; level >= 0; --level) {
     const int w = g.w[level], h = g.h[level], pitch = g.pitch[level];
     const uint8_t* I = Ibase + g.off[level];
@@ -128,7 +97,7 @@ lk_track_kernel(const uint8_t* __restrict__ pyrI, const uint8_t* __restrict__ py
     bilinear_weights(px - (float)ipx, py - (float)ipy, w00, w01, w10, w11);
 
     // ---- template patch: Ival (5 guard bits), Ix, Iy (Scharr, int16 range) -------------------
-    int tIc[WIN], tXY[WIN];   // tIc = (1<<8) - (Ival<<9); tXY = Iy<<16 | Ix&0xffff
+    int tI[WIN], tX[WIN], tY[WIN];
     int a11 = 0, a12 = 0, a22 = 0;
     {
       const int x = ipx + lane;
@@ -160,8 +129,7 @@ lk_track_kernel(const uint8_t* __restrict__ pyrI, const uint8_t* __restrict__ py
           int ix = (qX * w00 + qXr * w01 + vX * w10 + vXr * w11 + (1 << (WB - 1))) >> WB;
           int iy = (qY * w00 + qYr * w01 + vY * w10 + vYr * w11 + (1 << (WB - 1))) >> WB;
           iv = live ? iv : 0; ix = live ? ix : 0; iy = live ? iy : 0;
-          tIc[k - 1] = (1 << (WB - 5 - 1)) - (iv << (WB - 5));
-          tXY[k - 1] = (iy << 16) | (ix & 0xffff);
+          tI[k - 1] = iv; tX[k - 1] = ix; tY[k - 1] = iy;
           a11 += ix * ix; a12 += ix * iy; a22 += iy * iy;
         }
         qI = vI; qX = vX; qY = vY; qIr = vIr; qXr = vXr; qYr = vYr;
@@ -183,7 +151,6 @@ lk_track_kernel(const uint8_t* __restrict__ pyrI, const uint8_t* __restrict__ py
     D = 1.f / D;
     float cx = nx - half, cy = ny - half;
     float pdx = 0.f, pdy = 0.f;
-#pragma unroll 1
     for (int j = 0; j < max_iter; ++j) {
       const int inx = (int)floorf(cx), iny = (int)floorf(cy);
       if (inx < -WIN || inx >= w || iny < -WIN || iny >= h) {
@@ -191,11 +158,20 @@ lk_track_kernel(const uint8_t* __restrict__ pyrI, const uint8_t* __restrict__ py
         break;
       }
       bilinear_weights(cx - (float)inx, cy - (float)iny, w00, w01, w10, w11);
+      const int xj = reflect101(inx + lane, w);
       int b1 = 0, b2 = 0;
-      if (inx >= 0 && inx + WIN < w && iny >= 0 && iny + WIN < h)
-        window_pass<true, false>(J, pitch, w, h, inx, iny, lane, w00, w01, w10, w11, tIc, tXY, live, b1, b2);
-      else
-        window_pass<false, false>(J, pitch, w, h, inx, iny, lane, w00, w01, w10, w11, tIc, tXY, live, b1, b2);
+      int q = J[(size_t)reflect101(iny, h) * pitch + xj];
+      int qr = __shfl_down_sync(FULL, q, 1);
+#pragma unroll
+      for (int r = 1; r <= WIN; ++r) {
+        const int v = J[(size_t)reflect101(iny + r, h) * pitch + xj];
+        const int vr = __shfl_down_sync(FULL, v, 1);
+        const int jv = (q * w00 + qr * w01 + v * w10 + vr * w11 + (1 << (WB - 5 - 1))) >> (WB - 5);
+        const int diff = jv - tI[r - 1];
+        b1 += diff * tX[r - 1];
+        b2 += diff * tY[r - 1];
+        q = v; qr = vr;
+      }
       const float fb1 = __ll2float_rn(warp_sum_exact(b1)) * FLT_SCALE;
       const float fb2 = __ll2float_rn(warp_sum_exact(b2)) * FLT_SCALE;
       const float dx = (A12 * fb2 - A22 * fb1) * D;
@@ -217,8 +193,19 @@ lk_track_kernel(const uint8_t* __restrict__ pyrI, const uint8_t* __restrict__ py
         st = 0;
       } else {
         bilinear_weights(qx - (float)inx, qy - (float)iny, w00, w01, w10, w11);
-        int e = 0, unused = 0;    // once per point: the generic (reflecting) pass keeps the code footprint small
-        window_pass<false, true>(J, pitch, w, h, inx, iny, lane, w00, w01, w10, w11, tIc, tXY, live, e, unused);
+        const int xj = reflect101(inx + lane, w);
+        int e = 0;
+        int q = J[(size_t)reflect101(iny, h) * pitch + xj];
+        int qr = __shfl_down_sync(FULL, q, 1);
+#pragma unroll
+        for (int r = 1; r <= WIN; ++r) {
+          const int v = J[(size_t)reflect101(iny + r, h) * pitch + xj];
+          const int vr = __shfl_down_sync(FULL, v, 1);
+          const int jv = (q * w00 + qr * w01 + v * w10 + vr * w11 + (1 << (WB - 5 - 1))) >> (WB - 5);
+          const int diff = live ? (jv - tI[r - 1]) : 0;
+          e += diff < 0 ? -diff : diff;
+          q = v; qr = vr;
+        }
         er = __ll2float_rn(warp_sum_exact(e)) * err_scale;
       }
     }
@@ -231,38 +218,9 @@ lk_track_kernel(const uint8_t* __restrict__ pyrI, const uint8_t* __restrict__ py
   }
 }
 
-__global__ void select_tracked_kernel(const int* __restrict__ npts, const float2* __restrict__ prev,
-                                      const float2* __restrict__ next, const uint8_t* __restrict__ status,
-                                      uint8_t* __restrict__ keep, float2* __restrict__ out,
-                                      double2* __restrict__ out64, int max_pts, int w, int h) {
-  const int s = blockIdx.y, i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= npts[s]) return;
-  const size_t k = (size_t)s * max_pts + i;
-  const float2 n = next[k], p = prev[k];
-  const bool ok = status[k] == 1 && n.x > 0.f && n.y > 0.f && n.x < (float)(w - 1) && n.y < (float)(h - 1);
-  const float2 o = ok ? n : p;
-  if (keep) keep[k] = ok ? 1 : 0;
-  if (out) out[k] = o;
-  if (out64) out64[k] = make_double2((double)o.x, (double)o.y);
-}
-
 }  // namespace
 
-int flv_launch_select(flv_ctx* ctx, int n_streams, const int* d_npts, const float* prev, const float* next,
-                      const uint8_t* status, uint8_t* keep, float* out, double* out64) {
-  dim3 grid((ctx->max_pts + 127) / 128, n_streams);
-  select_tracked_kernel<<<grid, 128, 0, ctx->stream>>>(d_npts, (const float2*)prev, (const float2*)next, status, keep,
-                                                       (float2*)out, (double2*)out64, ctx->max_pts, ctx->w, ctx->h);
-  ctx->launches++;
-  FLV_CUDA(ctx, cudaGetLastError());
-  return FLV_OK;
-}
-
 int flv_launch_lk_v1(flv_ctx* ctx, int src_slot, int dst_slot, int n_streams, const int* d_npts,
-                     const float* d_prev, const float* d_init, float* d_next, uint8_t* d_status,
-                     float* d_err, int nlev_used, int max_iter, double eps2, double min_eig_thr);
-
-int flv_launch_lk(flv_ctx* ctx, int src_slot, int dst_slot, int n_streams, const int* d_npts,
                   const float* d_prev, const float* d_init, float* d_next, uint8_t* d_status,
                   float* d_err, int nlev_used, int max_iter, double eps2, double min_eig_thr) {
   LKGeom g;
@@ -275,19 +233,9 @@ int flv_launch_lk(flv_ctx* ctx, int src_slot, int dst_slot, int n_streams, const
   constexpr int WARPS = 4;
   dim3 grid((ctx->max_pts + WARPS - 1) / WARPS, n_streams);
   const float err_scale = (float)(1.0 / (32 * WIN * WIN));
-  // two register budgets of the same kernel: 168 regs / 12 warps per SM (no spills) or 128 regs / 16 warps per SM
-  static const int variant = getenv("FLV_LK_VARIANT") ? atoi(getenv("FLV_LK_VARIANT")) : 3;
-  if (variant == 1)
-    return flv_launch_lk_v1(ctx, src_slot, dst_slot, n_streams, d_npts, d_prev, d_init, d_next, d_status, d_err, nlev_used,
-                            max_iter, eps2, min_eig_thr);
-  if (variant == 4)
-    lk_track_kernel<WARPS, 4><<<grid, WARPS * 32, 0, ctx->stream>>>(
-        ctx->pyr[src_slot], ctx->pyr[dst_slot], g, d_npts, d_prev, d_init, d_next, d_status, d_err,
-        ctx->max_pts, nlev_used, max_iter, eps2, min_eig_thr, err_scale);
-  else
-    lk_track_kernel<WARPS, 3><<<grid, WARPS * 32, 0, ctx->stream>>>(
-        ctx->pyr[src_slot], ctx->pyr[dst_slot], g, d_npts, d_prev, d_init, d_next, d_status, d_err,
-        ctx->max_pts, nlev_used, max_iter, eps2, min_eig_thr, err_scale);
+  lk_track_kernel_v1<WARPS><<<grid, WARPS * 32, 0, ctx->stream>>>(
+      ctx->pyr[src_slot], ctx->pyr[dst_slot], g, d_npts, d_prev, d_init, d_next, d_status, d_err,
+      ctx->max_pts, nlev_used, max_iter, eps2, min_eig_thr, err_scale);
   ctx->launches++;
   FLV_CUDA(ctx, cudaGetLastError());
   return FLV_OK;

@@ -60,7 +60,46 @@ __global__ void __launch_bounds__(256) pyr_down_kernel(const uint8_t* __restrict
   }
 }
 
+// level-0 ingest: tight or strided source images (device memory) -> the slot's pitched level-0 rows, all streams
+// in one launch.  VEC = 16-byte path when every row start is 16-byte aligned and w % 16 == 0.
+template <bool VEC>
+__global__ void __launch_bounds__(256) unpack_images_kernel(const uint8_t* __restrict__ src, size_t row_stride,
+                                                            size_t img_stride, uint8_t* __restrict__ dst_base,
+                                                            size_t stream_stride, int pitch, int w, int h) {
+  const int s = blockIdx.z;
+  const int y = blockIdx.y * blockDim.y + threadIdx.y;
+  if (y >= h) return;
+  const uint8_t* srow = src + (size_t)s * img_stride + (size_t)y * row_stride;
+  uint8_t* drow = dst_base + (size_t)s * stream_stride + (size_t)y * pitch;
+  if (VEC) {
+    const int n16 = w >> 4;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += gridDim.x * blockDim.x)
+      reinterpret_cast<uint4*>(drow)[i] = reinterpret_cast<const uint4*>(srow)[i];
+  } else {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < w; i += gridDim.x * blockDim.x) drow[i] = srow[i];
+  }
+}
+
 }  // namespace
+
+int flv_launch_unpack(flv_ctx* ctx, int slot, int n_streams, const uint8_t* d_src, size_t row_stride,
+                      size_t img_stride) {
+  const LevelGeom& L0 = ctx->geom.lv[0];
+  const bool vec = (ctx->w % 16 == 0) && (row_stride % 16 == 0) && (img_stride % 16 == 0) &&
+                   (reinterpret_cast<size_t>(d_src) % 16 == 0);
+  dim3 block(64, 4);
+  dim3 grid(1, (ctx->h + 3) / 4, n_streams);
+  uint8_t* dst = ctx->pyr[slot] + L0.off;
+  if (vec)
+    unpack_images_kernel<true><<<grid, block, 0, ctx->stream>>>(d_src, row_stride, img_stride, dst,
+                                                                 ctx->geom.stream_stride, L0.pitch, ctx->w, ctx->h);
+  else
+    unpack_images_kernel<false><<<grid, block, 0, ctx->stream>>>(d_src, row_stride, img_stride, dst,
+                                                                  ctx->geom.stream_stride, L0.pitch, ctx->w, ctx->h);
+  ctx->launches++;
+  FLV_CUDA(ctx, cudaGetLastError());
+  return FLV_OK;
+}
 
 int flv_launch_pyramid(flv_ctx* ctx, int slot, int n_streams) {
   const PyrGeom& g = ctx->geom;

@@ -1,0 +1,146 @@
+#include "local_map.h"
+#include <algorithm>
+
+namespace flv {
+
+LocalMap::LocalMap(flv_ctx* ctx, int window_size, double fx, double fy, double cx, double cy)
+    : ctx_(ctx), W_(window_size), fx_(fx), fy_(fy), cx_(cx), cy_(cy), bag(window_size) {
+  reset();
+}
+
+void LocalMap::reset() {                         // KFMSG_CMD_RESET_LM branch, vo_localmap.cpp:89-98
+  optimizer_state = UN_INITIALIZED;
+  bag.reset();
+  kfs.clear();
+  pose_est.assign(W_, Pose7{0, 0, 0, 1, 0, 0, 0});
+  pose_present.assign(W_, 0);
+  fixed_slot = -1;
+  lm_est.clear();
+  edges.clear();
+}
+
+void LocalMap::remove_pose_vertex(int slot) {    // g2o removeVertex deletes the incident edges (hyper_graph.cpp:214-220)
+  pose_present[slot] = 0;
+  if (fixed_slot == slot) fixed_slot = -1;
+  edges.erase(std::remove_if(edges.begin(), edges.end(), [slot](const Edge& e) { return e.pose_slot == slot; }),
+              edges.end());
+}
+
+void LocalMap::remove_lm_vertex(int64_t id) {
+  lm_est.erase(id);
+  edges.erase(std::remove_if(edges.begin(), edges.end(), [id](const Edge& e) { return e.lm_id == id; }), edges.end());
+}
+
+bool LocalMap::frame_callback(const KeyFrameStruct& kf, CorrectionInfStruct& out) {
+  kfs.push_back(kf);
+  bool solved = false;
+  switch (optimizer_state) {
+    case OPTIMIZING: break;
+    case UN_INITIALIZED:
+      if ((int)kfs.size() >= W_) {                                     // vo_localmap.cpp:125-209
+        for (int f = 0; f < W_; ++f) {
+          bag.addPose(kfs[f].frame_id, kfs[f].T_c_w);
+          for (int i = 0; i < kfs[f].lm_count; ++i) bag.addLMObservation(kfs[f].lm_id[i], kfs[f].lm_3d[i]);
+        }
+        const int oldest = bag.getOldestPoseInOptimizerIdx();
+        std::vector<POSE_ITEM> poses; bag.getAllPoses(poses);
+        for (const POSE_ITEM& it : poses) {
+          pose_est[it.pose_id] = g2o_pose_from_quat(it.pose);
+          pose_present[it.pose_id] = 1;
+          if (it.pose_id == oldest) fixed_slot = (int)it.pose_id;
+        }
+        std::vector<LM_ITEM> lms; bag.getAllLMs(lms);
+        for (const LM_ITEM& it : lms) lm_est[it.id] = it.p3d_w;
+        edges.clear();
+        for (int f = 0; f < W_; ++f) {
+          const int slot = (int)bag.getPoseIdByReleventFrameId(kfs[f].frame_id);
+          for (int i = 0; i < kfs[f].lm_count; ++i) edges.push_back(Edge{kfs[f].lm_id[i], slot, kfs[f].lm_2d[i]});
+        }
+        optimizer_state = OPTIMIZING;
+      } else {
+        return false;                                                  // :211-214 (no pop_front)
+      }
+      break;
+    case SLIDING_WINDOW: {                                             // :218-284
+      remove_pose_vertex(bag.getOldestPoseInOptimizerIdx());
+      for (int64_t id : kfs.at(0).lm_id)                               // off-by-one keyframe on purpose (:226-232)
+        if (bag.removeLMObservation(id)) remove_lm_vertex(id);
+      bag.addPose(kfs.back().frame_id, kfs.back().T_c_w);
+      const int newest = bag.getNewestPoseInOptimizerIdx();
+      pose_est[newest] = g2o_pose_from_quat(kfs.back().T_c_w);
+      pose_present[newest] = 1;
+      fixed_slot = bag.getOldestPoseInOptimizerIdx();                  // :241
+      for (int i = 0; i < kfs.back().lm_count; ++i)
+        if (bag.addLMObservationSlidingWindow(kfs.back().lm_id[i], kfs.back().lm_3d[i]))
+          lm_est[kfs.back().lm_id[i]] = kfs.back().lm_3d[i];
+      for (int i = 0; i < kfs.back().lm_count; ++i) {
+        // g2o refuses an edge whose landmark vertex is missing (setVertex(nullptr) then addEdge fails)
+        if (lm_est.count(kfs.back().lm_id[i])) edges.push_back(Edge{kfs.back().lm_id[i], newest, kfs.back().lm_2d[i]});
+      }
+      optimizer_state = OPTIMIZING;
+    } break;
+    default: break;
+  }
+  if (optimizer_state == OPTIMIZING) {
+    solved = solve(out);
+    optimizer_state = SLIDING_WINDOW;
+  }
+  kfs.pop_front();                                                     // :379
+  return solved;
+}
+
+bool LocalMap::solve(CorrectionInfStruct& out) {                       // vo_localmap.cpp:292-366
+  // flatten: poses by slot id, landmarks by id (g2o orders vertices by id), edges in insertion order
+  const int P = W_;
+  std::vector<int64_t> ids; ids.reserve(lm_est.size());
+  std::vector<double> lms; lms.reserve(3 * lm_est.size());
+  for (const auto& kv : lm_est) { ids.push_back(kv.first); lms.insert(lms.end(), kv.second.begin(), kv.second.end()); }
+  const int L = (int)ids.size(), E = (int)edges.size();
+  std::vector<double> poses(7 * P), uv(2 * (size_t)E);
+  for (int p = 0; p < P; ++p) std::copy(pose_est[p].begin(), pose_est[p].end(), poses.begin() + 7 * p);
+  std::vector<int> ep(E), el(E);
+  std::vector<uint8_t> active(E, 1);
+  for (int e = 0; e < E; ++e) {
+    ep[e] = edges[e].pose_slot;
+    el[e] = (int)(std::lower_bound(ids.begin(), ids.end(), edges[e].lm_id) - ids.begin());
+    uv[2 * e] = edges[e].uv[0]; uv[2 * e + 1] = edges[e].uv[1];
+  }
+  if (P > reserved_P || L > reserved_L || E > reserved_E) {
+    reserved_P = std::max(P, reserved_P); reserved_L = std::max(L + L / 2 + 64, reserved_L);
+    reserved_E = std::max(E + E / 2 + 64, reserved_E);
+    if (flv_ba_reserve(ctx_, reserved_P, reserved_L, reserved_E) != FLV_OK) return false;
+  }
+  // the C ABI takes per-stream strides = the reserved sizes
+  std::vector<double> poses_s(7 * (size_t)reserved_P, 0.0), lms_s(3 * (size_t)reserved_L, 0.0), uv_s(2 * (size_t)reserved_E, 0.0);
+  std::vector<int> ep_s(reserved_E, 0), el_s(reserved_E, 0);
+  std::vector<uint8_t> act_s(reserved_E, 0);
+  std::copy(poses.begin(), poses.end(), poses_s.begin()); std::copy(lms.begin(), lms.end(), lms_s.begin());
+  std::copy(uv.begin(), uv.end(), uv_s.begin()); std::copy(ep.begin(), ep.end(), ep_s.begin());
+  std::copy(el.begin(), el.end(), el_s.begin()); std::copy(active.begin(), active.end(), act_s.begin());
+  flv_ba_problem pb{P, L, E, fixed_slot, 0, fx_, fy_, cx_, cy_};
+  flv_ba_params prm{12, 8, 1.0, 3.0, 0, 0};
+  if (flv_ba_optimize(ctx_, 1, &pb, &prm, poses_s.data(), lms_s.data(), ep_s.data(), el_s.data(), uv_s.data(),
+                      act_s.data(), &stats_, FLV_MEM_HOST) != FLV_OK)
+    return false;
+  // estimates persist in the graph
+  for (int p = 0; p < P; ++p) std::copy(poses_s.begin() + 7 * p, poses_s.begin() + 7 * p + 7, pose_est[p].begin());
+  for (int l = 0; l < L; ++l) lm_est[ids[l]] = Vec3{lms_s[3 * l], lms_s[3 * l + 1], lms_s[3 * l + 2]};
+  // culled edges leave the graph for good; the reference walks `edges` from the back (:303-316)
+  out = CorrectionInfStruct();
+  for (int e = E - 1; e >= 0; --e)
+    if (!act_s[e]) { out.lm_outlier_id.push_back(edges[e].lm_id); }
+  out.lm_outlier_count = (int)out.lm_outlier_id.size();
+  {
+    std::vector<Edge> kept; kept.reserve(E);
+    for (int e = 0; e < E; ++e) if (act_s[e]) kept.push_back(edges[e]);
+    edges.swap(kept);
+  }
+  out.frame_id = kfs.back().frame_id;
+  out.T_c_w = pose_est[bag.getNewestPoseInOptimizerIdx()];
+  std::vector<LM_ITEM> mv; bag.getMultiViewLMs(mv, 4);                 // :329-357
+  out.lm_count = (int)mv.size();
+  for (const LM_ITEM& lm : mv) { out.lm_id.push_back(lm.id); out.lm_3d.push_back(lm_est[lm.id]); }
+  return true;
+}
+
+}  // namespace flv

@@ -1,0 +1,31 @@
+/*
+ * C handles of the C++ host layer of flvis_b200 (flvis_b200/host/), for callers that cannot include the C++
+ * headers (the ctypes tests, other languages).  The C++ classes keep the reference's names and semantics:
+ *   flv::PoseLMBag  <- src/backend/include/poselmbag.h:24-63
+ *   flv::LocalMap   <- LocalMapNodeletClass::frame_callback, src/backend/vo_localmap.cpp:87-380
+ */
+#ifndef FLVIS_B200_HOST_H
+#define FLVIS_B200_HOST_H
+#include "flvis_b200.h"
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct flv_localmap flv_localmap;
+
+flv_localmap* flv_localmap_create(flv_ctx* ctx, int window_size, double fx, double fy, double cx, double cy);
+void flv_localmap_destroy(flv_localmap* lm);
+void flv_localmap_reset(flv_localmap* lm);      /* KFMSG_CMD_RESET_LM, vo_localmap.cpp:89-98 */
+/* One KeyFrame message (msg/KeyFrame.msg without the images): lm_2d[n][2] undistorted px, lm_3d[n][3] world,
+ * T_c_w = [qx qy qz qw tx ty tz].  Returns 1 when a solve ran and the CorrectionInf outputs were written
+ * (msg/CorrectionInf.msg), 0 when the window is still filling, <0 on error (buffers too small = FLV_ERR_OVERFLOW). */
+int flv_localmap_add_keyframe(flv_localmap* lm, int64_t frame_id, int n, const int64_t* lm_id, const double* lm_2d,
+                              const double* lm_3d, const double* T_c_w, int64_t* out_frame_id, double* out_T_c_w,
+                              int* out_lm_count, int64_t* out_lm_id, double* out_lm_3d, int lm_cap,
+                              int* out_outlier_count, int64_t* out_outlier_id, int outlier_cap,
+                              flv_ba_stats* out_stats);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
