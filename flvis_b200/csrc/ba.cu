@@ -198,7 +198,7 @@ __device__ __forceinline__ void mark(Sh& sh, int slot) {
 }
 
 struct Ws {   // per-stream global workspace views
-  double *pbk, *lbk, *W, *Bw, *g, *Hll, *bl, *Dinv, *xl;
+  double *pbk, *lbk, *W, *Y, *Bw, *g, *Hll, *bl, *Dinv, *xl;
   int *eidx; unsigned* lmask; int* plist; int* pairs; int pair_cap;
 };
 
@@ -415,10 +415,22 @@ __device__ void solve_system(const flv_ba_problem& pb, double lambda, double* S,
       double Di[6] = {c00 * id, c01 * id, c02 * id, (a * f - c * c) * id, (b * c - a * e) * id, (a * d - b * b) * id};
 #pragma unroll
       for (int i = 0; i < 6; ++i) ws.Dinv[6 * (size_t)l + i] = Di[i];
-      const double* bl = ws.bl + 3 * (size_t)l;
-      ws.xl[3 * (size_t)l + 0] = Di[0] * bl[0] + Di[1] * bl[1] + Di[2] * bl[2];     // db = Dinv * bl
-      ws.xl[3 * (size_t)l + 1] = Di[1] * bl[0] + Di[3] * bl[1] + Di[4] * bl[2];
-      ws.xl[3 * (size_t)l + 2] = Di[2] * bl[0] + Di[4] * bl[1] + Di[5] * bl[2];
+      // Y_e = W_e * Dinv for every edge of this landmark with a free pose (used by all pose pairs of the landmark)
+      unsigned m = ws.lmask[l];
+      while (m) {
+        const int p = __ffs(m) - 1; m &= m - 1;
+        if (sh.pidx[p] < 0) continue;
+        const size_t e = (size_t)ws.eidx[p * L + l];
+        const double* W = ws.W + 18 * e;
+        double* Y = ws.Y + 18 * e;
+#pragma unroll
+        for (int i = 0; i < 6; ++i) {
+          const double w0 = W[3 * i], w1 = W[3 * i + 1], w2 = W[3 * i + 2];
+          Y[3 * i] = w0 * Di[0] + w1 * Di[1] + w2 * Di[2];
+          Y[3 * i + 1] = w0 * Di[1] + w1 * Di[3] + w2 * Di[4];
+          Y[3 * i + 2] = w0 * Di[2] + w1 * Di[4] + w2 * Di[5];
+        }
+      }
     }
     __syncthreads();
   }
@@ -434,24 +446,22 @@ __device__ void solve_system(const flv_ba_problem& pb, double lambda, double* S,
       const int i0 = sh.pair_off[blk], i1 = sh.pair_off[blk + 1];
       for (int k = i0 + lane; k < i1; k += 32) {
         const int* it = ws.pairs + 3 * (size_t)k;
-        const double* Wa = ws.W + 18 * (size_t)it[0];
+        const double* Ya = ws.Y + 18 * (size_t)it[0];
         const double* Wb = ws.W + 18 * (size_t)it[1];
-        const int l = it[2];
-        const double* Di = ws.Dinv + 6 * (size_t)l;
-        const double d0 = Di[0], d1 = Di[1], d2 = Di[2], d3 = Di[3], d4 = Di[4], d5 = Di[5];
-        double wb[18];
+        double ya[18], wb[18];
 #pragma unroll
-        for (int i = 0; i < 18; ++i) wb[i] = Wb[i];
-        const double* db = ws.xl + 3 * (size_t)l;
-        const double db0 = db[0], db1 = db[1], db2 = db[2];
+        for (int i = 0; i < 18; ++i) { ya[i] = Ya[i]; wb[i] = Wb[i]; }
+        if (a == b) {
+          const double* bl = ws.bl + 3 * (size_t)it[2];
+          const double b0 = bl[0], b1 = bl[1], b2 = bl[2];
 #pragma unroll
-        for (int i = 0; i < 6; ++i) {
-          const double w0 = Wa[3 * i], w1 = Wa[3 * i + 1], w2 = Wa[3 * i + 2];
-          const double y0 = w0 * d0 + w1 * d1 + w2 * d2, y1 = w0 * d1 + w1 * d3 + w2 * d4, y2 = w0 * d2 + w1 * d4 + w2 * d5;
-#pragma unroll
-          for (int j = 0; j < 6; ++j) acc[6 * i + j] += y0 * wb[3 * j] + y1 * wb[3 * j + 1] + y2 * wb[3 * j + 2];
-          if (a == b) cf[i] += w0 * db0 + w1 * db1 + w2 * db2;
+          for (int i = 0; i < 6; ++i) cf[i] += ya[3 * i] * b0 + ya[3 * i + 1] * b1 + ya[3 * i + 2] * b2;
         }
+#pragma unroll
+        for (int i = 0; i < 6; ++i)
+#pragma unroll
+          for (int j = 0; j < 6; ++j)
+            acc[6 * i + j] += ya[3 * i] * wb[3 * j] + ya[3 * i + 1] * wb[3 * j + 1] + ya[3 * i + 2] * wb[3 * j + 2];
       }
     }
 #pragma unroll
@@ -504,11 +514,11 @@ __device__ void solve_system(const flv_ba_problem& pb, double lambda, double* S,
     __syncthreads();
     const double d = sh.piv;
     if (!(d > 0)) { if (tid == 0) sh.fail = 1; }
-    const double sd = sqrt(d > 0 ? d : 1.0);
+    const double isd = rsqrt(d > 0 ? d : 1.0);
     if (mine && t == 0) {
-      if (row == j) S[j * ld + j] = sd;
-      else if (row < n) S[row * ld + j] = sres / sd;
-      else y[j] = sres / sd;
+      if (row == j) S[j * ld + j] = d * isd;
+      else if (row < n) S[row * ld + j] = sres * isd;
+      else y[j] = sres * isd;
     }
     __syncthreads();
   }
@@ -597,6 +607,7 @@ __global__ void __launch_bounds__(BA_THREADS, 1) ba_kernel(BAArgs a) {
     ws.bl = d; d += 3 * a.max_lms;
     ws.Dinv = d; d += 6 * a.max_lms;
     ws.xl = d; d += 3 * a.max_lms;
+    ws.Y = d; d += 18 * (size_t)a.max_edges;
     ws.eidx = (int*)d;
     ws.lmask = (unsigned*)(ws.eidx + (size_t)a.max_poses * a.max_lms);
     ws.plist = (int*)(ws.lmask + a.max_lms);
@@ -698,7 +709,7 @@ __global__ void __launch_bounds__(BA_THREADS, 1) ba_kernel(BAArgs a) {
 }
 
 size_t ws_stride_bytes(int max_poses, int max_lms, int max_edges) {
-  size_t d = 7 * (size_t)max_poses + 3 * (size_t)max_lms + (18 + 12 + 2) * (size_t)max_edges + 6 * (size_t)max_lms +
+  size_t d = 7 * (size_t)max_poses + 3 * (size_t)max_lms + (18 + 18 + 12 + 2) * (size_t)max_edges + 6 * (size_t)max_lms +
              3 * (size_t)max_lms + 6 * (size_t)max_lms + 3 * (size_t)max_lms;
   size_t ints = (size_t)max_poses * max_lms + max_lms + max_edges + 3 * pair_capacity(max_poses, max_edges);
   size_t b = d * 8 + ints * 4;

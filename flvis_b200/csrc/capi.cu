@@ -71,7 +71,7 @@ int flv_create(flv_ctx** out, int device, int max_streams, int img_w, int img_h,
   }
   ctx->gftt_cap = 4096;
   ctx->cand_cap = 65536;
-  ctx->max_cells = 8192;
+  ctx->max_cells = 8191;   // cstart[max_cells+1] + ccount[max_cells] must fit the 64 KB half of the fast path's region A
   int rc = 0;
   rc |= dev_alloc(ctx, &ctx->d_npts, S);
   rc |= dev_alloc(ctx, &ctx->d_eig, S * img_w * img_h);

@@ -149,7 +149,7 @@ corner_response_kernel(const uint8_t* __restrict__ img_base, size_t stream_strid
 
 // ------------------------------------------------------------------------------------------------
 constexpr int MD_THREADS = 1024;
-constexpr int SEL_CAP = 8192;    // candidates handled by the shared-memory fast path
+constexpr int SEL_CAP = 16384;   // candidates handled by the shared-memory fast path
 constexpr int HBINS = 4096;      // histogram over float bits [30:19]
 
 __device__ __forceinline__ int block_exclusive_scan(int v, int* warp_sums, int* total) {
@@ -180,8 +180,8 @@ __device__ __forceinline__ int block_exclusive_scan(int v, int* warp_sums, int* 
 
 // Greedy min-distance selection over `n` keys sorted in DESCENDING priority order (index == rank).
 // keys: shared or global; cstart/ccount: ints [ncell+1]/[ncell]; items: ranks grouped by cell; state: u8[n].
-template <typename ItemT>
-__device__ void greedy_fixed_point(const unsigned long long* keys, int n, int cell, int gw, int gh, double d2,
+template <typename KeyT, typename ItemT>
+__device__ void greedy_fixed_point(const KeyT* keys, int n, int cell, int gw, int gh, double d2,
                                    int* cstart, int* ccount, ItemT* items, unsigned char* state, int* warp_sums,
                                    int* sh_total) {
   const int tid = threadIdx.x;
@@ -260,7 +260,8 @@ __device__ void bitonic_desc(unsigned long long* a, int np2) {
 }
 
 // write the first `max_corners` accepted keys (rank order) as corners; returns count via ncorners
-__device__ void emit_accepted(const unsigned long long* keys, const unsigned char* state, int n, bool all,
+template <typename KeyT>
+__device__ void emit_accepted(const KeyT* keys, const unsigned char* state, int n, bool all,
                               int max_corners, float* corners, int corner_stride, int* ncorners_s, int* warp_sums,
                               int* sh_total) {
   const int tid = threadIdx.x;
@@ -289,13 +290,17 @@ mindist_fast_kernel(const unsigned long long* __restrict__ cand_base, const int*
                     int max_corners, float* __restrict__ corners_base, int* __restrict__ ncorners,
                     int corner_stride, int* __restrict__ flags, int* __restrict__ need_full, int max_cells) {
   extern __shared__ unsigned char smem_raw[];
-  // layout: keys [SEL_CAP] u64 | cstart [max_cells+1] | ccount/hist [max(max_cells,HBINS)] | items u16 [SEL_CAP] | state [SEL_CAP]
+  // region A [0,128K): u64 keys[SEL_CAP] while selecting + sorting; afterwards pos u32[SEL_CAP] (low halves, rank order)
+  //                    in its first half and cstart / ccount in its second half.
+  // region B [128K, 176K): hist int[HBINS] while selecting; afterwards items u16[SEL_CAP] | state u8[SEL_CAP].
   unsigned long long* keys = (unsigned long long*)smem_raw;
-  int* cstart = (int*)(keys + SEL_CAP);
+  unsigned* pos = (unsigned*)smem_raw;
+  int* cstart = (int*)(smem_raw + (size_t)SEL_CAP * 4);
   int* ccount = cstart + (max_cells + 1);
-  const int cc_len = max_cells > HBINS ? max_cells : HBINS;
-  unsigned short* items = (unsigned short*)(ccount + cc_len);
-  unsigned char* state = (unsigned char*)(items + SEL_CAP);
+  unsigned char* regB = smem_raw + (size_t)SEL_CAP * 8;
+  int* hist = (int*)regB;
+  unsigned short* items = (unsigned short*)regB;
+  unsigned char* state = regB + (size_t)SEL_CAP * 2;
   __shared__ int warp_sums[32];
   __shared__ int sh_total, sh_nsel, sh_cut, sh_npass;
 
@@ -307,7 +312,6 @@ mindist_fast_kernel(const unsigned long long* __restrict__ cand_base, const int*
   const float thr = (float)((double)__int_as_float(eigmax[s]) * quality);
   if (tid == 0) { need_full[s] = 0; sh_nsel = 0; sh_npass = 0; }
   // 1. histogram of the candidates that pass the quality threshold
-  int* hist = ccount;
   for (int i = tid; i < HBINS; i += MD_THREADS) hist[i] = 0;
   __syncthreads();
   for (int i = tid; i < n; i += MD_THREADS) {
@@ -357,14 +361,24 @@ mindist_fast_kernel(const unsigned long long* __restrict__ cand_base, const int*
   __syncthreads();
   bitonic_desc(keys, np2);
   const bool complete = nsel == npass;
+  {   // compact the sorted keys to their 32-bit positions in place (registers in between: the arrays alias)
+    constexpr int PER = SEL_CAP / MD_THREADS;
+    unsigned lo[PER];
+#pragma unroll
+    for (int k = 0; k < PER; ++k) { const int i = tid + k * MD_THREADS; lo[k] = i < nsel ? (unsigned)keys[i] : 0u; }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < PER; ++k) { const int i = tid + k * MD_THREADS; if (i < nsel) pos[i] = lo[k]; }
+    __syncthreads();
+  }
   if (min_distance >= 1.0) {
     const int cell = (int)rint(min_distance);
     const int gw = (w + cell - 1) / cell, gh = (h + cell - 1) / cell;
-    greedy_fixed_point<unsigned short>(keys, nsel, cell, gw, gh, min_distance * min_distance, cstart, ccount, items,
-                                       state, warp_sums, &sh_total);
-    emit_accepted(keys, state, nsel, false, max_corners, corners, corner_stride, &ncorners[s], warp_sums, &sh_total);
+    greedy_fixed_point<unsigned, unsigned short>(pos, nsel, cell, gw, gh, min_distance * min_distance, cstart, ccount,
+                                                 items, state, warp_sums, &sh_total);
+    emit_accepted<unsigned>(pos, state, nsel, false, max_corners, corners, corner_stride, &ncorners[s], warp_sums, &sh_total);
   } else {
-    emit_accepted(keys, state, nsel, true, max_corners, corners, corner_stride, &ncorners[s], warp_sums, &sh_total);
+    emit_accepted<unsigned>(pos, state, nsel, true, max_corners, corners, corner_stride, &ncorners[s], warp_sums, &sh_total);
   }
   __syncthreads();
   if (tid == 0 && !complete && sh_total < max_corners) need_full[s] = 1;   // prefix too short: slow path decides
@@ -409,11 +423,11 @@ mindist_full_kernel(const unsigned long long* __restrict__ cand_base, const int*
   if (min_distance >= 1.0) {
     const int cell = (int)rint(min_distance);
     const int gw = (w + cell - 1) / cell, gh = (h + cell - 1) / cell;
-    greedy_fixed_point<int>(keys, m, cell, gw, gh, min_distance * min_distance, cstart, ccount, items, state,
+    greedy_fixed_point<unsigned long long, int>(keys, m, cell, gw, gh, min_distance * min_distance, cstart, ccount, items, state,
                             warp_sums, &sh_total);
-    emit_accepted(keys, state, m, false, max_corners, corners, corner_stride, &ncorners[s], warp_sums, &sh_total);
+    emit_accepted<unsigned long long>(keys, state, m, false, max_corners, corners, corner_stride, &ncorners[s], warp_sums, &sh_total);
   } else {
-    emit_accepted(keys, state, m, true, max_corners, corners, corner_stride, &ncorners[s], warp_sums, &sh_total);
+    emit_accepted<unsigned long long>(keys, state, m, true, max_corners, corners, corner_stride, &ncorners[s], warp_sums, &sh_total);
   }
 }
 
@@ -423,8 +437,8 @@ __global__ void gftt_reset_kernel(int* eigmax, int* ncand, int n) {
 }
 
 size_t fast_smem(int max_cells) {
-  const int cc_len = max_cells > HBINS ? max_cells : HBINS;
-  return (size_t)SEL_CAP * 8 + (size_t)(max_cells + 1 + cc_len) * 4 + (size_t)SEL_CAP * 2 + SEL_CAP;
+  (void)max_cells;                       // cstart/ccount live inside region A: needs 2*max_cells+1 ints <= SEL_CAP ints
+  return (size_t)SEL_CAP * 8 + (size_t)SEL_CAP * 2 + SEL_CAP;
 }
 size_t full_smem(int max_cells) { return (size_t)(2 * max_cells + 1) * 4; }
 

@@ -262,6 +262,10 @@ int flv_launch_lk_v1(flv_ctx* ctx, int src_slot, int dst_slot, int n_streams, co
                      const float* d_prev, const float* d_init, float* d_next, uint8_t* d_status,
                      float* d_err, int nlev_used, int max_iter, double eps2, double min_eig_thr);
 
+int flv_launch_lk_v3(flv_ctx* ctx, int src_slot, int dst_slot, int n_streams, const int* d_npts,
+                     const float* d_prev, const float* d_init, float* d_next, uint8_t* d_status,
+                     float* d_err, int nlev_used, int max_iter, double eps2, double min_eig_thr);
+
 int flv_launch_lk(flv_ctx* ctx, int src_slot, int dst_slot, int n_streams, const int* d_npts,
                   const float* d_prev, const float* d_init, float* d_next, uint8_t* d_status,
                   float* d_err, int nlev_used, int max_iter, double eps2, double min_eig_thr) {
@@ -276,7 +280,10 @@ int flv_launch_lk(flv_ctx* ctx, int src_slot, int dst_slot, int n_streams, const
   dim3 grid((ctx->max_pts + WARPS - 1) / WARPS, n_streams);
   const float err_scale = (float)(1.0 / (32 * WIN * WIN));
   // two register budgets of the same kernel: 168 regs / 12 warps per SM (no spills) or 128 regs / 16 warps per SM
-  static const int variant = getenv("FLV_LK_VARIANT") ? atoi(getenv("FLV_LK_VARIANT")) : 3;
+  const int variant = getenv("FLV_LK_VARIANT") ? atoi(getenv("FLV_LK_VARIANT")) : 1;
+  if (variant == 5)
+    return flv_launch_lk_v3(ctx, src_slot, dst_slot, n_streams, d_npts, d_prev, d_init, d_next, d_status, d_err, nlev_used,
+                            max_iter, eps2, min_eig_thr);
   if (variant == 1)
     return flv_launch_lk_v1(ctx, src_slot, dst_slot, n_streams, d_npts, d_prev, d_init, d_next, d_status, d_err, nlev_used,
                             max_iter, eps2, min_eig_thr);

@@ -25,6 +25,22 @@ int flv_localmap_add_keyframe(flv_localmap* lm, int64_t frame_id, int n, const i
                               int* out_outlier_count, int64_t* out_outlier_id, int outlier_cap,
                               flv_ba_stats* out_stats);
 
+/* ---- flv::VIMOTION <- src/processing/include/vi_motion.h, src/processing/vi_motion.cpp:3-464 -------------------
+ * Poses are [qx qy qz qw tx ty tz]; orientation outputs are Eigen order [qw qx qy qz] like the reference's
+ * Quaterniond.  flv_vimotion_imu_feed = F2FTracking::imu_feed (src/frontend/f2f_tracking.cpp:46-57). */
+typedef struct flv_vimotion flv_vimotion;
+flv_vimotion* flv_vimotion_create(const double* T_i_c, double magnitude_g, double para1, double para2, double para3,
+                                  double para4, double para5, double para6);
+void flv_vimotion_destroy(flv_vimotion* vm);
+int flv_vimotion_imu_feed(flv_vimotion* vm, double t, const double* acc, const double* gyro, double* q_wxyz,
+                          double* pos, double* vel);                      /* returns 1 once imu_initialized */
+int flv_vimotion_vision_trigger(flv_vimotion* vm, double* q_wxyz);
+int flv_vimotion_correction(flv_vimotion* vm, double t_curr, const double* Tcw_curr, double t_last, const double* Tcw_last);
+int flv_vimotion_corr_frame_state(flv_vimotion* vm, double t, double* T_c_w);     /* 1 found, 0 not in queue */
+int flv_vimotion_rp_compensation(flv_vimotion* vm, double t, double* T_c_w_inout);
+int flv_vimotion_get_bias(flv_vimotion* vm, double* acc_bias, double* gyro_bias);
+int flv_vimotion_queue_size(flv_vimotion* vm);
+
 #ifdef __cplusplus
 }
 #endif

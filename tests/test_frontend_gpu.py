@@ -50,6 +50,23 @@ def test_lk_bit_exact_vs_oracle_and_golden(name):
     ctx.close()
 
 
+@pytest.mark.parametrize("variant", ["1", "3", "4", "5"])
+def test_lk_kernel_variants_bit_exact(variant, monkeypatch):
+    """All register-budget / shared-memory variants of the tracker obey the same arithmetic contract."""
+    monkeypatch.setenv("FLV_LK_VARIANT", variant)
+    g, I, J = cases.load_lk("euroc_rot")
+    h, w = I.shape
+    ctx = _ctx(1, w, h)
+    ctx.upload(0, I); ctx.upload(1, J)
+    ctx.build_pyramid(0, 1); ctx.build_pyramid(1, 1)
+    nxt, st, err = ctx.lk_track(0, 1, g["pts"], g["init"], max_level=int(g["max_level"]))
+    o_nxt, o_st, o_err = lk_ref.calc_optical_flow_pyr_lk(I, J, g["pts"], g["init"], max_level=int(g["max_level"]))
+    assert np.array_equal(st, o_st)
+    assert np.array_equal(nxt.view(np.uint32), o_nxt.view(np.uint32))
+    assert np.array_equal(err.view(np.uint32), o_err.view(np.uint32))
+    ctx.close()
+
+
 def test_lk_batched_streams_ragged_and_empty():
     names = cases.lk_cases()
     e = [n for n in names if n.startswith("euroc")]
