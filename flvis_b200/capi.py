@@ -18,7 +18,7 @@ SYMBOLS = [
     "flv_launch_count", "flv_level_info", "flv_num_levels", "flv_upload_images", "flv_build_pyramid",
     "flv_download_level", "flv_lk_track", "flv_select_tracked", "flv_gftt", "flv_download_eig", "flv_gftt_capacity",
     "flv_feature_detect", "flv_feature_redetect", "flv_ba_reserve", "flv_ba_optimize", "flv_gftt_keep_response",
-    "flv_ba_profile", "flv_set_ba_stream",
+    "flv_ba_profile", "flv_set_ba_stream", "flv_depth_innovation", "flv_reprojection_inliers",
 ]
 
 
@@ -31,6 +31,15 @@ class FeatureParams(C.Structure):
     _fields_ = [("max_region_feature_num", C.c_int), ("min_region_feature_num", C.c_int),
                 ("boundary_dis", C.c_int), ("gftt_num", C.c_int), ("gftt_ql", C.c_double),
                 ("gftt_dis", C.c_int)]
+
+
+class Camera(C.Structure):
+    _fields_ = [("fx", C.c_double), ("fy", C.c_double), ("cx", C.c_double), ("cy", C.c_double),
+                ("P0", C.c_double * 12), ("P1", C.c_double * 12), ("cam_type", C.c_int), ("depth_scale", C.c_double)]
+
+
+class DepthParams(C.Structure):
+    _fields_ = [("iir_ratio", C.c_float), ("range", C.c_float), ("dummy_depth", C.c_int)]
 
 
 class BAProblem(C.Structure):
@@ -84,6 +93,8 @@ def load_library(path=LIB_PATH):
     lib.flv_download_eig.argtypes = [vp, C.c_int, vp, C.c_int]
     lib.flv_feature_detect.argtypes = [vp, C.c_int, C.c_int, C.POINTER(FeatureParams), vp, vp, C.c_int]
     lib.flv_feature_redetect.argtypes = [vp, C.c_int, C.c_int, C.POINTER(FeatureParams), vp, vp, vp, vp, C.c_int]
+    lib.flv_depth_innovation.argtypes = [vp, C.c_int, vp, C.POINTER(Camera), C.POINTER(DepthParams)] + [vp] * 13 + [C.c_int]
+    lib.flv_reprojection_inliers.argtypes = [vp, C.c_int, vp, C.POINTER(Camera), vp, vp, vp, C.c_double, vp, vp, C.c_int]
     lib.flv_ba_reserve.argtypes = [vp, C.c_int, C.c_int, C.c_int]
     lib.flv_ba_optimize.argtypes = [vp, C.c_int, C.POINTER(BAProblem), C.POINTER(BAParams), vp, vp, vp, vp, vp,
                                     vp, C.POINTER(BAStats), C.c_int]

@@ -444,8 +444,14 @@ __device__ void solve_system(const flv_ba_problem& pb, double lambda, double* S,
     for (int i = 0; i < 6; ++i) cf[i] = 0;
     if (!pb.fix_landmarks) {
       const int i0 = sh.pair_off[blk], i1 = sh.pair_off[blk + 1];
-      for (int k = i0 + lane; k < i1; k += 32) {
-        const int* it = ws.pairs + 3 * (size_t)k;
+      // the (ea, eb, l) triple of the NEXT member is fetched while this one is processed: one dependent L2 round
+      // trip per member instead of two (the pass is latency-bound: ~20 B/clk of L2 traffic on 16 warps)
+      int k = i0 + lane;
+      int n0 = 0, n1 = 0, n2 = 0;
+      if (k < i1) { const int* it = ws.pairs + 3 * (size_t)k; n0 = it[0]; n1 = it[1]; n2 = it[2]; }
+      for (; k < i1; k += 32) {
+        const int it[3] = {n0, n1, n2};
+        if (k + 32 < i1) { const int* nx = ws.pairs + 3 * (size_t)(k + 32); n0 = nx[0]; n1 = nx[1]; n2 = nx[2]; }
         const double* Ya = ws.Y + 18 * (size_t)it[0];
         const double* Wb = ws.W + 18 * (size_t)it[1];
         double ya[18], wb[18];

@@ -61,9 +61,11 @@ corner_response_kernel(const uint8_t* __restrict__ img_base, size_t stream_strid
   float* eig_s = eig_out ? eig_out + (size_t)s * w * h : nullptr;
   unsigned long long* cand = cand_base + (size_t)s * cand_cap;
 
-  auto load_row = [&](int r) -> Row3 {
+  auto load_raw = [&](int r) -> int {
     const int yy = clampi(reflect101(r, h), 0, h - 1);
-    const int c = img[(size_t)yy * pitch + xl];
+    return img[(size_t)yy * pitch + xl];
+  };
+  auto make_row = [&](int c) -> Row3 {
     const int up = __shfl_down_sync(FULL, c, 1), dn = __shfl_up_sync(FULL, c, 1);
     Row3 o;
     o.c = c;
@@ -72,12 +74,15 @@ corner_response_kernel(const uint8_t* __restrict__ img_base, size_t stream_strid
     return o;
   };
 
-  Row3 Ia, Ib = load_row(y0 - 3), Ic = load_row(y0 - 2);
+  // software prefetch: the row consumed at step r was requested 4 steps earlier (ncu: 52 % long-scoreboard without it)
+  Row3 Ia, Ib = make_row(load_raw(y0 - 3)), Ic = make_row(load_raw(y0 - 2));
+  int pf0 = load_raw(y0 - 1), pf1 = load_raw(y0), pf2 = load_raw(y0 + 1), pf3 = load_raw(y0 + 2);
   double Rm[3] = {0, 0, 0}, R0[3] = {0, 0, 0}, Rp[3] = {0, 0, 0};
   float Ea = 0.f, Eb = 0.f, m3a = 0.f, m3b = 0.f, nb = 0.f;   // eig rows y-2 (a), y-1 (b); nb = max(left,right) of row b
   float best = 0.f;
   for (int r = y0 - 2; r <= y0 + CS_ROWS + 1; ++r) {
-    Ia = Ib; Ib = Ic; Ic = load_row(r + 1);
+    Ia = Ib; Ib = Ic; Ic = make_row(pf0);
+    pf0 = pf1; pf1 = pf2; pf2 = pf3; pf3 = load_raw(r + 5);
     // covariance of row r at this lane's column (only inside the image)
     float vxx = 0.f, vxy = 0.f, vyy = 0.f;
     if (r >= 0 && r < h && in_x) {
@@ -292,13 +297,13 @@ mindist_fast_kernel(const unsigned long long* __restrict__ cand_base, const int*
   extern __shared__ unsigned char smem_raw[];
   // region A [0,128K): u64 keys[SEL_CAP] while selecting + sorting; afterwards pos u32[SEL_CAP] (low halves, rank order)
   //                    in its first half and cstart / ccount in its second half.
-  // region B [128K, 176K): hist int[HBINS] while selecting; afterwards items u16[SEL_CAP] | state u8[SEL_CAP].
+  // region B [128K, 176K): items u16[SEL_CAP] | state u8[SEL_CAP];  then hist int[HBINS].
   unsigned long long* keys = (unsigned long long*)smem_raw;
   unsigned* pos = (unsigned*)smem_raw;
   int* cstart = (int*)(smem_raw + (size_t)SEL_CAP * 4);
   int* ccount = cstart + (max_cells + 1);
   unsigned char* regB = smem_raw + (size_t)SEL_CAP * 8;
-  int* hist = (int*)regB;
+  int* hist = (int*)(regB + (size_t)SEL_CAP * 3);          // own 16 KB: survives the retries
   unsigned short* items = (unsigned short*)regB;
   unsigned char* state = regB + (size_t)SEL_CAP * 2;
   __shared__ int warp_sums[32];
@@ -319,69 +324,82 @@ mindist_fast_kernel(const unsigned long long* __restrict__ cand_base, const int*
     if (__uint_as_float(vb) > thr) atomicAdd(&hist[(vb >> 19) & (HBINS - 1)], 1);
   }
   __syncthreads();
-  // 2. lowest bin `cut` such that everything in bins >= cut fits the fast path (suffix sums by one warp)
-  if (tid < 32) {
-    int run = 0, cut = HBINS, npass = 0;
-    for (int b0 = HBINS - 32; b0 >= 0; b0 -= 32) {
-      const int v = hist[b0 + tid];
-      int suf = v;                                        // inclusive suffix sum within the 32-bin chunk
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        const int t = __shfl_down_sync(FULL, suf, o);
-        if (tid + o < 32) suf += t;
+  // Adaptive prefix: the greedy result only depends on stronger corners, so the strongest `cap` candidates decide the
+  // first accepted corners exactly; start with 4*N and double while fewer than N corners come out.
+  int cap = 4 * max_corners < 2048 ? 2048 : 4 * max_corners;
+  if (cap > SEL_CAP) cap = SEL_CAP;
+  bool decided = false;
+  for (;;) {
+    // 2. lowest bin `cut` such that everything in bins >= cut fits the fast path (suffix sums by one warp)
+    if (tid < 32) {
+      int run = 0, cut = HBINS, npass = 0;
+      for (int b0 = HBINS - 32; b0 >= 0; b0 -= 32) {
+        const int v = hist[b0 + tid];
+        int suf = v;                                        // inclusive suffix sum within the 32-bin chunk
+  #pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const int t = __shfl_down_sync(FULL, suf, o);
+          if (tid + o < 32) suf += t;
+        }
+        const bool fits = run + suf <= cap;
+        const unsigned fm = __ballot_sync(FULL, fits);
+        if (cut == b0 + 32) {                               // still contiguous from the top
+          // lanes that fit form a suffix of the chunk (suffix sums are monotone)
+          const int nfit = __popc(fm);
+          if (nfit > 0) cut = b0 + 32 - nfit;
+        }
+        run += __shfl_sync(FULL, suf, 0);
+        npass = run;
       }
-      const bool fits = run + suf <= SEL_CAP;
-      const unsigned fm = __ballot_sync(FULL, fits);
-      if (cut == b0 + 32) {                               // still contiguous from the top
-        // lanes that fit form a suffix of the chunk (suffix sums are monotone)
-        const int nfit = __popc(fm);
-        if (nfit > 0) cut = b0 + 32 - nfit;
+      if (tid == 0) { sh_cut = cut; sh_npass = npass; }
+    }
+    __syncthreads();
+    const int cut = sh_cut, npass = sh_npass;
+    if (tid == 0) sh_nsel = 0;
+    __syncthreads();
+    // 3. gather the selected prefix into shared memory
+    for (int i = tid; i < n; i += MD_THREADS) {
+      const unsigned long long k = cand[i];
+      const unsigned vb = (unsigned)(k >> 32);
+      if (__uint_as_float(vb) > thr && (int)((vb >> 19) & (HBINS - 1)) >= cut) {
+        const int p = atomicAdd(&sh_nsel, 1);
+        if (p < SEL_CAP) keys[p] = k;
       }
-      run += __shfl_sync(FULL, suf, 0);
-      npass = run;
     }
-    if (tid == 0) { sh_cut = cut; sh_npass = npass; }
-  }
-  __syncthreads();
-  const int cut = sh_cut, npass = sh_npass;
-  // 3. gather the selected prefix into shared memory
-  for (int i = tid; i < n; i += MD_THREADS) {
-    const unsigned long long k = cand[i];
-    const unsigned vb = (unsigned)(k >> 32);
-    if (__uint_as_float(vb) > thr && (int)((vb >> 19) & (HBINS - 1)) >= cut) {
-      const int p = atomicAdd(&sh_nsel, 1);
-      if (p < SEL_CAP) keys[p] = k;
+    __syncthreads();
+    const int nsel = sh_nsel < SEL_CAP ? sh_nsel : SEL_CAP;
+    int np2 = 1;
+    while (np2 < nsel) np2 <<= 1;
+    for (int i = nsel + tid; i < np2; i += MD_THREADS) keys[i] = 0ull;
+    __syncthreads();
+    bitonic_desc(keys, np2);
+    const bool complete = nsel == npass;
+    {   // compact the sorted keys to their 32-bit positions in place (registers in between: the arrays alias)
+      constexpr int PER = SEL_CAP / MD_THREADS;
+      unsigned lo[PER];
+  #pragma unroll
+      for (int k = 0; k < PER; ++k) { const int i = tid + k * MD_THREADS; lo[k] = i < nsel ? (unsigned)keys[i] : 0u; }
+      __syncthreads();
+  #pragma unroll
+      for (int k = 0; k < PER; ++k) { const int i = tid + k * MD_THREADS; if (i < nsel) pos[i] = lo[k]; }
+      __syncthreads();
     }
-  }
-  __syncthreads();
-  const int nsel = sh_nsel < SEL_CAP ? sh_nsel : SEL_CAP;
-  int np2 = 1;
-  while (np2 < nsel) np2 <<= 1;
-  for (int i = nsel + tid; i < np2; i += MD_THREADS) keys[i] = 0ull;
-  __syncthreads();
-  bitonic_desc(keys, np2);
-  const bool complete = nsel == npass;
-  {   // compact the sorted keys to their 32-bit positions in place (registers in between: the arrays alias)
-    constexpr int PER = SEL_CAP / MD_THREADS;
-    unsigned lo[PER];
-#pragma unroll
-    for (int k = 0; k < PER; ++k) { const int i = tid + k * MD_THREADS; lo[k] = i < nsel ? (unsigned)keys[i] : 0u; }
+    if (min_distance >= 1.0) {
+      const int cell = (int)rint(min_distance);
+      const int gw = (w + cell - 1) / cell, gh = (h + cell - 1) / cell;
+      greedy_fixed_point<unsigned, unsigned short>(pos, nsel, cell, gw, gh, min_distance * min_distance, cstart, ccount,
+                                                   items, state, warp_sums, &sh_total);
+      emit_accepted<unsigned>(pos, state, nsel, false, max_corners, corners, corner_stride, &ncorners[s], warp_sums, &sh_total);
+    } else {
+      emit_accepted<unsigned>(pos, state, nsel, true, max_corners, corners, corner_stride, &ncorners[s], warp_sums, &sh_total);
+    }
     __syncthreads();
-#pragma unroll
-    for (int k = 0; k < PER; ++k) { const int i = tid + k * MD_THREADS; if (i < nsel) pos[i] = lo[k]; }
+    decided = complete || sh_total >= max_corners || min_distance < 1.0;
+    if (decided || cap >= SEL_CAP) break;
+    cap = cap * 2 > SEL_CAP ? SEL_CAP : cap * 2;
     __syncthreads();
   }
-  if (min_distance >= 1.0) {
-    const int cell = (int)rint(min_distance);
-    const int gw = (w + cell - 1) / cell, gh = (h + cell - 1) / cell;
-    greedy_fixed_point<unsigned, unsigned short>(pos, nsel, cell, gw, gh, min_distance * min_distance, cstart, ccount,
-                                                 items, state, warp_sums, &sh_total);
-    emit_accepted<unsigned>(pos, state, nsel, false, max_corners, corners, corner_stride, &ncorners[s], warp_sums, &sh_total);
-  } else {
-    emit_accepted<unsigned>(pos, state, nsel, true, max_corners, corners, corner_stride, &ncorners[s], warp_sums, &sh_total);
-  }
-  __syncthreads();
-  if (tid == 0 && !complete && sh_total < max_corners) need_full[s] = 1;   // prefix too short: slow path decides
+  if (tid == 0 && !decided) need_full[s] = 1;   // prefix too short: slow path decides
 }
 
 // slow path: all passing candidates, keys sorted in global memory by a shared-memory-free odd route:
@@ -438,7 +456,7 @@ __global__ void gftt_reset_kernel(int* eigmax, int* ncand, int n) {
 
 size_t fast_smem(int max_cells) {
   (void)max_cells;                       // cstart/ccount live inside region A: needs 2*max_cells+1 ints <= SEL_CAP ints
-  return (size_t)SEL_CAP * 8 + (size_t)SEL_CAP * 2 + SEL_CAP;
+  return (size_t)SEL_CAP * 8 + (size_t)SEL_CAP * 2 + SEL_CAP + (size_t)HBINS * 4;
 }
 size_t full_smem(int max_cells) { return (size_t)(2 * max_cells + 1) * 4; }
 

@@ -56,25 +56,46 @@ __device__ __forceinline__ void window_pass(const uint8_t* __restrict__ J, int p
                                             int lane, int w00, int w01, int w10, int w11,
                                             const int2* __restrict__ tmpl, bool live, int& o1, int& o2) {
   const bool interior = inx >= 0 && inx + WIN < w && iny >= 0 && iny + WIN < h;
-  const int xj = interior ? inx + lane : reflect101(inx + lane, w);
-  const uint8_t* col = J + xj;
-  int q = col[(size_t)(interior ? iny : reflect101(iny, h)) * pitch];
-  int qr = __shfl_down_sync(FULL, q, 1);
+  // two ROLLED loops (small code either way): the interior one walks a pointer, the border one reflects indices
+  if (interior) {
+    const uint8_t* p = J + (size_t)iny * pitch + inx + lane;
+    int q = p[0];
+    int qr = __shfl_down_sync(FULL, q, 1);
 #pragma unroll 4
-  for (int r = 1; r <= WIN; ++r) {
-    const int yy = interior ? iny + r : reflect101(iny + r, h);
-    const int v = col[(size_t)yy * pitch];
-    const int vr = __shfl_down_sync(FULL, v, 1);
-    const int2 t = tmpl[(r - 1) * 32];
-    const int diff = (q * w00 + qr * w01 + v * w10 + vr * w11 + t.x) >> (WB - 5);
-    if (ERR) {
-      const int d = live ? diff : 0;
-      o1 += d < 0 ? -d : d;
-    } else {
-      o1 += diff * (int)(short)(t.y & 0xffff);
-      o2 += diff * (t.y >> 16);
+    for (int r = 1; r <= WIN; ++r) {
+      p += pitch;
+      const int v = p[0];
+      const int vr = __shfl_down_sync(FULL, v, 1);
+      const int2 t = tmpl[(r - 1) * 32];
+      const int diff = (q * w00 + qr * w01 + v * w10 + vr * w11 + t.x) >> (WB - 5);
+      if (ERR) {
+        const int d = live ? diff : 0;
+        o1 += d < 0 ? -d : d;
+      } else {
+        o1 += diff * (int)(short)(t.y & 0xffff);
+        o2 += diff * (t.y >> 16);
+      }
+      q = v; qr = vr;
     }
-    q = v; qr = vr;
+  } else {
+    const uint8_t* col = J + reflect101(inx + lane, w);
+    int q = col[(size_t)reflect101(iny, h) * pitch];
+    int qr = __shfl_down_sync(FULL, q, 1);
+#pragma unroll 2
+    for (int r = 1; r <= WIN; ++r) {
+      const int v = col[(size_t)reflect101(iny + r, h) * pitch];
+      const int vr = __shfl_down_sync(FULL, v, 1);
+      const int2 t = tmpl[(r - 1) * 32];
+      const int diff = (q * w00 + qr * w01 + v * w10 + vr * w11 + t.x) >> (WB - 5);
+      if (ERR) {
+        const int d = live ? diff : 0;
+        o1 += d < 0 ? -d : d;
+      } else {
+        o1 += diff * (int)(short)(t.y & 0xffff);
+        o2 += diff * (t.y >> 16);
+      }
+      q = v; qr = vr;
+    }
   }
 }
 

@@ -173,6 +173,36 @@ int flv_ba_optimize(flv_ctx* ctx, int n_streams, const flv_ba_problem* problems,
                     const int* edge_pose, const int* edge_lm, const double* edge_uv,
                     uint8_t* edge_active, flv_ba_stats* stats, flv_memspace mem);
 
+/* ---- per-landmark geometry (K6) -------------------------------------------------------------------
+ * flv_depth_innovation replaces CameraFrame::depthInnovation (src/processing/camera_frame.cpp:271-330) and the
+ * measurement sources it calls: recover3DPts_c_FromTriangulation (:236-270, Triangulation::triangulationPt,
+ * src/processing/triangulation.cpp:9-39,80-97), the part of recover3DPts_c_FromStereo after its LK call (:133-179;
+ * run flv_lk_track for the LK, then undistort on the host or pass rectified points) and recover3DPts_c_FromDepthImg
+ * (:182-234; the caller samples the u16 depth image at round(lm_2d_plane) into depth_at_pts).
+ * dummy_rand[s][i] holds the next d_rand values of the reference's rand() stream for that sequence, in draw order
+ * (flvis_b200/host/glibc_rand.h reproduces glibc's sequence); n_rand_used[s] returns how many were consumed.
+ * flv_reprojection_inliers replaces CameraFrame::calReprjInlierOutlier (:43-91).  All arrays [s][max_pts][...]. */
+typedef struct {
+  double fx, fy, cx, cy;   /* DepthCamera::cam0_fx .. cam0_cy */
+  double P0[12], P1[12];   /* DepthCamera::P0_, P1_ (row-major 3x4), stereo only */
+  int cam_type;            /* 0 = DEPTH_D435, 1 = STEREO_RECT / STEREO_UNRECT */
+  double depth_scale;      /* cam_scale_factor (depth image units per metre) */
+} flv_camera;
+typedef struct {
+  float iir_ratio;   /* dr_para1 */
+  float range;       /* dr_para2 */
+  int dummy_depth;   /* dr_para3 >= 0.5 */
+} flv_depth_params;
+int flv_depth_innovation(flv_ctx* ctx, int n_streams, const int* n_lms, const flv_camera* cam,
+                         const flv_depth_params* prm, const double* T_c_w, const double* lm_2d_plane,
+                         const double* lm_2d_undist, double* lm_3d_w, double* lm_3d_c, uint8_t* has_3d,
+                         const double* first_obs_2d, const double* first_obs_pose, const double* stereo_pt1_undist,
+                         const uint8_t* stereo_status, const uint16_t* depth_at_pts, const float* dummy_rand,
+                         int* n_rand_used, flv_memspace mem);
+int flv_reprojection_inliers(flv_ctx* ctx, int n_streams, const int* n_lms, const flv_camera* cam, const double* T_c_w,
+                             const double* lm_2d_undist, const double* lm_3d_w, double sh_over_med,
+                             uint8_t* is_inlier, double* mean_prjerr, flv_memspace mem);
+
 /* Run subsequent flv_ba_optimize calls on `cuda_stream` instead of the context stream (enable=1), the analogue of
  * FLVIS's separate local-map thread: the BA of keyframe k overlaps the tracking of the following frames.
  * enable=0 reverts to the context stream.  The caller orders the streams (events) as it needs. */
