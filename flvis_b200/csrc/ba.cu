@@ -435,29 +435,29 @@ __device__ void solve_system(const flv_ba_problem& pb, double lambda, double* S,
     __syncthreads();
   }
   const int nblk = np * (np + 1) / 2;
+  // One warp per pose pair.  TWO lanes share a member: lane parity h owns columns 3h..3h+2 of the 6x6 block, so a
+  // lane keeps 18 accumulators + Y_a (18) + half of W_b (9) in registers -- the full 36 + 18 + 18 layout spilled
+  // under the 128-register cap and made this pass local-memory bound (profiles/r01_ba_notes.md).
+  const int half = lane & 1, mslot = lane >> 1;
   for (int blk = warp; blk < nblk; blk += BA_WARPS) {
     int a, b; pair_of(blk, np, a, b);
-    double acc[36], cf[6];
+    double acc[18], cf[6];
 #pragma unroll
-    for (int i = 0; i < 36; ++i) acc[i] = 0;
+    for (int i = 0; i < 18; ++i) acc[i] = 0;
 #pragma unroll
     for (int i = 0; i < 6; ++i) cf[i] = 0;
     if (!pb.fix_landmarks) {
       const int i0 = sh.pair_off[blk], i1 = sh.pair_off[blk + 1];
-      // the (ea, eb, l) triple of the NEXT member is fetched while this one is processed: one dependent L2 round
-      // trip per member instead of two (the pass is latency-bound: ~20 B/clk of L2 traffic on 16 warps)
-      int k = i0 + lane;
-      int n0 = 0, n1 = 0, n2 = 0;
-      if (k < i1) { const int* it = ws.pairs + 3 * (size_t)k; n0 = it[0]; n1 = it[1]; n2 = it[2]; }
-      for (; k < i1; k += 32) {
-        const int it[3] = {n0, n1, n2};
-        if (k + 32 < i1) { const int* nx = ws.pairs + 3 * (size_t)(k + 32); n0 = nx[0]; n1 = nx[1]; n2 = nx[2]; }
+      for (int k = i0 + mslot; k < i1; k += 16) {
+        const int* it = ws.pairs + 3 * (size_t)k;
         const double* Ya = ws.Y + 18 * (size_t)it[0];
-        const double* Wb = ws.W + 18 * (size_t)it[1];
-        double ya[18], wb[18];
+        const double* Wb = ws.W + 18 * (size_t)it[1] + 9 * half;      // rows 3h..3h+2 of W_b (6x3, row-major)
+        double ya[18], wb[9];
 #pragma unroll
-        for (int i = 0; i < 18; ++i) { ya[i] = Ya[i]; wb[i] = Wb[i]; }
-        if (a == b) {
+        for (int i = 0; i < 18; ++i) ya[i] = Ya[i];
+#pragma unroll
+        for (int i = 0; i < 9; ++i) wb[i] = Wb[i];
+        if (a == b && half == 0) {
           const double* bl = ws.bl + 3 * (size_t)it[2];
           const double b0 = bl[0], b1 = bl[1], b2 = bl[2];
 #pragma unroll
@@ -466,33 +466,46 @@ __device__ void solve_system(const flv_ba_problem& pb, double lambda, double* S,
 #pragma unroll
         for (int i = 0; i < 6; ++i)
 #pragma unroll
-          for (int j = 0; j < 6; ++j)
-            acc[6 * i + j] += ya[3 * i] * wb[3 * j] + ya[3 * i + 1] * wb[3 * j + 1] + ya[3 * i + 2] * wb[3 * j + 2];
+          for (int j = 0; j < 3; ++j)
+            acc[3 * i + j] += ya[3 * i] * wb[3 * j] + ya[3 * i + 1] * wb[3 * j + 1] + ya[3 * i + 2] * wb[3 * j + 2];
       }
     }
+    // reduce over the 16 member slots (lanes of equal parity): xor 2, 4, 8, 16
 #pragma unroll
-    for (int i = 0; i < 36; ++i) acc[i] = warp_sum(acc[i]);
+    for (int i = 0; i < 18; ++i) {
+      double v = acc[i];
+#pragma unroll
+      for (int o = 2; o < 32; o <<= 1) v += __shfl_xor_sync(FULL, v, o);
+      acc[i] = v;
+    }
     if (a == b) {
 #pragma unroll
-      for (int i = 0; i < 6; ++i) cf[i] = warp_sum(cf[i]);
+      for (int i = 0; i < 6; ++i) {
+        double v = cf[i];
+#pragma unroll
+        for (int o = 2; o < 32; o <<= 1) v += __shfl_xor_sync(FULL, v, o);
+        cf[i] = v;
+      }
     }
-    // S block (b,a) of the lower triangle = -(acc)^T (+ Hpp + lambda on the diagonal block); lanes 0..35 write
-    if (lane < 32) {
+    // lanes 0 and 1 write their three columns: S block (b,a) of the lower triangle = -(acc)^T (+ Hpp + lambda)
+    if (lane < 2) {
 #pragma unroll
       for (int i = 0; i < 6; ++i)
 #pragma unroll
-        for (int j = 0; j < 6; ++j) {
-          if (((6 * i + j) & 31) == lane) {
-            double v = -acc[6 * i + j];
-            if (a == b) {
-              v += sh.Hd[a][i <= j ? sym21(i, j) : sym21(j, i)];
-              if (i == j) v += lambda;
-            }
-            S[(6 * b + j) * ld + 6 * a + i] = v;          // row index from pose b >= a: lower triangle
-            if (a == b) S[(6 * a + i) * ld + 6 * b + j] = v;
+        for (int jj = 0; jj < 3; ++jj) {
+          const int j = 3 * half + jj;
+          double v = -acc[3 * i + jj];
+          if (a == b) {
+            v += sh.Hd[a][i <= j ? sym21(i, j) : sym21(j, i)];
+            if (i == j) v += lambda;
           }
+          S[(6 * b + j) * ld + 6 * a + i] = v;            // row index from pose b >= a: lower triangle
+          if (a == b) S[(6 * a + i) * ld + 6 * b + j] = v;
         }
-      if (a == b && lane < 6) y[6 * a + lane] = sh.bp[6 * a + lane] - cf[lane];
+      if (a == b && lane == 0) {
+#pragma unroll
+        for (int i = 0; i < 6; ++i) y[6 * a + i] = sh.bp[6 * a + i] - cf[i];
+      }
     }
   }
   if (tid == 0) sh.fail = 0;

@@ -280,7 +280,9 @@ int flv_launch_lk(flv_ctx* ctx, int src_slot, int dst_slot, int n_streams, const
   dim3 grid((ctx->max_pts + WARPS - 1) / WARPS, n_streams);
   const float err_scale = (float)(1.0 / (32 * WIN * WIN));
   // two register budgets of the same kernel: 168 regs / 12 warps per SM (no spills) or 128 regs / 16 warps per SM
-  const int variant = getenv("FLV_LK_VARIANT") ? atoi(getenv("FLV_LK_VARIANT")) : 1;
+  // default: the shared-memory-template kernel (v3) once the batch fills the machine, the register-template kernel
+  // (v1, lower latency per point) for small batches; FLV_LK_VARIANT overrides (A/B measurements in profiles/)
+  const int variant = getenv("FLV_LK_VARIANT") ? atoi(getenv("FLV_LK_VARIANT")) : (n_streams >= 8 ? 5 : 1);
   if (variant == 5)
     return flv_launch_lk_v3(ctx, src_slot, dst_slot, n_streams, d_npts, d_prev, d_init, d_next, d_status, d_err, nlev_used,
                             max_iter, eps2, min_eig_thr);

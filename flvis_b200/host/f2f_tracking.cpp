@@ -1,0 +1,436 @@
+#include "f2f_tracking.h"
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+
+namespace flv {
+
+namespace {
+constexpr int MAX_PTS = 512;
+
+SE3 se3_from_R(const double* R, const Vec3& t) { return SE3(R_to_q(R), t); }
+Pose7 to7(const SE3& T) { return Pose7{T.q.x, T.q.y, T.q.z, T.q.w, T.t[0], T.t[1], T.t[2]}; }
+SE3 from7(const double* p) { return SE3(Quat{p[3], p[0], p[1], p[2]}, Vec3{p[4], p[5], p[6]}); }
+
+Vec3 so3_log(const Quat& q) {          // Sophus SO3::logAndTheta (so3.cpp:127-164), SMALL_EPS = 1e-10
+  const double n = std::sqrt(q.x * q.x + q.y * q.y + q.z * q.z), w = q.w;
+  double f;
+  if (n < 1e-10) f = 2. / w - 2. * (n * n) / (w * w * w);
+  else f = 2 * std::atan(n / w) / n;
+  return Vec3{f * q.x, f * q.y, f * q.z};
+}
+}  // namespace
+
+// ---- CameraFrame --------------------------------------------------------------------------------
+void CameraFrame::clear() {                                     // camera_frame.cpp:8-15
+  T_c_w = SE3();
+  d_img.clear();
+  landmarks.clear();
+}
+void CameraFrame::eraseReprjOutlier() {                         // :18-28
+  for (int i = (int)landmarks.size() - 1; i >= 0; i--)
+    if (!landmarks[i].is_tracking_inlier) landmarks.erase(landmarks.begin() + i);
+}
+void CameraFrame::eraseNoDepthPoint() {                         // :30-40
+  for (int i = (int)landmarks.size() - 1; i >= 0; i--)
+    if (!landmarks[i].has_3d) landmarks.erase(landmarks.begin() + i);
+}
+int CameraFrame::validLMCount() const {                         // :399-413
+  int ret = 0;
+  for (const LandMarkInFrame& lm : landmarks) ret += (lm.has_3d && lm.is_tracking_inlier);
+  return ret;
+}
+void CameraFrame::updateLMState(const std::vector<uint8_t>& status) {   // :445-461
+  int indexLM = 0;
+  for (LandMarkInFrame& lm : landmarks)
+    if (lm.has_3d && lm.is_tracking_inlier) {
+      if (status[indexLM] == 0) lm.is_tracking_inlier = false;
+      indexLM += 1;
+    }
+}
+std::vector<Vec2> CameraFrame::get2dPlaneVec() const {
+  std::vector<Vec2> r;
+  for (const LandMarkInFrame& lm : landmarks) r.push_back(lm.lm_2d_plane);
+  return r;
+}
+void CameraFrame::getKeyFrameInf(std::vector<int64_t>& lm_id, std::vector<Vec2>& lm_2d, std::vector<Vec3>& lm_3d) const {  // :515-529
+  lm_id.clear(); lm_2d.clear(); lm_3d.clear();
+  for (const LandMarkInFrame& lm : landmarks)
+    if (lm.has_3d && lm.is_tracking_inlier) { lm_3d.push_back(lm.lm_3d_w); lm_2d.push_back(lm.lm_2d_undistort); lm_id.push_back(lm.lm_id); }
+}
+
+// ---- F2FTracking ---------------------------------------------------------------------------------
+F2FTracking::F2FTracking() {}
+F2FTracking::~F2FTracking() { delete vimotion; if (ctx_) flv_destroy(ctx_); }
+
+int F2FTracking::init(const DepthCamera& dc, const SE3& T_i_c0, const double feature_para[6], const double vi_para[6],
+                      const double dc_para[3], int skip_first_n_imgs, bool need_equal_hist_in, int device) {   // f2f_tracking.cpp:5-38
+  if (dc.cam_type == STEREO_UNRECT || need_equal_hist_in) {
+    snprintf(err_, sizeof(err_), "STEREO_UNRECT / equalizeHist ingest is not implemented in the host layer");
+    return FLV_ERR_UNSUPPORTED;
+  }
+  skip_n_imgs = skip_first_n_imgs; need_equal_hist = need_equal_hist_in;
+  int rc = flv_create(&ctx_, device, 1, dc.img_w, dc.img_h, MAX_PTS);
+  if (rc) { snprintf(err_, sizeof(err_), "flv_create: %s", flv_last_error(ctx_)); return rc; }
+  fprm_.max_region_feature_num = (int)feature_para[0];
+  fprm_.min_region_feature_num = (int)feature_para[1];
+  fprm_.boundary_dis = (int)std::floor(feature_para[2] / 2.0);
+  fprm_.gftt_num = (int)feature_para[3];
+  fprm_.gftt_ql = feature_para[4];
+  fprm_.gftt_dis = (int)feature_para[5];
+  vimotion = new VIMOTION(T_i_c0, 9.81, vi_para[0], vi_para[1], vi_para[2], vi_para[3]);
+  curr_frame = std::make_shared<CameraFrame>();
+  last_frame = std::make_shared<CameraFrame>();
+  cam_type = dc.cam_type;
+  d_camera = curr_frame->d_camera = last_frame->d_camera = dc;
+  curr_frame->slot0 = 0; curr_frame->slot1 = 1; last_frame->slot0 = 2; last_frame->slot1 = 3;
+  iir_ratio = (float)dc_para[0];
+  range = (float)dc_para[1];
+  enable_dummy = !(dc_para[2] < 0.5);
+  frameCount = 0;
+  vo_tracking_state = UnInit;
+  return FLV_OK;
+}
+
+void F2FTracking::imu_feed(double time, const Vec3& acc, const Vec3& gyro, Quat& q_w_i, Vec3& pos_w_i, Vec3& vel_w_i) {   // :46-57
+  IMUSTATE s; s.timestamp = time; s.acc_raw = acc; s.gyro_raw = gyro;
+  if (!vimotion->imu_initialized) { has_imu = true; vimotion->viIMUinitialization(s, q_w_i, pos_w_i, vel_w_i); }
+  else vimotion->viIMUPropagation(s, q_w_i, pos_w_i, vel_w_i);
+}
+
+LandMarkInFrame F2FTracking::make_landmark(const Vec2& pt2d, const Vec2& pt2d_undist, const SE3& T_c_w, bool is_inlier) {   // landmark.cpp:18-39
+  LandMarkInFrame lm;
+  lm.lm_id = id_index++;
+  lm.lm_1st_obs_2d = lm.lm_2d_undistort = pt2d_undist;
+  lm.lm_2d_plane = pt2d;
+  lm.lm_1st_obs_frame_pose = T_c_w;
+  lm.is_tracking_inlier = is_inlier;
+  return lm;
+}
+
+int F2FTracking::feature_detect(CameraFrame& fr, std::vector<P2f>& pts) {
+  std::vector<float> out(2 * MAX_PTS); int n = 0;
+  int rc = flv_feature_detect(ctx_, fr.slot0, 1, &fprm_, out.data(), &n, FLV_MEM_HOST);
+  if (rc) return rc;
+  pts.resize(n);
+  memcpy(pts.data(), out.data(), (size_t)n * 8);
+  return FLV_OK;
+}
+int F2FTracking::feature_redetect(CameraFrame& fr, std::vector<P2f>& pts) {
+  std::vector<double> ex(2 * MAX_PTS, 0.0);
+  int ne = (int)std::min<size_t>(fr.landmarks.size(), MAX_PTS), n = 0;
+  for (int i = 0; i < ne; ++i) { ex[2 * i] = fr.landmarks[i].lm_2d_plane[0]; ex[2 * i + 1] = fr.landmarks[i].lm_2d_plane[1]; }
+  std::vector<float> out(2 * MAX_PTS);
+  int rc = flv_feature_redetect(ctx_, fr.slot0, 1, &fprm_, ex.data(), &ne, out.data(), &n, FLV_MEM_HOST);
+  if (rc) return rc;
+  pts.resize(n);
+  memcpy(pts.data(), out.data(), (size_t)n * 8);
+  return FLV_OK;
+}
+
+int F2FTracking::image_feed(double time, const uint8_t* img0, const void* img1, bool& new_keyframe, bool& reset_cmd) {   // :59-400
+  new_keyframe = false; reset_cmd = false;
+  frameCount++;
+  last_frame.swap(curr_frame);
+  curr_frame->clear();
+  curr_frame->frame_id = frameCount;
+  curr_frame->frame_time = time;
+  const int w = d_camera.img_w, h = d_camera.img_h;
+  int rc = flv_upload_images(ctx_, curr_frame->slot0, 1, img0, w, (size_t)w * h, FLV_MEM_HOST);
+  if (rc) return rc;
+  if (cam_type == DEPTH_D435) curr_frame->d_img.assign((const uint16_t*)img1, (const uint16_t*)img1 + (size_t)w * h);
+  else if ((rc = flv_upload_images(ctx_, curr_frame->slot1, 1, (const uint8_t*)img1, w, (size_t)w * h, FLV_MEM_HOST))) return rc;
+  if (skip_n_imgs > 0) { skip_n_imgs--; return FLV_OK; }
+  if ((rc = flv_build_pyramid(ctx_, curr_frame->slot0, 1))) return rc;
+  if (cam_type != DEPTH_D435 && (rc = flv_build_pyramid(ctx_, curr_frame->slot1, 1))) return rc;
+
+  switch (vo_tracking_state) {
+    case UnInit: {
+      const double R_w_c[9] = {0, 0, 1, -1, 0, 0, 0, -1, 0};
+      curr_frame->T_c_w = se3_from_R(R_w_c, Vec3{0, 0, 0}).inverse();
+      if (has_imu) {
+        if (vimotion->imu_initialized) {
+          Quat q_init;
+          vimotion->viVisiontrigger(q_init);
+          double Ra[9], Rb[9], Rc[9];
+          q_to_R(q_init, Ra); q_to_R(vimotion->T_i_c.q, Rb);
+          for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) Rc[3 * i + j] = Ra[3 * i] * Rb[j] + Ra[3 * i + 1] * Rb[3 + j] + Ra[3 * i + 2] * Rb[6 + j];
+          curr_frame->T_c_w = se3_from_R(Rc, Vec3{0, 0, 0}).inverse();
+        } else break;
+      }
+      if (init_frame()) { new_keyframe = true; vo_tracking_state = Tracking; }
+      break;
+    }
+    case Tracking: {
+      // STEP1 (local-map feedback) is dead code in the reference: correction_feed is never called (vo_tracking.cpp:373-385)
+      SE3 imu_guess; bool has_imu_guess = false;
+      if (has_imu) has_imu_guess = vimotion->viGetCorrFrameState(time, imu_guess);
+      const bool tracking_success = tracking(*last_frame, *curr_frame, imu_guess, has_imu_guess);
+      if (!tracking_success) {
+        continus_tracking_fail_cnt++;
+        last_frame.swap(curr_frame);
+        if (continus_tracking_fail_cnt >= 2) { vo_tracking_state = TrackingFail; continus_tracking_fail_cnt = 0; }
+        break;
+      }
+      continus_tracking_fail_cnt = 0;
+      if (has_imu) vimotion->viVisionRPCompensation(curr_frame->frame_time, curr_frame->T_c_w);
+      if (!optimize_in_frame(*curr_frame)) {
+        continus_tracking_fail_cnt++;
+        last_frame.swap(curr_frame);
+        if (continus_tracking_fail_cnt >= 2) { vo_tracking_state = TrackingFail; continus_tracking_fail_cnt = 0; }
+        break;
+      }
+      if ((rc = cal_reprj_inlier_outlier(*curr_frame, 1.5))) return rc;
+      curr_frame->eraseReprjOutlier();
+      if (has_imu)
+        vimotion->viCorrectionFromVision(curr_frame->frame_time, curr_frame->T_c_w, last_frame->frame_time, last_frame->T_c_w,
+                                         curr_frame->reprojection_error);
+      std::vector<P2f> pts2d;
+      const int orig_size = (int)curr_frame->landmarks.size();
+      if ((rc = feature_redetect(*curr_frame, pts2d))) return rc;
+      const bool add_as_inliers = orig_size < 60;
+      for (const P2f& p : pts2d)        // DEPTH_D435 / STEREO_RECT: pts2d_undistort = pts2d (:294-299)
+        curr_frame->landmarks.push_back(make_landmark(Vec2{p.x, p.y}, Vec2{p.x, p.y}, curr_frame->T_c_w, add_as_inliers));
+      if ((rc = depth_innovation(*curr_frame))) return rc;
+      curr_frame->eraseNoDepthPoint();
+      pose_records.push_back(ID_POSE{curr_frame->frame_id, curr_frame->T_c_w});
+      if (pose_records.size() >= 1000) pose_records.pop_front();
+      const SE3 T_diff = T_c_w_last_keyframe * curr_frame->T_c_w.inverse();
+      const Vec3 r = so3_log(T_diff.q);
+      const double t_norm = std::fabs(T_diff.t[0]) + std::fabs(T_diff.t[1]) + std::fabs(T_diff.t[2]);
+      const double r_norm = std::fabs(r[0]) + std::fabs(r[1]) + std::fabs(r[2]);
+      if (frameCount < 40 && (frameCount % 5) == 0) { new_keyframe = true; T_c_w_last_keyframe = curr_frame->T_c_w; }
+      if (t_norm >= 0.05 || r_norm >= 0.2) { new_keyframe = true; T_c_w_last_keyframe = curr_frame->T_c_w; }
+      break;
+    }
+    case TrackingFail: {
+      fail_cnt++;
+      if ((fail_cnt % 3) == 0) {
+        if (vimotion->viGetCorrFrameState(curr_frame->frame_time, curr_frame->T_c_w)) {
+          if (init_frame()) { new_keyframe = true; vo_tracking_state = Tracking; }
+          else last_frame.swap(curr_frame);
+        } else last_frame.swap(curr_frame);
+        fail_cnt = 0;
+      } else {
+        last_frame.swap(curr_frame);
+        if ((fail_cnt % 2) == 0) reset_cmd = true;
+      }
+      break;
+    }
+  }
+  return FLV_OK;
+}
+
+bool F2FTracking::init_frame() {                                   // f2f_tracking.cpp:402-453
+  std::vector<P2f> pts2d;
+  if (feature_detect(*curr_frame, pts2d)) return false;
+  // DEPTH: undistorted = plane.  STEREO_RECT: cv::undistortPoints(K0, D0=0, R0=I, P0) is the identity map up to rounding
+  for (const P2f& p : pts2d)
+    curr_frame->landmarks.push_back(make_landmark(Vec2{p.x, p.y}, Vec2{p.x, p.y}, curr_frame->T_c_w, true));
+  if (depth_innovation(*curr_frame)) return false;
+  curr_frame->eraseNoDepthPoint();
+  if (curr_frame->validLMCount() > 30) {
+    pose_records.push_back(ID_POSE{curr_frame->frame_id, curr_frame->T_c_w});
+    T_c_w_last_keyframe = curr_frame->T_c_w;
+    return true;
+  }
+  return false;
+}
+
+bool F2FTracking::tracking(CameraFrame& from, CameraFrame& to, const SE3& T_c_w_guess, bool use_guess) {   // lkorb_tracking.cpp:9-202
+  const int n = (int)std::min<size_t>(from.landmarks.size(), MAX_PTS);
+  std::vector<P2f> from_plane(n), tracked_plane(n), from_und(n);
+  std::vector<P3f> from_p3d(n);
+  for (int i = 0; i < n; ++i) {                                  // getAll2dPlaneUndistort3d_cvPf (float copies)
+    const LandMarkInFrame& lm = from.landmarks[i];
+    from_plane[i] = P2f{(float)lm.lm_2d_plane[0], (float)lm.lm_2d_plane[1]};
+    from_und[i] = P2f{(float)lm.lm_2d_undistort[0], (float)lm.lm_2d_undistort[1]};
+    from_p3d[i] = P3f{(float)lm.lm_3d_w[0], (float)lm.lm_3d_w[1], (float)lm.lm_3d_w[2]};
+  }
+  tracked_plane = from_plane;
+  if (use_guess)                                                 // :38-63 (pinhole projection; D0 = 0 for the supported types)
+    for (int i = 0; i < n; ++i) {
+      const Vec3 pc = DepthCamera::world2cameraT_c_w(Vec3{from_p3d[i].x, from_p3d[i].y, from_p3d[i].z}, T_c_w_guess);
+      const Vec2 px = from.d_camera.camera2pixel(pc);
+      tracked_plane[i] = P2f{(float)px[0], (float)px[1]};
+    }
+  std::vector<float> prev(2 * MAX_PTS, 0.f), init(2 * MAX_PTS, 0.f), next(2 * MAX_PTS), err(MAX_PTS);
+  std::vector<uint8_t> st(MAX_PTS);
+  memcpy(prev.data(), from_plane.data(), (size_t)n * 8);
+  memcpy(init.data(), tracked_plane.data(), (size_t)n * 8);
+  flv_lk_params lk{31, 10, 30, 1e-3, 1e-4};
+  if (flv_lk_track(ctx_, from.slot0, to.slot0, 1, &n, prev.data(), init.data(), next.data(), st.data(), err.data(), &lk, FLV_MEM_HOST))
+    return false;
+  memcpy(tracked_plane.data(), next.data(), (size_t)n * 8);
+  std::vector<P2f> tracked_und = tracked_plane;                  // DEPTH_D435 / STEREO_RECT (:78-85)
+  to.landmarks.clear();
+  const int wlim = to.d_camera.img_w - 1, hlim = to.d_camera.img_h - 1;
+  int of_inlier_cnt = 0;
+  for (int i = n - 1; i >= 0; i--) {                             // :98-119 -- `to.landmarks` ends up REVERSED
+    if (st[i] == 1 && tracked_plane[i].x > 0 && tracked_plane[i].y > 0 && tracked_plane[i].x < wlim && tracked_plane[i].y < hlim) {
+      of_inlier_cnt++;
+      LandMarkInFrame lm = from.landmarks[i];
+      lm.lm_2d_plane = Vec2{tracked_plane[i].x, tracked_plane[i].y};
+      lm.lm_2d_undistort = Vec2{tracked_und[i].x, tracked_und[i].y};
+      to.landmarks.push_back(lm);
+    } else {
+      from_plane.erase(from_plane.begin() + i); from_p3d.erase(from_p3d.begin() + i);
+      tracked_plane.erase(tracked_plane.begin() + i); from_und.erase(from_und.begin() + i);
+      tracked_und.erase(tracked_und.begin() + i);
+    }
+  }
+  last_of_inliers = of_inlier_cnt; last_f_inliers = last_pnp_inliers = 0;
+  if (of_inlier_cnt < 10) return false;
+  // STEP2: F-matrix consistency; mask index i is applied to to.landmarks[i] (mirrored order, kept: :138-149)
+  const int m = (int)from_und.size();
+  std::vector<uint8_t> maskF(m, 0);
+  if (fmat_fn_) {
+    if (fmat_fn_(hook_user_, m, &from_und[0].x, &tracked_und[0].x, maskF.data())) return false;
+  } else {
+    double F[9];
+    find_fundamental_ransac(from_und, tracked_und, 5.0, 0.99, maskF, F);
+  }
+  for (int i = 0; i < m; i++)
+    if (maskF[i] == 0) to.landmarks[i].is_tracking_inlier = false;
+  int F_inlier_cnt = 0;
+  for (const LandMarkInFrame& lm : to.landmarks) F_inlier_cnt += lm.is_tracking_inlier;
+  last_f_inliers = F_inlier_cnt;
+  if (F_inlier_cnt < 10) return false;
+  // STEP3: PnP RANSAC on (has depth && inlier) pairs
+  std::vector<P2f> p2d; std::vector<P3f> p3d;
+  for (const LandMarkInFrame& lm : to.landmarks)
+    if (lm.has_3d && lm.is_tracking_inlier) {
+      p2d.push_back(P2f{(float)lm.lm_2d_undistort[0], (float)lm.lm_2d_undistort[1]});
+      p3d.push_back(P3f{(float)lm.lm_3d_w[0], (float)lm.lm_3d_w[1], (float)lm.lm_3d_w[2]});
+    }
+  const double K[4] = {d_camera.cam0_fx, d_camera.cam0_fy, d_camera.cam0_cx, d_camera.cam0_cy};
+  Pose7 T = to7(use_guess ? T_c_w_guess : from.T_c_w);
+  std::vector<int> inl;
+  if (pnp_fn_) {
+    inl.resize(p2d.size());
+    int ninl = 0;
+    if (p2d.empty() || pnp_fn_(hook_user_, (int)p2d.size(), &p3d[0].x, &p2d[0].x, K, use_guess ? 1 : 0, T.data(), inl.data(), &ninl)) return false;
+    inl.resize(ninl);
+  } else {
+    solve_pnp_ransac(p3d, p2d, K, T, 100, 3.0, 0.99, inl);
+  }
+  std::vector<uint8_t> mask_pnp(p2d.size(), 0);
+  for (int k : inl) mask_pnp[k] = 1;
+  to.updateLMState(mask_pnp);
+  to.T_c_w = from7(T.data());
+  last_pnp_inliers = (int)inl.size();
+  return inl.size() >= 10;
+}
+
+bool F2FTracking::optimize_in_frame(CameraFrame& frame) {          // optimize_in_frame.cpp:10-90
+  std::vector<const LandMarkInFrame*> lms;
+  for (const LandMarkInFrame& lm : frame.landmarks) if (lm.has_3d && lm.is_tracking_inlier) lms.push_back(&lm);
+  const int n = (int)lms.size();
+  if (n < 10) return false;
+  if (flv_ba_reserve(ctx_, 1, MAX_PTS, MAX_PTS)) return false;
+  std::vector<double> pts(3 * MAX_PTS, 0.0), uv(2 * MAX_PTS, 0.0);
+  std::vector<int> ep(MAX_PTS, 0), el(MAX_PTS, 0);
+  std::vector<uint8_t> act(MAX_PTS, 0);
+  for (int i = 0; i < n; ++i) {
+    for (int k = 0; k < 3; ++k) pts[3 * i + k] = lms[i]->lm_3d_w[k];
+    uv[2 * i] = lms[i]->lm_2d_undistort[0]; uv[2 * i + 1] = lms[i]->lm_2d_undistort[1];
+    el[i] = i; act[i] = 1;
+  }
+  Pose7 pose = g2o_pose_from_quat(to7(frame.T_c_w));
+  flv_ba_problem pb{1, n, n, -1, 1, d_camera.cam0_fx, d_camera.cam0_fy, d_camera.cam0_cx, d_camera.cam0_cy};
+  flv_ba_params prm{2, 2, 1.0, 3.0, 10, 0};
+  flv_ba_stats st;
+  if (flv_ba_optimize(ctx_, 1, &pb, &prm, pose.data(), pts.data(), ep.data(), el.data(), uv.data(), act.data(), &st, FLV_MEM_HOST))
+    return false;
+  if (!st.ok) return false;                                        // < 10 edges after the chi2 cull: pose left untouched
+  frame.T_c_w = from7(pose.data());
+  return true;
+}
+
+int F2FTracking::cal_reprj_inlier_outlier(CameraFrame& fr, double sh_over_med) {   // camera_frame.cpp:43-91
+  const int n = (int)std::min<size_t>(fr.landmarks.size(), MAX_PTS);
+  std::vector<double> und(2 * MAX_PTS, 0.0), p3(3 * MAX_PTS, 0.0);
+  for (int i = 0; i < n; ++i) {
+    und[2 * i] = fr.landmarks[i].lm_2d_undistort[0]; und[2 * i + 1] = fr.landmarks[i].lm_2d_undistort[1];
+    for (int k = 0; k < 3; ++k) p3[3 * i + k] = fr.landmarks[i].lm_3d_w[k];
+  }
+  flv_camera cam{}; cam.fx = d_camera.cam0_fx; cam.fy = d_camera.cam0_fy; cam.cx = d_camera.cam0_cx; cam.cy = d_camera.cam0_cy;
+  const Pose7 T = to7(fr.T_c_w);
+  std::vector<uint8_t> inl(MAX_PTS, 0);
+  double mean = 0;
+  int rc = flv_reprojection_inliers(ctx_, 1, &n, &cam, T.data(), und.data(), p3.data(), sh_over_med, inl.data(), &mean, FLV_MEM_HOST);
+  if (rc) return rc;
+  for (int i = 0; i < n; ++i) fr.landmarks[i].is_tracking_inlier = inl[i] != 0;
+  fr.reprojection_error = mean;
+  return FLV_OK;
+}
+
+int F2FTracking::depth_innovation(CameraFrame& fr) {              // camera_frame.cpp:271-330 (+ :93-131 for the stereo LK)
+  const int n = (int)std::min<size_t>(fr.landmarks.size(), MAX_PTS);
+  std::vector<double> plane(2 * MAX_PTS, 0.0), und(2 * MAX_PTS, 0.0), p3w(3 * MAX_PTS, 0.0), p3c(3 * MAX_PTS, 0.0),
+      f2(2 * MAX_PTS, 0.0), fp(7 * MAX_PTS, 0.0), pt1(2 * MAX_PTS, 0.0);
+  std::vector<uint8_t> has(MAX_PTS, 0), st1(MAX_PTS, 0);
+  std::vector<uint16_t> dat(MAX_PTS, 0);
+  for (int i = 0; i < n; ++i) {
+    const LandMarkInFrame& lm = fr.landmarks[i];
+    plane[2 * i] = lm.lm_2d_plane[0]; plane[2 * i + 1] = lm.lm_2d_plane[1];
+    und[2 * i] = lm.lm_2d_undistort[0]; und[2 * i + 1] = lm.lm_2d_undistort[1];
+    for (int k = 0; k < 3; ++k) { p3w[3 * i + k] = lm.lm_3d_w[k]; p3c[3 * i + k] = lm.lm_3d_c[k]; }
+    has[i] = lm.has_3d;
+    f2[2 * i] = lm.lm_1st_obs_2d[0]; f2[2 * i + 1] = lm.lm_1st_obs_2d[1];
+    const Pose7 p = to7(lm.lm_1st_obs_frame_pose);
+    for (int k = 0; k < 7; ++k) fp[7 * i + k] = p[k];
+  }
+  flv_camera cam{};
+  cam.fx = d_camera.cam0_fx; cam.fy = d_camera.cam0_fy; cam.cx = d_camera.cam0_cx; cam.cy = d_camera.cam0_cy;
+  memcpy(cam.P0, d_camera.P0_, sizeof(cam.P0)); memcpy(cam.P1, d_camera.P1_, sizeof(cam.P1));
+  cam.cam_type = cam_type == DEPTH_D435 ? 0 : 1;
+  cam.depth_scale = d_camera.cam_scale_factor;
+  if (cam_type == DEPTH_D435) {
+    const int w = d_camera.img_w, h = d_camera.img_h;
+    for (int i = 0; i < n; ++i) {
+      const int px = (int)std::round(plane[2 * i]), py = (int)std::round(plane[2 * i + 1]);
+      dat[i] = (px >= 0 && px < w && py >= 0 && py < h) ? fr.d_img[(size_t)py * w + px] : 0;
+    }
+  } else {
+    // project the landmarks that already have depth into cam1 (cv::projectPoints with D1 = 0), else start at the cam0 position
+    std::vector<float> prev(2 * MAX_PTS, 0.f), init(2 * MAX_PTS, 0.f), next(2 * MAX_PTS), err(MAX_PTS);
+    const SE3 T_c1_w = d_camera.T_cam1_cam0 * fr.T_c_w;
+    for (int i = 0; i < n; ++i) {
+      const LandMarkInFrame& lm = fr.landmarks[i];
+      prev[2 * i] = (float)lm.lm_2d_plane[0]; prev[2 * i + 1] = (float)lm.lm_2d_plane[1];
+      init[2 * i] = prev[2 * i]; init[2 * i + 1] = prev[2 * i + 1];
+      if (lm.has_3d) {
+        const Vec3 pc = DepthCamera::world2cameraT_c_w(Vec3{(double)(float)lm.lm_3d_w[0], (double)(float)lm.lm_3d_w[1], (double)(float)lm.lm_3d_w[2]}, T_c1_w);
+        init[2 * i] = (float)(d_camera.cam1_fx * pc[0] / pc[2] + d_camera.cam1_cx);
+        init[2 * i + 1] = (float)(d_camera.cam1_fy * pc[1] / pc[2] + d_camera.cam1_cy);
+      }
+    }
+    flv_lk_params lk{31, 5, 30, 1e-3, 1e-4};
+    int rc = flv_lk_track(ctx_, fr.slot0, fr.slot1, 1, &n, prev.data(), init.data(), next.data(), st1.data(), err.data(), &lk, FLV_MEM_HOST);
+    if (rc) return rc;
+    for (int i = 0; i < n; ++i) { pt1[2 * i] = next[2 * i]; pt1[2 * i + 1] = next[2 * i + 1]; }   // rectified: undistort = identity
+  }
+  // the next MAX_PTS dummy depths of this sequence's rand() stream; only the consumed ones advance the generator
+  GlibcRand peek = rand_;
+  std::vector<float> rnd(MAX_PTS);
+  for (float& v : rnd) v = peek.dummy_depth();
+  flv_depth_params prm{iir_ratio, range, enable_dummy ? 1 : 0};
+  const Pose7 T = to7(fr.T_c_w);
+  int used = 0;
+  int rc = flv_depth_innovation(ctx_, 1, &n, &cam, &prm, T.data(), plane.data(), und.data(), p3w.data(), p3c.data(), has.data(),
+                                f2.data(), fp.data(), pt1.data(), st1.data(), dat.data(), rnd.data(), &used, FLV_MEM_HOST);
+  if (rc) return rc;
+  for (int i = 0; i < used; ++i) rand_.rand();
+  for (int i = 0; i < n; ++i) {
+    LandMarkInFrame& lm = fr.landmarks[i];
+    if (has[i]) {
+      for (int k = 0; k < 3; ++k) { lm.lm_3d_w[k] = p3w[3 * i + k]; lm.lm_3d_c[k] = p3c[3 * i + k]; }
+      lm.has_3d = true;
+    }
+  }
+  return FLV_OK;
+}
+
+}  // namespace flv

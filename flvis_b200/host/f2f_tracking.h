@@ -1,0 +1,125 @@
+// Host-side frame-to-frame tracker with the reference's class surface:
+//   LandMark / LandMarkInFrame   src/processing/include/landmark.h:8-36, src/processing/landmark.cpp:3-44
+//   DepthCamera                  src/processing/include/depth_camera.h:6-77, depth_camera.cpp:92-150
+//   CameraFrame                  src/processing/include/camera_frame.h:44-78, camera_frame.cpp:8-529
+//   LKORBTracking                src/processing/include/lkorb_tracking.h:14-20, lkorb_tracking.cpp:9-202
+//   OptimizeInFrame              src/processing/include/optimize_in_frame.h:31, optimize_in_frame.cpp:10-90
+//   FeatureDEM                   src/processing/include/feature_dem.h:35-50
+//   F2FTracking                  src/frontend/include/f2f_tracking.h:24-78, f2f_tracking.cpp:5-453
+// cv::Mat arguments become raw image pointers; every OpenCV / g2o call goes to the GPU through the C ABI
+// (include/flvis_b200.h) except the two RANSAC calls, which are host stand-ins (ransac.h) or caller callbacks.
+// Supported sensor types: DEPTH_D435 (type_of_vi 0/2) and STEREO_RECT (3/4).  STEREO_UNRECT (EuRoC raw, type 1) needs
+// lens undistortion + equalizeHist on ingest, which this layer does not implement yet (reported as an error).
+#pragma once
+#include <cstdint>
+#include <deque>
+#include <memory>
+#include <vector>
+#include "../../include/flvis_b200.h"
+#include "glibc_rand.h"
+#include "ransac.h"
+#include "sophus_lite.h"
+#include "vi_motion.h"
+
+namespace flv {
+
+enum TYPEOFCAMERA { DEPTH_D435 = 0, STEREO_RECT = 1, STEREO_UNRECT = 2 };
+
+struct DepthCamera {
+  int cam_type = DEPTH_D435;
+  int img_w = 0, img_h = 0;
+  double cam0_fx = 0, cam0_fy = 0, cam0_cx = 0, cam0_cy = 0;
+  double cam1_fx = 0, cam1_fy = 0, cam1_cx = 0, cam1_cy = 0;   // K1 (stereo)
+  double cam_scale_factor = 1000.0;
+  double P0_[12] = {0}, P1_[12] = {0};                          // rectified projection matrices, row-major 3x4
+  SE3 T_cam1_cam0;
+  Vec2 camera2pixel(const Vec3& p_c) const { return Vec2{cam0_fx * p_c[0] / p_c[2] + cam0_cx, cam0_fy * p_c[1] / p_c[2] + cam0_cy}; }
+  static Vec3 world2cameraT_c_w(const Vec3& p_w, const SE3& T) { const Vec3 r = q_rot(T.q, p_w); return Vec3{r[0] + T.t[0], r[1] + T.t[1], r[2] + T.t[2]}; }
+  static Vec3 camera2worldT_c_w(const Vec3& p_c, const SE3& T) { const SE3 Ti = T.inverse(); const Vec3 r = q_rot(Ti.q, p_c); return Vec3{r[0] + Ti.t[0], r[1] + Ti.t[1], r[2] + Ti.t[2]}; }
+};
+
+struct LandMarkInFrame {
+  int64_t lm_id = 0;
+  Vec3 lm_3d_w{0, 0, 0}, lm_3d_c{0, 0, 0};
+  Vec2 lm_2d_plane{0, 0}, lm_2d_undistort{0, 0};
+  bool has_3d = false, is_belong_to_kf = false, is_tracking_inlier = true;
+  Vec2 lm_1st_obs_2d{0, 0};
+  SE3 lm_1st_obs_frame_pose;
+  bool hasDepthInf() const { return has_3d; }
+};
+
+class CameraFrame {
+ public:
+  int64_t frame_id = 0;
+  double frame_time = 0;
+  int slot0 = 0, slot1 = 1;                       // pyramid slots of img0 / img1 in the tracker's flv_ctx
+  std::vector<uint16_t> d_img;                    // depth image (DEPTH_D435), host copy for the nearest-pixel lookups
+  DepthCamera d_camera;
+  std::vector<LandMarkInFrame> landmarks;
+  SE3 T_c_w;
+  double reprojection_error = 0;
+  void clear();
+  void eraseReprjOutlier();
+  void eraseNoDepthPoint();
+  int validLMCount() const;
+  void updateLMState(const std::vector<uint8_t>& status);
+  std::vector<Vec2> get2dPlaneVec() const;
+  void getKeyFrameInf(std::vector<int64_t>& lm_id, std::vector<Vec2>& lm_2d, std::vector<Vec3>& lm_3d) const;
+};
+
+// RANSAC hooks (default = host stand-ins of ransac.h).  Return 0 on success.
+typedef int (*flv_fmat_fn)(void* user, int n, const float* from_xy, const float* to_xy, uint8_t* mask_out);
+typedef int (*flv_pnp_fn)(void* user, int n, const float* p3d, const float* p2d, const double* K4, int use_guess,
+                          double* T_c_w_inout /*[qx qy qz qw tx ty tz]*/, int* inlier_idx_out, int* n_inliers_out);
+
+class F2FTracking {
+ public:
+  enum TRACKINGSTATE { UnInit = 0, Tracking, TrackingFail };
+  // one tracker = one sequence = one private flv_ctx with a single stream
+  F2FTracking();
+  ~F2FTracking();
+  // dc, T_i_c0, feature_para(6), vi_para(6), dc_para(3) as in f2f_tracking.cpp:5-38
+  int init(const DepthCamera& dc, const SE3& T_i_c0, const double feature_para[6], const double vi_para[6],
+           const double dc_para[3], int skip_first_n_imgs, bool need_equal_hist, int device = 0);
+  void imu_feed(double time, const Vec3& acc, const Vec3& gyro, Quat& q_w_i, Vec3& pos_w_i, Vec3& vel_w_i);
+  // img1: u8 right image (stereo) or u16 depth image (DEPTH_D435); rows tightly packed
+  int image_feed(double time, const uint8_t* img0, const void* img1, bool& new_keyframe, bool& reset_cmd);
+  void set_ransac_hooks(flv_fmat_fn f, flv_pnp_fn p, void* user) { fmat_fn_ = f; pnp_fn_ = p; hook_user_ = user; }
+
+  std::shared_ptr<CameraFrame> curr_frame, last_frame;
+  TRACKINGSTATE vo_tracking_state = UnInit;
+  bool has_imu = false;
+  int frameCount = 0;
+  VIMOTION* vimotion = nullptr;
+  const char* last_error() const { return err_; }
+  // last tracking() counters "pnp|F|of" (lkorb_tracking.cpp:191)
+  int last_of_inliers = 0, last_f_inliers = 0, last_pnp_inliers = 0;
+
+ private:
+  flv_ctx* ctx_ = nullptr;
+  DepthCamera d_camera;
+  flv_feature_params fprm_{};
+  float iir_ratio = 0.9f, range = 50.f;
+  bool enable_dummy = false, need_equal_hist = false;
+  int skip_n_imgs = 0, cam_type = DEPTH_D435;
+  int64_t id_index = 100;                         // landmark.cpp:3 (process-global there, per sequence here)
+  GlibcRand rand_;
+  SE3 T_c_w_last_keyframe;
+  struct ID_POSE { int64_t frame_id; SE3 T_c_w; };
+  std::deque<ID_POSE> pose_records;
+  int continus_tracking_fail_cnt = 0, fail_cnt = 0;
+  flv_fmat_fn fmat_fn_ = nullptr; flv_pnp_fn pnp_fn_ = nullptr; void* hook_user_ = nullptr;
+  char err_[256] = {0};
+  int slot_toggle = 0;
+
+  LandMarkInFrame make_landmark(const Vec2& pt2d, const Vec2& pt2d_undist, const SE3& T_c_w, bool is_inlier);
+  bool init_frame();
+  bool tracking(CameraFrame& from, CameraFrame& to, const SE3& T_c_w_guess, bool use_guess);   // LKORBTracking::tracking
+  bool optimize_in_frame(CameraFrame& frame);                                                   // OptimizeInFrame::optimize
+  int depth_innovation(CameraFrame& frame);                                                     // CameraFrame::depthInnovation
+  int cal_reprj_inlier_outlier(CameraFrame& frame, double sh_over_med);                         // CameraFrame::calReprjInlierOutlier
+  int feature_detect(CameraFrame& frame, std::vector<P2f>& pts);
+  int feature_redetect(CameraFrame& frame, std::vector<P2f>& pts);
+};
+
+}  // namespace flv

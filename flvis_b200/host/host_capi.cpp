@@ -3,6 +3,7 @@
 #include <new>
 #include "local_map.h"
 #include "vi_motion.h"
+#include "f2f_tracking.h"
 
 struct flv_localmap { flv::LocalMap impl; flv_localmap(flv_ctx* c, int w, double fx, double fy, double cx, double cy) : impl(c, w, fx, fy, cx, cy) {} };
 
@@ -99,5 +100,67 @@ int flv_vimotion_get_bias(flv_vimotion* vm, double* ab, double* gb) {
   return FLV_OK;
 }
 int flv_vimotion_queue_size(flv_vimotion* vm) { return vm ? (int)vm->impl.states.size() : FLV_ERR_INVALID; }
+
+struct flv_f2f { flv::F2FTracking impl; };
+
+flv_f2f* flv_f2f_create(const flv_f2f_config* c, int device) {
+  if (!c) return nullptr;
+  flv_f2f* f = new (std::nothrow) flv_f2f();
+  if (!f) return nullptr;
+  flv::DepthCamera dc;
+  dc.cam_type = c->cam_type == 0 ? flv::DEPTH_D435 : flv::STEREO_RECT;
+  dc.img_w = c->img_w; dc.img_h = c->img_h;
+  dc.cam0_fx = c->cam0[0]; dc.cam0_fy = c->cam0[1]; dc.cam0_cx = c->cam0[2]; dc.cam0_cy = c->cam0[3];
+  dc.cam1_fx = c->cam1[0]; dc.cam1_fy = c->cam1[1]; dc.cam1_cx = c->cam1[2]; dc.cam1_cy = c->cam1[3];
+  dc.cam_scale_factor = c->depth_scale;
+  for (int i = 0; i < 12; ++i) { dc.P0_[i] = c->P0[i]; dc.P1_[i] = c->P1[i]; }
+  dc.T_cam1_cam0 = se3_from7(c->T_cam1_cam0);
+  if (f->impl.init(dc, se3_from7(c->T_i_c0), c->feature_para, c->vi_para, c->dc_para, c->skip_first_n_imgs, false, device) != FLV_OK) {
+    // keep the object so the caller can read last_error; image_feed will fail
+  }
+  return f;
+}
+void flv_f2f_destroy(flv_f2f* f) { delete f; }
+const char* flv_f2f_last_error(flv_f2f* f) { return f ? f->impl.last_error() : "null"; }
+void flv_f2f_set_ransac_hooks(flv_f2f* f, flv_f2f_fmat_fn fmat, flv_f2f_pnp_fn pnp, void* user) {
+  if (f) f->impl.set_ransac_hooks(fmat, pnp, user);
+}
+int flv_f2f_imu_feed(flv_f2f* f, double t, const double* acc, const double* gyro) {
+  if (!f || !acc || !gyro || !f->impl.vimotion) return FLV_ERR_INVALID;
+  flv::Quat q; flv::Vec3 p, v;
+  f->impl.imu_feed(t, flv::Vec3{acc[0], acc[1], acc[2]}, flv::Vec3{gyro[0], gyro[1], gyro[2]}, q, p, v);
+  return FLV_OK;
+}
+int flv_f2f_image_feed(flv_f2f* f, double t, const uint8_t* img0, const void* img1, int* new_keyframe, int* reset_cmd) {
+  if (!f || !img0 || !img1 || !f->impl.vimotion) return FLV_ERR_INVALID;
+  bool kf = false, rs = false;
+  const int rc = f->impl.image_feed(t, img0, img1, kf, rs);
+  if (new_keyframe) *new_keyframe = kf;
+  if (reset_cmd) *reset_cmd = rs;
+  return rc;
+}
+int flv_f2f_state(flv_f2f* f) { return f ? (int)f->impl.vo_tracking_state : FLV_ERR_INVALID; }
+int flv_f2f_get_frame(flv_f2f* f, double* T_c_w, int64_t* lm_id, double* plane_xy, double* undist_xy, double* p3d_w,
+                      uint8_t* has_3d, uint8_t* is_inlier, int cap) {
+  if (!f || !f->impl.curr_frame) return FLV_ERR_INVALID;
+  const flv::CameraFrame& fr = *f->impl.curr_frame;
+  if (T_c_w) se3_to7(fr.T_c_w, T_c_w);
+  const int n = (int)fr.landmarks.size() < cap ? (int)fr.landmarks.size() : cap;
+  for (int i = 0; i < n; ++i) {
+    const flv::LandMarkInFrame& lm = fr.landmarks[i];
+    if (lm_id) lm_id[i] = lm.lm_id;
+    if (plane_xy) { plane_xy[2 * i] = lm.lm_2d_plane[0]; plane_xy[2 * i + 1] = lm.lm_2d_plane[1]; }
+    if (undist_xy) { undist_xy[2 * i] = lm.lm_2d_undistort[0]; undist_xy[2 * i + 1] = lm.lm_2d_undistort[1]; }
+    if (p3d_w) for (int k = 0; k < 3; ++k) p3d_w[3 * i + k] = lm.lm_3d_w[k];
+    if (has_3d) has_3d[i] = lm.has_3d;
+    if (is_inlier) is_inlier[i] = lm.is_tracking_inlier;
+  }
+  return n;
+}
+int flv_f2f_tracking_counts(flv_f2f* f, int* of, int* fi, int* pnp) {
+  if (!f) return FLV_ERR_INVALID;
+  if (of) *of = f->impl.last_of_inliers; if (fi) *fi = f->impl.last_f_inliers; if (pnp) *pnp = f->impl.last_pnp_inliers;
+  return FLV_OK;
+}
 
 }  // extern "C"

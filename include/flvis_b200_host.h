@@ -41,6 +41,37 @@ int flv_vimotion_rp_compensation(flv_vimotion* vm, double t, double* T_c_w_inout
 int flv_vimotion_get_bias(flv_vimotion* vm, double* acc_bias, double* gyro_bias);
 int flv_vimotion_queue_size(flv_vimotion* vm);
 
+/* ---- flv::F2FTracking <- src/frontend/include/f2f_tracking.h:24-78, src/frontend/f2f_tracking.cpp:5-453 --------
+ * One handle = one camera sequence (private single-stream context).  cam_type: 0 = DEPTH_D435 (img1 = u16 depth),
+ * 1 = STEREO_RECT (img1 = u8 right image).  Poses are [qx qy qz qw tx ty tz]. */
+typedef struct flv_f2f flv_f2f;
+typedef struct {
+  int cam_type, img_w, img_h;
+  double cam0[4];          /* fx fy cx cy */
+  double cam1[4];          /* K1 (stereo) */
+  double depth_scale;
+  double P0[12], P1[12];
+  double T_cam1_cam0[7];
+  double T_i_c0[7];
+  double feature_para[6], vi_para[6], dc_para[3];
+  int skip_first_n_imgs;
+} flv_f2f_config;
+/* RANSAC hooks replacing the host stand-ins (tests inject OpenCV's results through these) */
+typedef int (*flv_f2f_fmat_fn)(void* user, int n, const float* from_xy, const float* to_xy, uint8_t* mask_out);
+typedef int (*flv_f2f_pnp_fn)(void* user, int n, const float* p3d, const float* p2d, const double* K4, int use_guess,
+                              double* T_c_w_inout, int* inlier_idx_out, int* n_inliers_out);
+flv_f2f* flv_f2f_create(const flv_f2f_config* cfg, int device);
+void flv_f2f_destroy(flv_f2f* f);
+const char* flv_f2f_last_error(flv_f2f* f);
+void flv_f2f_set_ransac_hooks(flv_f2f* f, flv_f2f_fmat_fn fmat, flv_f2f_pnp_fn pnp, void* user);
+int flv_f2f_imu_feed(flv_f2f* f, double t, const double* acc, const double* gyro);
+int flv_f2f_image_feed(flv_f2f* f, double t, const uint8_t* img0, const void* img1, int* new_keyframe, int* reset_cmd);
+int flv_f2f_state(flv_f2f* f);     /* 0 UnInit, 1 Tracking, 2 TrackingFail */
+/* landmarks of the current frame (after image_feed): returns the count (<= cap) */
+int flv_f2f_get_frame(flv_f2f* f, double* T_c_w, int64_t* lm_id, double* plane_xy, double* undist_xy, double* p3d_w,
+                      uint8_t* has_3d, uint8_t* is_inlier, int cap);
+int flv_f2f_tracking_counts(flv_f2f* f, int* of_inliers, int* f_inliers, int* pnp_inliers);
+
 #ifdef __cplusplus
 }
 #endif

@@ -64,9 +64,10 @@ def test_depth_innovation_matches_oracle(cam_type):
     gens = [cf.GlibcRand() for _ in range(S)]
     for s, (fr, p1, st, depth) in enumerate(frames):
         n = ns[s]
-        T[s] = fr.T_c_w.to7(); plane[s, :n] = fr.plane; und[s, :n] = fr.undist; p3w[s, :n] = fr.p3d_w; has[s, :n] = fr.has_3d
-        f2[s, :n] = fr.first_2d; fp[s, :n] = np.array([t.to7() for t in fr.first_pose]).reshape(-1, 7)
-        pt1[s, :n] = p1; stt[s, :n] = st
+        T[s] = fr.T_c_w.to7(); plane[s, :n] = fr.plane.reshape(-1, 2); und[s, :n] = fr.undist.reshape(-1, 2)
+        p3w[s, :n] = fr.p3d_w.reshape(-1, 3); has[s, :n] = fr.has_3d
+        f2[s, :n] = np.asarray(fr.first_2d).reshape(-1, 2); fp[s, :n] = np.array([t.to7() for t in fr.first_pose]).reshape(-1, 7)
+        pt1[s, :n] = p1.reshape(-1, 2); stt[s, :n] = st
         for i in range(n):
             dat[s, i] = depth[int(round(fr.plane[i, 1])), int(round(fr.plane[i, 0]))]
         g2 = cf.GlibcRand()

@@ -1,0 +1,143 @@
+"""Frame-by-frame parity of the C++ host pipeline (flv::F2FTracking over the GPU C ABI) with the Python restatement
+of the reference pipeline (oracle/f2f_ref.py).  The two OpenCV RANSAC calls are injected through the tracker's
+hooks (hard part 1): both sides get cv2's masks for the same float inputs, so landmark id
+lists must be bit-exact and poses agree to the fp64 BA tolerance."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from oracle import f2f_ref
+from oracle.vimotion_ref import SE3
+
+pytestmark = pytest.mark.gpu
+
+
+class Cfg(C.Structure):
+    _fields_ = [("cam_type", C.c_int), ("img_w", C.c_int), ("img_h", C.c_int), ("cam0", C.c_double * 4),
+                ("cam1", C.c_double * 4), ("depth_scale", C.c_double), ("P0", C.c_double * 12), ("P1", C.c_double * 12),
+                ("T_cam1_cam0", C.c_double * 7), ("T_i_c0", C.c_double * 7), ("feature_para", C.c_double * 6),
+                ("vi_para", C.c_double * 6), ("dc_para", C.c_double * 3), ("skip_first_n_imgs", C.c_int)]
+
+
+FMAT = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_uint8))
+PNP = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_double), C.c_int,
+                  C.POINTER(C.c_double), C.POINTER(C.c_int), C.POINTER(C.c_int))
+
+
+@FMAT
+def fmat_hook(user, n, a, b, mask):
+    fa = np.ctypeslib.as_array(a, (n, 2)).copy(); fb = np.ctypeslib.as_array(b, (n, 2)).copy()
+    m = f2f_ref.fmat_cv2(fa, fb)
+    for i in range(n):
+        mask[i] = int(m[i])
+    return 0
+
+
+@PNP
+def pnp_hook(user, n, p3d, p2d, K, use_guess, T, inl, ninl):
+    a3 = np.ctypeslib.as_array(p3d, (n, 3)).copy(); a2 = np.ctypeslib.as_array(p2d, (n, 2)).copy()
+    Kt = tuple(K[i] for i in range(4))
+    guess = SE3.from7(np.array([T[i] for i in range(7)])) if use_guess else None
+    Tn, idx = f2f_ref.pnp_cv2(a3, a2, Kt, guess)
+    t7 = Tn.to7()
+    for i in range(7):
+        T[i] = float(t7[i])
+    for i, v in enumerate(idx):
+        inl[i] = int(v)
+    ninl[0] = len(idx)
+    return 0
+
+
+def _setup(lib):
+    lib.flv_f2f_create.restype = C.c_void_p
+    lib.flv_f2f_create.argtypes = [C.POINTER(Cfg), C.c_int]
+    lib.flv_f2f_destroy.argtypes = [C.c_void_p]
+    lib.flv_f2f_last_error.restype = C.c_char_p
+    lib.flv_f2f_last_error.argtypes = [C.c_void_p]
+    lib.flv_f2f_set_ransac_hooks.argtypes = [C.c_void_p, FMAT, PNP, C.c_void_p]
+    lib.flv_f2f_image_feed.argtypes = [C.c_void_p, C.c_double, C.c_void_p, C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int)]
+    lib.flv_f2f_state.argtypes = [C.c_void_p]
+    lib.flv_f2f_get_frame.argtypes = [C.c_void_p] + [C.c_void_p] * 7 + [C.c_int]
+    lib.flv_f2f_tracking_counts.argtypes = [C.c_void_p] + [C.POINTER(C.c_int)] * 3
+
+
+def test_depth_sequence_matches_oracle_frame_by_frame(lib):
+    _setup(lib)
+    K = (384.16455, 384.16455, 320.21445, 238.94403)
+    fpara = [30, 15, 5, 500, 0.01, 15]; vpara = [0.1, 0.01, 0.001, 0.001, 0.5, 0.1]; dpara = [0.98, 40.0, 1.0]
+    n_frames = 12
+    imgs, depths = f2f_ref.make_depth_sequence(n_frames, seed=7)
+    cfg = Cfg(0, 640, 480, (C.c_double * 4)(*K), (C.c_double * 4)(*K), 1000.0, (C.c_double * 12)(), (C.c_double * 12)(),
+              (C.c_double * 7)(0, 0, 0, 1, 0, 0, 0), (C.c_double * 7)(0, 0, 0, 1, 0, 0, 0), (C.c_double * 6)(*fpara),
+              (C.c_double * 6)(*vpara), (C.c_double * 3)(*dpara), 0)
+    h = lib.flv_f2f_create(C.byref(cfg), 0)
+    assert h and lib.flv_f2f_last_error(h) == b"", lib.flv_f2f_last_error(h)
+    lib.flv_f2f_set_ransac_hooks(h, fmat_hook, pnp_hook, None)
+    ref = f2f_ref.F2FTracking("depth", 640, 480, K, fpara, vpara, dpara)
+    cap = 600
+    vp = lambda a: a.ctypes.data_as(C.c_void_p)
+    n_kf = 0
+    for k in range(n_frames):
+        kf = C.c_int(0); rs = C.c_int(0)
+        img = np.ascontiguousarray(imgs[k]); dep = np.ascontiguousarray(depths[k])
+        rc = lib.flv_f2f_image_feed(h, 0.05 * k, vp(img), vp(dep), C.byref(kf), C.byref(rs))
+        assert rc == 0, lib.flv_f2f_last_error(h)
+        rkf, rrs = ref.image_feed(0.05 * k, imgs[k], depths[k])
+        state = {0: "UnInit", 1: "Tracking", 2: "TrackingFail"}[lib.flv_f2f_state(h)]
+        assert state == ref.state and bool(kf.value) == rkf and bool(rs.value) == rrs, (k, state, ref.state)
+        T = np.zeros(7); ids = np.zeros(cap, np.int64); pl = np.zeros((cap, 2)); un = np.zeros((cap, 2)); p3 = np.zeros((cap, 3))
+        has = np.zeros(cap, np.uint8); inl = np.zeros(cap, np.uint8)
+        n = lib.flv_f2f_get_frame(h, vp(T), vp(ids), vp(pl), vp(un), vp(p3), vp(has), vp(inl), cap)
+        cur = ref.curr
+        assert n == len(cur.lms), (k, n, len(cur.lms))
+        assert list(ids[:n]) == [l.lm_id for l in cur.lms]                       # landmark ids + order: bit-exact
+        assert list(inl[:n].astype(bool)) == [bool(l.inlier) for l in cur.lms]
+        assert list(has[:n].astype(bool)) == [bool(l.has_3d) for l in cur.lms]
+        if n:
+            assert np.array_equal(pl[:n], np.array([l.plane for l in cur.lms]))   # tracked pixel positions: bit-exact (LK contract)
+            assert np.abs(p3[:n] - np.array([l.p3d_w for l in cur.lms])).max() <= 1e-6
+        rT = cur.T_c_w.to7()
+        assert np.abs(T[4:] - rT[4:]).max() <= 1e-6                               # per-frame pose: 1e-6 m
+        assert 2 * np.arccos(min(1.0, abs(float(np.dot(T[:4], rT[:4]))))) <= 1e-6
+        if k > 0 and ref.state == "Tracking":
+            of = C.c_int(); fi = C.c_int(); pn = C.c_int()
+            lib.flv_f2f_tracking_counts(h, C.byref(of), C.byref(fi), C.byref(pn))
+            assert (of.value, fi.value, pn.value) == ref.counts
+            assert pn.value >= 30                                                 # the synthetic plane is trackable
+        n_kf += int(rkf)
+    assert ref.state == "Tracking" and n_kf >= 2
+    lib.flv_f2f_destroy(h)
+
+
+def test_builtin_ransac_tracks_without_hooks(lib):
+    """The product's own host RANSAC stand-ins (no OpenCV): the sequence must track with most points as inliers and
+    the recovered camera translation must follow the synthetic motion (12 mm per frame along the plane)."""
+    _setup(lib)
+    K = (384.16455, 384.16455, 320.21445, 238.94403)
+    fpara = [30, 15, 5, 500, 0.01, 15]; vpara = [0.1, 0.01, 0.001, 0.001, 0.5, 0.1]; dpara = [0.98, 40.0, 1.0]
+    imgs, depths = f2f_ref.make_depth_sequence(8, seed=9)
+    cfg = Cfg(0, 640, 480, (C.c_double * 4)(*K), (C.c_double * 4)(*K), 1000.0, (C.c_double * 12)(), (C.c_double * 12)(),
+              (C.c_double * 7)(0, 0, 0, 1, 0, 0, 0), (C.c_double * 7)(0, 0, 0, 1, 0, 0, 0), (C.c_double * 6)(*fpara),
+              (C.c_double * 6)(*vpara), (C.c_double * 3)(*dpara), 0)
+    h = lib.flv_f2f_create(C.byref(cfg), 0)
+    vp = lambda a: a.ctypes.data_as(C.c_void_p)
+    T0 = None
+    for k in range(8):
+        kf = C.c_int(0); rs = C.c_int(0)
+        assert lib.flv_f2f_image_feed(h, 0.05 * k, vp(np.ascontiguousarray(imgs[k])), vp(np.ascontiguousarray(depths[k])),
+                                      C.byref(kf), C.byref(rs)) == 0
+        assert lib.flv_f2f_state(h) == 1
+        T = np.zeros(7)
+        lib.flv_f2f_get_frame(h, vp(T), None, None, None, None, None, None, 0)
+        if k == 0:
+            T0 = T.copy()
+        if k > 0:
+            of = C.c_int(); fi = C.c_int(); pn = C.c_int()
+            lib.flv_f2f_tracking_counts(h, C.byref(of), C.byref(fi), C.byref(pn))
+            assert pn.value >= 0.8 * fi.value >= 0.5 * of.value > 50
+    # camera centre moved ~7 * 12 mm in total
+    c0 = -SE3.from7(T0).inverse().t if False else SE3.from7(T0).inverse().t
+    c7 = SE3.from7(T).inverse().t
+    assert abs(np.linalg.norm(c7 - c0) - 0.012 * 7) < 0.01
+    lib.flv_f2f_destroy(h)
