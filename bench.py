@@ -28,6 +28,7 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+from flvis_b200 import sharding  # noqa: E402
 
 W, H = 752, 480
 NPTS = 480
@@ -54,11 +55,12 @@ MOTION = [(3, 1), (2, -2), (-3, 2), (-2, -1)]     # cumulative motion is periodi
 
 
 def make_streams(n_streams, seed0, n_frames):
+    """Streams with global ids seed0 .. seed0+n_streams-1 (flvis_b200.sharding.stream_seed gives the texture seed)."""
     from oracle import synth
     frames0 = np.empty((n_frames, n_streams, H, W), np.uint8)
     frames1 = np.empty((n_frames, n_streams, H, W), np.uint8)
     for s in range(n_streams):
-        canvas = synth.texture(1000 + seed0 + s, H + 64, W + 128, blur=2)
+        canvas = synth.texture(sharding.stream_seed(seed0 + s), H + 64, W + 128, blur=2)
         ox, oy = 48, 32
         disp = 20 + (s % 7)
         for t in range(n_frames):
@@ -121,7 +123,7 @@ def run_ours(args):
     dev = torch.device("cuda", local_rank)
     S = args.streams
     n_pool = 8                                        # distinct frames per stream in the pool (cycled)
-    f0, f1 = make_streams(S, 100 * rank, n_pool)
+    f0, f1 = make_streams(S, sharding.stream_ids(rank, world, S)[0], n_pool)     # rank r owns streams [r*S, (r+1)*S)
     bench = FrontendBench(S, W, H, MAX_PTS, NPTS, FEATURE_PARA, local_rank, ba_window=BA_WINDOW,
                           kf_every=KF_EVERY, seed=rank)
     bench.load_pool(f0, f1)
@@ -149,10 +151,8 @@ def run_ours(args):
         barrier()
         ms = ev0.elapsed_time(ev1)
         lk_ms, lk_calls = bench.finish_lk_timing()
-        t = torch.tensor([ms], device=dev, dtype=torch.float64)
-        if world > 1:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item()), bench.ctx.launches - launches0, lk_ms, lk_calls
+        ms = sharding.max_over_ranks(ms, dist if world > 1 else None, dev)        # job time = slowest rank
+        return ms, bench.ctx.launches - launches0, lk_ms, lk_calls
 
     sampler = ClockSampler(local_rank) if rank == 0 else None
     if sampler:
@@ -168,7 +168,8 @@ def run_ours(args):
     if rank == 0:
         lk_us = 1e3 * lk_ms / max(lk_calls, 1)
         achieved = LK_BYTES_PER_CALL * S / (lk_us * 1e-6) / 1e9 if lk_us > 0 else 0.0
-        cpu = cpu_baseline(min(S, 8), 6, args) if world == 1 and not args.no_cpu else None
+        # bounded sample of the same workload on every host core: all S streams, 6 frames each
+        cpu = cpu_baseline(min(S, os.cpu_count() or 1), 6, args) if world == 1 and not args.no_cpu else None
         out = {
             "metric": "frames/sec (device-timed), EuRoC-shaped 752x480 stereo, LK frontend + 10-KF local BA",
             "value": frames / (ms_dev * 1e-3), "unit": "frames/s", "n_gpus": world, "steps": args.steps,
@@ -259,7 +260,7 @@ def run_reference(args):
     if rank != 0:
         return
     S = args.streams
-    n_streams = min(S, 16)
+    n_streams = min(S, os.cpu_count() or 1)
     steps = max(1, min(args.steps, 6))
     for _ in range(min(args.warmup, 1)):
         cpu_baseline(min(n_streams, 4), 1, args)

@@ -43,6 +43,7 @@ struct BAArgs {
   int max_poses, max_lms, max_edges;
   unsigned char* ws; size_t ws_stride;
   long long* prof;   // [S][8] cycle counters or nullptr
+  int stage_doubles, stage_offset_doubles;   // Schur staging area inside the dynamic shared memory (0 = not available)
 };
 
 // ---- SE3 helpers (g2o SE3Quat semantics, quaternion stored x,y,z,w) ----------------------------
@@ -116,6 +117,12 @@ __device__ void pose_oplus(double* pose, const double* u) {   // pose <- exp(u) 
   pose[0] = x / nn; pose[1] = y / nn; pose[2] = z / nn; pose[3] = w / nn;
   pose[4] = te[0] + rt[0]; pose[5] = te[1] + rt[1]; pose[6] = te[2] + rt[2];
 }
+
+// W and Y (6x3 blocks per edge) are stored as two 16-byte aligned halves of 9 (+1 pad) doubles: 20 doubles per edge,
+// so rows 0..2 / 3..5 can each be moved with 128-bit accesses.
+#define WOFF(t) ((t) < 9 ? (t) : (t) + 1)
+constexpr int WSTRIDE = 20;
+constexpr int STG_STRIDE = 42;          // doubles per staged member (Ya 20 | Wb 20 | 2 pad: 2-way bank conflicts at most)
 
 struct Cam { double fx, fy, cx, cy; };
 
@@ -332,11 +339,11 @@ __device__ void build_system(const flv_ba_problem& pb, const Cam& cam, const dou
         H[2] += rho1 * (A[0] * A[2] + A[3] * A[5]); H[3] += rho1 * (A[1] * A[1] + A[4] * A[4]);
         H[4] += rho1 * (A[1] * A[2] + A[4] * A[5]); H[5] += rho1 * (A[2] * A[2] + A[5] * A[5]);
         if (sh.pidx[p] >= 0) {
-          double* W = ws.W + 18 * (size_t)e;
+          double* W = ws.W + WSTRIDE * (size_t)e;
 #pragma unroll
           for (int i = 0; i < 6; ++i)
 #pragma unroll
-            for (int j = 0; j < 3; ++j) W[3 * i + j] = rho1 * (B[i] * A[j] + B[6 + i] * A[3 + j]);
+            for (int j = 0; j < 3; ++j) W[WOFF(3 * i + j)] = rho1 * (B[i] * A[j] + B[6 + i] * A[3 + j]);
           const double sr = sqrt(rho1);
           double* Bw = ws.Bw + 12 * (size_t)e;
 #pragma unroll
@@ -402,7 +409,8 @@ __device__ void build_system(const flv_ba_problem& pb, const Cam& cam, const dou
 }
 
 // (H + lambda I) x = b through the Schur complement: S (n x ld, shared, lower triangle used), y, x in shared
-__device__ void solve_system(const flv_ba_problem& pb, double lambda, double* S, double* y, int ld, Ws& ws, Sh& sh) {
+__device__ void solve_system(const flv_ba_problem& pb, double lambda, double* S, double* y, int ld, double* stage, Ws& ws,
+                             Sh& sh) {
   const int L = pb.n_landmarks, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int np = sh.np, n = 6 * np;
   if (!pb.fix_landmarks) {
@@ -421,14 +429,14 @@ __device__ void solve_system(const flv_ba_problem& pb, double lambda, double* S,
         const int p = __ffs(m) - 1; m &= m - 1;
         if (sh.pidx[p] < 0) continue;
         const size_t e = (size_t)ws.eidx[p * L + l];
-        const double* W = ws.W + 18 * e;
-        double* Y = ws.Y + 18 * e;
+        const double* W = ws.W + WSTRIDE * e;
+        double* Y = ws.Y + WSTRIDE * e;
 #pragma unroll
         for (int i = 0; i < 6; ++i) {
-          const double w0 = W[3 * i], w1 = W[3 * i + 1], w2 = W[3 * i + 2];
-          Y[3 * i] = w0 * Di[0] + w1 * Di[1] + w2 * Di[2];
-          Y[3 * i + 1] = w0 * Di[1] + w1 * Di[3] + w2 * Di[4];
-          Y[3 * i + 2] = w0 * Di[2] + w1 * Di[4] + w2 * Di[5];
+          const double w0 = W[WOFF(3 * i)], w1 = W[WOFF(3 * i + 1)], w2 = W[WOFF(3 * i + 2)];
+          Y[WOFF(3 * i)] = w0 * Di[0] + w1 * Di[1] + w2 * Di[2];
+          Y[WOFF(3 * i + 1)] = w0 * Di[1] + w1 * Di[3] + w2 * Di[4];
+          Y[WOFF(3 * i + 2)] = w0 * Di[2] + w1 * Di[4] + w2 * Di[5];
         }
       }
     }
@@ -448,13 +456,56 @@ __device__ void solve_system(const flv_ba_problem& pb, double lambda, double* S,
     for (int i = 0; i < 6; ++i) cf[i] = 0;
     if (!pb.fix_landmarks) {
       const int i0 = sh.pair_off[blk], i1 = sh.pair_off[blk + 1];
+      if (stage) {
+        // 16 members per round: the warp copies their Y_a | W_b blocks (2 x 160 B each) into its shared-memory
+        // staging area with fully coalesced 128-bit loads (every 32-byte sector is requested once; the direct
+        // per-lane 8-byte loads asked for each sector ~3x and made this pass LSU-bound), then computes from there.
+        double* stg = stage + (size_t)warp * 16 * STG_STRIDE;
+        for (int k0 = i0; k0 < i1; k0 += 16) {
+          const int cntm = i1 - k0 < 16 ? i1 - k0 : 16;
+          int ea = 0, eb = 0, ll = 0;
+          if (lane < cntm) { const int* it = ws.pairs + 3 * (size_t)(k0 + lane); ea = it[0]; eb = it[1]; ll = it[2]; }
+#pragma unroll
+          for (int pss = 0; pss < 10; ++pss) {
+            const int c = pss * 32 + lane, mem = c / 20, ch = c - 20 * mem;
+            const int sa = __shfl_sync(FULL, ea, mem), sb = __shfl_sync(FULL, eb, mem);
+            if (mem < cntm) {
+              const double* base = ch < 10 ? ws.Y + WSTRIDE * (size_t)sa : ws.W + WSTRIDE * (size_t)sb;
+              const double2 v = *reinterpret_cast<const double2*>(base + 2 * (ch < 10 ? ch : ch - 10));
+              *reinterpret_cast<double2*>(stg + (size_t)mem * STG_STRIDE + 2 * ch) = v;
+            }
+          }
+          const int myl = __shfl_sync(FULL, ll, mslot);
+          __syncwarp();
+          if (mslot < cntm) {
+            const double* m = stg + (size_t)mslot * STG_STRIDE;
+            double ya[18], wb[9];
+#pragma unroll
+            for (int i = 0; i < 18; ++i) ya[i] = m[WOFF(i)];
+#pragma unroll
+            for (int i = 0; i < 9; ++i) wb[i] = m[20 + 10 * half + i];
+            if (a == b && half == 0) {
+              const double* bl = ws.bl + 3 * (size_t)myl;
+              const double b0 = bl[0], b1 = bl[1], b2 = bl[2];
+#pragma unroll
+              for (int i = 0; i < 6; ++i) cf[i] += ya[3 * i] * b0 + ya[3 * i + 1] * b1 + ya[3 * i + 2] * b2;
+            }
+#pragma unroll
+            for (int i = 0; i < 6; ++i)
+#pragma unroll
+              for (int j = 0; j < 3; ++j)
+                acc[3 * i + j] += ya[3 * i] * wb[3 * j] + ya[3 * i + 1] * wb[3 * j + 1] + ya[3 * i + 2] * wb[3 * j + 2];
+          }
+          __syncwarp();
+        }
+      } else {
       for (int k = i0 + mslot; k < i1; k += 16) {
         const int* it = ws.pairs + 3 * (size_t)k;
-        const double* Ya = ws.Y + 18 * (size_t)it[0];
-        const double* Wb = ws.W + 18 * (size_t)it[1] + 9 * half;      // rows 3h..3h+2 of W_b (6x3, row-major)
+        const double* Ya = ws.Y + WSTRIDE * (size_t)it[0];
+        const double* Wb = ws.W + WSTRIDE * (size_t)it[1] + 10 * half;  // rows 3h..3h+2 of W_b
         double ya[18], wb[9];
 #pragma unroll
-        for (int i = 0; i < 18; ++i) ya[i] = Ya[i];
+        for (int i = 0; i < 18; ++i) ya[i] = Ya[WOFF(i)];
 #pragma unroll
         for (int i = 0; i < 9; ++i) wb[i] = Wb[i];
         if (a == b && half == 0) {
@@ -468,6 +519,7 @@ __device__ void solve_system(const flv_ba_problem& pb, double lambda, double* S,
 #pragma unroll
           for (int j = 0; j < 3; ++j)
             acc[3 * i + j] += ya[3 * i] * wb[3 * j] + ya[3 * i + 1] * wb[3 * j + 1] + ya[3 * i + 2] * wb[3 * j + 2];
+      }
       }
     }
     // reduce over the 16 member slots (lanes of equal parity): xor 2, 4, 8, 16
@@ -571,10 +623,10 @@ __device__ double apply_update(const flv_ba_problem& pb, double lambda, double* 
         const int p = __ffs(m) - 1; m &= m - 1;
         const int pi = sh.pidx[p];
         if (pi < 0) continue;
-        const double* W = ws.W + 18 * (size_t)ws.eidx[p * L + l];
+        const double* W = ws.W + WSTRIDE * (size_t)ws.eidx[p * L + l];
         const double* xp = sh.x + 6 * pi;
 #pragma unroll
-        for (int i = 0; i < 6; ++i) { c0 -= W[3 * i] * xp[i]; c1 -= W[3 * i + 1] * xp[i]; c2 -= W[3 * i + 2] * xp[i]; }
+        for (int i = 0; i < 6; ++i) { c0 -= W[WOFF(3 * i)] * xp[i]; c1 -= W[WOFF(3 * i + 1)] * xp[i]; c2 -= W[WOFF(3 * i + 2)] * xp[i]; }
       }
       const double* Di = ws.Dinv + 6 * (size_t)l;
       const double x0 = Di[0] * c0 + Di[1] * c1 + Di[2] * c2, x1 = Di[1] * c0 + Di[3] * c1 + Di[4] * c2,
@@ -619,14 +671,14 @@ __global__ void __launch_bounds__(BA_THREADS, 1) ba_kernel(BAArgs a) {
     double* d = (double*)(a.ws + (size_t)s * a.ws_stride);
     ws.pbk = d; d += 7 * a.max_poses;
     ws.lbk = d; d += 3 * a.max_lms;
-    ws.W = d; d += 18 * (size_t)a.max_edges;
+    ws.W = d; d += WSTRIDE * (size_t)a.max_edges;
     ws.Bw = d; d += 12 * (size_t)a.max_edges;
     ws.g = d; d += 2 * (size_t)a.max_edges;
     ws.Hll = d; d += 6 * a.max_lms;
     ws.bl = d; d += 3 * a.max_lms;
     ws.Dinv = d; d += 6 * a.max_lms;
     ws.xl = d; d += 3 * a.max_lms;
-    ws.Y = d; d += 18 * (size_t)a.max_edges;
+    ws.Y = d; d += WSTRIDE * (size_t)a.max_edges;
     ws.eidx = (int*)d;
     ws.lmask = (unsigned*)(ws.eidx + (size_t)a.max_poses * a.max_lms);
     ws.plist = (int*)(ws.lmask + a.max_lms);
@@ -653,6 +705,8 @@ __global__ void __launch_bounds__(BA_THREADS, 1) ba_kernel(BAArgs a) {
     const int n = 6 * sh.np, ld = n + 1;
     double* S = dyn;
     double* y = dyn + (size_t)n * ld;
+    // staging area of the Schur pass sits behind S | y when the launch reserved room for it (a.stage_doubles > 0)
+    double* stage = a.stage_doubles ? dyn + a.stage_offset_doubles : nullptr;
     double ni = 2;
     for (int it = 0; it < iters; ++it) {
       double currentChi = robust_chi2(pb, cam, poses, lms, ep, el, uv, act, delta, sh.red);
@@ -674,7 +728,7 @@ __global__ void __launch_bounds__(BA_THREADS, 1) ba_kernel(BAArgs a) {
       double rho = 0;
       int qmax = 0;
       do {
-        solve_system(pb, lambda, S, y, ld, ws, sh);
+        solve_system(pb, lambda, S, y, ld, stage, ws, sh);
         const int ok2 = !sh.fail;
         double scale = 0, tempChi;
         if (ok2) {
@@ -728,16 +782,24 @@ __global__ void __launch_bounds__(BA_THREADS, 1) ba_kernel(BAArgs a) {
 }
 
 size_t ws_stride_bytes(int max_poses, int max_lms, int max_edges) {
-  size_t d = 7 * (size_t)max_poses + 3 * (size_t)max_lms + (18 + 18 + 12 + 2) * (size_t)max_edges + 6 * (size_t)max_lms +
+  size_t d = 7 * (size_t)max_poses + 3 * (size_t)max_lms + (2 * WSTRIDE + 12 + 2) * (size_t)max_edges + 6 * (size_t)max_lms +
              3 * (size_t)max_lms + 6 * (size_t)max_lms + 3 * (size_t)max_lms;
   size_t ints = (size_t)max_poses * max_lms + max_lms + max_edges + 3 * pair_capacity(max_poses, max_edges);
   size_t b = d * 8 + ints * 4;
   return (b + 255) & ~(size_t)255;
 }
 
-size_t ba_dyn_smem(int nfree) {
+size_t ba_sys_doubles(int nfree) {
   const size_t n = 6 * (size_t)nfree;
-  return (n * (n + 1) + n + 8) * 8;
+  return ((n * (n + 1) + n + 8) + 1) & ~(size_t)1;          // S | y, rounded to 16 bytes
+}
+constexpr size_t BA_STAGE_DOUBLES = (size_t)BA_WARPS * 16 * STG_STRIDE;
+// dynamic shared memory of a launch: the reduced system plus, when it still fits next to the static state, the staging area
+size_t ba_dyn_smem(int nfree, bool* with_stage) {
+  const size_t sys = ba_sys_doubles(nfree) * 8, stg = BA_STAGE_DOUBLES * 8;
+  const bool fits = sys + stg + sizeof(Sh) + 1024 <= 227 * 1024;
+  if (with_stage) *with_stage = fits;
+  return sys + (fits ? stg : 0);
 }
 
 }  // namespace
@@ -763,7 +825,7 @@ int flv_ba_reserve(flv_ctx* ctx, int max_poses, int max_landmarks, int max_edges
   ctx->ba_ws_bytes = total;
   ctx->ba_max_poses = max_poses; ctx->ba_max_lms = max_landmarks; ctx->ba_max_edges = max_edges;
   int nfree = max_poses < BA_MAX_FREE ? max_poses : BA_MAX_FREE;
-  size_t smem = ba_dyn_smem(nfree);
+  size_t smem = ba_dyn_smem(nfree, nullptr);
   FLV_CUDA(ctx, cudaFuncSetAttribute(ba_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   return FLV_OK;
 }
@@ -787,7 +849,10 @@ int flv_ba_optimize(flv_ctx* ctx, int n_streams, const flv_ba_problem* problems,
   a.prm = *prm; a.max_poses = MP; a.max_lms = ML; a.max_edges = ME;
   a.ws = (unsigned char*)ctx->ba_ws + stride * slot0; a.ws_stride = stride;
   const int nfree = MP < BA_MAX_FREE ? MP : BA_MAX_FREE;
-  const size_t smem = ba_dyn_smem(nfree);
+  bool with_stage = false;
+  const size_t smem = ba_dyn_smem(nfree, &with_stage);
+  a.stage_doubles = with_stage ? (int)BA_STAGE_DOUBLES : 0;
+  a.stage_offset_doubles = (int)ba_sys_doubles(nfree);
   const size_t S = n_streams;
   cudaStream_t stream = ctx->ba_stream_set ? ctx->ba_stream : ctx->stream;
   if (mem == FLV_MEM_DEVICE) {
