@@ -254,7 +254,7 @@ class Context:
         self._chk(self.lib.flv_set_ba_stream(self.h, C.c_void_p(cuda_stream_ptr), 1 if enable else 0))
 
     def ba_profile(self, stream):
-        out = np.zeros(8, np.int64)
+        out = np.zeros(16, np.int64)
         self._chk(self.lib.flv_ba_profile(self.h, stream, _ptr(out)))
         return out
 

@@ -12,15 +12,16 @@
 //   callers                src/backend/vo_localmap.cpp:292-319 (12, cull chi2>3, 8),
 //                          src/processing/optimize_in_frame.cpp:64-80 (2, cull, <10 edges => fail, 2)
 //
-// Data layout (per stream, fp64, global memory that stays L2-resident; S/b/x in shared memory):
-//   eidx[p][l]   edge id observing landmark l from pose p (or -1): built once per optimize() call.
-//   lmask[l]     bitmask of poses observing l (P <= 32).
-//   W[e][6][3]   rho' * B^T A  (pose-landmark Hessian block of edge e).
-//   Hll[l][6], bl[l][3], Dinv[l][6], xl[l][3];  Hd[pi][21], bp[6 pi] (shared).
+// Data layout (per stream, fp64; global workspace stays L2-resident, S/b/x + one landmark chunk in shared memory):
+//   active edges get SLOTS ordered (landmark chunk, pose, landmark); every per-edge quantity is a structure-of-arrays
+//   plane indexed by slot (W[18][ME], Bw[12][ME], g[2][ME], hl[6][ME], bb[3][ME], uvs[2][ME]), every per-landmark
+//   quantity a plane indexed by landmark (Hll[6][ML], bl[3][ML], Dinv[6][ML], Dv[3][ML]) -> all passes are coalesced.
+//   tab[p][l] = slot of edge (p,l); lmask[l] = poses observing l (P <= 32); Hd[pi][21], bp[6 pi] in shared memory.
 // Passes per LM trial:
-//   build   thread per landmark (Hll, bl, W) ; warp per pose (Hpp diagonal blocks, bp)
-//   Schur   warp per pose pair (a<=b): members = landmarks seen by both (bitmask test + warp queue),
-//           lane-private 6x6 accumulators, shuffle tree reduction, one writer per block of S
+//   build   thread per slot (residual, Jacobians, W, Bw, g, Hll/bl shares); thread per landmark (Hll, bl sums);
+//           warp per (pose, part) (Hpp diagonal blocks, bp)
+//   Schur   per chunk: stage W planes + Dinv + Dinv*bl in shared memory (coalesced), then warp per pose pair,
+//           two lanes per member landmark, lane-private accumulators, shuffle tree, one writer per block of S
 //   solve   dense Cholesky of the reduced camera system in shared memory (n = 6*(free poses) <= 144)
 //   update  thread per landmark (back-substitution), thread per pose (exp map), chi2 block reduction
 // Algorithmic bytes: build 168E+392P+120L, Schur 144E+96L+288Pf^2+48Pf per trial.
@@ -43,7 +44,7 @@ struct BAArgs {
   int max_poses, max_lms, max_edges;
   unsigned char* ws; size_t ws_stride;
   long long* prof;   // [S][8] cycle counters or nullptr
-  int stage_doubles, stage_offset_doubles;   // Schur staging area inside the dynamic shared memory (0 = not available)
+  int dyn_doubles;   // dynamic shared memory of the launch, in doubles
 };
 
 // ---- SE3 helpers (g2o SE3Quat semantics, quaternion stored x,y,z,w) ----------------------------
@@ -118,12 +119,6 @@ __device__ void pose_oplus(double* pose, const double* u) {   // pose <- exp(u) 
   pose[4] = te[0] + rt[0]; pose[5] = te[1] + rt[1]; pose[6] = te[2] + rt[2];
 }
 
-// W and Y (6x3 blocks per edge) are stored as two 16-byte aligned halves of 9 (+1 pad) doubles: 20 doubles per edge,
-// so rows 0..2 / 3..5 can each be moved with 128-bit accesses.
-#define WOFF(t) ((t) < 9 ? (t) : (t) + 1)
-constexpr int WSTRIDE = 20;
-constexpr int STG_STRIDE = 42;          // doubles per staged member (Ya 20 | Wb 20 | 2 pad: 2-way bank conflicts at most)
-
 struct Cam { double fx, fy, cx, cy; };
 
 // residual r (2), optional A = d r / d point (2x3), B = d r / d pose (2x6).  One fp64 division per edge:
@@ -182,46 +177,81 @@ __device__ double block_max(double v, double* red) {
   return t;
 }
 
+
 constexpr int BA_MAX_PAIRS = BA_MAX_FREE * (BA_MAX_FREE + 1) / 2;   // 300
+constexpr int BA_MAX_CHUNKS = 128;
+constexpr int BA_CHUNK_PLANES = 18 + 6 + 3;   // W (6x3) per slot, Dinv (sym 3x3) + Dinv*bl per landmark
+constexpr int BA_MAX_CAP = 1023;              // chunk-local positions are packed 10 bits each
 
 struct Sh {   // fixed-size shared state
   double red[BA_WARPS];
   double Hd[BA_MAX_FREE][21];
-  double part[2 * BA_MAX_FREE][27];     // pose-pass partial sums (two halves per pose)
+  double part[2 * BA_MAX_FREE][27];     // pose-pass partial sums
   double bp[6 * BA_MAX_FREE];
   double x[6 * BA_MAX_FREE];
   double piv;
   int pidx[BA_MAX_POSES];
   int pose_of[BA_MAX_FREE];
   int pcount[BA_MAX_POSES];
-  int pstart[BA_MAX_POSES + 1];
-  int pair_off[BA_MAX_PAIRS + 1];
-  int np, fail, nact, overflow;
-  long long prof[8], tlast;   // cycle counters: 0 chi2, 1 build, 2 schur, 3 cholesky, 4 substitution, 5 update, 6 setup
+  int chunk_lb[BA_MAX_CHUNKS + 1];      // landmark range of a chunk
+  int chunk_sb[BA_MAX_CHUNKS + 1];      // slot range of a chunk
+  int scan[BA_WARPS];
+  unsigned char pair_a[BA_MAX_PAIRS], pair_b[BA_MAX_PAIRS];
+  int np, fail, nact, overflow, nch, cap, capq;
+  long long prof[16], tlast;  // cycle counters: 0 chi2, 1 build (pose pass), 2 schur (pair products), 3 cholesky, 4 substitution,
+                              // 5 update, 6 setup, 7 -, 8 schur init + Dinv, 9 schur chunk staging, 10 build edge pass, 11 build landmark pass
 };
 
 __device__ __forceinline__ void mark(Sh& sh, int slot) {
   if (threadIdx.x == 0) { const long long now = clock64(); sh.prof[slot] += now - sh.tlast; sh.tlast = now; }
 }
 
-struct Ws {   // per-stream global workspace views
-  double *pbk, *lbk, *W, *Y, *Bw, *g, *Hll, *bl, *Dinv, *xl;
-  int *eidx; unsigned* lmask; int* plist; int* pairs; int pair_cap;
+// per-stream global workspace views.  "slot" arrays are structure-of-arrays planes with stride ME (max edges),
+// landmark arrays planes with stride ML: consecutive threads touch consecutive addresses in every pass.
+struct Ws {
+  double *pbk, *lbk;
+  double *W, *Bw, *g, *hl, *bb, *uvs;       // [18|12|2|6|3|2][ME]
+  double *Hll, *bl, *Dinv, *Dv;             // [6|3|6|3][ML]
+  int *tab;                                 // [P][L]: edge id during setup, then slot of edge (p,l) or -1
+  unsigned* lmask;                          // [L]
+  int *slot_e, *slot_pl;                    // [ME]: edge id, p | l << 8
+  int *lw, *lstart;                         // [L+1] exclusive prefixes (chunk weights, edge counts)
+  int *cp_off;                              // [nch][P+1] slot offsets of (chunk, pose) runs
+  int *poff;                                // [nch*nblk + 1] member-list offsets of (chunk, pose pair)
+  int *pairs;                               // packed members: pos_a | pos_b << 10 | lpos << 20 (chunk-local)
+  int pair_cap, ME, ML;
 };
 
 __device__ __forceinline__ int sym21(int i, int j) {   // index into upper-triangular 6x6 (i<=j)
   return i * 6 - (i * (i - 1)) / 2 + (j - i);
 }
-__device__ __forceinline__ void pair_of(int blk, int np, int& a, int& b) {
-  a = 0;
-  int rem = blk;
-  while (rem >= np - a) { rem -= np - a; ++a; }
-  b = a + rem;
+
+// in-place exclusive prefix sum of a[0..n) (global ints), a[n] = total.  Deterministic; all threads call it.
+__device__ void block_exclusive_scan(int* a, int n, Sh& sh) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int seg = (n + BA_THREADS - 1) / BA_THREADS;
+  const int lo = min(tid * seg, n), hi = min(lo + seg, n);
+  int sum = 0;
+  for (int i = lo; i < hi; ++i) sum += a[i];
+  int inc = sum;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(FULL, inc, o); if (lane >= o) inc += t; }
+  __syncthreads();
+  if (lane == 31) sh.scan[warp] = inc;
+  __syncthreads();
+  int base = 0;
+#pragma unroll
+  for (int w = 0; w < BA_WARPS; ++w) if (w < warp) base += sh.scan[w];
+  int run = base + inc - sum;
+  for (int i = lo; i < hi; ++i) { const int v = a[i]; a[i] = run; run += v; }
+  if (tid == BA_THREADS - 1) a[n] = base + inc;
+  __syncthreads();
 }
 
-__device__ double robust_chi2(const flv_ba_problem& pb, const Cam& cam, const double* poses, const double* lms,
-                              const int* ep, const int* el, const double* uv, const uint8_t* act, double delta,
-                              double* red) {
+// chi2 over the edge arrays (used outside the LM loop, where no slot tables are required to be valid)
+__device__ double robust_chi2_edges(const flv_ba_problem& pb, const Cam& cam, const double* poses, const double* lms,
+                                    const int* ep, const int* el, const double* uv, const uint8_t* act, double delta,
+                                    double* red) {
   double acc = 0;
   const double d2 = delta * delta;
   for (int e = threadIdx.x; e < pb.n_edges; e += BA_THREADS) {
@@ -234,11 +264,29 @@ __device__ double robust_chi2(const flv_ba_problem& pb, const Cam& cam, const do
   return block_sum(acc, red);
 }
 
-// active sets + lookup tables (sparse_optimizer.cpp:168-272 semantics); built once per optimize() call:
-//   eidx[p][l], lmask[l]; per-pose edge lists (landmark order); per pose-pair member lists (landmark order).
-__device__ void setup_active(const flv_ba_problem& pb, const int* ep, const int* el, const uint8_t* act, Ws& ws, Sh& sh) {
+// chi2 over the active slots (inside the LM loop): coalesced reads of the slot tables
+__device__ double robust_chi2(const Cam& cam, const double* poses, const double* lms, double delta, Ws& ws, Sh& sh) {
+  double acc = 0;
+  const double d2 = delta * delta;
+  for (int s = threadIdx.x; s < sh.nact; s += BA_THREADS) {
+    const int pl = ws.slot_pl[s];
+    const double uv[2] = {ws.uvs[s], ws.uvs[ws.ME + s]};
+    double r[2];
+    edge_eval<false>(poses + 7 * (pl & 255), lms + 3 * (size_t)(pl >> 8), uv, cam, r, nullptr, nullptr);
+    const double c = r[0] * r[0] + r[1] * r[1];
+    acc += (c <= d2) ? c : 2 * sqrt(c) * delta - d2;
+  }
+  return block_sum(acc, sh.red);
+}
+
+// Active sets + lookup tables (sparse_optimizer.cpp:168-272 semantics), built once per optimize() phase.
+// Edges get "slots" ordered (chunk of landmarks, pose, landmark): a chunk is a run of consecutive landmarks whose
+// edges fit the shared-memory staging area of the Schur pass; inside a chunk the edges of one pose are contiguous
+// and sorted by landmark, so both the per-landmark and the per-pose passes read the planes nearly sequentially.
+__device__ void setup_active(const flv_ba_problem& pb, const int* ep, const int* el, const double* uv,
+                             const uint8_t* act, int chunk_area_doubles, Ws& ws, Sh& sh) {
   const int P = pb.n_poses, L = pb.n_landmarks, E = pb.n_edges, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  for (int i = tid; i < P * L; i += BA_THREADS) ws.eidx[i] = -1;
+  for (int i = tid; i < P * L; i += BA_THREADS) ws.tab[i] = -1;
   for (int i = tid; i < L; i += BA_THREADS) ws.lmask[i] = 0u;
   if (tid < BA_MAX_POSES) sh.pcount[tid] = 0;
   if (tid == 0) sh.overflow = 0;
@@ -246,7 +294,7 @@ __device__ void setup_active(const flv_ba_problem& pb, const int* ep, const int*
   for (int e = tid; e < E; e += BA_THREADS) {
     if (!act[e]) continue;
     const int p = ep[e], l = el[e];
-    ws.eidx[p * L + l] = e;
+    ws.tab[p * L + l] = e;
     atomicOr(&ws.lmask[l], 1u << p);
     atomicAdd(&sh.pcount[p], 1);
   }
@@ -254,144 +302,216 @@ __device__ void setup_active(const flv_ba_problem& pb, const int* ep, const int*
   if (tid == 0) {
     int np = 0, nact = 0;
     for (int p = 0; p < P; ++p) {
-      sh.pstart[p] = nact;
       nact += sh.pcount[p];
-      if (p != pb.fixed_pose && sh.pcount[p] > 0) { sh.pidx[p] = np; sh.pose_of[np] = p; ++np; }
+      if (p != pb.fixed_pose && sh.pcount[p] > 0) { sh.pidx[p] = np < BA_MAX_FREE ? np : -1; if (np < BA_MAX_FREE) sh.pose_of[np] = p; ++np; }
       else sh.pidx[p] = -1;
     }
-    sh.pstart[P] = nact;
     sh.np = np; sh.nact = nact;
+    // staging capacity of the Schur pass: what the reduced system leaves of the dynamic shared memory
+    const int npc = np < BA_MAX_FREE ? np : BA_MAX_FREE;
+    const int n = 6 * npc;
+    int cap = (chunk_area_doubles - (n * (n + 1) + n + 8)) / BA_CHUNK_PLANES;
+    cap = cap > BA_MAX_CAP ? BA_MAX_CAP : cap;
+    sh.cap = cap; sh.capq = cap - P;
   }
   __syncthreads();
-  // per-pose edge lists in landmark order (deterministic): warp per pose, ballot compaction
-  for (int p = warp; p < P; p += BA_WARPS) {
-    int base = sh.pstart[p];
-    for (int l0 = 0; l0 < L; l0 += 32) {
+  if (sh.np > BA_MAX_FREE) return;
+  if (sh.capq < 32 && !pb.fix_landmarks) { if (tid == 0) sh.overflow = 2; __syncthreads(); return; }
+  // prefixes over landmarks: edge counts (slot bases) and chunk weights max(count, 1) (bounds landmarks per chunk too)
+  for (int l = tid; l < L; l += BA_THREADS) {
+    const int c = __popc(ws.lmask[l]);
+    ws.lstart[l] = c; ws.lw[l] = c > 0 ? c : 1;
+  }
+  __syncthreads();
+  block_exclusive_scan(ws.lstart, L, sh);
+  block_exclusive_scan(ws.lw, L, sh);
+  // chunk of landmark l = lw[l] / capq: a landmark has <= P edges, so a chunk holds < capq + P = cap weight
+  const int capq = pb.fix_landmarks ? 0x3fffffff : sh.capq;
+  if (tid == 0) { sh.nch = L > 0 ? ws.lw[L - 1] / capq + 1 : 0; }
+  __syncthreads();
+  const int nch = sh.nch;
+  if (nch > BA_MAX_CHUNKS) { if (tid == 0) sh.overflow = 3; __syncthreads(); return; }
+  for (int l = tid; l < L; l += BA_THREADS) {
+    const int c = ws.lw[l] / capq;
+    if (l == 0 || ws.lw[l - 1] / capq != c) { sh.chunk_lb[c] = l; sh.chunk_sb[c] = ws.lstart[l]; }
+  }
+  if (tid == 0) { sh.chunk_lb[nch] = L; sh.chunk_sb[nch] = sh.nact; }
+  __syncthreads();
+  // (chunk, pose) run lengths -> offsets
+  const int P1 = P + 1;
+  for (int task = warp; task < nch * P; task += BA_WARPS) {
+    const int ch = task / P, p = task - ch * P;
+    const int lb = sh.chunk_lb[ch], le = sh.chunk_lb[ch + 1];
+    int cnt = 0;
+    for (int l0 = lb; l0 < le; l0 += 32) {
       const int l = l0 + lane;
-      const int e = l < L ? ws.eidx[p * L + l] : -1;
-      const unsigned bal = __ballot_sync(FULL, e >= 0);
-      if (e >= 0) ws.plist[base + __popc(bal & ((1u << lane) - 1))] = e;
+      cnt += __popc(__ballot_sync(FULL, l < le && ((ws.lmask[l] >> p) & 1u)));
+    }
+    if (lane == 0) ws.cp_off[ch * P1 + p] = cnt;
+  }
+  __syncthreads();
+  for (int ch = tid; ch < nch; ch += BA_THREADS) {
+    int run = sh.chunk_sb[ch];
+    for (int p = 0; p < P; ++p) { const int c = ws.cp_off[ch * P1 + p]; ws.cp_off[ch * P1 + p] = run; run += c; }
+    ws.cp_off[ch * P1 + P] = run;
+  }
+  __syncthreads();
+  // slot assignment (deterministic: ballot compaction in landmark order)
+  for (int task = warp; task < nch * P; task += BA_WARPS) {
+    const int ch = task / P, p = task - ch * P;
+    const int lb = sh.chunk_lb[ch], le = sh.chunk_lb[ch + 1];
+    int base = ws.cp_off[ch * P1 + p];
+    for (int l0 = lb; l0 < le; l0 += 32) {
+      const int l = l0 + lane;
+      const bool has = l < le && ((ws.lmask[l] >> p) & 1u);
+      const unsigned bal = __ballot_sync(FULL, has);
+      if (has) {
+        const int s = base + __popc(bal & ((1u << lane) - 1));
+        const int e = ws.tab[p * L + l];
+        ws.slot_e[s] = e; ws.slot_pl[s] = p | (l << 8);
+        ws.uvs[s] = uv[2 * (size_t)e]; ws.uvs[ws.ME + s] = uv[2 * (size_t)e + 1];
+        ws.tab[p * L + l] = s;
+      }
       base += __popc(bal);
     }
   }
-  if (pb.fix_landmarks || sh.np > BA_MAX_FREE) { __syncthreads(); return; }
-  // pose-pair member lists: count, prefix, fill (two scans over lmask)
+  __syncthreads();
+  if (pb.fix_landmarks) return;
+  // pose-pair member lists per chunk: count, prefix, fill
   const int np = sh.np, nblk = np * (np + 1) / 2;
-  for (int blk = warp; blk < nblk; blk += BA_WARPS) {
-    int a, b; pair_of(blk, np, a, b);
-    const unsigned need = (1u << sh.pose_of[a]) | (1u << sh.pose_of[b]);
+  for (int blk = tid; blk < nblk; blk += BA_THREADS) {
+    int a = 0, rem = blk;
+    while (rem >= np - a) { rem -= np - a; ++a; }
+    sh.pair_a[blk] = (unsigned char)a; sh.pair_b[blk] = (unsigned char)(a + rem);
+  }
+  __syncthreads();
+  for (int task = warp; task < nch * nblk; task += BA_WARPS) {
+    const int ch = task / nblk, blk = task - ch * nblk;
+    const unsigned need = (1u << sh.pose_of[sh.pair_a[blk]]) | (1u << sh.pose_of[sh.pair_b[blk]]);
+    const int lb = sh.chunk_lb[ch], le = sh.chunk_lb[ch + 1];
     int cnt = 0;
-    for (int l0 = 0; l0 < L; l0 += 32) {
+    for (int l0 = lb; l0 < le; l0 += 32) {
       const int l = l0 + lane;
-      cnt += __popc(__ballot_sync(FULL, l < L && (ws.lmask[l] & need) == need));
+      cnt += __popc(__ballot_sync(FULL, l < le && (ws.lmask[l] & need) == need));
     }
-    if (lane == 0) sh.pair_off[blk + 1] = cnt;
+    if (lane == 0) ws.poff[task] = cnt;
   }
   __syncthreads();
-  if (tid == 0) {
-    sh.pair_off[0] = 0;
-    for (int i = 0; i < nblk; ++i) sh.pair_off[i + 1] += sh.pair_off[i];
-    if (sh.pair_off[nblk] > ws.pair_cap) sh.overflow = 1;
-  }
-  __syncthreads();
-  if (sh.overflow) return;
-  for (int blk = warp; blk < nblk; blk += BA_WARPS) {
-    int a, b; pair_of(blk, np, a, b);
-    const int pa = sh.pose_of[a], pb_ = sh.pose_of[b];
+  block_exclusive_scan(ws.poff, nch * nblk, sh);
+  if (ws.poff[nch * nblk] > ws.pair_cap) { if (tid == 0) sh.overflow = 1; __syncthreads(); return; }
+  for (int task = warp; task < nch * nblk; task += BA_WARPS) {
+    const int ch = task / nblk, blk = task - ch * nblk;
+    const int pa = sh.pose_of[sh.pair_a[blk]], pb_ = sh.pose_of[sh.pair_b[blk]];
     const unsigned need = (1u << pa) | (1u << pb_);
-    int base = sh.pair_off[blk];
-    for (int l0 = 0; l0 < L; l0 += 32) {
+    const int lb = sh.chunk_lb[ch], le = sh.chunk_lb[ch + 1], sb = sh.chunk_sb[ch];
+    int base = ws.poff[task];
+    for (int l0 = lb; l0 < le; l0 += 32) {
       const int l = l0 + lane;
-      const bool mem = l < L && (ws.lmask[l] & need) == need;
+      const bool mem = l < le && (ws.lmask[l] & need) == need;
       const unsigned bal = __ballot_sync(FULL, mem);
-      if (mem) {
-        int* it = ws.pairs + 3 * (size_t)(base + __popc(bal & ((1u << lane) - 1)));
-        it[0] = ws.eidx[pa * L + l]; it[1] = ws.eidx[pb_ * L + l]; it[2] = l;
-      }
+      if (mem)
+        ws.pairs[base + __popc(bal & ((1u << lane) - 1))] =
+            (ws.tab[pa * L + l] - sb) | ((ws.tab[pb_ * L + l] - sb) << 10) | ((l - lb) << 20);
       base += __popc(bal);
     }
   }
   __syncthreads();
 }
 
+// Linearisation.  Pass A: thread per slot (edge): residual, Jacobians, W = rho' B^T A, Bw = sqrt(rho') B,
+// g = -sqrt(rho') r and the edge's share of Hll / bl.  Pass B: thread per landmark sums the shares (pose order).
+// Pass C: warp per (free pose, part of its slot runs): Hpp diagonal block and bp.
 __device__ void build_system(const flv_ba_problem& pb, const Cam& cam, const double* poses, const double* lms,
-                             const int* el, const double* uv, double delta, Ws& ws, Sh& sh) {
-  const int L = pb.n_landmarks, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+                             double delta, Ws& ws, Sh& sh) {
+  const int P = pb.n_poses, L = pb.n_landmarks, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int ME = ws.ME, ML = ws.ML;
   const double d2 = delta * delta;
   if (!pb.fix_landmarks) {
-    // thread per landmark: Hll, bl, and per edge W = rho' B^T A, Bw = sqrt(rho') B, g = -sqrt(rho') r
+    for (int s = tid; s < sh.nact; s += BA_THREADS) {
+      const int pl = ws.slot_pl[s], p = pl & 255;
+      const double uv[2] = {ws.uvs[s], ws.uvs[ME + s]};
+      double r[2], A[6], B[12];
+      edge_eval<true>(poses + 7 * p, lms + 3 * (size_t)(pl >> 8), uv, cam, r, A, B);
+      const double c = r[0] * r[0] + r[1] * r[1];
+      const double rho1 = (c <= d2) ? 1.0 : delta / sqrt(c);
+      const double o0 = -r[0] * rho1, o1 = -r[1] * rho1;
+#pragma unroll
+      for (int i = 0; i < 3; ++i) ws.bb[i * ME + s] = A[i] * o0 + A[3 + i] * o1;
+      ws.hl[0 * ME + s] = rho1 * (A[0] * A[0] + A[3] * A[3]); ws.hl[1 * ME + s] = rho1 * (A[0] * A[1] + A[3] * A[4]);
+      ws.hl[2 * ME + s] = rho1 * (A[0] * A[2] + A[3] * A[5]); ws.hl[3 * ME + s] = rho1 * (A[1] * A[1] + A[4] * A[4]);
+      ws.hl[4 * ME + s] = rho1 * (A[1] * A[2] + A[4] * A[5]); ws.hl[5 * ME + s] = rho1 * (A[2] * A[2] + A[5] * A[5]);
+      if (sh.pidx[p] >= 0) {
+#pragma unroll
+        for (int i = 0; i < 6; ++i)
+#pragma unroll
+          for (int j = 0; j < 3; ++j) ws.W[(3 * i + j) * ME + s] = rho1 * (B[i] * A[j] + B[6 + i] * A[3 + j]);
+        const double sr = sqrt(rho1);
+#pragma unroll
+        for (int i = 0; i < 12; ++i) ws.Bw[i * ME + s] = sr * B[i];
+        ws.g[s] = -sr * r[0]; ws.g[ME + s] = -sr * r[1];
+      }
+    }
+    __syncthreads();
+    mark(sh, 10);
     for (int l = tid; l < L; l += BA_THREADS) {
       unsigned m = ws.lmask[l];
       if (!m) continue;
       double H[6] = {0, 0, 0, 0, 0, 0}, b[3] = {0, 0, 0};
-      const double X[3] = {lms[3 * l], lms[3 * l + 1], lms[3 * l + 2]};
       while (m) {
         const int p = __ffs(m) - 1; m &= m - 1;
-        const int e = ws.eidx[p * L + l];
-        double r[2], A[6], B[12];
-        edge_eval<true>(poses + 7 * p, X, uv + 2 * e, cam, r, A, B);
-        const double c = r[0] * r[0] + r[1] * r[1];
-        const double rho1 = (c <= d2) ? 1.0 : delta / sqrt(c);
-        const double o0 = -r[0] * rho1, o1 = -r[1] * rho1;
+        const int s = ws.tab[p * L + l];
 #pragma unroll
-        for (int i = 0; i < 3; ++i) b[i] += A[i] * o0 + A[3 + i] * o1;
-        H[0] += rho1 * (A[0] * A[0] + A[3] * A[3]); H[1] += rho1 * (A[0] * A[1] + A[3] * A[4]);
-        H[2] += rho1 * (A[0] * A[2] + A[3] * A[5]); H[3] += rho1 * (A[1] * A[1] + A[4] * A[4]);
-        H[4] += rho1 * (A[1] * A[2] + A[4] * A[5]); H[5] += rho1 * (A[2] * A[2] + A[5] * A[5]);
-        if (sh.pidx[p] >= 0) {
-          double* W = ws.W + WSTRIDE * (size_t)e;
+        for (int i = 0; i < 6; ++i) H[i] += ws.hl[i * ME + s];
 #pragma unroll
-          for (int i = 0; i < 6; ++i)
-#pragma unroll
-            for (int j = 0; j < 3; ++j) W[WOFF(3 * i + j)] = rho1 * (B[i] * A[j] + B[6 + i] * A[3 + j]);
-          const double sr = sqrt(rho1);
-          double* Bw = ws.Bw + 12 * (size_t)e;
-#pragma unroll
-          for (int i = 0; i < 12; ++i) Bw[i] = sr * B[i];
-          ws.g[2 * (size_t)e] = -sr * r[0]; ws.g[2 * (size_t)e + 1] = -sr * r[1];
-        }
+        for (int i = 0; i < 3; ++i) b[i] += ws.bb[i * ME + s];
       }
 #pragma unroll
-      for (int i = 0; i < 6; ++i) ws.Hll[6 * (size_t)l + i] = H[i];
+      for (int i = 0; i < 6; ++i) ws.Hll[i * ML + l] = H[i];
 #pragma unroll
-      for (int i = 0; i < 3; ++i) ws.bl[3 * (size_t)l + i] = b[i];
+      for (int i = 0; i < 3; ++i) ws.bl[i * ML + l] = b[i];
     }
     __syncthreads();
+    mark(sh, 11);
   }
-  // pose diagonal blocks: task = (free pose, half of its edge list); lanes stride over the list
-  for (int task = warp; task < 2 * sh.np; task += BA_WARPS) {
-    const int pi = task >> 1, p = sh.pose_of[pi];
-    const int b0 = sh.pstart[p], cnt = sh.pstart[p + 1] - b0;
-    const int mid = (cnt + 1) >> 1;
-    const int lo = (task & 1) ? mid : 0, hi = (task & 1) ? cnt : mid;
+  // pose diagonal blocks: task = (free pose, split part); a part owns a contiguous range of chunks
+  const int np = sh.np, nch = sh.nch, P1 = P + 1;
+  int split = BA_WARPS / (np > 0 ? np : 1);
+  split = split < 1 ? 1 : (split > 4 ? 4 : split);
+  if (split > nch) split = nch > 0 ? nch : 1;
+  for (int task = warp; task < np * split; task += BA_WARPS) {
+    const int pi = task / split, part = task - pi * split, p = sh.pose_of[pi];
+    const int c0 = (nch * part) / split, c1 = (nch * (part + 1)) / split;
     double H[21], b[6];
 #pragma unroll
     for (int i = 0; i < 21; ++i) H[i] = 0;
 #pragma unroll
     for (int i = 0; i < 6; ++i) b[i] = 0;
-    for (int k = lo + lane; k < hi; k += 32) {
-      const int e = ws.plist[b0 + k];
-      double B[12], g0, g1;
-      if (pb.fix_landmarks) {
-        double r[2], A[6];
-        edge_eval<true>(poses + 7 * p, lms + 3 * el[e], uv + 2 * e, cam, r, A, B);
-        const double c = r[0] * r[0] + r[1] * r[1];
-        const double sr = (c <= d2) ? 1.0 : sqrt(delta / sqrt(c));
+    for (int ch = c0; ch < c1; ++ch) {
+      const int s0 = ws.cp_off[ch * P1 + p], s1 = ws.cp_off[ch * P1 + p + 1];
+      for (int s = s0 + lane; s < s1; s += 32) {
+        double B[12], g0, g1;
+        if (pb.fix_landmarks) {
+          const int pl = ws.slot_pl[s];
+          const double uv[2] = {ws.uvs[s], ws.uvs[ME + s]};
+          double r[2], A[6];
+          edge_eval<true>(poses + 7 * p, lms + 3 * (size_t)(pl >> 8), uv, cam, r, A, B);
+          const double c = r[0] * r[0] + r[1] * r[1];
+          const double sr = (c <= d2) ? 1.0 : sqrt(delta / sqrt(c));
 #pragma unroll
-        for (int i = 0; i < 12; ++i) B[i] *= sr;
-        g0 = -sr * r[0]; g1 = -sr * r[1];
-      } else {
-        const double* Bw = ws.Bw + 12 * (size_t)e;
+          for (int i = 0; i < 12; ++i) B[i] *= sr;
+          g0 = -sr * r[0]; g1 = -sr * r[1];
+        } else {
 #pragma unroll
-        for (int i = 0; i < 12; ++i) B[i] = Bw[i];
-        g0 = ws.g[2 * (size_t)e]; g1 = ws.g[2 * (size_t)e + 1];
-      }
-      int k2 = 0;
+          for (int i = 0; i < 12; ++i) B[i] = ws.Bw[i * ME + s];
+          g0 = ws.g[s]; g1 = ws.g[ME + s];
+        }
+        int k2 = 0;
 #pragma unroll
-      for (int i = 0; i < 6; ++i) {
-        b[i] += B[i] * g0 + B[6 + i] * g1;
+        for (int i = 0; i < 6; ++i) {
+          b[i] += B[i] * g0 + B[6 + i] * g1;
 #pragma unroll
-        for (int j = i; j < 6; ++j) H[k2++] += B[i] * B[j] + B[6 + i] * B[6 + j];
+          for (int j = i; j < 6; ++j) H[k2++] += B[i] * B[j] + B[6 + i] * B[6 + j];
+        }
       }
     }
 #pragma unroll
@@ -400,164 +520,135 @@ __device__ void build_system(const flv_ba_problem& pb, const Cam& cam, const dou
     for (int i = 0; i < 6; ++i) { const double v = warp_sum(b[i]); if (lane == 0) sh.part[task][21 + i] = v; }
   }
   __syncthreads();
-  for (int i = tid; i < sh.np * 27; i += BA_THREADS) {
+  for (int i = tid; i < np * 27; i += BA_THREADS) {
     const int pi = i / 27, k = i - 27 * pi;
-    const double v = sh.part[2 * pi][k] + sh.part[2 * pi + 1][k];
+    double v = 0;
+    for (int part = 0; part < split; ++part) v += sh.part[pi * split + part][k];
     if (k < 21) sh.Hd[pi][k] = v; else sh.bp[6 * pi + k - 21] = v;
   }
   __syncthreads();
 }
 
-// (H + lambda I) x = b through the Schur complement: S (n x ld, shared, lower triangle used), y, x in shared
-__device__ void solve_system(const flv_ba_problem& pb, double lambda, double* S, double* y, int ld, double* stage, Ws& ws,
-                             Sh& sh) {
+// (H + lambda I) x = b through the Schur complement: S (n x ld, shared, lower triangle used), y, x in shared.
+// The landmark side is streamed through shared memory chunk by chunk (W planes + Dinv + Dinv*bl of the chunk's
+// landmarks); a warp owns a pose pair, two lanes share a member landmark (lane parity h owns columns 3h..3h+2 of the
+// 6x6 block), member lists hold chunk-local positions, so every operand of the inner loop is a shared-memory read.
+__device__ void solve_system(const flv_ba_problem& pb, double lambda, double* S, double* y, double* chunk, int ld,
+                             Ws& ws, Sh& sh) {
   const int L = pb.n_landmarks, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int np = sh.np, n = 6 * np;
+  const int np = sh.np, n = 6 * np, ME = ws.ME, ML = ws.ML;
+  const int nblk = np * (np + 1) / 2;
+  // reduced system starts as the pose blocks (+ lambda); the chunks subtract W Dinv W^T from it
+  for (int i = tid; i < n * ld; i += BA_THREADS) S[i] = 0;
+  __syncthreads();
+  for (int i = tid; i < np * 36; i += BA_THREADS) {
+    const int pi = i / 36, k = i - 36 * pi, r = k / 6, c = k - 6 * r;
+    double v = sh.Hd[pi][r <= c ? sym21(r, c) : sym21(c, r)];
+    if (r == c) v += lambda;
+    S[(6 * pi + r) * ld + 6 * pi + c] = v;
+  }
+  if (tid < n) y[tid] = sh.bp[tid];
   if (!pb.fix_landmarks) {
     for (int l = tid; l < L; l += BA_THREADS) {
       if (!ws.lmask[l]) continue;
-      const double* H = ws.Hll + 6 * (size_t)l;
-      const double a = H[0] + lambda, b = H[1], c = H[2], d = H[3] + lambda, e = H[4], f = H[5] + lambda;
+      const double a = ws.Hll[l] + lambda, b = ws.Hll[ML + l], c = ws.Hll[2 * ML + l], d = ws.Hll[3 * ML + l] + lambda,
+                   e = ws.Hll[4 * ML + l], f = ws.Hll[5 * ML + l] + lambda;
       const double c00 = d * f - e * e, c01 = c * e - b * f, c02 = b * e - c * d;
       const double id = 1.0 / (a * c00 + b * c01 + c * c02);
-      double Di[6] = {c00 * id, c01 * id, c02 * id, (a * f - c * c) * id, (b * c - a * e) * id, (a * d - b * b) * id};
-#pragma unroll
-      for (int i = 0; i < 6; ++i) ws.Dinv[6 * (size_t)l + i] = Di[i];
-      // Y_e = W_e * Dinv for every edge of this landmark with a free pose (used by all pose pairs of the landmark)
-      unsigned m = ws.lmask[l];
-      while (m) {
-        const int p = __ffs(m) - 1; m &= m - 1;
-        if (sh.pidx[p] < 0) continue;
-        const size_t e = (size_t)ws.eidx[p * L + l];
-        const double* W = ws.W + WSTRIDE * e;
-        double* Y = ws.Y + WSTRIDE * e;
-#pragma unroll
-        for (int i = 0; i < 6; ++i) {
-          const double w0 = W[WOFF(3 * i)], w1 = W[WOFF(3 * i + 1)], w2 = W[WOFF(3 * i + 2)];
-          Y[WOFF(3 * i)] = w0 * Di[0] + w1 * Di[1] + w2 * Di[2];
-          Y[WOFF(3 * i + 1)] = w0 * Di[1] + w1 * Di[3] + w2 * Di[4];
-          Y[WOFF(3 * i + 2)] = w0 * Di[2] + w1 * Di[4] + w2 * Di[5];
-        }
-      }
+      const double D0 = c00 * id, D1 = c01 * id, D2 = c02 * id, D3 = (a * f - c * c) * id, D4 = (b * c - a * e) * id,
+                   D5 = (a * d - b * b) * id;
+      ws.Dinv[l] = D0; ws.Dinv[ML + l] = D1; ws.Dinv[2 * ML + l] = D2; ws.Dinv[3 * ML + l] = D3;
+      ws.Dinv[4 * ML + l] = D4; ws.Dinv[5 * ML + l] = D5;
+      const double b0 = ws.bl[l], b1 = ws.bl[ML + l], b2 = ws.bl[2 * ML + l];
+      ws.Dv[l] = D0 * b0 + D1 * b1 + D2 * b2; ws.Dv[ML + l] = D1 * b0 + D3 * b1 + D4 * b2;
+      ws.Dv[2 * ML + l] = D2 * b0 + D4 * b1 + D5 * b2;
     }
     __syncthreads();
-  }
-  const int nblk = np * (np + 1) / 2;
-  // One warp per pose pair.  TWO lanes share a member: lane parity h owns columns 3h..3h+2 of the 6x6 block, so a
-  // lane keeps 18 accumulators + Y_a (18) + half of W_b (9) in registers -- the full 36 + 18 + 18 layout spilled
-  // under the 128-register cap and made this pass local-memory bound (profiles/r01_ba_notes.md).
-  const int half = lane & 1, mslot = lane >> 1;
-  for (int blk = warp; blk < nblk; blk += BA_WARPS) {
-    int a, b; pair_of(blk, np, a, b);
-    double acc[18], cf[6];
+    mark(sh, 8);
+    const int cap = sh.cap, half = lane & 1, mslot = lane >> 1;
+    double* Wc = chunk;
+    double* Dc = chunk + 18 * cap;
+    for (int ch = 0; ch < sh.nch; ++ch) {
+      const int sb = sh.chunk_sb[ch], ns = sh.chunk_sb[ch + 1] - sb, lb = sh.chunk_lb[ch], nl = sh.chunk_lb[ch + 1] - lb;
+      // this warp's member-list bounds for the chunk (lane j <-> pair warp + 16 j); issued before the staging loads
+      int my0 = 0, my1 = 0;
+      {
+        const int blk = warp + BA_WARPS * lane;
+        if (blk < nblk) { my0 = ws.poff[ch * nblk + blk]; my1 = ws.poff[ch * nblk + blk + 1]; }
+      }
+#pragma unroll 6
+      for (int c = 0; c < 18; ++c)
+        for (int i = tid; i < ns; i += BA_THREADS) Wc[c * cap + i] = ws.W[c * ME + sb + i];
+      for (int i = tid; i < nl; i += BA_THREADS) {
 #pragma unroll
-    for (int i = 0; i < 18; ++i) acc[i] = 0;
+        for (int c = 0; c < 6; ++c) Dc[c * cap + i] = ws.Dinv[c * ML + lb + i];
 #pragma unroll
-    for (int i = 0; i < 6; ++i) cf[i] = 0;
-    if (!pb.fix_landmarks) {
-      const int i0 = sh.pair_off[blk], i1 = sh.pair_off[blk + 1];
-      if (stage) {
-        // 16 members per round: the warp copies their Y_a | W_b blocks (2 x 160 B each) into its shared-memory
-        // staging area with fully coalesced 128-bit loads (every 32-byte sector is requested once; the direct
-        // per-lane 8-byte loads asked for each sector ~3x and made this pass LSU-bound), then computes from there.
-        double* stg = stage + (size_t)warp * 16 * STG_STRIDE;
-        for (int k0 = i0; k0 < i1; k0 += 16) {
-          const int cntm = i1 - k0 < 16 ? i1 - k0 : 16;
-          int ea = 0, eb = 0, ll = 0;
-          if (lane < cntm) { const int* it = ws.pairs + 3 * (size_t)(k0 + lane); ea = it[0]; eb = it[1]; ll = it[2]; }
+        for (int c = 0; c < 3; ++c) Dc[(6 + c) * cap + i] = ws.Dv[c * ML + lb + i];
+      }
+      __syncthreads();
+      mark(sh, 9);
+      for (int j = 0, blk = warp; blk < nblk; blk += BA_WARPS, ++j) {
+        const int i0 = __shfl_sync(FULL, my0, j), i1 = __shfl_sync(FULL, my1, j);
+        if (i0 == i1) continue;
+        const int a = sh.pair_a[blk], b = sh.pair_b[blk];
+        double acc[18];
 #pragma unroll
-          for (int pss = 0; pss < 10; ++pss) {
-            const int c = pss * 32 + lane, mem = c / 20, ch = c - 20 * mem;
-            const int sa = __shfl_sync(FULL, ea, mem), sb = __shfl_sync(FULL, eb, mem);
-            if (mem < cntm) {
-              const double* base = ch < 10 ? ws.Y + WSTRIDE * (size_t)sa : ws.W + WSTRIDE * (size_t)sb;
-              const double2 v = *reinterpret_cast<const double2*>(base + 2 * (ch < 10 ? ch : ch - 10));
-              *reinterpret_cast<double2*>(stg + (size_t)mem * STG_STRIDE + 2 * ch) = v;
-            }
+        for (int i = 0; i < 18; ++i) acc[i] = 0;
+        int k = i0 + mslot;
+        int ent = k < i1 ? ws.pairs[k] : 0;
+        for (; k < i1; k += 16) {
+          const int cur = ent;
+          if (k + 16 < i1) ent = ws.pairs[k + 16];          // prefetch the next round's member
+          const int pa = cur & 1023, pbb = (cur >> 10) & 1023, lp = cur >> 20;
+          double wa[18], D[6];
+#pragma unroll
+          for (int i = 0; i < 18; ++i) wa[i] = Wc[i * cap + pa];
+#pragma unroll
+          for (int i = 0; i < 6; ++i) D[i] = Dc[i * cap + lp];
+#pragma unroll
+          for (int jj = 0; jj < 3; ++jj) {
+            const int row = 3 * half + jj;                   // row of W_b (6x3) = column of the 6x6 block
+            const double w0 = Wc[(3 * row) * cap + pbb], w1 = Wc[(3 * row + 1) * cap + pbb], w2 = Wc[(3 * row + 2) * cap + pbb];
+            const double t0 = w0 * D[0] + w1 * D[1] + w2 * D[2], t1 = w0 * D[1] + w1 * D[3] + w2 * D[4],
+                         t2 = w0 * D[2] + w1 * D[4] + w2 * D[5];
+#pragma unroll
+            for (int i = 0; i < 6; ++i) acc[3 * i + jj] += wa[3 * i] * t0 + wa[3 * i + 1] * t1 + wa[3 * i + 2] * t2;
           }
-          const int myl = __shfl_sync(FULL, ll, mslot);
-          __syncwarp();
-          if (mslot < cntm) {
-            const double* m = stg + (size_t)mslot * STG_STRIDE;
-            double ya[18], wb[9];
+        }
+        // reduce over the 16 member slots (lanes of equal parity): xor 2, 4, 8, 16
 #pragma unroll
-            for (int i = 0; i < 18; ++i) ya[i] = m[WOFF(i)];
+        for (int i = 0; i < 18; ++i) {
+          double v = acc[i];
 #pragma unroll
-            for (int i = 0; i < 9; ++i) wb[i] = m[20 + 10 * half + i];
-            if (a == b && half == 0) {
-              const double* bl = ws.bl + 3 * (size_t)myl;
-              const double b0 = bl[0], b1 = bl[1], b2 = bl[2];
+          for (int o = 2; o < 32; o <<= 1) v += __shfl_xor_sync(FULL, v, o);
+          acc[i] = v;
+        }
+        if (lane < 2) {
 #pragma unroll
-              for (int i = 0; i < 6; ++i) cf[i] += ya[3 * i] * b0 + ya[3 * i + 1] * b1 + ya[3 * i + 2] * b2;
+          for (int i = 0; i < 6; ++i)
+#pragma unroll
+            for (int jj = 0; jj < 3; ++jj) {
+              const int jc = 3 * half + jj;
+              S[(6 * b + jc) * ld + 6 * a + i] -= acc[3 * i + jj];   // block (b,a), b >= a: lower triangle (+ mirror if a == b)
             }
+        }
+        if (a == b) {
+          // right-hand side of pose a: y_a -= sum_l W_al (Dinv bl)_l ; lanes split the members 32 ways
+          double cf[6] = {0, 0, 0, 0, 0, 0};
+          for (int k2 = i0 + lane; k2 < i1; k2 += 32) {
+            const int cur = ws.pairs[k2];
+            const int pa = cur & 1023, lp = cur >> 20;
+            const double v0 = Dc[6 * cap + lp], v1 = Dc[7 * cap + lp], v2 = Dc[8 * cap + lp];
 #pragma unroll
             for (int i = 0; i < 6; ++i)
-#pragma unroll
-              for (int j = 0; j < 3; ++j)
-                acc[3 * i + j] += ya[3 * i] * wb[3 * j] + ya[3 * i + 1] * wb[3 * j + 1] + ya[3 * i + 2] * wb[3 * j + 2];
+              cf[i] += Wc[(3 * i) * cap + pa] * v0 + Wc[(3 * i + 1) * cap + pa] * v1 + Wc[(3 * i + 2) * cap + pa] * v2;
           }
-          __syncwarp();
+#pragma unroll
+          for (int i = 0; i < 6; ++i) { const double v = warp_sum(cf[i]); if (lane == 0) y[6 * a + i] -= v; }
         }
-      } else {
-      for (int k = i0 + mslot; k < i1; k += 16) {
-        const int* it = ws.pairs + 3 * (size_t)k;
-        const double* Ya = ws.Y + WSTRIDE * (size_t)it[0];
-        const double* Wb = ws.W + WSTRIDE * (size_t)it[1] + 10 * half;  // rows 3h..3h+2 of W_b
-        double ya[18], wb[9];
-#pragma unroll
-        for (int i = 0; i < 18; ++i) ya[i] = Ya[WOFF(i)];
-#pragma unroll
-        for (int i = 0; i < 9; ++i) wb[i] = Wb[i];
-        if (a == b && half == 0) {
-          const double* bl = ws.bl + 3 * (size_t)it[2];
-          const double b0 = bl[0], b1 = bl[1], b2 = bl[2];
-#pragma unroll
-          for (int i = 0; i < 6; ++i) cf[i] += ya[3 * i] * b0 + ya[3 * i + 1] * b1 + ya[3 * i + 2] * b2;
-        }
-#pragma unroll
-        for (int i = 0; i < 6; ++i)
-#pragma unroll
-          for (int j = 0; j < 3; ++j)
-            acc[3 * i + j] += ya[3 * i] * wb[3 * j] + ya[3 * i + 1] * wb[3 * j + 1] + ya[3 * i + 2] * wb[3 * j + 2];
       }
-      }
-    }
-    // reduce over the 16 member slots (lanes of equal parity): xor 2, 4, 8, 16
-#pragma unroll
-    for (int i = 0; i < 18; ++i) {
-      double v = acc[i];
-#pragma unroll
-      for (int o = 2; o < 32; o <<= 1) v += __shfl_xor_sync(FULL, v, o);
-      acc[i] = v;
-    }
-    if (a == b) {
-#pragma unroll
-      for (int i = 0; i < 6; ++i) {
-        double v = cf[i];
-#pragma unroll
-        for (int o = 2; o < 32; o <<= 1) v += __shfl_xor_sync(FULL, v, o);
-        cf[i] = v;
-      }
-    }
-    // lanes 0 and 1 write their three columns: S block (b,a) of the lower triangle = -(acc)^T (+ Hpp + lambda)
-    if (lane < 2) {
-#pragma unroll
-      for (int i = 0; i < 6; ++i)
-#pragma unroll
-        for (int jj = 0; jj < 3; ++jj) {
-          const int j = 3 * half + jj;
-          double v = -acc[3 * i + jj];
-          if (a == b) {
-            v += sh.Hd[a][i <= j ? sym21(i, j) : sym21(j, i)];
-            if (i == j) v += lambda;
-          }
-          S[(6 * b + j) * ld + 6 * a + i] = v;            // row index from pose b >= a: lower triangle
-          if (a == b) S[(6 * a + i) * ld + 6 * b + j] = v;
-        }
-      if (a == b && lane == 0) {
-#pragma unroll
-        for (int i = 0; i < 6; ++i) y[6 * a + i] = sh.bp[6 * a + i] - cf[i];
-      }
+      __syncthreads();
+      mark(sh, 2);
     }
   }
   if (tid == 0) sh.fail = 0;
@@ -608,7 +699,7 @@ __device__ void solve_system(const flv_ba_problem& pb, double lambda, double* S,
 // state update (sparse_optimizer.cpp:433-446) incl. landmark back-substitution (block_solver.hpp:422-444).
 // Returns sum_j x_j (lambda x_j + b_j) (computeScale, optimization_algorithm_levenberg.cpp:168-175).
 __device__ double apply_update(const flv_ba_problem& pb, double lambda, double* poses, double* lms, Ws& ws, Sh& sh) {
-  const int P = pb.n_poses, L = pb.n_landmarks, tid = threadIdx.x;
+  const int P = pb.n_poses, L = pb.n_landmarks, tid = threadIdx.x, ME = ws.ME, ML = ws.ML;
   double sc = 0;
   for (int i = tid; i < 7 * P; i += BA_THREADS) ws.pbk[i] = poses[i];
   if (!pb.fix_landmarks) {
@@ -617,21 +708,23 @@ __device__ double apply_update(const flv_ba_problem& pb, double lambda, double* 
       ws.lbk[3 * (size_t)l] = X[0]; ws.lbk[3 * (size_t)l + 1] = X[1]; ws.lbk[3 * (size_t)l + 2] = X[2];
       unsigned m = ws.lmask[l];
       if (!m) continue;
-      const double* bl = ws.bl + 3 * (size_t)l;
-      double c0 = bl[0], c1 = bl[1], c2 = bl[2];
+      const double bl0 = ws.bl[l], bl1 = ws.bl[ML + l], bl2 = ws.bl[2 * ML + l];
+      double c0 = bl0, c1 = bl1, c2 = bl2;
       while (m) {
         const int p = __ffs(m) - 1; m &= m - 1;
         const int pi = sh.pidx[p];
         if (pi < 0) continue;
-        const double* W = ws.W + WSTRIDE * (size_t)ws.eidx[p * L + l];
+        const int s = ws.tab[p * L + l];
         const double* xp = sh.x + 6 * pi;
 #pragma unroll
-        for (int i = 0; i < 6; ++i) { c0 -= W[WOFF(3 * i)] * xp[i]; c1 -= W[WOFF(3 * i + 1)] * xp[i]; c2 -= W[WOFF(3 * i + 2)] * xp[i]; }
+        for (int i = 0; i < 6; ++i) {
+          c0 -= ws.W[(3 * i) * ME + s] * xp[i]; c1 -= ws.W[(3 * i + 1) * ME + s] * xp[i]; c2 -= ws.W[(3 * i + 2) * ME + s] * xp[i];
+        }
       }
-      const double* Di = ws.Dinv + 6 * (size_t)l;
-      const double x0 = Di[0] * c0 + Di[1] * c1 + Di[2] * c2, x1 = Di[1] * c0 + Di[3] * c1 + Di[4] * c2,
-                   x2 = Di[2] * c0 + Di[4] * c1 + Di[5] * c2;
-      sc += x0 * (lambda * x0 + bl[0]) + x1 * (lambda * x1 + bl[1]) + x2 * (lambda * x2 + bl[2]);
+      const double D0 = ws.Dinv[l], D1 = ws.Dinv[ML + l], D2 = ws.Dinv[2 * ML + l], D3 = ws.Dinv[3 * ML + l],
+                   D4 = ws.Dinv[4 * ML + l], D5 = ws.Dinv[5 * ML + l];
+      const double x0 = D0 * c0 + D1 * c1 + D2 * c2, x1 = D1 * c0 + D3 * c1 + D4 * c2, x2 = D2 * c0 + D4 * c1 + D5 * c2;
+      sc += x0 * (lambda * x0 + bl0) + x1 * (lambda * x1 + bl1) + x2 * (lambda * x2 + bl2);
       X[0] += x0; X[1] += x1; X[2] += x2;
     }
   }
@@ -651,6 +744,28 @@ __device__ void restore_state(const flv_ba_problem& pb, double* poses, double* l
 __host__ __device__ inline size_t pair_capacity(int max_poses, int max_edges) {
   return (size_t)max_edges * ((max_poses + 2) / 2);
 }
+__host__ __device__ inline size_t poff_capacity() { return (size_t)BA_MAX_CHUNKS * BA_MAX_PAIRS + 1; }
+
+// workspace carve-up (doubles first, then ints); shared by the kernel and ws_stride_bytes()
+struct WsLayout {
+  size_t pbk, lbk, W, Bw, g, hl, bb, uvs, Hll, bl, Dinv, Dv, n_doubles;
+  size_t tab, lmask, slot_e, slot_pl, lw, lstart, cp_off, poff, pairs, n_ints;
+};
+__host__ __device__ inline WsLayout ws_layout(int MP, int ML, int ME) {
+  WsLayout o; size_t d = 0, i = 0;
+  const size_t E = (size_t)ME, L = (size_t)ML, P = (size_t)MP;
+  o.pbk = d; d += 7 * P + (P & 1);
+  o.lbk = d; d += 3 * L + (L & 1);
+  o.W = d; d += 18 * E; o.Bw = d; d += 12 * E; o.g = d; d += 2 * E; o.hl = d; d += 6 * E; o.bb = d; d += 3 * E;
+  o.uvs = d; d += 2 * E;
+  o.Hll = d; d += 6 * L; o.bl = d; d += 3 * L; o.Dinv = d; d += 6 * L; o.Dv = d; d += 3 * L;
+  o.n_doubles = d;
+  o.tab = i; i += P * L; o.lmask = i; i += L; o.slot_e = i; i += E; o.slot_pl = i; i += E;
+  o.lw = i; i += L + 1; o.lstart = i; i += L + 1; o.cp_off = i; i += (size_t)BA_MAX_CHUNKS * (P + 1);
+  o.poff = i; i += poff_capacity(); o.pairs = i; i += pair_capacity(MP, ME);
+  o.n_ints = i;
+  return o;
+}
 
 __global__ void __launch_bounds__(BA_THREADS, 1) ba_kernel(BAArgs a) {
   extern __shared__ double dyn[];
@@ -664,26 +779,18 @@ __global__ void __launch_bounds__(BA_THREADS, 1) ba_kernel(BAArgs a) {
   const int* el = a.el + (size_t)s * a.max_edges;
   const double* uv = a.uv + (size_t)s * a.max_edges * 2;
   uint8_t* act = a.active + (size_t)s * a.max_edges;
-  const int P = pb.n_poses, L = pb.n_landmarks, E = pb.n_edges;
-  // carve the per-stream workspace
+  const int P = pb.n_poses, E = pb.n_edges;
   Ws ws;
   {
+    const WsLayout lo = ws_layout(a.max_poses, a.max_lms, a.max_edges);
     double* d = (double*)(a.ws + (size_t)s * a.ws_stride);
-    ws.pbk = d; d += 7 * a.max_poses;
-    ws.lbk = d; d += 3 * a.max_lms;
-    ws.W = d; d += WSTRIDE * (size_t)a.max_edges;
-    ws.Bw = d; d += 12 * (size_t)a.max_edges;
-    ws.g = d; d += 2 * (size_t)a.max_edges;
-    ws.Hll = d; d += 6 * a.max_lms;
-    ws.bl = d; d += 3 * a.max_lms;
-    ws.Dinv = d; d += 6 * a.max_lms;
-    ws.xl = d; d += 3 * a.max_lms;
-    ws.Y = d; d += WSTRIDE * (size_t)a.max_edges;
-    ws.eidx = (int*)d;
-    ws.lmask = (unsigned*)(ws.eidx + (size_t)a.max_poses * a.max_lms);
-    ws.plist = (int*)(ws.lmask + a.max_lms);
-    ws.pairs = ws.plist + a.max_edges;
-    ws.pair_cap = (int)pair_capacity(a.max_poses, a.max_edges);
+    int* ib = (int*)(d + lo.n_doubles);
+    ws.pbk = d + lo.pbk; ws.lbk = d + lo.lbk; ws.W = d + lo.W; ws.Bw = d + lo.Bw; ws.g = d + lo.g; ws.hl = d + lo.hl;
+    ws.bb = d + lo.bb; ws.uvs = d + lo.uvs; ws.Hll = d + lo.Hll; ws.bl = d + lo.bl; ws.Dinv = d + lo.Dinv; ws.Dv = d + lo.Dv;
+    ws.tab = ib + lo.tab; ws.lmask = (unsigned*)(ib + lo.lmask); ws.slot_e = ib + lo.slot_e; ws.slot_pl = ib + lo.slot_pl;
+    ws.lw = ib + lo.lw; ws.lstart = ib + lo.lstart; ws.cp_off = ib + lo.cp_off; ws.poff = ib + lo.poff;
+    ws.pairs = ib + lo.pairs;
+    ws.pair_cap = (int)pair_capacity(a.max_poses, a.max_edges); ws.ME = a.max_edges; ws.ML = a.max_lms;
   }
   const double delta = a.prm.huber_delta;
   flv_ba_stats st;
@@ -693,25 +800,24 @@ __global__ void __launch_bounds__(BA_THREADS, 1) ba_kernel(BAArgs a) {
     if (tid == 0) { st.ok = 0; st.reserved = 1; a.stats[s] = st; }
     return;
   }
-  if (tid == 0) { for (int i = 0; i < 8; ++i) sh.prof[i] = 0; sh.tlast = clock64(); }
-  st.chi2_initial = robust_chi2(pb, cam, poses, lms, ep, el, uv, act, delta, sh.red);
+  if (tid == 0) { for (int i = 0; i < 16; ++i) sh.prof[i] = 0; sh.tlast = clock64(); }
+  st.chi2_initial = robust_chi2_edges(pb, cam, poses, lms, ep, el, uv, act, delta, sh.red);
   double lambda = 0;
   for (int phase = 0; phase < 2; ++phase) {
     const int iters = phase == 0 ? a.prm.iters1 : a.prm.iters2;
-    setup_active(pb, ep, el, act, ws, sh);
+    setup_active(pb, ep, el, uv, act, a.dyn_doubles, ws, sh);
     mark(sh, 6);
     if (sh.np > BA_MAX_FREE) { st.ok = 0; st.reserved = 2; break; }
-    if (sh.overflow) { st.ok = 0; st.reserved = 3; break; }
+    if (sh.overflow) { st.ok = 0; st.reserved = sh.overflow == 1 ? 3 : 4; break; }
     const int n = 6 * sh.np, ld = n + 1;
     double* S = dyn;
     double* y = dyn + (size_t)n * ld;
-    // staging area of the Schur pass sits behind S | y when the launch reserved room for it (a.stage_doubles > 0)
-    double* stage = a.stage_doubles ? dyn + a.stage_offset_doubles : nullptr;
+    double* chunk = y + ((n + 8) & ~1);
     double ni = 2;
     for (int it = 0; it < iters; ++it) {
-      double currentChi = robust_chi2(pb, cam, poses, lms, ep, el, uv, act, delta, sh.red);
+      double currentChi = robust_chi2(cam, poses, lms, delta, ws, sh);
       mark(sh, 0);
-      build_system(pb, cam, poses, lms, el, uv, delta, ws, sh);
+      build_system(pb, cam, poses, lms, delta, ws, sh);
       mark(sh, 1);
       if (it == 0) {
         double md = 0;
@@ -720,22 +826,22 @@ __global__ void __launch_bounds__(BA_THREADS, 1) ba_kernel(BAArgs a) {
           for (int i = 0; i < 6; ++i) md = fmax(md, fabs(sh.Hd[tid][sym21(i, i)]));
         }
         if (!pb.fix_landmarks)
-          for (int l = tid; l < L; l += BA_THREADS)
-            if (ws.lmask[l]) md = fmax(md, fmax(fabs(ws.Hll[6 * (size_t)l]), fmax(fabs(ws.Hll[6 * (size_t)l + 3]), fabs(ws.Hll[6 * (size_t)l + 5]))));
+          for (int l = tid; l < pb.n_landmarks; l += BA_THREADS)
+            if (ws.lmask[l]) md = fmax(md, fmax(fabs(ws.Hll[l]), fmax(fabs(ws.Hll[3 * ws.ML + l]), fabs(ws.Hll[5 * ws.ML + l]))));
         lambda = 1e-5 * block_max(md, sh.red);
         ni = 2;
       }
       double rho = 0;
       int qmax = 0;
       do {
-        solve_system(pb, lambda, S, y, ld, stage, ws, sh);
+        solve_system(pb, lambda, S, y, chunk, ld, ws, sh);
         const int ok2 = !sh.fail;
         double scale = 0, tempChi;
         if (ok2) {
           scale = apply_update(pb, lambda, poses, lms, ws, sh);
           __syncthreads();
           mark(sh, 5);
-          tempChi = robust_chi2(pb, cam, poses, lms, ep, el, uv, act, delta, sh.red);
+          tempChi = robust_chi2(cam, poses, lms, delta, ws, sh);
           mark(sh, 0);
         } else {
           tempChi = 1.7976931348623157e308;
@@ -758,14 +864,15 @@ __global__ void __launch_bounds__(BA_THREADS, 1) ba_kernel(BAArgs a) {
       if (qmax == 10 || rho == 0 || !isfinite(lambda)) break;
     }
     if (phase == 0) {
-      st.chi2_after1 = robust_chi2(pb, cam, poses, lms, ep, el, uv, act, delta, sh.red);
+      st.chi2_after1 = robust_chi2(cam, poses, lms, delta, ws, sh);
       // cull: un-robustified chi2 > threshold (vo_localmap.cpp:303-316, optimize_in_frame.cpp:67-74)
       int culled = 0, remaining = 0;
-      for (int e = tid; e < E; e += BA_THREADS) {
-        if (!act[e]) continue;
+      for (int sl = tid; sl < sh.nact; sl += BA_THREADS) {
+        const int pl = ws.slot_pl[sl];
+        const double uvv[2] = {ws.uvs[sl], ws.uvs[ws.ME + sl]};
         double r[2];
-        edge_eval<false>(poses + 7 * ep[e], lms + 3 * el[e], uv + 2 * e, cam, r, nullptr, nullptr);
-        if (r[0] * r[0] + r[1] * r[1] > a.prm.cull_chi2) { act[e] = 0; ++culled; } else ++remaining;
+        edge_eval<false>(poses + 7 * (pl & 255), lms + 3 * (size_t)(pl >> 8), uvv, cam, r, nullptr, nullptr);
+        if (r[0] * r[0] + r[1] * r[1] > a.prm.cull_chi2) { act[ws.slot_e[sl]] = 0; ++culled; } else ++remaining;
       }
       st.n_culled = (int)(block_sum((double)culled, sh.red) + 0.5);
       const int rem = (int)(block_sum((double)remaining, sh.red) + 0.5);
@@ -773,33 +880,26 @@ __global__ void __launch_bounds__(BA_THREADS, 1) ba_kernel(BAArgs a) {
       if (rem < a.prm.min_edges_after_cull) { st.ok = 0; break; }
     }
   }
-  st.chi2_final = robust_chi2(pb, cam, poses, lms, ep, el, uv, act, delta, sh.red);
+  st.chi2_final = robust_chi2_edges(pb, cam, poses, lms, ep, el, uv, act, delta, sh.red);
   st.lambda_final = lambda;
   if (tid == 0) {
     a.stats[s] = st;
-    if (a.prof) for (int i = 0; i < 8; ++i) a.prof[8 * s + i] = sh.prof[i];
+    if (a.prof) for (int i = 0; i < 16; ++i) a.prof[16 * s + i] = sh.prof[i];
   }
 }
 
 size_t ws_stride_bytes(int max_poses, int max_lms, int max_edges) {
-  size_t d = 7 * (size_t)max_poses + 3 * (size_t)max_lms + (2 * WSTRIDE + 12 + 2) * (size_t)max_edges + 6 * (size_t)max_lms +
-             3 * (size_t)max_lms + 6 * (size_t)max_lms + 3 * (size_t)max_lms;
-  size_t ints = (size_t)max_poses * max_lms + max_lms + max_edges + 3 * pair_capacity(max_poses, max_edges);
-  size_t b = d * 8 + ints * 4;
+  const WsLayout lo = ws_layout(max_poses, max_lms, max_edges);
+  const size_t b = lo.n_doubles * 8 + lo.n_ints * 4;
   return (b + 255) & ~(size_t)255;
 }
 
-size_t ba_sys_doubles(int nfree) {
-  const size_t n = 6 * (size_t)nfree;
-  return ((n * (n + 1) + n + 8) + 1) & ~(size_t)1;          // S | y, rounded to 16 bytes
-}
-constexpr size_t BA_STAGE_DOUBLES = (size_t)BA_WARPS * 16 * STG_STRIDE;
-// dynamic shared memory of a launch: the reduced system plus, when it still fits next to the static state, the staging area
-size_t ba_dyn_smem(int nfree, bool* with_stage) {
-  const size_t sys = ba_sys_doubles(nfree) * 8, stg = BA_STAGE_DOUBLES * 8;
-  const bool fits = sys + stg + sizeof(Sh) + 1024 <= 227 * 1024;
-  if (with_stage) *with_stage = fits;
-  return sys + (fits ? stg : 0);
+// dynamic shared memory of the kernel: everything the SM has left after the static state
+int ba_dyn_doubles() {
+  cudaFuncAttributes fa;
+  if (cudaFuncGetAttributes(&fa, ba_kernel) != cudaSuccess) return 0;
+  const long avail = 232448L - (long)fa.sharedSizeBytes - 1024;   // 227 KB per block on sm_100
+  return (int)(avail / 8);
 }
 
 }  // namespace
@@ -820,12 +920,12 @@ int flv_ba_reserve(flv_ctx* ctx, int max_poses, int max_landmarks, int max_edges
   flv_ba_free(ctx);
   size_t stride = ws_stride_bytes(max_poses, max_landmarks, max_edges);
   // tail: device copies of problems / stats / staging are carved after the per-stream blocks
-  size_t total = stride * ctx->S + (size_t)ctx->S * (sizeof(flv_ba_problem) + sizeof(flv_ba_stats) + 64) + 512;
+  size_t total = stride * ctx->S + (size_t)ctx->S * (sizeof(flv_ba_problem) + sizeof(flv_ba_stats) + 128) + 512;
   FLV_CUDA(ctx, cudaMalloc(&ctx->ba_ws, total));
   ctx->ba_ws_bytes = total;
   ctx->ba_max_poses = max_poses; ctx->ba_max_lms = max_landmarks; ctx->ba_max_edges = max_edges;
-  int nfree = max_poses < BA_MAX_FREE ? max_poses : BA_MAX_FREE;
-  size_t smem = ba_dyn_smem(nfree, nullptr);
+  const size_t smem = (size_t)ba_dyn_doubles() * 8;
+  if (smem == 0) FLV_FAIL(ctx, FLV_ERR_CUDA, "cudaFuncGetAttributes(ba_kernel) failed");
   FLV_CUDA(ctx, cudaFuncSetAttribute(ba_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   return FLV_OK;
 }
@@ -845,14 +945,11 @@ int flv_ba_optimize(flv_ctx* ctx, int n_streams, const flv_ba_problem* problems,
   flv_ba_problem* d_prob = (flv_ba_problem*)tail + slot0;
   flv_ba_stats* d_stats = (flv_ba_stats*)(tail + (size_t)ctx->S * sizeof(flv_ba_problem)) + slot0;
   BAArgs a;
-  a.prof = (long long*)(tail + (size_t)ctx->S * (sizeof(flv_ba_problem) + sizeof(flv_ba_stats))) + 8 * slot0;
+  a.prof = (long long*)(tail + (size_t)ctx->S * (sizeof(flv_ba_problem) + sizeof(flv_ba_stats))) + 16 * slot0;
   a.prm = *prm; a.max_poses = MP; a.max_lms = ML; a.max_edges = ME;
   a.ws = (unsigned char*)ctx->ba_ws + stride * slot0; a.ws_stride = stride;
-  const int nfree = MP < BA_MAX_FREE ? MP : BA_MAX_FREE;
-  bool with_stage = false;
-  const size_t smem = ba_dyn_smem(nfree, &with_stage);
-  a.stage_doubles = with_stage ? (int)BA_STAGE_DOUBLES : 0;
-  a.stage_offset_doubles = (int)ba_sys_doubles(nfree);
+  a.dyn_doubles = ba_dyn_doubles();
+  const size_t smem = (size_t)a.dyn_doubles * 8;
   const size_t S = n_streams;
   cudaStream_t stream = ctx->ba_stream_set ? ctx->ba_stream : ctx->stream;
   if (mem == FLV_MEM_DEVICE) {
@@ -893,7 +990,7 @@ int flv_ba_optimize(flv_ctx* ctx, int n_streams, const flv_ba_problem* problems,
   for (int s = 0; s < n_streams; ++s)
     if (stats[s].reserved)
       FLV_FAIL(ctx, FLV_ERR_UNSUPPORTED, "stream %d: %s", s,
-               stats[s].reserved == 1 ? "pose count outside [1,32]" : stats[s].reserved == 2 ? "more than 24 free poses (reduced system > 144)" : "pose-pair list capacity exceeded");
+               stats[s].reserved == 1 ? "pose count outside [1,32]" : stats[s].reserved == 2 ? "more than 24 free poses (reduced system > 144)" : stats[s].reserved == 3 ? "pose-pair list capacity exceeded" : "window too large for the shared-memory landmark chunks");
   return FLV_OK;
 }
 
@@ -905,13 +1002,13 @@ int flv_set_ba_stream(flv_ctx* ctx, void* cuda_stream, int enable) {
 }
 
 /* debug: cycle counters of the last flv_ba_optimize for `stream` (8 values, see Sh::prof) */
-int flv_ba_profile(flv_ctx* ctx, int stream, long long* out8) {
-  if (!ctx || !ctx->ba_ws || !out8 || stream < 0 || stream >= ctx->S) return FLV_ERR_INVALID;
+int flv_ba_profile(flv_ctx* ctx, int stream, long long* out16) {
+  if (!ctx || !ctx->ba_ws || !out16 || stream < 0 || stream >= ctx->S) return FLV_ERR_INVALID;
   const size_t stride = ws_stride_bytes(ctx->ba_max_poses, ctx->ba_max_lms, ctx->ba_max_edges);
   unsigned char* tail = (unsigned char*)ctx->ba_ws + stride * ctx->S;
   long long* d = (long long*)(tail + (size_t)ctx->S * (sizeof(flv_ba_problem) + sizeof(flv_ba_stats)));
   FLV_CUDA(ctx, cudaDeviceSynchronize());
-  FLV_CUDA(ctx, cudaMemcpy(out8, d + 8 * stream, 64, cudaMemcpyDeviceToHost));
+  FLV_CUDA(ctx, cudaMemcpy(out16, d + 16 * stream, 128, cudaMemcpyDeviceToHost));
   return FLV_OK;
 }
 

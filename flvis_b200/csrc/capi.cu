@@ -109,7 +109,11 @@ void flv_destroy(flv_ctx* ctx) {
   flv_ba_free(ctx);
   if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
   if (ctx->d_stage) cudaFree(ctx->d_stage);
-  if (ctx->d_img_stage) cudaFree(ctx->d_img_stage);
+  if (ctx->img_stage_bytes) for (int i = 0; i < flv_ctx::IMG_RING; ++i) cudaFree(ctx->d_img_stage[i]);
+  if (ctx->copy_stream) {
+    for (int i = 0; i < flv_ctx::IMG_RING; ++i) { cudaEventDestroy(ctx->img_ready[i]); cudaEventDestroy(ctx->img_free[i]); }
+    cudaStreamDestroy(ctx->copy_stream);
+  }
   if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
 }
@@ -154,26 +158,40 @@ int flv_upload_images(flv_ctx* ctx, int slot, int n_streams, const uint8_t* imgs
       row_stride_bytes < (size_t)ctx->w)
     return FLV_ERR_INVALID;
   if (mem == FLV_MEM_DEVICE) return flv_launch_unpack(ctx, slot, n_streams, imgs, row_stride_bytes, img_stride_bytes);
-  // host images: one (2D) H2D copy of all streams into a tight device staging area, then one unpack launch.
+  // host images: one (2D) H2D copy of all streams into a tight device landing area on the copy stream, then one unpack
+  // launch on the compute stream.  The landing areas form a ring, so a caller that submits frame k+1 before it waits for
+  // the results of frame k gets the copy of k+1 overlapped with the kernels of k.
   const size_t w = ctx->w, h = ctx->h, bytes = (size_t)n_streams * w * h;
-  if (bytes > ctx->img_stage_bytes) {
-    if (ctx->d_img_stage) cudaFree(ctx->d_img_stage);
-    ctx->d_img_stage = nullptr; ctx->img_stage_bytes = 0;
-    FLV_CUDA(ctx, cudaMalloc(&ctx->d_img_stage, (size_t)ctx->S * w * h));
+  if (!ctx->copy_stream) {
+    FLV_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+    for (int i = 0; i < flv_ctx::IMG_RING; ++i) {
+      FLV_CUDA(ctx, cudaEventCreateWithFlags(&ctx->img_ready[i], cudaEventDisableTiming));
+      FLV_CUDA(ctx, cudaEventCreateWithFlags(&ctx->img_free[i], cudaEventDisableTiming));
+    }
+  }
+  if (ctx->img_stage_bytes == 0) {
+    for (int i = 0; i < flv_ctx::IMG_RING; ++i) FLV_CUDA(ctx, cudaMalloc(&ctx->d_img_stage[i], (size_t)ctx->S * w * h));
     ctx->img_stage_bytes = (size_t)ctx->S * w * h;
   }
-  uint8_t* st = (uint8_t*)ctx->d_img_stage;
+  const int ring = (int)(ctx->img_ring_pos++ % flv_ctx::IMG_RING);
+  uint8_t* st = (uint8_t*)ctx->d_img_stage[ring];
+  cudaStream_t cs = ctx->copy_stream;
+  FLV_CUDA(ctx, cudaStreamWaitEvent(cs, ctx->img_free[ring], 0));        // last unpack that read this landing area
   if (row_stride_bytes == w && img_stride_bytes == w * h) {
-    FLV_CUDA(ctx, cudaMemcpyAsync(st, imgs, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    FLV_CUDA(ctx, cudaMemcpyAsync(st, imgs, bytes, cudaMemcpyHostToDevice, cs));
   } else if (img_stride_bytes == row_stride_bytes * h) {
-    FLV_CUDA(ctx, cudaMemcpy2DAsync(st, w, imgs, row_stride_bytes, w, h * (size_t)n_streams, cudaMemcpyHostToDevice,
-                                    ctx->stream));
+    FLV_CUDA(ctx, cudaMemcpy2DAsync(st, w, imgs, row_stride_bytes, w, h * (size_t)n_streams, cudaMemcpyHostToDevice, cs));
   } else {
     for (int s = 0; s < n_streams; ++s)
       FLV_CUDA(ctx, cudaMemcpy2DAsync(st + (size_t)s * w * h, w, imgs + (size_t)s * img_stride_bytes, row_stride_bytes,
-                                      w, h, cudaMemcpyHostToDevice, ctx->stream));
+                                      w, h, cudaMemcpyHostToDevice, cs));
   }
-  return flv_launch_unpack(ctx, slot, n_streams, st, w, w * h);
+  FLV_CUDA(ctx, cudaEventRecord(ctx->img_ready[ring], cs));
+  FLV_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->img_ready[ring], 0));
+  const int rc = flv_launch_unpack(ctx, slot, n_streams, st, w, w * h);
+  if (rc) return rc;
+  FLV_CUDA(ctx, cudaEventRecord(ctx->img_free[ring], ctx->stream));
+  return FLV_OK;
 }
 
 int flv_build_pyramid(flv_ctx* ctx, int slot, int n_streams) {

@@ -32,7 +32,13 @@ struct flv_ctx {
   // staging for FLV_MEM_HOST calls (pinned host + device mirrors)
   void* h_stage; size_t h_stage_bytes;
   void* d_stage; size_t d_stage_bytes;
-  void* d_img_stage; size_t img_stage_bytes;   // tight [S][h][w] landing area of host image uploads
+  // host image uploads: ring of tight [S][h][w] landing areas filled by H2D copies on `copy_stream`, so the copy of the
+  // next frame overlaps the kernels of the current one (the ROS image queue of the reference, tracking nodelet)
+  static constexpr int IMG_RING = 4;
+  void* d_img_stage[IMG_RING]; size_t img_stage_bytes;
+  cudaEvent_t img_ready[IMG_RING], img_free[IMG_RING];
+  cudaStream_t copy_stream;
+  unsigned img_ring_pos;
 
   // LK
   int* d_npts;                    // [S]

@@ -55,9 +55,13 @@ class FrontendBench:
         self.d_nnew = z(S, dtype=torch.int32)
         # pinned result buffers for the e2e mode
         pin = lambda *shape, dtype: torch.zeros(*shape, dtype=dtype).pin_memory()
-        self.h_cur = pin(S, M, 2, dtype=torch.float32); self.h_keep = pin(S, M, dtype=torch.uint8)
-        self.h_right = pin(S, M, 2, dtype=torch.float32); self.h_rstatus = pin(S, M, dtype=torch.uint8)
-        self.h_new = pin(S, M, 2, dtype=torch.float32); self.h_nnew = pin(S, dtype=torch.int32)
+        # (double-buffered: the host reads the results of frame k-1 while frame k computes)
+        self.h_out = [dict(cur=pin(S, M, 2, dtype=torch.float32), keep=pin(S, M, dtype=torch.uint8),
+                           right=pin(S, M, 2, dtype=torch.float32), rstatus=pin(S, M, dtype=torch.uint8),
+                           new=pin(S, M, 2, dtype=torch.float32), nnew=pin(S, dtype=torch.int32)) for _ in range(2)]
+        self.done = [torch.cuda.Event(), torch.cuda.Event()]
+        self.prefetched = -1            # frame-pool index whose host upload is already in flight
+        self.pending = None             # index of the result buffer the host has not consumed yet
         self.slots = [0, 1, 2]          # prev0, cur0, cur1
         self.kf_every = kf_every
         self.collect_lk = False
@@ -88,6 +92,7 @@ class FrontendBench:
         """Frame 0: upload, pyramid, FeatureDEM::detect => the tracked set (init_frame, f2f_tracking.cpp:402-453)."""
         ctx, S = self.ctx, self.S
         self.torch.cuda.synchronize()
+        self.prefetched, self.pending = -1, None
         prev0 = self.slots[0]
         ctx.upload_dev(prev0, S, self.d_pool0[0].data_ptr())
         ctx.build_pyramid(prev0, S)
@@ -115,6 +120,9 @@ class FrontendBench:
     def join(self):
         if self.has_ba:
             self.ba.join(self.stream)
+        if self.pending is not None:                       # last frame's results
+            self.done[self.pending].synchronize()
+            self.pending = None
 
     def step(self, i, mode):
         with self.torch.cuda.stream(self.stream):
@@ -125,9 +133,11 @@ class FrontendBench:
         prev0, cur0, cur1 = self.slots
         k = (i + 1) % self.n_pool
         if mode == "host":
-            ctx.upload_host_async(cur0, S, self.h_pool0[k].data_ptr())
-            ctx.upload_host_async(cur1, S, self.h_pool1[k].data_ptr())
+            if self.prefetched != k:                       # first host-mode step: nothing in flight yet
+                ctx.upload_host_async(cur0, S, self.h_pool0[k].data_ptr())
+                ctx.upload_host_async(cur1, S, self.h_pool1[k].data_ptr())
         else:
+            self.prefetched = -1
             ctx.upload_dev(cur0, S, self.d_pool0[k].data_ptr())
             ctx.upload_dev(cur1, S, self.d_pool1[k].data_ptr())
         ctx.build_pyramid(cur0, S)
@@ -145,11 +155,20 @@ class FrontendBench:
         if self.has_ba:
             self.ba.step(i, mode, self.kf_every)
         if mode == "host":
-            nb = True
-            self.h_cur.copy_(self.d_cur, non_blocking=nb); self.h_keep.copy_(self.d_keep, non_blocking=nb)
-            self.h_right.copy_(self.d_right, non_blocking=nb); self.h_rstatus.copy_(self.d_rstatus, non_blocking=nb)
-            self.h_new.copy_(self.d_new, non_blocking=nb); self.h_nnew.copy_(self.d_nnew, non_blocking=nb)
-            self.stream.synchronize()      # the caller consumes the results every frame
+            o = self.h_out[i & 1]
+            o["cur"].copy_(self.d_cur, non_blocking=True); o["keep"].copy_(self.d_keep, non_blocking=True)
+            o["right"].copy_(self.d_right, non_blocking=True); o["rstatus"].copy_(self.d_rstatus, non_blocking=True)
+            o["new"].copy_(self.d_new, non_blocking=True); o["nnew"].copy_(self.d_nnew, non_blocking=True)
+            self.done[i & 1].record(self.stream)
+            # submit the NEXT frame's images now (library copy stream: the H2D overlaps this frame's kernels), then
+            # consume the PREVIOUS frame's results -- every frame's inputs and outputs cross PCIe, one frame of latency
+            k2 = (i + 2) % self.n_pool
+            ctx.upload_host_async(prev0, S, self.h_pool0[k2].data_ptr())      # next step's cur0 slot
+            ctx.upload_host_async(cur1, S, self.h_pool1[k2].data_ptr())
+            self.prefetched = k2
+            if self.pending is not None:
+                self.done[self.pending].synchronize()
+            self.pending = i & 1
         # the tracked set of the next frame lives in cur0
         self.d_pts, self.d_cur = self.d_cur, self.d_pts
         self.slots = [cur0, prev0, cur1]

@@ -209,8 +209,9 @@ int flv_reprojection_inliers(flv_ctx* ctx, int n_streams, const int* n_lms, cons
 int flv_set_ba_stream(flv_ctx* ctx, void* cuda_stream, int enable);
 
 /* Debug: SM cycle counters of the last flv_ba_optimize for `stream`:
- * out8 = {chi2, build, schur, cholesky, substitution, update, setup, unused}. Synchronises. */
-int flv_ba_profile(flv_ctx* ctx, int stream, long long* out8);
+ * out16 = {chi2, build pose pass, schur products, cholesky, substitution, update, setup, -, schur init, schur staging,
+ * build edge pass, build landmark pass, -...}. Synchronises. */
+int flv_ba_profile(flv_ctx* ctx, int stream, long long* out16);
 
 #ifdef __cplusplus
 }

@@ -280,6 +280,29 @@ def fmat_cv2(from_xy, to_xy):
     return np.zeros(len(from_xy), np.uint8) if m is None else m.ravel().astype(np.uint8)
 
 
+def make_stereo_sequence(n_frames, seed=0, w=640, h=480, K=(384.16455, 384.16455, 320.21445, 238.94403), Z=3.0, baseline=0.05):
+    """Rectified stereo views of the same fronto-parallel plane: right image = left image shifted by the constant
+    disparity fx*b/Z.  Returns (left images, right images, P0, P1, T_cam1_cam0 as SE3)."""
+    from . import synth
+    margin = 96
+    canvas = synth.texture(seed, h + 2 * margin, w + 2 * margin, blur=2)
+    lefts, rights = [], []
+    cx, cy = w / 2.0, h / 2.0
+    disp = K[0] * baseline / Z
+    for k in range(n_frames):
+        tx = 0.012 * k; ty = 0.006 * math.sin(0.5 * k); th = math.radians(0.15 * k)
+        sx, sy = K[0] * tx / Z, K[1] * ty / Z
+        R = np.array([[math.cos(th), -math.sin(th)], [math.sin(th), math.cos(th)]])
+        Rinv = np.linalg.inv(R)
+        for dx, out in ((0.0, lefts), (-disp, rights)):
+            tvec = np.array([cx, cy]) + np.array([sx + dx, sy])
+            A = np.zeros((2, 3)); A[:, :2] = Rinv; A[:, 2] = -Rinv @ tvec + np.array([cx, cy]) + margin
+            out.append(synth.warp_affine(canvas, A, h, w))
+    P0 = np.array([[K[0], 0, K[2], 0], [0, K[1], K[3], 0], [0, 0, 1, 0.0]])
+    P1 = np.array([[K[0], 0, K[2], -K[0] * baseline], [0, K[1], K[3], 0], [0, 0, 1, 0.0]])
+    return lefts, rights, P0, P1, SE3([1.0, 0, 0, 0], [-baseline, 0, 0])
+
+
 def make_depth_sequence(n_frames, seed=0, w=640, h=480, K=(384.16455, 384.16455, 320.21445, 238.94403), Z=3.0):
     """Fronto-parallel textured plane at depth Z seen by a camera that translates parallel to it and rolls slightly:
     the image motion is an exact similarity, the depth image is constant (mm)."""

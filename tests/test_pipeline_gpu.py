@@ -110,6 +110,44 @@ def test_depth_sequence_matches_oracle_frame_by_frame(lib):
     lib.flv_f2f_destroy(h)
 
 
+def test_stereo_rect_sequence_matches_oracle(lib):
+    """STEREO_RECT: exercises the left->right LK + DLT triangulation path of depthInnovation inside the pipeline."""
+    _setup(lib)
+    K = (384.16455, 384.16455, 320.21445, 238.94403)
+    fpara = [30, 15, 5, 500, 0.01, 15]; vpara = [0.1, 0.01, 0.001, 0.001, 0.5, 0.1]; dpara = [0.9, 50.0, 0.0]
+    n_frames = 6
+    L, R, P0, P1, T10 = f2f_ref.make_stereo_sequence(n_frames, seed=5)
+    cfg = Cfg(1, 640, 480, (C.c_double * 4)(*K), (C.c_double * 4)(*K), 1000.0, (C.c_double * 12)(*P0.ravel()),
+              (C.c_double * 12)(*P1.ravel()), (C.c_double * 7)(*T10.to7()), (C.c_double * 7)(0, 0, 0, 1, 0, 0, 0),
+              (C.c_double * 6)(*fpara), (C.c_double * 6)(*vpara), (C.c_double * 3)(*dpara), 0)
+    h = lib.flv_f2f_create(C.byref(cfg), 0)
+    assert h and lib.flv_f2f_last_error(h) == b""
+    lib.flv_f2f_set_ransac_hooks(h, fmat_hook, pnp_hook, None)
+    ref = f2f_ref.F2FTracking("stereo", 640, 480, K, fpara, vpara, dpara, K1=K, P0=P0, P1=P1, T_c1_c0=T10)
+    cap = 600
+    vp = lambda a: a.ctypes.data_as(C.c_void_p)
+    for k in range(n_frames):
+        kf = C.c_int(0); rs = C.c_int(0)
+        rc = lib.flv_f2f_image_feed(h, 0.05 * k, vp(np.ascontiguousarray(L[k])), vp(np.ascontiguousarray(R[k])), C.byref(kf), C.byref(rs))
+        assert rc == 0, lib.flv_f2f_last_error(h)
+        rkf, rrs = ref.image_feed(0.05 * k, L[k], R[k])
+        assert {0: "UnInit", 1: "Tracking", 2: "TrackingFail"}[lib.flv_f2f_state(h)] == ref.state
+        T = np.zeros(7); ids = np.zeros(cap, np.int64); p3 = np.zeros((cap, 3)); has = np.zeros(cap, np.uint8)
+        n = lib.flv_f2f_get_frame(h, vp(T), vp(ids), None, None, vp(p3), vp(has), None, cap)
+        cur = ref.curr
+        assert n == len(cur.lms) and list(ids[:n]) == [l.lm_id for l in cur.lms]
+        if n:
+            ref3 = np.array([l.p3d_w for l in cur.lms])
+            assert np.abs(p3[:n] - ref3).max() <= 1e-6 * max(1.0, np.abs(ref3).max())
+        rT = cur.T_c_w.to7()
+        assert np.abs(T[4:] - rT[4:]).max() <= 1e-6
+    assert ref.state == "Tracking"
+    # the triangulated depth of the plane is ~3 m
+    z = np.array([l.p3d_c[2] for l in ref.curr.lms])
+    assert abs(np.median(z) - 3.0) < 0.1
+    lib.flv_f2f_destroy(h)
+
+
 def test_builtin_ransac_tracks_without_hooks(lib):
     """The product's own host RANSAC stand-ins (no OpenCV): the sequence must track with most points as inliers and
     the recovered camera translation must follow the synthetic motion (12 mm per frame along the plane)."""

@@ -13,10 +13,10 @@ for rep in range(2):
     t = time.perf_counter()
     poses, lms, active, stats = ba_synth.solve_batch_host(ctx, batch)
     dt = time.perf_counter() - t
-names = ["chi2", "build", "schur", "cholesky", "subst", "update", "setup", "-"]
+names = ["chi2", "build:pose", "schur:prod", "cholesky", "subst", "update", "setup", "-", "schur:init", "schur:stage", "build:edge", "build:lm", "-", "-", "-", "-"]
 pr = ctx.ba_profile(0)
 tot = pr.sum()
 print(f"W={W} S={S} E={len(probs[0].ep)} L={len(probs[0].lms)} iters={stats[0].iterations_run} culled={stats[0].n_culled} "
       f"host wall {dt*1e3:.2f} ms, kernel cycles {tot} (~{tot/1.9e6:.2f} ms @1.9GHz)")
 for n, v in zip(names, pr):
-    print(f"  {n:9s} {v:12d} cycles {100.0*v/max(tot,1):5.1f}%")
+    print(f"  {n:12s} {v:12d} cycles {100.0*v/max(tot,1):5.1f}%")
