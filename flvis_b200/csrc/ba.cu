@@ -29,7 +29,7 @@
 
 namespace {
 
-constexpr int BA_THREADS = 512;
+constexpr int BA_THREADS = 384;          // 12 warps: 168 registers per thread keep the 36 Schur accumulators of a lane resident
 constexpr int BA_WARPS = BA_THREADS / 32;
 constexpr int BA_MAX_POSES = 32;
 constexpr int BA_MAX_FREE = 24;          // reduced system n <= 144 -> S fits shared memory
@@ -180,7 +180,7 @@ __device__ double block_max(double v, double* red) {
 
 constexpr int BA_MAX_PAIRS = BA_MAX_FREE * (BA_MAX_FREE + 1) / 2;   // 300
 constexpr int BA_MAX_CHUNKS = 128;
-constexpr int BA_CHUNK_PLANES = 18 + 6 + 3;   // W (6x3) per slot, Dinv (sym 3x3) + Dinv*bl per landmark
+constexpr int BA_CHUNK_PLANES = 18 + 3;       // Z = W Ld (6x3) per slot, Ld^T bl per landmark
 constexpr int BA_MAX_CAP = 1023;              // chunk-local positions are packed 10 bits each
 
 struct Sh {   // fixed-size shared state
@@ -189,7 +189,7 @@ struct Sh {   // fixed-size shared state
   double part[2 * BA_MAX_FREE][27];     // pose-pass partial sums
   double bp[6 * BA_MAX_FREE];
   double x[6 * BA_MAX_FREE];
-  double piv;
+  double invd[6 * BA_MAX_FREE];
   int pidx[BA_MAX_POSES];
   int pose_of[BA_MAX_FREE];
   int pcount[BA_MAX_POSES];
@@ -211,10 +211,10 @@ __device__ __forceinline__ void mark(Sh& sh, int slot) {
 struct Ws {
   double *pbk, *lbk;
   double *W, *Bw, *g, *hl, *bb, *uvs;       // [18|12|2|6|3|2][ME]
-  double *Hll, *bl, *Dinv, *Dv;             // [6|3|6|3][ML]
+  double *Hll, *bl, *Dinv, *Dv, *Ld;        // [6|3|6|3|6][ML]
   int *tab;                                 // [P][L]: edge id during setup, then slot of edge (p,l) or -1
   unsigned* lmask;                          // [L]
-  int *slot_e, *slot_pl;                    // [ME]: edge id, p | l << 8
+  int *slot_e, *slot_pl, *slot_lp;          // [ME]: edge id, p | l << 8, position in the landmark-major (CSR) order
   int *lw, *lstart;                         // [L+1] exclusive prefixes (chunk weights, edge counts)
   int *cp_off;                              // [nch][P+1] slot offsets of (chunk, pose) runs
   int *poff;                                // [nch*nblk + 1] member-list offsets of (chunk, pose pair)
@@ -369,6 +369,7 @@ __device__ void setup_active(const flv_ba_problem& pb, const int* ep, const int*
         const int s = base + __popc(bal & ((1u << lane) - 1));
         const int e = ws.tab[p * L + l];
         ws.slot_e[s] = e; ws.slot_pl[s] = p | (l << 8);
+        ws.slot_lp[s] = ws.lstart[l] + __popc(ws.lmask[l] & ((1u << p) - 1));
         ws.uvs[s] = uv[2 * (size_t)e]; ws.uvs[ws.ME + s] = uv[2 * (size_t)e + 1];
         ws.tab[p * L + l] = s;
       }
@@ -435,11 +436,12 @@ __device__ void build_system(const flv_ba_problem& pb, const Cam& cam, const dou
       const double c = r[0] * r[0] + r[1] * r[1];
       const double rho1 = (c <= d2) ? 1.0 : delta / sqrt(c);
       const double o0 = -r[0] * rho1, o1 = -r[1] * rho1;
+      const int lp = ws.slot_lp[s];           // shares are stored landmark-major so that the landmark pass reads runs
 #pragma unroll
-      for (int i = 0; i < 3; ++i) ws.bb[i * ME + s] = A[i] * o0 + A[3 + i] * o1;
-      ws.hl[0 * ME + s] = rho1 * (A[0] * A[0] + A[3] * A[3]); ws.hl[1 * ME + s] = rho1 * (A[0] * A[1] + A[3] * A[4]);
-      ws.hl[2 * ME + s] = rho1 * (A[0] * A[2] + A[3] * A[5]); ws.hl[3 * ME + s] = rho1 * (A[1] * A[1] + A[4] * A[4]);
-      ws.hl[4 * ME + s] = rho1 * (A[1] * A[2] + A[4] * A[5]); ws.hl[5 * ME + s] = rho1 * (A[2] * A[2] + A[5] * A[5]);
+      for (int i = 0; i < 3; ++i) ws.bb[i * ME + lp] = A[i] * o0 + A[3 + i] * o1;
+      ws.hl[0 * ME + lp] = rho1 * (A[0] * A[0] + A[3] * A[3]); ws.hl[1 * ME + lp] = rho1 * (A[0] * A[1] + A[3] * A[4]);
+      ws.hl[2 * ME + lp] = rho1 * (A[0] * A[2] + A[3] * A[5]); ws.hl[3 * ME + lp] = rho1 * (A[1] * A[1] + A[4] * A[4]);
+      ws.hl[4 * ME + lp] = rho1 * (A[1] * A[2] + A[4] * A[5]); ws.hl[5 * ME + lp] = rho1 * (A[2] * A[2] + A[5] * A[5]);
       if (sh.pidx[p] >= 0) {
 #pragma unroll
         for (int i = 0; i < 6; ++i)
@@ -454,16 +456,14 @@ __device__ void build_system(const flv_ba_problem& pb, const Cam& cam, const dou
     __syncthreads();
     mark(sh, 10);
     for (int l = tid; l < L; l += BA_THREADS) {
-      unsigned m = ws.lmask[l];
-      if (!m) continue;
+      const int j0 = ws.lstart[l], j1 = ws.lstart[l + 1];
+      if (j0 == j1) continue;
       double H[6] = {0, 0, 0, 0, 0, 0}, b[3] = {0, 0, 0};
-      while (m) {
-        const int p = __ffs(m) - 1; m &= m - 1;
-        const int s = ws.tab[p * L + l];
+      for (int j = j0; j < j1; ++j) {             // pose order; addresses do not depend on loaded data
 #pragma unroll
-        for (int i = 0; i < 6; ++i) H[i] += ws.hl[i * ME + s];
+        for (int i = 0; i < 6; ++i) H[i] += ws.hl[i * ME + j];
 #pragma unroll
-        for (int i = 0; i < 3; ++i) b[i] += ws.bb[i * ME + s];
+        for (int i = 0; i < 3; ++i) b[i] += ws.bb[i * ME + j];
       }
 #pragma unroll
       for (int i = 0; i < 6; ++i) ws.Hll[i * ML + l] = H[i];
@@ -559,15 +559,19 @@ __device__ void solve_system(const flv_ba_problem& pb, double lambda, double* S,
                    D5 = (a * d - b * b) * id;
       ws.Dinv[l] = D0; ws.Dinv[ML + l] = D1; ws.Dinv[2 * ML + l] = D2; ws.Dinv[3 * ML + l] = D3;
       ws.Dinv[4 * ML + l] = D4; ws.Dinv[5 * ML + l] = D5;
+      // Dinv = Ld Ld^T (3x3 Cholesky): W Dinv W^T = (W Ld)(W Ld)^T, so the pair products need ONE factor Z = W Ld per edge
+      const double l00 = sqrt(D0), il00 = 1.0 / l00, l10 = D1 * il00, l20 = D2 * il00;
+      const double l11 = sqrt(D3 - l10 * l10), l21 = (D4 - l20 * l10) / l11, l22 = sqrt(D5 - l20 * l20 - l21 * l21);
+      ws.Ld[l] = l00; ws.Ld[ML + l] = l10; ws.Ld[2 * ML + l] = l20; ws.Ld[3 * ML + l] = l11; ws.Ld[4 * ML + l] = l21;
+      ws.Ld[5 * ML + l] = l22;
       const double b0 = ws.bl[l], b1 = ws.bl[ML + l], b2 = ws.bl[2 * ML + l];
-      ws.Dv[l] = D0 * b0 + D1 * b1 + D2 * b2; ws.Dv[ML + l] = D1 * b0 + D3 * b1 + D4 * b2;
-      ws.Dv[2 * ML + l] = D2 * b0 + D4 * b1 + D5 * b2;
+      ws.Dv[l] = l00 * b0 + l10 * b1 + l20 * b2; ws.Dv[ML + l] = l11 * b1 + l21 * b2; ws.Dv[2 * ML + l] = l22 * b2;   // Ld^T bl
     }
     __syncthreads();
     mark(sh, 8);
-    const int cap = sh.cap, half = lane & 1, mslot = lane >> 1;
-    double* Wc = chunk;
-    double* Dc = chunk + 18 * cap;
+    const int cap = sh.cap;
+    double* Zc = chunk;                   // [18][cap]  Z = W Ld of the chunk's slots
+    double* Vc = chunk + 18 * cap;        // [3][cap]   Ld^T bl of the chunk's landmarks
     for (int ch = 0; ch < sh.nch; ++ch) {
       const int sb = sh.chunk_sb[ch], ns = sh.chunk_sb[ch + 1] - sb, lb = sh.chunk_lb[ch], nl = sh.chunk_lb[ch + 1] - lb;
       // this warp's member-list bounds for the chunk (lane j <-> pair warp + 16 j); issued before the staging loads
@@ -576,14 +580,25 @@ __device__ void solve_system(const flv_ba_problem& pb, double lambda, double* S,
         const int blk = warp + BA_WARPS * lane;
         if (blk < nblk) { my0 = ws.poff[ch * nblk + blk]; my1 = ws.poff[ch * nblk + blk + 1]; }
       }
-#pragma unroll 6
-      for (int c = 0; c < 18; ++c)
-        for (int i = tid; i < ns; i += BA_THREADS) Wc[c * cap + i] = ws.W[c * ME + sb + i];
+      for (int i = tid; i < ns; i += BA_THREADS) {
+        const int sl = sb + i, pl = ws.slot_pl[sl];
+        double w[18];
+#pragma unroll
+        for (int c = 0; c < 18; ++c) w[c] = ws.W[c * ME + sl];          // 18 independent coalesced loads in flight
+        if (sh.pidx[pl & 255] < 0) continue;                            // fixed pose: W was never written, Z is never read
+        const int l = pl >> 8;
+        const double l00 = ws.Ld[l], l10 = ws.Ld[ML + l], l20 = ws.Ld[2 * ML + l], l11 = ws.Ld[3 * ML + l],
+                     l21 = ws.Ld[4 * ML + l], l22 = ws.Ld[5 * ML + l];
+#pragma unroll
+        for (int r = 0; r < 6; ++r) {
+          Zc[(3 * r) * cap + i] = w[3 * r] * l00 + w[3 * r + 1] * l10 + w[3 * r + 2] * l20;
+          Zc[(3 * r + 1) * cap + i] = w[3 * r + 1] * l11 + w[3 * r + 2] * l21;
+          Zc[(3 * r + 2) * cap + i] = w[3 * r + 2] * l22;
+        }
+      }
       for (int i = tid; i < nl; i += BA_THREADS) {
-#pragma unroll
-        for (int c = 0; c < 6; ++c) Dc[c * cap + i] = ws.Dinv[c * ML + lb + i];
-#pragma unroll
-        for (int c = 0; c < 3; ++c) Dc[(6 + c) * cap + i] = ws.Dv[c * ML + lb + i];
+        const double v0 = ws.Dv[lb + i], v1 = ws.Dv[ML + lb + i], v2 = ws.Dv[2 * ML + lb + i];
+        Vc[i] = v0; Vc[cap + i] = v1; Vc[2 * cap + i] = v2;
       }
       __syncthreads();
       mark(sh, 9);
@@ -591,57 +606,57 @@ __device__ void solve_system(const flv_ba_problem& pb, double lambda, double* S,
         const int i0 = __shfl_sync(FULL, my0, j), i1 = __shfl_sync(FULL, my1, j);
         if (i0 == i1) continue;
         const int a = sh.pair_a[blk], b = sh.pair_b[blk];
-        double acc[18];
+        // one lane per member: acc[6 i + jc] += sum_c Za[i][c] Zb[jc][c]  (block (a,b) of W Dinv W^T)
+        double acc[36];
 #pragma unroll
-        for (int i = 0; i < 18; ++i) acc[i] = 0;
-        int k = i0 + mslot;
+        for (int i = 0; i < 36; ++i) acc[i] = 0;
+        int k = i0 + lane;
         int ent = k < i1 ? ws.pairs[k] : 0;
-        for (; k < i1; k += 16) {
+        for (; k < i1; k += 32) {
           const int cur = ent;
-          if (k + 16 < i1) ent = ws.pairs[k + 16];          // prefetch the next round's member
-          const int pa = cur & 1023, pbb = (cur >> 10) & 1023, lp = cur >> 20;
-          double wa[18], D[6];
+          if (k + 32 < i1) ent = ws.pairs[k + 32];          // prefetch the next round's member
+          const int pa = cur & 1023, pbb = (cur >> 10) & 1023;
+          double za[18];
 #pragma unroll
-          for (int i = 0; i < 18; ++i) wa[i] = Wc[i * cap + pa];
+          for (int i = 0; i < 18; ++i) za[i] = Zc[i * cap + pa];
 #pragma unroll
-          for (int i = 0; i < 6; ++i) D[i] = Dc[i * cap + lp];
+          for (int jc = 0; jc < 6; ++jc) {
+            const double z0 = Zc[(3 * jc) * cap + pbb], z1 = Zc[(3 * jc + 1) * cap + pbb], z2 = Zc[(3 * jc + 2) * cap + pbb];
 #pragma unroll
-          for (int jj = 0; jj < 3; ++jj) {
-            const int row = 3 * half + jj;                   // row of W_b (6x3) = column of the 6x6 block
-            const double w0 = Wc[(3 * row) * cap + pbb], w1 = Wc[(3 * row + 1) * cap + pbb], w2 = Wc[(3 * row + 2) * cap + pbb];
-            const double t0 = w0 * D[0] + w1 * D[1] + w2 * D[2], t1 = w0 * D[1] + w1 * D[3] + w2 * D[4],
-                         t2 = w0 * D[2] + w1 * D[4] + w2 * D[5];
-#pragma unroll
-            for (int i = 0; i < 6; ++i) acc[3 * i + jj] += wa[3 * i] * t0 + wa[3 * i + 1] * t1 + wa[3 * i + 2] * t2;
+            for (int i = 0; i < 6; ++i) acc[6 * i + jc] += za[3 * i] * z0 + za[3 * i + 1] * z1 + za[3 * i + 2] * z2;
           }
         }
-        // reduce over the 16 member slots (lanes of equal parity): xor 2, 4, 8, 16
+        // butterfly reduce-scatter of the first 32 sums (lane e ends with the total of acc[e]); plain tree for the last 4
 #pragma unroll
-        for (int i = 0; i < 18; ++i) {
-          double v = acc[i];
+        for (int e = 32; e < 36; ++e) acc[e] = warp_sum(acc[e]);
 #pragma unroll
-          for (int o = 2; o < 32; o <<= 1) v += __shfl_xor_sync(FULL, v, o);
-          acc[i] = v;
+        for (int w2 = 16; w2 >= 1; w2 >>= 1) {
+          const bool up = (lane & w2) != 0;
+#pragma unroll
+          for (int i = 0; i < w2; ++i) {
+            const double send = up ? acc[i] : acc[i + w2];
+            const double keep = up ? acc[i + w2] : acc[i];
+            acc[i] = keep + __shfl_xor_sync(FULL, send, w2);
+          }
         }
-        if (lane < 2) {
-#pragma unroll
-          for (int i = 0; i < 6; ++i)
-#pragma unroll
-            for (int jj = 0; jj < 3; ++jj) {
-              const int jc = 3 * half + jj;
-              S[(6 * b + jc) * ld + 6 * a + i] -= acc[3 * i + jj];   // block (b,a), b >= a: lower triangle (+ mirror if a == b)
-            }
+        {
+          const int e = lane, i = e / 6, jc = e - 6 * i;
+          S[(6 * b + jc) * ld + 6 * a + i] -= acc[0];        // block (b,a), b >= a: lower triangle (both triangles if a == b)
+          if (lane < 4) {
+            const double v = lane == 0 ? acc[32] : lane == 1 ? acc[33] : lane == 2 ? acc[34] : acc[35];
+            S[(6 * b + 2 + lane) * ld + 6 * a + 5] -= v;     // e = 32 + lane: i = 5, jc = 2 + lane
+          }
         }
         if (a == b) {
-          // right-hand side of pose a: y_a -= sum_l W_al (Dinv bl)_l ; lanes split the members 32 ways
+          // right-hand side of pose a: y_a -= sum_l Z_al (Ld^T bl)_l
           double cf[6] = {0, 0, 0, 0, 0, 0};
           for (int k2 = i0 + lane; k2 < i1; k2 += 32) {
             const int cur = ws.pairs[k2];
             const int pa = cur & 1023, lp = cur >> 20;
-            const double v0 = Dc[6 * cap + lp], v1 = Dc[7 * cap + lp], v2 = Dc[8 * cap + lp];
+            const double v0 = Vc[lp], v1 = Vc[cap + lp], v2 = Vc[2 * cap + lp];
 #pragma unroll
             for (int i = 0; i < 6; ++i)
-              cf[i] += Wc[(3 * i) * cap + pa] * v0 + Wc[(3 * i + 1) * cap + pa] * v1 + Wc[(3 * i + 2) * cap + pa] * v2;
+              cf[i] += Zc[(3 * i) * cap + pa] * v0 + Zc[(3 * i + 1) * cap + pa] * v1 + Zc[(3 * i + 2) * cap + pa] * v2;
           }
 #pragma unroll
           for (int i = 0; i < 6; ++i) { const double v = warp_sum(cf[i]); if (lane == 0) y[6 * a + i] -= v; }
@@ -654,45 +669,50 @@ __device__ void solve_system(const flv_ba_problem& pb, double lambda, double* S,
   if (tid == 0) sh.fail = 0;
   __syncthreads();
   mark(sh, 2);
-  // left-looking Cholesky on the augmented matrix [S ; y^T]: row n is the right-hand side, so the forward
-  // substitution comes for free.  T threads per row split each dot product.
+  // Right-looking Cholesky (LDL^T form) of the augmented matrix [S ; y^T] (row n = right-hand side): one barrier per
+  // column, no square roots -- after step j column j holds A_ij = L_ij sqrt(d_j), the diagonal d_j = L_jj^2, and
+  //   x_j = (y_j - sum_{k>j} A_kj x_k) / d_j.
   int T = 1;
   while ((n + 1) * (T << 1) <= BA_THREADS && T < 32) T <<= 1;
   const int row = tid / T, t = tid - row * T;
+  bool bad = false;
   for (int j = 0; j < n; ++j) {
-    double sres = 0;
-    const bool mine = row >= j && row <= n;
-    const double* Li = row < n ? S + row * ld : y;         // row n: y holds b (entries < j already y_k)
-    double acc = 0;
-    if (mine) {
-      const double* Lj = S + j * ld;
-      for (int k = t; k < j; k += T) acc += Li[k] * Lj[k];
-    }
-    for (int o = T >> 1; o > 0; o >>= 1) acc += __shfl_xor_sync(FULL, acc, o);   // whole warp, uniform
-    if (mine) {
-      sres = Li[j] - acc;
-      if (row == j && t == 0) sh.piv = sres;
-    }
-    __syncthreads();
-    const double d = sh.piv;
-    if (!(d > 0)) { if (tid == 0) sh.fail = 1; }
-    const double isd = rsqrt(d > 0 ? d : 1.0);
-    if (mine && t == 0) {
-      if (row == j) S[j * ld + j] = d * isd;
-      else if (row < n) S[row * ld + j] = sres * isd;
-      else y[j] = sres * isd;
+    const double d = S[j * ld + j];
+    if (!(d > 0)) { bad = true; break; }                     // same value in every thread: uniform exit
+    const double inv = 1.0 / d;
+    if (tid == 0) sh.invd[j] = inv;
+    if (row > j && row <= n) {
+      double* Ai = row < n ? S + row * ld : y;
+      const double f = Ai[j] * inv;
+      const int kmax = row < n ? row : n - 1;
+      for (int k = j + 1 + t; k <= kmax; k += T) Ai[k] -= f * S[k * ld + j];
     }
     __syncthreads();
   }
+  if (bad && tid == 0) sh.fail = 1;
+  __syncthreads();
   mark(sh, 3);
-  // back substitution x = L^-T y, column oriented
-  for (int j = n - 1; j >= 0; --j) {
-    const double xj = y[j] / S[j * ld + j];
-    __syncthreads();
-    if (tid < j) y[tid] -= S[j * ld + tid] * xj;
-    if (tid == j) sh.x[j] = xj;
-    __syncthreads();
+  // back substitution inside one warp: lane holds w[lane + 32 q]; row j of the factor is read contiguously
+  if (warp == 0 && !bad) {
+    double wv[5];
+#pragma unroll
+    for (int q = 0; q < 5; ++q) wv[q] = (lane + 32 * q) < n ? y[lane + 32 * q] : 0.0;
+    for (int j = n - 1; j >= 0; --j) {
+      const int jq = j >> 5, jl = j & 31;
+      double own = wv[0];
+#pragma unroll
+      for (int q = 1; q < 5; ++q) own = jq == q ? wv[q] : own;
+      const double xj = __shfl_sync(FULL, own, jl) * sh.invd[j];
+      const double* Aj = S + j * ld;
+#pragma unroll
+      for (int q = 0; q < 5; ++q) {
+        const int k = lane + 32 * q;
+        if (k < j) wv[q] -= Aj[k] * xj;
+      }
+      if (lane == 0) sh.x[j] = xj;
+    }
   }
+  __syncthreads();
   mark(sh, 4);
 }
 
@@ -703,24 +723,28 @@ __device__ double apply_update(const flv_ba_problem& pb, double lambda, double* 
   double sc = 0;
   for (int i = tid; i < 7 * P; i += BA_THREADS) ws.pbk[i] = poses[i];
   if (!pb.fix_landmarks) {
-    for (int l = tid; l < L; l += BA_THREADS) {
-      double* X = lms + 3 * (size_t)l;
-      ws.lbk[3 * (size_t)l] = X[0]; ws.lbk[3 * (size_t)l + 1] = X[1]; ws.lbk[3 * (size_t)l + 2] = X[2];
-      unsigned m = ws.lmask[l];
-      if (!m) continue;
-      const double bl0 = ws.bl[l], bl1 = ws.bl[ML + l], bl2 = ws.bl[2 * ML + l];
-      double c0 = bl0, c1 = bl1, c2 = bl2;
-      while (m) {
-        const int p = __ffs(m) - 1; m &= m - 1;
-        const int pi = sh.pidx[p];
-        if (pi < 0) continue;
-        const int s = ws.tab[p * L + l];
+    // slot pass: t_s = W_s^T x_p, stored landmark-major (reuses the bb planes); landmark pass: c = bl - sum t, dX = Dinv c
+    for (int s = tid; s < sh.nact; s += BA_THREADS) {
+      const int pi = sh.pidx[ws.slot_pl[s] & 255], lp = ws.slot_lp[s];
+      double t0 = 0, t1 = 0, t2 = 0;
+      if (pi >= 0) {
         const double* xp = sh.x + 6 * pi;
 #pragma unroll
         for (int i = 0; i < 6; ++i) {
-          c0 -= ws.W[(3 * i) * ME + s] * xp[i]; c1 -= ws.W[(3 * i + 1) * ME + s] * xp[i]; c2 -= ws.W[(3 * i + 2) * ME + s] * xp[i];
+          t0 += ws.W[(3 * i) * ME + s] * xp[i]; t1 += ws.W[(3 * i + 1) * ME + s] * xp[i]; t2 += ws.W[(3 * i + 2) * ME + s] * xp[i];
         }
       }
+      ws.bb[lp] = t0; ws.bb[ME + lp] = t1; ws.bb[2 * ME + lp] = t2;
+    }
+    __syncthreads();
+    for (int l = tid; l < L; l += BA_THREADS) {
+      double* X = lms + 3 * (size_t)l;
+      ws.lbk[3 * (size_t)l] = X[0]; ws.lbk[3 * (size_t)l + 1] = X[1]; ws.lbk[3 * (size_t)l + 2] = X[2];
+      const int j0 = ws.lstart[l], j1 = ws.lstart[l + 1];
+      if (j0 == j1) continue;
+      const double bl0 = ws.bl[l], bl1 = ws.bl[ML + l], bl2 = ws.bl[2 * ML + l];
+      double c0 = bl0, c1 = bl1, c2 = bl2;
+      for (int j = j0; j < j1; ++j) { c0 -= ws.bb[j]; c1 -= ws.bb[ME + j]; c2 -= ws.bb[2 * ME + j]; }
       const double D0 = ws.Dinv[l], D1 = ws.Dinv[ML + l], D2 = ws.Dinv[2 * ML + l], D3 = ws.Dinv[3 * ML + l],
                    D4 = ws.Dinv[4 * ML + l], D5 = ws.Dinv[5 * ML + l];
       const double x0 = D0 * c0 + D1 * c1 + D2 * c2, x1 = D1 * c0 + D3 * c1 + D4 * c2, x2 = D2 * c0 + D4 * c1 + D5 * c2;
@@ -748,8 +772,8 @@ __host__ __device__ inline size_t poff_capacity() { return (size_t)BA_MAX_CHUNKS
 
 // workspace carve-up (doubles first, then ints); shared by the kernel and ws_stride_bytes()
 struct WsLayout {
-  size_t pbk, lbk, W, Bw, g, hl, bb, uvs, Hll, bl, Dinv, Dv, n_doubles;
-  size_t tab, lmask, slot_e, slot_pl, lw, lstart, cp_off, poff, pairs, n_ints;
+  size_t pbk, lbk, W, Bw, g, hl, bb, uvs, Hll, bl, Dinv, Dv, Ld, n_doubles;
+  size_t tab, lmask, slot_e, slot_pl, slot_lp, lw, lstart, cp_off, poff, pairs, n_ints;
 };
 __host__ __device__ inline WsLayout ws_layout(int MP, int ML, int ME) {
   WsLayout o; size_t d = 0, i = 0;
@@ -758,9 +782,9 @@ __host__ __device__ inline WsLayout ws_layout(int MP, int ML, int ME) {
   o.lbk = d; d += 3 * L + (L & 1);
   o.W = d; d += 18 * E; o.Bw = d; d += 12 * E; o.g = d; d += 2 * E; o.hl = d; d += 6 * E; o.bb = d; d += 3 * E;
   o.uvs = d; d += 2 * E;
-  o.Hll = d; d += 6 * L; o.bl = d; d += 3 * L; o.Dinv = d; d += 6 * L; o.Dv = d; d += 3 * L;
+  o.Hll = d; d += 6 * L; o.bl = d; d += 3 * L; o.Dinv = d; d += 6 * L; o.Dv = d; d += 3 * L; o.Ld = d; d += 6 * L;
   o.n_doubles = d;
-  o.tab = i; i += P * L; o.lmask = i; i += L; o.slot_e = i; i += E; o.slot_pl = i; i += E;
+  o.tab = i; i += P * L; o.lmask = i; i += L; o.slot_e = i; i += E; o.slot_pl = i; i += E; o.slot_lp = i; i += E;
   o.lw = i; i += L + 1; o.lstart = i; i += L + 1; o.cp_off = i; i += (size_t)BA_MAX_CHUNKS * (P + 1);
   o.poff = i; i += poff_capacity(); o.pairs = i; i += pair_capacity(MP, ME);
   o.n_ints = i;
@@ -786,8 +810,8 @@ __global__ void __launch_bounds__(BA_THREADS, 1) ba_kernel(BAArgs a) {
     double* d = (double*)(a.ws + (size_t)s * a.ws_stride);
     int* ib = (int*)(d + lo.n_doubles);
     ws.pbk = d + lo.pbk; ws.lbk = d + lo.lbk; ws.W = d + lo.W; ws.Bw = d + lo.Bw; ws.g = d + lo.g; ws.hl = d + lo.hl;
-    ws.bb = d + lo.bb; ws.uvs = d + lo.uvs; ws.Hll = d + lo.Hll; ws.bl = d + lo.bl; ws.Dinv = d + lo.Dinv; ws.Dv = d + lo.Dv;
-    ws.tab = ib + lo.tab; ws.lmask = (unsigned*)(ib + lo.lmask); ws.slot_e = ib + lo.slot_e; ws.slot_pl = ib + lo.slot_pl;
+    ws.bb = d + lo.bb; ws.uvs = d + lo.uvs; ws.Hll = d + lo.Hll; ws.bl = d + lo.bl; ws.Dinv = d + lo.Dinv; ws.Dv = d + lo.Dv; ws.Ld = d + lo.Ld;
+    ws.tab = ib + lo.tab; ws.lmask = (unsigned*)(ib + lo.lmask); ws.slot_e = ib + lo.slot_e; ws.slot_pl = ib + lo.slot_pl; ws.slot_lp = ib + lo.slot_lp;
     ws.lw = ib + lo.lw; ws.lstart = ib + lo.lstart; ws.cp_off = ib + lo.cp_off; ws.poff = ib + lo.poff;
     ws.pairs = ib + lo.pairs;
     ws.pair_cap = (int)pair_capacity(a.max_poses, a.max_edges); ws.ME = a.max_edges; ws.ML = a.max_lms;

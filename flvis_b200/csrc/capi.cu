@@ -1,6 +1,7 @@
 // C ABI of libflvis_b200: context management, host<->device staging, argument checking.
 // The entry points are declared (with the reference call each replaces) in include/flvis_b200.h.
 #include <new>
+#include <stdlib.h>
 #include "ctx.h"
 
 namespace {
@@ -62,6 +63,7 @@ int flv_create(flv_ctx** out, int device, int max_streams, int img_w, int img_h,
   ctx->device = device; ctx->S = max_streams; ctx->w = img_w; ctx->h = img_h; ctx->max_pts = max_pts;
   FLV_CUDA(ctx, cudaSetDevice(device));
   build_geom(ctx->geom, img_w, img_h);
+  ctx->no_fused_ingest = getenv("FLV_NO_FUSED_INGEST") ? atoi(getenv("FLV_NO_FUSED_INGEST")) : 0;
   FLV_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
   ctx->own_stream = true;
   const size_t S = max_streams;

@@ -27,6 +27,8 @@ struct flv_ctx {
   cudaStream_t stream;
   bool own_stream;
   long long launches;
+  int l1_valid[FLV_NUM_SLOTS];   // level 1 of the slot was produced by the fused ingest kernel (consumed by build_pyramid)
+  int no_fused_ingest;           // FLV_NO_FUSED_INGEST=1: A/B switch for tests
   char err[512];
 
   // staging for FLV_MEM_HOST calls (pinned host + device mirrors)

@@ -80,11 +80,90 @@ __global__ void __launch_bounds__(256) unpack_images_kernel(const uint8_t* __res
   }
 }
 
+
+// Fused ingest + first pyrDown: one pass over the source image writes the slot's pitched level 0 AND level 1.
+// A warp owns 64 output columns (lane = two adjacent outputs = one aligned input word + a byte from each neighbour,
+// fetched by shuffle) and marches down ROWS output rows keeping the five horizontal sums of the vertical window in
+// registers as packed u16 pairs -- no shared memory; (t0 + 4 t1 + 6 t2 + 4 t3 + t4) <= 4080 and 16 * 4080 + 128 < 65536,
+// so both halves of a register are summed and rounded with ordinary 32-bit adds.  Requires w % 4 == 0 and 4-byte
+// aligned source rows (otherwise the generic unpack + pyr_down path runs).
+constexpr int FUSED_ROWS = 8;     // output rows per warp (16 owned input rows + 3 halo rows)
+constexpr int FUSED_WARPS = 4;
+
+__device__ __forceinline__ unsigned hsum_pair(unsigned A, unsigned B, unsigned C) {
+  const unsigned lo = __dp4a(__byte_perm(A, B, 0x5432), 0x04060401u, (B >> 16) & 0xffu);   // taps X-2 .. X+2
+  const unsigned hi = __dp4a(B, 0x04060401u, C & 0xffu);                                     // taps X   .. X+4
+  return lo | (hi << 16);
+}
+
+__global__ void __launch_bounds__(FUSED_WARPS * 32) ingest_l1_kernel(const uint8_t* __restrict__ src, size_t row_stride,
+                                                                     size_t img_stride, uint8_t* __restrict__ slot_base,
+                                                                     size_t stream_stride, size_t off0, int pitch0,
+                                                                     size_t off1, int pitch1, int w, int h, int ow, int oh) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int s = blockIdx.z;
+  const int oy0 = (blockIdx.y * FUSED_WARPS + warp) * FUSED_ROWS;
+  if (oy0 >= oh) return;
+  const int X = blockIdx.x * 128 + 4 * lane;          // first input column of this lane's word
+  const bool act = X < w;                              // w % 4 == 0: a word is entirely inside or outside
+  const uint8_t* img = src + (size_t)s * img_stride;
+  uint8_t* L0 = slot_base + (size_t)s * stream_stride + off0;
+  uint8_t* L1 = slot_base + (size_t)s * stream_stride + off1;
+  const int y_lo = 2 * oy0, y_hi = min(2 * (oy0 + FUSED_ROWS), h);     // owned input rows (written to level 0)
+
+  auto row_sums = [&](int y) -> unsigned {              // y may be outside [0,h): BORDER_REFLECT_101
+    const int yr = y < 0 ? -y : (y >= h ? 2 * h - 2 - y : y);
+    unsigned B = 0;
+    if (act) B = *reinterpret_cast<const unsigned*>(img + (size_t)yr * row_stride + X);
+    unsigned A = __shfl_up_sync(0xffffffffu, B, 1);
+    unsigned C = __shfl_down_sync(0xffffffffu, B, 1);
+    if (act) {
+      if (lane == 0) {
+        if (X == 0) A = __byte_perm(B, 0, 0x1244);     // columns -2,-1 -> 2,1 into bytes 2,3
+        else A = *reinterpret_cast<const unsigned*>(img + (size_t)yr * row_stride + X - 4);
+      }
+      if (X + 4 >= w) C = (B >> 16) & 0xffu;            // column w -> w-2
+      else if (lane == 31) C = *reinterpret_cast<const unsigned*>(img + (size_t)yr * row_stride + X + 4);
+      if (y == yr && y >= y_lo && y < y_hi) *reinterpret_cast<unsigned*>(L0 + (size_t)y * pitch0 + X) = B;
+    }
+    return hsum_pair(A, B, C);
+  };
+
+  unsigned h0 = row_sums(2 * oy0 - 2), h1 = row_sums(2 * oy0 - 1), h2 = row_sums(2 * oy0);
+  const int ox = blockIdx.x * 64 + 2 * lane;
+#pragma unroll 2
+  for (int r = 0; r < FUSED_ROWS; ++r) {
+    const int oy = oy0 + r;
+    if (oy >= oh) break;
+    const unsigned h3 = row_sums(2 * oy + 1), h4 = row_sums(2 * oy + 2);
+    const unsigned v = h0 + 4u * h1 + 6u * h2 + 4u * h3 + h4 + 0x00800080u;
+    if (act && ox < ow) {
+      const unsigned short o2 = (unsigned short)(((v >> 8) & 0xffu) | ((v >> 16) & 0xff00u));
+      if (ox + 1 < ow) *reinterpret_cast<unsigned short*>(L1 + (size_t)oy * pitch1 + ox) = o2;
+      else L1[(size_t)oy * pitch1 + ox] = (uint8_t)(o2 & 0xff);
+    }
+    h0 = h2; h1 = h3; h2 = h4;
+  }
+}
+
 }  // namespace
 
 int flv_launch_unpack(flv_ctx* ctx, int slot, int n_streams, const uint8_t* d_src, size_t row_stride,
                       size_t img_stride) {
   const LevelGeom& L0 = ctx->geom.lv[0];
+  ctx->l1_valid[slot] = 0;
+  if (ctx->geom.nlev > 1 && ctx->w % 4 == 0 && row_stride % 4 == 0 && img_stride % 4 == 0 &&
+      reinterpret_cast<size_t>(d_src) % 4 == 0 && !ctx->no_fused_ingest) {
+    const LevelGeom& L1 = ctx->geom.lv[1];
+    dim3 grid((ctx->w + 127) / 128, (L1.h + FUSED_ROWS * FUSED_WARPS - 1) / (FUSED_ROWS * FUSED_WARPS), n_streams);
+    ingest_l1_kernel<<<grid, FUSED_WARPS * 32, 0, ctx->stream>>>(d_src, row_stride, img_stride, ctx->pyr[slot],
+                                                                 ctx->geom.stream_stride, L0.off, L0.pitch, L1.off, L1.pitch,
+                                                                 ctx->w, ctx->h, L1.w, L1.h);
+    ctx->launches++;
+    FLV_CUDA(ctx, cudaGetLastError());
+    ctx->l1_valid[slot] = 1;
+    return FLV_OK;
+  }
   const bool vec = (ctx->w % 16 == 0) && (row_stride % 16 == 0) && (img_stride % 16 == 0) &&
                    (reinterpret_cast<size_t>(d_src) % 16 == 0);
   dim3 block(64, 4);
@@ -103,7 +182,9 @@ int flv_launch_unpack(flv_ctx* ctx, int slot, int n_streams, const uint8_t* d_sr
 
 int flv_launch_pyramid(flv_ctx* ctx, int slot, int n_streams) {
   const PyrGeom& g = ctx->geom;
-  for (int l = 1; l < g.nlev; ++l) {
+  const int first = ctx->l1_valid[slot] ? 2 : 1;      // level 1 already built by the fused ingest kernel
+  ctx->l1_valid[slot] = 0;
+  for (int l = first; l < g.nlev; ++l) {
     const LevelGeom& a = g.lv[l - 1];
     const LevelGeom& b = g.lv[l];
     dim3 grid((b.w + TW - 1) / TW, (b.h + TH - 1) / TH, n_streams);
