@@ -103,7 +103,7 @@ void flv_destroy(flv_ctx* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
   cudaDeviceSynchronize();
-  for (int i = 0; i < FLV_NUM_SLOTS; ++i) cudaFree(ctx->pyr[i]);
+  for (int i = 0; i < FLV_NUM_SLOTS; ++i) { cudaFree(ctx->pyr[i]); if (ctx->deriv[i]) cudaFree(ctx->deriv[i]); }
   cudaFree(ctx->d_npts); cudaFree(ctx->d_eig); cudaFree(ctx->d_eigmax); cudaFree(ctx->d_cand);
   cudaFree(ctx->d_ncand); cudaFree(ctx->d_sorted); cudaFree(ctx->d_items); cudaFree(ctx->d_state); cudaFree(ctx->d_need_full); cudaFree(ctx->d_corners); cudaFree(ctx->d_ncorners);
   cudaFree(ctx->d_flags); cudaFree(ctx->d_exist); cudaFree(ctx->d_nexist); cudaFree(ctx->d_newxy);

@@ -28,6 +28,8 @@ struct flv_ctx {
   bool own_stream;
   long long launches;
   int l1_valid[FLV_NUM_SLOTS];   // level 1 of the slot was produced by the fused ingest kernel (consumed by build_pyramid)
+  unsigned* deriv[FLV_NUM_SLOTS];      // Scharr derivative pyramids (LK v4), allocated on first use
+  int deriv_streams[FLV_NUM_SLOTS];    // streams for which deriv[slot] matches the slot's current images (0 = stale)
   int no_fused_ingest;           // FLV_NO_FUSED_INGEST=1: A/B switch for tests
   char err[512];
 

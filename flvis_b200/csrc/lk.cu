@@ -262,6 +262,9 @@ int flv_launch_lk_v1(flv_ctx* ctx, int src_slot, int dst_slot, int n_streams, co
                      const float* d_prev, const float* d_init, float* d_next, uint8_t* d_status,
                      float* d_err, int nlev_used, int max_iter, double eps2, double min_eig_thr);
 
+int flv_launch_lk_v4(flv_ctx* ctx, int src_slot, int dst_slot, int n_streams, const int* d_npts,
+                     const float* d_prev, const float* d_init, float* d_next, uint8_t* d_status,
+                     float* d_err, int nlev_used, int max_iter, double eps2, double min_eig_thr);
 int flv_launch_lk_v3(flv_ctx* ctx, int src_slot, int dst_slot, int n_streams, const int* d_npts,
                      const float* d_prev, const float* d_init, float* d_next, uint8_t* d_status,
                      float* d_err, int nlev_used, int max_iter, double eps2, double min_eig_thr);
@@ -280,9 +283,12 @@ int flv_launch_lk(flv_ctx* ctx, int src_slot, int dst_slot, int n_streams, const
   dim3 grid((ctx->max_pts + WARPS - 1) / WARPS, n_streams);
   const float err_scale = (float)(1.0 / (32 * WIN * WIN));
   // two register budgets of the same kernel: 168 regs / 12 warps per SM (no spills) or 128 regs / 16 warps per SM
-  // default: the shared-memory-template kernel (v3) once the batch fills the machine, the register-template kernel
-  // (v1, lower latency per point) for small batches; FLV_LK_VARIANT overrides (A/B measurements in profiles/)
-  const int variant = getenv("FLV_LK_VARIANT") ? atoi(getenv("FLV_LK_VARIANT")) : (n_streams >= 8 ? 5 : 1);
+  // default: v4 (lk_v4.cu: precomputed Scharr pyramid, packed register patch, DP2A blend); FLV_LK_VARIANT selects the
+  // earlier kernels (1 = register template, 3/4 = v2 register budgets, 5 = shared-memory template) for A/B runs
+  const int variant = getenv("FLV_LK_VARIANT") ? atoi(getenv("FLV_LK_VARIANT")) : 6;
+  if (variant == 6)
+    return flv_launch_lk_v4(ctx, src_slot, dst_slot, n_streams, d_npts, d_prev, d_init, d_next, d_status, d_err, nlev_used,
+                            max_iter, eps2, min_eig_thr);
   if (variant == 5)
     return flv_launch_lk_v3(ctx, src_slot, dst_slot, n_streams, d_npts, d_prev, d_init, d_next, d_status, d_err, nlev_used,
                             max_iter, eps2, min_eig_thr);

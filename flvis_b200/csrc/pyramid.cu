@@ -152,6 +152,7 @@ int flv_launch_unpack(flv_ctx* ctx, int slot, int n_streams, const uint8_t* d_sr
                       size_t img_stride) {
   const LevelGeom& L0 = ctx->geom.lv[0];
   ctx->l1_valid[slot] = 0;
+  ctx->deriv_streams[slot] = 0;
   if (ctx->geom.nlev > 1 && ctx->w % 4 == 0 && row_stride % 4 == 0 && img_stride % 4 == 0 &&
       reinterpret_cast<size_t>(d_src) % 4 == 0 && !ctx->no_fused_ingest) {
     const LevelGeom& L1 = ctx->geom.lv[1];
@@ -182,6 +183,7 @@ int flv_launch_unpack(flv_ctx* ctx, int slot, int n_streams, const uint8_t* d_sr
 
 int flv_launch_pyramid(flv_ctx* ctx, int slot, int n_streams) {
   const PyrGeom& g = ctx->geom;
+  ctx->deriv_streams[slot] = 0;
   const int first = ctx->l1_valid[slot] ? 2 : 1;      // level 1 already built by the fused ingest kernel
   ctx->l1_valid[slot] = 0;
   for (int l = first; l < g.nlev; ++l) {

@@ -50,7 +50,33 @@ def test_lk_bit_exact_vs_oracle_and_golden(name):
     ctx.close()
 
 
-@pytest.mark.parametrize("variant", ["1", "3", "4", "5"])
+@pytest.mark.parametrize("name", cases.lk_cases())
+def test_lk_v4_packed_patch_all_cases(name, monkeypatch):
+    """LK v4 (precomputed Scharr pyramid + packed register patch + DP2A blend) on every golden case, incl. border points
+    and a second call that reuses the cached derivative pyramid."""
+    monkeypatch.setenv("FLV_LK_VARIANT", "6")
+    g, I, J = cases.load_lk(name)
+    h, w = I.shape
+    ctx = _ctx(1, w, h)
+    ctx.upload(0, I); ctx.upload(1, J)
+    ctx.build_pyramid(0, 1); ctx.build_pyramid(1, 1)
+    o_nxt, o_st, o_err = lk_ref.calc_optical_flow_pyr_lk(I, J, g["pts"], g["init"], max_level=int(g["max_level"]))
+    for rep in range(2):
+        nxt, st, err = ctx.lk_track(0, 1, g["pts"], g["init"], max_level=int(g["max_level"]))
+        assert np.array_equal(st, o_st)
+        assert np.array_equal(nxt.view(np.uint32), o_nxt.view(np.uint32))
+        assert np.array_equal(err.view(np.uint32), o_err.view(np.uint32))
+    # new images in the template slot invalidate the cached derivatives
+    ctx.upload(0, J); ctx.build_pyramid(0, 1)
+    ctx.upload(1, I); ctx.build_pyramid(1, 1)
+    nxt, st, err = ctx.lk_track(0, 1, g["pts"], g["init"], max_level=int(g["max_level"]))
+    o_nxt, o_st, o_err = lk_ref.calc_optical_flow_pyr_lk(J, I, g["pts"], g["init"], max_level=int(g["max_level"]))
+    assert np.array_equal(st, o_st)
+    assert np.array_equal(nxt.view(np.uint32), o_nxt.view(np.uint32))
+    ctx.close()
+
+
+@pytest.mark.parametrize("variant", ["1", "3", "4", "5", "6"])
 def test_lk_kernel_variants_bit_exact(variant, monkeypatch):
     """All register-budget / shared-memory variants of the tracker obey the same arithmetic contract."""
     monkeypatch.setenv("FLV_LK_VARIANT", variant)
