@@ -112,6 +112,7 @@ void flv_destroy(flv_ctx* ctx) {
   if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
   if (ctx->d_stage) cudaFree(ctx->d_stage);
   if (ctx->img_stage_bytes) for (int i = 0; i < flv_ctx::IMG_RING; ++i) cudaFree(ctx->d_img_stage[i]);
+  if (ctx->aux_stream) { cudaEventDestroy(ctx->ev_fork); cudaEventDestroy(ctx->ev_gftt); cudaStreamDestroy(ctx->aux_stream); }
   if (ctx->copy_stream) {
     for (int i = 0; i < flv_ctx::IMG_RING; ++i) { cudaEventDestroy(ctx->img_ready[i]); cudaEventDestroy(ctx->img_free[i]); }
     cudaStreamDestroy(ctx->copy_stream);
@@ -286,6 +287,7 @@ int flv_gftt(flv_ctx* ctx, int slot, int n_streams, int max_corners, double qual
   if (!ctx || !xy_out || !n_out || slot < 0 || slot >= FLV_NUM_SLOTS || n_streams < 1 ||
       n_streams > ctx->S || out_stride_pts < max_corners)
     return FLV_ERR_INVALID;
+  if (ctx->prep_valid) { FLV_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_gftt, 0)); ctx->prep_valid = 0; }
   int rc = flv_launch_gftt(ctx, slot, n_streams, max_corners, quality, min_distance);
   if (rc) return rc;
   cudaMemcpyKind kind = mem == FLV_MEM_HOST ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice;
@@ -324,13 +326,44 @@ static int feature_common(flv_ctx* ctx, int slot, int n_streams, const flv_featu
     FLV_CUDA(ctx, cudaMemcpyAsync(ctx->d_exist, existing_xy, np * 16, up, ctx->stream));
     FLV_CUDA(ctx, cudaMemcpyAsync(ctx->d_nexist, n_existing, (size_t)n_streams * 4, up, ctx->stream));
   }
-  int rc = flv_launch_gftt(ctx, slot, n_streams, ncorn, prm->gftt_ql, (double)prm->gftt_dis);
+  int rc = FLV_OK;
+  if (ctx->prep_valid && ctx->prep_slot == slot && ctx->prep_streams == n_streams && ctx->prep_ncorn == ncorn &&
+      ctx->prep_ql == prm->gftt_ql && ctx->prep_dis == prm->gftt_dis) {
+    FLV_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_gftt, 0));      // corners were computed ahead of time
+  } else {
+    if (ctx->prep_valid) FLV_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_gftt, 0));   // scratch buffers in use
+    rc = flv_launch_gftt(ctx, slot, n_streams, ncorn, prm->gftt_ql, (double)prm->gftt_dis);
+  }
+  ctx->prep_valid = 0;
   if (rc) return rc;
   rc = flv_launch_region(ctx, slot, n_streams, prm, redetect);
   if (rc) return rc;
   FLV_CUDA(ctx, cudaMemcpyAsync(new_xy, ctx->d_newxy, np * 8, down, ctx->stream));
   FLV_CUDA(ctx, cudaMemcpyAsync(n_new, ctx->d_nnew, (size_t)n_streams * 4, down, ctx->stream));
   if (mem == FLV_MEM_HOST) return check_flags(ctx, n_streams);
+  return FLV_OK;
+}
+
+int flv_feature_prepare(flv_ctx* ctx, int slot, int n_streams, const flv_feature_params* prm, int redetect) {
+  if (!ctx || !prm || slot < 0 || slot >= FLV_NUM_SLOTS || n_streams < 1 || n_streams > ctx->S) return FLV_ERR_INVALID;
+  if (!ctx->aux_stream) {
+    FLV_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->aux_stream, cudaStreamNonBlocking));
+    FLV_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
+    FLV_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_gftt, cudaEventDisableTiming));
+  }
+  const int ncorn = redetect ? prm->gftt_num : 2 * prm->gftt_num;
+  // fork: the auxiliary stream sees everything enqueued so far (the slot's pyramid, the previous consumer of the
+  // GFTT scratch buffers), then runs corner response + min-distance selection concurrently with the caller's stream
+  FLV_CUDA(ctx, cudaEventRecord(ctx->ev_fork, ctx->stream));
+  FLV_CUDA(ctx, cudaStreamWaitEvent(ctx->aux_stream, ctx->ev_fork, 0));
+  cudaStream_t main_stream = ctx->stream;
+  ctx->stream = ctx->aux_stream;
+  const int rc = flv_launch_gftt(ctx, slot, n_streams, ncorn, prm->gftt_ql, (double)prm->gftt_dis);
+  ctx->stream = main_stream;
+  if (rc) return rc;
+  FLV_CUDA(ctx, cudaEventRecord(ctx->ev_gftt, ctx->aux_stream));
+  ctx->prep_valid = 1; ctx->prep_slot = slot; ctx->prep_streams = n_streams; ctx->prep_ncorn = ncorn;
+  ctx->prep_ql = prm->gftt_ql; ctx->prep_dis = prm->gftt_dis;
   return FLV_OK;
 }
 

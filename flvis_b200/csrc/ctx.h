@@ -30,6 +30,9 @@ struct flv_ctx {
   int l1_valid[FLV_NUM_SLOTS];   // level 1 of the slot was produced by the fused ingest kernel (consumed by build_pyramid)
   unsigned* deriv[FLV_NUM_SLOTS];      // Scharr derivative pyramids (LK v4), allocated on first use
   int deriv_streams[FLV_NUM_SLOTS];    // streams for which deriv[slot] matches the slot's current images (0 = stale)
+  // GFTT started early on an auxiliary stream by flv_feature_prepare, consumed by the next detect/redetect
+  cudaStream_t aux_stream; cudaEvent_t ev_fork, ev_gftt;
+  int prep_valid, prep_slot, prep_streams, prep_ncorn, prep_dis; double prep_ql;
   int no_fused_ingest;           // FLV_NO_FUSED_INGEST=1: A/B switch for tests
   char err[512];
 

@@ -35,6 +35,8 @@ class FrontendBench:
         self.ctx = capi.Context(n_streams, w, h, max_pts, device=device_index)
         # a dedicated (non-default) torch stream: the library launches on it and all events are recorded on it
         self.stream = torch.cuda.Stream(self.dev)
+        self.side = torch.cuda.Stream(self.dev)
+        self.ev_sel, self.ev_red = torch.cuda.Event(), torch.cuda.Event()
         self.ctx.set_stream(self.stream.cuda_stream)
         self.fp = capi.FeatureParams(int(feature_para[0]), int(feature_para[1]), int(feature_para[2] // 2),
                                      int(feature_para[3]), float(feature_para[4]), int(feature_para[5]))
@@ -141,17 +143,27 @@ class FrontendBench:
             ctx.upload_dev(cur0, S, self.d_pool0[k].data_ptr())
             ctx.upload_dev(cur1, S, self.d_pool1[k].data_ptr())
         ctx.build_pyramid(cur0, S)
+        # Shi-Tomasi of the new left image only needs the image: start it now on the library's auxiliary stream, it
+        # overlaps the right pyramid, the frame->frame LK and the keep rule (results identical, see flv_feature_prepare)
+        ctx.feature_prepare(cur0, S, self.fp, redetect=True)
         ctx.build_pyramid(cur1, S)
         # frame -> frame LK (lkorb_tracking.cpp:64-73) + keep rule (:98-119)
         self._lk(prev0, cur0, self.d_pts, self.d_pts, self.d_next, self.d_status, self.d_err, 10)
         ctx.select_tracked_dev(S, self.d_npts.data_ptr(), self.d_pts.data_ptr(), self.d_next.data_ptr(),
                                self.d_status.data_ptr(), self.d_keep.data_ptr(), self.d_cur.data_ptr(),
                                self.d_cur64.data_ptr())
-        # redetect on cur0 against the surviving features (f2f_tracking.cpp:291 -> feature_dem.cpp:124)
+        # redetect on cur0 against the surviving features (f2f_tracking.cpp:291 -> feature_dem.cpp:124): the region
+        # selection is a one-CTA-per-stream kernel, so it runs on a side stream next to the left -> right LK of the
+        # surviving features (camera_frame.cpp:124-128, maxLevel 5, initial flow = cam0 position); both only read cur0
+        self.ev_sel.record(self.stream)
+        self.side.wait_event(self.ev_sel)
+        ctx.set_stream(self.side.cuda_stream)
         ctx.feature_redetect_dev(cur0, S, self.fp, self.d_cur64.data_ptr(), self.d_npts.data_ptr(),
                                  self.d_new.data_ptr(), self.d_nnew.data_ptr())
-        # left -> right LK (camera_frame.cpp:124-128, maxLevel 5), initial flow = cam0 position
+        self.ev_red.record(self.side)
+        ctx.set_stream(self.stream.cuda_stream)
         self._lk(cur0, cur1, self.d_cur, self.d_cur, self.d_right, self.d_rstatus, self.d_rerr, 5)
+        self.stream.wait_event(self.ev_red)
         if self.has_ba:
             self.ba.step(i, mode, self.kf_every)
         if mode == "host":

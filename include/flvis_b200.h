@@ -129,6 +129,13 @@ int flv_feature_redetect(flv_ctx* ctx, int slot, int n_streams, const flv_featur
                          const double* existing_xy, const int* n_existing, float* new_xy,
                          int* n_new, flv_memspace mem);
 
+/* Optional: start the Shi-Tomasi part (corner response + min-distance selection, feature_dem.cpp:160 / :221) of the next
+ * flv_feature_detect (redetect = 0) / flv_feature_redetect (redetect = 1) call for `slot` NOW, on an internal auxiliary
+ * stream, so it overlaps whatever the caller enqueues next (the reference runs goodFeaturesToTrack after tracking; it
+ * only needs the image).  The next detect / redetect call with the same slot / n_streams / params consumes the result;
+ * any other GFTT call waits for it and discards it.  Results are identical with or without this call. */
+int flv_feature_prepare(flv_ctx* ctx, int slot, int n_streams, const flv_feature_params* prm, int redetect);
+
 /* ---- local bundle adjustment (K7-K10) and pose-only BA ---------------------------------------
  * Replaces the g2o calls of LocalMapNodeletClass::frame_callback
  * (src/backend/vo_localmap.cpp:292-319: initializeOptimization(); optimize(12); chi2>3 edge

@@ -190,4 +190,15 @@ def test_feature_dem_detect_redetect_bit_exact(sensor, name):
     # no existing features at all
     red = ctx.feature_redetect(0, 2, fp, [np.zeros((0, 2)), ex1])
     assert np.array_equal(red[0], fd.redetect(img, np.zeros((0, 2))))
+    # flv_feature_prepare (GFTT started early on the auxiliary stream) must not change any result; a prepared GFTT
+    # that does not match the next call (detect wants 2N corners) is discarded
+    ctx.feature_prepare(0, 2, fp, redetect=True)
+    red = ctx.feature_redetect(0, 2, fp, [ex0, ex1])
+    assert np.array_equal(red[0], fd.redetect(img, ex0)) and np.array_equal(red[1], fd.redetect(img[::-1].copy(), ex1))
+    ctx.feature_prepare(0, 2, fp, redetect=True)
+    det = ctx.feature_detect(0, 2, fp)
+    assert np.array_equal(det[0], o0) and np.array_equal(det[1], o1)
+    ctx.feature_prepare(0, 2, fp, redetect=False)
+    det = ctx.feature_detect(0, 2, fp)
+    assert np.array_equal(det[0], o0) and np.array_equal(det[1], o1)
     ctx.close()
