@@ -1,13 +1,8 @@
-timeout 900 python -m pytest tests -m gpu -q -x 2>&1 | tail -3
-timeout 300 python bench.py --steps 20 --warmup 3 > gpurun_out/bench_v11.json 2> gpurun_out/bench_v11.err
+python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 20 --warmup 3 > gpurun_out/bench_2gpu.json 2> gpurun_out/bench_2gpu.err
 python -c "
 import json
-d=json.load(open('gpurun_out/bench_v11.json'))
-print('value',round(d['value']),'ms/step',round(d['ms_per_step'],3),'e2e',round(d['e2e']['value']),'cpu',round(d['cpu_baseline']['value']),'lk us',round(d['roofline']['us_per_launch']))
+d=json.load(open('gpurun_out/bench_2gpu.json'))
+print('N=2 value',round(d['value']),'ms/step',round(d['ms_per_step'],3),'e2e',round(d['e2e']['value']),'n_gpus',d['n_gpus'],d['scaling'], d['clocks'])
 "
-tail -3 gpurun_out/bench_v11.err
-timeout 300 python bench.py --steps 50 --warmup 5 --no-cpu 2>/dev/null | python -c "
-import json,sys
-d=json.loads(sys.stdin.read())
-print('K=50: value',round(d['value']),'ms/step',round(d['ms_per_step'],3),'e2e',round(d['e2e']['value']))
-"
+tail -3 gpurun_out/bench_2gpu.err
+python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29512 bench.py --impl reference --gpus 2 --steps 3 --warmup 1 2>/dev/null | cut -c1-300
