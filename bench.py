@@ -156,6 +156,8 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    host_ms = {}
+
     def timed(mode, steps, warmup):
         bench.reset()
         for i in range(warmup):
@@ -167,8 +169,10 @@ def run_ours(args):
         bench.lk_ms = 0.0
         bench.collect_lk = True
         ev0.record(bench.stream)
+        t_host = time.perf_counter()
         for i in range(steps):
             bench.step(warmup + i, mode)
+        host_ms[mode] = (time.perf_counter() - t_host) * 1e3 / steps      # host time to SUBMIT one step (no sync in device mode)
         bench.join()                       # the timed region ends when the asynchronous BA streams have drained too
         ev1.record(bench.stream)
         barrier()
@@ -208,7 +212,8 @@ def run_ours(args):
                        "e2e_pipeline": "H2D of frame k+1 (library copy stream) and the host's read of frame k-1's results "
                                        "overlap the kernels of frame k; every frame's inputs and outputs cross PCIe "
                                        "inside the timed region (pinned host buffers, one frame of result latency)",
-                       "parallelism": f"streams sharded {S}/GPU x {world} GPU, no data-path collective"},
+                       "parallelism": f"streams sharded {S}/GPU x {world} GPU, no data-path collective",
+                       "host_submit_ms_per_step": {k: round(v, 3) for k, v in host_ms.items()}},
             "e2e": {"value": frames / (ms_e2e * 1e-3), "unit": "frames/s",
                     "h2d_bytes_per_step": bench.h2d_bytes_per_step, "d2h_bytes_per_step": bench.d2h_bytes_per_step,
                     "ms_per_step": ms_e2e / args.steps},

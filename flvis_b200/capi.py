@@ -18,7 +18,7 @@ SYMBOLS = [
     "flv_launch_count", "flv_level_info", "flv_num_levels", "flv_upload_images", "flv_build_pyramid",
     "flv_download_level", "flv_lk_track", "flv_select_tracked", "flv_gftt", "flv_download_eig", "flv_gftt_capacity",
     "flv_feature_detect", "flv_feature_redetect", "flv_ba_reserve", "flv_ba_optimize", "flv_gftt_keep_response",
-    "flv_ba_profile", "flv_set_ba_stream", "flv_feature_prepare", "flv_depth_innovation", "flv_reprojection_inliers",
+    "flv_ba_profile", "flv_set_ba_stream", "flv_feature_prepare", "flv_set_equalize_hist", "flv_depth_innovation", "flv_reprojection_inliers",
 ]
 
 
@@ -91,6 +91,7 @@ def load_library(path=LIB_PATH):
     lib.flv_select_tracked.argtypes = [vp, C.c_int, vp, vp, vp, vp, vp, vp, vp]
     lib.flv_gftt.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double, vp, vp, C.c_int, C.c_int]
     lib.flv_download_eig.argtypes = [vp, C.c_int, vp, C.c_int]
+    lib.flv_set_equalize_hist.argtypes = [vp, C.c_int]
     lib.flv_feature_prepare.argtypes = [vp, C.c_int, C.c_int, C.POINTER(FeatureParams), C.c_int]
     lib.flv_feature_detect.argtypes = [vp, C.c_int, C.c_int, C.POINTER(FeatureParams), vp, vp, C.c_int]
     lib.flv_feature_redetect.argtypes = [vp, C.c_int, C.c_int, C.POINTER(FeatureParams), vp, vp, vp, vp, C.c_int]
@@ -286,6 +287,9 @@ class Context:
         self._chk(self.lib.flv_feature_redetect(self.h, slot, n_streams, C.byref(fp), _ptr(ex), _ptr(ne), _ptr(xy),
                                                 _ptr(n), MEM_HOST))
         return [xy[s, :n[s]].copy() for s in range(n_streams)]
+
+    def set_equalize_hist(self, enable):
+        self._chk(self.lib.flv_set_equalize_hist(self.h, 1 if enable else 0))
 
     def feature_prepare(self, slot, n_streams, fp, redetect=True):
         self._chk(self.lib.flv_feature_prepare(self.h, slot, n_streams, C.byref(fp), 1 if redetect else 0))

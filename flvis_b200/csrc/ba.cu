@@ -428,17 +428,17 @@ __device__ void build_system(const flv_ba_problem& pb, const Cam& cam, const dou
   const int ME = ws.ME, ML = ws.ML;
   const double d2 = delta * delta;
   if (!pb.fix_landmarks) {
-    for (int s = tid; s < sh.nact; s += BA_THREADS) {
-      const int pl = ws.slot_pl[s], p = pl & 255;
-      const double uv[2] = {ws.uvs[s], ws.uvs[ME + s]};
+    // two slots per thread and trip: all inputs of both edges are loaded before any store, so the two (long, mostly
+    // serial) fp64 chains can be interleaved by the scheduler -- the pass was latency-, not throughput-bound
+    auto emit = [&](int s, int pl, int lp, const double* pose, const double* X, const double* uv) {
+      const int p = pl & 255;
       double r[2], A[6], B[12];
-      edge_eval<true>(poses + 7 * p, lms + 3 * (size_t)(pl >> 8), uv, cam, r, A, B);
+      edge_eval<true>(pose, X, uv, cam, r, A, B);
       const double c = r[0] * r[0] + r[1] * r[1];
       const double rho1 = (c <= d2) ? 1.0 : delta / sqrt(c);
       const double o0 = -r[0] * rho1, o1 = -r[1] * rho1;
-      const int lp = ws.slot_lp[s];           // shares are stored landmark-major so that the landmark pass reads runs
 #pragma unroll
-      for (int i = 0; i < 3; ++i) ws.bb[i * ME + lp] = A[i] * o0 + A[3 + i] * o1;
+      for (int i = 0; i < 3; ++i) ws.bb[i * ME + lp] = A[i] * o0 + A[3 + i] * o1;   // landmark-major: the landmark pass reads runs
       ws.hl[0 * ME + lp] = rho1 * (A[0] * A[0] + A[3] * A[3]); ws.hl[1 * ME + lp] = rho1 * (A[0] * A[1] + A[3] * A[4]);
       ws.hl[2 * ME + lp] = rho1 * (A[0] * A[2] + A[3] * A[5]); ws.hl[3 * ME + lp] = rho1 * (A[1] * A[1] + A[4] * A[4]);
       ws.hl[4 * ME + lp] = rho1 * (A[1] * A[2] + A[4] * A[5]); ws.hl[5 * ME + lp] = rho1 * (A[2] * A[2] + A[5] * A[5]);
@@ -452,6 +452,20 @@ __device__ void build_system(const flv_ba_problem& pb, const Cam& cam, const dou
         for (int i = 0; i < 12; ++i) ws.Bw[i * ME + s] = sr * B[i];
         ws.g[s] = -sr * r[0]; ws.g[ME + s] = -sr * r[1];
       }
+    };
+    for (int s0 = tid; s0 < sh.nact; s0 += 2 * BA_THREADS) {
+      const int s1 = s0 + BA_THREADS;
+      const bool two = s1 < sh.nact;
+      const int sb1 = two ? s1 : s0;
+      const int pl0 = ws.slot_pl[s0], pl1 = ws.slot_pl[sb1], lp0 = ws.slot_lp[s0], lp1 = ws.slot_lp[sb1];
+      const double uv0[2] = {ws.uvs[s0], ws.uvs[ME + s0]}, uv1[2] = {ws.uvs[sb1], ws.uvs[ME + sb1]};
+      double pose0[7], pose1[7], X0[3], X1[3];
+#pragma unroll
+      for (int i = 0; i < 7; ++i) { pose0[i] = poses[7 * (pl0 & 255) + i]; pose1[i] = poses[7 * (pl1 & 255) + i]; }
+#pragma unroll
+      for (int i = 0; i < 3; ++i) { X0[i] = lms[3 * (size_t)(pl0 >> 8) + i]; X1[i] = lms[3 * (size_t)(pl1 >> 8) + i]; }
+      emit(s0, pl0, lp0, pose0, X0, uv0);
+      if (two) emit(s1, pl1, lp1, pose1, X1, uv1);
     }
     __syncthreads();
     mark(sh, 10);
@@ -838,8 +852,11 @@ __global__ void __launch_bounds__(BA_THREADS, 1) ba_kernel(BAArgs a) {
     double* y = dyn + (size_t)n * ld;
     double* chunk = y + ((n + 8) & ~1);
     double ni = 2;
+    double currentChi = 0;
     for (int it = 0; it < iters; ++it) {
-      double currentChi = robust_chi2(cam, poses, lms, delta, ws, sh);
+      // g2o recomputes activeRobustChi2 at the start of every iteration; the state only changes through accepted trials
+      // (whose chi2 was just computed by the same code on the same state), so the value is carried over bit-identically
+      if (it == 0) currentChi = robust_chi2(cam, poses, lms, delta, ws, sh);
       mark(sh, 0);
       build_system(pb, cam, poses, lms, delta, ws, sh);
       mark(sh, 1);

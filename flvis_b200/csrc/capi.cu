@@ -112,6 +112,7 @@ void flv_destroy(flv_ctx* ctx) {
   if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
   if (ctx->d_stage) cudaFree(ctx->d_stage);
   if (ctx->img_stage_bytes) for (int i = 0; i < flv_ctx::IMG_RING; ++i) cudaFree(ctx->d_img_stage[i]);
+  if (ctx->d_hist) cudaFree(ctx->d_hist);
   if (ctx->aux_stream) { cudaEventDestroy(ctx->ev_fork); cudaEventDestroy(ctx->ev_gftt); cudaStreamDestroy(ctx->aux_stream); }
   if (ctx->copy_stream) {
     for (int i = 0; i < flv_ctx::IMG_RING; ++i) { cudaEventDestroy(ctx->img_ready[i]); cudaEventDestroy(ctx->img_free[i]); }
@@ -160,7 +161,7 @@ int flv_upload_images(flv_ctx* ctx, int slot, int n_streams, const uint8_t* imgs
   if (!ctx || !imgs || slot < 0 || slot >= FLV_NUM_SLOTS || n_streams < 1 || n_streams > ctx->S ||
       row_stride_bytes < (size_t)ctx->w)
     return FLV_ERR_INVALID;
-  if (mem == FLV_MEM_DEVICE) return flv_launch_unpack(ctx, slot, n_streams, imgs, row_stride_bytes, img_stride_bytes);
+  if (mem == FLV_MEM_DEVICE && !ctx->equalize) return flv_launch_unpack(ctx, slot, n_streams, imgs, row_stride_bytes, img_stride_bytes);
   // host images: one (2D) H2D copy of all streams into a tight device landing area on the copy stream, then one unpack
   // launch on the compute stream.  The landing areas form a ring, so a caller that submits frame k+1 before it waits for
   // the results of frame k gets the copy of k+1 overlapped with the kernels of k.
@@ -179,6 +180,15 @@ int flv_upload_images(flv_ctx* ctx, int slot, int n_streams, const uint8_t* imgs
   const int ring = (int)(ctx->img_ring_pos++ % flv_ctx::IMG_RING);
   uint8_t* st = (uint8_t*)ctx->d_img_stage[ring];
   cudaStream_t cs = ctx->copy_stream;
+  if (mem == FLV_MEM_DEVICE) {       // equalizeHist of device-resident images: the landing area receives the equalized copy
+    FLV_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->img_free[ring], 0));
+    int rc = flv_launch_equalize(ctx, n_streams, imgs, row_stride_bytes, img_stride_bytes, st);
+    if (rc) return rc;
+    rc = flv_launch_unpack(ctx, slot, n_streams, st, w, w * h);
+    if (rc) return rc;
+    FLV_CUDA(ctx, cudaEventRecord(ctx->img_free[ring], ctx->stream));
+    return FLV_OK;
+  }
   FLV_CUDA(ctx, cudaStreamWaitEvent(cs, ctx->img_free[ring], 0));        // last unpack that read this landing area
   if (row_stride_bytes == w && img_stride_bytes == w * h) {
     FLV_CUDA(ctx, cudaMemcpyAsync(st, imgs, bytes, cudaMemcpyHostToDevice, cs));
@@ -191,9 +201,19 @@ int flv_upload_images(flv_ctx* ctx, int slot, int n_streams, const uint8_t* imgs
   }
   FLV_CUDA(ctx, cudaEventRecord(ctx->img_ready[ring], cs));
   FLV_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->img_ready[ring], 0));
+  if (ctx->equalize) {
+    const int rc0 = flv_launch_equalize(ctx, n_streams, st, w, w * h, st);          // in place (element-wise LUT)
+    if (rc0) return rc0;
+  }
   const int rc = flv_launch_unpack(ctx, slot, n_streams, st, w, w * h);
   if (rc) return rc;
   FLV_CUDA(ctx, cudaEventRecord(ctx->img_free[ring], ctx->stream));
+  return FLV_OK;
+}
+
+int flv_set_equalize_hist(flv_ctx* ctx, int enable) {
+  if (!ctx) return FLV_ERR_INVALID;
+  ctx->equalize = enable ? 1 : 0;
   return FLV_OK;
 }
 

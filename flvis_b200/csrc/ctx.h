@@ -33,6 +33,7 @@ struct flv_ctx {
   // GFTT started early on an auxiliary stream by flv_feature_prepare, consumed by the next detect/redetect
   cudaStream_t aux_stream; cudaEvent_t ev_fork, ev_gftt;
   int prep_valid, prep_slot, prep_streams, prep_ncorn, prep_dis; double prep_ql;
+  int equalize; int* d_hist;     // cv::equalizeHist on ingest (flv_set_equalize_hist)
   int no_fused_ingest;           // FLV_NO_FUSED_INGEST=1: A/B switch for tests
   char err[512];
 
@@ -99,6 +100,7 @@ int flv_stage_reserve(flv_ctx* ctx, size_t bytes);
 
 // kernel launchers (one per .cu)
 int flv_launch_pyramid(flv_ctx* ctx, int slot, int n_streams);
+int flv_launch_equalize(flv_ctx* ctx, int n_streams, const uint8_t* d_src, size_t row_stride, size_t img_stride, uint8_t* d_dst_tight);
 int flv_launch_unpack(flv_ctx* ctx, int slot, int n_streams, const uint8_t* d_src, size_t row_stride, size_t img_stride);
 int flv_launch_lk(flv_ctx* ctx, int src_slot, int dst_slot, int n_streams, const int* d_npts,
                   const float* d_prev, const float* d_init, float* d_next, uint8_t* d_status,

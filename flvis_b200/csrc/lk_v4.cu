@@ -215,6 +215,72 @@ __device__ __forceinline__ void window_pass(const unsigned (&P)[8], const unsign
   }
 }
 
+// Template of one point and level -> shared memory: tmpl[r*32] = ((1<<8) - (Ival<<9), Iy<<16 | Ix&0xffff) for window
+// rows r = 0..30 of this lane's column, plus the lane's share of the gradient matrix sums.  Ival / Ix / Iy are the
+// bilinear blends of the u8 level (BORDER_REFLECT_101) and of the Scharr pyramid (zero outside the image).
+// Rolled over groups of four window rows (small code: the instruction cache, not the ALUs, limited the unrolled form):
+// a group loads its 4 new image rows + derivative rows up front, packs the u8 column, blends.
+// INTERIOR: the whole 32x32 footprint is inside the image (no reflection, no range tests, pointer walk).
+template <bool INTERIOR>
+__device__ __forceinline__ void build_template(const uint8_t* __restrict__ I, const unsigned* __restrict__ Dv, int pitch,
+                                               int w, int h, int ipx, int ipy, int lane, bool live, int w00, int w01,
+                                               int w10, int w11, int2* __restrict__ tmpl, int& a11, int& a12, int& a22) {
+  const int wv0 = (w00 & 0xffff) | (w10 << 16), wv1 = (w01 & 0xffff) | (w11 << 16);
+  const int x = ipx + lane;
+  const bool in_x = INTERIOR || (x >= 0 && x < w);
+  const uint8_t* icol = INTERIOR ? I + (size_t)ipy * pitch + x : I + reflect101(x, w);
+  const unsigned* dcol = INTERIOR ? Dv + (size_t)ipy * pitch + x : Dv + x;
+  unsigned bI0, d0;
+  if (INTERIOR) { bI0 = icol[0]; d0 = dcol[0]; }
+  else {
+    bI0 = icol[(size_t)reflect101(ipy, h) * pitch];
+    d0 = (in_x && ipy >= 0 && ipy < h) ? dcol[(size_t)ipy * pitch] : 0u;
+  }
+  unsigned d0r = __shfl_down_sync(FULL, d0, 1);
+  int qX = (int)(short)(d0 & 0xffffu), qY = (int)d0 >> 16, qXr = (int)(short)(d0r & 0xffffu), qYr = (int)d0r >> 16;
+#pragma unroll 1
+  for (int k = 0; k < 8; ++k) {
+    unsigned bI[5], dd[4];
+    bI[0] = bI0;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      if (INTERIOR) {
+        bI[j + 1] = icol[(size_t)(j + 1) * pitch];
+        dd[j] = dcol[(size_t)(j + 1) * pitch];
+      } else {
+        const int y1 = ipy + 4 * k + j + 1;
+        bI[j + 1] = icol[(size_t)reflect101(y1, h) * pitch];
+        dd[j] = (in_x && y1 >= 0 && y1 < h) ? dcol[(size_t)y1 * pitch] : 0u;
+      }
+    }
+    if (INTERIOR) { icol += 4 * (size_t)pitch; dcol += 4 * (size_t)pitch; }
+    bI0 = bI[4];
+    const unsigned Pk = pack4(bI[0], bI[1], bI[2], bI[3]), Pn = bI[4];
+    const unsigned Qk = __shfl_down_sync(FULL, Pk, 1), Qn = __shfl_down_sync(FULL, Pn, 1);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int r = 4 * k + j;                                  // window row r blends image rows r, r+1
+      const unsigned d1 = dd[j];
+      const unsigned d1r = __shfl_down_sync(FULL, d1, 1);
+      const int vX = (int)(short)(d1 & 0xffffu), vY = (int)d1 >> 16, vXr = (int)(short)(d1r & 0xffffu), vYr = (int)d1r >> 16;
+      int sI;
+      if (j == 0) sI = blend_row<0>(Pk, Pn, Qk, Qn, wv0, wv1, 1 << (WB - 5 - 1));
+      else if (j == 1) sI = blend_row<1>(Pk, Pn, Qk, Qn, wv0, wv1, 1 << (WB - 5 - 1));
+      else if (j == 2) sI = blend_row<2>(Pk, Pn, Qk, Qn, wv0, wv1, 1 << (WB - 5 - 1));
+      else sI = blend_row<3>(Pk, Pn, Qk, Qn, wv0, wv1, 1 << (WB - 5 - 1));
+      const int iv = sI >> (WB - 5);                             // lane 31's value is never used (Ix = Iy = 0, ERR masks it)
+      int ix = (qX * w00 + qXr * w01 + vX * w10 + vXr * w11 + (1 << (WB - 1))) >> WB;
+      int iy = (qY * w00 + qYr * w01 + vY * w10 + vYr * w11 + (1 << (WB - 1))) >> WB;
+      ix = live ? ix : 0; iy = live ? iy : 0;
+      if (r < WIN) {
+        tmpl[r * 32] = make_int2((1 << (WB - 5 - 1)) - (iv << (WB - 5)), (iy << 16) | (ix & 0xffff));
+        a11 += ix * ix; a12 += ix * iy; a22 += iy * iy;
+      }
+      qX = vX; qY = vY; qXr = vXr; qYr = vYr;
+    }
+  }
+}
+
 __global__ void __launch_bounds__(V4_WARPS * 32, 5)
 lk_track_kernel_v4(const uint8_t* __restrict__ pyrI, const unsigned* __restrict__ derivI, const uint8_t* __restrict__ pyrJ,
                    LKGeom g, const int* __restrict__ npts, const float* __restrict__ prev_xy,
@@ -268,55 +334,11 @@ lk_track_kernel_v4(const uint8_t* __restrict__ pyrI, const unsigned* __restrict_
 
     unsigned P[8], Q[8];
     // ---- template patch -> shared memory ------------------------------------------------------
-    // Rolled over groups of four window rows (small code: the instruction cache, not the ALUs, limited the unrolled
-    // form): a group loads its 4 new image rows + derivative rows up front, packs the u8 column, blends.
     int a11 = 0, a12 = 0, a22 = 0;
-    {
-      const int wv0 = (w00 & 0xffff) | (w10 << 16), wv1 = (w01 & 0xffff) | (w11 << 16);
-      const int x = ipx + lane;
-      const bool in_x = x >= 0 && x < w;
-      const uint8_t* icol = I + reflect101(x, w);                  // I: BORDER_REFLECT_101
-      const unsigned* dcol = Dv + x;                               // derivative: zero outside the image
-      unsigned bI0 = icol[(size_t)reflect101(ipy, h) * pitch];
-      unsigned d0 = (in_x && ipy >= 0 && ipy < h) ? dcol[(size_t)ipy * pitch] : 0u;
-      unsigned d0r = __shfl_down_sync(FULL, d0, 1);
-      int qX = (int)(short)(d0 & 0xffffu), qY = (int)d0 >> 16, qXr = (int)(short)(d0r & 0xffffu), qYr = (int)d0r >> 16;
-#pragma unroll 1
-      for (int k = 0; k < 8; ++k) {
-        unsigned bI[5], dd[4];
-        bI[0] = bI0;
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const int y1 = ipy + 4 * k + j + 1;
-          bI[j + 1] = icol[(size_t)reflect101(y1, h) * pitch];
-          dd[j] = (in_x && y1 >= 0 && y1 < h) ? dcol[(size_t)y1 * pitch] : 0u;
-        }
-        bI0 = bI[4];
-        const unsigned Pk = pack4(bI[0], bI[1], bI[2], bI[3]), Pn = bI[4];
-        const unsigned Qk = __shfl_down_sync(FULL, Pk, 1), Qn = __shfl_down_sync(FULL, Pn, 1);
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const int r = 4 * k + j;                                  // window row r blends image rows r, r+1
-          const unsigned d1 = dd[j];
-          const unsigned d1r = __shfl_down_sync(FULL, d1, 1);
-          const int vX = (int)(short)(d1 & 0xffffu), vY = (int)d1 >> 16, vXr = (int)(short)(d1r & 0xffffu), vYr = (int)d1r >> 16;
-          int sI;
-          if (j == 0) sI = blend_row<0>(Pk, Pn, Qk, Qn, wv0, wv1, 1 << (WB - 5 - 1));
-          else if (j == 1) sI = blend_row<1>(Pk, Pn, Qk, Qn, wv0, wv1, 1 << (WB - 5 - 1));
-          else if (j == 2) sI = blend_row<2>(Pk, Pn, Qk, Qn, wv0, wv1, 1 << (WB - 5 - 1));
-          else sI = blend_row<3>(Pk, Pn, Qk, Qn, wv0, wv1, 1 << (WB - 5 - 1));
-          int iv = sI >> (WB - 5);
-          int ix = (qX * w00 + qXr * w01 + vX * w10 + vXr * w11 + (1 << (WB - 1))) >> WB;
-          int iy = (qY * w00 + qYr * w01 + vY * w10 + vYr * w11 + (1 << (WB - 1))) >> WB;
-          iv = live ? iv : 0; ix = live ? ix : 0; iy = live ? iy : 0;
-          if (r < WIN) {
-            tmpl[r * 32] = make_int2((1 << (WB - 5 - 1)) - (iv << (WB - 5)), (iy << 16) | (ix & 0xffff));
-            a11 += ix * ix; a12 += ix * iy; a22 += iy * iy;
-          }
-          qX = vX; qY = vY; qXr = vXr; qYr = vYr;
-        }
-      }
-    }
+    if (ipx >= 0 && ipx + 32 <= w && ipy >= 0 && ipy + 32 <= h)
+      build_template<true>(I, Dv, pitch, w, h, ipx, ipy, lane, live, w00, w01, w10, w11, tmpl, a11, a12, a22);
+    else
+      build_template<false>(I, Dv, pitch, w, h, ipx, ipy, lane, live, w00, w01, w10, w11, tmpl, a11, a12, a22);
     const float A11 = __ll2float_rn(warp_sum_exact(a11)) * FLT_SCALE;
     const float A12 = __ll2float_rn(warp_sum_exact(a12)) * FLT_SCALE;
     const float A22 = __ll2float_rn(warp_sum_exact(a22)) * FLT_SCALE;

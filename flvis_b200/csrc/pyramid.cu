@@ -146,7 +146,65 @@ __global__ void __launch_bounds__(FUSED_WARPS * 32) ingest_l1_kernel(const uint8
   }
 }
 
+// ---- cv::equalizeHist on ingest (need_equal_hist, src/frontend/f2f_tracking.cpp:125-145) -----------------------------
+// OpenCV: hist over the whole image; i0 = first non-empty bin; if it holds every pixel the image becomes the constant i0;
+// else scale = 255.f / (total - hist[i0]) and lut[i] = saturate_cast<uchar>(sum_{i0 < j <= i} hist[j] * scale) (float
+// product, round half even).  Pinned to cv2.equalizeHist by tests/test_frontend_gpu.py.
+constexpr int EQ_ROWS = 16;      // image rows per CTA
+
+__global__ void __launch_bounds__(256) hist_kernel(const uint8_t* __restrict__ src, size_t row_stride, size_t img_stride, int w, int h,
+                                                   int* __restrict__ hist) {
+  __shared__ int sh[256];
+  sh[threadIdx.x] = 0;
+  __syncthreads();
+  const uint8_t* img = src + (size_t)blockIdx.y * img_stride;
+  const int y0 = blockIdx.x * EQ_ROWS, y1 = min(y0 + EQ_ROWS, h);
+  for (int y = y0; y < y1; ++y)
+    for (int x = threadIdx.x; x < w; x += 256) atomicAdd(&sh[img[(size_t)y * row_stride + x]], 1);
+  __syncthreads();
+  if (sh[threadIdx.x]) atomicAdd(&hist[blockIdx.y * 256 + threadIdx.x], sh[threadIdx.x]);
+}
+
+__global__ void __launch_bounds__(256) equalize_apply_kernel(const uint8_t* __restrict__ src, size_t row_stride, size_t img_stride,
+                                                             uint8_t* __restrict__ dst, int w, int h, const int* __restrict__ hist) {
+  __shared__ int sh[256];
+  __shared__ unsigned char lut[256];
+  __shared__ int s_i0;
+  const int t = threadIdx.x;
+  sh[t] = hist[blockIdx.y * 256 + t];
+  if (t == 0) s_i0 = 256;
+  __syncthreads();
+  if (sh[t]) atomicMin(&s_i0, t);
+  __syncthreads();
+  const int i0 = s_i0, total = w * h;
+  if (sh[i0] == total) lut[t] = (unsigned char)i0;
+  else {
+    const float scale = __fdiv_rn(255.f, (float)(total - sh[i0]));
+    int sum = 0;
+    for (int j = i0 + 1; j <= t; ++j) sum += sh[j];
+    int v = t <= i0 ? 0 : __float2int_rn(__fmul_rn((float)sum, scale));
+    lut[t] = (unsigned char)(v > 255 ? 255 : v);
+  }
+  __syncthreads();
+  const uint8_t* img = src + (size_t)blockIdx.y * img_stride;
+  uint8_t* out = dst + (size_t)blockIdx.y * (size_t)w * h;        // tight [S][h][w]
+  const int y0 = blockIdx.x * EQ_ROWS, y1 = min(y0 + EQ_ROWS, h);
+  for (int y = y0; y < y1; ++y)
+    for (int x = t; x < w; x += 256) out[(size_t)y * w + x] = lut[img[(size_t)y * row_stride + x]];
+}
+
 }  // namespace
+
+int flv_launch_equalize(flv_ctx* ctx, int n_streams, const uint8_t* d_src, size_t row_stride, size_t img_stride, uint8_t* d_dst_tight) {
+  if (!ctx->d_hist) FLV_CUDA(ctx, cudaMalloc(&ctx->d_hist, (size_t)ctx->S * 256 * sizeof(int)));
+  FLV_CUDA(ctx, cudaMemsetAsync(ctx->d_hist, 0, (size_t)n_streams * 256 * sizeof(int), ctx->stream));
+  dim3 grid((ctx->h + EQ_ROWS - 1) / EQ_ROWS, n_streams);
+  hist_kernel<<<grid, 256, 0, ctx->stream>>>(d_src, row_stride, img_stride, ctx->w, ctx->h, ctx->d_hist);
+  equalize_apply_kernel<<<grid, 256, 0, ctx->stream>>>(d_src, row_stride, img_stride, d_dst_tight, ctx->w, ctx->h, ctx->d_hist);
+  ctx->launches += 2;
+  FLV_CUDA(ctx, cudaGetLastError());
+  return FLV_OK;
+}
 
 int flv_launch_unpack(flv_ctx* ctx, int slot, int n_streams, const uint8_t* d_src, size_t row_stride,
                       size_t img_stride) {

@@ -66,13 +66,10 @@ F2FTracking::~F2FTracking() { delete vimotion; if (ctx_) flv_destroy(ctx_); }
 
 int F2FTracking::init(const DepthCamera& dc, const SE3& T_i_c0, const double feature_para[6], const double vi_para[6],
                       const double dc_para[3], int skip_first_n_imgs, bool need_equal_hist_in, int device) {   // f2f_tracking.cpp:5-38
-  if (dc.cam_type == STEREO_UNRECT || need_equal_hist_in) {
-    snprintf(err_, sizeof(err_), "STEREO_UNRECT / equalizeHist ingest is not implemented in the host layer");
-    return FLV_ERR_UNSUPPORTED;
-  }
   skip_n_imgs = skip_first_n_imgs; need_equal_hist = need_equal_hist_in;
   int rc = flv_create(&ctx_, device, 1, dc.img_w, dc.img_h, MAX_PTS);
   if (rc) { snprintf(err_, sizeof(err_), "flv_create: %s", flv_last_error(ctx_)); return rc; }
+  if (need_equal_hist && (rc = flv_set_equalize_hist(ctx_, 1))) return rc;    // f2f_tracking.cpp:125-145
   fprm_.max_region_feature_num = (int)feature_para[0];
   fprm_.min_region_feature_num = (int)feature_para[1];
   fprm_.boundary_dis = (int)std::floor(feature_para[2] / 2.0);
@@ -190,8 +187,11 @@ int F2FTracking::image_feed(double time, const uint8_t* img0, const void* img1, 
       const int orig_size = (int)curr_frame->landmarks.size();
       if ((rc = feature_redetect(*curr_frame, pts2d))) return rc;
       const bool add_as_inliers = orig_size < 60;
-      for (const P2f& p : pts2d)        // DEPTH_D435 / STEREO_RECT: pts2d_undistort = pts2d (:294-299)
-        curr_frame->landmarks.push_back(make_landmark(Vec2{p.x, p.y}, Vec2{p.x, p.y}, curr_frame->T_c_w, add_as_inliers));
+      for (const P2f& p : pts2d) {      // DEPTH_D435 / STEREO_RECT: pts2d_undistort = pts2d (:294-299); UNRECT: undistortPoints (:300-303)
+        P2f u = p;
+        if (cam_type == STEREO_UNRECT) undistort_point(d_camera.lens0, p.x, p.y, u.x, u.y);
+        curr_frame->landmarks.push_back(make_landmark(Vec2{p.x, p.y}, Vec2{u.x, u.y}, curr_frame->T_c_w, add_as_inliers));
+      }
       if ((rc = depth_innovation(*curr_frame))) return rc;
       curr_frame->eraseNoDepthPoint();
       pose_records.push_back(ID_POSE{curr_frame->frame_id, curr_frame->T_c_w});
@@ -226,8 +226,11 @@ bool F2FTracking::init_frame() {                                   // f2f_tracki
   std::vector<P2f> pts2d;
   if (feature_detect(*curr_frame, pts2d)) return false;
   // DEPTH: undistorted = plane.  STEREO_RECT: cv::undistortPoints(K0, D0=0, R0=I, P0) is the identity map up to rounding
-  for (const P2f& p : pts2d)
-    curr_frame->landmarks.push_back(make_landmark(Vec2{p.x, p.y}, Vec2{p.x, p.y}, curr_frame->T_c_w, true));
+  for (const P2f& p : pts2d) {
+    P2f u = p;
+    if (cam_type == STEREO_UNRECT) undistort_point(d_camera.lens0, p.x, p.y, u.x, u.y);      // :425
+    curr_frame->landmarks.push_back(make_landmark(Vec2{p.x, p.y}, Vec2{u.x, u.y}, curr_frame->T_c_w, true));
+  }
   if (depth_innovation(*curr_frame)) return false;
   curr_frame->eraseNoDepthPoint();
   if (curr_frame->validLMCount() > 30) {
@@ -249,12 +252,20 @@ bool F2FTracking::tracking(CameraFrame& from, CameraFrame& to, const SE3& T_c_w_
     from_p3d[i] = P3f{(float)lm.lm_3d_w[0], (float)lm.lm_3d_w[1], (float)lm.lm_3d_w[2]};
   }
   tracked_plane = from_plane;
-  if (use_guess)                                                 // :38-63 (pinhole projection; D0 = 0 for the supported types)
-    for (int i = 0; i < n; ++i) {
-      const Vec3 pc = DepthCamera::world2cameraT_c_w(Vec3{from_p3d[i].x, from_p3d[i].y, from_p3d[i].z}, T_c_w_guess);
-      const Vec2 px = from.d_camera.camera2pixel(pc);
-      tracked_plane[i] = P2f{(float)px[0], (float)px[1]};
+  if (use_guess) {                                               // :38-63
+    if (cam_type == STEREO_UNRECT) {                             // cv::projectPoints(K0, D0): back into the distorted image
+      double Rg[9]; q_to_R(T_c_w_guess.q, Rg);
+      const double tg[3] = {T_c_w_guess.t[0], T_c_w_guess.t[1], T_c_w_guess.t[2]};
+      for (int i = 0; i < n; ++i)
+        project_point(d_camera.lens0, Rg, tg, from_p3d[i].x, from_p3d[i].y, from_p3d[i].z, tracked_plane[i].x, tracked_plane[i].y);
+    } else {                                                     // pinhole (DEPTH_D435; STEREO_RECT has D0 = 0)
+      for (int i = 0; i < n; ++i) {
+        const Vec3 pc = DepthCamera::world2cameraT_c_w(Vec3{from_p3d[i].x, from_p3d[i].y, from_p3d[i].z}, T_c_w_guess);
+        const Vec2 px = from.d_camera.camera2pixel(pc);
+        tracked_plane[i] = P2f{(float)px[0], (float)px[1]};
+      }
     }
+  }
   std::vector<float> prev(2 * MAX_PTS, 0.f), init(2 * MAX_PTS, 0.f), next(2 * MAX_PTS), err(MAX_PTS);
   std::vector<uint8_t> st(MAX_PTS);
   memcpy(prev.data(), from_plane.data(), (size_t)n * 8);
@@ -264,6 +275,8 @@ bool F2FTracking::tracking(CameraFrame& from, CameraFrame& to, const SE3& T_c_w_
     return false;
   memcpy(tracked_plane.data(), next.data(), (size_t)n * 8);
   std::vector<P2f> tracked_und = tracked_plane;                  // DEPTH_D435 / STEREO_RECT (:78-85)
+  if (cam_type == STEREO_UNRECT)                                 // cv::undistortPoints(K0, D0, R0, P0) (:86-89)
+    for (int i = 0; i < n; ++i) undistort_point(d_camera.lens0, tracked_plane[i].x, tracked_plane[i].y, tracked_und[i].x, tracked_und[i].y);
   to.landmarks.clear();
   const int wlim = to.d_camera.img_w - 1, hlim = to.d_camera.img_h - 1;
   int of_inlier_cnt = 0;
@@ -397,11 +410,15 @@ int F2FTracking::depth_innovation(CameraFrame& fr) {              // camera_fram
     // project the landmarks that already have depth into cam1 (cv::projectPoints with D1 = 0), else start at the cam0 position
     std::vector<float> prev(2 * MAX_PTS, 0.f), init(2 * MAX_PTS, 0.f), next(2 * MAX_PTS), err(MAX_PTS);
     const SE3 T_c1_w = d_camera.T_cam1_cam0 * fr.T_c_w;
+    double R1w[9]; q_to_R(T_c1_w.q, R1w);
+    const double t1w[3] = {T_c1_w.t[0], T_c1_w.t[1], T_c1_w.t[2]};
     for (int i = 0; i < n; ++i) {
       const LandMarkInFrame& lm = fr.landmarks[i];
       prev[2 * i] = (float)lm.lm_2d_plane[0]; prev[2 * i + 1] = (float)lm.lm_2d_plane[1];
       init[2 * i] = prev[2 * i]; init[2 * i + 1] = prev[2 * i + 1];
-      if (lm.has_3d) {
+      if (lm.has_3d && cam_type == STEREO_UNRECT) {                // cv::projectPoints(K1, D1) (camera_frame.cpp:113-122)
+        project_point(d_camera.lens1, R1w, t1w, (float)lm.lm_3d_w[0], (float)lm.lm_3d_w[1], (float)lm.lm_3d_w[2], init[2 * i], init[2 * i + 1]);
+      } else if (lm.has_3d) {
         const Vec3 pc = DepthCamera::world2cameraT_c_w(Vec3{(double)(float)lm.lm_3d_w[0], (double)(float)lm.lm_3d_w[1], (double)(float)lm.lm_3d_w[2]}, T_c1_w);
         init[2 * i] = (float)(d_camera.cam1_fx * pc[0] / pc[2] + d_camera.cam1_cx);
         init[2 * i + 1] = (float)(d_camera.cam1_fy * pc[1] / pc[2] + d_camera.cam1_cy);
@@ -410,7 +427,11 @@ int F2FTracking::depth_innovation(CameraFrame& fr) {              // camera_fram
     flv_lk_params lk{31, 5, 30, 1e-3, 1e-4};
     int rc = flv_lk_track(ctx_, fr.slot0, fr.slot1, 1, &n, prev.data(), init.data(), next.data(), st1.data(), err.data(), &lk, FLV_MEM_HOST);
     if (rc) return rc;
-    for (int i = 0; i < n; ++i) { pt1[2 * i] = next[2 * i]; pt1[2 * i + 1] = next[2 * i + 1]; }   // rectified: undistort = identity
+    for (int i = 0; i < n; ++i) {                                  // cv::undistortPoints(K1, D1, R1, P1) (camera_frame.cpp:130)
+      float ux = next[2 * i], uy = next[2 * i + 1];                // rectified input: the map is the identity
+      if (cam_type == STEREO_UNRECT) undistort_point(d_camera.lens1, next[2 * i], next[2 * i + 1], ux, uy);
+      pt1[2 * i] = ux; pt1[2 * i + 1] = uy;
+    }
   }
   // the next MAX_PTS dummy depths of this sequence's rand() stream; only the consumed ones advance the generator
   GlibcRand peek = rand_;

@@ -8,8 +8,8 @@
 //   F2FTracking                  src/frontend/include/f2f_tracking.h:24-78, f2f_tracking.cpp:5-453
 // cv::Mat arguments become raw image pointers; every OpenCV / g2o call goes to the GPU through the C ABI
 // (include/flvis_b200.h) except the two RANSAC calls, which are host stand-ins (ransac.h) or caller callbacks.
-// Supported sensor types: DEPTH_D435 (type_of_vi 0/2) and STEREO_RECT (3/4).  STEREO_UNRECT (EuRoC raw, type 1) needs
-// lens undistortion + equalizeHist on ingest, which this layer does not implement yet (reported as an error).
+// Sensor types: DEPTH_D435, STEREO_RECT, STEREO_UNRECT (EuRoC raw: LK runs on the distorted images, points go through
+// cv::undistortPoints / cv::projectPoints restated in undistort.h); need_equal_hist = cv::equalizeHist on ingest (GPU).
 #pragma once
 #include <cstdint>
 #include <deque>
@@ -19,6 +19,7 @@
 #include "glibc_rand.h"
 #include "ransac.h"
 #include "sophus_lite.h"
+#include "undistort.h"
 #include "vi_motion.h"
 
 namespace flv {
@@ -33,6 +34,7 @@ struct DepthCamera {
   double cam_scale_factor = 1000.0;
   double P0_[12] = {0}, P1_[12] = {0};                          // rectified projection matrices, row-major 3x4
   SE3 T_cam1_cam0;
+  LensModel lens0, lens1;                                       // K0/D0/R0/P0, K1/D1/R1/P1 (STEREO_UNRECT: raw lens models)
   Vec2 camera2pixel(const Vec3& p_c) const { return Vec2{cam0_fx * p_c[0] / p_c[2] + cam0_cx, cam0_fy * p_c[1] / p_c[2] + cam0_cy}; }
   static Vec3 world2cameraT_c_w(const Vec3& p_w, const SE3& T) { const Vec3 r = q_rot(T.q, p_w); return Vec3{r[0] + T.t[0], r[1] + T.t[1], r[2] + T.t[2]}; }
   static Vec3 camera2worldT_c_w(const Vec3& p_c, const SE3& T) { const SE3 Ti = T.inverse(); const Vec3 r = q_rot(Ti.q, p_c); return Vec3{r[0] + Ti.t[0], r[1] + Ti.t[1], r[2] + Ti.t[2]}; }
@@ -85,6 +87,15 @@ class F2FTracking {
   // img1: u8 right image (stereo) or u16 depth image (DEPTH_D435); rows tightly packed
   int image_feed(double time, const uint8_t* img0, const void* img1, bool& new_keyframe, bool& reset_cmd);
   void set_ransac_hooks(flv_fmat_fn f, flv_pnp_fn p, void* user) { fmat_fn_ = f; pnp_fn_ = p; hook_user_ = user; }
+  // raw lens model of camera `cam` (K, D[14], R rectification); P stays the rectified projection given at init
+  int set_lens(int cam, const double* K4, const double* D14, const double* R9) {
+    LensModel& m = cam == 0 ? d_camera.lens0 : d_camera.lens1;
+    m.fx = K4[0]; m.fy = K4[1]; m.cx = K4[2]; m.cy = K4[3];
+    for (int i = 0; i < 14; ++i) m.k[i] = D14[i];
+    for (int i = 0; i < 9; ++i) m.R[i] = R9[i];
+    return 0;
+  }
+  int set_equalize_hist(bool enable) { need_equal_hist = enable; return flv_set_equalize_hist(ctx_, enable ? 1 : 0); }
 
   std::shared_ptr<CameraFrame> curr_frame, last_frame;
   TRACKINGSTATE vo_tracking_state = UnInit;

@@ -108,19 +108,56 @@ flv_f2f* flv_f2f_create(const flv_f2f_config* c, int device) {
   flv_f2f* f = new (std::nothrow) flv_f2f();
   if (!f) return nullptr;
   flv::DepthCamera dc;
-  dc.cam_type = c->cam_type == 0 ? flv::DEPTH_D435 : flv::STEREO_RECT;
+  dc.cam_type = c->cam_type == 0 ? flv::DEPTH_D435 : c->cam_type == 1 ? flv::STEREO_RECT : flv::STEREO_UNRECT;
   dc.img_w = c->img_w; dc.img_h = c->img_h;
   dc.cam0_fx = c->cam0[0]; dc.cam0_fy = c->cam0[1]; dc.cam0_cx = c->cam0[2]; dc.cam0_cy = c->cam0[3];
   dc.cam1_fx = c->cam1[0]; dc.cam1_fy = c->cam1[1]; dc.cam1_cx = c->cam1[2]; dc.cam1_cy = c->cam1[3];
   dc.cam_scale_factor = c->depth_scale;
   for (int i = 0; i < 12; ++i) { dc.P0_[i] = c->P0[i]; dc.P1_[i] = c->P1[i]; }
   dc.T_cam1_cam0 = se3_from7(c->T_cam1_cam0);
+  // lens models default to the rectified pinhole (K from P, D = 0, R = I); flv_f2f_set_lens installs the raw models
+  dc.lens0.fx = dc.cam0_fx; dc.lens0.fy = dc.cam0_fy; dc.lens0.cx = dc.cam0_cx; dc.lens0.cy = dc.cam0_cy;
+  dc.lens1.fx = dc.cam1_fx; dc.lens1.fy = dc.cam1_fy; dc.lens1.cx = dc.cam1_cx; dc.lens1.cy = dc.cam1_cy;
+  for (int i = 0; i < 12; ++i) { dc.lens0.P[i] = c->P0[i]; dc.lens1.P[i] = c->P1[i]; }
   if (f->impl.init(dc, se3_from7(c->T_i_c0), c->feature_para, c->vi_para, c->dc_para, c->skip_first_n_imgs, false, device) != FLV_OK) {
     // keep the object so the caller can read last_error; image_feed will fail
   }
   return f;
 }
 void flv_f2f_destroy(flv_f2f* f) { delete f; }
+int flv_f2f_set_lens(flv_f2f* f, int cam, const double* K4, const double* D14, const double* R9) {
+  if (!f || (cam != 0 && cam != 1) || !K4 || !D14 || !R9) return FLV_ERR_INVALID;
+  if (D14[12] != 0 || D14[13] != 0) return FLV_ERR_UNSUPPORTED;      // tilted sensor model
+  for (flv::CameraFrame* fr : {f->impl.curr_frame.get(), f->impl.last_frame.get()}) {
+    if (!fr) continue;
+    flv::LensModel& m = cam == 0 ? fr->d_camera.lens0 : fr->d_camera.lens1;
+    m.fx = K4[0]; m.fy = K4[1]; m.cx = K4[2]; m.cy = K4[3];
+    for (int i = 0; i < 14; ++i) m.k[i] = D14[i];
+    for (int i = 0; i < 9; ++i) m.R[i] = R9[i];
+  }
+  return f->impl.set_lens(cam, K4, D14, R9);
+}
+int flv_f2f_set_equalize_hist(flv_f2f* f, int enable) { return f ? f->impl.set_equalize_hist(enable != 0) : FLV_ERR_INVALID; }
+int flv_host_undistort_points(const double* K4, const double* D14, const double* R9, const double* P12, int n, const float* in_xy,
+                              float* out_xy) {
+  if (!K4 || !D14 || !R9 || !P12 || !in_xy || !out_xy || n < 0) return FLV_ERR_INVALID;
+  flv::LensModel m;
+  m.fx = K4[0]; m.fy = K4[1]; m.cx = K4[2]; m.cy = K4[3];
+  for (int i = 0; i < 14; ++i) m.k[i] = D14[i];
+  for (int i = 0; i < 9; ++i) m.R[i] = R9[i];
+  for (int i = 0; i < 12; ++i) m.P[i] = P12[i];
+  for (int i = 0; i < n; ++i) flv::undistort_point(m, in_xy[2 * i], in_xy[2 * i + 1], out_xy[2 * i], out_xy[2 * i + 1]);
+  return FLV_OK;
+}
+int flv_host_project_points(const double* K4, const double* D14, const double* Rcw9, const double* t3, int n, const float* xyz,
+                            float* out_xy) {
+  if (!K4 || !D14 || !Rcw9 || !t3 || !xyz || !out_xy || n < 0) return FLV_ERR_INVALID;
+  flv::LensModel m;
+  m.fx = K4[0]; m.fy = K4[1]; m.cx = K4[2]; m.cy = K4[3];
+  for (int i = 0; i < 14; ++i) m.k[i] = D14[i];
+  for (int i = 0; i < n; ++i) flv::project_point(m, Rcw9, t3, xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2], out_xy[2 * i], out_xy[2 * i + 1]);
+  return FLV_OK;
+}
 const char* flv_f2f_last_error(flv_f2f* f) { return f ? f->impl.last_error() : "null"; }
 void flv_f2f_set_ransac_hooks(flv_f2f* f, flv_f2f_fmat_fn fmat, flv_f2f_pnp_fn pnp, void* user) {
   if (f) f->impl.set_ransac_hooks(fmat, pnp, user);

@@ -72,6 +72,9 @@ class FrontendBench:
         self.has_ba = False
         self.ba = None
         try:
+            import os
+            if os.environ.get("FLV_BENCH_NO_BA"):          # diagnostic only: frontend alone under bench conditions
+                raise ImportError
             from . import ba_synth
             self.ba = ba_synth.DeviceBatch(self.ctx, make_ba_batch(n_streams, ba_window, seed=seed), self.dev)
             self.has_ba = True

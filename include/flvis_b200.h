@@ -57,6 +57,9 @@ long long flv_launch_count(flv_ctx* ctx);
 int flv_level_info(flv_ctx* ctx, int level, int* w, int* h, int* pitch, size_t* offset);
 int flv_num_levels(flv_ctx* ctx);
 
+/* need_equal_hist (src/frontend/f2f_tracking.cpp:125-145): when enabled, every image ingested by flv_upload_images goes
+ * through cv::equalizeHist (per-image histogram, LUT) before level 0 is written.  Bit-exact with cv2.equalizeHist. */
+int flv_set_equalize_hist(flv_ctx* ctx, int enable);
 /* ---- images + pyramid (K1) ---------------------------------------------------------------
  * Replaces the image hand-over of F2FTracking::image_feed (src/frontend/f2f_tracking.cpp:59-145)
  * and cv::buildOpticalFlowPyramid inside cv::calcOpticalFlowPyrLK (called at

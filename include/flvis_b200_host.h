@@ -43,7 +43,7 @@ int flv_vimotion_queue_size(flv_vimotion* vm);
 
 /* ---- flv::F2FTracking <- src/frontend/include/f2f_tracking.h:24-78, src/frontend/f2f_tracking.cpp:5-453 --------
  * One handle = one camera sequence (private single-stream context).  cam_type: 0 = DEPTH_D435 (img1 = u16 depth),
- * 1 = STEREO_RECT (img1 = u8 right image).  Poses are [qx qy qz qw tx ty tz]. */
+ * 1 = STEREO_RECT, 2 = STEREO_UNRECT (img1 = u8 right image).  Poses are [qx qy qz qw tx ty tz]. */
 typedef struct flv_f2f flv_f2f;
 typedef struct {
   int cam_type, img_w, img_h;
@@ -62,6 +62,17 @@ typedef int (*flv_f2f_pnp_fn)(void* user, int n, const float* p3d, const float* 
                               double* T_c_w_inout, int* inlier_idx_out, int* n_inliers_out);
 flv_f2f* flv_f2f_create(const flv_f2f_config* cfg, int device);
 void flv_f2f_destroy(flv_f2f* f);
+/* STEREO_UNRECT (cam_type 2; EuRoC raw images): raw lens model of camera `cam` (0 | 1) = DepthCamera::K0/D0/R0 or K1/D1/R1
+ * (src/processing/depth_camera.cpp:27-72): K4 = fx fy cx cy, D14 = OpenCV order k1 k2 p1 p2 k3 k4 k5 k6 s1 s2 s3 s4 0 0,
+ * R9 = rectification rotation (row-major).  The rectified projection P0 / P1 comes from flv_f2f_config.  Call before the
+ * first image_feed.  need_equal_hist (f2f_tracking.cpp:125-145): cv::equalizeHist of every ingested image, on the GPU. */
+int flv_f2f_set_lens(flv_f2f* f, int cam, const double* K4, const double* D14, const double* R9);
+int flv_f2f_set_equalize_hist(flv_f2f* f, int enable);
+/* the two per-point OpenCV calls of the UNRECT path, exported for the parity tests (flvis_b200/host/undistort.h) */
+int flv_host_undistort_points(const double* K4, const double* D14, const double* R9, const double* P12, int n, const float* in_xy,
+                              float* out_xy);
+int flv_host_project_points(const double* K4, const double* D14, const double* Rcw9, const double* t3, int n, const float* xyz,
+                            float* out_xy);
 const char* flv_f2f_last_error(flv_f2f* f);
 void flv_f2f_set_ransac_hooks(flv_f2f* f, flv_f2f_fmat_fn fmat, flv_f2f_pnp_fn pnp, void* user);
 int flv_f2f_imu_feed(flv_f2f* f, double t, const double* acc, const double* gyro);

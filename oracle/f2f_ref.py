@@ -5,7 +5,9 @@ Follows /root/reference/src/frontend/f2f_tracking.cpp:5-453, src/processing/lkor
 optimize_in_frame.cpp:10-90, camera_frame.cpp (via oracle/camera_frame_ref.py), landmark.cpp:3-44.
 OpenCV calls: LK = oracle/lk_ref.py (bit-exact contract of the CUDA kernel; cv2 itself is <= 1e-3 px away),
 FeatureDEM = oracle/feature_dem_ref.py, findFundamentalMat / solvePnPRansac = cv2 (the reference's real library).
-Sensor types: "depth" (DEPTH_D435) and "stereo" (STEREO_RECT, zero distortion).  The dead local-map feedback
+Sensor types: "depth" (DEPTH_D435), "stereo" (STEREO_RECT, zero distortion) and "stereo_unrect" (STEREO_UNRECT: LK on the
+raw images, cv2.undistortPoints / cv2.projectPoints per point with the raw lens models `lens0` / `lens1` =
+(K 3x3, D, R 3x3)); `equalize` = need_equal_hist (cv2.equalizeHist on ingest).  The dead local-map feedback
 (f2f_tracking.cpp:189-219) is not restated.
 """
 import math
@@ -47,13 +49,14 @@ def so3_log(q):
 
 class F2FTracking:
     def __init__(self, cam_type, w, h, K, feature_para, vi_para, dc_para, T_i_c=None, skip=0, depth_scale=1000.0,
-                 K1=None, P0=None, P1=None, T_c1_c0=None):
+                 K1=None, P0=None, P1=None, T_c1_c0=None, lens0=None, lens1=None, equalize=False):
         self.cam_type, self.w, self.h, self.K = cam_type, w, h, tuple(K)
         self.fd = feature_dem_ref.FeatureDEM(w, h, feature_para)
         self.vim = VIMOTION(T_i_c or SE3(), 9.81, vi_para[0], vi_para[1], vi_para[2], vi_para[3])
         self.iir = float(f32(dc_para[0])); self.range = float(f32(dc_para[1])); self.dummy = not (dc_para[2] < 0.5)
         self.skip = skip; self.depth_scale = depth_scale
         self.K1, self.P0, self.P1, self.T_c1_c0 = K1, P0, P1, T_c1_c0
+        self.lens0, self.lens1, self.equalize = lens0, lens1, equalize
         self.curr, self.last = Frame(), Frame()
         self.state = "UnInit"; self.has_imu = False; self.frameCount = 0
         self.id_index = 100; self.rnd = cf.GlibcRand()
@@ -72,6 +75,20 @@ class F2FTracking:
         lm.first_pose = T; lm.inlier = inlier; lm.p3d_w = np.zeros(3); lm.p3d_c = np.zeros(3); lm.has_3d = False
         return lm
 
+    def _undist(self, lens, P, pts):
+        """cv::undistortPoints(pts, K, D, R, P) on an (n,2) float32 array."""
+        if len(pts) == 0:
+            return np.zeros((0, 2), f32)
+        K, D, R = lens
+        return cv2.undistortPoints(np.asarray(pts, f32).reshape(-1, 1, 2), K, D, R=R, P=P[:3, :3]).reshape(-1, 2)
+
+    def _project(self, lens, T, p3d):
+        """cv::projectPoints(p3d, rvec(T), tvec(T), K, D) -> (n,2) float32."""
+        K, D, _ = lens
+        rvec, _ = cv2.Rodrigues(q2R(T.q))
+        out, _ = cv2.projectPoints(np.asarray(p3d, np.float64).reshape(-1, 1, 3), rvec, T.t.reshape(3, 1), K, D)
+        return out.reshape(-1, 2).astype(f32)
+
     # -- CameraFrame::depthInnovation through the SoA oracle
     def _depth_innovation(self, fr):
         n = len(fr.lms)
@@ -86,11 +103,18 @@ class F2FTracking:
             prev = np.array([l.plane for l in fr.lms], f32)
             init = prev.copy()
             T1 = self.T_c1_c0 * fr.T_c_w
-            for i, l in enumerate(fr.lms):
-                if l.has_3d:
-                    pc = cf.world2camera(f32(l.p3d_w).astype(np.float64), T1)
-                    init[i] = (f32(self.K1[0] * pc[0] / pc[2] + self.K1[2]), f32(self.K1[1] * pc[1] / pc[2] + self.K1[3]))
+            if self.cam_type == "stereo_unrect":
+                idx = [i for i, l in enumerate(fr.lms) if l.has_3d]
+                if idx:
+                    init[idx] = self._project(self.lens1, T1, np.array([f32(fr.lms[i].p3d_w) for i in idx]))
+            else:
+                for i, l in enumerate(fr.lms):
+                    if l.has_3d:
+                        pc = cf.world2camera(f32(l.p3d_w).astype(np.float64), T1)
+                        init[i] = (f32(self.K1[0] * pc[0] / pc[2] + self.K1[2]), f32(self.K1[1] * pc[1] / pc[2] + self.K1[3]))
             nxt, st, _ = lk_ref.calc_optical_flow_pyr_lk(fr.img0, fr.img1, prev, init, max_level=5)
+            if self.cam_type == "stereo_unrect":
+                nxt = self._undist(self.lens1, self.P1, nxt)
             cf.depth_innovation(F, self.iir, self.range, self.dummy, self.rnd, stereo=(nxt.astype(np.float64), st))
         for i, l in enumerate(fr.lms):
             if F.has_3d[i]:
@@ -98,8 +122,9 @@ class F2FTracking:
 
     def _init_frame(self):
         pts = self.fd.detect(self.curr.img0)
-        for p in pts:
-            self.curr.lms.append(self._new_lm(p, p, self.curr.T_c_w, True))
+        und = self._undist(self.lens0, self.P0, pts) if self.cam_type == "stereo_unrect" else pts
+        for p, u in zip(pts, und):
+            self.curr.lms.append(self._new_lm(p, u, self.curr.T_c_w, True))
         self._depth_innovation(self.curr)
         self.curr.lms = [l for l in self.curr.lms if l.has_3d]
         if sum(1 for l in self.curr.lms if l.has_3d and l.inlier) > 30:
@@ -113,14 +138,17 @@ class F2FTracking:
         fund = np.array([l.undist for l in frm.lms], f32).reshape(-1, 2)
         fp3 = np.array([l.p3d_w for l in frm.lms], f32).reshape(-1, 3)
         tplane = fplane.copy()
-        if use_guess:
+        if use_guess and self.cam_type == "stereo_unrect":
+            if n:
+                tplane = self._project(self.lens0, guess, fp3)
+        elif use_guess:
             for i in range(n):
                 pc = cf.world2camera(fp3[i].astype(np.float64), guess)
                 px = cf.camera2pixel(pc, self.K)
                 tplane[i] = (f32(px[0]), f32(px[1]))
         nxt, st, _ = lk_ref.calc_optical_flow_pyr_lk(frm.img0, to.img0, fplane, tplane, max_level=10)
         tplane = nxt
-        tund = tplane.copy()
+        tund = self._undist(self.lens0, self.P0, tplane) if self.cam_type == "stereo_unrect" else tplane.copy()
         to.lms = []
         keep = np.ones(n, bool)
         wl, hl = self.w - 1, self.h - 1
@@ -195,6 +223,10 @@ class F2FTracking:
         if self.skip > 0:
             self.skip -= 1
             return new_kf, reset
+        if self.equalize:                                   # f2f_tracking.cpp:125-145
+            self.curr.img0 = cv2.equalizeHist(self.curr.img0)
+            if self.cam_type != "depth":
+                self.curr.img1 = cv2.equalizeHist(self.curr.img1)
         if self.state == "UnInit":
             R_w_c = np.array([[0, 0, 1.0], [-1, 0, 0], [0, -1, 0]])
             self.curr.T_c_w = SE3(R2q(R_w_c), np.zeros(3)).inverse()
@@ -231,8 +263,9 @@ class F2FTracking:
                 self.vim.correction_from_vision(self.curr.time, self.curr.T_c_w, self.last.time, self.last.T_c_w)
             orig = len(self.curr.lms)
             new = self.fd.redetect(self.curr.img0, np.array([l.plane for l in self.curr.lms], np.float64).reshape(-1, 2))
-            for p in new:
-                self.curr.lms.append(self._new_lm(p, p, self.curr.T_c_w, orig < 60))
+            und = self._undist(self.lens0, self.P0, new) if self.cam_type == "stereo_unrect" else new
+            for p, u in zip(new, und):
+                self.curr.lms.append(self._new_lm(p, u, self.curr.T_c_w, orig < 60))
             self._depth_innovation(self.curr)
             self.curr.lms = [l for l in self.curr.lms if l.has_3d]
             Td = self.T_kf * self.curr.T_c_w.inverse()

@@ -202,3 +202,32 @@ def test_feature_dem_detect_redetect_bit_exact(sensor, name):
     det = ctx.feature_detect(0, 2, fp)
     assert np.array_equal(det[0], o0) and np.array_equal(det[1], o1)
     ctx.close()
+
+
+def test_equalize_hist_on_ingest_bit_exact():
+    """flv_set_equalize_hist: level 0 (and the pyramid built from it) of an ingested image == cv2.equalizeHist(image);
+    host and device sources, a low-contrast image, and a constant image (OpenCV's early-out)."""
+    import cv2
+    import torch
+    g, I, J = cases.load_lk("euroc_shift")
+    h, w = I.shape
+    low = (I // 4 + 60).astype(np.uint8)
+    const = np.full_like(I, 77)
+    imgs = np.stack([I, low, const, J])
+    ctx = _ctx(4, w, h)
+    ctx.set_equalize_hist(True)
+    ctx.upload(0, imgs)
+    ctx.build_pyramid(0, 4)
+    for s in range(4):
+        ref = cv2.equalizeHist(imgs[s])
+        assert np.array_equal(ctx.download_level(0, s, 0), ref)
+        assert np.array_equal(ctx.download_level(0, s, 1), lk_ref.pyr_down(ref))
+    d = torch.from_numpy(imgs).cuda()
+    ctx.upload_dev(1, 4, d.data_ptr())
+    torch.cuda.synchronize()
+    for s in range(4):
+        assert np.array_equal(ctx.download_level(1, s, 0), cv2.equalizeHist(imgs[s]))
+    ctx.set_equalize_hist(False)
+    ctx.upload(2, imgs)
+    assert np.array_equal(ctx.download_level(2, 1, 0), low)
+    ctx.close()

@@ -148,6 +148,60 @@ def test_stereo_rect_sequence_matches_oracle(lib):
     lib.flv_f2f_destroy(h)
 
 
+def test_stereo_unrect_equalize_sequence_matches_oracle(lib):
+    """STEREO_UNRECT (EuRoC raw): LK on the raw images, cv::undistortPoints / cv::projectPoints per point with raw lens
+    models, cv::equalizeHist on ingest -- frame by frame against oracle/f2f_ref.py (which calls cv2 for all three)."""
+    import cv2
+    _setup(lib)
+    K = (384.16455, 384.16455, 320.21445, 238.94403)
+    fpara = [30, 15, 5, 500, 0.01, 15]; vpara = [0.1, 0.01, 0.001, 0.001, 0.5, 0.1]; dpara = [0.9, 50.0, 0.0]
+    n_frames = 6
+    L, R, P0, P1, T10 = f2f_ref.make_stereo_sequence(n_frames, seed=9)
+    # the images are rectified views; treating them as raw with mild lens models keeps the geometry consistent to ~1 px
+    Km = np.array([[K[0], 0, K[2]], [0, K[1], K[3]], [0, 0, 1.0]])
+    K0r = Km + np.array([[1.3, 0, -0.8], [0, 0.9, 0.6], [0, 0, 0]])
+    K1r = Km + np.array([[-0.7, 0, 0.5], [0, 1.1, -0.4], [0, 0, 0]])
+    D0 = np.array([-0.004, 0.0015, 1e-4, -8e-5]); D1 = np.array([-0.0035, 0.001, -6e-5, 5e-5])
+    R0, _ = cv2.Rodrigues(np.array([4e-4, -6e-4, 3e-4])); R1, _ = cv2.Rodrigues(np.array([-3e-4, 5e-4, -2e-4]))
+    cfg = Cfg(2, 640, 480, (C.c_double * 4)(*K), (C.c_double * 4)(*K), 1000.0, (C.c_double * 12)(*P0.ravel()),
+              (C.c_double * 12)(*P1.ravel()), (C.c_double * 7)(*T10.to7()), (C.c_double * 7)(0, 0, 0, 1, 0, 0, 0),
+              (C.c_double * 6)(*fpara), (C.c_double * 6)(*vpara), (C.c_double * 3)(*dpara), 0)
+    h = lib.flv_f2f_create(C.byref(cfg), 0)
+    assert h and lib.flv_f2f_last_error(h) == b""
+    vp = lambda a: np.ascontiguousarray(a, np.float64).ctypes.data_as(C.c_void_p)
+    d14 = lambda D: np.concatenate([D, np.zeros(14 - len(D))])
+    lib.flv_f2f_set_lens.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.flv_f2f_set_equalize_hist.argtypes = [C.c_void_p, C.c_int]
+    for cam, (Kr, D, Rr) in enumerate([(K0r, D0, R0), (K1r, D1, R1)]):
+        assert lib.flv_f2f_set_lens(h, cam, vp([Kr[0, 0], Kr[1, 1], Kr[0, 2], Kr[1, 2]]), vp(d14(D)), vp(Rr.ravel())) == 0
+    assert lib.flv_f2f_set_equalize_hist(h, 1) == 0
+    lib.flv_f2f_set_ransac_hooks(h, fmat_hook, pnp_hook, None)
+    ref = f2f_ref.F2FTracking("stereo_unrect", 640, 480, K, fpara, vpara, dpara, K1=K, P0=P0, P1=P1, T_c1_c0=T10,
+                              lens0=(K0r, D0, R0), lens1=(K1r, D1, R1), equalize=True)
+    cap = 600
+    vq = lambda a: a.ctypes.data_as(C.c_void_p)
+    for k in range(n_frames):
+        kf = C.c_int(0); rs = C.c_int(0)
+        rc = lib.flv_f2f_image_feed(h, 0.05 * k, vq(np.ascontiguousarray(L[k])), vq(np.ascontiguousarray(R[k])), C.byref(kf), C.byref(rs))
+        assert rc == 0, lib.flv_f2f_last_error(h)
+        ref.image_feed(0.05 * k, L[k], R[k])
+        assert {0: "UnInit", 1: "Tracking", 2: "TrackingFail"}[lib.flv_f2f_state(h)] == ref.state
+        T = np.zeros(7); ids = np.zeros(cap, np.int64); p3 = np.zeros((cap, 3)); und = np.zeros((cap, 2)); pl = np.zeros((cap, 2))
+        n = lib.flv_f2f_get_frame(h, vq(T), vq(ids), vq(pl), vq(und), vq(p3), None, None, cap)
+        cur = ref.curr
+        assert n == len(cur.lms) and list(ids[:n]) == [l.lm_id for l in cur.lms]
+        if n:
+            assert np.array_equal(pl[:n], np.array([l.plane for l in cur.lms]))                 # LK positions: bit-exact
+            assert np.abs(und[:n] - np.array([l.undist for l in cur.lms])).max() <= 6.2e-5      # cv2 float rounding
+            ref3 = np.array([l.p3d_w for l in cur.lms])
+            assert np.abs(p3[:n] - ref3).max() <= 1e-5 * max(1.0, np.abs(ref3).max())
+        assert np.abs(T[4:] - cur.T_c_w.to7()[4:]).max() <= 1e-5
+    assert ref.state == "Tracking"
+    und_shift = np.abs(np.array([l.undist for l in ref.curr.lms]) - np.array([l.plane for l in ref.curr.lms])).max()
+    assert und_shift > 0.3          # the lens model really moves points
+    lib.flv_f2f_destroy(h)
+
+
 def test_builtin_ransac_tracks_without_hooks(lib):
     """The product's own host RANSAC stand-ins (no OpenCV): the sequence must track with most points as inliers and
     the recovered camera translation must follow the synthetic motion (12 mm per frame along the plane)."""
