@@ -35,38 +35,29 @@ constexpr int CS_ROWS = 32;   // output rows per strip
 constexpr int CS_COLS = 26;   // output columns per warp (32 lanes - 3 halo lanes each side)
 constexpr int CS_WARPS = 4;
 
-struct Row3 { int l, c, r; };
+struct Row3 { float l, c, r; };      // pixel values are small integers: exact in float, converted once per loaded row
 
-__global__ void __launch_bounds__(CS_WARPS * 32)
-corner_response_kernel(const uint8_t* __restrict__ img_base, size_t stream_stride, int pitch, int w, int h,
-                       int nsx, int nsy, float* __restrict__ eig_out, int* __restrict__ eigmax, double quality,
-                       unsigned long long* __restrict__ cand_base, int* __restrict__ ncand, int cand_cap) {
-  const int lane = threadIdx.x & 31;
-  const int strip = blockIdx.x * CS_WARPS + (threadIdx.x >> 5);
-  if (strip >= nsx * nsy) return;
-  const int s = blockIdx.y;
-  const int sx = strip % nsx, sy = strip / nsx;
-  const uint8_t* img = img_base + (size_t)s * stream_stride;
-  const int x = sx * CS_COLS - 3 + lane;
-  const int y0 = sy * CS_ROWS;
-  const bool in_x = x >= 0 && x < w;
-  const int xl = clampi(reflect101(x, w), 0, w - 1);      // column this lane loads
-  const bool left_from_up = (x - 1 < 0);                  // reflect101(-1) = 1  -> neighbour value sits in lane+1
-  const bool right_from_down = (x + 1 > w - 1);           // reflect101(w) = w-2 -> neighbour value sits in lane-1
+// FAST: the strip and its halo lie strictly inside the image and left of OpenCV's scalar tail (x < w - w%32): no
+// reflection selects, no range predicates, FMA body everywhere.  The generic instantiation handles the border strips.
+template <bool FAST>
+__device__ __forceinline__ void corner_strip(const uint8_t* __restrict__ img, int pitch, int w, int h, int x, int y0, int lane,
+                                             float* __restrict__ eig_s, float pre_thr, unsigned long long* __restrict__ cand,
+                                             int* __restrict__ ncand_s, int cand_cap, float& best) {
+  const bool in_x = FAST || (x >= 0 && x < w);
+  const int xl = FAST ? x : clampi(reflect101(x, w), 0, w - 1);      // column this lane loads
+  const bool left_from_up = !FAST && (x - 1 < 0);                  // reflect101(-1) = 1  -> neighbour value sits in lane+1
+  const bool right_from_down = !FAST && (x + 1 > w - 1);           // reflect101(w) = w-2 -> neighbour value sits in lane-1
   const float k1 = (float)(1.0 / (4 * 3 * 255.0));
   const float k0 = 2.f * k1;
-  const bool body = x < w - (w & 31);
+  const bool body = FAST || (x < w - (w & 31));
   const bool out_lane = lane >= 3 && lane < 3 + CS_COLS && in_x;
-  const float pre_thr = (float)((double)__int_as_float(*(volatile int*)&eigmax[s]) * quality);
-  float* eig_s = eig_out ? eig_out + (size_t)s * w * h : nullptr;
-  unsigned long long* cand = cand_base + (size_t)s * cand_cap;
 
-  auto load_raw = [&](int r) -> int {
-    const int yy = clampi(reflect101(r, h), 0, h - 1);
-    return img[(size_t)yy * pitch + xl];
+  auto load_raw = [&](int r) -> float {
+    const int yy = FAST ? r : clampi(reflect101(r, h), 0, h - 1);
+    return (float)img[(size_t)yy * pitch + xl];
   };
-  auto make_row = [&](int c) -> Row3 {
-    const int up = __shfl_down_sync(FULL, c, 1), dn = __shfl_up_sync(FULL, c, 1);
+  auto make_row = [&](float c) -> Row3 {
+    const float up = __shfl_down_sync(FULL, c, 1), dn = __shfl_up_sync(FULL, c, 1);
     Row3 o;
     o.c = c;
     o.l = left_from_up ? up : dn;
@@ -76,24 +67,23 @@ corner_response_kernel(const uint8_t* __restrict__ img_base, size_t stream_strid
 
   // software prefetch: the row consumed at step r was requested 4 steps earlier (ncu: 52 % long-scoreboard without it)
   Row3 Ia, Ib = make_row(load_raw(y0 - 3)), Ic = make_row(load_raw(y0 - 2));
-  int pf0 = load_raw(y0 - 1), pf1 = load_raw(y0), pf2 = load_raw(y0 + 1), pf3 = load_raw(y0 + 2);
+  float pf0 = load_raw(y0 - 1), pf1 = load_raw(y0), pf2 = load_raw(y0 + 1), pf3 = load_raw(y0 + 2);
   double Rm[3] = {0, 0, 0}, R0[3] = {0, 0, 0}, Rp[3] = {0, 0, 0};
-  float Ea = 0.f, Eb = 0.f, m3a = 0.f, m3b = 0.f, nb = 0.f;   // eig rows y-2 (a), y-1 (b); nb = max(left,right) of row b
-  float best = 0.f;
+  float Eb = 0.f, m3a = 0.f, m3b = 0.f, nb = 0.f;   // eig row y-1 (b); nb = max(left,right) of row b
   for (int r = y0 - 2; r <= y0 + CS_ROWS + 1; ++r) {
     Ia = Ib; Ib = Ic; Ic = make_row(pf0);
-    pf0 = pf1; pf1 = pf2; pf2 = pf3; pf3 = load_raw(r + 5);
+    pf0 = pf1; pf1 = pf2; pf2 = pf3; pf3 = load_raw(r + 5 < h || !FAST ? r + 5 : h - 1);
     // covariance of row r at this lane's column (only inside the image)
     float vxx = 0.f, vxy = 0.f, vyy = 0.f;
-    if (r >= 0 && r < h && in_x) {
-      const float dx = __fmaf_rn(k1, (float)((Ia.r - Ia.l) + (Ic.r - Ic.l)), __fmul_rn(k0, (float)(Ib.r - Ib.l)));
+    if (FAST || (r >= 0 && r < h && in_x)) {
+      const float dx = __fmaf_rn(k1, __fadd_rn(__fsub_rn(Ia.r, Ia.l), __fsub_rn(Ic.r, Ic.l)), __fmul_rn(k0, __fsub_rn(Ib.r, Ib.l)));
       float sa, sc;
       if (body) {
-        sa = __fmaf_rn(k1, (float)Ia.r, __fmaf_rn(k0, (float)Ia.c, __fmul_rn(k1, (float)Ia.l)));
-        sc = __fmaf_rn(k1, (float)Ic.r, __fmaf_rn(k0, (float)Ic.c, __fmul_rn(k1, (float)Ic.l)));
+        sa = __fmaf_rn(k1, Ia.r, __fmaf_rn(k0, Ia.c, __fmul_rn(k1, Ia.l)));
+        sc = __fmaf_rn(k1, Ic.r, __fmaf_rn(k0, Ic.c, __fmul_rn(k1, Ic.l)));
       } else {
-        sa = __fadd_rn(__fadd_rn(__fmul_rn(k1, (float)Ia.l), __fmul_rn(k0, (float)Ia.c)), __fmul_rn(k1, (float)Ia.r));
-        sc = __fadd_rn(__fadd_rn(__fmul_rn(k1, (float)Ic.l), __fmul_rn(k0, (float)Ic.c)), __fmul_rn(k1, (float)Ic.r));
+        sa = __fadd_rn(__fadd_rn(__fmul_rn(k1, Ia.l), __fmul_rn(k0, Ia.c)), __fmul_rn(k1, Ia.r));
+        sc = __fadd_rn(__fadd_rn(__fmul_rn(k1, Ic.l), __fmul_rn(k0, Ic.c)), __fmul_rn(k1, Ic.r));
       }
       const float dy = __fsub_rn(sc, sa);
       vxx = __fmul_rn(dx, dx); vxy = __fmul_rn(dx, dy); vyy = __fmul_rn(dy, dy);
@@ -113,8 +103,8 @@ corner_response_kernel(const uint8_t* __restrict__ img_base, size_t stream_strid
     // eigenvalue of row y = r-1 (rows y-1, y, y+1 of R are Rm, R0, Rp; row reflection at the image border)
     const int y = r - 1;
     float e = 0.f;
-    if (y >= 0 && y < h) {
-      const bool top = (y == 0), bot = (y == h - 1);
+    if (FAST || (y >= 0 && y < h)) {
+      const bool top = !FAST && (y == 0), bot = !FAST && (y == h - 1);
       double sxx = R0[0] + (top ? Rp[0] : Rm[0]) + (bot ? Rm[0] : Rp[0]);
       double sxy = R0[1] + (top ? Rp[1] : Rm[1]) + (bot ? Rm[1] : Rp[1]);
       double syy = R0[2] + (top ? Rp[2] : Rm[2]) + (bot ? Rm[2] : Rp[2]);
@@ -131,12 +121,12 @@ corner_response_kernel(const uint8_t* __restrict__ img_base, size_t stream_strid
     const float m3c = fmaxf(nc, e);
     // non-max test of row yy = y-1 (its neighbours are rows a, c and its own left/right)
     const int yy = y - 1;
-    const bool is = out_lane && yy >= y0 && yy < y0 + CS_ROWS && yy >= 1 && yy < h - 1 && x >= 1 && x < w - 1 &&
+    const bool is = out_lane && yy >= y0 && yy < y0 + CS_ROWS && (FAST || (yy >= 1 && yy < h - 1 && x >= 1 && x < w - 1)) &&
                     Eb > pre_thr && Eb > 0.f && Eb >= m3a && Eb >= m3c && Eb >= nb;
     const unsigned mask = __ballot_sync(FULL, is);
     if (mask) {
       int base = 0;
-      if (lane == 0) base = atomicAdd(&ncand[s], __popc(mask));
+      if (lane == 0) base = atomicAdd(ncand_s, __popc(mask));
       base = __shfl_sync(FULL, base, 0);
       if (is) {
         const int pos = base + __popc(mask & ((1u << lane) - 1));
@@ -144,9 +134,31 @@ corner_response_kernel(const uint8_t* __restrict__ img_base, size_t stream_strid
           cand[pos] = ((unsigned long long)__float_as_uint(Eb) << 32) | ((unsigned)yy << 16) | (unsigned)x;
       }
     }
-    Ea = Eb; m3a = m3b; Eb = e; m3b = m3c; nb = nc;
-    (void)Ea;
+    m3a = m3b; Eb = e; m3b = m3c; nb = nc;
   }
+}
+
+__global__ void __launch_bounds__(CS_WARPS * 32)
+corner_response_kernel(const uint8_t* __restrict__ img_base, size_t stream_stride, int pitch, int w, int h,
+                       int nsx, int nsy, float* __restrict__ eig_out, int* __restrict__ eigmax, double quality,
+                       unsigned long long* __restrict__ cand_base, int* __restrict__ ncand, int cand_cap) {
+  const int lane = threadIdx.x & 31;
+  const int strip = blockIdx.x * CS_WARPS + (threadIdx.x >> 5);
+  if (strip >= nsx * nsy) return;
+  const int s = blockIdx.y;
+  const int sx = strip % nsx, sy = strip / nsx;
+  const uint8_t* img = img_base + (size_t)s * stream_stride;
+  const int x = sx * CS_COLS - 3 + lane;
+  const int y0 = sy * CS_ROWS;
+  const float pre_thr = (float)((double)__int_as_float(*(volatile int*)&eigmax[s]) * quality);
+  float* eig_s = eig_out ? eig_out + (size_t)s * w * h : nullptr;
+  unsigned long long* cand = cand_base + (size_t)s * cand_cap;
+  const int x_lo = sx * CS_COLS - 3, x_hi = x_lo + 31;
+  // rows touched: y0-3 .. y0+CS_ROWS+6 (incl. prefetch); all lanes' columns and their neighbours inside, FMA body
+  const bool fast = x_lo >= 1 && x_hi <= w - 2 && x_hi < w - (w & 31) && y0 - 3 >= 1 && y0 + CS_ROWS + 2 <= h - 2;
+  float best = 0.f;
+  if (fast) corner_strip<true>(img, pitch, w, h, x, y0, lane, eig_s, pre_thr, cand, &ncand[s], cand_cap, best);
+  else corner_strip<false>(img, pitch, w, h, x, y0, lane, eig_s, pre_thr, cand, &ncand[s], cand_cap, best);
   int bi = __float_as_int(best);
   bi = __reduce_max_sync(FULL, bi);
   if (lane == 0 && bi > 0) atomicMax(&eigmax[s], bi);
