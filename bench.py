@@ -158,7 +158,7 @@ def run_ours(args):
 
     host_ms = {}
 
-    def timed(mode, steps, warmup):
+    def timed(mode, steps, warmup, bench=bench):
         bench.reset()
         for i in range(warmup):
             bench.step(i, mode)
@@ -188,6 +188,17 @@ def run_ours(args):
     ms_e2e, _, _, _ = timed("host", args.steps, args.warmup)
     if sampler:
         sampler.stop_flag.set(); sampler.join(timeout=2)
+    # BASELINE configs[1]: ONE stream on the GPU (latency-oriented), reported next to the batched headline
+    single = None
+    if world == 1 and S > 1:
+        b1 = FrontendBench(1, W, H, MAX_PTS, NPTS, FEATURE_PARA, local_rank, ba_window=BA_WINDOW, kf_every=KF_EVERY, seed=rank)
+        b1.load_pool(f0[:, :1].copy(), f1[:, :1].copy())
+        k1 = max(args.steps, 50)
+        ms1, _, _, _ = timed("device", k1, args.warmup, bench=b1)
+        ms1h, _, _, _ = timed("host", k1, args.warmup, bench=b1)
+        single = {"workload": "1 EuRoC-shaped 752x480 stereo stream, LK frontend + 10-KF local BA (BASELINE configs[1])",
+                  "steps": k1, "value": k1 / (ms1 * 1e-3), "e2e": k1 / (ms1h * 1e-3), "unit": "frames/s",
+                  "ms_per_frame": ms1 / k1}
 
     frames = args.steps * S * world
     peak, peak_src = load_peaks()
@@ -197,6 +208,8 @@ def run_ours(args):
         achieved = LK_BYTES_PER_CALL * S / (lk_us * 1e-6) / 1e9 if lk_us > 0 else 0.0
         # bounded sample of the same workload on every host core: all S streams, 6 frames each
         cpu = cpu_baseline(min(S, os.cpu_count() or 1), 6, args) if world == 1 and not args.no_cpu else None
+        if single is not None and not args.no_cpu:
+            single["cpu_value"] = cpu_baseline(1, 10, args)["value"]      # same single stream on the host (cv2 uses all cores)
         out = {
             "metric": "frames/sec (device-timed), EuRoC-shaped 752x480 stereo, LK frontend + 10-KF local BA",
             "value": frames / (ms_dev * 1e-3), "unit": "frames/s", "n_gpus": world, "steps": args.steps,
@@ -218,6 +231,7 @@ def run_ours(args):
                     "h2d_bytes_per_step": bench.h2d_bytes_per_step, "d2h_bytes_per_step": bench.d2h_bytes_per_step,
                     "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": launches,
+            "single_stream": single,
             "roofline": {"kernel": "lk_track_kernel_v4 (frame->frame + left->right)", "bound": "hbm",
                          "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": LK_NCU_TRAFFIC * S / 32, "peak_source": peak_src,

@@ -18,13 +18,17 @@ SYMBOLS = [
     "flv_launch_count", "flv_level_info", "flv_num_levels", "flv_upload_images", "flv_build_pyramid",
     "flv_download_level", "flv_lk_track", "flv_select_tracked", "flv_gftt", "flv_download_eig", "flv_gftt_capacity",
     "flv_feature_detect", "flv_feature_redetect", "flv_ba_reserve", "flv_ba_optimize", "flv_gftt_keep_response",
-    "flv_ba_profile", "flv_set_ba_stream", "flv_feature_prepare", "flv_set_equalize_hist", "flv_depth_innovation", "flv_reprojection_inliers",
+    "flv_ba_profile", "flv_set_ba_stream", "flv_feature_prepare", "flv_set_equalize_hist", "flv_fundamental_ransac", "flv_pnp_ransac", "flv_depth_innovation", "flv_reprojection_inliers",
 ]
 
 
 class LKParams(C.Structure):
     _fields_ = [("win", C.c_int), ("max_level", C.c_int), ("max_iter", C.c_int), ("eps", C.c_double),
                 ("min_eig_threshold", C.c_double)]
+
+
+class RansacParams(C.Structure):
+    _fields_ = [("threshold_px", C.c_double), ("confidence", C.c_double), ("max_iterations", C.c_int)]
 
 
 class FeatureParams(C.Structure):
@@ -92,6 +96,8 @@ def load_library(path=LIB_PATH):
     lib.flv_gftt.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double, vp, vp, C.c_int, C.c_int]
     lib.flv_download_eig.argtypes = [vp, C.c_int, vp, C.c_int]
     lib.flv_set_equalize_hist.argtypes = [vp, C.c_int]
+    lib.flv_fundamental_ransac.argtypes = [vp, C.c_int, vp, vp, vp, C.POINTER(RansacParams), vp, vp, vp, C.c_int]
+    lib.flv_pnp_ransac.argtypes = [vp, C.c_int, vp, vp, vp, vp, vp, C.POINTER(RansacParams), vp, vp, vp, C.c_int]
     lib.flv_feature_prepare.argtypes = [vp, C.c_int, C.c_int, C.POINTER(FeatureParams), C.c_int]
     lib.flv_feature_detect.argtypes = [vp, C.c_int, C.c_int, C.POINTER(FeatureParams), vp, vp, C.c_int]
     lib.flv_feature_redetect.argtypes = [vp, C.c_int, C.c_int, C.POINTER(FeatureParams), vp, vp, vp, vp, C.c_int]
@@ -287,6 +293,25 @@ class Context:
         self._chk(self.lib.flv_feature_redetect(self.h, slot, n_streams, C.byref(fp), _ptr(ex), _ptr(ne), _ptr(xy),
                                                 _ptr(n), MEM_HOST))
         return [xy[s, :n[s]].copy() for s in range(n_streams)]
+
+    def fundamental_ransac(self, from_xy, to_xy, n_pts, thr=5.0):
+        """from_xy/to_xy: (S,max_pts,2) f32 host arrays. Returns (mask (S,max_pts) u8, F (S,3,3), n_inliers (S,))."""
+        S = from_xy.shape[0]
+        a = np.ascontiguousarray(from_xy, np.float32); b = np.ascontiguousarray(to_xy, np.float32)
+        n = np.ascontiguousarray(n_pts, np.int32)
+        mask = np.zeros((S, self.max_pts), np.uint8); F = np.zeros((S, 9)); ni = np.zeros(S, np.int32)
+        prm = RansacParams(thr, 0.99, 1000)
+        self._chk(self.lib.flv_fundamental_ransac(self.h, S, _ptr(n), _ptr(a), _ptr(b), C.byref(prm), _ptr(mask), _ptr(F), _ptr(ni), MEM_HOST))
+        return mask, F.reshape(S, 3, 3), ni
+
+    def pnp_ransac(self, p3d, p2d, n_pts, K4, T_in, thr=3.0):
+        S = p3d.shape[0]
+        x = np.ascontiguousarray(p3d, np.float32); u = np.ascontiguousarray(p2d, np.float32)
+        n = np.ascontiguousarray(n_pts, np.int32); K = np.ascontiguousarray(K4, np.float64); Ti = np.ascontiguousarray(T_in, np.float64)
+        mask = np.zeros((S, self.max_pts), np.uint8); To = np.zeros((S, 7)); ni = np.zeros(S, np.int32)
+        prm = RansacParams(thr, 0.99, 100)
+        self._chk(self.lib.flv_pnp_ransac(self.h, S, _ptr(n), _ptr(x), _ptr(u), _ptr(K), _ptr(Ti), C.byref(prm), _ptr(To), _ptr(mask), _ptr(ni), MEM_HOST))
+        return To, mask, ni
 
     def set_equalize_hist(self, enable):
         self._chk(self.lib.flv_set_equalize_hist(self.h, 1 if enable else 0))

@@ -279,6 +279,63 @@ int flv_lk_track(flv_ctx* ctx, int src_slot, int dst_slot, int n_streams, const 
   return FLV_OK;
 }
 
+int flv_fundamental_ransac(flv_ctx* ctx, int n_streams, const int* n_pts, const float* from_xy, const float* to_xy,
+                           const flv_ransac_params* prm, uint8_t* mask, double* F, int* n_inliers, flv_memspace mem) {
+  if (!ctx || !n_pts || !from_xy || !to_xy || !prm || !mask || !F || !n_inliers || n_streams < 1 || n_streams > ctx->S ||
+      !(prm->threshold_px > 0))
+    return FLV_ERR_INVALID;
+  if (mem == FLV_MEM_DEVICE) return flv_launch_fmat_ransac(ctx, n_streams, n_pts, from_xy, to_xy, prm->threshold_px, mask, F, n_inliers);
+  for (int s = 0; s < n_streams; ++s)
+    if (n_pts[s] < 0 || n_pts[s] > ctx->max_pts) return FLV_ERR_INVALID;
+  const size_t np = (size_t)n_streams * ctx->max_pts, S = n_streams;
+  // staging: npts | from | to || F | ninl | mask
+  const size_t o_np = 0, o_from = 256 + ((S * 4 + 255) & ~(size_t)255), o_to = o_from + np * 8, o_F = o_to + np * 8,
+               o_ni = o_F + S * 72, o_mask = o_ni + ((S * 4 + 255) & ~(size_t)255), total = o_mask + np;
+  int rc = flv_stage_reserve(ctx, total);
+  if (rc) return rc;
+  char* hs = (char*)ctx->h_stage; char* ds = (char*)ctx->d_stage;
+  memcpy(hs + o_np, n_pts, S * 4); memcpy(hs + o_from, from_xy, np * 8); memcpy(hs + o_to, to_xy, np * 8);
+  FLV_CUDA(ctx, cudaMemcpyAsync(ds, hs, o_F, cudaMemcpyHostToDevice, ctx->stream));
+  rc = flv_launch_fmat_ransac(ctx, n_streams, (const int*)(ds + o_np), (const float*)(ds + o_from), (const float*)(ds + o_to),
+                              prm->threshold_px, (uint8_t*)(ds + o_mask), (double*)(ds + o_F), (int*)(ds + o_ni));
+  if (rc) return rc;
+  FLV_CUDA(ctx, cudaMemcpyAsync(hs + o_F, ds + o_F, total - o_F, cudaMemcpyDeviceToHost, ctx->stream));
+  FLV_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  memcpy(F, hs + o_F, S * 72); memcpy(n_inliers, hs + o_ni, S * 4); memcpy(mask, hs + o_mask, np);
+  return FLV_OK;
+}
+
+int flv_pnp_ransac(flv_ctx* ctx, int n_streams, const int* n_pts, const float* p3d, const float* p2d, const double* K4,
+                   const double* T_c_w_in, const flv_ransac_params* prm, double* T_c_w_out, uint8_t* mask, int* n_inliers,
+                   flv_memspace mem) {
+  if (!ctx || !n_pts || !p3d || !p2d || !K4 || !T_c_w_in || !prm || !T_c_w_out || !mask || !n_inliers || n_streams < 1 ||
+      n_streams > ctx->S || !(prm->threshold_px > 0))
+    return FLV_ERR_INVALID;
+  if (mem == FLV_MEM_DEVICE)
+    return flv_launch_pnp_ransac(ctx, n_streams, n_pts, p3d, p2d, K4, T_c_w_in, prm->threshold_px, T_c_w_out, mask, n_inliers);
+  for (int s = 0; s < n_streams; ++s)
+    if (n_pts[s] < 0 || n_pts[s] > ctx->max_pts) return FLV_ERR_INVALID;
+  const size_t np = (size_t)n_streams * ctx->max_pts, S = n_streams;
+  // staging: npts | K | Tin | p3d | p2d || Tout | ninl | mask
+  const size_t o_np = 0, o_K = 256 + ((S * 4 + 255) & ~(size_t)255), o_Ti = o_K + S * 32, o_p3 = (o_Ti + S * 56 + 255) & ~(size_t)255,
+               o_p2 = o_p3 + np * 12, o_To = (o_p2 + np * 8 + 255) & ~(size_t)255, o_ni = o_To + S * 56,
+               o_mask = (o_ni + S * 4 + 255) & ~(size_t)255, total = o_mask + np;
+  int rc = flv_stage_reserve(ctx, total);
+  if (rc) return rc;
+  char* hs = (char*)ctx->h_stage; char* ds = (char*)ctx->d_stage;
+  memcpy(hs + o_np, n_pts, S * 4); memcpy(hs + o_K, K4, S * 32); memcpy(hs + o_Ti, T_c_w_in, S * 56);
+  memcpy(hs + o_p3, p3d, np * 12); memcpy(hs + o_p2, p2d, np * 8);
+  FLV_CUDA(ctx, cudaMemcpyAsync(ds, hs, o_To, cudaMemcpyHostToDevice, ctx->stream));
+  rc = flv_launch_pnp_ransac(ctx, n_streams, (const int*)(ds + o_np), (const float*)(ds + o_p3), (const float*)(ds + o_p2),
+                             (const double*)(ds + o_K), (const double*)(ds + o_Ti), prm->threshold_px, (double*)(ds + o_To),
+                             (uint8_t*)(ds + o_mask), (int*)(ds + o_ni));
+  if (rc) return rc;
+  FLV_CUDA(ctx, cudaMemcpyAsync(hs + o_To, ds + o_To, total - o_To, cudaMemcpyDeviceToHost, ctx->stream));
+  FLV_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  memcpy(T_c_w_out, hs + o_To, S * 56); memcpy(n_inliers, hs + o_ni, S * 4); memcpy(mask, hs + o_mask, np);
+  return FLV_OK;
+}
+
 int flv_select_tracked(flv_ctx* ctx, int n_streams, const int* n_pts, const float* prev_xy,
                        const float* next_xy, const uint8_t* status, uint8_t* keep, float* out_xy,
                        double* out_xy_f64) {

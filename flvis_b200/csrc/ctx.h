@@ -100,6 +100,10 @@ int flv_stage_reserve(flv_ctx* ctx, size_t bytes);
 
 // kernel launchers (one per .cu)
 int flv_launch_pyramid(flv_ctx* ctx, int slot, int n_streams);
+int flv_launch_fmat_ransac(flv_ctx* ctx, int n_streams, const int* d_npts, const float* d_from, const float* d_to, double thr_px,
+                           uint8_t* d_mask, double* d_F, int* d_ninl);
+int flv_launch_pnp_ransac(flv_ctx* ctx, int n_streams, const int* d_npts, const float* d_p3d, const float* d_p2d, const double* d_K4,
+                          const double* d_Tin, double thr_px, double* d_Tout, uint8_t* d_mask, int* d_ninl);
 int flv_launch_equalize(flv_ctx* ctx, int n_streams, const uint8_t* d_src, size_t row_stride, size_t img_stride, uint8_t* d_dst_tight);
 int flv_launch_unpack(flv_ctx* ctx, int slot, int n_streams, const uint8_t* d_src, size_t row_stride, size_t img_stride);
 int flv_launch_lk(flv_ctx* ctx, int src_slot, int dst_slot, int n_streams, const int* d_npts,

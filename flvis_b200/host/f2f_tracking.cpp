@@ -300,9 +300,18 @@ bool F2FTracking::tracking(CameraFrame& from, CameraFrame& to, const SE3& T_c_w_
   std::vector<uint8_t> maskF(m, 0);
   if (fmat_fn_) {
     if (fmat_fn_(hook_user_, m, &from_und[0].x, &tracked_und[0].x, maskF.data())) return false;
-  } else {
+  } else if (host_ransac_) {
     double F[9];
     find_fundamental_ransac(from_und, tracked_und, 5.0, 0.99, maskF, F);
+  } else {                                                       // K11 on the device (flv_fundamental_ransac)
+    std::vector<float> a(2 * MAX_PTS, 0.f), b(2 * MAX_PTS, 0.f);
+    std::vector<uint8_t> mk(MAX_PTS, 0);
+    int nn = std::min(m, MAX_PTS), ni = 0;
+    memcpy(a.data(), from_und.data(), (size_t)nn * 8); memcpy(b.data(), tracked_und.data(), (size_t)nn * 8);
+    double F[9];
+    const flv_ransac_params rp{5.0, 0.99, 1000};
+    if (flv_fundamental_ransac(ctx_, 1, &nn, a.data(), b.data(), &rp, mk.data(), F, &ni, FLV_MEM_HOST)) return false;
+    for (int i = 0; i < nn; ++i) maskF[i] = mk[i];
   }
   for (int i = 0; i < m; i++)
     if (maskF[i] == 0) to.landmarks[i].is_tracking_inlier = false;
@@ -325,8 +334,18 @@ bool F2FTracking::tracking(CameraFrame& from, CameraFrame& to, const SE3& T_c_w_
     int ninl = 0;
     if (p2d.empty() || pnp_fn_(hook_user_, (int)p2d.size(), &p3d[0].x, &p2d[0].x, K, use_guess ? 1 : 0, T.data(), inl.data(), &ninl)) return false;
     inl.resize(ninl);
-  } else {
+  } else if (host_ransac_) {
     solve_pnp_ransac(p3d, p2d, K, T, 100, 3.0, 0.99, inl);
+  } else {                                                       // K11 on the device (flv_pnp_ransac), prior = guess / last pose
+    std::vector<float> x3(3 * MAX_PTS, 0.f), x2(2 * MAX_PTS, 0.f);
+    std::vector<uint8_t> mk(MAX_PTS, 0);
+    int nn = std::min((int)p2d.size(), MAX_PTS), ni = 0;
+    if (nn > 0) { memcpy(x3.data(), p3d.data(), (size_t)nn * 12); memcpy(x2.data(), p2d.data(), (size_t)nn * 8); }
+    Pose7 Tout = T;
+    const flv_ransac_params rp{3.0, 0.99, 100};
+    if (flv_pnp_ransac(ctx_, 1, &nn, x3.data(), x2.data(), K, T.data(), &rp, Tout.data(), mk.data(), &ni, FLV_MEM_HOST)) return false;
+    T = Tout;
+    for (int i = 0; i < nn; ++i) if (mk[i]) inl.push_back(i);
   }
   std::vector<uint8_t> mask_pnp(p2d.size(), 0);
   for (int k : inl) mask_pnp[k] = 1;

@@ -7,7 +7,8 @@
 //   FeatureDEM                   src/processing/include/feature_dem.h:35-50
 //   F2FTracking                  src/frontend/include/f2f_tracking.h:24-78, f2f_tracking.cpp:5-453
 // cv::Mat arguments become raw image pointers; every OpenCV / g2o call goes to the GPU through the C ABI
-// (include/flvis_b200.h) except the two RANSAC calls, which are host stand-ins (ransac.h) or caller callbacks.
+// (include/flvis_b200.h), including the two RANSAC calls (K11: flv_fundamental_ransac / flv_pnp_ransac; caller callbacks
+// or the host stand-ins of ransac.h can be selected instead).
 // Sensor types: DEPTH_D435, STEREO_RECT, STEREO_UNRECT (EuRoC raw: LK runs on the distorted images, points go through
 // cv::undistortPoints / cv::projectPoints restated in undistort.h); need_equal_hist = cv::equalizeHist on ingest (GPU).
 #pragma once
@@ -95,6 +96,7 @@ class F2FTracking {
     for (int i = 0; i < 9; ++i) m.R[i] = R9[i];
     return 0;
   }
+  void set_host_ransac(bool on) { host_ransac_ = on; }
   int set_equalize_hist(bool enable) { need_equal_hist = enable; return flv_set_equalize_hist(ctx_, enable ? 1 : 0); }
 
   std::shared_ptr<CameraFrame> curr_frame, last_frame;
@@ -120,6 +122,7 @@ class F2FTracking {
   std::deque<ID_POSE> pose_records;
   int continus_tracking_fail_cnt = 0, fail_cnt = 0;
   flv_fmat_fn fmat_fn_ = nullptr; flv_pnp_fn pnp_fn_ = nullptr; void* hook_user_ = nullptr;
+  bool host_ransac_ = false;                       // true: the host stand-ins of ransac.h instead of the device K11 kernels
   char err_[256] = {0};
   int slot_toggle = 0;
 

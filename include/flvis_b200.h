@@ -213,6 +213,22 @@ int flv_reprojection_inliers(flv_ctx* ctx, int n_streams, const int* n_lms, cons
                              const double* lm_2d_undist, const double* lm_3d_w, double sh_over_med,
                              uint8_t* is_inlier, double* mean_prjerr, flv_memspace mem);
 
+/* ---- geometric verification (K11) -------------------------------------------------------------------
+ * Batched RANSAC replacing cv::findFundamentalMat(from, to, FM_RANSAC, 5.0, 0.99) (src/processing/lkorb_tracking.cpp:134)
+ * and cv::solvePnPRansac(p3d, p2d, K, D=0, rvec, tvec, guess, 100, 3.0, 0.99) (:170-177) for all streams in one launch.
+ * Same models, thresholds and error measures as OpenCV; OpenCV's private RNG stream / LAPACK solvers are not
+ * reproducible, so the inlier sets agree with cv2 statistically, not bit for bit (tests/test_ransac_gpu.py).  A fixed
+ * budget of hypotheses (256 / 128) is evaluated in parallel: `confidence` and `max_iterations` are accepted for
+ * signature compatibility only.  Arrays are [s][max_pts][..]; mask[s][i] = 1 for inliers; F[s][9] row-major maps
+ * `from` to epipolar lines in `to` (x_to^T F x_from = 0); poses are [qx qy qz qw tx ty tz]; T_c_w_in is the pose prior
+ * (IMU prediction or the previous frame's pose), K4 = fx fy cx cy per stream. */
+typedef struct { double threshold_px; double confidence; int max_iterations; } flv_ransac_params;
+int flv_fundamental_ransac(flv_ctx* ctx, int n_streams, const int* n_pts, const float* from_xy, const float* to_xy,
+                           const flv_ransac_params* prm, uint8_t* mask, double* F, int* n_inliers, flv_memspace mem);
+int flv_pnp_ransac(flv_ctx* ctx, int n_streams, const int* n_pts, const float* p3d, const float* p2d, const double* K4,
+                   const double* T_c_w_in, const flv_ransac_params* prm, double* T_c_w_out, uint8_t* mask, int* n_inliers,
+                   flv_memspace mem);
+
 /* Run subsequent flv_ba_optimize calls on `cuda_stream` instead of the context stream (enable=1), the analogue of
  * FLVIS's separate local-map thread: the BA of keyframe k overlaps the tracking of the following frames.
  * enable=0 reverts to the context stream.  The caller orders the streams (events) as it needs. */

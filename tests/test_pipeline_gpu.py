@@ -62,6 +62,15 @@ def _setup(lib):
     lib.flv_f2f_tracking_counts.argtypes = [C.c_void_p] + [C.POINTER(C.c_int)] * 3
 
 
+def _cam_centre(T7):
+    """camera centre in the world frame of a T_c_w pose [qx qy qz qw tx ty tz]: -R^T t."""
+    x, y, z, w = T7[:4]
+    R = np.array([[1 - 2 * (y * y + z * z), 2 * (x * y - z * w), 2 * (x * z + y * w)],
+                  [2 * (x * y + z * w), 1 - 2 * (x * x + z * z), 2 * (y * z - x * w)],
+                  [2 * (x * z - y * w), 2 * (y * z + x * w), 1 - 2 * (x * x + y * y)]])
+    return -R.T @ np.asarray(T7[4:], float)
+
+
 def test_depth_sequence_matches_oracle_frame_by_frame(lib):
     _setup(lib)
     K = (384.16455, 384.16455, 320.21445, 238.94403)
@@ -78,6 +87,7 @@ def test_depth_sequence_matches_oracle_frame_by_frame(lib):
     cap = 600
     vp = lambda a: a.ctypes.data_as(C.c_void_p)
     n_kf = 0
+    traj, traj_ref = [], []
     for k in range(n_frames):
         kf = C.c_int(0); rs = C.c_int(0)
         img = np.ascontiguousarray(imgs[k]); dep = np.ascontiguousarray(depths[k])
@@ -100,6 +110,7 @@ def test_depth_sequence_matches_oracle_frame_by_frame(lib):
         rT = cur.T_c_w.to7()
         assert np.abs(T[4:] - rT[4:]).max() <= 1e-6                               # per-frame pose: 1e-6 m
         assert 2 * np.arccos(min(1.0, abs(float(np.dot(T[:4], rT[:4]))))) <= 1e-6
+        traj.append(_cam_centre(T)); traj_ref.append(_cam_centre(rT))
         if k > 0 and ref.state == "Tracking":
             of = C.c_int(); fi = C.c_int(); pn = C.c_int()
             lib.flv_f2f_tracking_counts(h, C.byref(of), C.byref(fi), C.byref(pn))
@@ -107,6 +118,11 @@ def test_depth_sequence_matches_oracle_frame_by_frame(lib):
             assert pn.value >= 30                                                 # the synthetic plane is trackable
         n_kf += int(rkf)
     assert ref.state == "Tracking" and n_kf >= 2
+    # absolute trajectory error against the reference path (BASELINE: ATE within 1 % of the reference's)
+    traj, traj_ref = np.array(traj), np.array(traj_ref)
+    ate = float(np.sqrt(np.mean(np.sum((traj - traj_ref) ** 2, axis=1))))
+    path = float(np.sum(np.linalg.norm(np.diff(traj_ref, axis=0), axis=1)))
+    assert path > 0.05 and ate <= 1e-6 and ate <= 0.01 * path
     lib.flv_f2f_destroy(h)
 
 

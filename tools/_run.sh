@@ -1,8 +1,2 @@
-timeout 900 python -m pytest tests -m gpu -q 2>&1 | tail -4
-timeout 300 python bench.py --steps 20 --warmup 3 > gpurun_out/bench_v13.json 2> gpurun_out/bench_v13.err
-python -c "
-import json
-d=json.load(open('gpurun_out/bench_v13.json'))
-print('value',round(d['value']),'ms/step',round(d['ms_per_step'],3),'e2e',round(d['e2e']['value']),'cpu',round(d['cpu_baseline']['value']),'lk us',round(d['roofline']['us_per_launch']), d['clocks'])
-"
-tail -2 gpurun_out/bench_v13.err
+timeout 900 python -m pytest tests/test_ransac_gpu.py tests/test_pipeline_gpu.py tests/test_fullsize_gpu.py -m gpu -q 2>&1 | grep -v "^  \|Warning\|^$" | tail -40 > gpurun_out/ransac_test.txt
+tail -3 gpurun_out/ransac_test.txt
