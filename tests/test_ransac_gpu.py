@@ -57,7 +57,8 @@ def test_fundamental_ransac_vs_cv2():
         mc = mc.ravel()
         good = ~truth[s]
         assert m[good].mean() > 0.96                       # ground-truth inliers kept (cv2: 0.99 .. 1.0 on these scenes)
-        assert m[truth[s]].mean() < 0.25                   # gross outliers rejected (some land near their epipolar line)
+        # gross outliers rejected (some land within 5 px of their epipolar line; cv2 keeps 4 .. 13 % of them here)
+        assert m[truth[s]].mean() <= max(0.2, mc[truth[s]].mean() + 0.15)
         assert _iou(m, mc) > 0.93, (s, _iou(m, mc))
         # the refit model explains the clean correspondences: symmetric epipolar distance of ground-truth inliers
         x1 = np.c_[A[s, :n], np.ones(n)]; x2 = np.c_[B[s, :n], np.ones(n)]
