@@ -218,6 +218,75 @@ def test_stereo_unrect_equalize_sequence_matches_oracle(lib):
     lib.flv_f2f_destroy(h)
 
 
+def test_system_tracker_keyframes_feed_local_map(lib):
+    """Both hot paths chained as in FLVIS: the tracker's keyframes (KeyFrame message = ids / undistorted 2-d / world 3-d
+    of the inlier landmarks with depth + T_c_w, keyframe_msg.cpp:30-110) drive the sliding-window local map; every
+    CorrectionInf is compared with the chained oracles (f2f_ref -> localmap_ref)."""
+    from flvis_b200 import capi
+    from oracle import localmap_ref
+    _setup(lib)
+    K = (384.16455, 384.16455, 320.21445, 238.94403)
+    fpara = [30, 15, 5, 500, 0.01, 15]; vpara = [0.1, 0.01, 0.001, 0.001, 0.5, 0.1]; dpara = [0.9, 50.0, 0.0]
+    n_frames, window = 26, 5
+    imgs, depths = f2f_ref.make_depth_sequence(n_frames, seed=21)
+    cfg = Cfg(0, 640, 480, (C.c_double * 4)(*K), (C.c_double * 4)(*K), 1000.0, (C.c_double * 12)(), (C.c_double * 12)(),
+              (C.c_double * 7)(0, 0, 0, 1, 0, 0, 0), (C.c_double * 7)(0, 0, 0, 1, 0, 0, 0),
+              (C.c_double * 6)(*fpara), (C.c_double * 6)(*vpara), (C.c_double * 3)(*dpara), 0)
+    h = lib.flv_f2f_create(C.byref(cfg), 0)
+    assert h and lib.flv_f2f_last_error(h) == b""
+    lib.flv_f2f_set_ransac_hooks(h, fmat_hook, pnp_hook, None)
+    ref = f2f_ref.F2FTracking("depth", 640, 480, K, fpara, vpara, dpara)
+    ctx = capi.Context(1, 640, 480)
+    clib = ctx.lib
+    clib.flv_localmap_create.restype = C.c_void_p
+    clib.flv_localmap_create.argtypes = [C.c_void_p, C.c_int] + [C.c_double] * 4
+    clib.flv_localmap_destroy.argtypes = [C.c_void_p]
+    clib.flv_localmap_add_keyframe.argtypes = [C.c_void_p, C.c_int64, C.c_int] + [C.c_void_p] * 4 + [C.c_void_p] * 5 + \
+        [C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.POINTER(capi.BAStats)]
+    lm = clib.flv_localmap_create(ctx.h, window, *K)
+    lm_ref = localmap_ref.LocalMap(window, K)
+    cap = 600
+    vp = lambda a: a.ctypes.data_as(C.c_void_p)
+    n_solved = 0
+    for k in range(n_frames):
+        kf = C.c_int(0); rs = C.c_int(0)
+        assert lib.flv_f2f_image_feed(h, 0.05 * k, vp(np.ascontiguousarray(imgs[k])), vp(np.ascontiguousarray(depths[k])),
+                                      C.byref(kf), C.byref(rs)) == 0
+        rkf, _ = ref.image_feed(0.05 * k, imgs[k], depths[k])
+        assert bool(kf.value) == rkf
+        if not rkf:
+            continue
+        T = np.zeros(7); ids = np.zeros(cap, np.int64); und = np.zeros((cap, 2)); p3 = np.zeros((cap, 3))
+        has = np.zeros(cap, np.uint8); inl = np.zeros(cap, np.uint8)
+        n = lib.flv_f2f_get_frame(h, vp(T), vp(ids), None, vp(und), vp(p3), vp(has), vp(inl), cap)
+        sel = (has[:n] == 1) & (inl[:n] == 1)                                   # CameraFrame::getKeyFrameInf
+        kids = np.ascontiguousarray(ids[:n][sel]); kuv = np.ascontiguousarray(und[:n][sel]); k3 = np.ascontiguousarray(p3[:n][sel])
+        rsel = [l for l in ref.curr.lms if l.has_3d and l.inlier]
+        okf = {"frame_id": ref.curr.frame_id, "lm_id": [l.lm_id for l in rsel], "lm_2d": np.array([l.undist for l in rsel]),
+               "lm_3d": np.array([l.p3d_w for l in rsel]), "T_c_w": ref.curr.T_c_w.to7()}
+        assert list(kids) == okf["lm_id"]
+        o = lm_ref.frame_callback(okf)
+        fid = np.zeros(1, np.int64); oT = np.zeros(7); nlm = np.zeros(1, np.int32); olm = np.zeros(8192, np.int64)
+        o3 = np.zeros((8192, 3)); nout = np.zeros(1, np.int32); oout = np.zeros(8192, np.int64)
+        st = capi.BAStats()
+        rc = clib.flv_localmap_add_keyframe(lm, int(ref.curr.frame_id), len(kids), vp(kids), vp(kuv), vp(k3), vp(T), vp(fid), vp(oT),
+                                            vp(nlm), vp(olm), vp(o3), 8192, vp(nout), vp(oout), 8192, C.byref(st))
+        if o is None:
+            assert rc == 0
+            continue
+        assert rc == 1, clib.flv_last_error(ctx.h)
+        n_solved += 1
+        assert fid[0] == o["frame_id"] and list(olm[:nlm[0]]) == o["lm_id"]
+        assert sorted(oout[:nout[0]]) == sorted(o["outlier_id"])
+        assert np.abs(oT[4:] - o["T_c_w"][4:]).max() <= 1e-5
+        if nlm[0]:
+            assert np.abs(o3[:nlm[0]] - o["lm_3d"]).max() <= 1e-4
+    assert n_solved >= 2
+    clib.flv_localmap_destroy(lm)
+    ctx.close()
+    lib.flv_f2f_destroy(h)
+
+
 def test_builtin_ransac_tracks_without_hooks(lib):
     """The product's own host RANSAC stand-ins (no OpenCV): the sequence must track with most points as inliers and
     the recovered camera translation must follow the synthetic motion (12 mm per frame along the plane)."""
