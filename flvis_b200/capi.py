@@ -18,7 +18,7 @@ SYMBOLS = [
     "flv_launch_count", "flv_level_info", "flv_num_levels", "flv_upload_images", "flv_build_pyramid",
     "flv_download_level", "flv_lk_track", "flv_select_tracked", "flv_gftt", "flv_download_eig", "flv_gftt_capacity",
     "flv_feature_detect", "flv_feature_redetect", "flv_ba_reserve", "flv_ba_optimize", "flv_gftt_keep_response",
-    "flv_ba_profile", "flv_set_ba_stream", "flv_feature_prepare", "flv_set_equalize_hist", "flv_fundamental_ransac", "flv_pnp_ransac", "flv_depth_innovation", "flv_reprojection_inliers",
+    "flv_ba_profile", "flv_set_ba_stream", "flv_feature_prepare", "flv_set_equalize_hist", "flv_fundamental_ransac", "flv_pnp_ransac", "flv_upload_color_images", "flv_depth_innovation", "flv_reprojection_inliers",
 ]
 
 
@@ -96,6 +96,7 @@ def load_library(path=LIB_PATH):
     lib.flv_gftt.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double, vp, vp, C.c_int, C.c_int]
     lib.flv_download_eig.argtypes = [vp, C.c_int, vp, C.c_int]
     lib.flv_set_equalize_hist.argtypes = [vp, C.c_int]
+    lib.flv_upload_color_images.argtypes = [vp, C.c_int, C.c_int, vp, C.c_size_t, C.c_size_t, C.c_int, C.c_int, C.c_int]
     lib.flv_fundamental_ransac.argtypes = [vp, C.c_int, vp, vp, vp, C.POINTER(RansacParams), vp, vp, vp, C.c_int]
     lib.flv_pnp_ransac.argtypes = [vp, C.c_int, vp, vp, vp, vp, vp, C.POINTER(RansacParams), vp, vp, vp, C.c_int]
     lib.flv_feature_prepare.argtypes = [vp, C.c_int, C.c_int, C.POINTER(FeatureParams), C.c_int]
@@ -312,6 +313,12 @@ class Context:
         prm = RansacParams(thr, 0.99, 100)
         self._chk(self.lib.flv_pnp_ransac(self.h, S, _ptr(n), _ptr(x), _ptr(u), _ptr(K), _ptr(Ti), C.byref(prm), _ptr(To), _ptr(mask), _ptr(ni), MEM_HOST))
         return To, mask, ni
+
+    def upload_color(self, slot, imgs, is_rgb=False):
+        """imgs: (S,h,w,3|4) u8 host array, interleaved BGR(A) (or RGB(A) with is_rgb)."""
+        a = np.ascontiguousarray(imgs, np.uint8)
+        S, h, w, ch = a.shape
+        self._chk(self.lib.flv_upload_color_images(self.h, slot, S, _ptr(a), w * ch, h * w * ch, ch, 1 if is_rgb else 0, MEM_HOST))
 
     def set_equalize_hist(self, enable):
         self._chk(self.lib.flv_set_equalize_hist(self.h, 1 if enable else 0))

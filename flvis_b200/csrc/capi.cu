@@ -113,6 +113,7 @@ void flv_destroy(flv_ctx* ctx) {
   if (ctx->d_stage) cudaFree(ctx->d_stage);
   if (ctx->img_stage_bytes) for (int i = 0; i < flv_ctx::IMG_RING; ++i) cudaFree(ctx->d_img_stage[i]);
   if (ctx->d_hist) cudaFree(ctx->d_hist);
+  if (ctx->d_color_stage) cudaFree(ctx->d_color_stage);
   if (ctx->aux_stream) { cudaEventDestroy(ctx->ev_fork); cudaEventDestroy(ctx->ev_gftt); cudaStreamDestroy(ctx->aux_stream); }
   if (ctx->copy_stream) {
     for (int i = 0; i < flv_ctx::IMG_RING; ++i) { cudaEventDestroy(ctx->img_ready[i]); cudaEventDestroy(ctx->img_free[i]); }
@@ -206,6 +207,47 @@ int flv_upload_images(flv_ctx* ctx, int slot, int n_streams, const uint8_t* imgs
     if (rc0) return rc0;
   }
   const int rc = flv_launch_unpack(ctx, slot, n_streams, st, w, w * h);
+  if (rc) return rc;
+  FLV_CUDA(ctx, cudaEventRecord(ctx->img_free[ring], ctx->stream));
+  return FLV_OK;
+}
+
+int flv_upload_color_images(flv_ctx* ctx, int slot, int n_streams, const uint8_t* imgs, size_t row_stride_bytes,
+                            size_t img_stride_bytes, int channels, int is_rgb, flv_memspace mem) {
+  if (!ctx || !imgs || slot < 0 || slot >= FLV_NUM_SLOTS || n_streams < 1 || n_streams > ctx->S || (channels != 3 && channels != 4) ||
+      row_stride_bytes < (size_t)ctx->w * channels || img_stride_bytes < row_stride_bytes * ctx->h)
+    return FLV_ERR_INVALID;
+  const size_t w = ctx->w, h = ctx->h;
+  const uint8_t* d_src = imgs;
+  if (mem == FLV_MEM_HOST) {                         // one H2D copy of the interleaved frames, converted on the device
+    const size_t bytes = (size_t)n_streams * img_stride_bytes;
+    if (bytes > ctx->color_stage_bytes) {
+      if (ctx->d_color_stage) cudaFree(ctx->d_color_stage);
+      ctx->d_color_stage = nullptr; ctx->color_stage_bytes = 0;
+      FLV_CUDA(ctx, cudaMalloc(&ctx->d_color_stage, bytes));
+      ctx->color_stage_bytes = bytes;
+    }
+    FLV_CUDA(ctx, cudaMemcpyAsync(ctx->d_color_stage, imgs, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    d_src = (const uint8_t*)ctx->d_color_stage;
+  }
+  if (ctx->img_stage_bytes == 0) {
+    for (int i = 0; i < flv_ctx::IMG_RING; ++i) FLV_CUDA(ctx, cudaMalloc(&ctx->d_img_stage[i], (size_t)ctx->S * w * h));
+    ctx->img_stage_bytes = (size_t)ctx->S * w * h;
+  }
+  if (!ctx->copy_stream) {
+    FLV_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+    for (int i = 0; i < flv_ctx::IMG_RING; ++i) {
+      FLV_CUDA(ctx, cudaEventCreateWithFlags(&ctx->img_ready[i], cudaEventDisableTiming));
+      FLV_CUDA(ctx, cudaEventCreateWithFlags(&ctx->img_free[i], cudaEventDisableTiming));
+    }
+  }
+  const int ring = (int)(ctx->img_ring_pos++ % flv_ctx::IMG_RING);
+  uint8_t* st = (uint8_t*)ctx->d_img_stage[ring];
+  FLV_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->img_free[ring], 0));
+  int rc = flv_launch_gray(ctx, n_streams, d_src, row_stride_bytes, img_stride_bytes, channels, is_rgb ? 1 : 0, st);
+  if (rc) return rc;
+  if (ctx->equalize && (rc = flv_launch_equalize(ctx, n_streams, st, w, w * h, st))) return rc;
+  rc = flv_launch_unpack(ctx, slot, n_streams, st, w, w * h);
   if (rc) return rc;
   FLV_CUDA(ctx, cudaEventRecord(ctx->img_free[ring], ctx->stream));
   return FLV_OK;

@@ -33,6 +33,7 @@ struct flv_ctx {
   // GFTT started early on an auxiliary stream by flv_feature_prepare, consumed by the next detect/redetect
   cudaStream_t aux_stream; cudaEvent_t ev_fork, ev_gftt;
   int prep_valid, prep_slot, prep_streams, prep_ncorn, prep_dis; double prep_ql;
+  void* d_color_stage; size_t color_stage_bytes;   // landing area of interleaved colour uploads
   int equalize; int* d_hist;     // cv::equalizeHist on ingest (flv_set_equalize_hist)
   int no_fused_ingest;           // FLV_NO_FUSED_INGEST=1: A/B switch for tests
   char err[512];
@@ -104,6 +105,8 @@ int flv_launch_fmat_ransac(flv_ctx* ctx, int n_streams, const int* d_npts, const
                            uint8_t* d_mask, double* d_F, int* d_ninl);
 int flv_launch_pnp_ransac(flv_ctx* ctx, int n_streams, const int* d_npts, const float* d_p3d, const float* d_p2d, const double* d_K4,
                           const double* d_Tin, double thr_px, double* d_Tout, uint8_t* d_mask, int* d_ninl);
+int flv_launch_gray(flv_ctx* ctx, int n_streams, const uint8_t* d_src, size_t row_stride, size_t img_stride, int channels, int rgb,
+                    uint8_t* d_dst_tight);
 int flv_launch_equalize(flv_ctx* ctx, int n_streams, const uint8_t* d_src, size_t row_stride, size_t img_stride, uint8_t* d_dst_tight);
 int flv_launch_unpack(flv_ctx* ctx, int slot, int n_streams, const uint8_t* d_src, size_t row_stride, size_t img_stride);
 int flv_launch_lk(flv_ctx* ctx, int src_slot, int dst_slot, int n_streams, const int* d_npts,

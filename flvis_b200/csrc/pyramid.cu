@@ -146,82 +146,17 @@ __global__ void __launch_bounds__(FUSED_WARPS * 32) ingest_l1_kernel(const uint8
   }
 }
 
-// Two pyrDown steps in one launch (levels l -> l+1 -> l+2; used for 1 -> 2 -> 3 after the fused ingest built level 1):
-// a CTA owns L23_ROWS rows of the coarsest level over the full width, recomputes the 2*R+3 rows of the middle level it
-// needs in shared memory (writing the 2*R rows it owns), then filters those.  The two small levels used to cost two
-// launches of ~12 us each for 0.9 MB of pixels; this is one launch, latency-bound by design (10 CTAs per image).
-constexpr int L23_ROWS = 6;
-constexpr int L23_MAXW = 512;          // width of the middle level that fits the shared buffers
-
-__global__ void __launch_bounds__(256) pyr_down2_kernel(uint8_t* __restrict__ slot_base, size_t stream_stride, size_t offA,
-                                                        int wA, int hA, int pA, size_t offB, int wB, int hB, int pB,
-                                                        size_t offC, int wC, int hC, int pC) {
-  __shared__ uint16_t hb[4 * L23_ROWS + 9][L23_MAXW];      // horizontal sums of level A rows (middle-level width)
-  __shared__ uint8_t mid[2 * L23_ROWS + 3][L23_MAXW];      // middle-level rows
-  uint8_t* base = slot_base + (size_t)blockIdx.y * stream_stride;
-  const uint8_t* A = base + offA;
-  uint8_t* B = base + offB;
-  uint8_t* Cc = base + offC;
-  const int r0 = blockIdx.x * L23_ROWS;                    // first row of level C owned by this CTA
-  const int b0 = 2 * r0 - 2;                               // first (possibly negative) row of level B needed
-  const int a0 = 2 * b0 - 2;                               // first row of level A needed
-  const int nB = 2 * L23_ROWS + 3, nA = 2 * nB + 3;
-  const int tid = threadIdx.x;
-  // horizontal pass on level A rows a0 .. a0+nA-1 (row index reflected), output width wB
-  for (int i = tid; i < nA * wB; i += 256) {
-    const int r = i / wB, x = i - r * wB;
-    const uint8_t* row = A + (size_t)reflect101(reflect101(a0 + r, hA), hA) * pA;
-    const int c = 2 * x;
-    hb[r][x] = (uint16_t)(row[reflect101(c - 2, wA)] + 4 * row[reflect101(c - 1, wA)] + 6 * row[c] +
-                          4 * row[reflect101(c + 1, wA)] + row[reflect101(c + 2, wA)]);
-  }
-  __syncthreads();
-  // vertical pass -> middle rows b0 .. b0+nB-1 (level-B row index yb may lie outside [0,hB): it is only used reflected)
-  for (int i = tid; i < nB * wB; i += 256) {
-    const int j = i / wB, x = i - j * wB;
-    const int yb = reflect101(reflect101(b0 + j, hB), hB); // the B row this buffer row stands for
-    // rows of A for B row yb are 2*yb-2 .. 2*yb+2 (reflected in A); find them in hb (which holds A rows a0 + r, reflected)
-    int sum = 0;
-    const int wgt[5] = {1, 4, 6, 4, 1};
-#pragma unroll
-    for (int k = 0; k < 5; ++k) {
-      const int ya = reflect101(reflect101(2 * yb - 2 + k, hA), hA);
-      // locate ya among the staged rows: staged row r stands for reflect(a0 + r); search the (at most two) candidates
-      int r = ya - a0;
-      if (r < 0 || r >= nA || reflect101(reflect101(a0 + r, hA), hA) != ya) {
-        r = -1;
-        for (int q = 0; q < nA; ++q) if (reflect101(reflect101(a0 + q, hA), hA) == ya) { r = q; break; }
-      }
-      sum += wgt[k] * hb[r][x];
-    }
-    const uint8_t v = (uint8_t)((sum + 128) >> 8);
-    mid[j][x] = v;
-    const int ybraw = b0 + j;
-    if (ybraw >= 2 * r0 && ybraw < 2 * r0 + 2 * L23_ROWS && ybraw < hB) B[(size_t)ybraw * pB + x] = v;
-  }
-  __syncthreads();
-  // second step: level C rows r0 .. r0+L23_ROWS-1 from the middle rows
-  for (int i = tid; i < L23_ROWS * wC; i += 256) {
-    const int j = i / wC, x = i - j * wC;
-    const int yc = r0 + j;
-    if (yc >= hC) continue;
-    int sum = 0;
-    const int wgt[5] = {1, 4, 6, 4, 1};
-#pragma unroll
-    for (int k = 0; k < 5; ++k) {
-      const int yb = reflect101(reflect101(2 * yc - 2 + k, hB), hB);
-      int r = yb - b0;
-      if (r < 0 || r >= nB || reflect101(reflect101(b0 + r, hB), hB) != yb) {
-        r = -1;
-        for (int q = 0; q < nB; ++q) if (reflect101(reflect101(b0 + q, hB), hB) == yb) { r = q; break; }
-      }
-      const uint8_t* row = mid[r];
-      const int c = 2 * x;
-      sum += wgt[k] * (row[reflect101(c - 2, wB)] + 4 * row[reflect101(c - 1, wB)] + 6 * row[c] + 4 * row[reflect101(c + 1, wB)] +
-                       row[reflect101(c + 2, wB)]);
-    }
-    Cc[(size_t)yc * pC + x] = (uint8_t)((sum + 128) >> 8);
-  }
+// ---- cv::cvtColor(BGR/RGB/BGRA/RGBA -> GRAY) on ingest (src/frontend/f2f_tracking.cpp:78-110) --------------------------------
+// OpenCV 4's 8-bit path (15-bit coefficients, probed against cv2 4.13): gray = (B * 3735 + G * 19235 + R * 9798 + (1 << 14)) >> 15.  One thread per pixel, interleaved
+// source of `ch` (3 | 4) channels -> tight [S][h][w] landing area.
+__global__ void __launch_bounds__(256) gray_kernel(const uint8_t* __restrict__ src, size_t row_stride, size_t img_stride, int ch,
+                                                   int rgb, uint8_t* __restrict__ dst, int w, int h) {
+  const int x = blockIdx.x * 256 + threadIdx.x, y = blockIdx.y;
+  if (x >= w) return;
+  const uint8_t* p = src + (size_t)blockIdx.z * img_stride + (size_t)y * row_stride + (size_t)x * ch;
+  const int c0 = p[0], c1 = p[1], c2 = p[2];
+  const int b = rgb ? c2 : c0, r = rgb ? c0 : c2;
+  dst[(size_t)blockIdx.z * w * h + (size_t)y * w + x] = (uint8_t)((b * 3735 + c1 * 19235 + r * 9798 + (1 << 14)) >> 15);
 }
 
 // ---- cv::equalizeHist on ingest (need_equal_hist, src/frontend/f2f_tracking.cpp:125-145) -----------------------------
@@ -273,6 +208,15 @@ __global__ void __launch_bounds__(256) equalize_apply_kernel(const uint8_t* __re
 
 }  // namespace
 
+int flv_launch_gray(flv_ctx* ctx, int n_streams, const uint8_t* d_src, size_t row_stride, size_t img_stride, int channels, int rgb,
+                    uint8_t* d_dst_tight) {
+  dim3 grid((ctx->w + 255) / 256, ctx->h, n_streams);
+  gray_kernel<<<grid, 256, 0, ctx->stream>>>(d_src, row_stride, img_stride, channels, rgb, d_dst_tight, ctx->w, ctx->h);
+  ctx->launches++;
+  FLV_CUDA(ctx, cudaGetLastError());
+  return FLV_OK;
+}
+
 int flv_launch_equalize(flv_ctx* ctx, int n_streams, const uint8_t* d_src, size_t row_stride, size_t img_stride, uint8_t* d_dst_tight) {
   if (!ctx->d_hist) FLV_CUDA(ctx, cudaMalloc(&ctx->d_hist, (size_t)ctx->S * 256 * sizeof(int)));
   FLV_CUDA(ctx, cudaMemsetAsync(ctx->d_hist, 0, (size_t)n_streams * 256 * sizeof(int), ctx->stream));
@@ -322,15 +266,6 @@ int flv_launch_pyramid(flv_ctx* ctx, int slot, int n_streams) {
   ctx->deriv_streams[slot] = 0;
   const int first = ctx->l1_valid[slot] ? 2 : 1;      // level 1 already built by the fused ingest kernel
   ctx->l1_valid[slot] = 0;
-  if (first == 2 && g.nlev == 4 && g.lv[2].w <= L23_MAXW && !ctx->no_fused_ingest) {
-    const LevelGeom &a = g.lv[1], &b = g.lv[2], &c = g.lv[3];
-    dim3 grid((c.h + L23_ROWS - 1) / L23_ROWS, n_streams);
-    pyr_down2_kernel<<<grid, 256, 0, ctx->stream>>>(ctx->pyr[slot], g.stream_stride, a.off, a.w, a.h, a.pitch, b.off, b.w, b.h,
-                                                    b.pitch, c.off, c.w, c.h, c.pitch);
-    ctx->launches++;
-    FLV_CUDA(ctx, cudaGetLastError());
-    return FLV_OK;
-  }
   for (int l = first; l < g.nlev; ++l) {
     const LevelGeom& a = g.lv[l - 1];
     const LevelGeom& b = g.lv[l];

@@ -57,6 +57,12 @@ long long flv_launch_count(flv_ctx* ctx);
 int flv_level_info(flv_ctx* ctx, int level, int* w, int* h, int* pitch, size_t* offset);
 int flv_num_levels(flv_ctx* ctx);
 
+/* Colour frames (F2FTracking::image_feed converts 3- / 4-channel input with cvtColor BGR2GRAY / BGRA2GRAY, or the RGB
+ * variants when mbRGB is set: src/frontend/f2f_tracking.cpp:78-110): interleaved u8 pixels, `channels` = 3 | 4,
+ * is_rgb = 0 for BGR(A) order.  Bit-exact with cv2.cvtColor; equalizeHist (below) applies after the conversion. */
+int flv_upload_color_images(flv_ctx* ctx, int slot, int n_streams, const uint8_t* imgs, size_t row_stride_bytes,
+                            size_t img_stride_bytes, int channels, int is_rgb, flv_memspace mem);
+
 /* need_equal_hist (src/frontend/f2f_tracking.cpp:125-145): when enabled, every image ingested by flv_upload_images goes
  * through cv::equalizeHist (per-image histogram, LUT) before level 0 is written.  Bit-exact with cv2.equalizeHist. */
 int flv_set_equalize_hist(flv_ctx* ctx, int enable);

@@ -231,3 +231,19 @@ def test_equalize_hist_on_ingest_bit_exact():
     ctx.upload(2, imgs)
     assert np.array_equal(ctx.download_level(2, 1, 0), low)
     ctx.close()
+
+
+@pytest.mark.parametrize("ch,rgb", [(3, False), (3, True), (4, False), (4, True)])
+def test_color_ingest_matches_cv2_cvtcolor(ch, rgb):
+    """flv_upload_color_images == cv2.cvtColor(BGR/RGB/BGRA/RGBA -> GRAY) (f2f_tracking.cpp:78-110), bit-exact."""
+    import cv2
+    rng = np.random.default_rng(ch * 2 + rgb)
+    h, w = 480, 752
+    imgs = rng.integers(0, 256, (2, h, w, ch), dtype=np.uint8)
+    code = {(3, False): cv2.COLOR_BGR2GRAY, (3, True): cv2.COLOR_RGB2GRAY, (4, False): cv2.COLOR_BGRA2GRAY,
+            (4, True): cv2.COLOR_RGBA2GRAY}[(ch, rgb)]
+    ctx = _ctx(2, w, h)
+    ctx.upload_color(0, imgs, is_rgb=rgb)
+    for s in range(2):
+        assert np.array_equal(ctx.download_level(0, s, 0), cv2.cvtColor(imgs[s], code))
+    ctx.close()
