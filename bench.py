@@ -35,6 +35,14 @@ NPTS = 480
 MAX_PTS = 512
 KF_EVERY = 5
 BA_WINDOW = 10
+BA_LANDMARKS = 1500
+STEREO = True
+WORKLOAD = "euroc"
+WORKLOADS = {   # BASELINE.json configs: image size, stereo, local-BA window / landmarks
+    "euroc": dict(w=752, h=480, stereo=True, window=10, landmarks=1500, name="EuRoC-shaped 752x480 stereo (configs[1]/[2])"),
+    "kitti": dict(w=1241, h=376, stereo=True, window=20, landmarks=2000, name="KITTI-shaped 1241x376 stereo, 20-KF / 2k-landmark window (configs[3])"),
+    "d435": dict(w=640, h=480, stereo=False, window=10, landmarks=1500, name="640x480 D435i depth (configs[4]); depth lookups are per-point reads, no right image"),
+}
 FEATURE_PARA = [30, 20, 5, 1000, 0.01, 10]       # launch/EuRoC_MAV/euroc.yaml:57-67
 P_PYR = 479400                                    # pyramid pixels of 752x480
 LK_BYTES_PER_CALL = 6 * P_PYR + 29 * NPTS         # algorithmic bytes of one LK call, one stream: both u8 pyramids + the
@@ -148,7 +156,7 @@ def run_ours(args):
     n_pool = 8                                        # distinct frames per stream in the pool (cycled)
     f0, f1 = make_streams(S, sharding.stream_ids(rank, world, S)[0], n_pool)     # rank r owns streams [r*S, (r+1)*S)
     bench = FrontendBench(S, W, H, MAX_PTS, NPTS, FEATURE_PARA, local_rank, ba_window=BA_WINDOW,
-                          kf_every=KF_EVERY, seed=rank)
+                          kf_every=KF_EVERY, seed=rank, stereo=STEREO, ba_landmarks=BA_LANDMARKS)
     bench.load_pool(f0, f1)
 
     def barrier():
@@ -191,7 +199,8 @@ def run_ours(args):
     # BASELINE configs[1]: ONE stream on the GPU (latency-oriented), reported next to the batched headline
     single = None
     if world == 1 and S > 1:
-        b1 = FrontendBench(1, W, H, MAX_PTS, NPTS, FEATURE_PARA, local_rank, ba_window=BA_WINDOW, kf_every=KF_EVERY, seed=rank)
+        b1 = FrontendBench(1, W, H, MAX_PTS, NPTS, FEATURE_PARA, local_rank, ba_window=BA_WINDOW, kf_every=KF_EVERY, seed=rank,
+                           stereo=STEREO, ba_landmarks=BA_LANDMARKS)
         b1.load_pool(f0[:, :1].copy(), f1[:, :1].copy())
         k1 = max(args.steps, 50)
         ms1, _, _, _ = timed("device", k1, args.warmup, bench=b1)
@@ -211,12 +220,14 @@ def run_ours(args):
         if single is not None and not args.no_cpu:
             single["cpu_value"] = cpu_baseline(1, 10, args)["value"]      # same single stream on the host (cv2 uses all cores)
         out = {
-            "metric": "frames/sec (device-timed), EuRoC-shaped 752x480 stereo, LK frontend + 10-KF local BA",
+            "metric": "frames/sec (device-timed), EuRoC-shaped 752x480 stereo, LK frontend + 10-KF local BA" if WORKLOAD == "euroc"
+                      else f"frames/sec (device-timed), {WORKLOADS[WORKLOAD]['name']}",
             "value": frames / (ms_dev * 1e-3), "unit": "frames/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_dev / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "u8/i32 fixed-point + f32 (frontend), f64 (BA)",
             "data": "synthetic",
-            "config": {"workload": f"{S} concurrent EuRoC-shaped 752x480 stereo streams per GPU (BASELINE configs[2]); "
+            "config": {"workload": (f"{S} concurrent EuRoC-shaped 752x480 stereo streams per GPU (BASELINE configs[2]); " if WORKLOAD == "euroc"
+                                    else f"{S} concurrent streams per GPU, {WORKLOADS[WORKLOAD]['name']}; ") +
                                    f"480 pts/stream, LK 31x31 4 levels x2, GFTT N=1000 + FeatureDEM redetect, "
                                    f"local BA W={BA_WINDOW} every {KF_EVERY}th frame" + ("" if bench.has_ba else " [BA NOT YET IN STEP]"),
                        "streams_per_gpu": S, "image": [W, H], "points_per_stream": NPTS,
@@ -234,7 +245,7 @@ def run_ours(args):
             "single_stream": single,
             "roofline": {"kernel": "lk_track_kernel_v4 (frame->frame + left->right)", "bound": "hbm",
                          "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": LK_NCU_TRAFFIC * S / 32, "peak_source": peak_src,
+                         "traffic": LK_NCU_TRAFFIC * S / 32 if WORKLOAD == "euroc" else None, "peak_source": peak_src,
                          "us_per_launch": lk_us, "algorithmic_bytes_per_launch": LK_BYTES_PER_CALL * S,
                          "note": "LK is instruction-issue bound, not HBM bound (ncu: DRAM < 3 % busy, traffic == algorithmic "
                                  "bytes, i.e. no re-reads); us_per_launch is measured inside the step, where other streams' "
@@ -256,8 +267,9 @@ def cpu_frame(cv2, fd_para, prev0, cur0, cur1, pts, crit):
                                           flags=cv2.OPTFLOW_USE_INITIAL_FLOW)            # lkorb_tracking.cpp:64-73
     mask = np.full(cur0.shape, 255, np.uint8)
     cv2.goodFeaturesToTrack(cur0, fd_para[3], fd_para[4], fd_para[5], mask=mask)        # feature_dem.cpp:160
-    cv2.calcOpticalFlowPyrLK(cur0, cur1, nxt, nxt.copy(), winSize=(31, 31), maxLevel=5, criteria=crit,
-                             flags=cv2.OPTFLOW_USE_INITIAL_FLOW)                         # camera_frame.cpp:124-128
+    if STEREO:
+        cv2.calcOpticalFlowPyrLK(cur0, cur1, nxt, nxt.copy(), winSize=(31, 31), maxLevel=5, criteria=crit,
+                                 flags=cv2.OPTFLOW_USE_INITIAL_FLOW)                     # camera_frame.cpp:124-128
     ok = st.ravel() == 1
     nxt[~ok] = pts[~ok]
     return nxt
@@ -276,7 +288,7 @@ def cpu_baseline(n_streams, n_frames, args):
     ba = None
     try:
         from flvis_b200.pipeline import make_ba_batch, cpu_ba_solve
-        ba = make_ba_batch(n_streams, BA_WINDOW, seed=7)
+        ba = make_ba_batch(n_streams, BA_WINDOW, seed=7, n_landmarks=BA_LANDMARKS)
     except Exception:
         ba = None
 
@@ -332,7 +344,14 @@ def main():
     ap.add_argument("--streams", type=int, default=32)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--workload", default="euroc", choices=sorted(WORKLOADS), help="euroc = the headline (default)")
     args = ap.parse_args()
+    global W, H, STEREO, BA_WINDOW, BA_LANDMARKS, WORKLOAD, P_PYR, LK_BYTES_PER_CALL
+    wl = WORKLOADS[args.workload]
+    WORKLOAD, W, H, STEREO, BA_WINDOW, BA_LANDMARKS = args.workload, wl["w"], wl["h"], wl["stereo"], wl["window"], wl["landmarks"]
+    if args.workload != "euroc":
+        P_PYR = sum(((W + (1 << l) - 1) >> l) * ((H + (1 << l) - 1) >> l) for l in range(4))
+        LK_BYTES_PER_CALL = 6 * P_PYR + 29 * NPTS
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3
     if args.impl == "reference":

@@ -29,7 +29,7 @@
 
 namespace {
 
-constexpr int BA_THREADS = 384;          // 12 warps: 168 registers per thread keep the 36 Schur accumulators of a lane resident
+constexpr int BA_THREADS = 384;          // 12 warps: 168 registers per thread keep the 36 Schur accumulators of a lane resident (512 threads x 128 regs measured slower: spills in the pair products)
 constexpr int BA_WARPS = BA_THREADS / 32;
 constexpr int BA_MAX_POSES = 32;
 constexpr int BA_MAX_FREE = 24;          // reduced system n <= 144 -> S fits shared memory

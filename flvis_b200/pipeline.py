@@ -27,10 +27,12 @@ def cpu_ba_solve(batch, s):
 
 
 class FrontendBench:
-    def __init__(self, n_streams, w, h, max_pts, npts, feature_para, device_index, ba_window=10, kf_every=5, seed=0):
+    def __init__(self, n_streams, w, h, max_pts, npts, feature_para, device_index, ba_window=10, kf_every=5, seed=0,
+                 stereo=True, ba_landmarks=1500):
         import torch
         self.torch = torch
         self.S, self.w, self.h, self.max_pts, self.npts = n_streams, w, h, max_pts, npts
+        self.stereo = stereo            # False: depth camera (DEPTH_D435): no right image, no left->right LK
         self.dev = torch.device("cuda", device_index)
         self.ctx = capi.Context(n_streams, w, h, max_pts, device=device_index)
         # a dedicated (non-default) torch stream: the library launches on it and all events are recorded on it
@@ -76,11 +78,11 @@ class FrontendBench:
             if os.environ.get("FLV_BENCH_NO_BA"):          # diagnostic only: frontend alone under bench conditions
                 raise ImportError
             from . import ba_synth
-            self.ba = ba_synth.DeviceBatch(self.ctx, make_ba_batch(n_streams, ba_window, seed=seed), self.dev)
+            self.ba = ba_synth.DeviceBatch(self.ctx, make_ba_batch(n_streams, ba_window, seed=seed, n_landmarks=ba_landmarks), self.dev)
             self.has_ba = True
         except ImportError:
             self.ba = None
-        self.h2d_bytes_per_step = 2 * S * w * h + (self.ba.h2d_bytes_per_step(kf_every) if self.has_ba else 0)
+        self.h2d_bytes_per_step = (2 if stereo else 1) * S * w * h + (self.ba.h2d_bytes_per_step(kf_every) if self.has_ba else 0)
         self.d2h_bytes_per_step = (S * M * (8 + 1) * 2 + S * M * 8 + S * 4 +
                                    (self.ba.d2h_bytes_per_step(kf_every) if self.has_ba else 0))
 
@@ -140,16 +142,19 @@ class FrontendBench:
         if mode == "host":
             if self.prefetched != k:                       # first host-mode step: nothing in flight yet
                 ctx.upload_host_async(cur0, S, self.h_pool0[k].data_ptr())
-                ctx.upload_host_async(cur1, S, self.h_pool1[k].data_ptr())
+                if self.stereo:
+                    ctx.upload_host_async(cur1, S, self.h_pool1[k].data_ptr())
         else:
             self.prefetched = -1
             ctx.upload_dev(cur0, S, self.d_pool0[k].data_ptr())
-            ctx.upload_dev(cur1, S, self.d_pool1[k].data_ptr())
+            if self.stereo:
+                ctx.upload_dev(cur1, S, self.d_pool1[k].data_ptr())
         ctx.build_pyramid(cur0, S)
         # Shi-Tomasi of the new left image only needs the image: start it now on the library's auxiliary stream, it
         # overlaps the right pyramid, the frame->frame LK and the keep rule (results identical, see flv_feature_prepare)
         ctx.feature_prepare(cur0, S, self.fp, redetect=True)
-        ctx.build_pyramid(cur1, S)
+        if self.stereo:
+            ctx.build_pyramid(cur1, S)
         # frame -> frame LK (lkorb_tracking.cpp:64-73) + keep rule (:98-119)
         self._lk(prev0, cur0, self.d_pts, self.d_pts, self.d_next, self.d_status, self.d_err, 10)
         ctx.select_tracked_dev(S, self.d_npts.data_ptr(), self.d_pts.data_ptr(), self.d_next.data_ptr(),
@@ -165,7 +170,8 @@ class FrontendBench:
                                  self.d_new.data_ptr(), self.d_nnew.data_ptr())
         self.ev_red.record(self.side)
         ctx.set_stream(self.stream.cuda_stream)
-        self._lk(cur0, cur1, self.d_cur, self.d_cur, self.d_right, self.d_rstatus, self.d_rerr, 5)
+        if self.stereo:
+            self._lk(cur0, cur1, self.d_cur, self.d_cur, self.d_right, self.d_rstatus, self.d_rerr, 5)
         self.stream.wait_event(self.ev_red)
         if self.has_ba:
             self.ba.step(i, mode, self.kf_every)
@@ -179,7 +185,8 @@ class FrontendBench:
             # consume the PREVIOUS frame's results -- every frame's inputs and outputs cross PCIe, one frame of latency
             k2 = (i + 2) % self.n_pool
             ctx.upload_host_async(prev0, S, self.h_pool0[k2].data_ptr())      # next step's cur0 slot
-            ctx.upload_host_async(cur1, S, self.h_pool1[k2].data_ptr())
+            if self.stereo:
+                ctx.upload_host_async(cur1, S, self.h_pool1[k2].data_ptr())
             self.prefetched = k2
             if self.pending is not None:
                 self.done[self.pending].synchronize()
