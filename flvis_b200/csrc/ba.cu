@@ -686,8 +686,8 @@ __device__ void solve_system(const flv_ba_problem& pb, double lambda, double* S,
   // Right-looking Cholesky (LDL^T form) of the augmented matrix [S ; y^T] (row n = right-hand side): one barrier per
   // column, no square roots -- after step j column j holds A_ij = L_ij sqrt(d_j), the diagonal d_j = L_jj^2, and
   //   x_j = (y_j - sum_{k>j} A_kj x_k) / d_j.
-  int T = 1;
-  while ((n + 1) * (T << 1) <= BA_THREADS && T < 32) T <<= 1;
+  int T = BA_THREADS / (n + 1);                   // threads per row (no shuffles here: any count works)
+  T = T < 1 ? 1 : (T > 32 ? 32 : T);
   const int row = tid / T, t = tid - row * T;
   bool bad = false;
   for (int j = 0; j < n; ++j) {
