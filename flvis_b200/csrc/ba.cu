@@ -197,6 +197,9 @@ struct Sh {   // fixed-size shared state
   int chunk_sb[BA_MAX_CHUNKS + 1];      // slot range of a chunk
   int scan[BA_WARPS];
   unsigned char pair_a[BA_MAX_PAIRS], pair_b[BA_MAX_PAIRS];
+  int task_bounds[BA_MAX_PAIRS + 1];    // member-list bounds of the pose pairs for the chunk being processed
+  unsigned short task_order[BA_MAX_PAIRS];   // pose pairs by decreasing member count: the order warps pick them up in
+  int next_task;
   int np, fail, nact, overflow, nch, cap, capq;
   long long prof[16], tlast;  // cycle counters: 0 chi2, 1 build (pose pass), 2 schur (pair products), 3 cholesky, 4 substitution,
                               // 5 update, 6 setup, 7 -, 8 schur init + Dinv, 9 schur chunk staging, 10 build edge pass, 11 build landmark pass
@@ -208,9 +211,13 @@ __device__ __forceinline__ void mark(Sh& sh, int slot) {
 
 // per-stream global workspace views.  "slot" arrays are structure-of-arrays planes with stride ME (max edges),
 // landmark arrays planes with stride ML: consecutive threads touch consecutive addresses in every pass.
+// plane PAIRS: two consecutive planes are interleaved per slot so that every access is one 16-byte load / store
+#define PL2(p) reinterpret_cast<double2*>(p)
+#define CPL2(p) reinterpret_cast<const double2*>(p)
+
 struct Ws {
   double *pbk, *lbk;
-  double *W, *Bw, *g, *hl, *bb, *uvs;       // [18|12|2|6|3|2][ME]
+  double *W, *Bw, *g, *hl, *bb, *uvs;       // double2 [9|6|1|3|2|1][ME]: plane pairs (2k, 2k+1) interleaved per slot
   double *Hll, *bl, *Dinv, *Dv, *Ld;        // [6|3|6|3|6][ML]
   int *tab;                                 // [P][L]: edge id during setup, then slot of edge (p,l) or -1
   unsigned* lmask;                          // [L]
@@ -270,7 +277,8 @@ __device__ double robust_chi2(const Cam& cam, const double* poses, const double*
   const double d2 = delta * delta;
   for (int s = threadIdx.x; s < sh.nact; s += BA_THREADS) {
     const int pl = ws.slot_pl[s];
-    const double uv[2] = {ws.uvs[s], ws.uvs[ws.ME + s]};
+    const double2 q2 = CPL2(ws.uvs)[s];
+    const double uv[2] = {q2.x, q2.y};
     double r[2];
     edge_eval<false>(poses + 7 * (pl & 255), lms + 3 * (size_t)(pl >> 8), uv, cam, r, nullptr, nullptr);
     const double c = r[0] * r[0] + r[1] * r[1];
@@ -370,7 +378,7 @@ __device__ void setup_active(const flv_ba_problem& pb, const int* ep, const int*
         const int e = ws.tab[p * L + l];
         ws.slot_e[s] = e; ws.slot_pl[s] = p | (l << 8);
         ws.slot_lp[s] = ws.lstart[l] + __popc(ws.lmask[l] & ((1u << p) - 1));
-        ws.uvs[s] = uv[2 * (size_t)e]; ws.uvs[ws.ME + s] = uv[2 * (size_t)e + 1];
+        PL2(ws.uvs)[s] = make_double2(uv[2 * (size_t)e], uv[2 * (size_t)e + 1]);
         ws.tab[p * L + l] = s;
       }
       base += __popc(bal);
@@ -396,6 +404,20 @@ __device__ void setup_active(const flv_ba_problem& pb, const int* ep, const int*
       cnt += __popc(__ballot_sync(FULL, l < le && (ws.lmask[l] & need) == need));
     }
     if (lane == 0) ws.poff[task] = cnt;
+  }
+  __syncthreads();
+  // pick-up order of the pair tasks: largest first (a warp that draws a diagonal pair late would make the others wait)
+  for (int blk = tid; blk < nblk; blk += BA_THREADS) {
+    int tot = 0;
+    for (int ch = 0; ch < nch; ++ch) tot += ws.poff[ch * nblk + blk];
+    sh.task_bounds[blk] = tot;
+  }
+  __syncthreads();
+  for (int blk = tid; blk < nblk; blk += BA_THREADS) {
+    const int mine = sh.task_bounds[blk];
+    int rank = 0;
+    for (int j = 0; j < nblk; ++j) { const int o = sh.task_bounds[j]; rank += (o > mine) || (o == mine && j < blk); }
+    sh.task_order[rank] = (unsigned short)blk;
   }
   __syncthreads();
   block_exclusive_scan(ws.poff, nch * nblk, sh);
@@ -437,20 +459,23 @@ __device__ void build_system(const flv_ba_problem& pb, const Cam& cam, const dou
       const double c = r[0] * r[0] + r[1] * r[1];
       const double rho1 = (c <= d2) ? 1.0 : delta / sqrt(c);
       const double o0 = -r[0] * rho1, o1 = -r[1] * rho1;
-#pragma unroll
-      for (int i = 0; i < 3; ++i) ws.bb[i * ME + lp] = A[i] * o0 + A[3 + i] * o1;   // landmark-major: the landmark pass reads runs
-      ws.hl[0 * ME + lp] = rho1 * (A[0] * A[0] + A[3] * A[3]); ws.hl[1 * ME + lp] = rho1 * (A[0] * A[1] + A[3] * A[4]);
-      ws.hl[2 * ME + lp] = rho1 * (A[0] * A[2] + A[3] * A[5]); ws.hl[3 * ME + lp] = rho1 * (A[1] * A[1] + A[4] * A[4]);
-      ws.hl[4 * ME + lp] = rho1 * (A[1] * A[2] + A[4] * A[5]); ws.hl[5 * ME + lp] = rho1 * (A[2] * A[2] + A[5] * A[5]);
+      // shares are stored landmark-major (CSR position lp): the landmark pass reads runs
+      PL2(ws.bb)[lp] = make_double2(A[0] * o0 + A[3] * o1, A[1] * o0 + A[4] * o1);
+      PL2(ws.bb)[ME + lp] = make_double2(A[2] * o0 + A[5] * o1, 0.0);
+      PL2(ws.hl)[lp] = make_double2(rho1 * (A[0] * A[0] + A[3] * A[3]), rho1 * (A[0] * A[1] + A[3] * A[4]));
+      PL2(ws.hl)[ME + lp] = make_double2(rho1 * (A[0] * A[2] + A[3] * A[5]), rho1 * (A[1] * A[1] + A[4] * A[4]));
+      PL2(ws.hl)[2 * ME + lp] = make_double2(rho1 * (A[1] * A[2] + A[4] * A[5]), rho1 * (A[2] * A[2] + A[5] * A[5]));
       if (sh.pidx[p] >= 0) {
 #pragma unroll
-        for (int i = 0; i < 6; ++i)
-#pragma unroll
-          for (int j = 0; j < 3; ++j) ws.W[(3 * i + j) * ME + s] = rho1 * (B[i] * A[j] + B[6 + i] * A[3 + j]);
+        for (int cp = 0; cp < 9; ++cp) {
+          const int t0 = 2 * cp, t1 = 2 * cp + 1;                // W entry t = 3 i + j
+          PL2(ws.W)[cp * ME + s] = make_double2(rho1 * (B[t0 / 3] * A[t0 % 3] + B[6 + t0 / 3] * A[3 + t0 % 3]),
+                                               rho1 * (B[t1 / 3] * A[t1 % 3] + B[6 + t1 / 3] * A[3 + t1 % 3]));
+        }
         const double sr = sqrt(rho1);
 #pragma unroll
-        for (int i = 0; i < 12; ++i) ws.Bw[i * ME + s] = sr * B[i];
-        ws.g[s] = -sr * r[0]; ws.g[ME + s] = -sr * r[1];
+        for (int i = 0; i < 6; ++i) PL2(ws.Bw)[i * ME + s] = make_double2(sr * B[2 * i], sr * B[2 * i + 1]);
+        PL2(ws.g)[s] = make_double2(-sr * r[0], -sr * r[1]);
       }
     };
     for (int s0 = tid; s0 < sh.nact; s0 += 2 * BA_THREADS) {
@@ -458,7 +483,8 @@ __device__ void build_system(const flv_ba_problem& pb, const Cam& cam, const dou
       const bool two = s1 < sh.nact;
       const int sb1 = two ? s1 : s0;
       const int pl0 = ws.slot_pl[s0], pl1 = ws.slot_pl[sb1], lp0 = ws.slot_lp[s0], lp1 = ws.slot_lp[sb1];
-      const double uv0[2] = {ws.uvs[s0], ws.uvs[ME + s0]}, uv1[2] = {ws.uvs[sb1], ws.uvs[ME + sb1]};
+      const double2 qa = CPL2(ws.uvs)[s0], qb = CPL2(ws.uvs)[sb1];
+      const double uv0[2] = {qa.x, qa.y}, uv1[2] = {qb.x, qb.y};
       double pose0[7], pose1[7], X0[3], X1[3];
 #pragma unroll
       for (int i = 0; i < 7; ++i) { pose0[i] = poses[7 * (pl0 & 255) + i]; pose1[i] = poses[7 * (pl1 & 255) + i]; }
@@ -475,9 +501,8 @@ __device__ void build_system(const flv_ba_problem& pb, const Cam& cam, const dou
       double H[6] = {0, 0, 0, 0, 0, 0}, b[3] = {0, 0, 0};
       for (int j = j0; j < j1; ++j) {             // pose order; addresses do not depend on loaded data
 #pragma unroll
-        for (int i = 0; i < 6; ++i) H[i] += ws.hl[i * ME + j];
-#pragma unroll
-        for (int i = 0; i < 3; ++i) b[i] += ws.bb[i * ME + j];
+        for (int i = 0; i < 3; ++i) { const double2 v = CPL2(ws.hl)[i * ME + j]; H[2 * i] += v.x; H[2 * i + 1] += v.y; }
+        { const double2 v = CPL2(ws.bb)[j], u = CPL2(ws.bb)[ME + j]; b[0] += v.x; b[1] += v.y; b[2] += u.x; }
       }
 #pragma unroll
       for (int i = 0; i < 6; ++i) ws.Hll[i * ML + l] = H[i];
@@ -506,7 +531,8 @@ __device__ void build_system(const flv_ba_problem& pb, const Cam& cam, const dou
         double B[12], g0, g1;
         if (pb.fix_landmarks) {
           const int pl = ws.slot_pl[s];
-          const double uv[2] = {ws.uvs[s], ws.uvs[ME + s]};
+          const double2 q2 = CPL2(ws.uvs)[s];
+          const double uv[2] = {q2.x, q2.y};
           double r[2], A[6];
           edge_eval<true>(poses + 7 * p, lms + 3 * (size_t)(pl >> 8), uv, cam, r, A, B);
           const double c = r[0] * r[0] + r[1] * r[1];
@@ -516,8 +542,8 @@ __device__ void build_system(const flv_ba_problem& pb, const Cam& cam, const dou
           g0 = -sr * r[0]; g1 = -sr * r[1];
         } else {
 #pragma unroll
-          for (int i = 0; i < 12; ++i) B[i] = ws.Bw[i * ME + s];
-          g0 = ws.g[s]; g1 = ws.g[ME + s];
+          for (int i = 0; i < 6; ++i) { const double2 v = CPL2(ws.Bw)[i * ME + s]; B[2 * i] = v.x; B[2 * i + 1] = v.y; }
+          { const double2 v = CPL2(ws.g)[s]; g0 = v.x; g1 = v.y; }
         }
         int k2 = 0;
 #pragma unroll
@@ -588,17 +614,14 @@ __device__ void solve_system(const flv_ba_problem& pb, double lambda, double* S,
     double* Vc = chunk + 18 * cap;        // [3][cap]   Ld^T bl of the chunk's landmarks
     for (int ch = 0; ch < sh.nch; ++ch) {
       const int sb = sh.chunk_sb[ch], ns = sh.chunk_sb[ch + 1] - sb, lb = sh.chunk_lb[ch], nl = sh.chunk_lb[ch + 1] - lb;
-      // this warp's member-list bounds for the chunk (lane j <-> pair warp + 16 j); issued before the staging loads
-      int my0 = 0, my1 = 0;
-      {
-        const int blk = warp + BA_WARPS * lane;
-        if (blk < nblk) { my0 = ws.poff[ch * nblk + blk]; my1 = ws.poff[ch * nblk + blk + 1]; }
-      }
+      // member-list bounds of every pose pair for this chunk -> shared memory; tasks are drawn dynamically below
+      for (int i = tid; i <= nblk; i += BA_THREADS) sh.task_bounds[i] = ws.poff[ch * nblk + i];
+      if (tid == 0) sh.next_task = 0;
       for (int i = tid; i < ns; i += BA_THREADS) {
         const int sl = sb + i, pl = ws.slot_pl[sl];
         double w[18];
 #pragma unroll
-        for (int c = 0; c < 18; ++c) w[c] = ws.W[c * ME + sl];          // 18 independent coalesced loads in flight
+        for (int c = 0; c < 9; ++c) { const double2 v = CPL2(ws.W)[c * ME + sl]; w[2 * c] = v.x; w[2 * c + 1] = v.y; }   // 9 independent 16-byte loads
         if (sh.pidx[pl & 255] < 0) continue;                            // fixed pose: W was never written, Z is never read
         const int l = pl >> 8;
         const double l00 = ws.Ld[l], l10 = ws.Ld[ML + l], l20 = ws.Ld[2 * ML + l], l11 = ws.Ld[3 * ML + l],
@@ -616,8 +639,13 @@ __device__ void solve_system(const flv_ba_problem& pb, double lambda, double* S,
       }
       __syncthreads();
       mark(sh, 9);
-      for (int j = 0, blk = warp; blk < nblk; blk += BA_WARPS, ++j) {
-        const int i0 = __shfl_sync(FULL, my0, j), i1 = __shfl_sync(FULL, my1, j);
+      for (;;) {
+        int tsk = 0;
+        if (lane == 0) tsk = atomicAdd(&sh.next_task, 1);
+        tsk = __shfl_sync(FULL, tsk, 0);
+        if (tsk >= nblk) break;
+        const int blk = sh.task_order[tsk];
+        const int i0 = sh.task_bounds[blk], i1 = sh.task_bounds[blk + 1];
         if (i0 == i1) continue;
         const int a = sh.pair_a[blk], b = sh.pair_b[blk];
         // one lane per member: acc[6 i + jc] += sum_c Za[i][c] Zb[jc][c]  (block (a,b) of W Dinv W^T)
@@ -744,11 +772,13 @@ __device__ double apply_update(const flv_ba_problem& pb, double lambda, double* 
       if (pi >= 0) {
         const double* xp = sh.x + 6 * pi;
 #pragma unroll
-        for (int i = 0; i < 6; ++i) {
-          t0 += ws.W[(3 * i) * ME + s] * xp[i]; t1 += ws.W[(3 * i + 1) * ME + s] * xp[i]; t2 += ws.W[(3 * i + 2) * ME + s] * xp[i];
-        }
+        double w[18];
+#pragma unroll
+        for (int c = 0; c < 9; ++c) { const double2 v = CPL2(ws.W)[c * ME + s]; w[2 * c] = v.x; w[2 * c + 1] = v.y; }
+#pragma unroll
+        for (int i = 0; i < 6; ++i) { t0 += w[3 * i] * xp[i]; t1 += w[3 * i + 1] * xp[i]; t2 += w[3 * i + 2] * xp[i]; }
       }
-      ws.bb[lp] = t0; ws.bb[ME + lp] = t1; ws.bb[2 * ME + lp] = t2;
+      PL2(ws.bb)[lp] = make_double2(t0, t1); PL2(ws.bb)[ME + lp] = make_double2(t2, 0.0);
     }
     __syncthreads();
     for (int l = tid; l < L; l += BA_THREADS) {
@@ -758,7 +788,7 @@ __device__ double apply_update(const flv_ba_problem& pb, double lambda, double* 
       if (j0 == j1) continue;
       const double bl0 = ws.bl[l], bl1 = ws.bl[ML + l], bl2 = ws.bl[2 * ML + l];
       double c0 = bl0, c1 = bl1, c2 = bl2;
-      for (int j = j0; j < j1; ++j) { c0 -= ws.bb[j]; c1 -= ws.bb[ME + j]; c2 -= ws.bb[2 * ME + j]; }
+      for (int j = j0; j < j1; ++j) { const double2 v = CPL2(ws.bb)[j], u = CPL2(ws.bb)[ME + j]; c0 -= v.x; c1 -= v.y; c2 -= u.x; }
       const double D0 = ws.Dinv[l], D1 = ws.Dinv[ML + l], D2 = ws.Dinv[2 * ML + l], D3 = ws.Dinv[3 * ML + l],
                    D4 = ws.Dinv[4 * ML + l], D5 = ws.Dinv[5 * ML + l];
       const double x0 = D0 * c0 + D1 * c1 + D2 * c2, x1 = D1 * c0 + D3 * c1 + D4 * c2, x2 = D2 * c0 + D4 * c1 + D5 * c2;
@@ -794,7 +824,7 @@ __host__ __device__ inline WsLayout ws_layout(int MP, int ML, int ME) {
   const size_t E = (size_t)ME, L = (size_t)ML, P = (size_t)MP;
   o.pbk = d; d += 7 * P + (P & 1);
   o.lbk = d; d += 3 * L + (L & 1);
-  o.W = d; d += 18 * E; o.Bw = d; d += 12 * E; o.g = d; d += 2 * E; o.hl = d; d += 6 * E; o.bb = d; d += 3 * E;
+  o.W = d; d += 18 * E; o.Bw = d; d += 12 * E; o.g = d; d += 2 * E; o.hl = d; d += 6 * E; o.bb = d; d += 4 * E;
   o.uvs = d; d += 2 * E;
   o.Hll = d; d += 6 * L; o.bl = d; d += 3 * L; o.Dinv = d; d += 6 * L; o.Dv = d; d += 3 * L; o.Ld = d; d += 6 * L;
   o.n_doubles = d;
@@ -910,7 +940,8 @@ __global__ void __launch_bounds__(BA_THREADS, 1) ba_kernel(BAArgs a) {
       int culled = 0, remaining = 0;
       for (int sl = tid; sl < sh.nact; sl += BA_THREADS) {
         const int pl = ws.slot_pl[sl];
-        const double uvv[2] = {ws.uvs[sl], ws.uvs[ws.ME + sl]};
+        const double2 q2 = CPL2(ws.uvs)[sl];
+        const double uvv[2] = {q2.x, q2.y};
         double r[2];
         edge_eval<false>(poses + 7 * (pl & 255), lms + 3 * (size_t)(pl >> 8), uvv, cam, r, nullptr, nullptr);
         if (r[0] * r[0] + r[1] * r[1] > a.prm.cull_chi2) { act[ws.slot_e[sl]] = 0; ++culled; } else ++remaining;
