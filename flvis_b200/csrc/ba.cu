@@ -217,11 +217,11 @@ __device__ __forceinline__ void mark(Sh& sh, int slot) {
 
 struct Ws {
   double *pbk, *lbk;
-  double *W, *Bw, *g, *hl, *bb, *uvs;       // double2 [9|6|1|3|2|1][ME]: plane pairs (2k, 2k+1) interleaved per slot
+  double *W, *luv, *bb, *uvs;               // double2 [9|1|2|1][ME]: plane pairs (2k, 2k+1) interleaved per slot (luv, bb: CSR order)
   double *Hll, *bl, *Dinv, *Dv, *Ld;        // [6|3|6|3|6][ML]
   int *tab;                                 // [P][L]: edge id during setup, then slot of edge (p,l) or -1
   unsigned* lmask;                          // [L]
-  int *slot_e, *slot_pl, *slot_lp;          // [ME]: edge id, p | l << 8, position in the landmark-major (CSR) order
+  int *slot_e, *slot_pl, *slot_lp, *csr_p;  // [ME]: edge id, p | l << 8, position in the landmark-major (CSR) order; pose of CSR entry
   int *lw, *lstart;                         // [L+1] exclusive prefixes (chunk weights, edge counts)
   int *cp_off;                              // [nch][P+1] slot offsets of (chunk, pose) runs
   int *poff;                                // [nch*nblk + 1] member-list offsets of (chunk, pose pair)
@@ -377,7 +377,10 @@ __device__ void setup_active(const flv_ba_problem& pb, const int* ep, const int*
         const int s = base + __popc(bal & ((1u << lane) - 1));
         const int e = ws.tab[p * L + l];
         ws.slot_e[s] = e; ws.slot_pl[s] = p | (l << 8);
-        ws.slot_lp[s] = ws.lstart[l] + __popc(ws.lmask[l] & ((1u << p) - 1));
+        const int lp = ws.lstart[l] + __popc(ws.lmask[l] & ((1u << p) - 1));
+        ws.slot_lp[s] = lp;
+        PL2(ws.luv)[lp] = make_double2(uv[2 * (size_t)e], uv[2 * (size_t)e + 1]);      // landmark-major copies for the landmark pass
+        ws.csr_p[lp] = p;
         PL2(ws.uvs)[s] = make_double2(uv[2 * (size_t)e], uv[2 * (size_t)e + 1]);
         ws.tab[p * L + l] = s;
       }
@@ -452,19 +455,12 @@ __device__ void build_system(const flv_ba_problem& pb, const Cam& cam, const dou
   if (!pb.fix_landmarks) {
     // two slots per thread and trip: all inputs of both edges are loaded before any store, so the two (long, mostly
     // serial) fp64 chains can be interleaved by the scheduler -- the pass was latency-, not throughput-bound
-    auto emit = [&](int s, int pl, int lp, const double* pose, const double* X, const double* uv) {
+    auto emit = [&](int s, int pl, const double* pose, const double* X, const double* uv) {
       const int p = pl & 255;
       double r[2], A[6], B[12];
       edge_eval<true>(pose, X, uv, cam, r, A, B);
       const double c = r[0] * r[0] + r[1] * r[1];
       const double rho1 = (c <= d2) ? 1.0 : delta / sqrt(c);
-      const double o0 = -r[0] * rho1, o1 = -r[1] * rho1;
-      // shares are stored landmark-major (CSR position lp): the landmark pass reads runs
-      PL2(ws.bb)[lp] = make_double2(A[0] * o0 + A[3] * o1, A[1] * o0 + A[4] * o1);
-      PL2(ws.bb)[ME + lp] = make_double2(A[2] * o0 + A[5] * o1, 0.0);
-      PL2(ws.hl)[lp] = make_double2(rho1 * (A[0] * A[0] + A[3] * A[3]), rho1 * (A[0] * A[1] + A[3] * A[4]));
-      PL2(ws.hl)[ME + lp] = make_double2(rho1 * (A[0] * A[2] + A[3] * A[5]), rho1 * (A[1] * A[1] + A[4] * A[4]));
-      PL2(ws.hl)[2 * ME + lp] = make_double2(rho1 * (A[1] * A[2] + A[4] * A[5]), rho1 * (A[2] * A[2] + A[5] * A[5]));
       if (sh.pidx[p] >= 0) {
 #pragma unroll
         for (int cp = 0; cp < 9; ++cp) {
@@ -472,17 +468,13 @@ __device__ void build_system(const flv_ba_problem& pb, const Cam& cam, const dou
           PL2(ws.W)[cp * ME + s] = make_double2(rho1 * (B[t0 / 3] * A[t0 % 3] + B[6 + t0 / 3] * A[3 + t0 % 3]),
                                                rho1 * (B[t1 / 3] * A[t1 % 3] + B[6 + t1 / 3] * A[3 + t1 % 3]));
         }
-        const double sr = sqrt(rho1);
-#pragma unroll
-        for (int i = 0; i < 6; ++i) PL2(ws.Bw)[i * ME + s] = make_double2(sr * B[2 * i], sr * B[2 * i + 1]);
-        PL2(ws.g)[s] = make_double2(-sr * r[0], -sr * r[1]);
       }
     };
     for (int s0 = tid; s0 < sh.nact; s0 += 2 * BA_THREADS) {
       const int s1 = s0 + BA_THREADS;
       const bool two = s1 < sh.nact;
       const int sb1 = two ? s1 : s0;
-      const int pl0 = ws.slot_pl[s0], pl1 = ws.slot_pl[sb1], lp0 = ws.slot_lp[s0], lp1 = ws.slot_lp[sb1];
+      const int pl0 = ws.slot_pl[s0], pl1 = ws.slot_pl[sb1];
       const double2 qa = CPL2(ws.uvs)[s0], qb = CPL2(ws.uvs)[sb1];
       const double uv0[2] = {qa.x, qa.y}, uv1[2] = {qb.x, qb.y};
       double pose0[7], pose1[7], X0[3], X1[3];
@@ -490,8 +482,8 @@ __device__ void build_system(const flv_ba_problem& pb, const Cam& cam, const dou
       for (int i = 0; i < 7; ++i) { pose0[i] = poses[7 * (pl0 & 255) + i]; pose1[i] = poses[7 * (pl1 & 255) + i]; }
 #pragma unroll
       for (int i = 0; i < 3; ++i) { X0[i] = lms[3 * (size_t)(pl0 >> 8) + i]; X1[i] = lms[3 * (size_t)(pl1 >> 8) + i]; }
-      emit(s0, pl0, lp0, pose0, X0, uv0);
-      if (two) emit(s1, pl1, lp1, pose1, X1, uv1);
+      emit(s0, pl0, pose0, X0, uv0);
+      if (two) emit(s1, pl1, pose1, X1, uv1);
     }
     __syncthreads();
     mark(sh, 10);
@@ -499,10 +491,20 @@ __device__ void build_system(const flv_ba_problem& pb, const Cam& cam, const dou
       const int j0 = ws.lstart[l], j1 = ws.lstart[l + 1];
       if (j0 == j1) continue;
       double H[6] = {0, 0, 0, 0, 0, 0}, b[3] = {0, 0, 0};
-      for (int j = j0; j < j1; ++j) {             // pose order; addresses do not depend on loaded data
+      const double X[3] = {lms[3 * (size_t)l], lms[3 * (size_t)l + 1], lms[3 * (size_t)l + 2]};
+      for (int j = j0; j < j1; ++j) {             // pose order; the landmark-major copies make the addresses data-independent
+        const double2 q2 = CPL2(ws.luv)[j];
+        const double uv[2] = {q2.x, q2.y};
+        double r[2], A[6], Bu[12];
+        edge_eval<true>(poses + 7 * ws.csr_p[j], X, uv, cam, r, A, Bu);          // the pose Jacobian is dead code here
+        const double c = r[0] * r[0] + r[1] * r[1];
+        const double rho1 = (c <= d2) ? 1.0 : delta / sqrt(c);
+        const double o0 = -r[0] * rho1, o1 = -r[1] * rho1;
 #pragma unroll
-        for (int i = 0; i < 3; ++i) { const double2 v = CPL2(ws.hl)[i * ME + j]; H[2 * i] += v.x; H[2 * i + 1] += v.y; }
-        { const double2 v = CPL2(ws.bb)[j], u = CPL2(ws.bb)[ME + j]; b[0] += v.x; b[1] += v.y; b[2] += u.x; }
+        for (int i = 0; i < 3; ++i) b[i] += A[i] * o0 + A[3 + i] * o1;
+        H[0] += rho1 * (A[0] * A[0] + A[3] * A[3]); H[1] += rho1 * (A[0] * A[1] + A[3] * A[4]);
+        H[2] += rho1 * (A[0] * A[2] + A[3] * A[5]); H[3] += rho1 * (A[1] * A[1] + A[4] * A[4]);
+        H[4] += rho1 * (A[1] * A[2] + A[4] * A[5]); H[5] += rho1 * (A[2] * A[2] + A[5] * A[5]);
       }
 #pragma unroll
       for (int i = 0; i < 6; ++i) ws.Hll[i * ML + l] = H[i];
@@ -529,7 +531,7 @@ __device__ void build_system(const flv_ba_problem& pb, const Cam& cam, const dou
       const int s0 = ws.cp_off[ch * P1 + p], s1 = ws.cp_off[ch * P1 + p + 1];
       for (int s = s0 + lane; s < s1; s += 32) {
         double B[12], g0, g1;
-        if (pb.fix_landmarks) {
+        {                                             // sqrt(rho') B and -sqrt(rho') r recomputed: cheaper than 7 loads per edge
           const int pl = ws.slot_pl[s];
           const double2 q2 = CPL2(ws.uvs)[s];
           const double uv[2] = {q2.x, q2.y};
@@ -540,10 +542,6 @@ __device__ void build_system(const flv_ba_problem& pb, const Cam& cam, const dou
 #pragma unroll
           for (int i = 0; i < 12; ++i) B[i] *= sr;
           g0 = -sr * r[0]; g1 = -sr * r[1];
-        } else {
-#pragma unroll
-          for (int i = 0; i < 6; ++i) { const double2 v = CPL2(ws.Bw)[i * ME + s]; B[2 * i] = v.x; B[2 * i + 1] = v.y; }
-          { const double2 v = CPL2(ws.g)[s]; g0 = v.x; g1 = v.y; }
         }
         int k2 = 0;
 #pragma unroll
@@ -718,16 +716,21 @@ __device__ void solve_system(const flv_ba_problem& pb, double lambda, double* S,
   T = T < 1 ? 1 : (T > 32 ? 32 : T);
   const int row = tid / T, t = tid - row * T;
   bool bad = false;
+  if (tid == 0) sh.invd[0] = 1.0 / S[0];
+  __syncthreads();
   for (int j = 0; j < n; ++j) {
     const double d = S[j * ld + j];
     if (!(d > 0)) { bad = true; break; }                     // same value in every thread: uniform exit
-    const double inv = 1.0 / d;
-    if (tid == 0) sh.invd[j] = inv;
+    const double inv = sh.invd[j];                           // 1 / d_j, computed by the owner of d_j during step j-1
     if (row > j && row <= n) {
       double* Ai = row < n ? S + row * ld : y;
       const double f = Ai[j] * inv;
       const int kmax = row < n ? row : n - 1;
-      for (int k = j + 1 + t; k <= kmax; k += T) Ai[k] -= f * S[k * ld + j];
+      for (int k = j + 1 + t; k <= kmax; k += T) {
+        const double v = Ai[k] - f * S[k * ld + j];
+        Ai[k] = v;
+        if (k == j + 1 && row == j + 1) sh.invd[j + 1] = 1.0 / v;   // next pivot: its reciprocal leaves the critical path
+      }
     }
     __syncthreads();
   }
@@ -816,19 +819,19 @@ __host__ __device__ inline size_t poff_capacity() { return (size_t)BA_MAX_CHUNKS
 
 // workspace carve-up (doubles first, then ints); shared by the kernel and ws_stride_bytes()
 struct WsLayout {
-  size_t pbk, lbk, W, Bw, g, hl, bb, uvs, Hll, bl, Dinv, Dv, Ld, n_doubles;
-  size_t tab, lmask, slot_e, slot_pl, slot_lp, lw, lstart, cp_off, poff, pairs, n_ints;
+  size_t pbk, lbk, W, luv, bb, uvs, Hll, bl, Dinv, Dv, Ld, n_doubles;
+  size_t tab, lmask, slot_e, slot_pl, slot_lp, csr_p, lw, lstart, cp_off, poff, pairs, n_ints;
 };
 __host__ __device__ inline WsLayout ws_layout(int MP, int ML, int ME) {
   WsLayout o; size_t d = 0, i = 0;
   const size_t E = (size_t)ME, L = (size_t)ML, P = (size_t)MP;
   o.pbk = d; d += 7 * P + (P & 1);
   o.lbk = d; d += 3 * L + (L & 1);
-  o.W = d; d += 18 * E; o.Bw = d; d += 12 * E; o.g = d; d += 2 * E; o.hl = d; d += 6 * E; o.bb = d; d += 4 * E;
+  o.W = d; d += 18 * E; o.luv = d; d += 2 * E; o.bb = d; d += 4 * E;
   o.uvs = d; d += 2 * E;
   o.Hll = d; d += 6 * L; o.bl = d; d += 3 * L; o.Dinv = d; d += 6 * L; o.Dv = d; d += 3 * L; o.Ld = d; d += 6 * L;
   o.n_doubles = d;
-  o.tab = i; i += P * L; o.lmask = i; i += L; o.slot_e = i; i += E; o.slot_pl = i; i += E; o.slot_lp = i; i += E;
+  o.tab = i; i += P * L; o.lmask = i; i += L; o.slot_e = i; i += E; o.slot_pl = i; i += E; o.slot_lp = i; i += E; o.csr_p = i; i += E;
   o.lw = i; i += L + 1; o.lstart = i; i += L + 1; o.cp_off = i; i += (size_t)BA_MAX_CHUNKS * (P + 1);
   o.poff = i; i += poff_capacity(); o.pairs = i; i += pair_capacity(MP, ME);
   o.n_ints = i;
@@ -853,9 +856,9 @@ __global__ void __launch_bounds__(BA_THREADS, 1) ba_kernel(BAArgs a) {
     const WsLayout lo = ws_layout(a.max_poses, a.max_lms, a.max_edges);
     double* d = (double*)(a.ws + (size_t)s * a.ws_stride);
     int* ib = (int*)(d + lo.n_doubles);
-    ws.pbk = d + lo.pbk; ws.lbk = d + lo.lbk; ws.W = d + lo.W; ws.Bw = d + lo.Bw; ws.g = d + lo.g; ws.hl = d + lo.hl;
+    ws.pbk = d + lo.pbk; ws.lbk = d + lo.lbk; ws.W = d + lo.W; ws.luv = d + lo.luv;
     ws.bb = d + lo.bb; ws.uvs = d + lo.uvs; ws.Hll = d + lo.Hll; ws.bl = d + lo.bl; ws.Dinv = d + lo.Dinv; ws.Dv = d + lo.Dv; ws.Ld = d + lo.Ld;
-    ws.tab = ib + lo.tab; ws.lmask = (unsigned*)(ib + lo.lmask); ws.slot_e = ib + lo.slot_e; ws.slot_pl = ib + lo.slot_pl; ws.slot_lp = ib + lo.slot_lp;
+    ws.tab = ib + lo.tab; ws.lmask = (unsigned*)(ib + lo.lmask); ws.slot_e = ib + lo.slot_e; ws.slot_pl = ib + lo.slot_pl; ws.slot_lp = ib + lo.slot_lp; ws.csr_p = ib + lo.csr_p;
     ws.lw = ib + lo.lw; ws.lstart = ib + lo.lstart; ws.cp_off = ib + lo.cp_off; ws.poff = ib + lo.poff;
     ws.pairs = ib + lo.pairs;
     ws.pair_cap = (int)pair_capacity(a.max_poses, a.max_edges); ws.ME = a.max_edges; ws.ML = a.max_lms;
