@@ -149,6 +149,20 @@ __device__ __forceinline__ void edge_eval(const double* pose, const double* X, c
   }
 }
 
+// W = rho' B^T A of one edge (6x3, w[3 i + j]): recomputed where it is needed instead of being stored -- every pass of this
+// kernel waits on memory, not on the fp64 pipe, and 150 flops cost less than nine 16-byte round trips per edge
+__device__ __forceinline__ void edge_W(const double* pose, const double* X, const double* uv, const Cam& cam, double delta,
+                                       double d2, double* w) {
+  double r[2], A[6], B[12];
+  edge_eval<true>(pose, X, uv, cam, r, A, B);
+  const double c = r[0] * r[0] + r[1] * r[1];
+  const double rho1 = (c <= d2) ? 1.0 : delta / sqrt(c);
+#pragma unroll
+  for (int i = 0; i < 6; ++i)
+#pragma unroll
+    for (int j = 0; j < 3; ++j) w[3 * i + j] = rho1 * (B[i] * A[j] + B[6 + i] * A[3 + j]);
+}
+
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
@@ -217,7 +231,7 @@ __device__ __forceinline__ void mark(Sh& sh, int slot) {
 
 struct Ws {
   double *pbk, *lbk;
-  double *W, *luv, *bb, *uvs;               // double2 [9|1|2|1][ME]: plane pairs (2k, 2k+1) interleaved per slot (luv, bb: CSR order)
+  double *luv, *uvs;                        // double2 [ME]: pixel measurement per slot (uvs) and per landmark-major CSR position (luv)
   double *Hll, *bl, *Dinv, *Dv, *Ld;        // [6|3|6|3|6][ML]
   int *tab;                                 // [P][L]: edge id during setup, then slot of edge (p,l) or -1
   unsigned* lmask;                          // [L]
@@ -453,39 +467,6 @@ __device__ void build_system(const flv_ba_problem& pb, const Cam& cam, const dou
   const int ME = ws.ME, ML = ws.ML;
   const double d2 = delta * delta;
   if (!pb.fix_landmarks) {
-    // two slots per thread and trip: all inputs of both edges are loaded before any store, so the two (long, mostly
-    // serial) fp64 chains can be interleaved by the scheduler -- the pass was latency-, not throughput-bound
-    auto emit = [&](int s, int pl, const double* pose, const double* X, const double* uv) {
-      const int p = pl & 255;
-      double r[2], A[6], B[12];
-      edge_eval<true>(pose, X, uv, cam, r, A, B);
-      const double c = r[0] * r[0] + r[1] * r[1];
-      const double rho1 = (c <= d2) ? 1.0 : delta / sqrt(c);
-      if (sh.pidx[p] >= 0) {
-#pragma unroll
-        for (int cp = 0; cp < 9; ++cp) {
-          const int t0 = 2 * cp, t1 = 2 * cp + 1;                // W entry t = 3 i + j
-          PL2(ws.W)[cp * ME + s] = make_double2(rho1 * (B[t0 / 3] * A[t0 % 3] + B[6 + t0 / 3] * A[3 + t0 % 3]),
-                                               rho1 * (B[t1 / 3] * A[t1 % 3] + B[6 + t1 / 3] * A[3 + t1 % 3]));
-        }
-      }
-    };
-    for (int s0 = tid; s0 < sh.nact; s0 += 2 * BA_THREADS) {
-      const int s1 = s0 + BA_THREADS;
-      const bool two = s1 < sh.nact;
-      const int sb1 = two ? s1 : s0;
-      const int pl0 = ws.slot_pl[s0], pl1 = ws.slot_pl[sb1];
-      const double2 qa = CPL2(ws.uvs)[s0], qb = CPL2(ws.uvs)[sb1];
-      const double uv0[2] = {qa.x, qa.y}, uv1[2] = {qb.x, qb.y};
-      double pose0[7], pose1[7], X0[3], X1[3];
-#pragma unroll
-      for (int i = 0; i < 7; ++i) { pose0[i] = poses[7 * (pl0 & 255) + i]; pose1[i] = poses[7 * (pl1 & 255) + i]; }
-#pragma unroll
-      for (int i = 0; i < 3; ++i) { X0[i] = lms[3 * (size_t)(pl0 >> 8) + i]; X1[i] = lms[3 * (size_t)(pl1 >> 8) + i]; }
-      emit(s0, pl0, pose0, X0, uv0);
-      if (two) emit(s1, pl1, pose1, X1, uv1);
-    }
-    __syncthreads();
     mark(sh, 10);
     for (int l = tid; l < L; l += BA_THREADS) {
       const int j0 = ws.lstart[l], j1 = ws.lstart[l + 1];
@@ -571,8 +552,8 @@ __device__ void build_system(const flv_ba_problem& pb, const Cam& cam, const dou
 // The landmark side is streamed through shared memory chunk by chunk (W planes + Dinv + Dinv*bl of the chunk's
 // landmarks); a warp owns a pose pair, two lanes share a member landmark (lane parity h owns columns 3h..3h+2 of the
 // 6x6 block), member lists hold chunk-local positions, so every operand of the inner loop is a shared-memory read.
-__device__ void solve_system(const flv_ba_problem& pb, double lambda, double* S, double* y, double* chunk, int ld,
-                             Ws& ws, Sh& sh) {
+__device__ void solve_system(const flv_ba_problem& pb, const Cam& cam, const double* poses, const double* lms, double delta,
+                             double lambda, double* S, double* y, double* chunk, int ld, Ws& ws, Sh& sh) {
   const int L = pb.n_landmarks, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int np = sh.np, n = 6 * np, ME = ws.ME, ML = ws.ML;
   const int nblk = np * (np + 1) / 2;
@@ -617,11 +598,12 @@ __device__ void solve_system(const flv_ba_problem& pb, double lambda, double* S,
       if (tid == 0) sh.next_task = 0;
       for (int i = tid; i < ns; i += BA_THREADS) {
         const int sl = sb + i, pl = ws.slot_pl[sl];
-        double w[18];
-#pragma unroll
-        for (int c = 0; c < 9; ++c) { const double2 v = CPL2(ws.W)[c * ME + sl]; w[2 * c] = v.x; w[2 * c + 1] = v.y; }   // 9 independent 16-byte loads
-        if (sh.pidx[pl & 255] < 0) continue;                            // fixed pose: W was never written, Z is never read
+        if (sh.pidx[pl & 255] < 0) continue;                            // fixed pose: Z is never read
         const int l = pl >> 8;
+        const double2 q2 = CPL2(ws.uvs)[sl];
+        const double uv[2] = {q2.x, q2.y};
+        double w[18];
+        edge_W(poses + 7 * (pl & 255), lms + 3 * (size_t)l, uv, cam, delta, delta * delta, w);   // state == linearisation point here
         const double l00 = ws.Ld[l], l10 = ws.Ld[ML + l], l20 = ws.Ld[2 * ML + l], l11 = ws.Ld[3 * ML + l],
                      l21 = ws.Ld[4 * ML + l], l22 = ws.Ld[5 * ML + l];
 #pragma unroll
@@ -763,35 +745,36 @@ __device__ void solve_system(const flv_ba_problem& pb, double lambda, double* S,
 
 // state update (sparse_optimizer.cpp:433-446) incl. landmark back-substitution (block_solver.hpp:422-444).
 // Returns sum_j x_j (lambda x_j + b_j) (computeScale, optimization_algorithm_levenberg.cpp:168-175).
-__device__ double apply_update(const flv_ba_problem& pb, double lambda, double* poses, double* lms, Ws& ws, Sh& sh) {
+__device__ double apply_update(const flv_ba_problem& pb, const Cam& cam, double delta, double lambda, double* poses, double* lms,
+                               Ws& ws, Sh& sh) {
   const int P = pb.n_poses, L = pb.n_landmarks, tid = threadIdx.x, ME = ws.ME, ML = ws.ML;
   double sc = 0;
   for (int i = tid; i < 7 * P; i += BA_THREADS) ws.pbk[i] = poses[i];
   if (!pb.fix_landmarks) {
-    // slot pass: t_s = W_s^T x_p, stored landmark-major (reuses the bb planes); landmark pass: c = bl - sum t, dX = Dinv c
-    for (int s = tid; s < sh.nact; s += BA_THREADS) {
-      const int pi = sh.pidx[ws.slot_pl[s] & 255], lp = ws.slot_lp[s];
-      double t0 = 0, t1 = 0, t2 = 0;
-      if (pi >= 0) {
-        const double* xp = sh.x + 6 * pi;
-#pragma unroll
-        double w[18];
-#pragma unroll
-        for (int c = 0; c < 9; ++c) { const double2 v = CPL2(ws.W)[c * ME + s]; w[2 * c] = v.x; w[2 * c + 1] = v.y; }
-#pragma unroll
-        for (int i = 0; i < 6; ++i) { t0 += w[3 * i] * xp[i]; t1 += w[3 * i + 1] * xp[i]; t2 += w[3 * i + 2] * xp[i]; }
-      }
-      PL2(ws.bb)[lp] = make_double2(t0, t1); PL2(ws.bb)[ME + lp] = make_double2(t2, 0.0);
-    }
-    __syncthreads();
+    // thread per landmark: c = bl - sum_edges W^T x_p with W recomputed per edge (poses are still the linearisation point:
+    // they move after the barrier below; a thread only writes its own landmark), dX = Dinv c
+    const double d2 = delta * delta;
     for (int l = tid; l < L; l += BA_THREADS) {
       double* X = lms + 3 * (size_t)l;
-      ws.lbk[3 * (size_t)l] = X[0]; ws.lbk[3 * (size_t)l + 1] = X[1]; ws.lbk[3 * (size_t)l + 2] = X[2];
+      const double X0[3] = {X[0], X[1], X[2]};
+      ws.lbk[3 * (size_t)l] = X0[0]; ws.lbk[3 * (size_t)l + 1] = X0[1]; ws.lbk[3 * (size_t)l + 2] = X0[2];
       const int j0 = ws.lstart[l], j1 = ws.lstart[l + 1];
       if (j0 == j1) continue;
       const double bl0 = ws.bl[l], bl1 = ws.bl[ML + l], bl2 = ws.bl[2 * ML + l];
       double c0 = bl0, c1 = bl1, c2 = bl2;
-      for (int j = j0; j < j1; ++j) { const double2 v = CPL2(ws.bb)[j], u = CPL2(ws.bb)[ME + j]; c0 -= v.x; c1 -= v.y; c2 -= u.x; }
+      for (int j = j0; j < j1; ++j) {
+        const int p = ws.csr_p[j], pi = sh.pidx[p];
+        if (pi < 0) continue;
+        const double2 q2 = CPL2(ws.luv)[j];
+        const double uv[2] = {q2.x, q2.y};
+        double w[18];
+        edge_W(poses + 7 * p, X0, uv, cam, delta, d2, w);
+        const double* xp = sh.x + 6 * pi;
+        double t0 = 0, t1 = 0, t2 = 0;
+#pragma unroll
+        for (int i = 0; i < 6; ++i) { t0 += w[3 * i] * xp[i]; t1 += w[3 * i + 1] * xp[i]; t2 += w[3 * i + 2] * xp[i]; }
+        c0 -= t0; c1 -= t1; c2 -= t2;
+      }
       const double D0 = ws.Dinv[l], D1 = ws.Dinv[ML + l], D2 = ws.Dinv[2 * ML + l], D3 = ws.Dinv[3 * ML + l],
                    D4 = ws.Dinv[4 * ML + l], D5 = ws.Dinv[5 * ML + l];
       const double x0 = D0 * c0 + D1 * c1 + D2 * c2, x1 = D1 * c0 + D3 * c1 + D4 * c2, x2 = D2 * c0 + D4 * c1 + D5 * c2;
@@ -819,7 +802,7 @@ __host__ __device__ inline size_t poff_capacity() { return (size_t)BA_MAX_CHUNKS
 
 // workspace carve-up (doubles first, then ints); shared by the kernel and ws_stride_bytes()
 struct WsLayout {
-  size_t pbk, lbk, W, luv, bb, uvs, Hll, bl, Dinv, Dv, Ld, n_doubles;
+  size_t pbk, lbk, luv, uvs, Hll, bl, Dinv, Dv, Ld, n_doubles;
   size_t tab, lmask, slot_e, slot_pl, slot_lp, csr_p, lw, lstart, cp_off, poff, pairs, n_ints;
 };
 __host__ __device__ inline WsLayout ws_layout(int MP, int ML, int ME) {
@@ -827,7 +810,7 @@ __host__ __device__ inline WsLayout ws_layout(int MP, int ML, int ME) {
   const size_t E = (size_t)ME, L = (size_t)ML, P = (size_t)MP;
   o.pbk = d; d += 7 * P + (P & 1);
   o.lbk = d; d += 3 * L + (L & 1);
-  o.W = d; d += 18 * E; o.luv = d; d += 2 * E; o.bb = d; d += 4 * E;
+  o.luv = d; d += 2 * E;
   o.uvs = d; d += 2 * E;
   o.Hll = d; d += 6 * L; o.bl = d; d += 3 * L; o.Dinv = d; d += 6 * L; o.Dv = d; d += 3 * L; o.Ld = d; d += 6 * L;
   o.n_doubles = d;
@@ -856,8 +839,8 @@ __global__ void __launch_bounds__(BA_THREADS, 1) ba_kernel(BAArgs a) {
     const WsLayout lo = ws_layout(a.max_poses, a.max_lms, a.max_edges);
     double* d = (double*)(a.ws + (size_t)s * a.ws_stride);
     int* ib = (int*)(d + lo.n_doubles);
-    ws.pbk = d + lo.pbk; ws.lbk = d + lo.lbk; ws.W = d + lo.W; ws.luv = d + lo.luv;
-    ws.bb = d + lo.bb; ws.uvs = d + lo.uvs; ws.Hll = d + lo.Hll; ws.bl = d + lo.bl; ws.Dinv = d + lo.Dinv; ws.Dv = d + lo.Dv; ws.Ld = d + lo.Ld;
+    ws.pbk = d + lo.pbk; ws.lbk = d + lo.lbk; ws.luv = d + lo.luv;
+    ws.uvs = d + lo.uvs; ws.Hll = d + lo.Hll; ws.bl = d + lo.bl; ws.Dinv = d + lo.Dinv; ws.Dv = d + lo.Dv; ws.Ld = d + lo.Ld;
     ws.tab = ib + lo.tab; ws.lmask = (unsigned*)(ib + lo.lmask); ws.slot_e = ib + lo.slot_e; ws.slot_pl = ib + lo.slot_pl; ws.slot_lp = ib + lo.slot_lp; ws.csr_p = ib + lo.csr_p;
     ws.lw = ib + lo.lw; ws.lstart = ib + lo.lstart; ws.cp_off = ib + lo.cp_off; ws.poff = ib + lo.poff;
     ws.pairs = ib + lo.pairs;
@@ -908,11 +891,11 @@ __global__ void __launch_bounds__(BA_THREADS, 1) ba_kernel(BAArgs a) {
       double rho = 0;
       int qmax = 0;
       do {
-        solve_system(pb, lambda, S, y, chunk, ld, ws, sh);
+        solve_system(pb, cam, poses, lms, delta, lambda, S, y, chunk, ld, ws, sh);
         const int ok2 = !sh.fail;
         double scale = 0, tempChi;
         if (ok2) {
-          scale = apply_update(pb, lambda, poses, lms, ws, sh);
+          scale = apply_update(pb, cam, delta, lambda, poses, lms, ws, sh);
           __syncthreads();
           mark(sh, 5);
           tempChi = robust_chi2(cam, poses, lms, delta, ws, sh);
