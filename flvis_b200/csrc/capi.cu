@@ -192,7 +192,11 @@ int flv_upload_images(flv_ctx* ctx, int slot, int n_streams, const uint8_t* imgs
   }
   FLV_CUDA(ctx, cudaStreamWaitEvent(cs, ctx->img_free[ring], 0));        // last unpack that read this landing area
   if (row_stride_bytes == w && img_stride_bytes == w * h) {
-    FLV_CUDA(ctx, cudaMemcpyAsync(st, imgs, bytes, cudaMemcpyHostToDevice, cs));
+    // in pieces: a copy engine serves one request at a time, and small copies of other streams (BA windows, results)
+    // should not queue behind 11 MB of pixels
+    const size_t piece = (size_t)2 << 20;
+    for (size_t o = 0; o < bytes; o += piece)
+      FLV_CUDA(ctx, cudaMemcpyAsync(st + o, imgs + o, bytes - o < piece ? bytes - o : piece, cudaMemcpyHostToDevice, cs));
   } else if (img_stride_bytes == row_stride_bytes * h) {
     FLV_CUDA(ctx, cudaMemcpy2DAsync(st, w, imgs, row_stride_bytes, w, h * (size_t)n_streams, cudaMemcpyHostToDevice, cs));
   } else {
