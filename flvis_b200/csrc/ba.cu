@@ -1029,7 +1029,8 @@ int flv_ba_optimize(flv_ctx* ctx, int n_streams, const flv_ba_problem* problems,
   a.prof = (long long*)(tail + (size_t)ctx->S * (sizeof(flv_ba_problem) + sizeof(flv_ba_stats))) + 16 * slot0;
   a.prm = *prm; a.max_poses = MP; a.max_lms = ML; a.max_edges = ME;
   a.ws = (unsigned char*)ctx->ba_ws + stride * slot0; a.ws_stride = stride;
-  a.dyn_doubles = ba_dyn_doubles();
+  if (!ctx->ba_dyn) ctx->ba_dyn = ba_dyn_doubles();
+  a.dyn_doubles = ctx->ba_dyn;
   const size_t smem = (size_t)a.dyn_doubles * 8;
   const size_t S = n_streams;
   cudaStream_t stream = ctx->ba_stream_set ? ctx->ba_stream : ctx->stream;

@@ -35,6 +35,8 @@ struct flv_ctx {
   int prep_valid, prep_slot, prep_streams, prep_ncorn, prep_dis; double prep_ql;
   void* d_color_stage; size_t color_stage_bytes;   // landing area of interleaved colour uploads
   int equalize; int* d_hist;     // cv::equalizeHist on ingest (flv_set_equalize_hist)
+  int attr_lk3, attr_lk4, attr_region;     // cudaFuncSetAttribute done for this context's device
+  int ba_dyn;                              // cached dynamic shared memory of ba_kernel (doubles)
   int no_fused_ingest;           // FLV_NO_FUSED_INGEST=1: A/B switch for tests
   char err[512];
 

@@ -260,12 +260,11 @@ int flv_launch_lk_v3(flv_ctx* ctx, int src_slot, int dst_slot, int n_streams, co
   }
   g.stream_stride = ctx->geom.stream_stride;
   const size_t smem = (size_t)V3_WARPS * TMPL_WORDS * sizeof(int2);
-  static bool attr = false;
-  if (!attr) {
+  if (!ctx->attr_lk3) {          // per context (= per device): function attributes do not carry across devices
     FLV_CUDA(ctx, cudaFuncSetAttribute(lk_track_kernel_v3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     FLV_CUDA(ctx, cudaFuncSetAttribute(lk_track_kernel_v3, cudaFuncAttributePreferredSharedMemoryCarveout,
                                        getenv("FLV_LK_CARVEOUT") ? atoi(getenv("FLV_LK_CARVEOUT")) : 75));
-    attr = true;
+    ctx->attr_lk3 = 1;
   }
   dim3 grid((ctx->max_pts + V3_WARPS - 1) / V3_WARPS, n_streams);
   const float err_scale = (float)(1.0 / (32 * WIN * WIN));

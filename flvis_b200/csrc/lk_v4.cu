@@ -430,12 +430,11 @@ int flv_launch_lk_v4(flv_ctx* ctx, int src_slot, int dst_slot, int n_streams, co
     ctx->deriv_streams[src_slot] = n_streams;
   }
   const size_t smem = (size_t)V4_WARPS * TMPL_WORDS * sizeof(int2);
-  static bool attr = false;
-  if (!attr) {
+  if (!ctx->attr_lk4) {          // per context (= per device): function attributes do not carry across devices
     FLV_CUDA(ctx, cudaFuncSetAttribute(lk_track_kernel_v4, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     FLV_CUDA(ctx, cudaFuncSetAttribute(lk_track_kernel_v4, cudaFuncAttributePreferredSharedMemoryCarveout,
                                        getenv("FLV_LK_CARVEOUT") ? atoi(getenv("FLV_LK_CARVEOUT")) : 75));
-    attr = true;
+    ctx->attr_lk4 = 1;
   }
   dim3 grid((ctx->max_pts + V4_WARPS - 1) / V4_WARPS, n_streams);
   const float err_scale = (float)(1.0 / (32 * WIN * WIN));

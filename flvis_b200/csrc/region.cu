@@ -260,10 +260,9 @@ region_select_kernel(const uint8_t* __restrict__ img_base, size_t stream_stride,
 int flv_launch_region(flv_ctx* ctx, int slot, int n_streams, const flv_feature_params* prm,
                       int redetect) {
   size_t smem = (size_t)ctx->gftt_cap * (sizeof(Item) + 1);
-  static bool attr_set = false;
-  if (!attr_set) {
+  if (!ctx->attr_region) {          // per context (= per device): function attributes do not carry across devices
     FLV_CUDA(ctx, cudaFuncSetAttribute(region_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_set = true;
+    ctx->attr_region = 1;
   }
   region_select_kernel<<<n_streams, RG_THREADS, smem, ctx->stream>>>(
       ctx->pyr[slot] + ctx->geom.lv[0].off, ctx->geom.stream_stride, ctx->geom.lv[0].pitch, ctx->w,

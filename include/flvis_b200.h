@@ -14,7 +14,9 @@
  *     through pinned buffers and synchronises before returning) or FLV_MEM_DEVICE (device
  *     pointers on ctx's device, work is enqueued on the ctx stream, no synchronisation);
  *   - per-stream arrays are laid out [stream][max_pts] with the ctx's `max_pts` stride;
- *   - images are 8-bit single channel, row-major.
+ *   - images are 8-bit single channel, row-major (flv_upload_color_images converts 3- / 4-channel frames);
+ *   - a context is not thread-safe: one thread drives it at a time (several contexts, e.g. one per camera sequence or
+ *     per GPU, are independent); FLV_MEM_HOST calls return results, FLV_MEM_DEVICE calls only enqueue work.
  */
 #ifndef FLVIS_B200_H
 #define FLVIS_B200_H
