@@ -161,17 +161,29 @@ class DeviceBatch:
                 if not sel:
                     self.groups.append(None)
                     continue
-                idx = torch.tensor(sel, device=self.dev)
                 cp = (capi.BAProblem * len(sel))(*[self.b.cprob[s] for s in sel])
                 h_prob = torch.frombuffer(bytearray(bytes(cp)), dtype=torch.uint8).pin_memory()
+                # one packed blob per group: [poses | lms | stats | uv | ep | el | active] so that a (re)load of the windows
+                # is ONE copy and the read-back of the results ONE copy (they sit in front of / behind every solve)
+                isel = torch.tensor(sel)
+                parts = {k: self.h0[k][isel].contiguous() for k in ("poses", "lms", "uv", "ep", "el", "active")}
+                order = ["poses", "lms", "stats", "uv", "ep", "el", "active"]
+                sizes = {k: v.numel() * v.element_size() for k, v in parts.items()}
+                sizes["stats"] = len(sel) * nstat
+                off, o = {}, 0
+                for k in order:
+                    off[k] = o
+                    o = (o + sizes[k] + 63) & ~63
+                total = o
+                h_blob = torch.zeros(total, dtype=torch.uint8).pin_memory()
+                for k, v in parts.items():
+                    h_blob[off[k]:off[k] + sizes[k]] = v.reshape(-1).view(torch.uint8)
+                d_src = h_blob.to(self.dev)                       # pristine inputs, HBM-resident
+                d_blob = torch.zeros(total, dtype=torch.uint8, device=self.dev)
+                h_res = torch.zeros(off["uv"], dtype=torch.uint8).pin_memory()      # poses | lms | stats
+                ptr = {k: d_blob.data_ptr() + off[k] for k in order}
                 g = {"sel": sel, "d_prob": h_prob.to(self.dev), "prm": capi.BAParams(12, 8, 1.0, 3.0, 0, slot0),
-                     "w": {k: self.d0[k][idx].contiguous() for k in self.d0},
-                     "src": {k: self.d0[k][idx].contiguous() for k in self.d0},
-                     "hsrc": {k: self.h0[k][torch.tensor(sel)].contiguous().pin_memory() for k in self.h0},
-                     "d_stats": torch.zeros(len(sel) * nstat, dtype=torch.uint8, device=self.dev),
-                     "h_stats": torch.zeros(len(sel) * nstat, dtype=torch.uint8).pin_memory(),
-                     "h_poses": torch.zeros(len(sel), self.b.MP, 7, dtype=torch.float64).pin_memory(),
-                     "h_lms": torch.zeros(len(sel), self.b.ML, 3, dtype=torch.float64).pin_memory()}
+                     "h_blob": h_blob, "d_src": d_src, "d_blob": d_blob, "h_res": h_res, "ptr": ptr, "res_bytes": off["uv"]}
                 slot0 += len(sel)      # concurrent launches of different phases use disjoint workspace slots
                 self.groups.append(g)
         return self.groups
@@ -207,17 +219,12 @@ class DeviceBatch:
                 main_stream.wait_stream(st)
 
     def _solve(self, g, mode):
-        w = g["w"]
-        src = g["hsrc"] if mode == "host" else g["src"]
-        for k in w:                                               # (re)load the windows: H2D in e2e mode, D2D otherwise
-            w[k].copy_(src[k], non_blocking=True)
+        g["d_blob"].copy_(g["h_blob"] if mode == "host" else g["d_src"], non_blocking=True)   # (re)load: H2D in e2e mode, D2D otherwise
         n = len(g["sel"])
+        p = g["ptr"]
         self.ctx._chk(self.ctx.lib.flv_ba_optimize(
             self.ctx.h, n, C.cast(C.c_void_p(g["d_prob"].data_ptr()), C.POINTER(capi.BAProblem)), C.byref(g["prm"]),
-            C.c_void_p(w["poses"].data_ptr()), C.c_void_p(w["lms"].data_ptr()), C.c_void_p(w["ep"].data_ptr()),
-            C.c_void_p(w["el"].data_ptr()), C.c_void_p(w["uv"].data_ptr()), C.c_void_p(w["active"].data_ptr()),
-            C.cast(C.c_void_p(g["d_stats"].data_ptr()), C.POINTER(capi.BAStats)), capi.MEM_DEVICE))
+            C.c_void_p(p["poses"]), C.c_void_p(p["lms"]), C.c_void_p(p["ep"]), C.c_void_p(p["el"]), C.c_void_p(p["uv"]),
+            C.c_void_p(p["active"]), C.cast(C.c_void_p(p["stats"]), C.POINTER(capi.BAStats)), capi.MEM_DEVICE))
         if mode == "host":
-            g["h_poses"].copy_(w["poses"], non_blocking=True)
-            g["h_lms"].copy_(w["lms"], non_blocking=True)
-            g["h_stats"].copy_(g["d_stats"], non_blocking=True)
+            g["h_res"].copy_(g["d_blob"][:g["res_bytes"]], non_blocking=True)                 # poses | landmarks | stats
