@@ -38,6 +38,8 @@ class FrontendBench:
         # a dedicated (non-default) torch stream: the library launches on it and all events are recorded on it
         self.stream = torch.cuda.Stream(self.dev)
         self.side = torch.cuda.Stream(self.dev)
+        self.res_stream = torch.cuda.Stream(self.dev)     # result read-back (e2e mode) off the compute stream
+        self.ev_step = torch.cuda.Event()
         self.ev_sel, self.ev_red = torch.cuda.Event(), torch.cuda.Event()
         self.ctx.set_stream(self.stream.cuda_stream)
         self.fp = capi.FeatureParams(int(feature_para[0]), int(feature_para[1]), int(feature_para[2] // 2),
@@ -157,6 +159,8 @@ class FrontendBench:
             ctx.build_pyramid(cur1, S)
         # frame -> frame LK (lkorb_tracking.cpp:64-73) + keep rule (:98-119)
         self._lk(prev0, cur0, self.d_pts, self.d_pts, self.d_next, self.d_status, self.d_err, 10)
+        if mode == "host" and self.pending is not None:
+            self.stream.wait_event(self.done[self.pending])      # the previous frame's read-back precedes the overwrite
         ctx.select_tracked_dev(S, self.d_npts.data_ptr(), self.d_pts.data_ptr(), self.d_next.data_ptr(),
                                self.d_status.data_ptr(), self.d_keep.data_ptr(), self.d_cur.data_ptr(),
                                self.d_cur64.data_ptr())
@@ -176,11 +180,16 @@ class FrontendBench:
         if self.has_ba:
             self.ba.step(i, mode, self.kf_every)
         if mode == "host":
+            # read the frame's results back on their own stream: the compute stream goes straight on to the next frame
+            # (its kernels that overwrite these buffers wait for this copy, see the wait before the keep rule)
             o = self.h_out[i & 1]
-            o["cur"].copy_(self.d_cur, non_blocking=True); o["keep"].copy_(self.d_keep, non_blocking=True)
-            o["right"].copy_(self.d_right, non_blocking=True); o["rstatus"].copy_(self.d_rstatus, non_blocking=True)
-            o["new"].copy_(self.d_new, non_blocking=True); o["nnew"].copy_(self.d_nnew, non_blocking=True)
-            self.done[i & 1].record(self.stream)
+            self.ev_step.record(self.stream)
+            self.res_stream.wait_event(self.ev_step)
+            with self.torch.cuda.stream(self.res_stream):
+                o["cur"].copy_(self.d_cur, non_blocking=True); o["keep"].copy_(self.d_keep, non_blocking=True)
+                o["right"].copy_(self.d_right, non_blocking=True); o["rstatus"].copy_(self.d_rstatus, non_blocking=True)
+                o["new"].copy_(self.d_new, non_blocking=True); o["nnew"].copy_(self.d_nnew, non_blocking=True)
+                self.done[i & 1].record(self.res_stream)
             # submit the NEXT frame's images now (library copy stream: the H2D overlaps this frame's kernels), then
             # consume the PREVIOUS frame's results -- every frame's inputs and outputs cross PCIe, one frame of latency
             k2 = (i + 2) % self.n_pool
