@@ -196,7 +196,9 @@ int flv_f2f_get_frame(flv_f2f* f, double* T_c_w, int64_t* lm_id, double* plane_x
 }
 int flv_f2f_tracking_counts(flv_f2f* f, int* of, int* fi, int* pnp) {
   if (!f) return FLV_ERR_INVALID;
-  if (of) *of = f->impl.last_of_inliers; if (fi) *fi = f->impl.last_f_inliers; if (pnp) *pnp = f->impl.last_pnp_inliers;
+  if (of) *of = f->impl.last_of_inliers;
+  if (fi) *fi = f->impl.last_f_inliers;
+  if (pnp) *pnp = f->impl.last_pnp_inliers;
   return FLV_OK;
 }
 
