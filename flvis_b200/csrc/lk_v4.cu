@@ -245,8 +245,9 @@ __device__ __forceinline__ void build_template(const uint8_t* __restrict__ I, co
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       if (INTERIOR) {
-        bI[j + 1] = icol[(size_t)(j + 1) * pitch];
-        dd[j] = dcol[(size_t)(j + 1) * pitch];
+        const bool used = 4 * k + j + 1 <= WIN;      // image row 32 of the footprint is never blended: do not touch it
+        bI[j + 1] = used ? icol[(size_t)(j + 1) * pitch] : 0u;
+        dd[j] = used ? dcol[(size_t)(j + 1) * pitch] : 0u;
       } else {
         const int y1 = ipy + 4 * k + j + 1;
         bI[j + 1] = icol[(size_t)reflect101(y1, h) * pitch];
