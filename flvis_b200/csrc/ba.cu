@@ -13,17 +13,21 @@
 //                          src/processing/optimize_in_frame.cpp:64-80 (2, cull, <10 edges => fail, 2)
 //
 // Data layout (per stream, fp64; global workspace stays L2-resident, S/b/x + one landmark chunk in shared memory):
-//   active edges get SLOTS ordered (landmark chunk, pose, landmark); every per-edge quantity is a structure-of-arrays
-//   plane indexed by slot (W[18][ME], Bw[12][ME], g[2][ME], hl[6][ME], bb[3][ME], uvs[2][ME]), every per-landmark
-//   quantity a plane indexed by landmark (Hll[6][ML], bl[3][ML], Dinv[6][ML], Dv[3][ML]) -> all passes are coalesced.
+//   active edges get SLOTS ordered (landmark chunk, pose, landmark) and CSR positions ordered (landmark, pose).  Per
+//   edge only the pixel measurement is kept (uvs by slot, luv by CSR position, with csr_p / csr_l); NO Jacobian product
+//   is stored: every pass of this kernel waits on memory, not on the fp64 pipe, so W = rho' B^T A is recomputed from the
+//   state wherever it is needed (the state equals the linearisation point in all those places).  Per-landmark
+//   quantities are planes indexed by landmark (Hll[6][ML], bl[3][ML], Dinv[6][ML], Ld[6][ML], Dv[3][ML]).
 //   tab[p][l] = slot of edge (p,l); lmask[l] = poses observing l (P <= 32); Hd[pi][21], bp[6 pi] in shared memory.
-// Passes per LM trial:
-//   build   thread per slot (residual, Jacobians, W, Bw, g, Hll/bl shares); thread per landmark (Hll, bl sums);
-//           warp per (pose, part) (Hpp diagonal blocks, bp)
-//   Schur   per chunk: stage W planes + Dinv + Dinv*bl in shared memory (coalesced), then warp per pose pair,
-//           two lanes per member landmark, lane-private accumulators, shuffle tree, one writer per block of S
-//   solve   dense Cholesky of the reduced camera system in shared memory (n = 6*(free poses) <= 144)
-//   update  thread per landmark (back-substitution), thread per pose (exp map), chi2 block reduction
+// Passes per LM iteration / trial:
+//   build   thread per landmark over its CSR entries (point Jacobians -> Hll, bl); warp per (pose, part) (Hpp, bp)
+//   Schur   per landmark chunk: stage Z = W chol((Hll + lambda)^-1) and Ld^T bl in shared memory, then warp per pose pair
+//           (tasks drawn dynamically, largest first), ONE lane per member landmark with 36 accumulators, butterfly
+//           reduce-scatter, one writer per block of S
+//   solve   right-looking LDL^T of the reduced camera system in shared memory (n = 6*(free poses) <= 144), one barrier per
+//           column; back substitution inside one warp
+//   update  thread per CSR entry (W^T x_p into the idle chunk area), thread per landmark (back-substitution), thread per
+//           pose (exp map), chi2 block reduction
 // Algorithmic bytes: build 168E+392P+120L, Schur 144E+96L+288Pf^2+48Pf per trial.
 #include "ctx.h"
 
