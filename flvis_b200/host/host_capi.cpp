@@ -149,6 +149,29 @@ int flv_host_undistort_points(const double* K4, const double* D14, const double*
   for (int i = 0; i < n; ++i) flv::undistort_point(m, in_xy[2 * i], in_xy[2 * i + 1], out_xy[2 * i], out_xy[2 * i + 1]);
   return FLV_OK;
 }
+int flv_host_fundamental_ransac(int n, const float* from_xy, const float* to_xy, double thr_px, double conf, uint8_t* mask, double* F9) {
+  if (n < 0 || !from_xy || !to_xy || !mask || !F9) return FLV_ERR_INVALID;
+  std::vector<flv::P2f> a(n), b(n);
+  for (int i = 0; i < n; ++i) { a[i] = flv::P2f{from_xy[2 * i], from_xy[2 * i + 1]}; b[i] = flv::P2f{to_xy[2 * i], to_xy[2 * i + 1]}; }
+  std::vector<uint8_t> m;
+  const bool ok = flv::find_fundamental_ransac(a, b, thr_px, conf, m, F9);
+  for (int i = 0; i < n; ++i) mask[i] = ok ? m[i] : 0;
+  return ok ? 1 : 0;
+}
+int flv_host_pnp_ransac(int n, const float* p3d, const float* p2d, const double* K4, double* T_c_w_inout, int iterations, double thr_px,
+                        double conf, uint8_t* mask) {
+  if (n < 0 || !p3d || !p2d || !K4 || !T_c_w_inout || !mask) return FLV_ERR_INVALID;
+  std::vector<flv::P3f> x(n); std::vector<flv::P2f> u(n);
+  for (int i = 0; i < n; ++i) { x[i] = flv::P3f{p3d[3 * i], p3d[3 * i + 1], p3d[3 * i + 2]}; u[i] = flv::P2f{p2d[2 * i], p2d[2 * i + 1]}; }
+  flv::Pose7 T;
+  for (int k = 0; k < 7; ++k) T[k] = T_c_w_inout[k];
+  std::vector<int> inl;
+  const bool ok = flv::solve_pnp_ransac(x, u, K4, T, iterations, thr_px, conf, inl);
+  for (int i = 0; i < n; ++i) mask[i] = 0;
+  for (int k : inl) mask[k] = 1;
+  for (int k = 0; k < 7; ++k) T_c_w_inout[k] = T[k];
+  return ok ? (int)inl.size() : 0;
+}
 int flv_host_project_points(const double* K4, const double* D14, const double* Rcw9, const double* t3, int n, const float* xyz,
                             float* out_xy) {
   if (!K4 || !D14 || !Rcw9 || !t3 || !xyz || !out_xy || n < 0) return FLV_ERR_INVALID;

@@ -71,6 +71,11 @@ int flv_f2f_set_equalize_hist(flv_f2f* f, int enable);
 /* the two per-point OpenCV calls of the UNRECT path, exported for the parity tests (flvis_b200/host/undistort.h) */
 int flv_host_undistort_points(const double* K4, const double* D14, const double* R9, const double* P12, int n, const float* in_xy,
                               float* out_xy);
+/* the host stand-ins of the two RANSAC calls (flvis_b200/host/ransac.h; selectable instead of the device kernels), exported
+ * for the CPU tests.  Return value: fundamental 1 / 0 (model found), PnP = number of inliers (0 = failed). */
+int flv_host_fundamental_ransac(int n, const float* from_xy, const float* to_xy, double thr_px, double conf, uint8_t* mask, double* F9);
+int flv_host_pnp_ransac(int n, const float* p3d, const float* p2d, const double* K4, double* T_c_w_inout, int iterations, double thr_px,
+                        double conf, uint8_t* mask);
 int flv_host_project_points(const double* K4, const double* D14, const double* Rcw9, const double* t3, int n, const float* xyz,
                             float* out_xy);
 const char* flv_f2f_last_error(flv_f2f* f);
