@@ -67,7 +67,7 @@ MOTION = [(3, 1), (2, -2), (-3, 2), (-2, -1)]     # cumulative motion is periodi
 
 def make_streams(n_streams, seed0, n_frames):
     """Streams with global ids seed0 .. seed0+n_streams-1 (flvis_b200.sharding.stream_seed gives the texture seed)."""
-    from oracle import synth
+    from synthdata import textures as synth
     frames0 = np.empty((n_frames, n_streams, H, W), np.uint8)
     frames1 = np.empty((n_frames, n_streams, H, W), np.uint8)
     for s in range(n_streams):
@@ -287,8 +287,13 @@ def cpu_baseline(n_streams, n_frames, args):
     pts0 = [cv2.goodFeaturesToTrack(f0[0, s], NPTS, 0.01, 10).reshape(-1, 2) for s in range(n_streams)]
     ba = None
     try:
-        from flvis_b200.pipeline import make_ba_batch, cpu_ba_solve
+        from flvis_b200.pipeline import make_ba_batch
+        from oracle import ba_ref                    # the cpu_baseline leg: the one place bench.py executes oracle/
         ba = make_ba_batch(n_streams, BA_WINDOW, seed=7, n_landmarks=BA_LANDMARKS)
+
+        def cpu_ba_solve(batch, s):
+            p = batch.problems[s]
+            ba_ref.optimize(ba_ref.BAData(p.poses.copy(), p.lms.copy(), p.ep, p.el, p.uv, p.K, p.fixed_pose, p.fix_landmarks), 12, 8)
     except Exception:
         ba = None
 

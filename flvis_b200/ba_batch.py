@@ -1,94 +1,10 @@
-"""Synthetic sliding-window BA problems (g2o ba_demo pattern) and their device-side
-batch for bench.py.  Bench/test support, not part of the C ABI product.
-
-Geometry: P keyframes moving along +x looking down +z at a cloud of landmarks 4..12 m away; each landmark
-is seen by a run of consecutive keyframes; 1 px Gaussian pixel noise, a fraction of gross outliers,
-perturbed initial poses / points -- pattern of 3rdPartLib/g2o/g2o/examples/ba/ba_demo.cpp:126-250.
-"""
+"""Batched array form of BA problems for flv_ba_optimize (host and device-resident variants): bench / test support
+around the C ABI.  The problems themselves come from synthdata/ba_problems.py; nothing here touches oracle/."""
 import ctypes as C
 
 import numpy as np
 
 from . import capi
-
-EUROC_K = (458.654, 457.296, 367.215, 248.375)
-
-
-class Problem:
-    def __init__(self, poses, lms, ep, el, uv, K, fixed_pose=0, fix_landmarks=0, gt=None):
-        self.poses, self.lms, self.ep, self.el, self.uv, self.K = poses, lms, ep, el, uv, K
-        self.fixed_pose, self.fix_landmarks, self.gt = fixed_pose, fix_landmarks, gt
-
-    def oracle_data(self):
-        from oracle import ba_ref
-        return ba_ref.BAData(self.poses.copy(), self.lms.copy(), self.ep, self.el, self.uv, self.K, self.fixed_pose,
-                             self.fix_landmarks)
-
-
-def make_problem(window=10, n_landmarks=1500, obs_per_frame=480, seed=0, K=EUROC_K, w=752, h=480, noise_px=1.0,
-                 outlier_frac=0.05, pose_noise=(0.01, 0.03), point_noise=0.05):
-    rng = np.random.default_rng(seed)
-    P = window
-    gt_poses = np.zeros((P, 7)); gt_poses[:, 3] = 1.0
-    gt_poses[:, 4] = -0.12 * np.arange(P)                   # T_c_w translation: camera moves along +x
-    gt_poses[:, 5] = 0.01 * np.sin(np.arange(P))
-    fx, fy, cx, cy = K
-    ep, el, uv, lms = [], [], [], []
-    # landmarks are created until every frame has ~obs_per_frame observations (each seen by 2..P consecutive KFs)
-    counts = np.zeros(P, int)
-    tries = 0
-    while len(lms) < n_landmarks and tries < 50 * n_landmarks:
-        tries += 1
-        first = int(rng.integers(0, P - 1))
-        run = int(rng.integers(2, P + 1))
-        frames = [f for f in range(first, min(P, first + run)) if counts[f] < obs_per_frame]
-        if len(frames) < 2:
-            continue
-        z = rng.uniform(4.0, 12.0)
-        xc = (rng.uniform(40, w - 40) - cx) / fx * z; yc = (rng.uniform(40, h - 40) - cy) / fy * z
-        Xw = np.array([xc - gt_poses[frames[0], 4], yc - gt_poses[frames[0], 5], z])
-        obs = []
-        for f in frames:
-            Xc = Xw + gt_poses[f, 4:7]
-            u = fx * Xc[0] / Xc[2] + cx; v = fy * Xc[1] / Xc[2] + cy
-            if 0 < u < w - 1 and 0 < v < h - 1:
-                obs.append((f, u, v))
-        if len(obs) < 2:
-            continue
-        li = len(lms)
-        lms.append(Xw)
-        for f, u, v in obs:
-            n = rng.normal(0, noise_px, 2) if noise_px > 0 else np.zeros(2)
-            if rng.uniform() < outlier_frac:
-                n = n + rng.uniform(-40, 40, 2)
-            ep.append(f); el.append(li); uv.append((u + n[0], v + n[1])); counts[f] += 1
-    lms = np.array(lms)
-    poses = gt_poses.copy()
-    for p in range(1, P):                                    # pose 0 is the fixed gauge
-        aa = rng.normal(0, pose_noise[0], 3)
-        q = np.concatenate([0.5 * aa, [1.0]]); q /= np.linalg.norm(q)
-        poses[p, :4] = q
-        poses[p, 4:7] += rng.normal(0, pose_noise[1], 3)
-    lms_init = lms + rng.normal(0, point_noise, lms.shape)
-    order = np.lexsort((np.array(el), np.array(ep)))         # keyframe-major = g2o insertion order (vo_localmap.cpp:185-208)
-    return Problem(poses, lms_init, np.array(ep, np.int32)[order], np.array(el, np.int32)[order],
-                   np.array(uv, np.float64)[order], K, gt=(gt_poses, lms))
-
-
-def make_pose_only(n_pts=300, seed=0, K=EUROC_K, w=752, h=480, noise_px=0.7, outlier_frac=0.1):
-    """OptimizeInFrame-shaped problem: one free pose, all points fixed (optimize_in_frame.cpp:35-63)."""
-    rng = np.random.default_rng(seed)
-    fx, fy, cx, cy = K
-    z = rng.uniform(2, 15, n_pts)
-    X = np.stack([(rng.uniform(20, w - 20, n_pts) - cx) / fx * z, (rng.uniform(20, h - 20, n_pts) - cy) / fy * z, z], 1)
-    gt = np.array([[0, 0, 0, 1.0, 0, 0, 0]])
-    uv = np.stack([fx * X[:, 0] / X[:, 2] + cx, fy * X[:, 1] / X[:, 2] + cy], 1) + rng.normal(0, noise_px, (n_pts, 2))
-    bad = rng.uniform(size=n_pts) < outlier_frac
-    uv[bad] += rng.uniform(-30, 30, (int(bad.sum()), 2))
-    aa = rng.normal(0, 0.01, 3); q = np.concatenate([0.5 * aa, [1.0]]); q /= np.linalg.norm(q)
-    pose = np.concatenate([q, rng.normal(0, 0.05, 3)])[None]
-    return Problem(pose, X, np.zeros(n_pts, np.int32), np.arange(n_pts, dtype=np.int32), uv, K, fixed_pose=-1,
-                   fix_landmarks=1, gt=(gt, X))
 
 
 class Batch:
@@ -111,12 +27,10 @@ class Batch:
             self.ep[s, :E] = p.ep; self.el[s, :E] = p.el; self.uv[s, :E] = p.uv; self.active[s, :E] = 1
             self.cprob[s] = capi.BAProblem(len(p.poses), len(p.lms), E, p.fixed_pose, p.fix_landmarks, *p.K)
 
-    def problem(self, s):
-        return self.problems[s].oracle_data()
-
 
 def make_batch(n_streams, window, n_landmarks, obs_per_frame, seed):
-    return Batch([make_problem(window, n_landmarks, obs_per_frame, seed=1000 * seed + s) for s in range(n_streams)])
+    from synthdata import ba_problems
+    return Batch([ba_problems.make_problem(window, n_landmarks, obs_per_frame, seed=1000 * seed + s) for s in range(n_streams)])
 
 
 def solve_batch_host(ctx, batch, prm=None):

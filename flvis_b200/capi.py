@@ -19,6 +19,7 @@ SYMBOLS = [
     "flv_download_level", "flv_lk_track", "flv_select_tracked", "flv_gftt", "flv_download_eig", "flv_gftt_capacity",
     "flv_feature_detect", "flv_feature_redetect", "flv_ba_reserve", "flv_ba_optimize", "flv_gftt_keep_response",
     "flv_ba_profile", "flv_set_ba_stream", "flv_feature_prepare", "flv_set_equalize_hist", "flv_fundamental_ransac", "flv_pnp_ransac", "flv_upload_color_images", "flv_depth_innovation", "flv_reprojection_inliers",
+    "flv_ba_trace", "flv_ba_debug_edges",
 ]
 
 
@@ -84,6 +85,9 @@ def load_library(path=LIB_PATH):
     lib.flv_gftt_capacity.argtypes = [vp]
     lib.flv_gftt_keep_response.argtypes = [vp, C.c_int]
     lib.flv_ba_profile.argtypes = [vp, C.c_int, vp]
+    lib.flv_ba_trace.argtypes = [vp, C.c_int, vp, C.c_int, C.c_int]
+    lib.flv_ba_debug_edges.argtypes = [vp, C.c_int, vp, vp, vp, vp, vp, vp, vp]
+    lib.flv_ba_reserve.argtypes = [vp, C.c_int, C.c_int, C.c_int]
     lib.flv_set_ba_stream.argtypes = [vp, vp, C.c_int]
     lib.flv_level_info.argtypes = [vp, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int),
                                    C.POINTER(C.c_size_t)]
@@ -266,6 +270,23 @@ class Context:
         out = np.zeros(16, np.int64)
         self._chk(self.lib.flv_ba_profile(self.h, stream, _ptr(out)))
         return out
+
+    def ba_trace(self, stream, iterations_run):
+        """Per-iteration LM trace of the last solve: rows of (chi2, lambda, rho, trials)."""
+        out = np.zeros((32, 4))
+        n = self.lib.flv_ba_trace(self.h, stream, _ptr(out), 32, int(iterations_run))
+        if n < 0:
+            self._chk(n)
+        return out[:n]
+
+    def ba_debug_edges(self, poses7, pts3, uv2, K4):
+        """(r, A, B) exactly as ba_kernel evaluates them for n independent edges."""
+        poses7 = np.ascontiguousarray(poses7, np.float64).reshape(-1, 7); n = len(poses7)
+        pts3 = np.ascontiguousarray(pts3, np.float64).reshape(n, 3); uv2 = np.ascontiguousarray(uv2, np.float64).reshape(n, 2)
+        K4 = np.ascontiguousarray(K4, np.float64)
+        r = np.zeros((n, 2)); A = np.zeros((n, 2, 3)); B = np.zeros((n, 2, 6))
+        self._chk(self.lib.flv_ba_debug_edges(self.h, n, _ptr(poses7), _ptr(pts3), _ptr(uv2), _ptr(K4), _ptr(r), _ptr(A), _ptr(B)))
+        return r, A, B
 
     def download_eig(self, stream):
         out = np.empty((self.hh, self.w), np.float32)

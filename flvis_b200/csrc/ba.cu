@@ -38,6 +38,7 @@ constexpr int BA_WARPS = BA_THREADS / 32;
 constexpr int BA_MAX_POSES = 32;
 constexpr int BA_MAX_FREE = 24;          // reduced system n <= 144 -> S fits shared memory
 constexpr unsigned FULL = 0xffffffffu;
+constexpr int BA_TRACE_ITERS = 32;       // per-iteration debug trace rows kept per stream (flv_ba_trace)
 
 struct BAArgs {
   const flv_ba_problem* problems;
@@ -48,6 +49,7 @@ struct BAArgs {
   int max_poses, max_lms, max_edges;
   unsigned char* ws; size_t ws_stride;
   long long* prof;   // [S][8] cycle counters or nullptr
+  double* trace;     // [S][BA_TRACE_ITERS][4] per LM iteration: chi2 at the end, lambda, rho of the last trial, trials
   int dyn_doubles;   // dynamic shared memory of the launch, in doubles
 };
 
@@ -944,6 +946,10 @@ __global__ void __launch_bounds__(BA_THREADS, 1) ba_kernel(BAArgs a) {
         }
         ++qmax;
       } while (rho < 0 && qmax < 10);
+      if (a.trace && tid == 0 && st.iterations_run < BA_TRACE_ITERS) {
+        double* tr = a.trace + ((size_t)s * BA_TRACE_ITERS + st.iterations_run) * 4;
+        tr[0] = currentChi; tr[1] = lambda; tr[2] = rho; tr[3] = (double)qmax;
+      }
       ++st.iterations_run;
       if (qmax == 10 || rho == 0 || !isfinite(lambda)) break;
     }
@@ -971,6 +977,17 @@ __global__ void __launch_bounds__(BA_THREADS, 1) ba_kernel(BAArgs a) {
     a.stats[s] = st;
     if (a.prof) for (int i = 0; i < 16; ++i) a.prof[16 * s + i] = sh.prof[i];
   }
+}
+
+__global__ void ba_debug_edges_kernel(int n, const double* poses, const double* pts, const double* uv, Cam cam, double* out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double r[2], A[6], B[12];
+  edge_eval<true>(poses + 7 * (size_t)i, pts + 3 * (size_t)i, uv + 2 * (size_t)i, cam, r, A, B);
+  double* o = out + 20 * (size_t)i;
+  o[0] = r[0]; o[1] = r[1];
+  for (int k = 0; k < 6; ++k) o[2 + k] = A[k];
+  for (int k = 0; k < 12; ++k) o[8 + k] = B[k];
 }
 
 size_t ws_stride_bytes(int max_poses, int max_lms, int max_edges) {
@@ -1002,10 +1019,18 @@ int flv_ba_reserve(flv_ctx* ctx, int max_poses, int max_landmarks, int max_edges
   if (max_poses > BA_MAX_POSES)
     FLV_FAIL(ctx, FLV_ERR_UNSUPPORTED, "window of %d poses: this build supports <= %d (<= %d free poses)", max_poses,
              BA_MAX_POSES, BA_MAX_FREE);
+  // already large enough: nothing to do (the host tracker reserves per frame; a realloc would synchronise the device)
+  if (ctx->ba_ws && max_poses <= ctx->ba_max_poses && max_landmarks <= ctx->ba_max_lms && max_edges <= ctx->ba_max_edges) return FLV_OK;
+  if (ctx->ba_ws) {                        // grow: keep the union of the old and new capacities
+    max_poses = max_poses > ctx->ba_max_poses ? max_poses : ctx->ba_max_poses;
+    max_landmarks = max_landmarks > ctx->ba_max_lms ? max_landmarks : ctx->ba_max_lms;
+    max_edges = max_edges > ctx->ba_max_edges ? max_edges : ctx->ba_max_edges;
+    FLV_CUDA(ctx, cudaDeviceSynchronize());
+  }
   flv_ba_free(ctx);
   size_t stride = ws_stride_bytes(max_poses, max_landmarks, max_edges);
   // tail: device copies of problems / stats / staging are carved after the per-stream blocks
-  size_t total = stride * ctx->S + (size_t)ctx->S * (sizeof(flv_ba_problem) + sizeof(flv_ba_stats) + 128) + 512;
+  size_t total = stride * ctx->S + (size_t)ctx->S * (sizeof(flv_ba_problem) + sizeof(flv_ba_stats) + 128 + BA_TRACE_ITERS * 32) + 512;
   FLV_CUDA(ctx, cudaMalloc(&ctx->ba_ws, total));
   ctx->ba_ws_bytes = total;
   ctx->ba_max_poses = max_poses; ctx->ba_max_lms = max_landmarks; ctx->ba_max_edges = max_edges;
@@ -1031,6 +1056,7 @@ int flv_ba_optimize(flv_ctx* ctx, int n_streams, const flv_ba_problem* problems,
   flv_ba_stats* d_stats = (flv_ba_stats*)(tail + (size_t)ctx->S * sizeof(flv_ba_problem)) + slot0;
   BAArgs a;
   a.prof = (long long*)(tail + (size_t)ctx->S * (sizeof(flv_ba_problem) + sizeof(flv_ba_stats))) + 16 * slot0;
+  a.trace = (double*)(tail + (size_t)ctx->S * (sizeof(flv_ba_problem) + sizeof(flv_ba_stats) + 128)) + (size_t)BA_TRACE_ITERS * 4 * slot0;
   a.prm = *prm; a.max_poses = MP; a.max_lms = ML; a.max_edges = ME;
   a.ws = (unsigned char*)ctx->ba_ws + stride * slot0; a.ws_stride = stride;
   if (!ctx->ba_dyn) ctx->ba_dyn = ba_dyn_doubles();
@@ -1095,6 +1121,45 @@ int flv_ba_profile(flv_ctx* ctx, int stream, long long* out16) {
   long long* d = (long long*)(tail + (size_t)ctx->S * (sizeof(flv_ba_problem) + sizeof(flv_ba_stats)));
   FLV_CUDA(ctx, cudaDeviceSynchronize());
   FLV_CUDA(ctx, cudaMemcpy(out16, d + 16 * stream, 128, cudaMemcpyDeviceToHost));
+  return FLV_OK;
+}
+
+/* debug: per-iteration LM trace of the last flv_ba_optimize for `stream`: out[it][4] = {robust chi2 after the iteration,
+ * lambda after it, rho of its last trial, trials}; returns the rows written (<= cap_iters, <= 32). */
+int flv_ba_trace(flv_ctx* ctx, int stream, double* out, int cap_iters, int iterations_run) {
+  if (!ctx || !ctx->ba_ws || !out || stream < 0 || stream >= ctx->S || cap_iters < 0) return FLV_ERR_INVALID;
+  const size_t stride = ws_stride_bytes(ctx->ba_max_poses, ctx->ba_max_lms, ctx->ba_max_edges);
+  unsigned char* tail = (unsigned char*)ctx->ba_ws + stride * ctx->S;
+  const double* d = (const double*)(tail + (size_t)ctx->S * (sizeof(flv_ba_problem) + sizeof(flv_ba_stats) + 128)) + (size_t)BA_TRACE_ITERS * 4 * stream;
+  int n = iterations_run < BA_TRACE_ITERS ? iterations_run : BA_TRACE_ITERS;
+  n = n < cap_iters ? n : cap_iters;
+  FLV_CUDA(ctx, cudaDeviceSynchronize());
+  if (n > 0) FLV_CUDA(ctx, cudaMemcpy(out, d, (size_t)n * 32, cudaMemcpyDeviceToHost));
+  return n;
+}
+
+/* debug: the kernel's own residual and analytic Jacobians (EdgeSE3ProjectXYZ::computeError / linearizeOplus as ba_kernel
+ * evaluates them) for n independent (pose, point, measurement) triples: r[n][2], A[n][2][3] = dr/dpoint,
+ * B[n][2][6] = dr/dpose (rotation first).  Host arrays; synchronises. */
+int flv_ba_debug_edges(flv_ctx* ctx, int n, const double* poses7, const double* pts3, const double* uv2, const double* K4,
+                       double* r, double* A, double* B) {
+  if (!ctx || n < 1 || !poses7 || !pts3 || !uv2 || !K4 || !r || !A || !B) return FLV_ERR_INVALID;
+  const size_t in_b = (size_t)n * (7 + 3 + 2) * 8, out_b = (size_t)n * (2 + 6 + 12) * 8;
+  int rc = flv_stage_reserve(ctx, in_b + out_b + 64);
+  if (rc) return rc;
+  double* hs = (double*)ctx->h_stage; double* ds = (double*)ctx->d_stage;
+  memcpy(hs, poses7, (size_t)n * 56); memcpy(hs + 7 * (size_t)n, pts3, (size_t)n * 24); memcpy(hs + 10 * (size_t)n, uv2, (size_t)n * 16);
+  FLV_CUDA(ctx, cudaMemcpyAsync(ds, hs, in_b, cudaMemcpyHostToDevice, ctx->stream));
+  const Cam cam = {K4[0], K4[1], K4[2], K4[3]};
+  ba_debug_edges_kernel<<<(n + 127) / 128, 128, 0, ctx->stream>>>(n, ds, ds + 7 * (size_t)n, ds + 10 * (size_t)n, cam, ds + 12 * (size_t)n);
+  ctx->launches++;
+  FLV_CUDA(ctx, cudaGetLastError());
+  FLV_CUDA(ctx, cudaMemcpyAsync(hs + 12 * (size_t)n, ds + 12 * (size_t)n, out_b, cudaMemcpyDeviceToHost, ctx->stream));
+  FLV_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  const double* o = hs + 12 * (size_t)n;
+  for (int i = 0; i < n; ++i) {
+    memcpy(r + 2 * i, o + 20 * (size_t)i, 16); memcpy(A + 6 * i, o + 20 * (size_t)i + 2, 48); memcpy(B + 12 * i, o + 20 * (size_t)i + 8, 96);
+  }
   return FLV_OK;
 }
 

@@ -48,14 +48,18 @@ int flv_localmap_add_keyframe(flv_localmap* lm, int64_t frame_id, int n, const i
   return 1;
 }
 
-struct flv_vimotion { flv::VIMOTION impl; explicit flv_vimotion(const flv::VIMOTION& v) : impl(v) {} };
+struct flv_vimotion {
+  flv::VIMOTION impl;
+  flv_vimotion(const flv::SE3& T_i_c, double g, double p1, double p2, double p3, double p4, double p5, double p6)
+      : impl(T_i_c, g, p1, p2, p3, p4, p5, p6) {}
+};
 
 static flv::SE3 se3_from7(const double* p) { return flv::SE3(flv::Quat{p[3], p[0], p[1], p[2]}, flv::Vec3{p[4], p[5], p[6]}); }
 static void se3_to7(const flv::SE3& T, double* p) { p[0] = T.q.x; p[1] = T.q.y; p[2] = T.q.z; p[3] = T.q.w; p[4] = T.t[0]; p[5] = T.t[1]; p[6] = T.t[2]; }
 
 flv_vimotion* flv_vimotion_create(const double* T_i_c, double g, double p1, double p2, double p3, double p4, double p5, double p6) {
   if (!T_i_c) return nullptr;
-  return new (std::nothrow) flv_vimotion(flv::VIMOTION(se3_from7(T_i_c), g, p1, p2, p3, p4, p5, p6));
+  return new (std::nothrow) flv_vimotion(se3_from7(T_i_c), g, p1, p2, p3, p4, p5, p6);
 }
 void flv_vimotion_destroy(flv_vimotion* vm) { delete vm; }
 int flv_vimotion_imu_feed(flv_vimotion* vm, double t, const double* acc, const double* gyro, double* q, double* pos, double* vel) {
@@ -216,6 +220,14 @@ int flv_f2f_get_frame(flv_f2f* f, double* T_c_w, int64_t* lm_id, double* plane_x
     if (is_inlier) is_inlier[i] = lm.is_tracking_inlier;
   }
   return n;
+}
+int flv_f2f_get_imu_bias(flv_f2f* f, double* acc_bias, double* gyro_bias) {
+  if (!f || !f->impl.vimotion) return FLV_ERR_INVALID;
+  for (int k = 0; k < 3; ++k) {
+    if (acc_bias) acc_bias[k] = f->impl.vimotion->acc_bias[k];
+    if (gyro_bias) gyro_bias[k] = f->impl.vimotion->gyro_bias[k];
+  }
+  return f->impl.has_imu ? 1 : 0;
 }
 int flv_f2f_tracking_counts(flv_f2f* f, int* of, int* fi, int* pnp) {
   if (!f) return FLV_ERR_INVALID;

@@ -39,6 +39,7 @@ Quat VIMOTION::madgwick_qdot(const Quat& q_prev, const Vec3& acc, const Vec3& gy
 }
 
 void VIMOTION::viIMUinitialization(const IMUSTATE imu_read, Quat& q_w_i, Vec3& pos_w_i, Vec3& vel_w_i) {   // :34-115
+  std::lock_guard<std::recursive_mutex> lock(mtx_states_RW);
   q_w_i = Quat{1, 0, 0, 0};
   pos_w_i = vel_w_i = Vec3{0, 0, 0};
   init_state.imu_data = imu_read;
@@ -66,6 +67,7 @@ void VIMOTION::viIMUinitialization(const IMUSTATE imu_read, Quat& q_w_i, Vec3& p
 }
 
 void VIMOTION::viVisiontrigger(Quat& init_orientation) {                                                    // :117-137
+  std::lock_guard<std::recursive_mutex> lock(mtx_states_RW);
   MOTION_STATE state = states.back();
   state.pos = Vec3{0, 0, 0}; state.vel = Vec3{0, 0, 0};
   Vec3 rpy = Q2rpy(state.q_w_i);
@@ -77,6 +79,7 @@ void VIMOTION::viVisiontrigger(Quat& init_orientation) {                        
 }
 
 void VIMOTION::viIMUPropagation(const IMUSTATE imu_read, Quat& q_w_i, Vec3& pos_w_i, Vec3& vel_w_i) {      // :139-209
+  std::lock_guard<std::recursive_mutex> lock(mtx_states_RW);
   MOTION_STATE s_new;
   const Vec3 acc = sub3(imu_read.acc_raw, acc_bias), gyro = sub3(imu_read.gyro_raw, gyro_bias);
   const MOTION_STATE s_prev = states.back();
@@ -107,6 +110,7 @@ bool VIMOTION::viFindStateIdx(const double time, int& idx_in_q) {               
 
 void VIMOTION::viCorrectionFromVision(const double t_curr, const SE3 Tcw_curr, const double t_last, const SE3 Tcw_last,
                                       const double /*err*/) {                                               // :212-342
+  std::lock_guard<std::recursive_mutex> lock(mtx_states_RW);
   Vec3 acc_bias_est{0, 0, 0}, gyro_bias_est{0, 0, 0};
   int idx_curr, idx_last, idx_mid;
   if (viFindStateIdx(t_last, idx_last) && viFindStateIdx(t_curr, idx_curr)) {
@@ -160,6 +164,7 @@ void VIMOTION::viCorrectionFromVision(const double t_curr, const SE3 Tcw_curr, c
 }
 
 bool VIMOTION::viGetIMURollPitchAtTime(const double time, double& roll, double& pitch) {                    // :386-406
+  std::lock_guard<std::recursive_mutex> lock(mtx_states_RW);
   int idx;
   if (viFindStateIdx(time, idx)) {
     const SE3 T_w_i(states.at(idx).q_w_i, states.at(idx).pos);
@@ -171,11 +176,13 @@ bool VIMOTION::viGetIMURollPitchAtTime(const double time, double& roll, double& 
 }
 
 void VIMOTION::viGetLatestImuState(SE3& T_w_i, Vec3& vel) {
+  std::lock_guard<std::recursive_mutex> lock(mtx_states_RW);
   T_w_i = SE3(states.back().q_w_i, states.back().pos);
   vel = states.back().vel;
 }
 
 bool VIMOTION::viGetCorrFrameState(const double time, SE3& T_c_w) {                                         // :416-435
+  std::lock_guard<std::recursive_mutex> lock(mtx_states_RW);
   int idx;
   if (viFindStateIdx(time, idx)) {
     const SE3 T_w_i(states.at(idx).q_w_i, states.at(idx).pos);

@@ -5,6 +5,7 @@
 // decay terms).  Sequential, a few hundred flops per 200 Hz sample: it stays on the host.
 #pragma once
 #include <deque>
+#include <mutex>
 #include "sophus_lite.h"
 
 namespace flv {
@@ -37,6 +38,11 @@ class VIMOTION {
   void viVisionRPCompensation(const double time, SE3& T_c_w);
 
  private:
+  // imu_feed runs on other threads than image_feed (ROS callback threads in the reference): `states`, the biases and
+  // the init flags are guarded like the reference's mtx_states_RW (vi_motion.cpp:119-131, :150-205, :220-339, :390-433);
+  // the reference leaves viIMUinitialization unguarded (:34-115), here it takes the lock too.  Recursive because
+  // viVisionRPCompensation -> viGetIMURollPitchAtTime nests.
+  mutable std::recursive_mutex mtx_states_RW;
   Quat madgwick_qdot(const Quat& q_prev, const Vec3& acc, const Vec3& gyro, double gain) const;
 };
 

@@ -15,15 +15,8 @@ from . import capi
 
 def make_ba_batch(n_streams, window, seed=0, n_landmarks=1500, obs_per_frame=480):
     """Synthetic local-BA windows (ba_demo pattern, SURVEY.md 8(d) C1: W=10, E=4800, L~1500)."""
-    from . import ba_synth
-    return ba_synth.make_batch(n_streams, window, n_landmarks, obs_per_frame, seed)
-
-
-def cpu_ba_solve(batch, s):
-    """One local-BA solve of stream s with the CPU oracle port (bench cpu_baseline leg only)."""
-    from oracle import ba_ref
-    p = batch.problem(s)
-    ba_ref.optimize(p.copy(), 12, 8)
+    from . import ba_batch
+    return ba_batch.make_batch(n_streams, window, n_landmarks, obs_per_frame, seed)
 
 
 class FrontendBench:
@@ -79,8 +72,8 @@ class FrontendBench:
             import os
             if os.environ.get("FLV_BENCH_NO_BA"):          # diagnostic only: frontend alone under bench conditions
                 raise ImportError
-            from . import ba_synth
-            self.ba = ba_synth.DeviceBatch(self.ctx, make_ba_batch(n_streams, ba_window, seed=seed, n_landmarks=ba_landmarks), self.dev)
+            from . import ba_batch
+            self.ba = ba_batch.DeviceBatch(self.ctx, make_ba_batch(n_streams, ba_window, seed=seed, n_landmarks=ba_landmarks), self.dev)
             self.has_ba = True
         except ImportError:
             self.ba = None

@@ -246,6 +246,16 @@ int flv_set_ba_stream(flv_ctx* ctx, void* cuda_stream, int enable);
  * out16 = {chi2, build pose pass, schur products, cholesky, substitution, update, setup, -, schur init, schur staging,
  * build edge pass, build landmark pass, -...}. Synchronises. */
 int flv_ba_profile(flv_ctx* ctx, int stream, long long* out16);
+/* Debug: Levenberg-Marquardt trace of the last flv_ba_optimize for `stream`, one row per iteration (both phases, in order):
+ * out[it][4] = {robustified chi2 at the end of the iteration, lambda after it, rho of its last trial, trials used}
+ * (optimization_algorithm_levenberg.cpp:58-150).  `iterations_run` = flv_ba_stats.iterations_run of that solve.
+ * Returns the number of rows written (<= cap_iters, <= 32).  Synchronises. */
+int flv_ba_trace(flv_ctx* ctx, int stream, double* out, int cap_iters, int iterations_run);
+/* Debug: residual + analytic Jacobians exactly as ba_kernel evaluates them (EdgeSE3ProjectXYZ::computeError /
+ * linearizeOplus, types_six_dof_expmap.cpp:389-433) for n independent (pose[7], point[3], uv[2]) triples:
+ * r[n][2], A[n][2][3] = d r / d point, B[n][2][6] = d r / d pose (rotation first, then translation).  Host arrays. */
+int flv_ba_debug_edges(flv_ctx* ctx, int n, const double* poses7, const double* pts3, const double* uv2, const double* K4,
+                       double* r, double* A, double* B);
 
 #ifdef __cplusplus
 }

@@ -86,6 +86,8 @@ int flv_f2f_state(flv_f2f* f);     /* 0 UnInit, 1 Tracking, 2 TrackingFail */
 /* landmarks of the current frame (after image_feed): returns the count (<= cap) */
 int flv_f2f_get_frame(flv_f2f* f, double* T_c_w, int64_t* lm_id, double* plane_xy, double* undist_xy, double* p3d_w,
                       uint8_t* has_3d, uint8_t* is_inlier, int cap);
+/* VIMOTION::acc_bias / gyro_bias of the tracker's IMU filter (vi_motion.cpp:322-330); returns has_imu */
+int flv_f2f_get_imu_bias(flv_f2f* f, double* acc_bias, double* gyro_bias);
 int flv_f2f_tracking_counts(flv_f2f* f, int* of_inliers, int* f_inliers, int* pnp_inliers);
 
 #ifdef __cplusplus

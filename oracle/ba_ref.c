@@ -316,6 +316,12 @@ static void setup_active(ba_ws* w) {
   free(pedges);
 }
 
+/* optional per-iteration trace for the tests: rows of {chi2 at the end of the iteration, lambda, rho of the last trial,
+ * trials}; set with oracle_ba_set_trace before a solve, rows accumulate over both optimize() phases */
+static double* g_trace = 0; static int g_trace_cap = 0, g_trace_n = 0;
+void oracle_ba_set_trace(double* buf, int cap_rows) { g_trace = buf; g_trace_cap = cap_rows; g_trace_n = 0; }
+int oracle_ba_trace_rows(void) { return g_trace_n; }
+
 /* g2o SparseOptimizer::optimize(iters) with OptimizationAlgorithmLevenberg; returns iterations run */
 static int lm_optimize(ba_ws* w, int iters, double* lambda_out, double* chi_out) {
   const oracle_ba_problem* pb = w->pb;
@@ -367,6 +373,10 @@ static int lm_optimize(ba_ws* w, int iters, double* lambda_out, double* chi_out)
       }
       qmax++;
     } while (rho < 0 && qmax < 10);
+    if (g_trace && g_trace_n < g_trace_cap) {
+      double* tr = g_trace + 4 * g_trace_n++;
+      tr[0] = currentChi; tr[1] = lambda; tr[2] = rho; tr[3] = (double)qmax;
+    }
     done++;
     chi_last = currentChi;
     if (qmax == 10 || rho == 0 || !isfinite(lambda)) break;   /* Terminate */

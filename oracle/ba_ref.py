@@ -44,9 +44,15 @@ def _p(a):
     return a.ctypes.data_as(C.c_void_p)
 
 
-def optimize(d, iters1=12, iters2=8, huber_delta=1.0, cull_chi2=3.0, min_edges_after_cull=0):
-    """In-place local BA on BAData `d` (12 it, cull chi2>3, 8 it by default). Returns Stats."""
+def optimize(d, iters1=12, iters2=8, huber_delta=1.0, cull_chi2=3.0, min_edges_after_cull=0, trace=None):
+    """In-place local BA on BAData `d` (12 it, cull chi2>3, 8 it by default). Returns Stats.
+    trace: optional list that receives one (chi2, lambda, rho, trials) tuple per LM iteration (not thread-safe)."""
     lib = helpers_lib()
+    tbuf = None
+    if trace is not None:
+        tbuf = np.zeros((iters1 + iters2 + 2, 4))
+        lib.oracle_ba_set_trace.argtypes = [C.c_void_p, C.c_int]
+        lib.oracle_ba_set_trace(_p(tbuf), len(tbuf))
     lib.oracle_ba_optimize.argtypes = [C.POINTER(Problem), C.c_int, C.c_int, C.c_double, C.c_double, C.c_int,
                                        C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                        C.POINTER(Stats)]
@@ -54,6 +60,10 @@ def optimize(d, iters1=12, iters2=8, huber_delta=1.0, cull_chi2=3.0, min_edges_a
     st = Stats()
     lib.oracle_ba_optimize(C.byref(pb), iters1, iters2, huber_delta, cull_chi2, min_edges_after_cull, _p(d.poses),
                            _p(d.lms), _p(d.ep), _p(d.el), _p(d.uv), _p(d.active), C.byref(st))
+    if trace is not None:
+        n = lib.oracle_ba_trace_rows()
+        lib.oracle_ba_set_trace(None, 0)
+        trace.extend(tuple(r) for r in tbuf[:n])
     return st
 
 

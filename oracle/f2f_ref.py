@@ -3,7 +3,7 @@ CameraFrame glue -- TEST INFRASTRUCTURE (oracle).
 
 Follows /root/reference/src/frontend/f2f_tracking.cpp:5-453, src/processing/lkorb_tracking.cpp:9-202,
 optimize_in_frame.cpp:10-90, camera_frame.cpp (via oracle/camera_frame_ref.py), landmark.cpp:3-44.
-OpenCV calls: LK = oracle/lk_ref.py (bit-exact contract of the CUDA kernel; cv2 itself is <= 1e-3 px away),
+OpenCV calls: LK = oracle/lk_ref.py through its C twin oracle/lk_ref.c (bit-identical, fast; bit-exact contract of the CUDA kernel; cv2 itself is <= 1e-3 px away),
 FeatureDEM = oracle/feature_dem_ref.py, findFundamentalMat / solvePnPRansac = cv2 (the reference's real library).
 Sensor types: "depth" (DEPTH_D435), "stereo" (STEREO_RECT, zero distortion) and "stereo_unrect" (STEREO_UNRECT: LK on the
 raw images, cv2.undistortPoints / cv2.projectPoints per point with the raw lens models `lens0` / `lens1` =
@@ -112,7 +112,7 @@ class F2FTracking:
                     if l.has_3d:
                         pc = cf.world2camera(f32(l.p3d_w).astype(np.float64), T1)
                         init[i] = (f32(self.K1[0] * pc[0] / pc[2] + self.K1[2]), f32(self.K1[1] * pc[1] / pc[2] + self.K1[3]))
-            nxt, st, _ = lk_ref.calc_optical_flow_pyr_lk(fr.img0, fr.img1, prev, init, max_level=5)
+            nxt, st, _ = lk_ref.calc_optical_flow_pyr_lk_c(fr.img0, fr.img1, prev, init, max_level=5)
             if self.cam_type == "stereo_unrect":
                 nxt = self._undist(self.lens1, self.P1, nxt)
             cf.depth_innovation(F, self.iir, self.range, self.dummy, self.rnd, stereo=(nxt.astype(np.float64), st))
@@ -146,7 +146,7 @@ class F2FTracking:
                 pc = cf.world2camera(fp3[i].astype(np.float64), guess)
                 px = cf.camera2pixel(pc, self.K)
                 tplane[i] = (f32(px[0]), f32(px[1]))
-        nxt, st, _ = lk_ref.calc_optical_flow_pyr_lk(frm.img0, to.img0, fplane, tplane, max_level=10)
+        nxt, st, _ = lk_ref.calc_optical_flow_pyr_lk_c(frm.img0, to.img0, fplane, tplane, max_level=10)
         tplane = nxt
         tund = self._undist(self.lens0, self.P0, tplane) if self.cam_type == "stereo_unrect" else tplane.copy()
         to.lms = []
@@ -316,7 +316,7 @@ def fmat_cv2(from_xy, to_xy):
 def make_stereo_sequence(n_frames, seed=0, w=640, h=480, K=(384.16455, 384.16455, 320.21445, 238.94403), Z=3.0, baseline=0.05):
     """Rectified stereo views of the same fronto-parallel plane: right image = left image shifted by the constant
     disparity fx*b/Z.  Returns (left images, right images, P0, P1, T_cam1_cam0 as SE3)."""
-    from . import synth
+    from synthdata import textures as synth
     margin = 96
     canvas = synth.texture(seed, h + 2 * margin, w + 2 * margin, blur=2)
     lefts, rights = [], []
@@ -339,7 +339,7 @@ def make_stereo_sequence(n_frames, seed=0, w=640, h=480, K=(384.16455, 384.16455
 def make_depth_sequence(n_frames, seed=0, w=640, h=480, K=(384.16455, 384.16455, 320.21445, 238.94403), Z=3.0):
     """Fronto-parallel textured plane at depth Z seen by a camera that translates parallel to it and rolls slightly:
     the image motion is an exact similarity, the depth image is constant (mm)."""
-    from . import synth
+    from synthdata import textures as synth
     margin = 96
     canvas = synth.texture(seed, h + 2 * margin, w + 2 * margin, blur=2)
     imgs, depths = [], []

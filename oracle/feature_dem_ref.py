@@ -24,8 +24,7 @@ def helpers_lib():
     global _LIB
     if _LIB is None:
         path = os.path.join(_HERE, "_build", "liboracle_helpers.so")
-        if not os.path.exists(path):
-            subprocess.check_call(["make", "-s", "-C", _HERE])
+        subprocess.check_call(["make", "-s", "-C", _HERE])     # no-op when up to date; rebuilds a stale helper library
         _LIB = ctypes.CDLL(path)
     return _LIB
 

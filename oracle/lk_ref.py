@@ -199,3 +199,24 @@ def calc_optical_flow_pyr_lk(prev_img, next_img, prev_pts, init_pts, win=31, max
     if return_iters:
         return nxt, status, errs, iters
     return nxt, status, errs
+
+
+def calc_optical_flow_pyr_lk_c(prev_img, next_img, prev_pts, init_pts, win=31, max_level=10, max_iter=30, eps=1e-3,
+                               min_eig_thr=1e-4):
+    """The same restatement compiled from oracle/lk_ref.c (bit-identical outputs, ~1000x faster): used where a test has
+    to run hundreds of frames live.  tests/test_oracle_cpu.py pins it to calc_optical_flow_pyr_lk above."""
+    import ctypes as C
+    from .feature_dem_ref import helpers_lib
+    lib = helpers_lib()
+    lib.lk_ref_track.restype = C.c_int
+    lib.lk_ref_track.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
+                                 C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double]
+    I = np.ascontiguousarray(prev_img, np.uint8); J = np.ascontiguousarray(next_img, np.uint8)
+    assert I.shape == J.shape and I.ndim == 2
+    p = np.ascontiguousarray(prev_pts, f32).reshape(-1, 2); q = np.ascontiguousarray(init_pts, f32).reshape(-1, 2)
+    n = len(p)
+    out = np.zeros((n, 2), f32); st = np.zeros(n, np.uint8); err = np.zeros(n, f32)
+    vp = lambda a: a.ctypes.data_as(C.c_void_p)
+    lib.lk_ref_track(vp(I), vp(J), I.shape[1], I.shape[0], n, vp(p), vp(q), vp(out), vp(st), vp(err), win, max_level,
+                     max_iter, float(eps), float(min_eig_thr))
+    return out, st, err

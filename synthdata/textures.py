@@ -34,6 +34,21 @@ def texture(seed, h, w, blur=2, passes=3):
     return ((a - lo) * 255 // max(hi - lo, 1)).astype(np.uint8)
 
 
+def texture_multiscale(seed, h, w, blurs=(2, 6, 16), weights=(2, 3, 4)):
+    """uint8 texture with structure at several scales (sum of blurred noise fields): coarse pyramid levels keep
+    gradients, so large displacements (KITTI-sized disparities) are trackable."""
+    rng = np.random.default_rng(seed)
+    acc = np.zeros((h, w), np.int64)
+    for b, wt in zip(blurs, weights):
+        a = rng.integers(0, 256, (h, w), dtype=np.int64) * 256
+        for _ in range(3):
+            a = _box_blur_int(a, b)
+        lo, hi = int(a.min()), int(a.max())
+        acc += wt * ((a - lo) * 1024 // max(hi - lo, 1))
+    lo, hi = int(acc.min()), int(acc.max())
+    return ((acc - lo) * 255 // max(hi - lo, 1)).astype(np.uint8)
+
+
 def warp_affine(canvas, A, out_h, out_w):
     """out(y,x) = bilinear(canvas at A @ [x,y,1]) rounded to uint8; A is 2x3 (dst -> src), float64."""
     ys, xs = np.mgrid[0:out_h, 0:out_w].astype(np.float64)

@@ -3,7 +3,7 @@ import glob
 import os
 import numpy as np
 
-from oracle import synth
+from synthdata import textures as synth
 
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 

@@ -15,7 +15,7 @@ import cv2
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, os.path.join(HERE, "..", ".."))
-from oracle import synth  # noqa: E402
+from synthdata import textures as synth  # noqa: E402
 
 LK_CASES = [
     # name, seed, (h,w), shift, rot, scale, npts, max_level

@@ -1,0 +1,198 @@
+"""Drives flv::F2FTracking (C handle, GPU) and oracle/f2f_ref.py side by side over a BASELINE-shaped sequence
+(oracle/sequences.py): IMU samples first, then the image pair, exactly the order TrackingNodeletClass delivers them
+(/root/reference/src/frontend/vo_tracking.cpp:326-371, :387-429); optional local map chained on the keyframes
+(vo_localmap.cpp:87-380).  Shared by tests/test_configs_gpu.py."""
+import ctypes as C
+
+import cv2
+import numpy as np
+
+from oracle import f2f_ref, localmap_ref
+from oracle.vimotion_ref import SE3 as OSE3, q2R
+
+from .test_pipeline_gpu import Cfg, _cam_centre, _setup, fmat_hook, pnp_hook
+
+STATE = {0: "UnInit", 1: "Tracking", 2: "TrackingFail"}
+
+
+def _vp(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def _c(vals, n):
+    return (C.c_double * n)(*[float(v) for v in vals])
+
+
+def stereo_rectify(cfg, T_c1_c0):
+    """cv::stereoRectify as vo_tracking.cpp:236-247 calls it (CALIB_ZERO_DISPARITY, alpha 0, same size)."""
+    K0 = np.array([[cfg["K0"][0], 0, cfg["K0"][2]], [0, cfg["K0"][1], cfg["K0"][3]], [0, 0, 1.0]])
+    K1 = np.array([[cfg["K1"][0], 0, cfg["K1"][2]], [0, cfg["K1"][1], cfg["K1"][3]], [0, 0, 1.0]])
+    D0, D1 = np.array(cfg["D0"]), np.array(cfg["D1"])
+    size = (cfg["w"], cfg["h"])
+    R0, R1, P0, P1, _, _, _ = cv2.stereoRectify(K0, D0, K1, D1, size, q2R(T_c1_c0.q), T_c1_c0.t.reshape(3, 1),
+                                                flags=cv2.CALIB_ZERO_DISPARITY, alpha=0, newImageSize=size)
+    return K0, D0, R0, P0, K1, D1, R1, P1
+
+
+def make_pair(lib, seq, hooks=True):
+    """-> (C tracker handle, oracle tracker) configured like TrackingNodeletClass::onInit does for the sequence's sensor."""
+    _setup(lib)
+    lib.flv_f2f_set_lens.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.flv_f2f_set_equalize_hist.argtypes = [C.c_void_p, C.c_int]
+    lib.flv_f2f_imu_feed.argtypes = [C.c_void_p, C.c_double, C.c_void_p, C.c_void_p]
+    lib.flv_f2f_get_imu_bias.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+    c = seq.cfg
+    Ti = seq.T_i_c0.to7()
+    T_i_c0 = OSE3.from7(Ti)                                   # the oracle's own SE3 type (arithmetic of sophus, not synthdata's)
+    if seq.cam_type == "depth":
+        K = c["K0"]
+        cfg = Cfg(0, c["w"], c["h"], _c(K, 4), _c(K, 4), c["depth_factor"], (C.c_double * 12)(), (C.c_double * 12)(),
+                  _c([0, 0, 0, 1, 0, 0, 0], 7), _c(Ti, 7), _c(c["feature_para"], 6), _c(c["vi_para"], 6), _c(c["dc_para"], 3), c["skip"])
+        h = lib.flv_f2f_create(C.byref(cfg), 0)
+        ref = f2f_ref.F2FTracking("depth", c["w"], c["h"], K, c["feature_para"], c["vi_para"], c["dc_para"], T_i_c=T_i_c0,
+                                  skip=c["skip"], depth_scale=c["depth_factor"])
+    elif seq.cam_type == "stereo_unrect":
+        T10 = OSE3.from7(seq.T_c0_c1.to7()).inverse()
+        K0, D0, R0, P0, K1, D1, R1, P1 = stereo_rectify(c, T10)
+        K = (P0[0, 0], P0[1, 1], P0[0, 2], P0[1, 2]); Kr1 = (P1[0, 0], P1[1, 1], P1[0, 2], P1[1, 2])     # depth_camera.cpp:76-84
+        cfg = Cfg(2, c["w"], c["h"], _c(K, 4), _c(Kr1, 4), 1000.0, _c(P0.ravel(), 12), _c(P1.ravel(), 12), _c(T10.to7(), 7),
+                  _c(Ti, 7), _c(c["feature_para"], 6), _c(c["vi_para"], 6), _c(c["dc_para"], 3), 0)
+        h = lib.flv_f2f_create(C.byref(cfg), 0)
+        d14 = lambda D: np.concatenate([D, np.zeros(14 - len(D))])
+        for cam, (Kr, D, Rr) in enumerate([(K0, D0, R0), (K1, D1, R1)]):
+            k4 = np.array([Kr[0, 0], Kr[1, 1], Kr[0, 2], Kr[1, 2]])
+            assert lib.flv_f2f_set_lens(h, cam, _vp(k4), _vp(d14(D)), _vp(np.ascontiguousarray(Rr).ravel())) == 0
+        assert lib.flv_f2f_set_equalize_hist(h, 1) == 0                       # vo_tracking.cpp:257-263: need_equal_hist = true
+        ref = f2f_ref.F2FTracking("stereo_unrect", c["w"], c["h"], K, c["feature_para"], c["vi_para"], c["dc_para"],
+                                  T_i_c=T_i_c0, K1=Kr1, P0=P0, P1=P1, T_c1_c0=T10, lens0=(K0, D0, R0), lens1=(K1, D1, R1),
+                                  equalize=True)
+    else:
+        K = c["K0"]
+        P0 = np.array([[K[0], 0, K[2], 0], [0, K[1], K[3], 0], [0, 0, 1, 0.0]]); P1 = P0.copy(); P1[0, 3] = -c["bf"]
+        T10 = OSE3.from7(seq.T_c0_c1.to7()).inverse()
+        cfg = Cfg(1, c["w"], c["h"], _c(K, 4), _c(K, 4), 1000.0, _c(P0.ravel(), 12), _c(P1.ravel(), 12), _c(T10.to7(), 7),
+                  _c(Ti, 7), _c(c["feature_para"], 6), _c(c["vi_para"], 6), _c(c["dc_para"], 3), 0)
+        h = lib.flv_f2f_create(C.byref(cfg), 0)
+        ref = f2f_ref.F2FTracking("stereo", c["w"], c["h"], K, c["feature_para"], c["vi_para"], c["dc_para"], K1=K, P0=P0, P1=P1,
+                                  T_c1_c0=T10)
+    assert h and lib.flv_f2f_last_error(h) == b"", lib.flv_f2f_last_error(h)
+    if hooks:
+        lib.flv_f2f_set_ransac_hooks(h, fmat_hook, pnp_hook, None)
+    return h, ref, K
+
+
+class LocalMapPair:
+    """flv::LocalMap (C handle) next to oracle/localmap_ref.LocalMap, fed with the tracker's keyframes."""
+
+    def __init__(self, window, K):
+        from flvis_b200 import capi
+        self.capi = capi
+        self.ctx = capi.Context(1, 64, 64)
+        cl = self.ctx.lib
+        cl.flv_localmap_create.restype = C.c_void_p
+        cl.flv_localmap_create.argtypes = [C.c_void_p, C.c_int] + [C.c_double] * 4
+        cl.flv_localmap_destroy.argtypes = [C.c_void_p]
+        cl.flv_localmap_add_keyframe.argtypes = [C.c_void_p, C.c_int64, C.c_int] + [C.c_void_p] * 4 + [C.c_void_p] * 5 + \
+            [C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.POINTER(capi.BAStats)]
+        self.lm = cl.flv_localmap_create(self.ctx.h, window, *[float(v) for v in K])
+        assert self.lm
+        self.ref = localmap_ref.LocalMap(window, K)
+        self.n_solved = 0
+        self.max_dt = 0.0
+
+    def add(self, frame_id, ids, und, p3, T, ref_kf, tol_t=1e-5, tol_lm=1e-4):
+        cl = self.ctx.lib
+        o = self.ref.frame_callback(ref_kf)
+        fid = np.zeros(1, np.int64); oT = np.zeros(7); nlm = np.zeros(1, np.int32); olm = np.zeros(16384, np.int64)
+        o3 = np.zeros((16384, 3)); nout = np.zeros(1, np.int32); oout = np.zeros(16384, np.int64)
+        st = self.capi.BAStats()
+        rc = cl.flv_localmap_add_keyframe(self.lm, int(frame_id), len(ids), _vp(ids), _vp(und), _vp(p3), _vp(T), _vp(fid), _vp(oT),
+                                          _vp(nlm), _vp(olm), _vp(o3), 16384, _vp(nout), _vp(oout), 16384, C.byref(st))
+        if o is None:
+            assert rc == 0, cl.flv_last_error(self.ctx.h)
+            return
+        assert rc == 1, cl.flv_last_error(self.ctx.h)
+        self.n_solved += 1
+        assert fid[0] == o["frame_id"] and list(olm[:nlm[0]]) == o["lm_id"]
+        assert sorted(oout[:nout[0]]) == sorted(o["outlier_id"])
+        self.max_dt = max(self.max_dt, float(np.abs(oT[4:] - o["T_c_w"][4:]).max()))
+        assert np.abs(oT[4:] - o["T_c_w"][4:]).max() <= tol_t
+        if nlm[0]:
+            assert np.abs(o3[:nlm[0]] - o["lm_3d"]).max() <= tol_lm * max(1.0, float(np.abs(o["lm_3d"]).max()))
+
+    def close(self):
+        self.ctx.lib.flv_localmap_destroy(self.lm)
+        self.ctx.close()
+
+
+def run_sequence(lib, seq, tol_pose=1e-6, tol_und=0.0, tol_p3=1e-6, window=None, hooks=True):
+    """Frame-by-frame comparison; returns a summary dict (trajectories, state history, counters)."""
+    h, ref, K = make_pair(lib, seq, hooks)
+    lmap = LocalMapPair(window, K) if window else None
+    cap = 600
+    out = dict(states=[], kf=0, reset=0, guess_used=0, traj=[], traj_ref=[], traj_gt=[], max_dpose=0.0, frames_tracked=0)
+    for k, (t, img0, img1, imu) in enumerate(seq.frames()):
+        for (ti, acc, gyro) in imu:
+            a = np.ascontiguousarray(acc); g = np.ascontiguousarray(gyro)
+            assert lib.flv_f2f_imu_feed(h, float(ti), _vp(a), _vp(g)) == 0
+            ref.imu_feed(float(ti), acc, gyro)
+        was_tracking = ref.state == "Tracking"
+        if was_tracking and ref.has_imu and ref.vim.corr_frame_state(t) is not None:
+            out["guess_used"] += 1
+        kf = C.c_int(0); rs = C.c_int(0)
+        rc = lib.flv_f2f_image_feed(h, float(t), _vp(np.ascontiguousarray(img0)), _vp(np.ascontiguousarray(img1)), C.byref(kf), C.byref(rs))
+        assert rc == 0, lib.flv_f2f_last_error(h)
+        rkf, rrs = ref.image_feed(float(t), img0, img1)
+        state = STATE[lib.flv_f2f_state(h)]
+        assert state == ref.state and bool(kf.value) == rkf and bool(rs.value) == rrs, (k, state, ref.state, kf.value, rkf)
+        out["states"].append(state); out["kf"] += int(rkf); out["reset"] += int(rrs)
+        T = np.zeros(7); ids = np.zeros(cap, np.int64); pl = np.zeros((cap, 2)); un = np.zeros((cap, 2)); p3 = np.zeros((cap, 3))
+        has = np.zeros(cap, np.uint8); inl = np.zeros(cap, np.uint8)
+        n = lib.flv_f2f_get_frame(h, _vp(T), _vp(ids), _vp(pl), _vp(un), _vp(p3), _vp(has), _vp(inl), cap)
+        cur = ref.curr
+        assert n == len(cur.lms), (k, n, len(cur.lms))
+        assert list(ids[:n]) == [l.lm_id for l in cur.lms], k                       # landmark ids + order: bit-exact
+        assert list(inl[:n].astype(bool)) == [bool(l.inlier) for l in cur.lms], k
+        assert list(has[:n].astype(bool)) == [bool(l.has_3d) for l in cur.lms], k
+        if n:
+            assert np.array_equal(pl[:n], np.array([l.plane for l in cur.lms])), k    # LK pixel positions: bit-exact
+            assert np.abs(un[:n] - np.array([l.undist for l in cur.lms])).max() <= tol_und, k
+            r3 = np.array([l.p3d_w for l in cur.lms])
+            assert np.abs(p3[:n] - r3).max() <= tol_p3 * max(1.0, float(np.abs(r3).max())), k
+        rT = cur.T_c_w.to7()
+        dpose = max(float(np.abs(T[4:] - rT[4:]).max()), 2 * float(np.arccos(min(1.0, abs(float(np.dot(T[:4], rT[:4])))))))
+        out["max_dpose"] = max(out["max_dpose"], dpose)
+        assert dpose <= tol_pose, (k, dpose)
+        if state == "Tracking":
+            out["frames_tracked"] += 1
+            out["traj"].append(_cam_centre(T)); out["traj_ref"].append(_cam_centre(rT))
+            out["traj_gt"].append(np.asarray(seq.T_w_c0(t).t, float))
+            if was_tracking:
+                of = C.c_int(); fi = C.c_int(); pn = C.c_int()
+                lib.flv_f2f_tracking_counts(h, C.byref(of), C.byref(fi), C.byref(pn))
+                assert (of.value, fi.value, pn.value) == ref.counts, k
+        if lmap is not None and rkf:
+            sel = (has[:n] == 1) & (inl[:n] == 1)                                   # CameraFrame::getKeyFrameInf
+            kids = np.ascontiguousarray(ids[:n][sel]); kuv = np.ascontiguousarray(un[:n][sel]); k3 = np.ascontiguousarray(p3[:n][sel])
+            rsel = [l for l in cur.lms if l.has_3d and l.inlier]
+            okf = {"frame_id": cur.frame_id, "lm_id": [l.lm_id for l in rsel], "lm_2d": np.array([l.undist for l in rsel]),
+                   "lm_3d": np.array([l.p3d_w for l in rsel]), "T_c_w": rT}
+            lmap.add(cur.frame_id, kids, kuv, k3, T, okf)
+    ab = np.zeros(3); gb = np.zeros(3)
+    out["has_imu"] = lib.flv_f2f_get_imu_bias(h, _vp(ab), _vp(gb))
+    out["acc_bias"], out["gyro_bias"] = ab, gb
+    out["ref_acc_bias"], out["ref_gyro_bias"] = ref.vim.acc_bias.copy(), ref.vim.gyro_bias.copy()
+    out["final_state"] = ref.state
+    if lmap is not None:
+        out["n_solved"] = lmap.n_solved; out["localmap_max_dt"] = lmap.max_dt
+        lmap.close()
+    lib.flv_f2f_destroy(h)
+    traj, traj_ref, gt = np.array(out["traj"]), np.array(out["traj_ref"]), np.array(out["traj_gt"])
+    out["ate_vs_ref"] = float(np.sqrt(np.mean(np.sum((traj - traj_ref) ** 2, axis=1))))
+    out["path"] = float(np.sum(np.linalg.norm(np.diff(traj_ref, axis=0), axis=1)))
+    # ATE of each path against the synthetic ground truth after removing the constant world-frame offset (the tracker's
+    # world starts at its first pose): BASELINE's "ATE within 1 % of the reference"
+    d = traj - gt; dr = traj_ref - gt
+    out["ate_gt"] = float(np.sqrt(np.mean(np.sum((d - d.mean(0)) ** 2, axis=1))))
+    out["ate_gt_ref"] = float(np.sqrt(np.mean(np.sum((dr - dr.mean(0)) ** 2, axis=1))))
+    return out

@@ -4,7 +4,8 @@ the oracle-contract floats are bit-exact; positions vs cv2 itself within 1e-3 px
 import numpy as np
 import pytest
 
-from oracle import lk_ref, gftt_ref, feature_dem_ref, synth
+from oracle import lk_ref, gftt_ref, feature_dem_ref
+from synthdata import textures as synth
 from tests import cases
 
 pytestmark = pytest.mark.gpu

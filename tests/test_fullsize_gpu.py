@@ -4,7 +4,8 @@ domain, plus spot checks of a few streams against the oracle."""
 import numpy as np
 import pytest
 
-from oracle import lk_ref, gftt_ref, synth
+from oracle import lk_ref, gftt_ref
+from synthdata import textures as synth
 
 pytestmark = pytest.mark.gpu
 
@@ -98,12 +99,14 @@ def test_gftt_invariants_all_streams(world):
 def test_ba_full_batch_reduces_chi2_and_recovers_poses():
     """32 EuRoC-sized windows (W=10, ~4.6k edges) in one launch: chi2 drops by > 10x, the culled fraction matches the
     noise model, pose errors are at the centimetre level, and stream 0 matches the fp64 oracle."""
-    from flvis_b200 import capi, ba_synth
+    from flvis_b200 import capi, ba_batch
     from oracle import ba_ref
-    probs = [ba_synth.make_problem(window=10, n_landmarks=1500, obs_per_frame=480, seed=50 + s) for s in range(S)]
-    batch = ba_synth.Batch(probs)
+    from synthdata import ba_problems
+    from .util import oracle_data
+    probs = [ba_problems.make_problem(window=10, n_landmarks=1500, obs_per_frame=480, seed=50 + s) for s in range(S)]
+    batch = ba_batch.Batch(probs)
     ctx = capi.Context(S, W, H)
-    poses, lms, active, stats = ba_synth.solve_batch_host(ctx, batch)
+    poses, lms, active, stats = ba_batch.solve_batch_host(ctx, batch)
     for s in range(S):
         assert stats[s].ok == 1 and stats[s].iterations_run == 20
         assert stats[s].chi2_final < 0.1 * stats[s].chi2_initial
@@ -111,7 +114,7 @@ def test_ba_full_batch_reduces_chi2_and_recovers_poses():
         assert 0.08 < frac < 0.4
         gt_poses = probs[s].gt[0]
         assert np.abs(poses[s, :len(gt_poses), 4:] - gt_poses[:, 4:]).max() < 0.2     # 1 px noise, 10 m scene (oracle: 0.01 .. 0.10)
-    d = probs[0].oracle_data()
+    d = oracle_data(probs[0])
     st = ba_ref.optimize(d, 12, 8)
     assert st.n_culled == stats[0].n_culled
     assert np.abs(poses[0, :d.poses.shape[0]] - d.poses).max() < 1e-6

@@ -2,16 +2,17 @@
 import sys, os, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
-from flvis_b200 import capi, ba_synth
+from flvis_b200 import capi, ba_batch
+from synthdata import ba_problems
 
 W = int(sys.argv[1]) if len(sys.argv) > 1 else 10
 S = int(sys.argv[2]) if len(sys.argv) > 2 else 1
-probs = [ba_synth.make_problem(window=W, n_landmarks=1500 if W <= 10 else 2000, obs_per_frame=480, seed=2 + s) for s in range(S)]
-batch = ba_synth.Batch(probs)
+probs = [ba_problems.make_problem(window=W, n_landmarks=1500 if W <= 10 else 2000, obs_per_frame=480, seed=2 + s) for s in range(S)]
+batch = ba_batch.Batch(probs)
 ctx = capi.Context(S, 752, 480)
 for rep in range(2):
     t = time.perf_counter()
-    poses, lms, active, stats = ba_synth.solve_batch_host(ctx, batch)
+    poses, lms, active, stats = ba_batch.solve_batch_host(ctx, batch)
     dt = time.perf_counter() - t
 names = ["chi2", "build:pose", "schur:prod", "cholesky", "subst", "update", "setup", "-", "schur:init", "schur:stage", "build:edge", "build:lm", "-", "-", "-", "-"]
 pr = ctx.ba_profile(0)
