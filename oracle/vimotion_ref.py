@@ -98,6 +98,20 @@ class SE3:
         return np.array([self.q[1], self.q[2], self.q[3], self.q[0], *self.t])
 
 
+def dot(a, b):
+    """left-to-right sum of products, the order the C++ expressions use (np.dot / `@` go through BLAS kernels whose
+    summation order and FMA use differ in the last bit)."""
+    r = a[0] * b[0]
+    for i in range(1, len(a)):
+        r = r + a[i] * b[i]
+    return float(r)
+
+
+def mat3_vec(R, v):
+    return np.array([R[0, 0] * v[0] + R[0, 1] * v[1] + R[0, 2] * v[2], R[1, 0] * v[0] + R[1, 1] * v[1] + R[1, 2] * v[2],
+                     R[2, 0] * v[0] + R[2, 1] * v[1] + R[2, 2] * v[2]])
+
+
 def q1_multi_q2(q1, q2):
     return np.array([q2[0] * q1[0] - q2[1] * q1[1] - q2[2] * q1[2] - q2[3] * q1[3],
                      q2[1] * q1[0] + q2[0] * q1[1] + q2[3] * q1[2] - q2[2] * q1[3],
@@ -122,7 +136,7 @@ class VIMOTION:
 
     def _qdot(self, q_prev, acc, gyro, gain):
         qdot = scalar_multi_q(0.5, q1_multi_q2(q_prev, np.array([0, gyro[0], gyro[1], gyro[2]])))
-        an = math.sqrt(float(acc @ acc))
+        an = math.sqrt(dot(acc, acc))
         if (an - self.g) < 0.3:
             ax, ay, az = acc[0] / an, acc[1] / an, acc[2] / an
             qw, qx, qy, qz = q_prev
@@ -131,7 +145,7 @@ class VIMOTION:
                 2 * qw * (ay + 2 * qw * qx + 2 * qy * qz) + 2 * qz * (ax - 2 * qw * qy + 2 * qx * qz) - 4 * qx * (-2 * qx * qx - 2 * qy * qy + az + 1),
                 2 * qz * (ay + 2 * qw * qx + 2 * qy * qz) - 2 * qw * (ax - 2 * qw * qy + 2 * qx * qz) - 4 * qy * (-2 * qx * qx - 2 * qy * qy + az + 1),
                 2 * qx * (ax - 2 * qw * qy + 2 * qx * qz) + 2 * qy * (ay + 2 * qw * qx + 2 * qy * qz)])
-            s = s * math.sqrt(float(s @ s))
+            s = s * math.sqrt(dot(s, s))
             qdot = qdot - gain * s
         return qdot
 
@@ -141,7 +155,7 @@ class VIMOTION:
         if not self.imu_initialized:
             q_out = np.array([1.0, 0, 0, 0]); z = np.zeros(3)
             if self.is_first:
-                if (math.sqrt(float(acc @ acc)) - self.g) < 0.3:
+                if (math.sqrt(dot(acc, acc)) - self.g) < 0.3:
                     rpy = np.array([math.atan2(-acc[1], -acc[2]), math.atan2(acc[0], -acc[2]), 0.0])
                     q = rpy2Q(rpy)
                     self._push(dict(pos=z.copy(), vel=z.copy(), q=q, t=t))
@@ -162,7 +176,7 @@ class VIMOTION:
         qd = self._qdot(sp["q"], acc, gyro, self.p1)
         qnew = qn(sp["q"] + scalar_multi_q(dt, qd))
         pos = sp["pos"] + sp["vel"] * dt
-        vel = sp["vel"] + ((R @ acc) - self.gravity) * dt
+        vel = sp["vel"] + (mat3_vec(R, acc) - self.gravity) * dt
         self._push(dict(pos=pos, vel=vel, q=qnew, t=t))
         return qnew, pos, vel
 
@@ -197,7 +211,7 @@ class VIMOTION:
         T_w_iA = Tcw_last.inverse() * self.T_c_i; T_w_iB = Tcw_curr.inverse() * self.T_c_i
         T_w_ia = SE3(st[il]["q"], st[il]["pos"]); T_w_ib = SE3(st[ic]["q"], st[ic]["pos"]); T_w_im = SE3(st[im]["q"], st[im]["pos"])
         T_iB_iA = T_w_iB.inverse() * T_w_iA; T_ib_ia = T_w_ib.inverse() * T_w_ia
-        qb = T_ib_ia.q; n2 = float(qb @ qb)
+        qb = T_ib_ia.q; n2 = dot(qb, qb)
         qbi = np.array([qb[0] / n2, -qb[1] / n2, -qb[2] / n2, -qb[3] / n2])
         QBb = qmul(T_iB_iA.q, qbi)
         gyro_est = np.array([QBb[1] / dt, QBb[2] / dt, QBb[3] / dt])
@@ -208,18 +222,18 @@ class VIMOTION:
         vel_imu = vel_imu * (1.0 / cnt)
         vel_vis = (T_w_iB.t - T_w_iA.t) / dt
         dvw = vel_vis - vel_imu
-        qm = T_w_im.q; m2 = float(qm @ qm)
+        qm = T_w_im.q; m2 = dot(qm, qm)
         Rm = q2R(np.array([qm[0] / m2, -qm[1] / m2, -qm[2] / m2, -qm[3] / m2]))
-        acc_est = -(Rm @ dvw) / dt
+        acc_est = -mat3_vec(Rm, dvw) / dt
         T_diff = T_w_iB * T_w_ib.inverse()
         for i in range(ic, len(st)):
             nT = T_diff * SE3(st[i]["q"], st[i]["pos"])
             st[i]["q"] = nT.q; st[i]["pos"] = nT.t; st[i]["vel"] = st[i]["vel"] + dvw
         if math.isnan(acc_est[0]): acc_est = np.zeros(3)
         if math.isnan(gyro_est[0]): gyro_est = np.zeros(3)
-        ban = math.sqrt(float(acc_est @ acc_est))
+        ban = math.sqrt(dot(acc_est, acc_est))
         if ban > self.ba_sat: acc_est = acc_est * (self.ba_sat / ban)
-        bwn = math.sqrt(float(gyro_est @ gyro_est))
+        bwn = math.sqrt(dot(gyro_est, gyro_est))
         if ban > self.bw_sat: gyro_est = gyro_est * (self.bw_sat / bwn)
         if dt < 0.1:
             self.acc_bias = (1 - self.p3) * self.acc_bias + self.p3 * acc_est

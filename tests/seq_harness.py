@@ -125,7 +125,7 @@ class LocalMapPair:
         self.ctx.close()
 
 
-def run_sequence(lib, seq, tol_pose=1e-6, tol_und=0.0, tol_p3=1e-6, window=None, hooks=True):
+def run_sequence(lib, seq, tol_pose=1e-6, tol_und=0.0, tol_p3=1e-6, window=None, hooks=True, tol_px=0.0):
     """Frame-by-frame comparison; returns a summary dict (trajectories, state history, counters)."""
     h, ref, K = make_pair(lib, seq, hooks)
     lmap = LocalMapPair(window, K) if window else None
@@ -155,8 +155,13 @@ def run_sequence(lib, seq, tol_pose=1e-6, tol_und=0.0, tol_p3=1e-6, window=None,
         assert list(inl[:n].astype(bool)) == [bool(l.inlier) for l in cur.lms], k
         assert list(has[:n].astype(bool)) == [bool(l.has_3d) for l in cur.lms], k
         if n:
-            assert np.array_equal(pl[:n], np.array([l.plane for l in cur.lms])), k    # LK pixel positions: bit-exact
-            assert np.abs(un[:n] - np.array([l.undist for l in cur.lms])).max() <= tol_und, k
+            rpl = np.array([l.plane for l in cur.lms])
+            if tol_px == 0.0:
+                assert np.array_equal(pl[:n], rpl), k                                 # LK pixel positions: bit-exact
+            else:                                                                     # IMU-guess runs: stated float tolerance
+                out["max_dpx"] = max(out.get("max_dpx", 0.0), float(np.abs(pl[:n] - rpl).max()))
+                assert np.abs(pl[:n] - rpl).max() <= tol_px, (k, float(np.abs(pl[:n] - rpl).max()))
+            assert np.abs(un[:n] - np.array([l.undist for l in cur.lms])).max() <= tol_und + tol_px, k
             r3 = np.array([l.p3d_w for l in cur.lms])
             assert np.abs(p3[:n] - r3).max() <= tol_p3 * max(1.0, float(np.abs(r3).max())), k
         rT = cur.T_c_w.to7()

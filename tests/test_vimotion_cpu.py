@@ -41,11 +41,11 @@ def test_vimotion_matches_oracle_sample_by_sample(lib):
         rc = lib.flv_vimotion_imu_feed(h, float(t[i]), vp(a), vp(g), vp(q), vp(p), vp(v))
         rq, rp, rv = ref.imu_feed(float(t[i]), acc[i], gyro[i])
         assert rc == (1 if ref.imu_initialized else 0)
-        assert np.abs(q - rq).max() < 1e-12 and np.abs(p - rp).max() < 1e-10 and np.abs(v - rv).max() < 1e-10
+        assert np.array_equal(q, rq) and np.array_equal(p, rp) and np.array_equal(v, rv)
         if ref.imu_initialized and not triggered and i > 60:
             qt = np.zeros(4)
             assert lib.flv_vimotion_vision_trigger(h, vp(qt)) == 0
-            assert np.abs(qt - ref.vision_trigger()).max() < 1e-12
+            assert np.array_equal(qt, ref.vision_trigger())
             assert lib.flv_vimotion_queue_size(h) == 1
             triggered = True
         # a "vision" pose every 10 samples (20 Hz): the IMU-predicted camera pose, nudged
@@ -56,12 +56,12 @@ def test_vimotion_matches_oracle_sample_by_sample(lib):
             assert found == (1 if rT is not None else 0)
             if rT is None:
                 continue
-            assert np.abs(T - rT.to7()).max() < 1e-10
+            assert np.array_equal(T, rT.to7())
             vis = rT.to7().copy(); vis[4:] += np.array([0.002, -0.001, 0.0015]) * np.sin(i)
             T2 = vis.copy()
             lib.flv_vimotion_rp_compensation(h, float(t[i]) + 1e-4, vp(T2))
             r2 = ref.rp_compensation(float(t[i]) + 1e-4, vr.SE3.from7(vis))
-            assert np.abs(T2 - r2.to7()).max() < 1e-10
+            assert np.array_equal(T2, r2.to7())
             if last_vis is not None:
                 lib.flv_vimotion_correction(h, float(t[i]) + 1e-4, vp(T2), last_vis[0], vp(last_vis[1]))
                 ref.correction_from_vision(float(t[i]) + 1e-4, vr.SE3.from7(T2), last_vis[0], vr.SE3.from7(last_vis[1]))
@@ -71,4 +71,52 @@ def test_vimotion_matches_oracle_sample_by_sample(lib):
             last_vis = (float(t[i]) + 1e-4, T2.copy())
     assert triggered and last_vis is not None
     assert np.abs(ref.acc_bias).max() > 0                      # the bias feedback path was exercised
+    lib.flv_vimotion_destroy(h)
+
+
+def test_vimotion_is_safe_under_concurrent_imu_and_vision_threads(lib):
+    """imu_feed runs on other threads than image_feed in the reference (ROS callback threads, vo_tracking.cpp:326-371), so
+    VIMOTION guards `states` with mtx_states_RW (vi_motion.cpp:119-205, :220-339, :390-433).  ctypes releases the GIL: the
+    feeder thread and the vision-side calls really run concurrently here."""
+    import threading
+    lib = _lib(lib)
+    T_i_c7 = np.array([0.0, 0.0, 0.7071067811865476, 0.7071067811865476, -0.02, -0.06, 0.01])
+    h = lib.flv_vimotion_create(vp(T_i_c7), 9.81, 0.1, 0.01, 0.001, 0.001, 0.5, 0.1)
+    t, acc, gyro = vr.synth_imu(6000, seed=5)
+    q = np.zeros(4); p = np.zeros(3); v = np.zeros(3)
+    for i in range(60):
+        lib.flv_vimotion_imu_feed(h, float(t[i]), vp(np.ascontiguousarray(acc[i])), vp(np.ascontiguousarray(gyro[i])), vp(q), vp(p), vp(v))
+    qt = np.zeros(4)
+    assert lib.flv_vimotion_vision_trigger(h, vp(qt)) == 0
+    now = [60]
+    stop = threading.Event()
+
+    def feeder():
+        q2 = np.zeros(4); p2 = np.zeros(3); v2 = np.zeros(3)
+        for i in range(60, len(t)):
+            a = np.ascontiguousarray(acc[i]); g = np.ascontiguousarray(gyro[i])
+            lib.flv_vimotion_imu_feed(h, float(t[i]), vp(a), vp(g), vp(q2), vp(p2), vp(v2))
+            now[0] = i
+        stop.set()
+
+    th = threading.Thread(target=feeder)
+    th.start()
+    n_found = 0
+    last = None
+    while not stop.is_set():
+        i = now[0]
+        T = np.zeros(7)
+        if lib.flv_vimotion_corr_frame_state(h, float(t[max(i - 3, 0)]), vp(T)) == 1:
+            n_found += 1
+            assert np.all(np.isfinite(T)) and abs(np.linalg.norm(T[:4]) - 1) < 1e-9
+            lib.flv_vimotion_rp_compensation(h, float(t[max(i - 3, 0)]), vp(T))
+            if last is not None and t[max(i - 3, 0)] > last[0]:
+                lib.flv_vimotion_correction(h, float(t[max(i - 3, 0)]), vp(T), last[0], vp(last[1]))
+            last = (float(t[max(i - 3, 0)]), T.copy())
+        assert 0 < lib.flv_vimotion_queue_size(h) <= 400
+    th.join()
+    assert n_found > 10
+    ab = np.zeros(3); gb = np.zeros(3)
+    lib.flv_vimotion_get_bias(h, vp(ab), vp(gb))
+    assert np.all(np.isfinite(ab)) and np.all(np.isfinite(gb))
     lib.flv_vimotion_destroy(h)
