@@ -105,6 +105,7 @@ class F2FTracking {
   int frameCount = 0;
   VIMOTION* vimotion = nullptr;
   const char* last_error() const { return err_; }
+  const SE3& last_keyframe_pose() const { return T_c_w_last_keyframe; }
   // last tracking() counters "pnp|F|of" (lkorb_tracking.cpp:191)
   int last_of_inliers = 0, last_f_inliers = 0, last_pnp_inliers = 0;
 

@@ -221,6 +221,23 @@ int flv_f2f_get_frame(flv_f2f* f, double* T_c_w, int64_t* lm_id, double* plane_x
   }
   return n;
 }
+int flv_f2f_get_frame_ex(flv_f2f* f, double* p3d_c, double* first_obs_2d, double* first_obs_pose, double* T_c_w_last_keyframe, int cap) {
+  if (!f || !f->impl.curr_frame) return FLV_ERR_INVALID;
+  const flv::CameraFrame& fr = *f->impl.curr_frame;
+  if (T_c_w_last_keyframe) se3_to7(f->impl.last_keyframe_pose(), T_c_w_last_keyframe);
+  const int n = (int)fr.landmarks.size() < cap ? (int)fr.landmarks.size() : cap;
+  for (int i = 0; i < n; ++i) {
+    const flv::LandMarkInFrame& lm = fr.landmarks[i];
+    if (p3d_c) for (int k = 0; k < 3; ++k) p3d_c[3 * i + k] = lm.lm_3d_c[k];
+    if (first_obs_2d) { first_obs_2d[2 * i] = lm.lm_1st_obs_2d[0]; first_obs_2d[2 * i + 1] = lm.lm_1st_obs_2d[1]; }
+    if (first_obs_pose) se3_to7(lm.lm_1st_obs_frame_pose, first_obs_pose + 7 * i);
+  }
+  return n;
+}
+int flv_f2f_get_imu_states(flv_f2f* f, double* out11, int cap) {
+  if (!f || !f->impl.vimotion || (!out11 && cap > 0)) return FLV_ERR_INVALID;
+  return f->impl.vimotion->dump_states(out11, cap);
+}
 int flv_f2f_get_imu_bias(flv_f2f* f, double* acc_bias, double* gyro_bias) {
   if (!f || !f->impl.vimotion) return FLV_ERR_INVALID;
   for (int k = 0; k < 3; ++k) {

@@ -192,6 +192,18 @@ bool VIMOTION::viGetCorrFrameState(const double time, SE3& T_c_w) {             
   return false;
 }
 
+int VIMOTION::dump_states(double* out, int cap) const {
+  std::lock_guard<std::recursive_mutex> lock(mtx_states_RW);
+  const int n = (int)states.size() < cap ? (int)states.size() : cap;
+  for (int i = 0; i < n; ++i) {
+    const MOTION_STATE& s = states[i];
+    double* o = out + 11 * (size_t)i;
+    o[0] = s.imu_data.timestamp; o[1] = s.q_w_i.w; o[2] = s.q_w_i.x; o[3] = s.q_w_i.y; o[4] = s.q_w_i.z;
+    for (int k = 0; k < 3; ++k) { o[5 + k] = s.pos[k]; o[8 + k] = s.vel[k]; }
+  }
+  return n;
+}
+
 void VIMOTION::viVisionRPCompensation(const double time, SE3& T_c_w) {                                       // :437-464
   const SE3 T_w_i_before = T_c_w.inverse() * T_c_i;
   const Vec3 rpy_before = Q2rpy(T_w_i_before.q);

@@ -36,6 +36,7 @@ class VIMOTION {
   void viGetLatestImuState(SE3& T_w_i, Vec3& vel);
   bool viGetCorrFrameState(const double time, SE3& T_c_w);
   void viVisionRPCompensation(const double time, SE3& T_c_w);
+  int dump_states(double* out11, int cap) const;     // {t, q wxyz, pos, vel} per queued state (tests / diagnostics)
 
  private:
   // imu_feed runs on other threads than image_feed (ROS callback threads in the reference): `states`, the biases and

@@ -86,6 +86,12 @@ int flv_f2f_state(flv_f2f* f);     /* 0 UnInit, 1 Tracking, 2 TrackingFail */
 /* landmarks of the current frame (after image_feed): returns the count (<= cap) */
 int flv_f2f_get_frame(flv_f2f* f, double* T_c_w, int64_t* lm_id, double* plane_xy, double* undist_xy, double* p3d_w,
                       uint8_t* has_3d, uint8_t* is_inlier, int cap);
+/* the remaining per-landmark state of the current frame (LandMarkInFrame::lm_3d_c, lm_1st_obs_2d, lm_1st_obs_frame_pose,
+ * landmark.h:8-36) and F2FTracking::T_c_w_last_keyframe; returns the count (<= cap).  With flv_f2f_get_frame and
+ * flv_f2f_get_imu_states this is the tracker's complete continuous state (the tests re-seed the oracle from it). */
+int flv_f2f_get_frame_ex(flv_f2f* f, double* p3d_c, double* first_obs_2d, double* first_obs_pose, double* T_c_w_last_keyframe, int cap);
+/* VIMOTION::states (vi_motion.h:30): out[i] = {t, qw qx qy qz, px py pz, vx vy vz}; returns the queue length (<= cap) */
+int flv_f2f_get_imu_states(flv_f2f* f, double* out11, int cap);
 /* VIMOTION::acc_bias / gyro_bias of the tracker's IMU filter (vi_motion.cpp:322-330); returns has_imu */
 int flv_f2f_get_imu_bias(flv_f2f* f, double* acc_bias, double* gyro_bias);
 int flv_f2f_tracking_counts(flv_f2f* f, int* of_inliers, int* f_inliers, int* pnp_inliers);

@@ -81,6 +81,33 @@ def make_pair(lib, seq, hooks=True):
     return h, ref, K
 
 
+def sync_oracle_from_tracker(lib, h, ref, n, T, pl, un, p3):
+    """Teacher forcing: overwrite the oracle's continuous state (current frame's landmarks and pose, last-keyframe pose,
+    IMU state queue and biases) with the C++ tracker's, bit for bit.  Both pipelines are chaotic in the last bits once the
+    IMU pose guess feeds LK's float start positions (a 1e-10 pose difference from the fp64 GPU bundle adjustment flips a
+    float rounding, then a FeatureDEM spacing test, then every later landmark id), so a free-running comparison can only
+    be statistical; re-seeding after every frame keeps the per-frame comparison exact: each frame's complete transition
+    (IMU guess -> LK -> RANSAC -> BA -> reprojection cull -> redetect -> depth innovation -> keyframe rule) is checked from
+    identical inputs."""
+    cap = max(n, 1)
+    p3c = np.zeros((cap, 3)); f2d = np.zeros((cap, 2)); fp = np.zeros((cap, 7)); Tkf = np.zeros(7)
+    m = lib.flv_f2f_get_frame_ex(h, _vp(p3c), _vp(f2d), _vp(fp), _vp(Tkf), cap)
+    assert m == n == len(ref.curr.lms)
+    raw = lambda t7: OSE3([t7[3], t7[0], t7[1], t7[2]], t7[4:7], normalize=False)
+    for i, l in enumerate(ref.curr.lms):
+        l.plane = pl[i].copy(); l.undist = un[i].copy(); l.p3d_w = p3[i].copy(); l.p3d_c = p3c[i].copy()
+        l.first_2d = f2d[i].copy(); l.first_pose = raw(fp[i])
+    ref.curr.T_c_w = raw(T)
+    ref.T_kf = raw(Tkf)
+    st = np.zeros((400, 11))
+    ns = lib.flv_f2f_get_imu_states(h, _vp(st), 400)
+    assert ns == len(ref.vim.states)
+    ref.vim.states = [dict(t=float(r[0]), q=r[1:5].copy(), pos=r[5:8].copy(), vel=r[8:11].copy()) for r in st[:ns]]
+    ab = np.zeros(3); gb = np.zeros(3)
+    lib.flv_f2f_get_imu_bias(h, _vp(ab), _vp(gb))
+    ref.vim.acc_bias, ref.vim.gyro_bias = ab, gb
+
+
 class LocalMapPair:
     """flv::LocalMap (C handle) next to oracle/localmap_ref.LocalMap, fed with the tracker's keyframes."""
 
@@ -125,9 +152,17 @@ class LocalMapPair:
         self.ctx.close()
 
 
-def run_sequence(lib, seq, tol_pose=1e-6, tol_und=0.0, tol_p3=1e-6, window=None, hooks=True, tol_px=0.0):
-    """Frame-by-frame comparison; returns a summary dict (trajectories, state history, counters)."""
+def run_sequence(lib, seq, tol_pose=1e-6, tol_und=0.0, tol_p3=1e-6, window=None, hooks=True, tol_px=0.0, lockstep=False,
+                 free_frames=0):
+    """Frame-by-frame comparison; returns a summary dict (trajectories, state history, counters).
+    lockstep: re-seed the oracle from the tracker after every frame (see sync_oracle_from_tracker);
+    free_frames: additionally run a second, free-running oracle over the first `free_frames` frames for the ATE comparison."""
     h, ref, K = make_pair(lib, seq, hooks)
+    free = None
+    if free_frames:
+        h2, free, _ = make_pair(lib, seq, hooks)
+        lib.flv_f2f_destroy(h2)
+    out_free = []
     lmap = LocalMapPair(window, K) if window else None
     cap = 600
     out = dict(states=[], kf=0, reset=0, guess_used=0, traj=[], traj_ref=[], traj_gt=[], max_dpose=0.0, frames_tracked=0)
@@ -136,6 +171,12 @@ def run_sequence(lib, seq, tol_pose=1e-6, tol_und=0.0, tol_p3=1e-6, window=None,
             a = np.ascontiguousarray(acc); g = np.ascontiguousarray(gyro)
             assert lib.flv_f2f_imu_feed(h, float(ti), _vp(a), _vp(g)) == 0
             ref.imu_feed(float(ti), acc, gyro)
+            if free is not None and k < free_frames:
+                free.imu_feed(float(ti), acc, gyro)
+        if free is not None and k < free_frames:
+            free.image_feed(float(t), img0, img1)
+            if free.state == "Tracking":
+                out_free.append((k, _cam_centre(free.curr.T_c_w.to7())))
         was_tracking = ref.state == "Tracking"
         if was_tracking and ref.has_imu and ref.vim.corr_frame_state(t) is not None:
             out["guess_used"] += 1
@@ -170,6 +211,7 @@ def run_sequence(lib, seq, tol_pose=1e-6, tol_und=0.0, tol_p3=1e-6, window=None,
         assert dpose <= tol_pose, (k, dpose)
         if state == "Tracking":
             out["frames_tracked"] += 1
+            out.setdefault("traj_k", []).append(k)
             out["traj"].append(_cam_centre(T)); out["traj_ref"].append(_cam_centre(rT))
             out["traj_gt"].append(np.asarray(seq.T_w_c0(t).t, float))
             if was_tracking:
@@ -183,7 +225,17 @@ def run_sequence(lib, seq, tol_pose=1e-6, tol_und=0.0, tol_p3=1e-6, window=None,
             okf = {"frame_id": cur.frame_id, "lm_id": [l.lm_id for l in rsel], "lm_2d": np.array([l.undist for l in rsel]),
                    "lm_3d": np.array([l.p3d_w for l in rsel]), "T_c_w": rT}
             lmap.add(cur.frame_id, kids, kuv, k3, T, okf)
+        if lockstep:
+            sync_oracle_from_tracker(lib, h, ref, n, T, pl, un, p3)
     ab = np.zeros(3); gb = np.zeros(3)
+    if free is not None:
+        # free-running reference path against the GPU path: absolute trajectory error over the common tracked frames
+        kk = {k: c for k, c in out_free}
+        pairs = [(c, kk[k]) for k, c in zip(out["traj_k"], out["traj"]) if k in kk]
+        a = np.array([p[0] for p in pairs]); b = np.array([p[1] for p in pairs])
+        out["free_frames_compared"] = len(pairs)
+        out["ate_vs_free_ref"] = float(np.sqrt(np.mean(np.sum((a - b) ** 2, axis=1))))
+        out["free_path"] = float(np.sum(np.linalg.norm(np.diff(b, axis=0), axis=1)))
     out["has_imu"] = lib.flv_f2f_get_imu_bias(h, _vp(ab), _vp(gb))
     out["acc_bias"], out["gyro_bias"] = ab, gb
     out["ref_acc_bias"], out["ref_gyro_bias"] = ref.vim.acc_bias.copy(), ref.vim.gyro_bias.copy()
