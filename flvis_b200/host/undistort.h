@@ -7,6 +7,11 @@
 // tests/test_undistort_cpu.py pins it to cv2 4.13.0.)  Plain double arithmetic in the order OpenCV uses, float in / out.
 #pragma once
 #include <cmath>
+#ifdef __CUDACC__
+#define FLV_HD __host__ __device__
+#else
+#define FLV_HD
+#endif
 
 namespace flv {
 
@@ -18,7 +23,7 @@ struct LensModel {
 };
 
 // cv::undistortPoints with the default criteria (COUNT, 5 iterations)
-inline void undistort_point(const LensModel& m, float u, float v, float& uo, float& vo) {
+FLV_HD inline void undistort_point(const LensModel& m, float u, float v, float& uo, float& vo) {
   const double ifx = 1. / m.fx, ify = 1. / m.fy;
   double x = ((double)u - m.cx) * ifx, y = ((double)v - m.cy) * ify;
   const double x0 = x, y0 = y;
@@ -40,7 +45,7 @@ inline void undistort_point(const LensModel& m, float u, float v, float& uo, flo
 }
 
 // cv::projectPoints for one point: X_c = Rcw X + t, plumb-bob distortion, K
-inline void project_point(const LensModel& m, const double Rcw[9], const double t[3], float X, float Y, float Z, float& u, float& v) {
+FLV_HD inline void project_point(const LensModel& m, const double Rcw[9], const double t[3], float X, float Y, float Z, float& u, float& v) {
   const double Xc = Rcw[0] * X + Rcw[1] * Y + Rcw[2] * Z + t[0];
   const double Yc = Rcw[3] * X + Rcw[4] * Y + Rcw[5] * Z + t[1];
   double z = Rcw[6] * X + Rcw[7] * Y + Rcw[8] * Z + t[2];
