@@ -96,6 +96,38 @@ int flv_f2f_get_imu_states(flv_f2f* f, double* out11, int cap);
 int flv_f2f_get_imu_bias(flv_f2f* f, double* acc_bias, double* gyro_bias);
 int flv_f2f_tracking_counts(flv_f2f* f, int* of_inliers, int* f_inliers, int* pnp_inliers);
 
+/* ---- flv_f2f_batch: S camera sequences of the same sensor advanced together ------------------------------------------
+ * The batched form of flv::F2FTracking (src/frontend/f2f_tracking.cpp:5-453): per stream the same state machine, IMU filter,
+ * landmark id counter and rand() stream as one flv_f2f handle, but every stage (pyramids, frame->frame LK, keep rule,
+ * F / PnP RANSAC, pose-only BA, reprojection cull, FeatureDEM redetect, left->right LK, depth innovation) is ONE launch for
+ * all streams and the landmark lists stay on the device between stages; the host synchronises once per frame.
+ * All streams share `cfg` (one sensor model).  Results per stream are identical to S separate flv_f2f handles
+ * (tests/test_batch_tracker_gpu.py).
+ *   imu_feed:   F2FTracking::imu_feed for one stream (may be called from another thread than image_feed).
+ *   image_feed: t[S]; img0 = S left images back to back (u8, tightly packed); img1 = S right images (u8) or S depth images
+ *               (u16); mem says where the images live (pinned host memory gives asynchronous copies);
+ *               new_keyframe[S] / reset_cmd[S] as F2FTracking::image_feed returns them per stream. */
+typedef struct flv_f2f_batch flv_f2f_batch;
+flv_f2f_batch* flv_f2f_batch_create(const flv_f2f_config* cfg, int n_streams, int device);
+void flv_f2f_batch_destroy(flv_f2f_batch* b);
+const char* flv_f2f_batch_last_error(flv_f2f_batch* b);
+flv_ctx* flv_f2f_batch_context(flv_f2f_batch* b);      /* the batch's kernel context (stream selection, launch counter) */
+int flv_f2f_batch_set_lens(flv_f2f_batch* b, int cam, const double* K4, const double* D14, const double* R9);
+int flv_f2f_batch_set_equalize_hist(flv_f2f_batch* b, int enable);
+void flv_f2f_batch_set_ransac_hooks(flv_f2f_batch* b, flv_f2f_fmat_fn fmat, flv_f2f_pnp_fn pnp, void* user);
+int flv_f2f_batch_imu_feed(flv_f2f_batch* b, int stream, double t, const double* acc, const double* gyro);
+int flv_f2f_batch_image_feed(flv_f2f_batch* b, const double* t, const uint8_t* img0, const void* img1, flv_memspace mem,
+                             int* new_keyframe, int* reset_cmd);
+int flv_f2f_batch_state(flv_f2f_batch* b, int stream);
+int flv_f2f_batch_get_frame(flv_f2f_batch* b, int stream, double* T_c_w, int64_t* lm_id, double* plane_xy, double* undist_xy,
+                            double* p3d_w, uint8_t* has_3d, uint8_t* is_inlier, int cap);
+int flv_f2f_batch_get_frame_ex(flv_f2f_batch* b, int stream, double* p3d_c, double* first_obs_2d, double* first_obs_pose,
+                               double* T_c_w_last_keyframe, int cap);
+int flv_f2f_batch_get_imu_states(flv_f2f_batch* b, int stream, double* out11, int cap);
+int flv_f2f_batch_get_imu_bias(flv_f2f_batch* b, int stream, double* acc_bias, double* gyro_bias);
+int flv_f2f_batch_tracking_counts(flv_f2f_batch* b, int stream, int* of_inliers, int* f_inliers, int* pnp_inliers);
+long long flv_f2f_batch_launch_count(flv_f2f_batch* b);
+
 #ifdef __cplusplus
 }
 #endif

@@ -194,15 +194,17 @@ class Sequence:
             yield t, img0, img1, imu
 
 
-def make_c0(n_frames=150, seed=0, blank_frames=()):
-    """C0: 640x480 D435i depth + IMU; the first 50 images are skipped by the tracker (vo_tracking.cpp:171)."""
-    c = D435
+def make_c0(n_frames=150, seed=0, blank_frames=(), skip=None, t_rest=1.9, imu=True):
+    """C0: 640x480 D435i depth + IMU; the first 50 images are skipped by the tracker (vo_tracking.cpp:171).
+    skip / t_rest / imu: overrides for short test sequences (fewer skipped images, earlier motion, no IMU samples)."""
+    c = D435 if skip is None else dict(D435, skip=skip)
     X0 = 3.0; ppm = c["K0"][0] / X0
     canvas = synth.texture(1000 * 0 + seed, int(5.2 * ppm), int(7.0 * ppm), blur=2)
-    traj = Trajectory(pos_amp=(0.10, 0.35, 0.20), pos_w=(0.9, 0.7, 0.8), rpy_amp=(0.06, 0.05, 0.08), rpy_w=(0.8, 0.6, 0.5), t_rest=1.9)
+    traj = Trajectory(pos_amp=(0.10, 0.35, 0.20), pos_w=(0.9, 0.7, 0.8), rpy_amp=(0.06, 0.05, 0.08), rpy_w=(0.8, 0.6, 0.5), t_rest=t_rest)
     T_i_c0 = _mat44_to_se3(c["T_imu_cam0"])
     r0 = PlaneRenderer(canvas, X0, ppm, c["w"], c["h"], c["K0"])
-    seq = Sequence("c0", "depth", n_frames, c["img_hz"], traj, T_i_c0, r0, blank_frames=blank_frames, depth_factor=c["depth_factor"], seed=seed)
+    seq = Sequence("c0", "depth", n_frames, c["img_hz"], traj, T_i_c0, r0, blank_frames=blank_frames, depth_factor=c["depth_factor"], seed=seed,
+                   imu_hz=200.0 if imu else 0)
     seq.cfg = c
     return seq
 
@@ -216,12 +218,12 @@ def euroc_rig():
     return T_i_mavi * T_mavi_c0, T_c0_c1
 
 
-def make_c1(n_frames=200, seed=0, blank_frames=()):
+def make_c1(n_frames=200, seed=0, blank_frames=(), t_rest=0.5):
     """C1: EuRoC-shaped raw stereo (radtan distortion => STEREO_UNRECT), 20 Hz images, 200 Hz IMU."""
     c = EUROC
     X0 = 3.0; ppm = c["K0"][0] / X0
     canvas = synth.texture(1000 * 1 + seed, int(6.0 * ppm), int(8.5 * ppm), blur=2)
-    traj = Trajectory(pos_amp=(0.12, 0.45, 0.25), pos_w=(0.5, 0.45, 0.55), rpy_amp=(0.05, 0.04, 0.07), rpy_w=(0.5, 0.45, 0.35), t_rest=0.5)
+    traj = Trajectory(pos_amp=(0.12, 0.45, 0.25), pos_w=(0.5, 0.45, 0.55), rpy_amp=(0.05, 0.04, 0.07), rpy_w=(0.5, 0.45, 0.35), t_rest=t_rest)
     T_i_c0, T_c0_c1 = euroc_rig()
     r0 = PlaneRenderer(canvas, X0, ppm, c["w"], c["h"], c["K0"], c["D0"])
     r1 = PlaneRenderer(canvas, X0, ppm, c["w"], c["h"], c["K1"], c["D1"])
