@@ -320,6 +320,7 @@ int flv_f2f_batch_image_feed(flv_f2f_batch* b, const double* t, const uint8_t* i
       case UnInit: {
         const double R_w_c[9] = {0, 0, 1, -1, 0, 0, 0, -1, 0};
         SE3 T0 = SE3(flv::R_to_q(R_w_c), Vec3{0, 0, 0}).inverse();
+        z.cur_T = T0;                                   // assigned before the IMU checks in the reference (:149-151)
         if (z.has_imu) {
           if (z.vim->imu_initialized) {
             Quat q_init;
