@@ -71,6 +71,8 @@ struct flv_f2f_batch {
   flv_f2f_fmat_fn fmat_fn = nullptr; flv_f2f_pnp_fn pnp_fn = nullptr; void* hook_user = nullptr;
   std::vector<char> have_last;                             // stream has an accepted "last" frame on the device
   cudaEvent_t ev_done = nullptr;
+  flv_localmap_batch* lmap = nullptr;                      // keyframes go here (flv_f2f_batch_attach_localmap)
+  std::vector<int> kf_streams, kf_counts; std::vector<int64_t> kf_frame, kf_ids; std::vector<double> kf_2d, kf_3d, kf_T;
   char err[512] = {0};
 };
 
@@ -428,16 +430,18 @@ int flv_f2f_batch_image_feed(flv_f2f_batch* b, const double* t, const uint8_t* i
   B_CUDA(b, cudaEventSynchronize(b->ev_done));
   // ---- per-stream state machine after the frame (f2f_tracking.cpp:229-247, :258-355, :376-394) --------------------------
   bool any_restore = false;
+  b->kf_streams.clear(); b->kf_counts.clear(); b->kf_frame.clear(); b->kf_ids.clear(); b->kf_2d.clear(); b->kf_3d.clear(); b->kf_T.clear();
   for (int s = 0; s < S; ++s) {
     StreamState& z = b->st[s];
     const TrkCtl& c = b->h_ctl[s];
     const TrkOut& o = b->h_out[s];
-    bool accepted = false;
+    bool accepted = false, is_kf = false;
     if (c.mode == 2) {
       for (int i = 0; i < o.rand_used; ++i) z.rnd.rand();
       if (o.ok && o.valid_cnt > 30) {                                     // init_frame succeeded (:443-452)
         z.T_kf = z.cur_T;
         if (new_keyframe) new_keyframe[s] = 1;
+        is_kf = true;
         z.state = Tracking;
         accepted = true;
       } else if (z.state == TrackingFail) {                               // last_frame.swap(curr_frame)
@@ -468,12 +472,29 @@ int flv_f2f_batch_image_feed(flv_f2f_batch* b, const double* t, const uint8_t* i
         if (z.frameCount < 40 && (z.frameCount % 5) == 0) { kf = true; z.T_kf = z.cur_T; }
         if (t_norm >= 0.05 || r_norm >= 0.2) { kf = true; z.T_kf = z.cur_T; }
         if (kf && new_keyframe) new_keyframe[s] = 1;
+        is_kf = kf;
         accepted = true;
       }
       z.n_lm = ((const int*)(b->h_tab + b->o_n))[s];
     } else {
       // idle frame: TrackingFail swaps back (:377-393); UnInit / skipped frames leave an empty current frame
       if (z.state == TrackingFail) { std::swap(z.cur_time, z.last_time); std::swap(z.cur_T, z.last_T); z.n_lm = ((const int*)(b->h_tab + b->o_n))[s]; }
+    }
+    if (is_kf && b->lmap) {                             // CameraFrame::getKeyFrameInf (camera_frame.cpp:515-529)
+      const size_t k0 = (size_t)s * M;
+      const unsigned char* tb = b->h_tab;
+      int cnt = 0;
+      for (int i = 0; i < z.n_lm; ++i) {
+        const size_t k = k0 + i;
+        if (!(tb + b->o_has)[k] || !(tb + b->o_inl)[k]) continue;
+        b->kf_ids.push_back(((const long long*)(tb + b->o_id))[k]);
+        b->kf_2d.push_back(((const double*)(tb + b->o_und))[2 * k]); b->kf_2d.push_back(((const double*)(tb + b->o_und))[2 * k + 1]);
+        for (int c3 = 0; c3 < 3; ++c3) b->kf_3d.push_back(((const double*)(tb + b->o_p3w))[3 * k + c3]);
+        ++cnt;
+      }
+      double T7[7]; to7(z.cur_T, T7);
+      b->kf_T.insert(b->kf_T.end(), T7, T7 + 7);
+      b->kf_streams.push_back(s); b->kf_counts.push_back(cnt); b->kf_frame.push_back(z.frameCount);
     }
     if (accepted) b->have_last[s] = 1;
     else if (b->have_last[s]) {
@@ -482,6 +503,11 @@ int flv_f2f_batch_image_feed(flv_f2f_batch* b, const double* t, const uint8_t* i
       B_CUDA(b, cudaMemcpyAsync(ctx->pyr[cur0] + (size_t)s * stride, ctx->pyr[prev0] + (size_t)s * stride, stride, cudaMemcpyDeviceToDevice, cs));
       any_restore = true;
     }
+  }
+  if (b->lmap && !b->kf_streams.empty()) {
+    const int rc = flv_localmap_batch_submit(b->lmap, (int)b->kf_streams.size(), b->kf_streams.data(), b->kf_frame.data(), b->kf_counts.data(),
+                                             b->kf_ids.data(), b->kf_2d.data(), b->kf_3d.data(), b->kf_T.data());
+    if (rc) { snprintf(b->err, sizeof(b->err), "flv_localmap_batch_submit: %s", flv_localmap_batch_last_error(b->lmap)); return rc; }
   }
   if (any_restore) ctx->deriv_streams[cur0] = 0;          // derivative pyramid of that slot: rebuild on next use
   b->slots[0] = cur0; b->slots[1] = prev0; b->slots[2] = cur1;
@@ -544,5 +570,10 @@ int flv_f2f_batch_tracking_counts(flv_f2f_batch* b, int stream, int* of, int* fi
   return FLV_OK;
 }
 long long flv_f2f_batch_launch_count(flv_f2f_batch* b) { return b && b->ctx ? flv_launch_count(b->ctx) : 0; }
+int flv_f2f_batch_attach_localmap(flv_f2f_batch* b, flv_localmap_batch* lm) {
+  if (!b) return FLV_ERR_INVALID;
+  b->lmap = lm;
+  return FLV_OK;
+}
 
 }  // extern "C"

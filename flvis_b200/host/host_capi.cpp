@@ -10,7 +10,9 @@ struct flv_localmap { flv::LocalMap impl; flv_localmap(flv_ctx* c, int w, double
 extern "C" {
 
 flv_localmap* flv_localmap_create(flv_ctx* ctx, int window_size, double fx, double fy, double cx, double cy) {
-  if (!ctx || window_size < 3 || window_size > 32) return nullptr;    // reference clamps to [3,100]; kernel limit 32
+  // reference clamps window_size to [3,100] (vo_localmap.cpp:441-447); the solver keeps the reduced camera system in
+  // shared memory: 24 free poses + the fixed one
+  if (!ctx || window_size < 3 || window_size > 25) return nullptr;
   return new (std::nothrow) flv_localmap(ctx, window_size, fx, fy, cx, cy);
 }
 void flv_localmap_destroy(flv_localmap* lm) { delete lm; }
@@ -33,6 +35,7 @@ int flv_localmap_add_keyframe(flv_localmap* lm, int64_t frame_id, int n, const i
   for (int k = 0; k < 7; ++k) kf.T_c_w[k] = T_c_w[k];
   flv::CorrectionInfStruct c;
   const bool was_ready = lm->impl.frame_callback(kf, c);
+  if (lm->impl.solve_failed()) return FLV_ERR_CUDA;          // a due solve did not run (flv_last_error of the context says why)
   if (!was_ready) return 0;
   if ((int)c.lm_id.size() > lm_cap || (int)c.lm_outlier_id.size() > outlier_cap) return FLV_ERR_OVERFLOW;
   if (out_frame_id) *out_frame_id = c.frame_id;

@@ -37,8 +37,24 @@ class LocalMap {
   void reset();
   // returns true when a solve ran and `out` was filled (the reference publishes CorrectionInf then)
   bool frame_callback(const KeyFrameStruct& kf, CorrectionInfStruct& out);
+  // The same callback split around the solver call, for callers that batch the solves of several sequences into one
+  // launch (flv_localmap_batch): begin() edits the graph and, when a solve is due (returns true), flattens it into `in`;
+  // the caller runs flv_ba_optimize on those arrays and hands them back to end().  begin() -> [solve] -> end() must
+  // alternate per LocalMap; begin() returning false needs no end().
+  struct SolveArrays {
+    int P = 0, L = 0, E = 0, fixed = -1;
+    std::vector<int64_t> ids;                 // landmark id of landmark vertex l
+    std::vector<double> poses, lms, uv;       // [P][7], [L][3], [E][2]
+    std::vector<int> ep, el;
+    std::vector<uint8_t> active;
+  };
+  bool begin(const KeyFrameStruct& kf, SolveArrays& in);
+  void end(const SolveArrays& solved, const flv_ba_stats& st, CorrectionInfStruct& out);
+  void intrinsics(double K4[4]) const { K4[0] = fx_; K4[1] = fy_; K4[2] = cx_; K4[3] = cy_; }
+  int window() const { return W_; }
   State state() const { return optimizer_state; }
   const flv_ba_stats& last_stats() const { return stats_; }
+  bool solve_failed() const { return solve_failed_; }   // the last frame_callback had a solve due and the solver call failed
 
  private:
   struct Edge { int64_t lm_id; int pose_slot; Vec2 uv; };
@@ -54,10 +70,13 @@ class LocalMap {
   std::map<int64_t, Vec3> lm_est;
   std::vector<Edge> edges;
   flv_ba_stats stats_{};
+  bool solve_failed_ = false;
   int reserved_P = 0, reserved_L = 0, reserved_E = 0;
 
   void remove_pose_vertex(int slot);
   void remove_lm_vertex(int64_t id);
+  bool edit_graph(const KeyFrameStruct& kf);          // the state machine up to OPTIMIZING; true = solve now
+  void flatten(SolveArrays& in) const;
   bool solve(CorrectionInfStruct& out);
 };
 

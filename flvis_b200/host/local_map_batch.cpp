@@ -1,0 +1,235 @@
+// flv_localmap_batch -- the local-map thread for S sequences (LocalMapNodeletClass, src/backend/vo_localmap.cpp:87-380).
+//
+// FLVIS runs the sliding-window BA in its own nodelet thread: keyframes arrive through a queue (depth 10,
+// vo_localmap.cpp:464-467) and never block tracking.  Here ONE worker thread serves all S sequences: the tracker thread
+// submits the keyframes of a frame, the worker edits each sequence's graph (flv::LocalMap::begin, the reference's state
+// machine with its quirks), solves ALL windows that are due with ONE flv_ba_optimize launch on its own context / CUDA
+// stream (so the kernels overlap the tracker's), and stores the CorrectionInf results (LocalMap::end).
+// Results are identical to S separate flv_localmap handles fed the same keyframes (tests/test_localmap.py).
+#include <algorithm>
+#include <atomic>
+#include <chrono>
+#include <condition_variable>
+#include <cstdio>
+#include <deque>
+#include <memory>
+#include <mutex>
+#include <thread>
+#include <vector>
+#include "../../include/flvis_b200_host.h"
+#include "local_map.h"
+
+namespace {
+struct KfMsg { int stream; flv::KeyFrameStruct kf; };
+}
+
+struct flv_localmap_batch {
+  int device = 0, S = 0, W = 0;
+  double K[4] = {0, 0, 0, 0};
+  flv_ctx* ctx = nullptr;                       // created and used by the worker thread only
+  std::vector<std::unique_ptr<flv::LocalMap>> maps;
+  std::vector<flv::CorrectionInfStruct> latest; // last CorrectionInf per sequence
+  std::vector<long long> n_results;
+  std::thread worker;
+  std::mutex mu;
+  std::condition_variable cv_work, cv_idle;
+  std::deque<std::vector<KfMsg>> queue;
+  bool stop = false, busy = false, failed = false, started = false;
+  long long n_keyframes = 0, n_solves = 0, n_launches = 0;
+  double solve_ms = 0;
+  int rP = 0, rL = 0, rE = 0;
+  char err[256] = {0};
+
+  void run();
+  bool process(std::vector<KfMsg>& batch);
+};
+
+bool flv_localmap_batch::process(std::vector<KfMsg>& batch) {
+  // a sequence may contribute several keyframes to one submission only if the caller batches frames; solve in rounds so
+  // that every LocalMap sees begin -> solve -> end in order
+  size_t done = 0;
+  std::vector<char> used(batch.size(), 0);
+  while (done < batch.size()) {
+    std::vector<int> round;                      // indices of this round: at most one keyframe per sequence
+    std::vector<char> seen(S, 0);
+    for (size_t i = 0; i < batch.size(); ++i)
+      if (!used[i] && !seen[batch[i].stream]) { seen[batch[i].stream] = 1; round.push_back((int)i); used[i] = 1; }
+    done += round.size();
+    std::vector<flv::LocalMap::SolveArrays> arr(round.size());
+    std::vector<int> due;
+    for (size_t r = 0; r < round.size(); ++r) {
+      const KfMsg& m = batch[round[r]];
+      if (maps[m.stream]->begin(m.kf, arr[r])) due.push_back((int)r);
+    }
+    n_keyframes += (long long)round.size();
+    if (due.empty()) continue;
+    int P = W, L = 0, E = 0;
+    for (int r : due) { L = std::max(L, arr[r].L); E = std::max(E, arr[r].E); }
+    if (P > rP || L > rL || E > rE) {
+      rP = std::max(P, rP); rL = std::max(L + L / 2 + 64, rL); rE = std::max(E + E / 2 + 64, rE);
+      if (flv_ba_reserve(ctx, rP, rL, rE) != FLV_OK) { snprintf(err, sizeof(err), "flv_ba_reserve: %s", flv_last_error(ctx)); return false; }
+    }
+    const size_t n = due.size();
+    std::vector<double> poses(n * rP * 7, 0.0), lms(n * (size_t)rL * 3, 0.0), uv(n * (size_t)rE * 2, 0.0);
+    std::vector<int> ep(n * (size_t)rE, 0), el(n * (size_t)rE, 0);
+    std::vector<uint8_t> act(n * (size_t)rE, 0);
+    std::vector<flv_ba_problem> pb(n);
+    std::vector<flv_ba_stats> st(n);
+    for (size_t j = 0; j < n; ++j) {
+      const flv::LocalMap::SolveArrays& a = arr[due[j]];
+      std::copy(a.poses.begin(), a.poses.end(), poses.begin() + j * rP * 7);
+      std::copy(a.lms.begin(), a.lms.end(), lms.begin() + j * (size_t)rL * 3);
+      std::copy(a.uv.begin(), a.uv.end(), uv.begin() + j * (size_t)rE * 2);
+      std::copy(a.ep.begin(), a.ep.end(), ep.begin() + j * (size_t)rE);
+      std::copy(a.el.begin(), a.el.end(), el.begin() + j * (size_t)rE);
+      std::copy(a.active.begin(), a.active.end(), act.begin() + j * (size_t)rE);
+      pb[j] = flv_ba_problem{a.P, a.L, a.E, a.fixed, 0, K[0], K[1], K[2], K[3]};
+    }
+    const flv_ba_params prm{12, 8, 1.0, 3.0, 0, 0};
+    const auto t0 = std::chrono::steady_clock::now();
+    if (flv_ba_optimize(ctx, (int)n, pb.data(), &prm, poses.data(), lms.data(), ep.data(), el.data(), uv.data(), act.data(), st.data(),
+                        FLV_MEM_HOST) != FLV_OK) {
+      snprintf(err, sizeof(err), "flv_ba_optimize: %s", flv_last_error(ctx));
+      return false;
+    }
+    solve_ms += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    n_solves += (long long)n; n_launches++;
+    for (size_t j = 0; j < n; ++j) {
+      flv::LocalMap::SolveArrays& a = arr[due[j]];
+      std::copy(poses.begin() + j * rP * 7, poses.begin() + j * rP * 7 + 7 * (size_t)a.P, a.poses.begin());
+      std::copy(lms.begin() + j * (size_t)rL * 3, lms.begin() + j * (size_t)rL * 3 + 3 * (size_t)a.L, a.lms.begin());
+      std::copy(act.begin() + j * (size_t)rE, act.begin() + j * (size_t)rE + a.E, a.active.begin());
+      const int s = batch[round[due[j]]].stream;
+      flv::CorrectionInfStruct out;
+      maps[s]->end(a, st[j], out);
+      std::lock_guard<std::mutex> lk(mu);
+      latest[s] = std::move(out);
+      n_results[s]++;
+    }
+  }
+  return true;
+}
+
+void flv_localmap_batch::run() {
+  // the context belongs to this thread: flv_create selects the device for the thread
+  const int rc = flv_create(&ctx, device, S, 64, 64, 64);
+  {
+    std::lock_guard<std::mutex> lk(mu);
+    started = true;
+    if (rc != FLV_OK) { failed = true; snprintf(err, sizeof(err), "flv_create failed (%d)", rc); }
+  }
+  cv_idle.notify_all();
+  for (;;) {
+    std::vector<KfMsg> batch;
+    {
+      std::unique_lock<std::mutex> lk(mu);
+      cv_work.wait(lk, [&] { return stop || !queue.empty(); });
+      if (queue.empty()) break;                  // stop requested and nothing left
+      batch = std::move(queue.front());
+      queue.pop_front();
+      busy = true;
+    }
+    const bool ok = failed ? false : process(batch);
+    {
+      std::lock_guard<std::mutex> lk(mu);
+      if (!ok) failed = true;
+      busy = false;
+    }
+    cv_idle.notify_all();
+  }
+  if (ctx) { flv_destroy(ctx); ctx = nullptr; }
+}
+
+extern "C" {
+
+flv_localmap_batch* flv_localmap_batch_create(int device, int n_streams, int window_size, double fx, double fy, double cx, double cy) {
+  if (n_streams < 1 || window_size < 3 || window_size > 25) return nullptr;
+  flv_localmap_batch* b = new (std::nothrow) flv_localmap_batch();
+  if (!b) return nullptr;
+  b->device = device; b->S = n_streams; b->W = window_size;
+  b->K[0] = fx; b->K[1] = fy; b->K[2] = cx; b->K[3] = cy;
+  b->latest.resize(n_streams); b->n_results.assign(n_streams, 0);
+  for (int s = 0; s < n_streams; ++s) b->maps.emplace_back(new flv::LocalMap(nullptr, window_size, fx, fy, cx, cy));
+  b->worker = std::thread([b] { b->run(); });
+  std::unique_lock<std::mutex> lk(b->mu);
+  b->cv_idle.wait(lk, [&] { return b->started; });
+  return b;
+}
+
+void flv_localmap_batch_destroy(flv_localmap_batch* b) {
+  if (!b) return;
+  { std::lock_guard<std::mutex> lk(b->mu); b->stop = true; }
+  b->cv_work.notify_all();
+  if (b->worker.joinable()) b->worker.join();
+  delete b;
+}
+
+const char* flv_localmap_batch_last_error(flv_localmap_batch* b) { return b ? b->err : "null"; }
+
+int flv_localmap_batch_submit(flv_localmap_batch* b, int n_kf, const int* streams, const int64_t* frame_ids, const int* lm_counts,
+                              const int64_t* lm_id, const double* lm_2d, const double* lm_3d, const double* T_c_w) {
+  if (!b || n_kf < 0 || (n_kf > 0 && (!streams || !frame_ids || !lm_counts || !lm_id || !lm_2d || !lm_3d || !T_c_w))) return FLV_ERR_INVALID;
+  if (n_kf == 0) return FLV_OK;
+  std::vector<KfMsg> batch(n_kf);
+  size_t off = 0;
+  for (int i = 0; i < n_kf; ++i) {
+    if (streams[i] < 0 || streams[i] >= b->S || lm_counts[i] < 0) return FLV_ERR_INVALID;
+    KfMsg& m = batch[i];
+    m.stream = streams[i];
+    m.kf.frame_id = frame_ids[i]; m.kf.lm_count = lm_counts[i];
+    m.kf.lm_id.assign(lm_id + off, lm_id + off + lm_counts[i]);
+    m.kf.lm_2d.resize(lm_counts[i]); m.kf.lm_3d.resize(lm_counts[i]);
+    for (int k = 0; k < lm_counts[i]; ++k) {
+      m.kf.lm_2d[k] = flv::Vec2{lm_2d[2 * (off + k)], lm_2d[2 * (off + k) + 1]};
+      m.kf.lm_3d[k] = flv::Vec3{lm_3d[3 * (off + k)], lm_3d[3 * (off + k) + 1], lm_3d[3 * (off + k) + 2]};
+    }
+    for (int k = 0; k < 7; ++k) m.kf.T_c_w[k] = T_c_w[7 * i + k];
+    off += lm_counts[i];
+  }
+  {
+    std::lock_guard<std::mutex> lk(b->mu);
+    if (b->failed) return FLV_ERR_CUDA;
+    b->queue.push_back(std::move(batch));
+  }
+  b->cv_work.notify_one();
+  return FLV_OK;
+}
+
+int flv_localmap_batch_wait(flv_localmap_batch* b) {
+  if (!b) return FLV_ERR_INVALID;
+  std::unique_lock<std::mutex> lk(b->mu);
+  b->cv_idle.wait(lk, [&] { return (b->queue.empty() && !b->busy) || b->failed; });
+  return b->failed ? FLV_ERR_CUDA : FLV_OK;
+}
+
+int flv_localmap_batch_stats(flv_localmap_batch* b, long long* n_keyframes, long long* n_solves, long long* n_launches, double* solve_ms) {
+  if (!b) return FLV_ERR_INVALID;
+  std::lock_guard<std::mutex> lk(b->mu);
+  if (n_keyframes) *n_keyframes = b->n_keyframes;
+  if (n_solves) *n_solves = b->n_solves;
+  if (n_launches) *n_launches = b->n_launches;
+  if (solve_ms) *solve_ms = b->solve_ms;
+  return FLV_OK;
+}
+
+int flv_localmap_batch_result(flv_localmap_batch* b, int stream, int64_t* out_frame_id, double* out_T_c_w, int* out_lm_count,
+                              int64_t* out_lm_id, double* out_lm_3d, int lm_cap, int* out_outlier_count, int64_t* out_outlier_id,
+                              int outlier_cap) {
+  if (!b || stream < 0 || stream >= b->S) return FLV_ERR_INVALID;
+  std::lock_guard<std::mutex> lk(b->mu);
+  if (b->n_results[stream] == 0) return 0;
+  const flv::CorrectionInfStruct& c = b->latest[stream];
+  if ((int)c.lm_id.size() > lm_cap || (int)c.lm_outlier_id.size() > outlier_cap) return FLV_ERR_OVERFLOW;
+  if (out_frame_id) *out_frame_id = c.frame_id;
+  if (out_T_c_w) for (int k = 0; k < 7; ++k) out_T_c_w[k] = c.T_c_w[k];
+  if (out_lm_count) *out_lm_count = c.lm_count;
+  for (size_t i = 0; i < c.lm_id.size(); ++i) {
+    if (out_lm_id) out_lm_id[i] = c.lm_id[i];
+    if (out_lm_3d) for (int k = 0; k < 3; ++k) out_lm_3d[3 * i + k] = c.lm_3d[i][k];
+  }
+  if (out_outlier_count) *out_outlier_count = c.lm_outlier_count;
+  if (out_outlier_id) for (size_t i = 0; i < c.lm_outlier_id.size(); ++i) out_outlier_id[i] = c.lm_outlier_id[i];
+  return (int)b->n_results[stream];
+}
+
+}  // extern "C"

@@ -18,7 +18,9 @@ void flv_localmap_destroy(flv_localmap* lm);
 void flv_localmap_reset(flv_localmap* lm);      /* KFMSG_CMD_RESET_LM, vo_localmap.cpp:89-98 */
 /* One KeyFrame message (msg/KeyFrame.msg without the images): lm_2d[n][2] undistorted px, lm_3d[n][3] world,
  * T_c_w = [qx qy qz qw tx ty tz].  Returns 1 when a solve ran and the CorrectionInf outputs were written
- * (msg/CorrectionInf.msg), 0 when the window is still filling, <0 on error (buffers too small = FLV_ERR_OVERFLOW). */
+ * (msg/CorrectionInf.msg), 0 when the window is still filling, <0 on error (buffers too small = FLV_ERR_OVERFLOW, a due solve
+ * that failed = FLV_ERR_CUDA with flv_last_error(ctx) set).  window_size: 3..25 (the reference allows up to 100,
+ * vo_localmap.cpp:441-447; the reduced camera system of this solver lives in shared memory: 24 free poses). */
 int flv_localmap_add_keyframe(flv_localmap* lm, int64_t frame_id, int n, const int64_t* lm_id, const double* lm_2d,
                               const double* lm_3d, const double* T_c_w, int64_t* out_frame_id, double* out_T_c_w,
                               int* out_lm_count, int64_t* out_lm_id, double* out_lm_3d, int lm_cap,
@@ -96,6 +98,24 @@ int flv_f2f_get_imu_states(flv_f2f* f, double* out11, int cap);
 int flv_f2f_get_imu_bias(flv_f2f* f, double* acc_bias, double* gyro_bias);
 int flv_f2f_tracking_counts(flv_f2f* f, int* of_inliers, int* f_inliers, int* pnp_inliers);
 
+/* ---- flv_localmap_batch: the local-map thread for S sequences ------------------------------------------------------
+ * One worker thread (FLVIS runs the local map in its own nodelet thread fed by a queue, vo_localmap.cpp:464-467) owns S
+ * LocalMap state machines and solves all windows that are due after a submission with ONE flv_ba_optimize launch on its own
+ * CUDA stream.  submit() returns immediately; wait() drains the queue; result() returns the latest CorrectionInf of a stream
+ * (return value = number of solves so far for that stream, 0 = none yet).  Keyframes of one submission are concatenated:
+ * lm_id / lm_2d / lm_3d hold lm_counts[0] entries of keyframe 0, then lm_counts[1] of keyframe 1, ...; T_c_w is [n_kf][7]. */
+typedef struct flv_localmap_batch flv_localmap_batch;
+flv_localmap_batch* flv_localmap_batch_create(int device, int n_streams, int window_size, double fx, double fy, double cx, double cy);
+void flv_localmap_batch_destroy(flv_localmap_batch* b);
+const char* flv_localmap_batch_last_error(flv_localmap_batch* b);
+int flv_localmap_batch_submit(flv_localmap_batch* b, int n_kf, const int* streams, const int64_t* frame_ids, const int* lm_counts,
+                              const int64_t* lm_id, const double* lm_2d, const double* lm_3d, const double* T_c_w);
+int flv_localmap_batch_wait(flv_localmap_batch* b);
+int flv_localmap_batch_stats(flv_localmap_batch* b, long long* n_keyframes, long long* n_solves, long long* n_launches, double* solve_ms);
+int flv_localmap_batch_result(flv_localmap_batch* b, int stream, int64_t* out_frame_id, double* out_T_c_w, int* out_lm_count,
+                              int64_t* out_lm_id, double* out_lm_3d, int lm_cap, int* out_outlier_count, int64_t* out_outlier_id,
+                              int outlier_cap);
+
 /* ---- flv_f2f_batch: S camera sequences of the same sensor advanced together ------------------------------------------
  * The batched form of flv::F2FTracking (src/frontend/f2f_tracking.cpp:5-453): per stream the same state machine, IMU filter,
  * landmark id counter and rand() stream as one flv_f2f handle, but every stage (pyramids, frame->frame LK, keep rule,
@@ -127,6 +147,9 @@ int flv_f2f_batch_get_imu_states(flv_f2f_batch* b, int stream, double* out11, in
 int flv_f2f_batch_get_imu_bias(flv_f2f_batch* b, int stream, double* acc_bias, double* gyro_bias);
 int flv_f2f_batch_tracking_counts(flv_f2f_batch* b, int stream, int* of_inliers, int* f_inliers, int* pnp_inliers);
 long long flv_f2f_batch_launch_count(flv_f2f_batch* b);
+/* Hand every new keyframe (KeyFrame message content: ids / undistorted pixels / world points of the inlier landmarks with
+ * depth + T_c_w, keyframe_msg.cpp:30-110) to `lm` from inside image_feed; NULL detaches.  The local map never blocks tracking. */
+int flv_f2f_batch_attach_localmap(flv_f2f_batch* b, flv_localmap_batch* lm);
 
 #ifdef __cplusplus
 }
