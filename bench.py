@@ -1,22 +1,27 @@
 #!/usr/bin/env python
-"""bench.py -- frames/sec of the FLVIS hot path on EuRoC-shaped 752x480 stereo streams (BASELINE.json metric).
+"""bench.py -- frames/sec of the FLVIS hot path on EuRoC-shaped 752x480 stereo+IMU streams (BASELINE.json metric).
 
-    python bench.py --gpus N --steps K --warmup W [--streams S] [--impl reference]
+    python bench.py --gpus N --steps K --warmup W [--streams S] [--workload euroc|kitti|d435] [--impl reference]
 
-A "step" is one stereo frame for every one of the S concurrent streams on this GPU:
-    pyramid(cur0), pyramid(cur1) -> LK frame->frame (prev0 -> cur0, 480 pts/stream)
-    -> FeatureDEM redetect on cur0 (Shi-Tomasi + region select) -> LK left->right (cur0 -> cur1)
-    -> local BA (10-KF window, 12 + cull + 8 LM iterations) for the streams whose keyframe falls on this step
-       (one keyframe every KF_EVERY frames, phases staggered so every step does the same amount of work).
-`value`  : device-timed, inputs already resident in HBM (a device-side frame pool), CUDA events.
-`e2e`    : the same step driven through the C ABI with pinned HOST buffers: the two images per stream are
-           copied H2D and the tracked points / status / new corners / BA poses are copied D2H every step.
-Multi-GPU: streams are independent; every rank runs its own S streams ("weak" scaling),
-no data-path collective; NCCL is used for the barrier and the max-over-ranks reduction of the timing only.
-`--impl reference`: the reference's CPU path (cv2 = the OpenCV the reference links, + the C port of its g2o
-path) on the host cores, bounded sample, same metric/config.
+A "step" is ONE CAMERA FRAME for every one of the S concurrent sequences on this GPU, through the product's public call
+(flv_f2f_batch_imu_feed_many + flv_f2f_batch_image_feed, include/flvis_b200_host.h) -- the complete
+F2FTracking::image_feed of the reference (src/frontend/f2f_tracking.cpp:59-400) per sequence:
+    ingest (equalizeHist for EuRoC) + 2 pyramids -> IMU pose guess -> LK frame->frame -> keep rule -> F-matrix RANSAC ->
+    PnP RANSAC -> IMU roll/pitch blend -> pose-only BA -> reprojection cull -> FeatureDEM redetect (Shi-Tomasi + region
+    select) -> new landmarks -> LK left->right -> triangulation / depth filter -> keyframe rule, IMU bias feedback
+and every keyframe goes to the local-map worker (10-keyframe sliding-window BA, 12 + cull + 8 LM iterations,
+src/backend/vo_localmap.cpp:87-380), which runs concurrently like FLVIS's local-map nodelet; the timed region ends when
+the last window it triggered is solved.
+`value`  : device-timed (CUDA events on the compute stream), frames already resident in HBM (device-side frame pool).
+`e2e`    : the same call with the frames in pinned HOST memory: both images of every sequence cross PCIe every step and the
+           per-sequence results (pose, landmark lists) are read back every step.
+Multi-GPU: sequences are independent; rank r owns global streams [r*S, (r+1)*S) ("weak" scaling), no
+collective in the frame loop; the per-frame results of every rank are all-gathered (NCCL) once per timed region.
+`--impl reference`: the reference's CPU path on the host cores -- the OpenCV calls through cv2 (the library the reference
+links) and the C port of its g2o solver -- same frame, bounded sample.
 """
 import argparse
+import ctypes as C
 import json
 import os
 import subprocess
@@ -29,85 +34,107 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 from flvis_b200 import sharding  # noqa: E402
+from synthdata import sequences  # noqa: E402
 
-W, H = 752, 480
-NPTS = 480
-MAX_PTS = 512
-KF_EVERY = 5
-BA_WINDOW = 10
-BA_LANDMARKS = 1500
-STEREO = True
-WORKLOAD = "euroc"
-WORKLOADS = {   # BASELINE.json configs: image size, stereo, local-BA window / landmarks
-    "euroc": dict(w=752, h=480, stereo=True, window=10, landmarks=1500, name="EuRoC-shaped 752x480 stereo (configs[1]/[2])"),
-    "kitti": dict(w=1241, h=376, stereo=True, window=20, landmarks=2000, name="KITTI-shaped 1241x376 stereo, 20-KF / 2k-landmark window (configs[3])"),
-    "d435": dict(w=640, h=480, stereo=False, window=10, landmarks=1500, name="640x480 D435i depth (configs[4]); depth lookups are per-point reads, no right image"),
+NPTS_MAX = 480                                    # 16 regions x 30 landmarks (feature_dem.cpp:21,188,250)
+WORKLOADS = {   # BASELINE.json configs: image size, sensor, local-BA window
+    "euroc": dict(w=752, h=480, stereo=True, window=10, imu=True,
+                  name="EuRoC-shaped 752x480 raw stereo (radtan lenses, STEREO_UNRECT, equalizeHist) + IMU 200 Hz, 10-KF local BA (configs[1]/[2])"),
+    "kitti": dict(w=1241, h=376, stereo=True, window=20, imu=False,
+                  name="KITTI-shaped 1241x376 rectified stereo, no IMU, 20-KF local-BA window (configs[3])"),
+    "d435": dict(w=640, h=480, stereo=False, window=8, imu=True,
+                 name="640x480 D435i depth + IMU 200 Hz, 8-KF local BA (configs[0]/[4])"),
 }
-FEATURE_PARA = [30, 20, 5, 1000, 0.01, 10]       # launch/EuRoC_MAV/euroc.yaml:57-67
-P_PYR = 479400                                    # pyramid pixels of 752x480
-LK_BYTES_PER_CALL = 6 * P_PYR + 29 * NPTS         # algorithmic bytes of one LK call, one stream: both u8 pyramids + the
-                                                  # 4 B/px Scharr pyramid of the first image + 29 B per point
-LK_NCU_TRAFFIC = 95.5e6                           # dram read+write of one lk_track_kernel_v4 launch, 32 streams
-                                                  # (profiles/r01_lk_v4_ncu_full.csv: 91.8 MB + 3.8 MB)
+PERIOD = 40                                       # frames per period of the synthetic rig trajectory
+LK_NCU_TRAFFIC = {"euroc": None}                  # dram bytes per launch from profiles/ (filled in when a capture exists)
+LK_WARP_INSTR_PER_POINT = 13900.0                 # profiles/r01_final_kernels_ncu_full.csv: 212.9 M warp instructions / (32 x 480) points
+
+
+def pyramid_pixels(w, h):
+    """P(w,h) of SURVEY.md 8(d): pixels of the levels OpenCV builds for a 31x31 window."""
+    tot, lw, lh = w * h, w, h
+    for _ in range(3):
+        lw, lh = (lw + 1) // 2, (lh + 1) // 2
+        if lw <= 31 or lh <= 31:
+            break
+        tot += lw * lh
+    return tot
+
+
+def lk_algorithmic_bytes(w, h, n_pts):
+    """both u8 pyramids read once + 29 B of point I/O per tracked point."""
+    return 2 * pyramid_pixels(w, h) + 29 * n_pts
 
 
 def load_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
         d = json.load(open(p))
-        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
-    return 6650.0, "fallback (B200_PROFILING.md)"
+        return float(d["hbm_gbs"]), float(d.get("sm_max_mhz", 1965.0)), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, 1965.0, "fallback (B200_PROFILING.md)"
 
 
 # ------------------------------------------------------------------------------------------------
-# synthetic EuRoC-shaped stereo streams: per-stream textured canvas, integer-pixel camera motion,
-# right image = left shifted by an integer disparity.  Frames are crops, so generation is cheap.
-MOTION = [(3, 1), (2, -2), (-3, 2), (-2, -1)]     # cumulative motion is periodic => points stay in view
+def build_pools(workload, first_stream, n_streams, procs):
+    """One period (+ start-up) of rendered frames and IMU samples per stream; rendering is CPU work done in a fork pool
+    BEFORE any CUDA initialisation."""
+    jobs = [(workload, first_stream + s, PERIOD) for s in range(n_streams)]
+    if procs > 1 and n_streams > 1:
+        import multiprocessing as mp
+        with mp.get_context("fork").Pool(min(procs, n_streams)) as pool:
+            res = pool.map(sequences.render_pool, jobs)
+    else:
+        res = [sequences.render_pool(j) for j in jobs]
+    f0 = np.stack([r[0] for r in res], 1)         # [n][S][h][w]
+    f1 = np.stack([r[1] for r in res], 1)
+    imu = [r[2] for r in res]                     # [S][n] arrays (k, 7)
+    return f0, f1, imu
 
 
-def make_streams(n_streams, seed0, n_frames):
-    """Streams with global ids seed0 .. seed0+n_streams-1 (flvis_b200.sharding.stream_seed gives the texture seed)."""
-    from synthdata import textures as synth
-    frames0 = np.empty((n_frames, n_streams, H, W), np.uint8)
-    frames1 = np.empty((n_frames, n_streams, H, W), np.uint8)
-    for s in range(n_streams):
-        canvas = synth.texture(sharding.stream_seed(seed0 + s), H + 64, W + 128, blur=2)
-        ox, oy = 48, 32
-        disp = 20 + (s % 7)
-        for t in range(n_frames):
-            frames0[t, s] = canvas[oy:oy + H, ox:ox + W]
-            frames1[t, s] = canvas[oy:oy + H, ox - disp + 32:ox - disp + 32 + W]
-            dx, dy = MOTION[t % len(MOTION)]
-            ox += dx; oy += dy
-    return frames0, frames1
+class FrameFeeder:
+    """Maps step i to (pool frame, time offset) and holds the IMU samples of every pool frame for all streams."""
+
+    def __init__(self, workload, first_stream, S, imu):
+        self.seq0 = sequences.make_bench(workload, first_stream, PERIOD, render=False)
+        self.n_startup, self.period, self.hz, self.S = self.seq0.n_startup, PERIOD, self.seq0.img_hz, S
+        self.Tp = PERIOD / self.hz
+        self.imu = []
+        for f in range(self.n_startup + PERIOD):
+            rows = [imu[s][f] for s in range(S)]
+            st = np.concatenate([np.full(len(r), s, np.int32) for s, r in enumerate(rows)])
+            a = np.concatenate(rows)
+            self.imu.append((np.ascontiguousarray(st), np.ascontiguousarray(a[:, 0]), np.ascontiguousarray(a[:, 1:4]), np.ascontiguousarray(a[:, 4:7])))
+
+    def locate(self, i):
+        if i < self.n_startup:
+            return i, 0.0
+        k = i - self.n_startup
+        return self.n_startup + k % self.period, (k // self.period) * self.Tp
+
+    def time_of(self, i):
+        return i / self.hz
 
 
 # ------------------------------------------------------------------------------------------------
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    """SM clocks / throttle reasons during the timed regions (B200_PROFILING.md recipe), NVML polling."""
 
     def __init__(self, index):
         super().__init__(daemon=True)
-        self.index = index
-        self.stop_flag = threading.Event()
-        self.rows = []
+        self.index, self.stop_flag, self.rows = index, threading.Event(), []
 
     def run(self):
-        # NVML (pynvml) polls every few milliseconds -- the timed region is only tens of milliseconds long; nvidia-smi
-        # (one process spawn per sample) is the fallback
         try:
             import pynvml
             pynvml.nvmlInit()
             h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
             mx = pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM)
-            bits = [("hw_slowdown", pynvml.nvmlClocksThrottleReasonHwSlowdown),
-                    ("hw_thermal_slowdown", pynvml.nvmlClocksThrottleReasonHwThermalSlowdown),
-                    ("sw_thermal_slowdown", pynvml.nvmlClocksThrottleReasonSwThermalSlowdown),
-                    ("sw_power_cap", pynvml.nvmlClocksThrottleReasonSwPowerCap)]
+            bits = [pynvml.nvmlClocksThrottleReasonHwSlowdown, pynvml.nvmlClocksThrottleReasonHwThermalSlowdown,
+                    pynvml.nvmlClocksThrottleReasonSwThermalSlowdown, pynvml.nvmlClocksThrottleReasonSwPowerCap]
             while not self.stop_flag.is_set():
                 sm = pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)
                 r = pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(h)
-                self.rows.append([str(sm), str(mx)] + ["Active" if (r & b) else "Not Active" for _, b in bits])
+                self.rows.append([float(sm), float(mx)] + [bool(r & b) for b in bits])
                 self.stop_flag.wait(0.005)
             return
         except Exception:
@@ -116,10 +143,11 @@ class ClockSampler(threading.Thread):
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
         while not self.stop_flag.is_set():
             try:
-                out = subprocess.run(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-i",
-                                      str(self.index)], capture_output=True, text=True, timeout=5).stdout.strip()
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
                 if out:
-                    self.rows.append([c.strip() for c in out.split(",")])
+                    c = [x.strip() for x in out.split(",")]
+                    self.rows.append([float(c[0]), float(c[1])] + [x.lower().startswith("active") for x in c[2:6]])
             except Exception:
                 pass
             self.stop_flag.wait(0.2)
@@ -127,215 +155,350 @@ class ClockSampler(threading.Thread):
     def summary(self):
         if not self.rows:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        sm = sorted(float(r[0]) for r in self.rows)
-        reasons = []
+        sm = sorted(r[0] for r in self.rows)
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for i, n in enumerate(names):
-            if any(r[2 + i].lower().startswith("active") for r in self.rows):
-                reasons.append(n)
-        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(self.rows[0][1]), "reasons": reasons,
-                "samples": len(self.rows)}
+        reasons = [n for i, n in enumerate(names) if any(r[2 + i] for r in self.rows)]
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": self.rows[0][1], "reasons": reasons, "samples": len(self.rows)}
+
+
+def _cam_centre(T7):
+    x, y, z, w = T7[:4]
+    R = np.array([[1 - 2 * (y * y + z * z), 2 * (x * y - z * w), 2 * (x * z + y * w)],
+                  [2 * (x * y + z * w), 1 - 2 * (x * x + z * z), 2 * (y * z - x * w)],
+                  [2 * (x * z - y * w), 2 * (y * z + x * w), 1 - 2 * (x * x + y * y)]])
+    return -R.T @ np.asarray(T7[4:], float)
+
+
+def _issue_roofline(lk_us, S, n_pts, sm_mhz):
+    """Secondary roofline for LK: warp instructions per launch against the chip's issue rate (4 schedulers x 148 SMs x clock)."""
+    if not lk_us:
+        return None
+    instr = LK_WARP_INSTR_PER_POINT * S * n_pts
+    peak = 4 * 148 * sm_mhz * 1e6
+    return {"warp_instructions_per_launch": instr, "achieved_per_s": instr / (lk_us * 1e-6), "peak_per_s": peak,
+            "frac": instr / (lk_us * 1e-6) / peak, "source": "instructions per point from the ncu capture in profiles/, time from this run"}
 
 
 # ------------------------------------------------------------------------------------------------
-def run_ours(args):
+def run_ours(args, wl, pools):
     import torch
     import torch.distributed as dist
-    from flvis_b200 import capi
-    from flvis_b200.pipeline import FrontendBench
+    from flvis_b200 import batch as fb
 
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if world > 1:
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")     # keep stdout to the one JSON line (NCCL prints its version)
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")     # keep stdout to the one JSON line
         dist.init_process_group("nccl", init_method="env://", device_id=torch.device("cuda", local_rank))
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     S = args.streams
-    n_pool = 8                                        # distinct frames per stream in the pool (cycled)
-    f0, f1 = make_streams(S, sharding.stream_ids(rank, world, S)[0], n_pool)     # rank r owns streams [r*S, (r+1)*S)
-    bench = FrontendBench(S, W, H, MAX_PTS, NPTS, FEATURE_PARA, local_rank, ba_window=BA_WINDOW,
-                          kf_every=KF_EVERY, seed=rank, stereo=STEREO, ba_landmarks=BA_LANDMARKS)
-    bench.load_pool(f0, f1)
+    W, H = wl["w"], wl["h"]
+    first = sharding.stream_ids(rank, world, S)[0]
+    f0, f1, imu = pools
+    feeder = FrameFeeder(args.workload, first, S, imu)
+    cfg, lenses, equalize, K, _ = fb.config_for(feeder.seq0)
+    h_pool0 = torch.from_numpy(f0).pin_memory()
+    h_pool1 = torch.from_numpy(f1.view(np.uint8) if f1.dtype == np.uint16 else f1).pin_memory()
+    d_pool0 = h_pool0.to(dev); d_pool1 = h_pool1.to(dev)
+    stream = torch.cuda.Stream(dev)
+
+    def make_tracker(n):
+        t = fb.BatchTracker(cfg, n, device=local_rank, lenses=lenses, equalize=equalize)
+        t.set_stream(stream.cuda_stream)
+        lm = fb.LocalMapBatch(n, wl["window"], K, device=local_rank)
+        t.attach_localmap(lm)
+        return t, lm
+
+    trk, lmap = make_tracker(S)
+    tvec = np.zeros(S)
+
+    def feed(t, i, mode, n=S):
+        f, off = feeder.locate(i)
+        if wl["imu"]:
+            st, ti, acc, gyro = feeder.imu[f]
+            if n != S:
+                m = st < n
+                st, ti, acc, gyro = np.ascontiguousarray(st[m]), np.ascontiguousarray(ti[m]), np.ascontiguousarray(acc[m]), np.ascontiguousarray(gyro[m])
+            t.imu_feed_many(st, (ti + off) if off else ti, acc, gyro)
+        tv = tvec[:n]
+        tv[:] = feeder.time_of(i)
+        if mode == "host":
+            t.image_feed(tv, h_pool0[f].data_ptr(), h_pool1[f].data_ptr(), False)
+        else:
+            t.image_feed(tv, d_pool0[f].data_ptr(), d_pool1[f].data_ptr(), True)
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    host_ms = {}
+    # per-frame results of every rank, all-gathered once per timed region (north_star: NCCL only for the batch gather)
+    gather = sharding.ResultGather(dist, args.steps, S, dev, stream) if world > 1 else None
 
-    def timed(mode, steps, warmup, bench=bench):
-        bench.reset()
-        for i in range(warmup):
-            bench.step(i, mode)
-        bench.join()
+    step_no = [0]
+    traj = [[] for _ in range(S)]
+
+    def region(t, lm, steps, mode, n=S, record=False):
         barrier()
-        launches0 = bench.ctx.launches
+        l0 = t.launches(); s0 = lm.stats()
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        bench.lk_ms = 0.0
-        bench.collect_lk = True
-        ev0.record(bench.stream)
-        t_host = time.perf_counter()
-        for i in range(steps):
-            bench.step(warmup + i, mode)
-        host_ms[mode] = (time.perf_counter() - t_host) * 1e3 / steps      # host time to SUBMIT one step (no sync in device mode)
-        bench.join()                       # the timed region ends when the asynchronous BA streams have drained too
-        ev1.record(bench.stream)
+        ev0.record(stream)
+        for j in range(steps):
+            feed(t, step_no[0], mode, n)
+            if gather is not None and n == S:
+                for s in range(S):
+                    gather.record(j, s, t.pose(s), t.n_landmarks(s))
+            if record:
+                tt = feeder.time_of(step_no[0])
+                for s in range(n):
+                    if t.state(s) == "Tracking":
+                        traj[s].append((tt, t.pose(s)))
+            step_no[0] += 1
+        lm.wait()                                  # the region ends when the last local-BA window it triggered is solved
+        if gather is not None and n == S:
+            gather.flush()
+            gather.wait()
+        ev1.record(stream)
         barrier()
         ms = ev0.elapsed_time(ev1)
-        lk_ms, lk_calls = bench.finish_lk_timing()
-        ms = sharding.max_over_ranks(ms, dist if world > 1 else None, dev)        # job time = slowest rank
-        return ms, bench.ctx.launches - launches0, lk_ms, lk_calls
+        s1 = lm.stats()
+        return ms, t.launches() - l0 + (s1["launches"] - s0["launches"]), {k: s1[k] - s0[k] for k in s1}
+
+    # start-up (UnInit -> IMU initialised -> first keyframe) + warm-up, untimed
+    for _ in range(feeder.n_startup + max(args.warmup, 3)):
+        feed(trk, step_no[0], "device"); step_no[0] += 1
+    lmap.wait()
+    n_tracking = sum(trk.state(s) == "Tracking" for s in range(S))
 
     sampler = ClockSampler(local_rank) if rank == 0 else None
     if sampler:
         sampler.start()
-    ms_dev, launches, lk_ms, lk_calls = timed("device", args.steps, args.warmup)
-    ms_e2e, _, _, _ = timed("host", args.steps, args.warmup)
+    trk.set_profile(True)
+    dev_runs, e2e_runs, launches, ba_tot = [], [], 0, dict(keyframes=0, solves=0, launches=0, solve_ms=0.0)
+    for r in range(args.reps):
+        ms, nl, ba = region(trk, lmap, args.steps, "device", record=(r == 0))
+        dev_runs.append(ms); launches = nl
+        for k in ba_tot:
+            ba_tot[k] += ba[k]
+    stage_ms, prof_frames = trk.profile()
+    trk.set_profile(False)
+    n_lm_mean = float(np.mean([trk.n_landmarks(s) for s in range(S)]))
+    for r in range(args.reps):
+        e2e_runs.append(region(trk, lmap, args.steps, "host")[0])
     if sampler:
         sampler.stop_flag.set(); sampler.join(timeout=2)
-    # BASELINE configs[1]: ONE stream on the GPU (latency-oriented), reported next to the batched headline
-    single = None
-    if world == 1 and S > 1:
-        b1 = FrontendBench(1, W, H, MAX_PTS, NPTS, FEATURE_PARA, local_rank, ba_window=BA_WINDOW, kf_every=KF_EVERY, seed=rank,
-                           stereo=STEREO, ba_landmarks=BA_LANDMARKS)
-        b1.load_pool(f0[:, :1].copy(), f1[:, :1].copy())
-        k1 = max(args.steps, 50)
-        ms1, _, _, _ = timed("device", k1, args.warmup, bench=b1)
-        ms1h, _, _, _ = timed("host", k1, args.warmup, bench=b1)
-        single = {"workload": "1 EuRoC-shaped 752x480 stereo stream, LK frontend + 10-KF local BA (BASELINE configs[1])",
-                  "steps": k1, "value": k1 / (ms1 * 1e-3), "e2e": k1 / (ms1h * 1e-3), "unit": "frames/s",
-                  "ms_per_frame": ms1 / k1}
+    still_tracking = sum(trk.state(s) == "Tracking" for s in range(S))
+    per_rank_ms = None
+    if world > 1:
+        t_all = [torch.zeros(1, device=dev, dtype=torch.float64) for _ in range(world)]
+        dist.all_gather(t_all, torch.tensor([float(np.median(dev_runs))], device=dev, dtype=torch.float64))
+        per_rank_ms = [float(x.item()) for x in t_all]
+    # job time = slowest rank, repetition by repetition
+    dev_runs = [sharding.max_over_ranks(m, dist if world > 1 else None, dev) for m in dev_runs]
+    e2e_runs = [sharding.max_over_ranks(m, dist if world > 1 else None, dev) for m in e2e_runs]
 
-    frames = args.steps * S * world
-    peak, peak_src = load_peaks()
+    # BASELINE configs[1]: ONE stream on the GPU (latency-oriented), same call
+    single = None
+    if world == 1 and S > 1 and not args.no_single:
+        t1, lm1 = make_tracker(1)
+        keep = step_no[0]
+        step_no[0] = 0
+        for _ in range(feeder.n_startup + 3):
+            feed(t1, step_no[0], "device", 1); step_no[0] += 1
+        k1 = max(args.steps, 40)
+        ms1 = sorted(region(t1, lm1, k1, "device", 1)[0] for _ in range(3))[1]
+        ms1h = sorted(region(t1, lm1, k1, "host", 1)[0] for _ in range(3))[1]
+        single = {"workload": "1 sequence, " + wl["name"], "steps": k1, "value": k1 / (ms1 * 1e-3), "e2e": k1 / (ms1h * 1e-3),
+                  "unit": "frames/s", "ms_per_frame": ms1 / k1}
+        step_no[0] = keep
+        t1.close(); lm1.close()
+
     out = None
     if rank == 0:
-        lk_us = 1e3 * lk_ms / max(lk_calls, 1)
-        achieved = LK_BYTES_PER_CALL * S / (lk_us * 1e-6) / 1e9 if lk_us > 0 else 0.0
-        # bounded sample of the same workload on every host core: all S streams, 6 frames each
-        cpu = cpu_baseline(min(S, os.cpu_count() or 1), 6, args) if world == 1 and not args.no_cpu else None
-        if single is not None and not args.no_cpu:
-            single["cpu_value"] = cpu_baseline(1, 10, args)["value"]      # same single stream on the host (cv2 uses all cores)
+        frames = args.steps * S * world
+        med = float(np.median(dev_runs)); med_e = float(np.median(e2e_runs))
+        peak, sm_max, peak_src = load_peaks()
+        per_frame = stage_ms / max(prof_frames, 1)
+        lk_us = 1e3 * float(per_frame[1])                                     # frame->frame call (maxLevel 10)
+        lk_lr_us = 1e3 * float(per_frame[7]) if wl["stereo"] else None        # + the tiny right-point undistortion kernel
+        alg = lk_algorithmic_bytes(W, H, n_lm_mean) * S
+        achieved = alg / (lk_us * 1e-6) / 1e9 if lk_us > 0 else 0.0
+        # ATE of the GPU trajectories against the synthetic ground truth (camera centres, constant offset removed)
+        ates = []
+        for s in range(S):
+            if len(traj[s]) < 5:
+                continue
+            gt_seq = sequences.make_bench(args.workload, first + s, PERIOD, render=False)
+            c = np.array([_cam_centre(T) for _, T in traj[s]]); g = np.array([gt_seq.T_w_c0(tt).t for tt, _ in traj[s]])
+            d = c - g
+            ates.append(float(np.sqrt(np.mean(np.sum((d - d.mean(0)) ** 2, axis=1)))))
+        img1_bytes = W * H * (1 if wl["stereo"] else 2)
+        h2d = S * (W * H + img1_bytes) + S * (160 + 512 * 4)                  # images + control block + dummy-depth table
+        d2h = S * 120 + S * 512 * 170                                         # summaries + the landmark lists (170 B per landmark slot)
+        cpu = cpu_baseline(args, wl, pools, min(S, os.cpu_count() or 1), 6) if world == 1 and not args.no_cpu else None
+        if single is not None and cpu is not None:
+            single["cpu_value"] = cpu_baseline(args, wl, pools, 1, 8)["value"]
         out = {
-            "metric": "frames/sec (device-timed), EuRoC-shaped 752x480 stereo, LK frontend + 10-KF local BA" if WORKLOAD == "euroc"
-                      else f"frames/sec (device-timed), {WORKLOADS[WORKLOAD]['name']}",
-            "value": frames / (ms_dev * 1e-3), "unit": "frames/s", "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms_dev / args.steps, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "u8/i32 fixed-point + f32 (frontend), f64 (BA)",
-            "data": "synthetic",
-            "config": {"workload": (f"{S} concurrent EuRoC-shaped 752x480 stereo streams per GPU (BASELINE configs[2]); " if WORKLOAD == "euroc"
-                                    else f"{S} concurrent streams per GPU, {WORKLOADS[WORKLOAD]['name']}; ") +
-                                   f"480 pts/stream, LK 31x31 4 levels x2, GFTT N=1000 + FeatureDEM redetect, "
-                                   f"local BA W={BA_WINDOW} every {KF_EVERY}th frame" + ("" if bench.has_ba else " [BA NOT YET IN STEP]"),
-                       "streams_per_gpu": S, "image": [W, H], "points_per_stream": NPTS,
-                       "l2_note": "no explicit L2 flush: every step ingests two fresh S*361 KB image sets from a rotating "
-                                  "frame pool and rewrites all pyramids, so no step reuses another step's cached inputs",
-                       "e2e_pipeline": "H2D of frame k+1 (library copy stream) and the host's read of frame k-1's results "
-                                       "overlap the kernels of frame k; every frame's inputs and outputs cross PCIe "
-                                       "inside the timed region (pinned host buffers, one frame of result latency)",
-                       "parallelism": f"streams sharded {S}/GPU x {world} GPU, no data-path collective",
-                       "host_submit_ms_per_step": {k: round(v, 3) for k, v in host_ms.items()}},
-            "e2e": {"value": frames / (ms_e2e * 1e-3), "unit": "frames/s",
-                    "h2d_bytes_per_step": bench.h2d_bytes_per_step, "d2h_bytes_per_step": bench.d2h_bytes_per_step,
-                    "ms_per_step": ms_e2e / args.steps},
-            "gpu_launches": launches,
+            "metric": f"frames/sec (device-timed), {wl['name']}",
+            "value": frames / (med * 1e-3), "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": med / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "u8/i32 fixed-point + f32 (LK, Shi-Tomasi), f64 (RANSAC, geometry, BA)", "data": "synthetic",
+            "config": {"workload": f"{S} concurrent sequences per GPU, {wl['name']}; full F2FTracking::image_feed per frame (LK x2, F + PnP RANSAC, "
+                                   f"pose-only BA, FeatureDEM redetect, depth innovation) + local BA W={wl['window']} on every keyframe"
+                                   + (" (BASELINE configs[2])" if args.workload == "euroc" else ""),
+                       "streams_per_gpu": S, "image": [W, H], "landmarks_per_stream_mean": n_lm_mean,
+                       "streams_tracking_before_after": [n_tracking, still_tracking],
+                       "repetitions": args.reps, "value_min_max": [frames / (max(dev_runs) * 1e-3), frames / (min(dev_runs) * 1e-3)],
+                       "l2_note": "no explicit L2 flush: every step ingests fresh images for all sequences from a rotating frame pool of "
+                                  f"{f0.shape[0]} frames per sequence ({round((f0.nbytes + f1.nbytes) / 1e6)} MB, larger than the 126 MB L2) and "
+                                  "rewrites every pyramid",
+                       "parallelism": f"sequences sharded {S}/GPU x {world} GPU, no collective in the frame loop; per-frame results of all ranks "
+                                      "all-gathered (NCCL) once per timed region" + ("" if world > 1 else " when N > 1"),
+                       "per_rank_ms": per_rank_ms},
+            "e2e": {"value": frames / (med_e * 1e-3), "unit": "frames/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                    "ms_per_step": med_e / args.steps, "value_min_max": [frames / (max(e2e_runs) * 1e-3), frames / (min(e2e_runs) * 1e-3)]},
+            "gpu_launches": int(launches),
+            "stages_ms_per_step": {n: round(float(v), 4) for n, v in zip(fb.STAGES, per_frame)},
+            "ba": {"ms_per_kf": (ba_tot["solve_ms"] / ba_tot["solves"]) if ba_tot["solves"] else None,
+                   "note": "wall time of one batched flv_ba_optimize call (H2D of the window arrays + ba_kernel + D2H) divided by the "
+                           "windows it solved; the worker overlaps the tracker's kernels",
+                   "window": wl["window"], "keyframes": ba_tot["keyframes"], "solves": ba_tot["solves"],
+                   "windows_per_launch": ba_tot["solves"] / max(ba_tot["launches"], 1),
+                   "keyframes_per_step": ba_tot["keyframes"] / (args.reps * args.steps)},
+            "ate": {"vs_ground_truth_m_mean": float(np.mean(ates)) if ates else None, "vs_ground_truth_m_max": float(np.max(ates)) if ates else None,
+                    "frames": args.steps, "note": "RMSE of the camera centres against the synthetic rig trajectory over the first timed "
+                                                  "region; ATE against the reference path is asserted in tests/test_configs_gpu.py"},
             "single_stream": single,
-            "roofline": {"kernel": "lk_track_kernel_v4 (frame->frame + left->right)", "bound": "hbm",
-                         "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": LK_NCU_TRAFFIC * S / 32 if WORKLOAD == "euroc" else None, "peak_source": peak_src,
-                         "us_per_launch": lk_us, "algorithmic_bytes_per_launch": LK_BYTES_PER_CALL * S,
-                         "note": "LK is instruction-issue bound, not HBM bound (ncu: DRAM < 3 % busy, traffic == algorithmic "
-                                 "bytes, i.e. no re-reads); us_per_launch is measured inside the step, where other streams' "
-                                 "kernels share the SMs (269 / 295 us alone); see DESIGN.md section 5"},
+            "roofline": {"kernel": "lk_track_kernel_v4 (frame->frame call)", "bound": "hbm", "achieved": achieved, "peak": peak,
+                         "unit": "GB/s", "frac": achieved / peak, "traffic": LK_NCU_TRAFFIC.get(args.workload),
+                         "peak_source": peak_src, "us_per_launch": lk_us, "us_per_launch_left_right": lk_lr_us,
+                         "algorithmic_bytes_per_launch": alg,
+                         "algorithmic_bytes_def": "SURVEY.md 8(d): (2 P(w,h) + 29 N) x S, P = pyramid pixels, N = mean tracked points per sequence",
+                         "traffic_expected": (6 * pyramid_pixels(W, H) + 29 * n_lm_mean) * S,
+                         "traffic_expected_def": "what the kernel must read with its 4 B/px Scharr derivative pyramid of the first image",
+                         "issue_slot_roofline": _issue_roofline(lk_us, S, n_lm_mean, sm_max),
+                         "note": "LK is bound by instruction issue, not by HBM (ncu: DRAM < 3 % busy); the issue-slot figure is the "
+                                 "roofline that explains it (DESIGN.md section 5)"},
             "clocks": sampler.summary() if sampler else None,
         }
         if cpu:
             out["cpu_baseline"] = cpu
         print(json.dumps(out))
+    trk.close(); lmap.close()
     if world > 1:
         dist.destroy_process_group()
     return out
 
 
 # ------------------------------------------------------------------------------------------------
-def cpu_frame(cv2, fd_para, prev0, cur0, cur1, pts, crit):
-    """One stereo frame of the reference's OpenCV stages for one stream (call sites in the module docstring)."""
+# The reference's CPU path for the same frame: every OpenCV call FLVIS makes per frame through cv2 (the same library),
+# its g2o solves through the C port (oracle/ba_ref.c).  The Python between the calls is array slicing only.
+def cpu_frame_chain(cv2, ba_ref, wl, rig, prev0, cur0, cur1, pts, p3d, T_guess, ba_window_problem, is_kf):
+    crit = (cv2.TERM_CRITERIA_COUNT + cv2.TERM_CRITERIA_EPS, 30, 0.001)
+    if rig["equalize"]:
+        cur0 = cv2.equalizeHist(cur0)                                                         # f2f_tracking.cpp:141-145
+        if cur1 is not None:
+            cur1 = cv2.equalizeHist(cur1)
     nxt, st, _ = cv2.calcOpticalFlowPyrLK(prev0, cur0, pts, pts.copy(), winSize=(31, 31), maxLevel=10, criteria=crit,
-                                          flags=cv2.OPTFLOW_USE_INITIAL_FLOW)            # lkorb_tracking.cpp:64-73
-    mask = np.full(cur0.shape, 255, np.uint8)
-    cv2.goodFeaturesToTrack(cur0, fd_para[3], fd_para[4], fd_para[5], mask=mask)        # feature_dem.cpp:160
-    if STEREO:
-        cv2.calcOpticalFlowPyrLK(cur0, cur1, nxt, nxt.copy(), winSize=(31, 31), maxLevel=5, criteria=crit,
-                                 flags=cv2.OPTFLOW_USE_INITIAL_FLOW)                     # camera_frame.cpp:124-128
+                                          flags=cv2.OPTFLOW_USE_INITIAL_FLOW)                 # lkorb_tracking.cpp:64-73
     ok = st.ravel() == 1
+    a, b = pts[ok], nxt[ok]
+    if rig["lens0"] is not None and len(a):                                                   # lkorb_tracking.cpp:86-89
+        K0, D0, R0, P0 = rig["lens0"]
+        a = cv2.undistortPoints(a.reshape(-1, 1, 2), K0, D0, R=R0, P=P0[:3, :3]).reshape(-1, 2)
+        b = cv2.undistortPoints(b.reshape(-1, 1, 2), K0, D0, R=R0, P=P0[:3, :3]).reshape(-1, 2)
+    if len(a) >= 8:
+        cv2.findFundamentalMat(a, b, cv2.FM_RANSAC, 5.0, 0.99)                                # :134-135
+    X = p3d[ok]
+    if len(X) >= 10:
+        rvec, tvec = T_guess
+        cv2.solvePnPRansac(X, b, rig["Km"], np.zeros(4), rvec.copy(), tvec.copy(), True, 100, 3.0, 0.99, flags=cv2.SOLVEPNP_ITERATIVE)   # :172-176
+        n = len(X)                                                                            # optimize_in_frame.cpp:10-90
+        d = ba_ref.BAData(rig["pose7"][None].copy(), X.astype(np.float64), np.zeros(n, np.int32), np.arange(n, dtype=np.int32),
+                          b.astype(np.float64), rig["K4"], fixed_pose=-1, fix_landmarks=1)
+        ba_ref.optimize(d, 2, 2, min_edges_after_cull=10)
+    mask = np.full(cur0.shape, 255, np.uint8)
+    cv2.goodFeaturesToTrack(cur0, rig["gftt"][0], rig["gftt"][1], rig["gftt"][2], mask=mask)  # feature_dem.cpp:160
+    if cur1 is not None:
+        r, _, _ = cv2.calcOpticalFlowPyrLK(cur0, cur1, nxt, nxt.copy(), winSize=(31, 31), maxLevel=5, criteria=crit,
+                                           flags=cv2.OPTFLOW_USE_INITIAL_FLOW)                # camera_frame.cpp:124-128
+        if rig["lens1"] is not None:
+            K1, D1, R1, P1 = rig["lens1"]
+            cv2.undistortPoints(r.reshape(-1, 1, 2), K1, D1, R=R1, P=P1[:3, :3])              # :130
+    if is_kf and ba_window_problem is not None:                                               # vo_localmap.cpp:292-319
+        p = ba_window_problem
+        ba_ref.optimize(ba_ref.BAData(p.poses.copy(), p.lms.copy(), p.ep, p.el, p.uv, p.K, p.fixed_pose, p.fix_landmarks), 12, 8)
     nxt[~ok] = pts[~ok]
-    return nxt
+    return nxt, cur0
 
 
-def cpu_baseline(n_streams, n_frames, args):
-    """Reference CPU path on this box's host cores, bounded sample: n_streams streams x n_frames frames."""
+def cpu_baseline(args, wl, pools, n_streams, n_frames):
+    """Reference CPU path on this box's host cores, bounded sample: n_streams sequences x n_frames frames."""
     import cv2
     from concurrent.futures import ThreadPoolExecutor
+    from oracle import ba_ref                      # the cpu_baseline leg: the one place bench.py executes oracle/
+    from flvis_b200 import batch as fb
+    from synthdata import ba_problems
     cores = os.cpu_count() or 1
     workers = min(n_streams, cores)
     cv2.setNumThreads(max(1, cores // workers))
-    f0, f1 = make_streams(n_streams, 0, n_frames + 1)
-    crit = (cv2.TERM_CRITERIA_COUNT + cv2.TERM_CRITERIA_EPS, 30, 0.001)
-    pts0 = [cv2.goodFeaturesToTrack(f0[0, s], NPTS, 0.01, 10).reshape(-1, 2) for s in range(n_streams)]
-    ba = None
-    try:
-        from flvis_b200.pipeline import make_ba_batch
-        from oracle import ba_ref                    # the cpu_baseline leg: the one place bench.py executes oracle/
-        ba = make_ba_batch(n_streams, BA_WINDOW, seed=7, n_landmarks=BA_LANDMARKS)
-
-        def cpu_ba_solve(batch, s):
-            p = batch.problems[s]
-            ba_ref.optimize(ba_ref.BAData(p.poses.copy(), p.lms.copy(), p.ep, p.el, p.uv, p.K, p.fixed_pose, p.fix_landmarks), 12, 8)
-    except Exception:
-        ba = None
+    f0, f1, _ = pools
+    seq0 = sequences.make_bench(args.workload, 0, PERIOD, render=False)
+    cfg, lenses, equalize, K, rect = fb.config_for(seq0)
+    c = seq0.cfg
+    rig = dict(equalize=equalize, K4=tuple(float(v) for v in K), Km=np.array([[K[0], 0, K[2]], [0, K[1], K[3]], [0, 0, 1.0]]),
+               gftt=(int(c["feature_para"][3]), float(c["feature_para"][4]), float(c["feature_para"][5])),
+               lens0=None, lens1=None, pose7=np.array([0, 0, 0, 1.0, 0, 0, 0]))
+    if rect is not None:
+        rig["lens0"] = (rect["K0"], rect["D0"], rect["R0"], rect["P0"]); rig["lens1"] = (rect["K1"], rect["D1"], rect["R1"], rect["P1"])
+    base = seq0.n_startup
+    kf_every = 4                                                                              # the GPU arm's keyframe rate on this trajectory
+    obs = 330                                                                                 # inlier landmarks with depth per keyframe in the GPU arm
+    windows = [ba_problems.make_problem(wl["window"], 3 * obs, obs, seed=900 + s, K=rig["K4"], w=wl["w"], h=wl["h"]) for s in range(n_streams)]
+    prev, pts0 = [], []
+    for s in range(n_streams):
+        img = cv2.equalizeHist(f0[base, s]) if equalize else f0[base, s]
+        prev.append(img)
+        pts0.append(cv2.goodFeaturesToTrack(img, NPTS_MAX, 0.01, 10).reshape(-1, 2))
+    rv, tv = np.zeros((3, 1)), np.zeros((3, 1))
+    Z = 3.0 if args.workload != "kitti" else 12.0
 
     def work(s):
-        pts = pts0[s]
+        pts, last = pts0[s], prev[s]
         for t in range(1, n_frames + 1):
-            pts = cpu_frame(cv2, FEATURE_PARA, f0[t - 1, s], f0[t, s], f1[t, s], pts, crit)
-            if ba is not None and (t + s) % KF_EVERY == 0:
-                cpu_ba_solve(ba, s)
+            # a fronto-parallel cloud at the plane depth gives PnP / BA the right problem size and conditioning
+            p3d = np.stack([(pts[:, 0] - K[2]) / K[0] * Z, (pts[:, 1] - K[3]) / K[1] * Z, np.full(len(pts), Z)], 1).astype(np.float32)
+            i1 = f1[base + t, s] if wl["stereo"] else None
+            pts, last = cpu_frame_chain(cv2, ba_ref, wl, rig, last, f0[base + t, s], i1, pts, p3d, (rv, tv), windows[s], (t + s) % kf_every == 0)
         return 0
 
     t0 = time.perf_counter()
     with ThreadPoolExecutor(workers) as ex:
         list(ex.map(work, range(n_streams)))
     dt = time.perf_counter() - t0
-    return {"value": n_streams * n_frames / dt, "unit": "frames/s", "cores": cores,
-            "kind": "port", "threads": workers * max(1, cores // workers),
-            "sample": f"{n_streams} streams x {n_frames} stereo frames; OpenCV stages = cv2 {cv2.__version__} (the library "
-                      f"the reference links: 2x calcOpticalFlowPyrLK + goodFeaturesToTrack), local BA = oracle/ba_ref.c "
-                      f"(C port of the vendored g2o LM/Schur path, 1 thread per stream like g2o)"
-                      + ("" if ba is not None else " [BA not in sample]")}
+    return {"value": n_streams * n_frames / dt, "unit": "frames/s", "cores": cores, "kind": "port",
+            "threads": workers * max(1, cores // workers),
+            "sample": f"{n_streams} sequences x {n_frames} frames; per frame the OpenCV calls of F2FTracking::image_feed through cv2 "
+                      f"{cv2.__version__} (equalizeHist, 2x calcOpticalFlowPyrLK, undistortPoints, findFundamentalMat, solvePnPRansac, "
+                      f"goodFeaturesToTrack) + pose-only BA and, every {kf_every}th frame, a W={wl['window']} local-BA window "
+                      f"({obs} observations per keyframe) through oracle/ba_ref.c (C port of the vendored g2o LM/Schur path, one thread "
+                      f"per solve like g2o); Python between the calls is array slicing only"}
 
 
-def run_reference(args):
-    rank = int(os.environ.get("RANK", "0"))
+def run_reference(args, wl, pools):
     world = int(os.environ.get("WORLD_SIZE", "1"))
-    if rank != 0:
-        return
     S = args.streams
     n_streams = min(S, os.cpu_count() or 1)
     steps = max(1, min(args.steps, 6))
-    for _ in range(min(args.warmup, 1)):
-        cpu_baseline(min(n_streams, 4), 1, args)
-    cpu = cpu_baseline(n_streams, steps, args)
-    out = {"impl": "reference",
-           "metric": "frames/sec (device-timed), EuRoC-shaped 752x480 stereo, LK frontend + 10-KF local BA",
-           "value": cpu["value"], "unit": "frames/s", "n_gpus": world, "steps": steps, "warmup": min(args.warmup, 1),
+    cpu_baseline(args, wl, pools, min(n_streams, 4), 1)
+    cpu = cpu_baseline(args, wl, pools, n_streams, steps)
+    out = {"impl": "reference", "metric": f"frames/sec (device-timed), {wl['name']}",
+           "value": cpu["value"], "unit": "frames/s", "n_gpus": world, "steps": steps, "warmup": 1,
            "ms_per_step": 1e3 * n_streams / cpu["value"], "higher_is_better": True, "scaling": "weak",
            "vs_baseline": None, "dtype": "u8/i16 fixed-point + f32 (OpenCV), f64 (g2o port)", "data": "synthetic",
-           "config": {"workload": f"{S} concurrent EuRoC-shaped 752x480 stereo streams (bounded sample: {n_streams} streams x "
-                                  f"{steps} frames on the host cores)", "streams_per_gpu": S, "image": [W, H],
-                      "points_per_stream": NPTS},
+           "config": {"workload": f"{S} concurrent sequences, {wl['name']} (bounded sample: {n_streams} sequences x {steps} frames on the host cores)",
+                      "streams_per_gpu": S, "image": [wl["w"], wl["h"]]},
            "cpu_baseline": cpu,
            "e2e": {"value": cpu["value"], "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(out))
@@ -347,22 +510,24 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--streams", type=int, default=32)
+    ap.add_argument("--reps", type=int, default=7, help="repetitions of the K-step timed region (median reported)")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-single", action="store_true", help="skip the single-stream leg")
     ap.add_argument("--workload", default="euroc", choices=sorted(WORKLOADS), help="euroc = the headline (default)")
     args = ap.parse_args()
-    global W, H, STEREO, BA_WINDOW, BA_LANDMARKS, WORKLOAD, P_PYR, LK_BYTES_PER_CALL
     wl = WORKLOADS[args.workload]
-    WORKLOAD, W, H, STEREO, BA_WINDOW, BA_LANDMARKS = args.workload, wl["w"], wl["h"], wl["stereo"], wl["window"], wl["landmarks"]
-    if args.workload != "euroc":
-        P_PYR = sum(((W + (1 << l) - 1) >> l) * ((H + (1 << l) - 1) >> l) for l in range(4))
-        LK_BYTES_PER_CALL = 6 * P_PYR + 29 * NPTS
-    if args.warmup < 3 and args.impl == "ours":
-        args.warmup = 3
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
+    cores = os.cpu_count() or 1
     if args.impl == "reference":
-        run_reference(args)
-    else:
-        run_ours(args)
+        if rank != 0:
+            return
+        n = min(args.streams, cores)
+        run_reference(args, wl, build_pools(args.workload, 0, n, cores))
+        return
+    first = sharding.stream_ids(rank, world, args.streams)[0]
+    pools = build_pools(args.workload, first, args.streams, max(1, cores // world))
+    run_ours(args, wl, pools)
 
 
 if __name__ == "__main__":

@@ -71,6 +71,9 @@ struct flv_f2f_batch {
   flv_f2f_fmat_fn fmat_fn = nullptr; flv_f2f_pnp_fn pnp_fn = nullptr; void* hook_user = nullptr;
   std::vector<char> have_last;                             // stream has an accepted "last" frame on the device
   cudaEvent_t ev_done = nullptr;
+  // optional per-stage device timing (flv_f2f_batch_set_profile): events on the compute stream at the stage boundaries
+  static constexpr int NSTAGE = 9;
+  bool profile = false; cudaEvent_t ev_stage[NSTAGE + 1] = {nullptr}; double stage_ms[NSTAGE] = {0}; long long prof_frames = 0;
   flv_localmap_batch* lmap = nullptr;                      // keyframes go here (flv_f2f_batch_attach_localmap)
   std::vector<int> kf_streams, kf_counts; std::vector<int64_t> kf_frame, kf_ids; std::vector<double> kf_2d, kf_3d, kf_T;
   char err[512] = {0};
@@ -267,6 +270,7 @@ void flv_f2f_batch_destroy(flv_f2f_batch* b) {
   if (b->h_rnd) cudaFreeHost(b->h_rnd);
   if (b->h_tab) cudaFreeHost(b->h_tab);
   if (b->ev_done) cudaEventDestroy(b->ev_done);
+  for (cudaEvent_t e : b->ev_stage) if (e) cudaEventDestroy(e);
   if (b->ctx) flv_destroy(b->ctx);
   delete b;
 }
@@ -369,6 +373,9 @@ int flv_f2f_batch_image_feed(flv_f2f_batch* b, const double* t, const uint8_t* i
     for (int i = 0; i < M; ++i) r[i] = peek.dummy_depth();
   }
   cudaStream_t cs = ctx->stream;
+  int mark_i = 0;
+  auto mark = [&]() { if (b->profile && mark_i <= flv_f2f_batch::NSTAGE) cudaEventRecord(b->ev_stage[mark_i++], cs); };
+  mark();                                                                 // 0: ingest + pyramids
   B_CUDA(b, cudaMemcpyAsync(b->d.b.ctl, b->h_ctl, (size_t)S * sizeof(TrkCtl), cudaMemcpyHostToDevice, cs));
   B_CUDA(b, cudaMemcpyAsync(b->d.b.rnd, b->h_rnd, (size_t)S * M * 4, cudaMemcpyHostToDevice, cs));
   // ---- images: level 0 + pyramids (f2f_tracking.cpp:78-145) -------------------------------------------------------------
@@ -382,26 +389,32 @@ int flv_f2f_batch_image_feed(flv_f2f_batch* b, const double* t, const uint8_t* i
   B_RC(b, flv_trk_stage_prepare(ctx, b->d, S));
   const flv_lk_params lk_f2f{31, 10, 30, 1e-3, 1e-4}, lk_lr{31, 5, 30, 1e-3, 1e-4};
   const TrkBufs& q = b->d.b;
+  mark();                                                                 // 1: frame -> frame LK
   if (any_track) {
     B_RC(b, flv_lk_track(ctx, prev0, cur0, S, q.n_lk, q.lk_prev, q.lk_init, q.lk_next, q.lk_st, q.lk_err, &lk_f2f, FLV_MEM_DEVICE));
+    mark();                                                               // 2: keep rule + F RANSAC
     B_RC(b, flv_trk_stage_keep(ctx, b->d, S));
     if (b->fmat_fn) { if (int rc = run_fmat_hooks(b)) return rc; }
     else {
       const flv_ransac_params rp{5.0, 0.99, 1000};
       B_RC(b, flv_fundamental_ransac(ctx, S, q.n_f, q.fa, q.fb, &rp, q.maskF, q.Fm, q.f_ninl, FLV_MEM_DEVICE));
     }
+    mark();                                                               // 3: PnP RANSAC
     B_RC(b, flv_trk_stage_after_f(ctx, b->d, S));
     if (b->pnp_fn) { if (int rc = run_pnp_hooks(b)) return rc; }
     else {
       const flv_ransac_params rp{3.0, 0.99, 100};
       B_RC(b, flv_pnp_ransac(ctx, S, q.n_pnp, q.pnp3, q.pnp2, q.pnp_K4, q.pnp_Tin, &rp, q.pnp_Tout, q.maskP, q.pnp_ninl, FLV_MEM_DEVICE));
     }
+    mark();                                                               // 4: pose-only BA
     B_RC(b, flv_trk_stage_after_pnp(ctx, b->d, S));
     const flv_ba_params bp{2, 2, 1.0, 3.0, 10, 0};
     B_RC(b, flv_ba_optimize(ctx, S, q.ba_prob, &bp, q.ba_poses, q.ba_lms, q.ba_ep, q.ba_el, q.ba_uv, q.ba_act, q.ba_stats, FLV_MEM_DEVICE));
+    mark();                                                               // 5: reprojection cull
     B_RC(b, flv_trk_stage_after_ba(ctx, b->d, S));
     B_RC(b, flv_reprojection_inliers(ctx, S, q.n_rep, &b->d.cam.c, b->d.C.T, b->d.C.undist, b->d.C.p3w, 1.5, b->d.C.inl, q.rep_mean, FLV_MEM_DEVICE));
     B_RC(b, flv_trk_stage_erase_outliers(ctx, b->d, S));
+    mark();                                                               // 6: FeatureDEM redetect
     // FeatureDEM::redetect: existing positions were written straight into the context's buffers by the kernel above
     if (ctx->prep_valid) { B_CUDA(b, cudaStreamWaitEvent(cs, ctx->ev_gftt, 0)); ctx->prep_valid = 0; }
     else B_RC(b, flv_launch_gftt(ctx, cur0, S, b->fprm.gftt_num, b->fprm.gftt_ql, (double)b->fprm.gftt_dis));
@@ -414,11 +427,14 @@ int flv_f2f_batch_image_feed(flv_f2f_batch* b, const double* t, const uint8_t* i
     B_RC(b, flv_launch_region(ctx, cur0, S, &b->fprm, 0));
     B_RC(b, flv_trk_stage_append(ctx, b->d, S, 2));
   }
+  while (mark_i < 7) mark();
+  mark();                                                                 // 7: left -> right LK
   if (any_track || any_init) {
     if (b->stereo) {
       B_RC(b, flv_lk_track(ctx, cur0, cur1, S, q.n_r, q.r_prev, q.r_init, q.r_next, q.r_st, q.r_err, &lk_lr, FLV_MEM_DEVICE));
       B_RC(b, flv_trk_stage_pt1(ctx, b->d, S));
     }
+    mark();                                                               // 8: depth innovation + finish
     B_RC(b, flv_depth_innovation(ctx, S, q.n_r, &b->d.cam.c, &b->dprm, b->d.C.T, b->d.C.plane, b->d.C.undist, b->d.C.p3w, b->d.C.p3c,
                                  b->d.C.has, b->d.C.f2d, b->d.C.fpose, q.pt1, q.r_st, q.dat, q.rnd, q.n_rand_used, FLV_MEM_DEVICE));
   }
@@ -426,8 +442,16 @@ int flv_f2f_batch_image_feed(flv_f2f_batch* b, const double* t, const uint8_t* i
   // ---- the frame's only synchronisation: summaries + the accepted frame's landmark lists ----------------------------------
   B_CUDA(b, cudaMemcpyAsync(b->h_out, q.out, (size_t)S * sizeof(TrkOut), cudaMemcpyDeviceToHost, cs));
   B_CUDA(b, cudaMemcpyAsync(b->h_tab, b->d_tab, b->tab_bytes, cudaMemcpyDeviceToHost, cs));
+  while (mark_i <= flv_f2f_batch::NSTAGE) mark();
   B_CUDA(b, cudaEventRecord(b->ev_done, cs));
   B_CUDA(b, cudaEventSynchronize(b->ev_done));
+  if (b->profile) {
+    for (int i = 0; i < flv_f2f_batch::NSTAGE; ++i) {
+      float ms = 0;
+      if (cudaEventElapsedTime(&ms, b->ev_stage[i], b->ev_stage[i + 1]) == cudaSuccess) b->stage_ms[i] += ms;
+    }
+    b->prof_frames++;
+  }
   // ---- per-stream state machine after the frame (f2f_tracking.cpp:229-247, :258-355, :376-394) --------------------------
   bool any_restore = false;
   b->kf_streams.clear(); b->kf_counts.clear(); b->kf_frame.clear(); b->kf_ids.clear(); b->kf_2d.clear(); b->kf_3d.clear(); b->kf_T.clear();
@@ -568,6 +592,29 @@ int flv_f2f_batch_tracking_counts(flv_f2f_batch* b, int stream, int* of, int* fi
   const StreamState& z = b->st[stream];
   if (of) *of = z.of_cnt; if (fi) *fi = z.f_cnt; if (pnp) *pnp = z.pnp_cnt;
   return FLV_OK;
+}
+int flv_f2f_batch_imu_feed_many(flv_f2f_batch* b, int n, const int* streams, const double* t, const double* acc, const double* gyro) {
+  if (!b || n < 0 || (n > 0 && (!streams || !t || !acc || !gyro))) return FLV_ERR_INVALID;
+  for (int i = 0; i < n; ++i) {
+    const int rc = flv_f2f_batch_imu_feed(b, streams[i], t[i], acc + 3 * (size_t)i, gyro + 3 * (size_t)i);
+    if (rc) return rc;
+  }
+  return FLV_OK;
+}
+int flv_f2f_batch_set_profile(flv_f2f_batch* b, int enable) {
+  if (!b) return FLV_ERR_INVALID;
+  if (enable && !b->ev_stage[0])
+    for (int i = 0; i <= flv_f2f_batch::NSTAGE; ++i) B_CUDA(b, cudaEventCreate(&b->ev_stage[i]));
+  b->profile = enable != 0;
+  for (double& v : b->stage_ms) v = 0;
+  b->prof_frames = 0;
+  return FLV_OK;
+}
+int flv_f2f_batch_get_profile(flv_f2f_batch* b, double* stage_ms9, long long* frames) {
+  if (!b || !stage_ms9) return FLV_ERR_INVALID;
+  for (int i = 0; i < flv_f2f_batch::NSTAGE; ++i) stage_ms9[i] = b->stage_ms[i];
+  if (frames) *frames = b->prof_frames;
+  return flv_f2f_batch::NSTAGE;
 }
 long long flv_f2f_batch_launch_count(flv_f2f_batch* b) { return b && b->ctx ? flv_launch_count(b->ctx) : 0; }
 int flv_f2f_batch_attach_localmap(flv_f2f_batch* b, flv_localmap_batch* lm) {

@@ -147,6 +147,13 @@ int flv_f2f_batch_get_imu_states(flv_f2f_batch* b, int stream, double* out11, in
 int flv_f2f_batch_get_imu_bias(flv_f2f_batch* b, int stream, double* acc_bias, double* gyro_bias);
 int flv_f2f_batch_tracking_counts(flv_f2f_batch* b, int stream, int* of_inliers, int* f_inliers, int* pnp_inliers);
 long long flv_f2f_batch_launch_count(flv_f2f_batch* b);
+/* n IMU samples in one call (sample i belongs to streams[i]; acc / gyro are [n][3]) */
+int flv_f2f_batch_imu_feed_many(flv_f2f_batch* b, int n, const int* streams, const double* t, const double* acc, const double* gyro);
+/* Per-stage device time (CUDA events on the compute stream at the stage boundaries, accumulated over frames): stage_ms9 =
+ * {ingest + pyramids, frame->frame LK, keep rule + F RANSAC, PnP RANSAC, pose-only BA, reprojection cull, FeatureDEM redetect,
+ *  left->right LK, depth innovation + finish}.  set_profile resets the accumulators. */
+int flv_f2f_batch_set_profile(flv_f2f_batch* b, int enable);
+int flv_f2f_batch_get_profile(flv_f2f_batch* b, double* stage_ms9, long long* frames);
 /* Hand every new keyframe (KeyFrame message content: ids / undistorted pixels / world points of the inlier landmarks with
  * depth + T_c_w, keyframe_msg.cpp:30-110) to `lm` from inside image_feed; NULL detaches.  The local map never blocks tracking. */
 int flv_f2f_batch_attach_localmap(flv_f2f_batch* b, flv_localmap_batch* lm);

@@ -247,3 +247,67 @@ def make_c3(n_frames=34, seed=0):
     seq = Sequence("c3", "stereo", n_frames, c["img_hz"], traj, T_i_c0, r0, r0, T_c0_c1, imu_hz=0, seed=seed)
     seq.cfg = c
     return seq
+
+
+# ---- periodic workloads for bench.py --------------------------------------------------------------------------------------
+def make_bench(workload, stream_id, period_frames=40, render=True):
+    """An endless sequence of the named BASELINE shape for throughput runs: after the start-up ramp the rig trajectory is
+    periodic with period `period_frames` images, so a pool of one period of rendered frames (plus the start-up frames) serves
+    any number of steps.  Motion is sized so that a keyframe falls on every 3rd-5th frame (f2f_tracking.cpp:339-355).
+    The sequence carries n_startup / period: frames [0, n_startup) are played once, then frames [n_startup, n_startup + period)
+    repeat.  render=False builds only the trajectory and rig (ground-truth poses), not the textures."""
+    seed = 7000 + stream_id
+    rng = np.random.default_rng(seed)
+    jitter = 1.0 + 0.15 * (rng.uniform(size=6) - 0.5)
+    if workload == "euroc":
+        c = EUROC; hz = c["img_hz"]
+    elif workload == "d435":
+        c = D435; hz = c["img_hz"]
+    else:
+        c = KITTI; hz = c["img_hz"]
+    Tp = period_frames / hz
+    w0 = 2 * math.pi / Tp
+    t_rest = 0.4
+    n_startup = int(math.ceil((t_rest + 1.0) * hz)) + 1            # rest + ramp: afterwards s = t - t_rest - 0.5 is linear in t
+    if workload == "euroc":
+        X0 = 3.0; ppm = c["K0"][0] / X0
+        canvas = synth.texture(seed, int(5.0 * ppm), int(7.0 * ppm), blur=2) if render else np.zeros((8, 8), np.uint8)
+        traj = Trajectory(pos_amp=(0.02 * jitter[0], 0.06 * jitter[1], 0.04 * jitter[2]), pos_w=(w0, w0, 2 * w0),
+                          rpy_amp=(0.03 * jitter[3], 0.02 * jitter[4], 0.04 * jitter[5]), rpy_w=(w0, 2 * w0, w0), t_rest=t_rest)
+        T_i_c0, T_c0_c1 = euroc_rig()
+        r0 = PlaneRenderer(canvas, X0, ppm, c["w"], c["h"], c["K0"], c["D0"]) if render else None
+        r1 = PlaneRenderer(canvas, X0, ppm, c["w"], c["h"], c["K1"], c["D1"]) if render else None
+        seq = Sequence("c1", "stereo_unrect", n_startup + period_frames, hz, traj, T_i_c0, r0, r1, T_c0_c1, seed=seed)
+    elif workload == "d435":
+        X0 = 3.0; ppm = c["K0"][0] / X0
+        canvas = synth.texture(seed, int(4.6 * ppm), int(6.2 * ppm), blur=2) if render else np.zeros((8, 8), np.uint8)
+        traj = Trajectory(pos_amp=(0.02 * jitter[0], 0.05 * jitter[1], 0.035 * jitter[2]), pos_w=(w0, w0, 2 * w0),
+                          rpy_amp=(0.03 * jitter[3], 0.02 * jitter[4], 0.04 * jitter[5]), rpy_w=(w0, 2 * w0, w0), t_rest=t_rest)
+        c = dict(c, skip=0)
+        r0 = PlaneRenderer(canvas, X0, ppm, c["w"], c["h"], c["K0"]) if render else None
+        seq = Sequence("c0", "depth", n_startup + period_frames, hz, traj, _mat44_to_se3(c["T_imu_cam0"]), r0, depth_factor=c["depth_factor"], seed=seed)
+    else:
+        X0 = 12.0; ppm = c["K0"][0] / X0
+        canvas = synth.texture_multiscale(seed, int(9.0 * ppm), int(26.0 * ppm)) if render else np.zeros((8, 8), np.uint8)
+        traj = Trajectory(pos_amp=(0.3 * jitter[0], 1.2 * jitter[1], 0.2 * jitter[2]), pos_w=(w0, w0, 2 * w0),
+                          rpy_amp=(0.0, 0.004, 0.01), rpy_w=(w0, w0, w0), t_rest=0.0)
+        n_startup = int(math.ceil(1.0 * hz)) + 1
+        b = c["bf"] / c["K0"][0]
+        r0 = PlaneRenderer(canvas, X0, ppm, c["w"], c["h"], c["K0"]) if render else None
+        seq = Sequence("c3", "stereo", n_startup + period_frames, hz, traj, _mat44_to_se3(D435["T_imu_cam0"]), r0, r0,
+                       SE3([1.0, 0, 0, 0], [b, 0, 0]), imu_hz=0, seed=seed)
+    seq.cfg = c
+    seq.n_startup, seq.period = n_startup, period_frames
+    return seq
+
+
+def render_pool(args):
+    """(workload, stream_id, period) -> (img0 [n,h,w] u8, img1 [n,h,w] u8|u16, imu list per frame); picklable entry point for a
+    process pool."""
+    workload, stream_id, period = args
+    seq = make_bench(workload, stream_id, period)
+    f0, f1, imu = [], [], []
+    for t, a, b, samples in seq.frames():
+        f0.append(a); f1.append(b)
+        imu.append(np.array([[ti, *acc, *gyro] for ti, acc, gyro in samples], np.float64).reshape(-1, 7))
+    return np.stack(f0), np.stack(f1), imu

@@ -27,8 +27,21 @@ def test_workload_table_and_lk_bytes():
     sys.path.insert(0, ROOT)
     import bench
     assert set(bench.WORKLOADS) == {"euroc", "kitti", "d435"}
-    # pyramid pixels of 752x480 with 4 levels: 360960 + 90240 + 22560 + 5640
-    assert bench.P_PYR == 360960 + 90240 + 22560 + 5640
-    assert bench.LK_BYTES_PER_CALL == 6 * bench.P_PYR + 29 * bench.NPTS
+    # pyramid pixels P(w,h) of SURVEY.md 8(d)
+    assert bench.pyramid_pixels(752, 480) == 360960 + 90240 + 22560 + 5640 == 479400
+    assert bench.pyramid_pixels(1241, 376) == 619930 and bench.pyramid_pixels(640, 480) == 408000
+    # algorithmic bytes of one LK call = 2 P + 29 N: 972 720 B at 752x480, N = 480
+    assert bench.lk_algorithmic_bytes(752, 480, 480) == 972720
+    assert bench.lk_algorithmic_bytes(1241, 376, 480) == 1253780 and bench.lk_algorithmic_bytes(640, 480, 480) == 829920
     for wl in bench.WORKLOADS.values():
-        assert wl["w"] >= 64 and wl["h"] >= 64 and wl["window"] <= 24
+        assert wl["w"] >= 64 and wl["h"] >= 64 and wl["window"] <= 25
+
+
+def test_periodic_bench_sequences_repeat_exactly():
+    from synthdata import sequences
+    for wl in ("euroc", "d435", "kitti"):
+        seq = sequences.make_bench(wl, 3, 40, render=False)
+        t0 = seq.n_startup / seq.img_hz; t1 = (seq.n_startup + seq.period) / seq.img_hz
+        a, b = seq.T_w_c0(t0), seq.T_w_c0(t1)
+        import numpy as np
+        assert np.abs(a.t - b.t).max() < 1e-12 and np.abs(a.q - b.q).max() < 1e-12
