@@ -275,13 +275,14 @@ def run_ours(args, wl, pools):
     if sampler:
         sampler.start()
     trk.set_profile(True)
-    dev_runs, e2e_runs, launches, ba_tot = [], [], 0, dict(keyframes=0, solves=0, launches=0, solve_ms=0.0)
+    dev_runs, e2e_runs, launches, ba_tot = [], [], 0, dict(keyframes=0, solves=0, launches=0, solve_ms=0.0, host_ms=0.0)
     for r in range(args.reps):
         ms, nl, ba = region(trk, lmap, args.steps, "device", record=(r == 0))
         dev_runs.append(ms); launches = nl
         for k in ba_tot:
             ba_tot[k] += ba[k]
     stage_ms, prof_frames = trk.profile()
+    host_ms = trk.host_profile()
     trk.set_profile(False)
     n_lm_mean = float(np.mean([trk.n_landmarks(s) for s in range(S)]))
     for r in range(args.reps):
@@ -360,6 +361,9 @@ def run_ours(args, wl, pools):
                     "ms_per_step": med_e / args.steps, "value_min_max": [frames / (max(e2e_runs) * 1e-3), frames / (min(e2e_runs) * 1e-3)]},
             "gpu_launches": int(launches),
             "stages_ms_per_step": {n: round(float(v), 4) for n, v in zip(fb.STAGES, per_frame)},
+            "host_ms_per_step": {"decisions": float(host_ms[0] / max(prof_frames, 1)), "enqueue": float(host_ms[1] / max(prof_frames, 1)),
+                                 "wait_for_device": float(host_ms[2] / max(prof_frames, 1)), "post_frame": float(host_ms[3] / max(prof_frames, 1)),
+                                 "local_map_worker": ba_tot["host_ms"] / (args.reps * args.steps)},
             "ba": {"ms_per_kf": (ba_tot["solve_ms"] / ba_tot["solves"]) if ba_tot["solves"] else None,
                    "note": "wall time of one batched flv_ba_optimize call (H2D of the window arrays + ba_kernel + D2H) divided by the "
                            "windows it solved; the worker overlaps the tracker's kernels",

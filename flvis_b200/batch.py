@@ -44,6 +44,7 @@ def _bind(lib):
     lib.flv_f2f_batch_attach_localmap.argtypes = [vp, vp]
     lib.flv_f2f_batch_set_profile.argtypes = [vp, C.c_int]
     lib.flv_f2f_batch_get_profile.argtypes = [vp, vp, vp]
+    lib.flv_f2f_batch_get_host_profile.argtypes = [vp, vp]
     lib.flv_f2f_batch_tracking_counts.argtypes = [vp, C.c_int] + [C.POINTER(C.c_int)] * 3
     lib.flv_localmap_batch_create.restype = vp
     lib.flv_localmap_batch_create.argtypes = [C.c_int, C.c_int, C.c_int] + [C.c_double] * 4
@@ -69,9 +70,9 @@ class LocalMapBatch:
             raise capi.FlvError(self.lib.flv_localmap_batch_last_error(self.h).decode())
 
     def stats(self):
-        nk = C.c_longlong(); ns = C.c_longlong(); nl = C.c_longlong(); ms = C.c_double()
-        self.lib.flv_localmap_batch_stats(self.h, C.byref(nk), C.byref(ns), C.byref(nl), C.byref(ms))
-        return dict(keyframes=nk.value, solves=ns.value, launches=nl.value, solve_ms=ms.value)
+        nk = C.c_longlong(); ns = C.c_longlong(); nl = C.c_longlong(); ms = (C.c_double * 2)()
+        self.lib.flv_localmap_batch_stats(self.h, C.byref(nk), C.byref(ns), C.byref(nl), ms)
+        return dict(keyframes=nk.value, solves=ns.value, launches=nl.value, solve_ms=ms[0], host_ms=ms[1])
 
     def close(self):
         if self.h:
@@ -140,6 +141,11 @@ class BatchTracker:
         ms = np.zeros(9); n = C.c_longlong()
         self.lib.flv_f2f_batch_get_profile(self.h, _p(ms), C.byref(n))
         return ms, n.value
+
+    def host_profile(self):
+        ms = np.zeros(4)
+        self.lib.flv_f2f_batch_get_host_profile(self.h, _p(ms))
+        return ms
 
     def close(self):
         if self.h:

@@ -9,6 +9,7 @@
 // everything the host needs from the device is needed only after the frame (viCorrectionFromVision :281, the keyframe
 // rule :339-355, the failure counters :229-247).  Tests may install the OpenCV RANSAC hooks; those force two more round
 // trips per frame (the correspondences go to the host and the masks come back).
+#include <chrono>
 #include <memory>
 #include <new>
 #include <vector>
@@ -73,6 +74,7 @@ struct flv_f2f_batch {
   cudaEvent_t ev_done = nullptr;
   // optional per-stage device timing (flv_f2f_batch_set_profile): events on the compute stream at the stage boundaries
   static constexpr int NSTAGE = 9;
+  double host_ms[4] = {0, 0, 0, 0};                        // host wall time: decisions, enqueue, wait for the device, post-frame
   bool profile = false; cudaEvent_t ev_stage[NSTAGE + 1] = {nullptr}; double stage_ms[NSTAGE] = {0}; long long prof_frames = 0;
   flv_localmap_batch* lmap = nullptr;                      // keyframes go here (flv_f2f_batch_attach_localmap)
   std::vector<int> kf_streams, kf_counts; std::vector<int64_t> kf_frame, kf_ids; std::vector<double> kf_2d, kf_3d, kf_T;
@@ -310,6 +312,7 @@ int flv_f2f_batch_image_feed(flv_f2f_batch* b, const double* t, const uint8_t* i
   const size_t w = b->cfg.img_w, h = b->cfg.img_h;
   const int prev0 = b->slots[0], cur0 = b->slots[1], cur1 = b->slots[2];
   // ---- per-stream decisions that need no image data (f2f_tracking.cpp:59-76, :146-186 entry, :225, :357-375) -----------
+  const auto tp0 = std::chrono::steady_clock::now();
   bool any_init = false, any_track = false;
   for (int s = 0; s < S; ++s) {
     StreamState& z = b->st[s];
@@ -373,8 +376,13 @@ int flv_f2f_batch_image_feed(flv_f2f_batch* b, const double* t, const uint8_t* i
     for (int i = 0; i < M; ++i) r[i] = peek.dummy_depth();
   }
   cudaStream_t cs = ctx->stream;
+  const auto tp1 = std::chrono::steady_clock::now();
   int mark_i = 0;
-  auto mark = [&]() { if (b->profile && mark_i <= flv_f2f_batch::NSTAGE) cudaEventRecord(b->ev_stage[mark_i++], cs); };
+  auto mark = [&]() {                                     // stage boundary: an event when profiling, a counter always
+    if (mark_i > flv_f2f_batch::NSTAGE) return;
+    if (b->profile) cudaEventRecord(b->ev_stage[mark_i], cs);
+    ++mark_i;
+  };
   mark();                                                                 // 0: ingest + pyramids
   B_CUDA(b, cudaMemcpyAsync(b->d.b.ctl, b->h_ctl, (size_t)S * sizeof(TrkCtl), cudaMemcpyHostToDevice, cs));
   B_CUDA(b, cudaMemcpyAsync(b->d.b.rnd, b->h_rnd, (size_t)S * M * 4, cudaMemcpyHostToDevice, cs));
@@ -444,7 +452,9 @@ int flv_f2f_batch_image_feed(flv_f2f_batch* b, const double* t, const uint8_t* i
   B_CUDA(b, cudaMemcpyAsync(b->h_tab, b->d_tab, b->tab_bytes, cudaMemcpyDeviceToHost, cs));
   while (mark_i <= flv_f2f_batch::NSTAGE) mark();
   B_CUDA(b, cudaEventRecord(b->ev_done, cs));
+  const auto tp2 = std::chrono::steady_clock::now();
   B_CUDA(b, cudaEventSynchronize(b->ev_done));
+  const auto tp3 = std::chrono::steady_clock::now();
   if (b->profile) {
     for (int i = 0; i < flv_f2f_batch::NSTAGE; ++i) {
       float ms = 0;
@@ -534,6 +544,11 @@ int flv_f2f_batch_image_feed(flv_f2f_batch* b, const double* t, const uint8_t* i
     if (rc) { snprintf(b->err, sizeof(b->err), "flv_localmap_batch_submit: %s", flv_localmap_batch_last_error(b->lmap)); return rc; }
   }
   if (any_restore) ctx->deriv_streams[cur0] = 0;          // derivative pyramid of that slot: rebuild on next use
+  if (b->profile) {
+    const auto tp4 = std::chrono::steady_clock::now();
+    auto ms = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point c) { return std::chrono::duration<double, std::milli>(c - a).count(); };
+    b->host_ms[0] += ms(tp0, tp1); b->host_ms[1] += ms(tp1, tp2); b->host_ms[2] += ms(tp2, tp3); b->host_ms[3] += ms(tp3, tp4);
+  }
   b->slots[0] = cur0; b->slots[1] = prev0; b->slots[2] = cur1;
   return FLV_OK;
 }
@@ -607,6 +622,7 @@ int flv_f2f_batch_set_profile(flv_f2f_batch* b, int enable) {
     for (int i = 0; i <= flv_f2f_batch::NSTAGE; ++i) B_CUDA(b, cudaEventCreate(&b->ev_stage[i]));
   b->profile = enable != 0;
   for (double& v : b->stage_ms) v = 0;
+  for (double& v : b->host_ms) v = 0;
   b->prof_frames = 0;
   return FLV_OK;
 }
@@ -615,6 +631,11 @@ int flv_f2f_batch_get_profile(flv_f2f_batch* b, double* stage_ms9, long long* fr
   for (int i = 0; i < flv_f2f_batch::NSTAGE; ++i) stage_ms9[i] = b->stage_ms[i];
   if (frames) *frames = b->prof_frames;
   return flv_f2f_batch::NSTAGE;
+}
+int flv_f2f_batch_get_host_profile(flv_f2f_batch* b, double* host_ms4) {
+  if (!b || !host_ms4) return FLV_ERR_INVALID;
+  for (int i = 0; i < 4; ++i) host_ms4[i] = b->host_ms[i];
+  return 4;
 }
 long long flv_f2f_batch_launch_count(flv_f2f_batch* b) { return b && b->ctx ? flv_launch_count(b->ctx) : 0; }
 int flv_f2f_batch_attach_localmap(flv_f2f_batch* b, flv_localmap_batch* lm) {

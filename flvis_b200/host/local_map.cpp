@@ -1,5 +1,6 @@
 #include "local_map.h"
 #include <algorithm>
+#include <set>
 
 namespace flv {
 
@@ -62,8 +63,13 @@ bool LocalMap::edit_graph(const KeyFrameStruct& kf) {
       break;
     case SLIDING_WINDOW: {                                             // :218-284
       remove_pose_vertex(bag.getOldestPoseInOptimizerIdx());
-      for (int64_t id : kfs.at(0).lm_id)                               // off-by-one keyframe on purpose (:226-232)
-        if (bag.removeLMObservation(id)) remove_lm_vertex(id);
+      {                                                                // off-by-one keyframe on purpose (:226-232)
+        std::set<int64_t> gone;                                        // removeVertex per landmark == one pass over the edges
+        for (int64_t id : kfs.at(0).lm_id)
+          if (bag.removeLMObservation(id)) { gone.insert(id); lm_est.erase(id); }
+        if (!gone.empty())
+          edges.erase(std::remove_if(edges.begin(), edges.end(), [&gone](const Edge& e) { return gone.count(e.lm_id) != 0; }), edges.end());
+      }
       bag.addPose(kfs.back().frame_id, kfs.back().T_c_w);
       const int newest = bag.getNewestPoseInOptimizerIdx();
       pose_est[newest] = g2o_pose_from_quat(kfs.back().T_c_w);

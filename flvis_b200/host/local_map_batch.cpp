@@ -36,7 +36,7 @@ struct flv_localmap_batch {
   std::deque<std::vector<KfMsg>> queue;
   bool stop = false, busy = false, failed = false, started = false;
   long long n_keyframes = 0, n_solves = 0, n_launches = 0;
-  double solve_ms = 0;
+  double solve_ms = 0, host_ms = 0;            // solver calls / graph editing + packing on the worker thread
   int rP = 0, rL = 0, rE = 0;
   char err[256] = {0};
 
@@ -48,6 +48,8 @@ bool flv_localmap_batch::process(std::vector<KfMsg>& batch) {
   // a sequence may contribute several keyframes to one submission only if the caller batches frames; solve in rounds so
   // that every LocalMap sees begin -> solve -> end in order
   size_t done = 0;
+  const auto th0 = std::chrono::steady_clock::now();
+  const double solve_before = solve_ms;
   std::vector<char> used(batch.size(), 0);
   while (done < batch.size()) {
     std::vector<int> round;                      // indices of this round: at most one keyframe per sequence
@@ -107,6 +109,7 @@ bool flv_localmap_batch::process(std::vector<KfMsg>& batch) {
       n_results[s]++;
     }
   }
+  host_ms += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - th0).count() - (solve_ms - solve_before);
   return true;
 }
 
@@ -203,6 +206,7 @@ int flv_localmap_batch_wait(flv_localmap_batch* b) {
 }
 
 int flv_localmap_batch_stats(flv_localmap_batch* b, long long* n_keyframes, long long* n_solves, long long* n_launches, double* solve_ms) {
+  if (b && solve_ms) solve_ms[1] = b->host_ms;        // solve_ms is double[2]: {solver calls, graph editing + packing}
   if (!b) return FLV_ERR_INVALID;
   std::lock_guard<std::mutex> lk(b->mu);
   if (n_keyframes) *n_keyframes = b->n_keyframes;

@@ -3,6 +3,7 @@
 // src/backend/poselmbag.cpp:5-208 (slot index == optimizer vertex id; a new pose overwrites the oldest slot;
 // addLMObservation keeps a running mean, the sliding variant only counts).
 #pragma once
+#include <unordered_map>
 #include <vector>
 #include "se3.h"
 
@@ -32,6 +33,14 @@ class PoseLMBag {
   int getNewestPoseInOptimizerIdx() { return newest; }
   int getOldestPoseInOptimizerIdx() { return oldest; }
   int64_t getPoseIdByReleventFrameId(int64_t frame_id);
+
+ private:
+  // The reference searches lm_sub_bag linearly (poselmbag.cpp:34-46) and erases from the middle of the vector: O(N L) per
+  // keyframe.  Same contents and order here, but the lookup goes through an id -> position index and an erased entry is a
+  // tombstone until the next compaction (relative order of the live entries, which getMultiViewLMs exposes, is unchanged).
+  std::unordered_map<int64_t, int> index_;
+  int n_dead_ = 0;
+  void compact();
 };
 
 }  // namespace flv

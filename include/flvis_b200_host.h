@@ -111,7 +111,8 @@ const char* flv_localmap_batch_last_error(flv_localmap_batch* b);
 int flv_localmap_batch_submit(flv_localmap_batch* b, int n_kf, const int* streams, const int64_t* frame_ids, const int* lm_counts,
                               const int64_t* lm_id, const double* lm_2d, const double* lm_3d, const double* T_c_w);
 int flv_localmap_batch_wait(flv_localmap_batch* b);
-int flv_localmap_batch_stats(flv_localmap_batch* b, long long* n_keyframes, long long* n_solves, long long* n_launches, double* solve_ms);
+/* solve_ms2 = {wall ms inside the solver calls, wall ms of graph editing + array packing on the worker thread} */
+int flv_localmap_batch_stats(flv_localmap_batch* b, long long* n_keyframes, long long* n_solves, long long* n_launches, double* solve_ms2);
 int flv_localmap_batch_result(flv_localmap_batch* b, int stream, int64_t* out_frame_id, double* out_T_c_w, int* out_lm_count,
                               int64_t* out_lm_id, double* out_lm_3d, int lm_cap, int* out_outlier_count, int64_t* out_outlier_id,
                               int outlier_cap);
@@ -154,6 +155,9 @@ int flv_f2f_batch_imu_feed_many(flv_f2f_batch* b, int n, const int* streams, con
  *  left->right LK, depth innovation + finish}.  set_profile resets the accumulators. */
 int flv_f2f_batch_set_profile(flv_f2f_batch* b, int enable);
 int flv_f2f_batch_get_profile(flv_f2f_batch* b, double* stage_ms9, long long* frames);
+/* host wall time of image_feed over the same frames: {per-stream decisions, enqueue of the frame's work, waiting for the
+ * device, per-stream post-frame work (IMU feedback, keyframe rule, keyframe hand-off)} */
+int flv_f2f_batch_get_host_profile(flv_f2f_batch* b, double* host_ms4);
 /* Hand every new keyframe (KeyFrame message content: ids / undistorted pixels / world points of the inlier landmarks with
  * depth + T_c_w, keyframe_msg.cpp:30-110) to `lm` from inside image_feed; NULL detaches.  The local map never blocks tracking. */
 int flv_f2f_batch_attach_localmap(flv_f2f_batch* b, flv_localmap_batch* lm);

@@ -112,7 +112,7 @@ def test_localmap_batch_worker_matches_oracle_per_stream(lib):
             if nlm[0]:
                 assert np.abs(o3[:nlm[0]] - o["lm_3d"]).max() <= 1e-5
             n_checked += 1
-    nk = C.c_longlong(); ns = C.c_longlong(); nl = C.c_longlong(); ms = C.c_double()
-    lib.flv_localmap_batch_stats(b, C.byref(nk), C.byref(ns), C.byref(nl), C.byref(ms))
+    nk = C.c_longlong(); ns = C.c_longlong(); nl = C.c_longlong(); ms = (C.c_double * 2)()
+    lib.flv_localmap_batch_stats(b, C.byref(nk), C.byref(ns), C.byref(nl), ms)
     assert ns.value == n_checked >= 15 and nl.value < ns.value          # several windows per launch
     lib.flv_localmap_batch_destroy(b)
