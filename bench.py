@@ -204,7 +204,7 @@ def run_ours(args, wl, pools):
     stream = torch.cuda.Stream(dev)
 
     def make_tracker(n):
-        t = fb.BatchTracker(cfg, n, device=local_rank, lenses=lenses, equalize=equalize)
+        t = fb.BatchTracker(cfg, n, device=local_rank, lenses=lenses, equalize=equalize, groups=args.groups if n == S else 1)
         t.set_stream(stream.cuda_stream)
         lm = fb.LocalMapBatch(n, wl["window"], K, device=local_rank)
         t.attach_localmap(lm)
@@ -323,7 +323,7 @@ def run_ours(args, wl, pools):
         per_frame = stage_ms / max(prof_frames, 1)
         lk_us = 1e3 * float(per_frame[1])                                     # frame->frame call (maxLevel 10)
         lk_lr_us = 1e3 * float(per_frame[7]) if wl["stereo"] else None        # + the tiny right-point undistortion kernel
-        alg = lk_algorithmic_bytes(W, H, n_lm_mean) * S
+        alg = lk_algorithmic_bytes(W, H, n_lm_mean) * S / max(trk.groups, 1)     # one launch serves one group's sequences
         achieved = alg / (lk_us * 1e-6) / 1e9 if lk_us > 0 else 0.0
         # ATE of the GPU trajectories against the synthetic ground truth (camera centres, constant offset removed)
         ates = []
@@ -348,7 +348,7 @@ def run_ours(args, wl, pools):
             "config": {"workload": f"{S} concurrent sequences per GPU, {wl['name']}; full F2FTracking::image_feed per frame (LK x2, F + PnP RANSAC, "
                                    f"pose-only BA, FeatureDEM redetect, depth innovation) + local BA W={wl['window']} on every keyframe"
                                    + (" (BASELINE configs[2])" if args.workload == "euroc" else ""),
-                       "streams_per_gpu": S, "image": [W, H], "landmarks_per_stream_mean": n_lm_mean,
+                       "streams_per_gpu": S, "stream_groups": trk.groups, "image": [W, H], "landmarks_per_stream_mean": n_lm_mean,
                        "streams_tracking_before_after": [n_tracking, still_tracking],
                        "repetitions": args.reps, "value_min_max": [frames / (max(dev_runs) * 1e-3), frames / (min(dev_runs) * 1e-3)],
                        "l2_note": "no explicit L2 flush: every step ingests fresh images for all sequences from a rotating frame pool of "
@@ -379,9 +379,11 @@ def run_ours(args, wl, pools):
                          "peak_source": peak_src, "us_per_launch": lk_us, "us_per_launch_left_right": lk_lr_us,
                          "algorithmic_bytes_per_launch": alg,
                          "algorithmic_bytes_def": "SURVEY.md 8(d): (2 P(w,h) + 29 N) x S, P = pyramid pixels, N = mean tracked points per sequence",
-                         "traffic_expected": (6 * pyramid_pixels(W, H) + 29 * n_lm_mean) * S,
+                         "traffic_expected": (6 * pyramid_pixels(W, H) + 29 * n_lm_mean) * S / max(trk.groups, 1),
                          "traffic_expected_def": "what the kernel must read with its 4 B/px Scharr derivative pyramid of the first image",
-                         "issue_slot_roofline": _issue_roofline(lk_us, S, n_lm_mean, sm_max),
+                         "issue_slot_roofline": _issue_roofline(lk_us, S / max(trk.groups, 1), n_lm_mean, sm_max),
+                         "launch_note": f"one launch tracks {S // max(trk.groups, 1)} sequences; with {trk.groups} stream groups the other group's "
+                                        "kernels share the SMs while it runs, so us_per_launch is the in-situ duration, not the kernel alone",
                          "note": "LK is bound by instruction issue, not by HBM (ncu: DRAM < 3 % busy); the issue-slot figure is the "
                                  "roofline that explains it (DESIGN.md section 5)"},
             "clocks": sampler.summary() if sampler else None,
@@ -514,6 +516,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--streams", type=int, default=32)
+    ap.add_argument("--groups", type=int, default=2, help="stream groups per GPU (own CUDA stream + host thread each)")
     ap.add_argument("--reps", type=int, default=7, help="repetitions of the K-step timed region (median reported)")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")

@@ -28,6 +28,9 @@ def _bind(lib):
     vp = C.c_void_p
     lib.flv_f2f_batch_create.restype = vp
     lib.flv_f2f_batch_create.argtypes = [C.POINTER(F2FConfig), C.c_int, C.c_int]
+    lib.flv_f2f_batch_create_grouped.restype = vp
+    lib.flv_f2f_batch_create_grouped.argtypes = [C.POINTER(F2FConfig), C.c_int, C.c_int, C.c_int]
+    lib.flv_f2f_batch_groups.argtypes = [vp]
     lib.flv_f2f_batch_destroy.argtypes = [vp]
     lib.flv_f2f_batch_last_error.restype = C.c_char_p
     lib.flv_f2f_batch_last_error.argtypes = [vp]
@@ -83,10 +86,11 @@ class LocalMapBatch:
 class BatchTracker:
     """S sequences of one sensor model.  cfg: F2FConfig; lenses: [(K4, D14, R9), (K4, D14, R9)] for STEREO_UNRECT."""
 
-    def __init__(self, cfg, n_streams, device=0, lenses=None, equalize=False, lib=None):
+    def __init__(self, cfg, n_streams, device=0, lenses=None, equalize=False, lib=None, groups=1):
         self.lib = _bind(lib or capi.load_library())
         self.S = n_streams
-        self.h = self.lib.flv_f2f_batch_create(C.byref(cfg), n_streams, device)
+        self.h = self.lib.flv_f2f_batch_create_grouped(C.byref(cfg), n_streams, device, groups)
+        self.groups = self.lib.flv_f2f_batch_groups(self.h) if self.h else 0
         err = self.lib.flv_f2f_batch_last_error(self.h) if self.h else b"allocation failed"
         if not self.h or err:
             raise capi.FlvError(f"flv_f2f_batch_create: {err.decode()}")
@@ -104,6 +108,9 @@ class BatchTracker:
             raise capi.FlvError(f"flv_f2f_batch ({rc}): {self.lib.flv_f2f_batch_last_error(self.h).decode()}")
 
     def set_stream(self, cuda_stream_ptr):
+        """Single-group batches only: run on the caller's CUDA stream (grouped batches own one stream per group)."""
+        if self.groups > 1:
+            return
         self.lib.flv_set_stream(self.lib.flv_f2f_batch_context(self.h), C.c_void_p(cuda_stream_ptr))
 
     def attach_localmap(self, lm):

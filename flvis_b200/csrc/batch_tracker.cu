@@ -10,7 +10,10 @@
 // rule :339-355, the failure counters :229-247).  Tests may install the OpenCV RANSAC hooks; those force two more round
 // trips per frame (the correspondences go to the host and the masks come back).
 #include <chrono>
+#include <condition_variable>
 #include <memory>
+#include <mutex>
+#include <thread>
 #include <new>
 #include <vector>
 #include "tracker.h"
@@ -76,6 +79,12 @@ struct flv_f2f_batch {
   static constexpr int NSTAGE = 9;
   double host_ms[4] = {0, 0, 0, 0};                        // host wall time: decisions, enqueue, wait for the device, post-frame
   bool profile = false; cudaEvent_t ev_stage[NSTAGE + 1] = {nullptr}; double stage_ms[NSTAGE] = {0}; long long prof_frames = 0;
+  // groups > 1: this object only dispatches to `sub` (stream s -> sub[s / per_group], local index s % per_group); every
+  // group has its own context / CUDA stream and a host thread, so the latency-bound one-CTA-per-stream stages of one
+  // group overlap the other groups' work and the per-frame host work of one group hides behind the others' kernels
+  std::vector<flv_f2f_batch*> sub; int per_group = 0, stream_offset = 0;
+  struct Pool;
+  Pool* pool = nullptr;
   flv_localmap_batch* lmap = nullptr;                      // keyframes go here (flv_f2f_batch_attach_localmap)
   std::vector<int> kf_streams, kf_counts; std::vector<int64_t> kf_frame, kf_ids; std::vector<double> kf_2d, kf_3d, kf_T;
   char err[512] = {0};
@@ -233,7 +242,94 @@ int run_pnp_hooks(flv_f2f_batch* b) {
 
 }  // namespace
 
+// one persistent host thread per group; image_feed hands every thread its slice of the frame and waits for all of them
+struct flv_f2f_batch::Pool {
+  struct Job { const double* t; const uint8_t* img0; const void* img1; flv_memspace mem; int* kf; int* rs; };
+  std::vector<std::thread> th;
+  std::mutex mu;
+  std::condition_variable cv_go, cv_done;
+  unsigned long gen = 0;
+  int pending = 0;
+  bool stop = false;
+  Job job{};
+  std::vector<int> rc;
+  flv_f2f_batch* owner;
+  explicit Pool(flv_f2f_batch* o) : owner(o) {
+    rc.assign(o->sub.size(), 0);
+    for (size_t g = 0; g < o->sub.size(); ++g) th.emplace_back([this, g] { loop((int)g); });
+  }
+  ~Pool() {
+    { std::lock_guard<std::mutex> lk(mu); stop = true; ++gen; }
+    cv_go.notify_all();
+    for (std::thread& t : th) t.join();
+  }
+  void loop(int g) {
+    cudaSetDevice(owner->device);
+    unsigned long seen = 0;
+    for (;;) {
+      Job j;
+      {
+        std::unique_lock<std::mutex> lk(mu);
+        cv_go.wait(lk, [&] { return gen != seen; });
+        seen = gen;
+        if (stop) return;
+        j = job;
+      }
+      flv_f2f_batch* sb = owner->sub[g];
+      const size_t first = (size_t)g * owner->per_group, w = owner->cfg.img_w, h = owner->cfg.img_h;
+      const size_t px1 = owner->stereo ? 1 : 2;
+      rc[g] = flv_f2f_batch_image_feed(sb, j.t + first, j.img0 + first * w * h, (const uint8_t*)j.img1 + first * w * h * px1, j.mem,
+                                       j.kf ? j.kf + first : nullptr, j.rs ? j.rs + first : nullptr);
+      {
+        std::lock_guard<std::mutex> lk(mu);
+        --pending;
+      }
+      cv_done.notify_all();
+    }
+  }
+  int run(const Job& j) {
+    {
+      std::lock_guard<std::mutex> lk(mu);
+      job = j; pending = (int)th.size(); ++gen;
+    }
+    cv_go.notify_all();
+    std::unique_lock<std::mutex> lk(mu);
+    cv_done.wait(lk, [&] { return pending == 0; });
+    for (size_t g = 0; g < rc.size(); ++g)
+      if (rc[g]) { snprintf(owner->err, sizeof(owner->err), "group %d: %s", (int)g, owner->sub[g]->err); return rc[g]; }
+    return FLV_OK;
+  }
+};
+
+namespace {
+// dispatch helpers for grouped batches
+inline flv_f2f_batch* sub_of(flv_f2f_batch* b, int& stream) {
+  if (b->sub.empty()) return b;
+  flv_f2f_batch* sb = b->sub[stream / b->per_group];
+  stream = stream % b->per_group;
+  return sb;
+}
+}  // namespace
+
 extern "C" {
+
+flv_f2f_batch* flv_f2f_batch_create_grouped(const flv_f2f_config* cfg, int n_streams, int device, int groups) {
+  if (!cfg || n_streams < 1 || groups < 1) return nullptr;
+  if (groups == 1 || n_streams % groups != 0 || n_streams / groups < 1) return flv_f2f_batch_create(cfg, n_streams, device);
+  flv_f2f_batch* b = new (std::nothrow) flv_f2f_batch();
+  if (!b) return nullptr;
+  b->cfg = *cfg; b->S = n_streams; b->device = device; b->per_group = n_streams / groups;
+  b->unrect = cfg->cam_type == 2; b->stereo = cfg->cam_type != 0;
+  for (int g = 0; g < groups; ++g) {
+    flv_f2f_batch* sb = flv_f2f_batch_create(cfg, b->per_group, device);
+    if (!sb) { snprintf(b->err, sizeof(b->err), "group %d: allocation failed", g); return b; }
+    sb->stream_offset = g * b->per_group;
+    b->sub.push_back(sb);
+    if (sb->err[0]) { snprintf(b->err, sizeof(b->err), "group %d: %s", g, sb->err); return b; }
+  }
+  b->pool = new flv_f2f_batch::Pool(b);
+  return b;
+}
 
 flv_f2f_batch* flv_f2f_batch_create(const flv_f2f_config* cfg, int n_streams, int device) {
   if (!cfg || n_streams < 1) return nullptr;
@@ -265,6 +361,12 @@ flv_f2f_batch* flv_f2f_batch_create(const flv_f2f_config* cfg, int n_streams, in
 
 void flv_f2f_batch_destroy(flv_f2f_batch* b) {
   if (!b) return;
+  if (!b->sub.empty() || b->pool) {
+    delete b->pool;
+    for (flv_f2f_batch* sb : b->sub) flv_f2f_batch_destroy(sb);
+    delete b;
+    return;
+  }
   if (b->ctx) { cudaSetDevice(b->device); cudaDeviceSynchronize(); }
   if (b->d_block) cudaFree(b->d_block);
   if (b->h_ctl) cudaFreeHost(b->h_ctl);
@@ -278,24 +380,30 @@ void flv_f2f_batch_destroy(flv_f2f_batch* b) {
 }
 
 const char* flv_f2f_batch_last_error(flv_f2f_batch* b) { return b ? b->err : "null"; }
-flv_ctx* flv_f2f_batch_context(flv_f2f_batch* b) { return b ? b->ctx : nullptr; }
+flv_ctx* flv_f2f_batch_context(flv_f2f_batch* b) { return b ? (b->sub.empty() ? b->ctx : b->sub[0]->ctx) : nullptr; }
+int flv_f2f_batch_groups(flv_f2f_batch* b) { return b ? (b->sub.empty() ? 1 : (int)b->sub.size()) : 0; }
 
 int flv_f2f_batch_set_lens(flv_f2f_batch* b, int cam, const double* K4, const double* D14, const double* R9) {
   if (!b || (cam != 0 && cam != 1) || !K4 || !D14 || !R9) return FLV_ERR_INVALID;
   if (D14[12] != 0 || D14[13] != 0) return FLV_ERR_UNSUPPORTED;
+  if (!b->sub.empty()) { for (flv_f2f_batch* sb : b->sub) { const int rc = flv_f2f_batch_set_lens(sb, cam, K4, D14, R9); if (rc) return rc; } return FLV_OK; }
   flv::LensModel& m = cam == 0 ? b->d.cam.lens0 : b->d.cam.lens1;
   m.fx = K4[0]; m.fy = K4[1]; m.cx = K4[2]; m.cy = K4[3];
   for (int i = 0; i < 14; ++i) m.k[i] = D14[i];
   for (int i = 0; i < 9; ++i) m.R[i] = R9[i];
   return FLV_OK;
 }
-int flv_f2f_batch_set_equalize_hist(flv_f2f_batch* b, int enable) { return b && b->ctx ? flv_set_equalize_hist(b->ctx, enable) : FLV_ERR_INVALID; }
+int flv_f2f_batch_set_equalize_hist(flv_f2f_batch* b, int enable) {
+  if (b && !b->sub.empty()) { for (flv_f2f_batch* sb : b->sub) { const int rc = flv_f2f_batch_set_equalize_hist(sb, enable); if (rc) return rc; } return FLV_OK; }
+  return b && b->ctx ? flv_set_equalize_hist(b->ctx, enable) : FLV_ERR_INVALID;
+}
 void flv_f2f_batch_set_ransac_hooks(flv_f2f_batch* b, flv_f2f_fmat_fn fmat, flv_f2f_pnp_fn pnp, void* user) {
-  if (b) { b->fmat_fn = fmat; b->pnp_fn = pnp; b->hook_user = user; }
+  if (b) { b->fmat_fn = fmat; b->pnp_fn = pnp; b->hook_user = user; for (flv_f2f_batch* sb : b->sub) flv_f2f_batch_set_ransac_hooks(sb, fmat, pnp, user); }
 }
 
 int flv_f2f_batch_imu_feed(flv_f2f_batch* b, int stream, double t, const double* acc, const double* gyro) {   // f2f_tracking.cpp:46-57
   if (!b || stream < 0 || stream >= b->S || !acc || !gyro) return FLV_ERR_INVALID;
+  b = sub_of(b, stream);
   StreamState& s = b->st[stream];
   flv::IMUSTATE im; im.timestamp = t; im.acc_raw = Vec3{acc[0], acc[1], acc[2]}; im.gyro_raw = Vec3{gyro[0], gyro[1], gyro[2]};
   Quat q; Vec3 p, v;
@@ -306,6 +414,10 @@ int flv_f2f_batch_imu_feed(flv_f2f_batch* b, int stream, double t, const double*
 
 int flv_f2f_batch_image_feed(flv_f2f_batch* b, const double* t, const uint8_t* img0, const void* img1, flv_memspace mem,
                              int* new_keyframe, int* reset_cmd) {
+  if (b && b->pool) {
+    if (!t || !img0 || !img1) return FLV_ERR_INVALID;
+    return b->pool->run(flv_f2f_batch::Pool::Job{t, img0, img1, mem, new_keyframe, reset_cmd});
+  }
   if (!b || !b->ctx || !b->d_block || !t || !img0 || !img1) return FLV_ERR_INVALID;
   flv_ctx* ctx = b->ctx;
   const int S = b->S, M = b->M;
@@ -528,7 +640,7 @@ int flv_f2f_batch_image_feed(flv_f2f_batch* b, const double* t, const uint8_t* i
       }
       double T7[7]; to7(z.cur_T, T7);
       b->kf_T.insert(b->kf_T.end(), T7, T7 + 7);
-      b->kf_streams.push_back(s); b->kf_counts.push_back(cnt); b->kf_frame.push_back(z.frameCount);
+      b->kf_streams.push_back(b->stream_offset + s); b->kf_counts.push_back(cnt); b->kf_frame.push_back(z.frameCount);
     }
     if (accepted) b->have_last[s] = 1;
     else if (b->have_last[s]) {
@@ -553,11 +665,16 @@ int flv_f2f_batch_image_feed(flv_f2f_batch* b, const double* t, const uint8_t* i
   return FLV_OK;
 }
 
-int flv_f2f_batch_state(flv_f2f_batch* b, int stream) { return (b && stream >= 0 && stream < b->S) ? b->st[stream].state : FLV_ERR_INVALID; }
+int flv_f2f_batch_state(flv_f2f_batch* b, int stream) {
+  if (!b || stream < 0 || stream >= b->S) return FLV_ERR_INVALID;
+  b = sub_of(b, stream);
+  return b->st[stream].state;
+}
 
 int flv_f2f_batch_get_frame(flv_f2f_batch* b, int stream, double* T_c_w, int64_t* lm_id, double* plane_xy, double* undist_xy,
                             double* p3d_w, uint8_t* has_3d, uint8_t* is_inlier, int cap) {
   if (!b || stream < 0 || stream >= b->S) return FLV_ERR_INVALID;
+  b = sub_of(b, stream);
   const StreamState& z = b->st[stream];
   if (T_c_w) to7(z.cur_T, T_c_w);
   const size_t k0 = (size_t)stream * b->M;
@@ -578,6 +695,7 @@ int flv_f2f_batch_get_frame(flv_f2f_batch* b, int stream, double* T_c_w, int64_t
 int flv_f2f_batch_get_frame_ex(flv_f2f_batch* b, int stream, double* p3d_c, double* first_obs_2d, double* first_obs_pose,
                                double* T_c_w_last_keyframe, int cap) {
   if (!b || stream < 0 || stream >= b->S) return FLV_ERR_INVALID;
+  b = sub_of(b, stream);
   const StreamState& z = b->st[stream];
   if (T_c_w_last_keyframe) to7(z.T_kf, T_c_w_last_keyframe);
   const size_t k0 = (size_t)stream * b->M;
@@ -594,16 +712,19 @@ int flv_f2f_batch_get_frame_ex(flv_f2f_batch* b, int stream, double* p3d_c, doub
 
 int flv_f2f_batch_get_imu_states(flv_f2f_batch* b, int stream, double* out11, int cap) {
   if (!b || stream < 0 || stream >= b->S) return FLV_ERR_INVALID;
+  b = sub_of(b, stream);
   return b->st[stream].vim->dump_states(out11, cap);
 }
 int flv_f2f_batch_get_imu_bias(flv_f2f_batch* b, int stream, double* acc_bias, double* gyro_bias) {
   if (!b || stream < 0 || stream >= b->S) return FLV_ERR_INVALID;
+  b = sub_of(b, stream);
   const StreamState& z = b->st[stream];
   for (int k = 0; k < 3; ++k) { if (acc_bias) acc_bias[k] = z.vim->acc_bias[k]; if (gyro_bias) gyro_bias[k] = z.vim->gyro_bias[k]; }
   return z.has_imu ? 1 : 0;
 }
 int flv_f2f_batch_tracking_counts(flv_f2f_batch* b, int stream, int* of, int* fi, int* pnp) {
   if (!b || stream < 0 || stream >= b->S) return FLV_ERR_INVALID;
+  b = sub_of(b, stream);
   const StreamState& z = b->st[stream];
   if (of) *of = z.of_cnt; if (fi) *fi = z.f_cnt; if (pnp) *pnp = z.pnp_cnt;
   return FLV_OK;
@@ -618,6 +739,7 @@ int flv_f2f_batch_imu_feed_many(flv_f2f_batch* b, int n, const int* streams, con
 }
 int flv_f2f_batch_set_profile(flv_f2f_batch* b, int enable) {
   if (!b) return FLV_ERR_INVALID;
+  if (!b->sub.empty()) { for (flv_f2f_batch* sb : b->sub) { const int rc = flv_f2f_batch_set_profile(sb, enable); if (rc) return rc; } return FLV_OK; }
   if (enable && !b->ev_stage[0])
     for (int i = 0; i <= flv_f2f_batch::NSTAGE; ++i) B_CUDA(b, cudaEventCreate(&b->ev_stage[i]));
   b->profile = enable != 0;
@@ -628,19 +750,34 @@ int flv_f2f_batch_set_profile(flv_f2f_batch* b, int enable) {
 }
 int flv_f2f_batch_get_profile(flv_f2f_batch* b, double* stage_ms9, long long* frames) {
   if (!b || !stage_ms9) return FLV_ERR_INVALID;
+  if (!b->sub.empty()) {                               // mean over the groups (their stages run concurrently)
+    for (int i = 0; i < flv_f2f_batch::NSTAGE; ++i) stage_ms9[i] = 0;
+    for (flv_f2f_batch* sb : b->sub) for (int i = 0; i < flv_f2f_batch::NSTAGE; ++i) stage_ms9[i] += sb->stage_ms[i] / (double)b->sub.size();
+    if (frames) *frames = b->sub[0]->prof_frames;
+    return flv_f2f_batch::NSTAGE;
+  }
   for (int i = 0; i < flv_f2f_batch::NSTAGE; ++i) stage_ms9[i] = b->stage_ms[i];
   if (frames) *frames = b->prof_frames;
   return flv_f2f_batch::NSTAGE;
 }
 int flv_f2f_batch_get_host_profile(flv_f2f_batch* b, double* host_ms4) {
   if (!b || !host_ms4) return FLV_ERR_INVALID;
+  if (!b->sub.empty()) {
+    for (int i = 0; i < 4; ++i) host_ms4[i] = 0;
+    for (flv_f2f_batch* sb : b->sub) for (int i = 0; i < 4; ++i) host_ms4[i] += sb->host_ms[i] / (double)b->sub.size();
+    return 4;
+  }
   for (int i = 0; i < 4; ++i) host_ms4[i] = b->host_ms[i];
   return 4;
 }
-long long flv_f2f_batch_launch_count(flv_f2f_batch* b) { return b && b->ctx ? flv_launch_count(b->ctx) : 0; }
+long long flv_f2f_batch_launch_count(flv_f2f_batch* b) {
+  if (b && !b->sub.empty()) { long long n = 0; for (flv_f2f_batch* sb : b->sub) n += flv_f2f_batch_launch_count(sb); return n; }
+  return b && b->ctx ? flv_launch_count(b->ctx) : 0;
+}
 int flv_f2f_batch_attach_localmap(flv_f2f_batch* b, flv_localmap_batch* lm) {
   if (!b) return FLV_ERR_INVALID;
   b->lmap = lm;
+  for (flv_f2f_batch* sb : b->sub) sb->lmap = lm;
   return FLV_OK;
 }
 

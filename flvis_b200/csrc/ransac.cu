@@ -103,13 +103,74 @@ __device__ void rank2(double* M) {
 // (sel(i) -> bool, evaluated for i in [i0, i1) with stride); returns partial sums for a later reduction
 struct NormT { double cax, cay, cbx, cby, sa, sb; };
 
-__device__ void f_from_gram(double* G /*9x9 destroyed*/, const NormT& T, double* F) {
-  double V[81];
-  jacobi_eigen<9>(G, V);
-  int lo = 0;
-  for (int i = 1; i < 9; ++i) if (G[10 * i] < G[10 * lo]) lo = i;
-  double Fn[9];
-  for (int i = 0; i < 9; ++i) Fn[i] = V[9 * i + lo];
+// null vector of an 8 x 9 matrix (row-major, destroyed) by Gaussian elimination with complete pivoting: the minimal
+// 8-point sample determines F up to scale exactly, so no eigen-decomposition is needed (a 9 x 9 Jacobi costs ~50x more
+// serial fp64 work per hypothesis thread).  Returns false for a rank-deficient sample.
+__device__ bool null_vector_8x9(double* A, double* x) {
+  int c[9];
+  for (int j = 0; j < 9; ++j) c[j] = j;
+  double amax0 = 0;
+  for (int k = 0; k < 8; ++k) {
+    int bi = k, bj = k;
+    double best = -1;
+    for (int i = k; i < 8; ++i)
+      for (int j = k; j < 9; ++j) { const double v = fabs(A[9 * i + c[j]]); if (v > best) { best = v; bi = i; bj = j; } }
+    if (k == 0) amax0 = best;
+    if (!(best > 1e-12 * amax0) || best == 0) return false;
+    if (bi != k) for (int j = 0; j < 9; ++j) { const double t = A[9 * k + j]; A[9 * k + j] = A[9 * bi + j]; A[9 * bi + j] = t; }
+    { const int t = c[k]; c[k] = c[bj]; c[bj] = t; }
+    const double ip = 1.0 / A[9 * k + c[k]];
+    for (int i = k + 1; i < 8; ++i) {
+      const double f = A[9 * i + c[k]] * ip;
+      if (f == 0) continue;
+      for (int j = k; j < 9; ++j) A[9 * i + c[j]] -= f * A[9 * k + c[j]];
+    }
+  }
+  x[c[8]] = 1.0;
+  for (int k = 7; k >= 0; --k) {
+    double sum = 0;
+    for (int j = k + 1; j < 9; ++j) sum += A[9 * k + c[j]] * x[c[j]];
+    x[c[k]] = -sum / A[9 * k + c[k]];
+  }
+  double n2 = 0;
+  for (int j = 0; j < 9; ++j) n2 += x[j] * x[j];
+  const double in = 1.0 / sqrt(n2);
+  for (int j = 0; j < 9; ++j) x[j] *= in;
+  return true;
+}
+
+// eigenvector of the smallest eigenvalue of a symmetric positive semi-definite 9 x 9 matrix (row-major, destroyed) by
+// inverse iteration on an LDL^T factorisation: the least-squares F of an over-determined inlier set
+__device__ void smallest_eigvec_9(double* G, double* x) {
+  double tr = 0;
+  for (int i = 0; i < 9; ++i) tr += G[10 * i];
+  const double eps = 1e-13 * tr + 1e-300;
+  for (int i = 0; i < 9; ++i) G[10 * i] += eps;
+  // in-place LDL^T: L below the diagonal (unit), D on it
+  for (int j = 0; j < 9; ++j) {
+    double d = G[10 * j];
+    for (int k = 0; k < j; ++k) d -= G[9 * j + k] * G[9 * j + k] * G[10 * k];
+    if (!(d > 1e-300)) d = 1e-300;
+    G[10 * j] = d;
+    for (int i = j + 1; i < 9; ++i) {
+      double v = G[9 * i + j];
+      for (int k = 0; k < j; ++k) v -= G[9 * i + k] * G[9 * j + k] * G[10 * k];
+      G[9 * i + j] = v / d;
+    }
+  }
+  for (int i = 0; i < 9; ++i) x[i] = 1.0 / 3.0 + 0.01 * i;      // generic start: not orthogonal to anything in particular
+  for (int it = 0; it < 10; ++it) {
+    for (int i = 0; i < 9; ++i) { double v = x[i]; for (int k = 0; k < i; ++k) v -= G[9 * i + k] * x[k]; x[i] = v; }
+    for (int i = 0; i < 9; ++i) x[i] /= G[10 * i];
+    for (int i = 8; i >= 0; --i) { double v = x[i]; for (int k = i + 1; k < 9; ++k) v -= G[9 * k + i] * x[k]; x[i] = v; }
+    double n2 = 0;
+    for (int i = 0; i < 9; ++i) n2 += x[i] * x[i];
+    const double in = 1.0 / sqrt(n2);
+    for (int i = 0; i < 9; ++i) x[i] *= in;
+  }
+}
+
+__device__ void f_from_vec(double* Fn /*unit 9-vector, destroyed*/, const NormT& T, double* F) {
   rank2(Fn);
   const double Ta[9] = {T.sa, 0, -T.sa * T.cax, 0, T.sa, -T.sa * T.cay, 0, 0, 1};
   const double TbT[9] = {T.sb, 0, 0, 0, T.sb, 0, -T.sb * T.cbx, -T.sb * T.cby, 1};
@@ -164,16 +225,14 @@ __global__ void __launch_bounds__(RS_THREADS) fmat_ransac_kernel(const int* __re
     double Fh[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
     if (da > 1e-9 && db > 1e-9) {
       T.sa = sqrt(2.0) * 8 / da; T.sb = sqrt(2.0) * 8 / db;
-      double G[81];
-      for (int i = 0; i < 81; ++i) G[i] = 0;
+      double R8[72], Fn[9];
       for (int i = 0; i < 8; ++i) {
         const double x1 = (A[2 * idx[i]] - T.cax) * T.sa, y1 = (A[2 * idx[i] + 1] - T.cay) * T.sa;
         const double x2 = (B[2 * idx[i]] - T.cbx) * T.sb, y2 = (B[2 * idx[i] + 1] - T.cby) * T.sb;
-        const double r[9] = {x2 * x1, x2 * y1, x2, y2 * x1, y2 * y1, y2, x1, y1, 1};
-        for (int a = 0; a < 9; ++a)
-          for (int b = 0; b < 9; ++b) G[9 * a + b] += r[a] * r[b];
+        double* r = R8 + 9 * i;
+        r[0] = x2 * x1; r[1] = x2 * y1; r[2] = x2; r[3] = y2 * x1; r[4] = y2 * y1; r[5] = y2; r[6] = x1; r[7] = y1; r[8] = 1;
       }
-      f_from_gram(G, T, Fh);
+      if (null_vector_8x9(R8, Fn)) f_from_vec(Fn, T, Fh);
     }
     for (int k = 0; k < 9; ++k) sF[h][k] = Fh[k];
   }
@@ -244,9 +303,10 @@ __global__ void __launch_bounds__(RS_THREADS) fmat_ransac_kernel(const int* __re
   }
   __syncthreads();
   if (tid == 0) {
-    double G[81], Fr[9];
+    double G[81], Fn[9], Fr[9];
     for (int k = 0; k < 81; ++k) G[k] = sG[k];
-    f_from_gram(G, T, Fr);
+    smallest_eigvec_9(G, Fn);
+    f_from_vec(Fn, T, Fr);
     for (int k = 0; k < 9; ++k) sF[0][k] = Fr[k];
   }
   __syncthreads();

@@ -12,6 +12,7 @@
 #include <condition_variable>
 #include <cstdio>
 #include <deque>
+#include <functional>
 #include <memory>
 #include <mutex>
 #include <thread>
@@ -21,6 +22,60 @@
 
 namespace {
 struct KfMsg { int stream; flv::KeyFrameStruct kf; };
+
+// The graph editing of different sequences is independent: a few helper threads share the loop over a submission's
+// keyframes (the solver launch itself stays one call).  Persistent threads, work handed out through an atomic counter.
+class Helpers {
+ public:
+  explicit Helpers(int n) {
+    for (int i = 0; i < n; ++i) th_.emplace_back([this] { loop(); });
+  }
+  ~Helpers() {
+    { std::lock_guard<std::mutex> lk(mu_); stop_ = true; ++gen_; }
+    cv_.notify_all();
+    for (std::thread& t : th_) t.join();
+  }
+  template <class F>
+  void parallel_for(int n, F&& f) {
+    if (n <= 1 || th_.empty()) { for (int i = 0; i < n; ++i) f(i); return; }
+    fn_ = [&f](int i) { f(i); };
+    n_ = n; next_.store(0); done_.store(0);
+    { std::lock_guard<std::mutex> lk(mu_); ++gen_; }
+    cv_.notify_all();
+    work();                                     // the caller takes part
+    while (done_.load(std::memory_order_acquire) < n_) std::this_thread::yield();
+  }
+
+ private:
+  void work() {
+    for (;;) {
+      const int i = next_.fetch_add(1);
+      if (i >= n_) break;
+      fn_(i);
+      done_.fetch_add(1, std::memory_order_release);
+    }
+  }
+  void loop() {
+    unsigned long seen = 0;
+    for (;;) {
+      {
+        std::unique_lock<std::mutex> lk(mu_);
+        cv_.wait(lk, [&] { return gen_ != seen; });
+        seen = gen_;
+        if (stop_) return;
+      }
+      work();
+    }
+  }
+  std::vector<std::thread> th_;
+  std::mutex mu_;
+  std::condition_variable cv_;
+  unsigned long gen_ = 0;
+  bool stop_ = false;
+  std::function<void(int)> fn_;
+  int n_ = 0;
+  std::atomic<int> next_{0}, done_{0};
+};
 }
 
 struct flv_localmap_batch {
@@ -38,6 +93,8 @@ struct flv_localmap_batch {
   long long n_keyframes = 0, n_solves = 0, n_launches = 0;
   double solve_ms = 0, host_ms = 0;            // solver calls / graph editing + packing on the worker thread
   int rP = 0, rL = 0, rE = 0;
+  std::unique_ptr<Helpers> helpers;
+  std::vector<double> poses, lms, uv; std::vector<int> ep, el; std::vector<uint8_t> act;
   char err[256] = {0};
 
   void run();
@@ -58,11 +115,13 @@ bool flv_localmap_batch::process(std::vector<KfMsg>& batch) {
       if (!used[i] && !seen[batch[i].stream]) { seen[batch[i].stream] = 1; round.push_back((int)i); used[i] = 1; }
     done += round.size();
     std::vector<flv::LocalMap::SolveArrays> arr(round.size());
-    std::vector<int> due;
-    for (size_t r = 0; r < round.size(); ++r) {
+    std::vector<char> is_due(round.size(), 0);
+    helpers->parallel_for((int)round.size(), [&](int r) {
       const KfMsg& m = batch[round[r]];
-      if (maps[m.stream]->begin(m.kf, arr[r])) due.push_back((int)r);
-    }
+      is_due[r] = maps[m.stream]->begin(m.kf, arr[r]) ? 1 : 0;
+    });
+    std::vector<int> due;
+    for (size_t r = 0; r < round.size(); ++r) if (is_due[r]) due.push_back((int)r);
     n_keyframes += (long long)round.size();
     if (due.empty()) continue;
     int P = W, L = 0, E = 0;
@@ -72,12 +131,15 @@ bool flv_localmap_batch::process(std::vector<KfMsg>& batch) {
       if (flv_ba_reserve(ctx, rP, rL, rE) != FLV_OK) { snprintf(err, sizeof(err), "flv_ba_reserve: %s", flv_last_error(ctx)); return false; }
     }
     const size_t n = due.size();
-    std::vector<double> poses(n * rP * 7, 0.0), lms(n * (size_t)rL * 3, 0.0), uv(n * (size_t)rE * 2, 0.0);
-    std::vector<int> ep(n * (size_t)rE, 0), el(n * (size_t)rE, 0);
-    std::vector<uint8_t> act(n * (size_t)rE, 0);
+    // launch arrays persist across submissions (strides = the reserved sizes; entries past a window's own counts are never read)
+    if (poses.size() < n * rP * 7) poses.resize(n * rP * 7);
+    if (lms.size() < n * (size_t)rL * 3) lms.resize(n * (size_t)rL * 3);
+    if (uv.size() < n * (size_t)rE * 2) uv.resize(n * (size_t)rE * 2);
+    if (ep.size() < n * (size_t)rE) { ep.resize(n * (size_t)rE); el.resize(n * (size_t)rE); act.resize(n * (size_t)rE); }
     std::vector<flv_ba_problem> pb(n);
     std::vector<flv_ba_stats> st(n);
-    for (size_t j = 0; j < n; ++j) {
+    helpers->parallel_for((int)n, [&](int jj) {
+      const size_t j = (size_t)jj;
       const flv::LocalMap::SolveArrays& a = arr[due[j]];
       std::copy(a.poses.begin(), a.poses.end(), poses.begin() + j * rP * 7);
       std::copy(a.lms.begin(), a.lms.end(), lms.begin() + j * (size_t)rL * 3);
@@ -86,7 +148,7 @@ bool flv_localmap_batch::process(std::vector<KfMsg>& batch) {
       std::copy(a.el.begin(), a.el.end(), el.begin() + j * (size_t)rE);
       std::copy(a.active.begin(), a.active.end(), act.begin() + j * (size_t)rE);
       pb[j] = flv_ba_problem{a.P, a.L, a.E, a.fixed, 0, K[0], K[1], K[2], K[3]};
-    }
+    });
     const flv_ba_params prm{12, 8, 1.0, 3.0, 0, 0};
     const auto t0 = std::chrono::steady_clock::now();
     if (flv_ba_optimize(ctx, (int)n, pb.data(), &prm, poses.data(), lms.data(), ep.data(), el.data(), uv.data(), act.data(), st.data(),
@@ -96,17 +158,22 @@ bool flv_localmap_batch::process(std::vector<KfMsg>& batch) {
     }
     solve_ms += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
     n_solves += (long long)n; n_launches++;
-    for (size_t j = 0; j < n; ++j) {
+    std::vector<flv::CorrectionInfStruct> outs(n);
+    helpers->parallel_for((int)n, [&](int jj) {
+      const size_t j = (size_t)jj;
       flv::LocalMap::SolveArrays& a = arr[due[j]];
       std::copy(poses.begin() + j * rP * 7, poses.begin() + j * rP * 7 + 7 * (size_t)a.P, a.poses.begin());
       std::copy(lms.begin() + j * (size_t)rL * 3, lms.begin() + j * (size_t)rL * 3 + 3 * (size_t)a.L, a.lms.begin());
       std::copy(act.begin() + j * (size_t)rE, act.begin() + j * (size_t)rE + a.E, a.active.begin());
-      const int s = batch[round[due[j]]].stream;
-      flv::CorrectionInfStruct out;
-      maps[s]->end(a, st[j], out);
+      maps[batch[round[due[j]]].stream]->end(a, st[j], outs[j]);
+    });
+    {
       std::lock_guard<std::mutex> lk(mu);
-      latest[s] = std::move(out);
-      n_results[s]++;
+      for (size_t j = 0; j < n; ++j) {
+        const int s = batch[round[due[j]]].stream;
+        latest[s] = std::move(outs[j]);
+        n_results[s]++;
+      }
     }
   }
   host_ms += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - th0).count() - (solve_ms - solve_before);
@@ -153,6 +220,8 @@ flv_localmap_batch* flv_localmap_batch_create(int device, int n_streams, int win
   b->K[0] = fx; b->K[1] = fy; b->K[2] = cx; b->K[3] = cy;
   b->latest.resize(n_streams); b->n_results.assign(n_streams, 0);
   for (int s = 0; s < n_streams; ++s) b->maps.emplace_back(new flv::LocalMap(nullptr, window_size, fx, fy, cx, cy));
+  const unsigned hw = std::thread::hardware_concurrency();
+  b->helpers.reset(new Helpers(n_streams > 1 ? (int)std::min<unsigned>(6, hw > 4 ? hw / 4 : 1) : 0));
   b->worker = std::thread([b] { b->run(); });
   std::unique_lock<std::mutex> lk(b->mu);
   b->cv_idle.wait(lk, [&] { return b->started; });

@@ -130,6 +130,11 @@ int flv_localmap_batch_result(flv_localmap_batch* b, int stream, int64_t* out_fr
  *               new_keyframe[S] / reset_cmd[S] as F2FTracking::image_feed returns them per stream. */
 typedef struct flv_f2f_batch flv_f2f_batch;
 flv_f2f_batch* flv_f2f_batch_create(const flv_f2f_config* cfg, int n_streams, int device);
+/* The same object split into `groups` equal groups of streams (n_streams % groups == 0, else one group): each group has its
+ * own kernel context, CUDA stream and host thread, so the one-CTA-per-stream stages of one group overlap the other groups'
+ * kernels and per-frame host work.  Per-stream results are unchanged (streams never interact). */
+flv_f2f_batch* flv_f2f_batch_create_grouped(const flv_f2f_config* cfg, int n_streams, int device, int groups);
+int flv_f2f_batch_groups(flv_f2f_batch* b);
 void flv_f2f_batch_destroy(flv_f2f_batch* b);
 const char* flv_f2f_batch_last_error(flv_f2f_batch* b);
 flv_ctx* flv_f2f_batch_context(flv_f2f_batch* b);      /* the batch's kernel context (stream selection, launch counter) */

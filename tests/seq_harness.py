@@ -145,9 +145,11 @@ class SingleTrackers:
 class BatchTracker:
     """One flv_f2f_batch handle advancing len(seqs) streams of the same sensor together."""
 
-    def __init__(self, lib, seqs, hooks):
+    def __init__(self, lib, seqs, hooks, groups=1):
         _setup(lib)
         vp = C.c_void_p
+        lib.flv_f2f_batch_create_grouped.restype = vp
+        lib.flv_f2f_batch_create_grouped.argtypes = [C.POINTER(Cfg), C.c_int, C.c_int, C.c_int]
         lib.flv_f2f_batch_create.restype = vp
         lib.flv_f2f_batch_create.argtypes = [C.POINTER(Cfg), C.c_int, C.c_int]
         lib.flv_f2f_batch_destroy.argtypes = [vp]
@@ -167,7 +169,7 @@ class BatchTracker:
         self.lib, self.S = lib, len(seqs)
         cfg, lenses, equalize, K, mk = make_cfg(seqs[0])
         self.K, self.mk = K, mk
-        self.b = lib.flv_f2f_batch_create(C.byref(cfg), self.S, 0)
+        self.b = lib.flv_f2f_batch_create_grouped(C.byref(cfg), self.S, 0, groups)
         assert self.b and lib.flv_f2f_batch_last_error(self.b) == b"", lib.flv_f2f_batch_last_error(self.b)
         if lenses:
             for cam, (k4, d14, r9) in enumerate(lenses):
@@ -293,13 +295,13 @@ def run_sequence(lib, seq, **kw):
     return run(lib, [seq], batch=False, **kw)[0]
 
 
-def run(lib, seqs, batch=False, tol_pose=1e-6, tol_und=0.0, tol_p3=1e-6, window=None, hooks=True, lockstep=False, free_frames=0):
+def run(lib, seqs, batch=False, tol_pose=1e-6, tol_und=0.0, tol_p3=1e-6, window=None, hooks=True, lockstep=False, free_frames=0, groups=1):
     """Frame-by-frame comparison of len(seqs) sequences (same sensor, same frame count), each against its own oracle, driven
     through N single trackers or ONE batched tracker; returns one summary dict per sequence.
     lockstep: re-seed the oracle from the tracker after every frame (see sync_oracle_from_tracker);
     free_frames: additionally run a free-running oracle over the first `free_frames` frames for the ATE comparison;
     window: chain a local map of that size on every stream's keyframes."""
-    trk = (BatchTracker if batch else SingleTrackers)(lib, seqs, hooks)
+    trk = BatchTracker(lib, seqs, hooks, groups) if batch else SingleTrackers(lib, seqs, hooks)
     N = len(seqs)
     refs = trk.refs
     frees = [make_cfg(q)[4]() for q in seqs] if free_frames else [None] * N

@@ -69,3 +69,12 @@ def test_batch_equals_separate_single_trackers_bit_for_bit(lib):
     assert saw_fail
     assert [batch.state(s) for s in range(3)][0] == "Tracking"
     single.close(); batch.close()
+
+
+def test_grouped_batch_two_groups_matches_oracles(lib):
+    """flv_f2f_batch_create_grouped: 4 depth + IMU streams in 2 groups (own context, CUDA stream and host thread each, the
+    hooks are called from the group threads); per-stream results are unchanged."""
+    seqs = [sequences.make_c0(30, seed=10 + s, skip=6, t_rest=0.25) for s in range(4)]
+    outs = sh.run(lib, seqs, batch=True, tol_pose=1e-6, tol_und=0.0, tol_p3=1e-6, lockstep=True, groups=2)
+    for r in outs:
+        assert r["final_state"] == "Tracking" and r["frames_tracked"] >= 22 and r["guess_used"] >= 20
