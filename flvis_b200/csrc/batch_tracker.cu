@@ -75,6 +75,9 @@ struct flv_f2f_batch {
   flv_f2f_fmat_fn fmat_fn = nullptr; flv_f2f_pnp_fn pnp_fn = nullptr; void* hook_user = nullptr;
   std::vector<char> have_last;                             // stream has an accepted "last" frame on the device
   cudaEvent_t ev_done = nullptr;
+  // the right image (ingest + pyramid) is only needed by the left->right LK late in the frame: it is prepared on a side
+  // stream while the frame->frame stages run
+  cudaStream_t side = nullptr; cudaEvent_t ev_fork_r = nullptr, ev_right = nullptr;
   // optional per-stage device timing (flv_f2f_batch_set_profile): events on the compute stream at the stage boundaries
   static constexpr int NSTAGE = 9;
   double host_ms[4] = {0, 0, 0, 0};                        // host wall time: decisions, enqueue, wait for the device, post-frame
@@ -179,6 +182,9 @@ int alloc_device(flv_f2f_batch* b) {
   B_CUDA(b, cudaMallocHost(&b->h_tab, b->tab_bytes));
   memset(b->h_tab, 0, b->tab_bytes);
   B_CUDA(b, cudaEventCreateWithFlags(&b->ev_done, cudaEventDisableTiming));
+  B_CUDA(b, cudaStreamCreateWithFlags(&b->side, cudaStreamNonBlocking));
+  B_CUDA(b, cudaEventCreateWithFlags(&b->ev_fork_r, cudaEventDisableTiming));
+  B_CUDA(b, cudaEventCreateWithFlags(&b->ev_right, cudaEventDisableTiming));
   return FLV_OK;
 }
 
@@ -374,6 +380,9 @@ void flv_f2f_batch_destroy(flv_f2f_batch* b) {
   if (b->h_rnd) cudaFreeHost(b->h_rnd);
   if (b->h_tab) cudaFreeHost(b->h_tab);
   if (b->ev_done) cudaEventDestroy(b->ev_done);
+  if (b->ev_fork_r) cudaEventDestroy(b->ev_fork_r);
+  if (b->ev_right) cudaEventDestroy(b->ev_right);
+  if (b->side) cudaStreamDestroy(b->side);
   for (cudaEvent_t e : b->ev_stage) if (e) cudaEventDestroy(e);
   if (b->ctx) flv_destroy(b->ctx);
   delete b;
@@ -500,11 +509,22 @@ int flv_f2f_batch_image_feed(flv_f2f_batch* b, const double* t, const uint8_t* i
   B_CUDA(b, cudaMemcpyAsync(b->d.b.rnd, b->h_rnd, (size_t)S * M * 4, cudaMemcpyHostToDevice, cs));
   // ---- images: level 0 + pyramids (f2f_tracking.cpp:78-145) -------------------------------------------------------------
   B_RC(b, flv_upload_images(ctx, cur0, S, img0, w, w * h, mem));
-  if (b->stereo) B_RC(b, flv_upload_images(ctx, cur1, S, (const uint8_t*)img1, w, w * h, mem));
-  else B_CUDA(b, cudaMemcpyAsync(b->d.depth, img1, (size_t)S * w * h * 2, mem == FLV_MEM_HOST ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice, cs));
+  if (b->stereo) {
+    // fork after the left ingest (the equalizeHist scratch is shared; the previous frame's readers of the cur1 slot are
+    // ordered before this point on the main stream)
+    B_CUDA(b, cudaEventRecord(b->ev_fork_r, cs));
+    B_CUDA(b, cudaStreamWaitEvent(b->side, b->ev_fork_r, 0));
+    ctx->stream = b->side;
+    int rc_r = flv_upload_images(ctx, cur1, S, (const uint8_t*)img1, w, w * h, mem);
+    if (!rc_r) rc_r = flv_build_pyramid(ctx, cur1, S);
+    ctx->stream = cs;
+    if (rc_r) { snprintf(b->err, sizeof(b->err), "right image: %s", flv_last_error(ctx)); return rc_r; }
+    B_CUDA(b, cudaEventRecord(b->ev_right, b->side));
+  } else {
+    B_CUDA(b, cudaMemcpyAsync(b->d.depth, img1, (size_t)S * w * h * 2, mem == FLV_MEM_HOST ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice, cs));
+  }
   B_RC(b, flv_build_pyramid(ctx, cur0, S));
   if (any_track) B_RC(b, flv_feature_prepare(ctx, cur0, S, &b->fprm, 1));      // Shi-Tomasi of the new image overlaps tracking
-  if (b->stereo) B_RC(b, flv_build_pyramid(ctx, cur1, S));
   // ---- tracking path (mode 1 streams; the others run on empty counts) ---------------------------------------------------
   B_RC(b, flv_trk_stage_prepare(ctx, b->d, S));
   const flv_lk_params lk_f2f{31, 10, 30, 1e-3, 1e-4}, lk_lr{31, 5, 30, 1e-3, 1e-4};
@@ -551,6 +571,7 @@ int flv_f2f_batch_image_feed(flv_f2f_batch* b, const double* t, const uint8_t* i
   mark();                                                                 // 7: left -> right LK
   if (any_track || any_init) {
     if (b->stereo) {
+      B_CUDA(b, cudaStreamWaitEvent(cs, b->ev_right, 0));
       B_RC(b, flv_lk_track(ctx, cur0, cur1, S, q.n_r, q.r_prev, q.r_init, q.r_next, q.r_st, q.r_err, &lk_lr, FLV_MEM_DEVICE));
       B_RC(b, flv_trk_stage_pt1(ctx, b->d, S));
     }

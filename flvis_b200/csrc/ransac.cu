@@ -107,35 +107,65 @@ struct NormT { double cax, cay, cbx, cby, sa, sb; };
 // 8-point sample determines F up to scale exactly, so no eigen-decomposition is needed (a 9 x 9 Jacobi costs ~50x more
 // serial fp64 work per hypothesis thread).  Returns false for a rank-deficient sample.
 __device__ bool null_vector_8x9(double* A, double* x) {
-  int c[9];
-  for (int j = 0; j < 9; ++j) c[j] = j;
+  // every index below is a compile-time constant after unrolling (pivot row / column swaps are predicated), so the
+  // matrix never needs dynamically indexed local memory
+  int swp[8];
   double amax0 = 0;
+  bool ok = true;
+#pragma unroll
   for (int k = 0; k < 8; ++k) {
     int bi = k, bj = k;
     double best = -1;
+#pragma unroll
     for (int i = k; i < 8; ++i)
-      for (int j = k; j < 9; ++j) { const double v = fabs(A[9 * i + c[j]]); if (v > best) { best = v; bi = i; bj = j; } }
+#pragma unroll
+      for (int j = k; j < 9; ++j) { const double v = fabs(A[9 * i + j]); if (v > best) { best = v; bi = i; bj = j; } }
     if (k == 0) amax0 = best;
-    if (!(best > 1e-12 * amax0) || best == 0) return false;
-    if (bi != k) for (int j = 0; j < 9; ++j) { const double t = A[9 * k + j]; A[9 * k + j] = A[9 * bi + j]; A[9 * bi + j] = t; }
-    { const int t = c[k]; c[k] = c[bj]; c[bj] = t; }
-    const double ip = 1.0 / A[9 * k + c[k]];
+    if (!(best > 1e-12 * amax0) || best == 0) ok = false;
+    swp[k] = bj;
+#pragma unroll
+    for (int i = k + 1; i < 8; ++i)
+      if (i == bi) {
+#pragma unroll
+        for (int j = 0; j < 9; ++j) { const double t = A[9 * k + j]; A[9 * k + j] = A[9 * i + j]; A[9 * i + j] = t; }
+      }
+#pragma unroll
+    for (int j = k + 1; j < 9; ++j)
+      if (j == bj) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { const double t = A[9 * i + k]; A[9 * i + k] = A[9 * i + j]; A[9 * i + j] = t; }
+      }
+    const double piv = A[9 * k + k];
+    const double ip = piv != 0 ? 1.0 / piv : 0.0;
+#pragma unroll
     for (int i = k + 1; i < 8; ++i) {
-      const double f = A[9 * i + c[k]] * ip;
-      if (f == 0) continue;
-      for (int j = k; j < 9; ++j) A[9 * i + c[j]] -= f * A[9 * k + c[j]];
+      const double f = A[9 * i + k] * ip;
+#pragma unroll
+      for (int j = k; j < 9; ++j) A[9 * i + j] -= f * A[9 * k + j];
     }
   }
-  x[c[8]] = 1.0;
+  if (!ok) return false;
+  double y[9];
+  y[8] = 1.0;
+#pragma unroll
   for (int k = 7; k >= 0; --k) {
     double sum = 0;
-    for (int j = k + 1; j < 9; ++j) sum += A[9 * k + c[j]] * x[c[j]];
-    x[c[k]] = -sum / A[9 * k + c[k]];
+#pragma unroll
+    for (int j = k + 1; j < 9; ++j) sum += A[9 * k + j] * y[j];
+    y[k] = -sum / A[9 * k + k];
   }
+  // undo the column swaps, last first
+#pragma unroll
+  for (int k = 7; k >= 0; --k)
+#pragma unroll
+    for (int j = k + 1; j < 9; ++j)
+      if (j == swp[k]) { const double t = y[k]; y[k] = y[j]; y[j] = t; }
   double n2 = 0;
-  for (int j = 0; j < 9; ++j) n2 += x[j] * x[j];
+#pragma unroll
+  for (int j = 0; j < 9; ++j) n2 += y[j] * y[j];
   const double in = 1.0 / sqrt(n2);
-  for (int j = 0; j < 9; ++j) x[j] *= in;
+#pragma unroll
+  for (int j = 0; j < 9; ++j) x[j] = y[j] * in;
   return true;
 }
 

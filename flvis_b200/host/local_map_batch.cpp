@@ -195,8 +195,14 @@ void flv_localmap_batch::run() {
       std::unique_lock<std::mutex> lk(mu);
       cv_work.wait(lk, [&] { return stop || !queue.empty(); });
       if (queue.empty()) break;                  // stop requested and nothing left
+      // everything that is queued goes into ONE launch: the solver's latency (a few ms) is paid once per drain, however
+      // many submissions (frames, stream groups) piled up behind the previous one
       batch = std::move(queue.front());
       queue.pop_front();
+      while (!queue.empty()) {
+        for (KfMsg& m : queue.front()) batch.push_back(std::move(m));
+        queue.pop_front();
+      }
       busy = true;
     }
     const bool ok = failed ? false : process(batch);
