@@ -206,6 +206,7 @@ def run_ours(args, wl, pools):
     def make_tracker(n):
         t = fb.BatchTracker(cfg, n, device=local_rank, lenses=lenses, equalize=equalize, groups=args.groups if n == S else 1)
         t.set_stream(stream.cuda_stream)
+        t.set_readback(False)                      # keyframe / pose consumers only need the lean landmark records
         lm = fb.LocalMapBatch(n, wl["window"], K, device=local_rank)
         t.attach_localmap(lm)
         return t, lm
@@ -336,7 +337,7 @@ def run_ours(args, wl, pools):
             ates.append(float(np.sqrt(np.mean(np.sum((d - d.mean(0)) ** 2, axis=1)))))
         img1_bytes = W * H * (1 if wl["stereo"] else 2)
         h2d = S * (W * H + img1_bytes) + S * (160 + 512 * 4)                  # images + control block + dummy-depth table
-        d2h = S * 120 + S * 512 * 170                                         # summaries + the landmark lists (170 B per landmark slot)
+        d2h = S * 120 + S * (512 * 50 + 60)                                   # summaries + lean landmark records (50 B per landmark slot)
         cpu = cpu_baseline(args, wl, pools, min(S, os.cpu_count() or 1), 6) if world == 1 and not args.no_cpu else None
         if single is not None and cpu is not None:
             single["cpu_value"] = cpu_baseline(args, wl, pools, 1, 8)["value"]

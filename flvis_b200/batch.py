@@ -45,6 +45,7 @@ def _bind(lib):
     lib.flv_f2f_batch_launch_count.restype = C.c_longlong
     lib.flv_f2f_batch_launch_count.argtypes = [vp]
     lib.flv_f2f_batch_attach_localmap.argtypes = [vp, vp]
+    lib.flv_f2f_batch_set_readback.argtypes = [vp, C.c_int]
     lib.flv_f2f_batch_set_profile.argtypes = [vp, C.c_int]
     lib.flv_f2f_batch_get_profile.argtypes = [vp, vp, vp]
     lib.flv_f2f_batch_get_host_profile.argtypes = [vp, vp]
@@ -112,6 +113,9 @@ class BatchTracker:
         if self.groups > 1:
             return
         self.lib.flv_set_stream(self.lib.flv_f2f_batch_context(self.h), C.c_void_p(cuda_stream_ptr))
+
+    def set_readback(self, full):
+        self._chk(self.lib.flv_f2f_batch_set_readback(self.h, 1 if full else 0))
 
     def attach_localmap(self, lm):
         self._chk(self.lib.flv_f2f_batch_attach_localmap(self.h, lm.h if lm else None))

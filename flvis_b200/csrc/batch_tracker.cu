@@ -68,7 +68,8 @@ struct flv_f2f_batch {
   void* d_block = nullptr; size_t d_bytes = 0;
   // pinned host mirrors
   TrkCtl* h_ctl = nullptr; TrkOut* h_out = nullptr; float* h_rnd = nullptr;
-  unsigned char* h_tab = nullptr; size_t tab_bytes = 0;   // read-back of the L tables
+  unsigned char* h_tab = nullptr; size_t tab_bytes = 0, lean_bytes = 0;   // read-back of the L tables
+  bool full_readback = true;
   size_t o_id = 0, o_plane = 0, o_und = 0, o_p3w = 0, o_p3c = 0, o_f2d = 0, o_fpose = 0, o_has = 0, o_inl = 0, o_n = 0, o_T = 0;
   void* d_tab = nullptr;                                   // the L table block on the device (contiguous, same offsets)
   int slots[3] = {0, 1, 2};                                // prev0, cur0, cur1
@@ -83,11 +84,11 @@ struct flv_f2f_batch {
   double host_ms[4] = {0, 0, 0, 0};                        // host wall time: decisions, enqueue, wait for the device, post-frame
   bool profile = false; cudaEvent_t ev_stage[NSTAGE + 1] = {nullptr}; double stage_ms[NSTAGE] = {0}; long long prof_frames = 0;
   // groups > 1: this object only dispatches to `sub` (stream s -> sub[s / per_group], local index s % per_group); every
-  // group has its own context / CUDA stream and a host thread, so the latency-bound one-CTA-per-stream stages of one
-  // group overlap the other groups' work and the per-frame host work of one group hides behind the others' kernels
+  // group has its own context / CUDA stream; image_feed enqueues the frame of every group before it waits for the first, so
+  // the latency-bound one-CTA-per-stream stages of one group overlap the other groups' kernels and per-frame host work
   std::vector<flv_f2f_batch*> sub; int per_group = 0, stream_offset = 0;
-  struct Pool;
-  Pool* pool = nullptr;
+  // frame in flight between feed_begin and feed_end
+  struct { int* kf; int* rs; int prev0, cur0, cur1; std::chrono::steady_clock::time_point tp0, tp1, tp2; bool active; } pend{};
   flv_localmap_batch* lmap = nullptr;                      // keyframes go here (flv_f2f_batch_attach_localmap)
   std::vector<int> kf_streams, kf_counts; std::vector<int64_t> kf_frame, kf_ids; std::vector<double> kf_2d, kf_3d, kf_T;
   char err[512] = {0};
@@ -118,9 +119,11 @@ int alloc_device(flv_f2f_batch* b) {
   const size_t S = b->S, M = b->M, np = S * M;
   // L table first, contiguous, so one D2H copy brings the whole frame state back
   Carver c;
-  b->o_id = c.take(np * 8); b->o_plane = c.take(np * 16); b->o_und = c.take(np * 16); b->o_p3w = c.take(np * 24);
-  b->o_p3c = c.take(np * 24); b->o_f2d = c.take(np * 16); b->o_fpose = c.take(np * 56); b->o_has = c.take(np);
+  // what a keyframe message needs comes first (the lean read-back copies only that part)
+  b->o_id = c.take(np * 8); b->o_und = c.take(np * 16); b->o_p3w = c.take(np * 24); b->o_has = c.take(np);
   b->o_inl = c.take(np); b->o_n = c.take(S * 4); b->o_T = c.take(S * 56);
+  b->lean_bytes = c.off;
+  b->o_plane = c.take(np * 16); b->o_p3c = c.take(np * 24); b->o_f2d = c.take(np * 16); b->o_fpose = c.take(np * 56);
   b->tab_bytes = c.off;
   const size_t o_C = c.take(b->tab_bytes);
   const size_t MP = b->ctx->ba_max_poses, ML = b->ctx->ba_max_lms, ME = b->ctx->ba_max_edges;
@@ -248,65 +251,6 @@ int run_pnp_hooks(flv_f2f_batch* b) {
 
 }  // namespace
 
-// one persistent host thread per group; image_feed hands every thread its slice of the frame and waits for all of them
-struct flv_f2f_batch::Pool {
-  struct Job { const double* t; const uint8_t* img0; const void* img1; flv_memspace mem; int* kf; int* rs; };
-  std::vector<std::thread> th;
-  std::mutex mu;
-  std::condition_variable cv_go, cv_done;
-  unsigned long gen = 0;
-  int pending = 0;
-  bool stop = false;
-  Job job{};
-  std::vector<int> rc;
-  flv_f2f_batch* owner;
-  explicit Pool(flv_f2f_batch* o) : owner(o) {
-    rc.assign(o->sub.size(), 0);
-    for (size_t g = 0; g < o->sub.size(); ++g) th.emplace_back([this, g] { loop((int)g); });
-  }
-  ~Pool() {
-    { std::lock_guard<std::mutex> lk(mu); stop = true; ++gen; }
-    cv_go.notify_all();
-    for (std::thread& t : th) t.join();
-  }
-  void loop(int g) {
-    cudaSetDevice(owner->device);
-    unsigned long seen = 0;
-    for (;;) {
-      Job j;
-      {
-        std::unique_lock<std::mutex> lk(mu);
-        cv_go.wait(lk, [&] { return gen != seen; });
-        seen = gen;
-        if (stop) return;
-        j = job;
-      }
-      flv_f2f_batch* sb = owner->sub[g];
-      const size_t first = (size_t)g * owner->per_group, w = owner->cfg.img_w, h = owner->cfg.img_h;
-      const size_t px1 = owner->stereo ? 1 : 2;
-      rc[g] = flv_f2f_batch_image_feed(sb, j.t + first, j.img0 + first * w * h, (const uint8_t*)j.img1 + first * w * h * px1, j.mem,
-                                       j.kf ? j.kf + first : nullptr, j.rs ? j.rs + first : nullptr);
-      {
-        std::lock_guard<std::mutex> lk(mu);
-        --pending;
-      }
-      cv_done.notify_all();
-    }
-  }
-  int run(const Job& j) {
-    {
-      std::lock_guard<std::mutex> lk(mu);
-      job = j; pending = (int)th.size(); ++gen;
-    }
-    cv_go.notify_all();
-    std::unique_lock<std::mutex> lk(mu);
-    cv_done.wait(lk, [&] { return pending == 0; });
-    for (size_t g = 0; g < rc.size(); ++g)
-      if (rc[g]) { snprintf(owner->err, sizeof(owner->err), "group %d: %s", (int)g, owner->sub[g]->err); return rc[g]; }
-    return FLV_OK;
-  }
-};
-
 namespace {
 // dispatch helpers for grouped batches
 inline flv_f2f_batch* sub_of(flv_f2f_batch* b, int& stream) {
@@ -333,7 +277,6 @@ flv_f2f_batch* flv_f2f_batch_create_grouped(const flv_f2f_config* cfg, int n_str
     b->sub.push_back(sb);
     if (sb->err[0]) { snprintf(b->err, sizeof(b->err), "group %d: %s", g, sb->err); return b; }
   }
-  b->pool = new flv_f2f_batch::Pool(b);
   return b;
 }
 
@@ -367,8 +310,7 @@ flv_f2f_batch* flv_f2f_batch_create(const flv_f2f_config* cfg, int n_streams, in
 
 void flv_f2f_batch_destroy(flv_f2f_batch* b) {
   if (!b) return;
-  if (!b->sub.empty() || b->pool) {
-    delete b->pool;
+  if (!b->sub.empty()) {
     for (flv_f2f_batch* sb : b->sub) flv_f2f_batch_destroy(sb);
     delete b;
     return;
@@ -421,12 +363,13 @@ int flv_f2f_batch_imu_feed(flv_f2f_batch* b, int stream, double t, const double*
   return FLV_OK;
 }
 
-int flv_f2f_batch_image_feed(flv_f2f_batch* b, const double* t, const uint8_t* img0, const void* img1, flv_memspace mem,
-                             int* new_keyframe, int* reset_cmd) {
-  if (b && b->pool) {
-    if (!t || !img0 || !img1) return FLV_ERR_INVALID;
-    return b->pool->run(flv_f2f_batch::Pool::Job{t, img0, img1, mem, new_keyframe, reset_cmd});
-  }
+}  // extern "C"
+
+namespace {
+
+// first half of image_feed: host decisions + the whole frame enqueued on the group's stream (no wait)
+int feed_begin(flv_f2f_batch* b, const double* t, const uint8_t* img0, const void* img1, flv_memspace mem, int* new_keyframe,
+               int* reset_cmd) {
   if (!b || !b->ctx || !b->d_block || !t || !img0 || !img1) return FLV_ERR_INVALID;
   flv_ctx* ctx = b->ctx;
   const int S = b->S, M = b->M;
@@ -582,10 +525,27 @@ int flv_f2f_batch_image_feed(flv_f2f_batch* b, const double* t, const uint8_t* i
   B_RC(b, flv_trk_stage_finish(ctx, b->d, S));
   // ---- the frame's only synchronisation: summaries + the accepted frame's landmark lists ----------------------------------
   B_CUDA(b, cudaMemcpyAsync(b->h_out, q.out, (size_t)S * sizeof(TrkOut), cudaMemcpyDeviceToHost, cs));
-  B_CUDA(b, cudaMemcpyAsync(b->h_tab, b->d_tab, b->tab_bytes, cudaMemcpyDeviceToHost, cs));
+  B_CUDA(b, cudaMemcpyAsync(b->h_tab, b->d_tab, b->full_readback ? b->tab_bytes : b->lean_bytes, cudaMemcpyDeviceToHost, cs));
   while (mark_i <= flv_f2f_batch::NSTAGE) mark();
   B_CUDA(b, cudaEventRecord(b->ev_done, cs));
-  const auto tp2 = std::chrono::steady_clock::now();
+  b->pend.kf = new_keyframe; b->pend.rs = reset_cmd; b->pend.prev0 = prev0; b->pend.cur0 = cur0; b->pend.cur1 = cur1;
+  b->pend.tp0 = tp0; b->pend.tp1 = tp1; b->pend.tp2 = std::chrono::steady_clock::now(); b->pend.active = true;
+  return FLV_OK;
+}
+
+// second half: wait for the frame, per-stream state machines, keyframe hand-off, slot rotation
+int feed_end(flv_f2f_batch* b) {
+  if (!b || !b->pend.active) return FLV_ERR_INVALID;
+  b->pend.active = false;
+  flv_ctx* ctx = b->ctx;
+  const int S = b->S, M = b->M;
+  int* new_keyframe = b->pend.kf; int* reset_cmd = b->pend.rs;
+  (void)reset_cmd;
+  const int prev0 = b->pend.prev0, cur0 = b->pend.cur0, cur1 = b->pend.cur1;
+  const auto tp0 = b->pend.tp0, tp1 = b->pend.tp1, tp2 = b->pend.tp2;
+  cudaStream_t cs = ctx->stream;
+  const TrkBufs& q = b->d.b;
+  (void)q;
   B_CUDA(b, cudaEventSynchronize(b->ev_done));
   const auto tp3 = std::chrono::steady_clock::now();
   if (b->profile) {
@@ -684,6 +644,35 @@ int flv_f2f_batch_image_feed(flv_f2f_batch* b, const double* t, const uint8_t* i
   }
   b->slots[0] = cur0; b->slots[1] = prev0; b->slots[2] = cur1;
   return FLV_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int flv_f2f_batch_image_feed(flv_f2f_batch* b, const double* t, const uint8_t* img0, const void* img1, flv_memspace mem,
+                             int* new_keyframe, int* reset_cmd) {
+  if (!b || !t || !img0 || !img1) return FLV_ERR_INVALID;
+  if (b->sub.empty()) {
+    const int rc = feed_begin(b, t, img0, img1, mem, new_keyframe, reset_cmd);
+    return rc ? rc : feed_end(b);
+  }
+  // grouped: every group's frame is in flight before the first wait
+  const size_t w = b->cfg.img_w, h = b->cfg.img_h, px1 = b->stereo ? 1 : 2;
+  int rc = FLV_OK;
+  size_t started = 0;
+  for (size_t g = 0; g < b->sub.size() && !rc; ++g) {
+    const size_t first = g * (size_t)b->per_group;
+    rc = feed_begin(b->sub[g], t + first, img0 + first * w * h, (const uint8_t*)img1 + first * w * h * px1, mem,
+                    new_keyframe ? new_keyframe + first : nullptr, reset_cmd ? reset_cmd + first : nullptr);
+    if (rc) snprintf(b->err, sizeof(b->err), "group %d: %s", (int)g, b->sub[g]->err);
+    else ++started;
+  }
+  for (size_t g = 0; g < started; ++g) {
+    const int rc2 = feed_end(b->sub[g]);
+    if (rc2 && !rc) { rc = rc2; snprintf(b->err, sizeof(b->err), "group %d: %s", (int)g, b->sub[g]->err); }
+  }
+  return rc;
 }
 
 int flv_f2f_batch_state(flv_f2f_batch* b, int stream) {
@@ -794,6 +783,12 @@ int flv_f2f_batch_get_host_profile(flv_f2f_batch* b, double* host_ms4) {
 long long flv_f2f_batch_launch_count(flv_f2f_batch* b) {
   if (b && !b->sub.empty()) { long long n = 0; for (flv_f2f_batch* sb : b->sub) n += flv_f2f_batch_launch_count(sb); return n; }
   return b && b->ctx ? flv_launch_count(b->ctx) : 0;
+}
+int flv_f2f_batch_set_readback(flv_f2f_batch* b, int full) {
+  if (!b) return FLV_ERR_INVALID;
+  b->full_readback = full != 0;
+  for (flv_f2f_batch* sb : b->sub) sb->full_readback = full != 0;
+  return FLV_OK;
 }
 int flv_f2f_batch_attach_localmap(flv_f2f_batch* b, flv_localmap_batch* lm) {
   if (!b) return FLV_ERR_INVALID;

@@ -166,6 +166,11 @@ int flv_f2f_batch_get_host_profile(flv_f2f_batch* b, double* host_ms4);
 /* Hand every new keyframe (KeyFrame message content: ids / undistorted pixels / world points of the inlier landmarks with
  * depth + T_c_w, keyframe_msg.cpp:30-110) to `lm` from inside image_feed; NULL detaches.  The local map never blocks tracking. */
 int flv_f2f_batch_attach_localmap(flv_f2f_batch* b, flv_localmap_batch* lm);
+/* What image_feed copies back per frame besides the per-stream summaries: full = 1 (default) the complete landmark lists
+ * (everything the get_frame / get_frame_ex accessors return), full = 0 only what a KeyFrame message and the pose consumers
+ * need (ids, undistorted pixels, world points, flags, counts, poses: 50 instead of 162 bytes per landmark slot); with
+ * full = 0 get_frame's plane_xy and get_frame_ex's outputs are not refreshed. */
+int flv_f2f_batch_set_readback(flv_f2f_batch* b, int full);
 
 #ifdef __cplusplus
 }
