@@ -41,11 +41,14 @@ def _bind(lib):
     lib.flv_f2f_batch_imu_feed_many.argtypes = [vp, C.c_int, vp, vp, vp, vp]
     lib.flv_f2f_batch_image_feed.argtypes = [vp, vp, vp, vp, C.c_int, vp, vp]
     lib.flv_f2f_batch_state.argtypes = [vp, C.c_int]
+    lib.flv_f2f_batch_frame_async.argtypes = [vp, vp, vp, vp, C.c_int, C.c_int, vp, vp, vp, vp]
+    lib.flv_f2f_batch_sync.argtypes = [vp, vp, vp]
     lib.flv_f2f_batch_get_frame.argtypes = [vp, C.c_int] + [vp] * 7 + [C.c_int]
     lib.flv_f2f_batch_launch_count.restype = C.c_longlong
     lib.flv_f2f_batch_launch_count.argtypes = [vp]
     lib.flv_f2f_batch_attach_localmap.argtypes = [vp, vp]
     lib.flv_f2f_batch_set_readback.argtypes = [vp, C.c_int]
+    lib.flv_f2f_batch_set_result_log.argtypes = [vp, vp, C.c_int]
     lib.flv_f2f_batch_set_profile.argtypes = [vp, C.c_int]
     lib.flv_f2f_batch_get_profile.argtypes = [vp, vp, vp]
     lib.flv_f2f_batch_get_host_profile.argtypes = [vp, vp]
@@ -117,6 +120,9 @@ class BatchTracker:
     def set_readback(self, full):
         self._chk(self.lib.flv_f2f_batch_set_readback(self.h, 1 if full else 0))
 
+    def set_result_log(self, ptr, block_frames):
+        self._chk(self.lib.flv_f2f_batch_set_result_log(self.h, C.c_void_p(ptr) if ptr else None, block_frames))
+
     def attach_localmap(self, lm):
         self._chk(self.lib.flv_f2f_batch_attach_localmap(self.h, lm.h if lm else None))
 
@@ -129,6 +135,20 @@ class BatchTracker:
         """t: float64[S]; img pointers: raw addresses of S images back to back (host or device memory)."""
         self._chk(self.lib.flv_f2f_batch_image_feed(self.h, _p(t), C.c_void_p(img0_ptr), C.c_void_p(img1_ptr), 1 if device_mem else 0,
                                                     _p(self.kf), _p(self.rs)))
+        return self.kf, self.rs
+
+    def frame_async(self, t, img0_ptr, img1_ptr, device_mem, imu=None):
+        """Pipelined frame: imu = (streams int32[n], t float64[n], acc float64[n,3], gyro float64[n,3]) or None."""
+        if imu is None or len(imu[0]) == 0:
+            self._chk(self.lib.flv_f2f_batch_frame_async(self.h, _p(t), C.c_void_p(img0_ptr), C.c_void_p(img1_ptr), 1 if device_mem else 0,
+                                                         0, None, None, None, None))
+        else:
+            st, ti, acc, gyro = imu
+            self._chk(self.lib.flv_f2f_batch_frame_async(self.h, _p(t), C.c_void_p(img0_ptr), C.c_void_p(img1_ptr), 1 if device_mem else 0,
+                                                         len(st), _p(st), _p(ti), _p(acc), _p(gyro)))
+
+    def sync(self):
+        self._chk(self.lib.flv_f2f_batch_sync(self.h, _p(self.kf), _p(self.rs)))
         return self.kf, self.rs
 
     def state(self, s):

@@ -74,6 +74,9 @@ struct flv_f2f_batch {
   void* d_tab = nullptr;                                   // the L table block on the device (contiguous, same offsets)
   int slots[3] = {0, 1, 2};                                // prev0, cur0, cur1
   flv_f2f_fmat_fn fmat_fn = nullptr; flv_f2f_pnp_fn pnp_fn = nullptr; void* hook_user = nullptr;
+  // optional per-frame result log for the multi-GPU gather: rlog[frame % rlog_K][stream_offset + s][8] = pose7 + landmark count
+  double* rlog = nullptr; int rlog_K = 0, S_total = 0; long long rlog_frame = 0;
+  std::vector<int> async_kf, async_rs;                     // flags of the frame started by flv_f2f_batch_frame_async
   std::vector<char> have_last;                             // stream has an accepted "last" frame on the device
   cudaEvent_t ev_done = nullptr;
   // the right image (ingest + pyramid) is only needed by the left->right LK late in the frame: it is prepared on a side
@@ -299,6 +302,7 @@ flv_f2f_batch* flv_f2f_batch_create(const flv_f2f_config* cfg, int n_streams, in
   b->dprm.iir_ratio = (float)cfg->dc_para[0]; b->dprm.range = (float)cfg->dc_para[1]; b->dprm.dummy_depth = !(cfg->dc_para[2] < 0.5) ? 1 : 0;
   b->st.resize(n_streams);
   b->have_last.assign(n_streams, 0);
+  b->async_kf.assign(n_streams, 0); b->async_rs.assign(n_streams, 0);
   for (StreamState& s : b->st) {
     s.vim.reset(new flv::VIMOTION(from7(cfg->T_i_c0), 9.81, cfg->vi_para[0], cfg->vi_para[1], cfg->vi_para[2], cfg->vi_para[3]));
     s.skip_n_imgs = cfg->skip_first_n_imgs;
@@ -623,6 +627,11 @@ int feed_end(flv_f2f_batch* b) {
       b->kf_T.insert(b->kf_T.end(), T7, T7 + 7);
       b->kf_streams.push_back(b->stream_offset + s); b->kf_counts.push_back(cnt); b->kf_frame.push_back(z.frameCount);
     }
+    if (b->rlog) {
+      double* row = b->rlog + ((size_t)(b->rlog_frame % b->rlog_K) * b->S_total + b->stream_offset + s) * 8;
+      to7(z.cur_T, row);
+      row[7] = z.n_lm;
+    }
     if (accepted) b->have_last[s] = 1;
     else if (b->have_last[s]) {
       // the stream keeps its old "last" frame: its image must survive the slot rotation below
@@ -636,6 +645,7 @@ int feed_end(flv_f2f_batch* b) {
                                              b->kf_ids.data(), b->kf_2d.data(), b->kf_3d.data(), b->kf_T.data());
     if (rc) { snprintf(b->err, sizeof(b->err), "flv_localmap_batch_submit: %s", flv_localmap_batch_last_error(b->lmap)); return rc; }
   }
+  if (b->rlog) b->rlog_frame++;
   if (any_restore) ctx->deriv_streams[cur0] = 0;          // derivative pyramid of that slot: rebuild on next use
   if (b->profile) {
     const auto tp4 = std::chrono::steady_clock::now();
@@ -650,9 +660,59 @@ int feed_end(flv_f2f_batch* b) {
 
 extern "C" {
 
+// Pipelined form of imu_feed_many + image_feed for grouped batches: for every group in turn, finish the group's previous frame
+// (wait, state machines, keyframe hand-off), feed the group's IMU samples, enqueue its new frame -- so while the host works
+// on one group the other groups' frames are running on the GPU.  Per stream the order of operations is exactly that of the
+// synchronous calls (previous frame finished -> IMU samples -> new frame); only the results become visible one call later
+// (flv_f2f_batch_sync finishes the frames in flight).
+int flv_f2f_batch_frame_async(flv_f2f_batch* b, const double* t, const uint8_t* img0, const void* img1, flv_memspace mem, int n_imu,
+                              const int* imu_streams, const double* imu_t, const double* imu_acc, const double* imu_gyro) {
+  if (!b || !t || !img0 || !img1 || n_imu < 0 || (n_imu > 0 && (!imu_streams || !imu_t || !imu_acc || !imu_gyro))) return FLV_ERR_INVALID;
+  const size_t w = b->cfg.img_w, h = b->cfg.img_h, px1 = b->stereo ? 1 : 2;
+  const size_t G = b->sub.empty() ? 1 : b->sub.size();
+  for (size_t g = 0; g < G; ++g) {
+    flv_f2f_batch* sb = b->sub.empty() ? b : b->sub[g];
+    const int first = b->sub.empty() ? 0 : (int)g * b->per_group, last = first + sb->S;
+    if (sb->pend.active) {
+      const int rc = feed_end(sb);
+      if (rc) { if (sb != b) snprintf(b->err, sizeof(b->err), "group %d: %s", (int)g, sb->err); return rc; }
+    }
+    for (int i = 0; i < n_imu; ++i) {
+      const int s = imu_streams[i];
+      if (s < first || s >= last) continue;
+      const int rc = flv_f2f_batch_imu_feed(sb, s - first, imu_t[i], imu_acc + 3 * (size_t)i, imu_gyro + 3 * (size_t)i);
+      if (rc) return rc;
+    }
+    const int rc = feed_begin(sb, t + first, img0 + (size_t)first * w * h, (const uint8_t*)img1 + (size_t)first * w * h * px1, mem,
+                              sb->async_kf.data(), sb->async_rs.data());
+    if (rc) { if (sb != b) snprintf(b->err, sizeof(b->err), "group %d: %s", (int)g, sb->err); return rc; }
+  }
+  return FLV_OK;
+}
+
+// finish every frame in flight; new_keyframe / reset_cmd (may be NULL) receive the flags of the last frame of every stream
+int flv_f2f_batch_sync(flv_f2f_batch* b, int* new_keyframe, int* reset_cmd) {
+  if (!b) return FLV_ERR_INVALID;
+  const size_t G = b->sub.empty() ? 1 : b->sub.size();
+  for (size_t g = 0; g < G; ++g) {
+    flv_f2f_batch* sb = b->sub.empty() ? b : b->sub[g];
+    const int first = b->sub.empty() ? 0 : (int)g * b->per_group;
+    if (sb->pend.active) {
+      const int rc = feed_end(sb);
+      if (rc) { if (sb != b) snprintf(b->err, sizeof(b->err), "group %d: %s", (int)g, sb->err); return rc; }
+    }
+    for (int s = 0; s < sb->S; ++s) {
+      if (new_keyframe) new_keyframe[first + s] = sb->async_kf[s];
+      if (reset_cmd) reset_cmd[first + s] = sb->async_rs[s];
+    }
+  }
+  return FLV_OK;
+}
+
 int flv_f2f_batch_image_feed(flv_f2f_batch* b, const double* t, const uint8_t* img0, const void* img1, flv_memspace mem,
                              int* new_keyframe, int* reset_cmd) {
   if (!b || !t || !img0 || !img1) return FLV_ERR_INVALID;
+  if (int rc0 = flv_f2f_batch_sync(b, nullptr, nullptr)) return rc0;      // a frame started by frame_async finishes first
   if (b->sub.empty()) {
     const int rc = feed_begin(b, t, img0, img1, mem, new_keyframe, reset_cmd);
     return rc ? rc : feed_end(b);
@@ -783,6 +843,12 @@ int flv_f2f_batch_get_host_profile(flv_f2f_batch* b, double* host_ms4) {
 long long flv_f2f_batch_launch_count(flv_f2f_batch* b) {
   if (b && !b->sub.empty()) { long long n = 0; for (flv_f2f_batch* sb : b->sub) n += flv_f2f_batch_launch_count(sb); return n; }
   return b && b->ctx ? flv_launch_count(b->ctx) : 0;
+}
+int flv_f2f_batch_set_result_log(flv_f2f_batch* b, double* buf, int block_frames) {
+  if (!b || (buf && block_frames < 1)) return FLV_ERR_INVALID;
+  b->rlog = buf; b->rlog_K = block_frames; b->S_total = b->S; b->rlog_frame = 0;
+  for (flv_f2f_batch* sb : b->sub) { sb->rlog = buf; sb->rlog_K = block_frames; sb->S_total = b->S; sb->rlog_frame = 0; }
+  return FLV_OK;
 }
 int flv_f2f_batch_set_readback(flv_f2f_batch* b, int full) {
   if (!b) return FLV_ERR_INVALID;

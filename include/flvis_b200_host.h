@@ -144,6 +144,14 @@ void flv_f2f_batch_set_ransac_hooks(flv_f2f_batch* b, flv_f2f_fmat_fn fmat, flv_
 int flv_f2f_batch_imu_feed(flv_f2f_batch* b, int stream, double t, const double* acc, const double* gyro);
 int flv_f2f_batch_image_feed(flv_f2f_batch* b, const double* t, const uint8_t* img0, const void* img1, flv_memspace mem,
                              int* new_keyframe, int* reset_cmd);
+/* Pipelined form of imu_feed_many + image_feed (worth it for grouped batches): for every group in turn the previous frame is
+ * finished, the group's IMU samples of this call are fed, and its new frame is enqueued, so the GPU works on the other
+ * groups while the host serves one.  Per stream the order of operations is that of the synchronous calls; results
+ * (accessors, keyframe hand-off to an attached local map) lag by one call.  flv_f2f_batch_sync finishes the frames in
+ * flight and returns the flags of every stream's last frame; the synchronous image_feed syncs first. */
+int flv_f2f_batch_frame_async(flv_f2f_batch* b, const double* t, const uint8_t* img0, const void* img1, flv_memspace mem, int n_imu,
+                              const int* imu_streams, const double* imu_t, const double* imu_acc, const double* imu_gyro);
+int flv_f2f_batch_sync(flv_f2f_batch* b, int* new_keyframe, int* reset_cmd);
 int flv_f2f_batch_state(flv_f2f_batch* b, int stream);
 int flv_f2f_batch_get_frame(flv_f2f_batch* b, int stream, double* T_c_w, int64_t* lm_id, double* plane_xy, double* undist_xy,
                             double* p3d_w, uint8_t* has_3d, uint8_t* is_inlier, int cap);
@@ -171,6 +179,10 @@ int flv_f2f_batch_attach_localmap(flv_f2f_batch* b, flv_localmap_batch* lm);
  * need (ids, undistorted pixels, world points, flags, counts, poses: 50 instead of 162 bytes per landmark slot); with
  * full = 0 get_frame's plane_xy and get_frame_ex's outputs are not refreshed. */
 int flv_f2f_batch_set_readback(flv_f2f_batch* b, int full);
+/* Per-frame result records for a gather across GPUs: after every finished frame, buf[frame % block_frames][stream][8] =
+ * {T_c_w as qx qy qz qw tx ty tz, landmark count} (host memory, e.g. the pinned staging block of the collective);
+ * buf = NULL stops logging; the frame counter restarts at 0 with every call. */
+int flv_f2f_batch_set_result_log(flv_f2f_batch* b, double* buf, int block_frames);
 
 #ifdef __cplusplus
 }

@@ -26,11 +26,12 @@ G = 9.81
 class Trajectory:
     """p(t), rpy(t) as sums of sinusoids that start from rest after `t_rest` seconds (smooth ramp)."""
 
-    def __init__(self, pos_amp, pos_w, rpy_amp, rpy_w, t_rest=0.6, vel=(0.0, 0.0, 0.0)):
+    def __init__(self, pos_amp, pos_w, rpy_amp, rpy_w, t_rest=0.6, vel=(0.0, 0.0, 0.0), phase=0.0):
         self.pa, self.pw = np.array(pos_amp, float), np.array(pos_w, float)
         self.ra, self.rw = np.array(rpy_amp, float), np.array(rpy_w, float)
         self.t_rest = t_rest
         self.vel = np.array(vel, float)
+        self.phase = float(phase)            # phase of the sinusoids (the pose at s = 0 stays the identity)
 
     def _s(self, t):
         """motion clock: 0 before t_rest, then a C2 ramp into s = t - t_rest - 0.5."""
@@ -44,14 +45,15 @@ class Trajectory:
     def eval(self, t):
         """-> p, v, a (world), rpy, rpy', (ignored rpy'') at time t."""
         s, sd, sdd = self._s(t)
-        sin_p, cos_p = np.sin(self.pw * s), np.cos(self.pw * s)
-        p = self.pa * (1 - cos_p) + self.vel * s
+        ph = self.phase
+        sin_p, cos_p = np.sin(self.pw * s + ph), np.cos(self.pw * s + ph)
+        p = self.pa * (math.cos(ph) - cos_p) + self.vel * s
         dp = self.pa * self.pw * sin_p + self.vel
         ddp = self.pa * self.pw ** 2 * cos_p
         v = dp * sd
         a = ddp * sd * sd + dp * sdd
-        sin_r, cos_r = np.sin(self.rw * s), np.cos(self.rw * s)
-        rpy = self.ra * sin_r
+        sin_r, cos_r = np.sin(self.rw * s + ph), np.cos(self.rw * s + ph)
+        rpy = self.ra * (sin_r - math.sin(ph))
         drpy = self.ra * self.rw * cos_r * sd
         return p, v, a, rpy, drpy
 
@@ -259,6 +261,7 @@ def make_bench(workload, stream_id, period_frames=40, render=True):
     seed = 7000 + stream_id
     rng = np.random.default_rng(seed)
     jitter = 1.0 + 0.15 * (rng.uniform(size=6) - 0.5)
+    phase = 2 * math.pi * float(rng.uniform())     # cameras are not synchronised: keyframes of different streams fall on different frames
     if workload == "euroc":
         c = EUROC; hz = c["img_hz"]
     elif workload == "d435":
@@ -273,7 +276,7 @@ def make_bench(workload, stream_id, period_frames=40, render=True):
         X0 = 3.0; ppm = c["K0"][0] / X0
         canvas = synth.texture(seed, int(5.0 * ppm), int(7.0 * ppm), blur=2) if render else np.zeros((8, 8), np.uint8)
         traj = Trajectory(pos_amp=(0.02 * jitter[0], 0.06 * jitter[1], 0.04 * jitter[2]), pos_w=(w0, w0, 2 * w0),
-                          rpy_amp=(0.03 * jitter[3], 0.02 * jitter[4], 0.04 * jitter[5]), rpy_w=(w0, 2 * w0, w0), t_rest=t_rest)
+                          rpy_amp=(0.03 * jitter[3], 0.02 * jitter[4], 0.04 * jitter[5]), rpy_w=(w0, 2 * w0, w0), t_rest=t_rest, phase=phase)
         T_i_c0, T_c0_c1 = euroc_rig()
         r0 = PlaneRenderer(canvas, X0, ppm, c["w"], c["h"], c["K0"], c["D0"]) if render else None
         r1 = PlaneRenderer(canvas, X0, ppm, c["w"], c["h"], c["K1"], c["D1"]) if render else None
@@ -282,7 +285,7 @@ def make_bench(workload, stream_id, period_frames=40, render=True):
         X0 = 3.0; ppm = c["K0"][0] / X0
         canvas = synth.texture(seed, int(4.6 * ppm), int(6.2 * ppm), blur=2) if render else np.zeros((8, 8), np.uint8)
         traj = Trajectory(pos_amp=(0.02 * jitter[0], 0.05 * jitter[1], 0.035 * jitter[2]), pos_w=(w0, w0, 2 * w0),
-                          rpy_amp=(0.03 * jitter[3], 0.02 * jitter[4], 0.04 * jitter[5]), rpy_w=(w0, 2 * w0, w0), t_rest=t_rest)
+                          rpy_amp=(0.03 * jitter[3], 0.02 * jitter[4], 0.04 * jitter[5]), rpy_w=(w0, 2 * w0, w0), t_rest=t_rest, phase=phase)
         c = dict(c, skip=0)
         r0 = PlaneRenderer(canvas, X0, ppm, c["w"], c["h"], c["K0"]) if render else None
         seq = Sequence("c0", "depth", n_startup + period_frames, hz, traj, _mat44_to_se3(c["T_imu_cam0"]), r0, depth_factor=c["depth_factor"], seed=seed)
@@ -290,7 +293,7 @@ def make_bench(workload, stream_id, period_frames=40, render=True):
         X0 = 12.0; ppm = c["K0"][0] / X0
         canvas = synth.texture_multiscale(seed, int(9.0 * ppm), int(26.0 * ppm)) if render else np.zeros((8, 8), np.uint8)
         traj = Trajectory(pos_amp=(0.3 * jitter[0], 1.2 * jitter[1], 0.2 * jitter[2]), pos_w=(w0, w0, 2 * w0),
-                          rpy_amp=(0.0, 0.004, 0.01), rpy_w=(w0, w0, w0), t_rest=0.0)
+                          rpy_amp=(0.0, 0.004, 0.01), rpy_w=(w0, w0, w0), t_rest=0.0, phase=phase)
         n_startup = int(math.ceil(1.0 * hz)) + 1
         b = c["bf"] / c["K0"][0]
         r0 = PlaneRenderer(canvas, X0, ppm, c["w"], c["h"], c["K0"]) if render else None
