@@ -1,4 +1,4 @@
-// flv_localmap_batch -- the local-map thread for S sequences (LocalMapNodeletClass, src/backend/vo_localmap.cpp:87-380).
+// flv_localmap_batch -- the local-map threads for S sequences (LocalMapNodeletClass, src/backend/vo_localmap.cpp:87-380).
 //
 // FLVIS runs the sliding-window BA in its own nodelet thread: keyframes arrive through a queue (depth 10,
 // vo_localmap.cpp:464-467) and never block tracking.  Here ONE worker thread serves all S sequences: the tracker thread
@@ -78,7 +78,7 @@ class Helpers {
 };
 }
 
-struct flv_localmap_batch {
+struct LmShard {
   int device = 0, S = 0, W = 0;
   double K[4] = {0, 0, 0, 0};
   flv_ctx* ctx = nullptr;                       // created and used by the worker thread only
@@ -101,7 +101,7 @@ struct flv_localmap_batch {
   bool process(std::vector<KfMsg>& batch);
 };
 
-bool flv_localmap_batch::process(std::vector<KfMsg>& batch) {
+bool LmShard::process(std::vector<KfMsg>& batch) {
   // a sequence may contribute several keyframes to one submission only if the caller batches frames; solve in rounds so
   // that every LocalMap sees begin -> solve -> end in order
   size_t done = 0;
@@ -180,7 +180,7 @@ bool flv_localmap_batch::process(std::vector<KfMsg>& batch) {
   return true;
 }
 
-void flv_localmap_batch::run() {
+void LmShard::run() {
   // the context belongs to this thread: flv_create selects the device for the thread
   const int rc = flv_create(&ctx, device, S, 64, 64, 64);
   {
@@ -216,44 +216,79 @@ void flv_localmap_batch::run() {
   if (ctx) { flv_destroy(ctx); ctx = nullptr; }
 }
 
+// The public object: `n_shards` independent shards (stream s -> shard s % n_shards, local index s / n_shards), each with its
+// own worker thread, kernel context and CUDA stream, so several solver launches are in flight at once and the graph editing
+// of one shard overlaps the solve of another.
+struct flv_localmap_batch {
+  int S = 0;
+  std::vector<std::unique_ptr<LmShard>> shards;
+  char err[256] = {0};
+};
+
+namespace {
+LmShard* make_shard(int device, int n_streams, int window_size, const double* K) {
+  LmShard* b = new (std::nothrow) LmShard();
+  if (!b) return nullptr;
+  b->device = device; b->S = n_streams; b->W = window_size;
+  for (int k = 0; k < 4; ++k) b->K[k] = K[k];
+  b->latest.resize(n_streams); b->n_results.assign(n_streams, 0);
+  for (int s = 0; s < n_streams; ++s) b->maps.emplace_back(new flv::LocalMap(nullptr, window_size, K[0], K[1], K[2], K[3]));
+  const unsigned hw = std::thread::hardware_concurrency();
+  b->helpers.reset(new Helpers(n_streams > 1 ? (int)std::min<unsigned>(3, hw > 8 ? hw / 8 : 1) : 0));
+  b->worker = std::thread([b] { b->run(); });
+  std::unique_lock<std::mutex> lk(b->mu);
+  b->cv_idle.wait(lk, [&] { return b->started; });
+  return b;
+}
+void destroy_shard(LmShard* b) {
+  { std::lock_guard<std::mutex> lk(b->mu); b->stop = true; }
+  b->cv_work.notify_all();
+  if (b->worker.joinable()) b->worker.join();
+}
+}  // namespace
+
 extern "C" {
 
 flv_localmap_batch* flv_localmap_batch_create(int device, int n_streams, int window_size, double fx, double fy, double cx, double cy) {
   if (n_streams < 1 || window_size < 3 || window_size > 25) return nullptr;
   flv_localmap_batch* b = new (std::nothrow) flv_localmap_batch();
   if (!b) return nullptr;
-  b->device = device; b->S = n_streams; b->W = window_size;
-  b->K[0] = fx; b->K[1] = fy; b->K[2] = cx; b->K[3] = cy;
-  b->latest.resize(n_streams); b->n_results.assign(n_streams, 0);
-  for (int s = 0; s < n_streams; ++s) b->maps.emplace_back(new flv::LocalMap(nullptr, window_size, fx, fy, cx, cy));
-  const unsigned hw = std::thread::hardware_concurrency();
-  b->helpers.reset(new Helpers(n_streams > 1 ? (int)std::min<unsigned>(6, hw > 4 ? hw / 4 : 1) : 0));
-  b->worker = std::thread([b] { b->run(); });
-  std::unique_lock<std::mutex> lk(b->mu);
-  b->cv_idle.wait(lk, [&] { return b->started; });
+  b->S = n_streams;
+  const double K[4] = {fx, fy, cx, cy};
+  const int n_shards = n_streams >= 16 ? 4 : (n_streams >= 4 ? 2 : 1);
+  for (int i = 0; i < n_shards; ++i) {
+    const int n_local = (n_streams - i + n_shards - 1) / n_shards;
+    LmShard* sh = make_shard(device, n_local, window_size, K);
+    if (!sh) { flv_localmap_batch_destroy(b); return nullptr; }
+    b->shards.emplace_back(sh);
+  }
   return b;
 }
 
 void flv_localmap_batch_destroy(flv_localmap_batch* b) {
   if (!b) return;
-  { std::lock_guard<std::mutex> lk(b->mu); b->stop = true; }
-  b->cv_work.notify_all();
-  if (b->worker.joinable()) b->worker.join();
+  for (auto& sh : b->shards) destroy_shard(sh.get());
   delete b;
 }
 
-const char* flv_localmap_batch_last_error(flv_localmap_batch* b) { return b ? b->err : "null"; }
+const char* flv_localmap_batch_last_error(flv_localmap_batch* b) {
+  if (!b) return "null";
+  for (auto& sh : b->shards) if (sh->err[0]) return sh->err;
+  return b->err;
+}
 
 int flv_localmap_batch_submit(flv_localmap_batch* b, int n_kf, const int* streams, const int64_t* frame_ids, const int* lm_counts,
                               const int64_t* lm_id, const double* lm_2d, const double* lm_3d, const double* T_c_w) {
   if (!b || n_kf < 0 || (n_kf > 0 && (!streams || !frame_ids || !lm_counts || !lm_id || !lm_2d || !lm_3d || !T_c_w))) return FLV_ERR_INVALID;
   if (n_kf == 0) return FLV_OK;
-  std::vector<KfMsg> batch(n_kf);
+  const int W = (int)b->shards.size();
+  std::vector<std::vector<KfMsg>> per(W);
   size_t off = 0;
   for (int i = 0; i < n_kf; ++i) {
     if (streams[i] < 0 || streams[i] >= b->S || lm_counts[i] < 0) return FLV_ERR_INVALID;
-    KfMsg& m = batch[i];
-    m.stream = streams[i];
+    per[streams[i] % W].emplace_back();
+    KfMsg& m = per[streams[i] % W].back();
+    m.stream = streams[i] / W;
     m.kf.frame_id = frame_ids[i]; m.kf.lm_count = lm_counts[i];
     m.kf.lm_id.assign(lm_id + off, lm_id + off + lm_counts[i]);
     m.kf.lm_2d.resize(lm_counts[i]); m.kf.lm_3d.resize(lm_counts[i]);
@@ -264,30 +299,43 @@ int flv_localmap_batch_submit(flv_localmap_batch* b, int n_kf, const int* stream
     for (int k = 0; k < 7; ++k) m.kf.T_c_w[k] = T_c_w[7 * i + k];
     off += lm_counts[i];
   }
-  {
-    std::lock_guard<std::mutex> lk(b->mu);
-    if (b->failed) return FLV_ERR_CUDA;
-    b->queue.push_back(std::move(batch));
+  for (int w = 0; w < W; ++w) {
+    if (per[w].empty()) continue;
+    LmShard* sh = b->shards[w].get();
+    {
+      std::lock_guard<std::mutex> lk(sh->mu);
+      if (sh->failed) return FLV_ERR_CUDA;
+      sh->queue.push_back(std::move(per[w]));
+    }
+    sh->cv_work.notify_one();
   }
-  b->cv_work.notify_one();
   return FLV_OK;
 }
 
 int flv_localmap_batch_wait(flv_localmap_batch* b) {
   if (!b) return FLV_ERR_INVALID;
-  std::unique_lock<std::mutex> lk(b->mu);
-  b->cv_idle.wait(lk, [&] { return (b->queue.empty() && !b->busy) || b->failed; });
-  return b->failed ? FLV_ERR_CUDA : FLV_OK;
+  int rc = FLV_OK;
+  for (auto& shp : b->shards) {
+    LmShard* sh = shp.get();
+    std::unique_lock<std::mutex> lk(sh->mu);
+    sh->cv_idle.wait(lk, [&] { return (sh->queue.empty() && !sh->busy) || sh->failed; });
+    if (sh->failed) rc = FLV_ERR_CUDA;
+  }
+  return rc;
 }
 
 int flv_localmap_batch_stats(flv_localmap_batch* b, long long* n_keyframes, long long* n_solves, long long* n_launches, double* solve_ms) {
-  if (b && solve_ms) solve_ms[1] = b->host_ms;        // solve_ms is double[2]: {solver calls, graph editing + packing}
   if (!b) return FLV_ERR_INVALID;
-  std::lock_guard<std::mutex> lk(b->mu);
-  if (n_keyframes) *n_keyframes = b->n_keyframes;
-  if (n_solves) *n_solves = b->n_solves;
-  if (n_launches) *n_launches = b->n_launches;
-  if (solve_ms) *solve_ms = b->solve_ms;
+  long long nk = 0, ns = 0, nl = 0; double ms = 0, hms = 0;
+  for (auto& shp : b->shards) {
+    LmShard* sh = shp.get();
+    std::lock_guard<std::mutex> lk(sh->mu);
+    nk += sh->n_keyframes; ns += sh->n_solves; nl += sh->n_launches; ms += sh->solve_ms; hms += sh->host_ms;
+  }
+  if (n_keyframes) *n_keyframes = nk;
+  if (n_solves) *n_solves = ns;
+  if (n_launches) *n_launches = nl;
+  if (solve_ms) { solve_ms[0] = ms; solve_ms[1] = hms; }   // solve_ms is double[2]: {solver calls, graph editing + packing}, summed over shards
   return FLV_OK;
 }
 
@@ -295,9 +343,12 @@ int flv_localmap_batch_result(flv_localmap_batch* b, int stream, int64_t* out_fr
                               int64_t* out_lm_id, double* out_lm_3d, int lm_cap, int* out_outlier_count, int64_t* out_outlier_id,
                               int outlier_cap) {
   if (!b || stream < 0 || stream >= b->S) return FLV_ERR_INVALID;
-  std::lock_guard<std::mutex> lk(b->mu);
-  if (b->n_results[stream] == 0) return 0;
-  const flv::CorrectionInfStruct& c = b->latest[stream];
+  const int W = (int)b->shards.size();
+  LmShard* sh = b->shards[stream % W].get();
+  const int ls = stream / W;
+  std::lock_guard<std::mutex> lk(sh->mu);
+  if (sh->n_results[ls] == 0) return 0;
+  const flv::CorrectionInfStruct& c = sh->latest[ls];
   if ((int)c.lm_id.size() > lm_cap || (int)c.lm_outlier_id.size() > outlier_cap) return FLV_ERR_OVERFLOW;
   if (out_frame_id) *out_frame_id = c.frame_id;
   if (out_T_c_w) for (int k = 0; k < 7; ++k) out_T_c_w[k] = c.T_c_w[k];
@@ -308,7 +359,7 @@ int flv_localmap_batch_result(flv_localmap_batch* b, int stream, int64_t* out_fr
   }
   if (out_outlier_count) *out_outlier_count = c.lm_outlier_count;
   if (out_outlier_id) for (size_t i = 0; i < c.lm_outlier_id.size(); ++i) out_outlier_id[i] = c.lm_outlier_id[i];
-  return (int)b->n_results[stream];
+  return (int)sh->n_results[ls];
 }
 
 }  // extern "C"
