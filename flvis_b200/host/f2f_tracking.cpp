@@ -160,7 +160,8 @@ int F2FTracking::image_feed(double time, const uint8_t* img0, const void* img1, 
       break;
     }
     case Tracking: {
-      // STEP1 (local-map feedback) is dead code in the reference: correction_feed is never called (vo_tracking.cpp:373-385)
+      // STEP1: local-map feedback (:189-219); only ever set through correction_feed, which the reference's nodelet never calls
+      if (has_localmap_feedback) apply_localmap_feedback();
       SE3 imu_guess; bool has_imu_guess = false;
       if (has_imu) has_imu_guess = vimotion->viGetCorrFrameState(time, imu_guess);
       const bool tracking_success = tracking(*last_frame, *curr_frame, imu_guess, has_imu_guess);
@@ -220,6 +221,38 @@ int F2FTracking::image_feed(double time, const uint8_t* img0, const void* img1, 
     }
   }
   return FLV_OK;
+}
+
+void F2FTracking::apply_localmap_feedback() {                       // f2f_tracking.cpp:189-219
+  const int corr_id = (int)correction_inf.frame_id;                  // `int corr_id = correction_inf.frame_id` (kept)
+  int old_pose_idx = 0;
+  for (int i = (int)pose_records.size() - 1; i >= 0; i--)
+    if (pose_records[i].frame_id == corr_id) { old_pose_idx = i; break; }
+  if (!pose_records.empty()) {
+    const SE3 old_T_c_w_inv = pose_records[old_pose_idx].T_c_w.inverse();
+    const Pose7& u = correction_inf.T_c_w;
+    const SE3 update_T_c_w(Quat{u[3], u[0], u[1], u[2]}, Vec3{u[4], u[5], u[6]});
+    for (size_t i = old_pose_idx; i < pose_records.size(); i++) {
+      const SE3 T_diff = pose_records[i].T_c_w * old_T_c_w_inv;
+      pose_records[i].T_c_w = T_diff * update_T_c_w;
+    }
+    const SE3 T_diff = last_frame->T_c_w * old_T_c_w_inv;
+    last_frame->T_c_w = T_diff * update_T_c_w;
+    // correctLMP3DWByLMP3DCandT (camera_frame.cpp:332-342) iterates its landmarks BY VALUE: no effect, nothing to do here
+    // forceCorrectLM3DW (:344-359): ids are compared through an `int` (kept), first match only
+    for (int i = 0; i < correction_inf.lm_count && i < (int)correction_inf.lm_id.size(); i++) {
+      const int id = (int)correction_inf.lm_id[i];
+      for (LandMarkInFrame& lm : last_frame->landmarks)
+        if (lm.lm_id == id) { lm.lm_3d_w = correction_inf.lm_3d[i]; break; }
+    }
+    // forceMarkOutlier (:361-376): every match, no break
+    for (int i = 0; i < correction_inf.lm_outlier_count && i < (int)correction_inf.lm_outlier_id.size(); i++) {
+      const int id = (int)correction_inf.lm_outlier_id[i];
+      for (LandMarkInFrame& lm : last_frame->landmarks)
+        if (lm.lm_id == id) lm.is_tracking_inlier = false;
+    }
+  }
+  has_localmap_feedback = false;
 }
 
 bool F2FTracking::init_frame() {                                   // f2f_tracking.cpp:402-453

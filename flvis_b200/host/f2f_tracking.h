@@ -22,6 +22,7 @@
 #include "sophus_lite.h"
 #include "undistort.h"
 #include "vi_motion.h"
+#include "local_map.h"
 
 namespace flv {
 
@@ -96,6 +97,10 @@ class F2FTracking {
     for (int i = 0; i < 9; ++i) m.R[i] = R9[i];
     return 0;
   }
+  // F2FTracking::correction_feed (f2f_tracking.cpp:40-44): the local map's CorrectionInf for a past keyframe; applied at the
+  // start of the next tracked frame (:189-219).  The reference's nodelet never calls it (vo_tracking.cpp:373-385 unpacks the
+  // message and drops it), so it is off unless the integrator wires it.
+  void correction_feed(double time, const CorrectionInfStruct& corr) { (void)time; correction_inf = corr; has_localmap_feedback = true; }
   void set_host_ransac(bool on) { host_ransac_ = on; }
   int set_equalize_hist(bool enable) { need_equal_hist = enable; return flv_set_equalize_hist(ctx_, enable ? 1 : 0); }
 
@@ -122,6 +127,9 @@ class F2FTracking {
   struct ID_POSE { int64_t frame_id; SE3 T_c_w; };
   std::deque<ID_POSE> pose_records;
   int continus_tracking_fail_cnt = 0, fail_cnt = 0;
+  bool has_localmap_feedback = false;
+  CorrectionInfStruct correction_inf;
+  void apply_localmap_feedback();
   flv_fmat_fn fmat_fn_ = nullptr; flv_pnp_fn pnp_fn_ = nullptr; void* hook_user_ = nullptr;
   bool host_ransac_ = false;                       // true: the host stand-ins of ransac.h instead of the device K11 kernels
   char err_[256] = {0};

@@ -224,6 +224,19 @@ int flv_f2f_get_frame(flv_f2f* f, double* T_c_w, int64_t* lm_id, double* plane_x
   }
   return n;
 }
+int flv_f2f_correction_feed(flv_f2f* f, double t, int64_t frame_id, const double* T_c_w, int lm_count, const int64_t* lm_id,
+                            const double* lm_3d, int outlier_count, const int64_t* outlier_id) {
+  if (!f || !T_c_w || lm_count < 0 || outlier_count < 0 || (lm_count > 0 && (!lm_id || !lm_3d)) || (outlier_count > 0 && !outlier_id))
+    return FLV_ERR_INVALID;
+  flv::CorrectionInfStruct c;
+  c.frame_id = frame_id;
+  for (int k = 0; k < 7; ++k) c.T_c_w[k] = T_c_w[k];
+  c.lm_count = lm_count; c.lm_outlier_count = outlier_count;
+  for (int i = 0; i < lm_count; ++i) { c.lm_id.push_back(lm_id[i]); c.lm_3d.push_back(flv::Vec3{lm_3d[3 * i], lm_3d[3 * i + 1], lm_3d[3 * i + 2]}); }
+  for (int i = 0; i < outlier_count; ++i) c.lm_outlier_id.push_back(outlier_id[i]);
+  f->impl.correction_feed(t, c);
+  return FLV_OK;
+}
 int flv_f2f_get_frame_ex(flv_f2f* f, double* p3d_c, double* first_obs_2d, double* first_obs_pose, double* T_c_w_last_keyframe, int cap) {
   if (!f || !f->impl.curr_frame) return FLV_ERR_INVALID;
   const flv::CameraFrame& fr = *f->impl.curr_frame;

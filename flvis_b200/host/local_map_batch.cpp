@@ -11,6 +11,7 @@
 #include <chrono>
 #include <condition_variable>
 #include <cstdio>
+#include <cstdlib>
 #include <deque>
 #include <functional>
 #include <memory>
@@ -255,7 +256,8 @@ flv_localmap_batch* flv_localmap_batch_create(int device, int n_streams, int win
   if (!b) return nullptr;
   b->S = n_streams;
   const double K[4] = {fx, fy, cx, cy};
-  const int n_shards = n_streams >= 16 ? 4 : (n_streams >= 4 ? 2 : 1);
+  int n_shards = n_streams >= 8 ? 2 : 1;
+  if (const char* e = getenv("FLV_LM_SHARDS")) { const int v = atoi(e); if (v >= 1 && v <= n_streams) n_shards = v; }   // tuning knob
   for (int i = 0; i < n_shards; ++i) {
     const int n_local = (n_streams - i + n_shards - 1) / n_shards;
     LmShard* sh = make_shard(device, n_local, window_size, K);

@@ -84,6 +84,13 @@ const char* flv_f2f_last_error(flv_f2f* f);
 void flv_f2f_set_ransac_hooks(flv_f2f* f, flv_f2f_fmat_fn fmat, flv_f2f_pnp_fn pnp, void* user);
 int flv_f2f_imu_feed(flv_f2f* f, double t, const double* acc, const double* gyro);
 int flv_f2f_image_feed(flv_f2f* f, double t, const uint8_t* img0, const void* img1, int* new_keyframe, int* reset_cmd);
+/* F2FTracking::correction_feed (src/frontend/f2f_tracking.cpp:40-44): hand a CorrectionInf message (msg/CorrectionInf.msg: the
+ * output of flv_localmap_add_keyframe) back to the tracker; it is applied at the start of the next tracked frame (:189-219:
+ * the pose record of that keyframe and everything after it are re-based, the last frame's landmarks get the optimised world
+ * points, the local map's outliers are flagged).  The reference's tracking nodelet drops the message (vo_tracking.cpp:373-385),
+ * so nothing calls this unless the integrator wires the feedback. */
+int flv_f2f_correction_feed(flv_f2f* f, double t, int64_t frame_id, const double* T_c_w, int lm_count, const int64_t* lm_id,
+                            const double* lm_3d, int outlier_count, const int64_t* outlier_id);
 int flv_f2f_state(flv_f2f* f);     /* 0 UnInit, 1 Tracking, 2 TrackingFail */
 /* landmarks of the current frame (after image_feed): returns the count (<= cap) */
 int flv_f2f_get_frame(flv_f2f* f, double* T_c_w, int64_t* lm_id, double* plane_xy, double* undist_xy, double* p3d_w,
@@ -97,6 +104,16 @@ int flv_f2f_get_imu_states(flv_f2f* f, double* out11, int cap);
 /* VIMOTION::acc_bias / gyro_bias of the tracker's IMU filter (vi_motion.cpp:322-330); returns has_imu */
 int flv_f2f_get_imu_bias(flv_f2f* f, double* acc_bias, double* gyro_bias);
 int flv_f2f_tracking_counts(flv_f2f* f, int* of_inliers, int* f_inliers, int* pnp_inliers);
+
+/* ---- trajectory files <- src/independ_modules/vo_repub_rec.cpp:80-126 -------------------------------------------------
+ * format 0: the recorder's pose line "stamp x y z qw qx qy qz" (qw first, precision 6, stamp as sec.nsec);
+ * format 1: KITTI odometry, 12 numbers = row-major [R | t], precision 6.
+ * Poses are given as the tracker's T_c_w = [qx qy qz qw tx ty tz]; the file holds the camera pose in the world (T_c_w^-1),
+ * which is what FLVIS publishes and the recorder subscribes to. */
+typedef struct flv_traj flv_traj;
+flv_traj* flv_traj_open(const char* path, int format);
+int flv_traj_write(flv_traj* t, double stamp, const double* T_c_w);
+void flv_traj_close(flv_traj* t);
 
 /* ---- flv_localmap_batch: the local-map thread for S sequences ------------------------------------------------------
  * One worker thread (FLVIS runs the local map in its own nodelet thread fed by a queue, vo_localmap.cpp:464-467) owns S

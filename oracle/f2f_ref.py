@@ -7,8 +7,8 @@ OpenCV calls: LK = oracle/lk_ref.py through its C twin oracle/lk_ref.c (bit-iden
 FeatureDEM = oracle/feature_dem_ref.py, findFundamentalMat / solvePnPRansac = cv2 (the reference's real library).
 Sensor types: "depth" (DEPTH_D435), "stereo" (STEREO_RECT, zero distortion) and "stereo_unrect" (STEREO_UNRECT: LK on the
 raw images, cv2.undistortPoints / cv2.projectPoints per point with the raw lens models `lens0` / `lens1` =
-(K 3x3, D, R 3x3)); `equalize` = need_equal_hist (cv2.equalizeHist on ingest).  The dead local-map feedback
-(f2f_tracking.cpp:189-219) is not restated.
+(K 3x3, D, R 3x3)); `equalize` = need_equal_hist (cv2.equalizeHist on ingest).  correction_feed + the local-map feedback
+step (f2f_tracking.cpp:40-44, :189-219; never called by the reference's own nodelet) are restated with their quirks.
 """
 import math
 
@@ -62,6 +62,41 @@ class F2FTracking:
         self.id_index = 100; self.rnd = cf.GlibcRand()
         self.T_kf = SE3(); self.fail_cnt = 0; self.tf_cnt = 0
         self.counts = (0, 0, 0)
+        self.pose_records = []                     # [frame_id, T_c_w]
+        self.feedback = None
+
+    def correction_feed(self, corr):
+        """corr: dict(frame_id, T_c_w (7,), lm_id, lm_3d, outlier_id) = the local map's CorrectionInf (f2f_tracking.cpp:40-44)."""
+        self.feedback = corr
+
+    def _apply_feedback(self):                     # f2f_tracking.cpp:189-219
+        c = self.feedback
+        self.feedback = None
+        if not self.pose_records:
+            return
+        def as_int(v):                             # `int correct_lm_id = ids.at(i)` (camera_frame.cpp:349,366)
+            return int(np.int64(v).astype(np.int32))
+        corr_id = as_int(c["frame_id"])
+        idx = 0
+        for i in range(len(self.pose_records) - 1, -1, -1):
+            if self.pose_records[i][0] == corr_id:
+                idx = i
+                break
+        old_inv = self.pose_records[idx][1].inverse()
+        upd = SE3.from7(np.asarray(c["T_c_w"], float))
+        for i in range(idx, len(self.pose_records)):
+            self.pose_records[i][1] = (self.pose_records[i][1] * old_inv) * upd
+        self.last.T_c_w = (self.last.T_c_w * old_inv) * upd
+        # correctLMP3DWByLMP3DCandT iterates by value in the reference: no effect
+        for lid, p in zip(c["lm_id"], c["lm_3d"]):
+            for l in self.last.lms:
+                if l.lm_id == as_int(lid):
+                    l.p3d_w = np.array(p, float)
+                    break
+        for lid in c["outlier_id"]:
+            for l in self.last.lms:
+                if l.lm_id == as_int(lid):
+                    l.inlier = False
 
     def imu_feed(self, t, acc, gyro):
         if not self.vim.imu_initialized:
@@ -128,6 +163,7 @@ class F2FTracking:
         self._depth_innovation(self.curr)
         self.curr.lms = [l for l in self.curr.lms if l.has_3d]
         if sum(1 for l in self.curr.lms if l.has_3d and l.inlier) > 30:
+            self.pose_records.append([self.curr.frame_id, self.curr.T_c_w])
             self.T_kf = self.curr.T_c_w
             return True
         return False
@@ -240,6 +276,8 @@ class F2FTracking:
             if self._init_frame():
                 new_kf = True; self.state = "Tracking"
         elif self.state == "Tracking":
+            if self.feedback is not None:
+                self._apply_feedback()
             guess = None
             if self.has_imu:
                 guess = self.vim.corr_frame_state(t)
@@ -268,6 +306,9 @@ class F2FTracking:
                 self.curr.lms.append(self._new_lm(p, u, self.curr.T_c_w, orig < 60))
             self._depth_innovation(self.curr)
             self.curr.lms = [l for l in self.curr.lms if l.has_3d]
+            self.pose_records.append([self.curr.frame_id, self.curr.T_c_w])
+            if len(self.pose_records) >= 1000:
+                self.pose_records.pop(0)
             Td = self.T_kf * self.curr.T_c_w.inverse()
             r = so3_log(Td.q)
             t_norm = abs(Td.t[0]) + abs(Td.t[1]) + abs(Td.t[2]); r_norm = abs(r[0]) + abs(r[1]) + abs(r[2])

@@ -318,3 +318,77 @@ def test_builtin_ransac_tracks_without_hooks(lib):
     c7 = SE3.from7(T).inverse().t
     assert abs(np.linalg.norm(c7 - c0) - 0.012 * 7) < 0.01
     lib.flv_f2f_destroy(h)
+
+
+def test_correction_feed_applies_local_map_feedback_like_the_reference(lib):
+    """F2FTracking::correction_feed + STEP1 of image_feed (src/frontend/f2f_tracking.cpp:40-44, :189-219), which the reference's
+    own nodelet never wires: every CorrectionInf of the chained local map is fed back to the tracker on both sides; poses are
+    re-based, the last frame's landmarks take the optimised world points, the local map's outliers are flagged -- frame by
+    frame against the oracle with the same feedback."""
+    from flvis_b200 import capi
+    from oracle import localmap_ref
+    _setup(lib)
+    lib.flv_f2f_correction_feed.argtypes = [C.c_void_p, C.c_double, C.c_int64, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+    K = (384.16455, 384.16455, 320.21445, 238.94403)
+    fpara = [30, 15, 5, 500, 0.01, 15]; vpara = [0.1, 0.01, 0.001, 0.001, 0.5, 0.1]; dpara = [0.9, 50.0, 0.0]
+    n_frames, window = 30, 4
+    imgs, depths = f2f_ref.make_depth_sequence(n_frames, seed=33)
+    cfg = Cfg(0, 640, 480, (C.c_double * 4)(*K), (C.c_double * 4)(*K), 1000.0, (C.c_double * 12)(), (C.c_double * 12)(),
+              (C.c_double * 7)(0, 0, 0, 1, 0, 0, 0), (C.c_double * 7)(0, 0, 0, 1, 0, 0, 0),
+              (C.c_double * 6)(*fpara), (C.c_double * 6)(*vpara), (C.c_double * 3)(*dpara), 0)
+    h = lib.flv_f2f_create(C.byref(cfg), 0)
+    assert h and lib.flv_f2f_last_error(h) == b""
+    lib.flv_f2f_set_ransac_hooks(h, fmat_hook, pnp_hook, None)
+    ref = f2f_ref.F2FTracking("depth", 640, 480, K, fpara, vpara, dpara)
+    ctx = capi.Context(1, 64, 64)
+    clib = ctx.lib
+    clib.flv_localmap_create.restype = C.c_void_p
+    clib.flv_localmap_create.argtypes = [C.c_void_p, C.c_int] + [C.c_double] * 4
+    clib.flv_localmap_destroy.argtypes = [C.c_void_p]
+    clib.flv_localmap_add_keyframe.argtypes = [C.c_void_p, C.c_int64, C.c_int] + [C.c_void_p] * 4 + [C.c_void_p] * 5 + \
+        [C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.POINTER(capi.BAStats)]
+    lm = clib.flv_localmap_create(ctx.h, window, *K)
+    lm_ref = localmap_ref.LocalMap(window, K)
+    cap = 600
+    vp = lambda a: a.ctypes.data_as(C.c_void_p)
+    n_fed = 0
+    for k in range(n_frames):
+        kf = C.c_int(0); rs = C.c_int(0)
+        assert lib.flv_f2f_image_feed(h, 0.05 * k, vp(np.ascontiguousarray(imgs[k])), vp(np.ascontiguousarray(depths[k])),
+                                      C.byref(kf), C.byref(rs)) == 0
+        rkf, _ = ref.image_feed(0.05 * k, imgs[k], depths[k])
+        assert bool(kf.value) == rkf
+        T = np.zeros(7); ids = np.zeros(cap, np.int64); und = np.zeros((cap, 2)); p3 = np.zeros((cap, 3))
+        has = np.zeros(cap, np.uint8); inl = np.zeros(cap, np.uint8)
+        n = lib.flv_f2f_get_frame(h, vp(T), vp(ids), None, vp(und), vp(p3), vp(has), vp(inl), cap)
+        cur = ref.curr
+        assert n == len(cur.lms) and list(ids[:n]) == [l.lm_id for l in cur.lms], k
+        assert list(inl[:n].astype(bool)) == [bool(l.inlier) for l in cur.lms], k          # the fed-back outlier flags show up here
+        if n:
+            assert np.abs(p3[:n] - np.array([l.p3d_w for l in cur.lms])).max() <= 1e-4     # and the fed-back world points here
+        assert np.abs(T[4:] - cur.T_c_w.to7()[4:]).max() <= 1e-5, k
+        if not rkf:
+            continue
+        sel = (has[:n] == 1) & (inl[:n] == 1)
+        kids = np.ascontiguousarray(ids[:n][sel]); kuv = np.ascontiguousarray(und[:n][sel]); k3 = np.ascontiguousarray(p3[:n][sel])
+        rsel = [l for l in cur.lms if l.has_3d and l.inlier]
+        okf = {"frame_id": cur.frame_id, "lm_id": [l.lm_id for l in rsel], "lm_2d": np.array([l.undist for l in rsel]),
+               "lm_3d": np.array([l.p3d_w for l in rsel]), "T_c_w": cur.T_c_w.to7()}
+        o = lm_ref.frame_callback(okf)
+        fid = np.zeros(1, np.int64); oT = np.zeros(7); nlm = np.zeros(1, np.int32); olm = np.zeros(8192, np.int64)
+        o3 = np.zeros((8192, 3)); nout = np.zeros(1, np.int32); oout = np.zeros(8192, np.int64)
+        st = capi.BAStats()
+        rc = clib.flv_localmap_add_keyframe(lm, int(cur.frame_id), len(kids), vp(kids), vp(kuv), vp(k3), vp(T), vp(fid), vp(oT),
+                                            vp(nlm), vp(olm), vp(o3), 8192, vp(nout), vp(oout), 8192, C.byref(st))
+        if o is None:
+            assert rc == 0
+            continue
+        assert rc == 1
+        # feed both trackers with their own local map's CorrectionInf
+        assert lib.flv_f2f_correction_feed(h, 0.05 * k, int(fid[0]), vp(oT), int(nlm[0]), vp(olm), vp(o3), int(nout[0]), vp(oout)) == 0
+        ref.correction_feed(dict(frame_id=o["frame_id"], T_c_w=o["T_c_w"], lm_id=o["lm_id"], lm_3d=o["lm_3d"], outlier_id=o["outlier_id"]))
+        n_fed += 1
+    assert n_fed >= 3 and ref.state == "Tracking"
+    clib.flv_localmap_destroy(lm)
+    ctx.close()
+    lib.flv_f2f_destroy(h)

@@ -7,7 +7,8 @@ from synthdata import ba_problems
 
 W = int(sys.argv[1]) if len(sys.argv) > 1 else 10
 S = int(sys.argv[2]) if len(sys.argv) > 2 else 1
-probs = [ba_problems.make_problem(window=W, n_landmarks=1500 if W <= 10 else 2000, obs_per_frame=480, seed=2 + s) for s in range(S)]
+OBS = int(sys.argv[3]) if len(sys.argv) > 3 else 480
+probs = [ba_problems.make_problem(window=W, n_landmarks=(3 * OBS if W <= 10 else 2000), obs_per_frame=OBS, seed=2 + s) for s in range(S)]
 batch = ba_batch.Batch(probs)
 ctx = capi.Context(S, 752, 480)
 for rep in range(2):
