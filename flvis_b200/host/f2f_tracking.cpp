@@ -62,7 +62,7 @@ void CameraFrame::getKeyFrameInf(std::vector<int64_t>& lm_id, std::vector<Vec2>&
 
 // ---- F2FTracking ---------------------------------------------------------------------------------
 F2FTracking::F2FTracking() {}
-F2FTracking::~F2FTracking() { delete vimotion; if (ctx_) flv_destroy(ctx_); }
+F2FTracking::~F2FTracking() { delete vimotion; delete feature_dem; delete lkorb_tracker; if (ctx_) flv_destroy(ctx_); }
 
 int F2FTracking::init(const DepthCamera& dc, const SE3& T_i_c0, const double feature_para[6], const double vi_para[6],
                       const double dc_para[3], int skip_first_n_imgs, bool need_equal_hist_in, int device) {   // f2f_tracking.cpp:5-38
@@ -70,18 +70,18 @@ int F2FTracking::init(const DepthCamera& dc, const SE3& T_i_c0, const double fea
   int rc = flv_create(&ctx_, device, 1, dc.img_w, dc.img_h, MAX_PTS);
   if (rc) { snprintf(err_, sizeof(err_), "flv_create: %s", flv_last_error(ctx_)); return rc; }
   if (need_equal_hist && (rc = flv_set_equalize_hist(ctx_, 1))) return rc;    // f2f_tracking.cpp:125-145
-  fprm_.max_region_feature_num = (int)feature_para[0];
-  fprm_.min_region_feature_num = (int)feature_para[1];
-  fprm_.boundary_dis = (int)std::floor(feature_para[2] / 2.0);
-  fprm_.gftt_num = (int)feature_para[3];
-  fprm_.gftt_ql = feature_para[4];
-  fprm_.gftt_dis = (int)feature_para[5];
+  if ((rc = flv_ba_reserve(ctx_, 1, MAX_PTS, MAX_PTS))) return rc;            // workspace of the per-frame pose-only BA, once
+  feature_dem = new FeatureDEM(ctx_, dc.img_w, dc.img_h, feature_para);       // f2f_tracking.cpp:16-19
+  lkorb_tracker = new LKORBTracking(dc.img_w, dc.img_h);
+  lkorb_tracker->d_camera = dc;
   vimotion = new VIMOTION(T_i_c0, 9.81, vi_para[0], vi_para[1], vi_para[2], vi_para[3]);
   curr_frame = std::make_shared<CameraFrame>();
   last_frame = std::make_shared<CameraFrame>();
   cam_type = dc.cam_type;
   d_camera = curr_frame->d_camera = last_frame->d_camera = dc;
   curr_frame->slot0 = 0; curr_frame->slot1 = 1; last_frame->slot0 = 2; last_frame->slot1 = 3;
+  curr_frame->ctx = last_frame->ctx = ctx_;
+  curr_frame->rand_stream = last_frame->rand_stream = &rand_;
   iir_ratio = (float)dc_para[0];
   range = (float)dc_para[1];
   enable_dummy = !(dc_para[2] < 0.5);
@@ -106,23 +106,34 @@ LandMarkInFrame F2FTracking::make_landmark(const Vec2& pt2d, const Vec2& pt2d_un
   return lm;
 }
 
-int F2FTracking::feature_detect(CameraFrame& fr, std::vector<P2f>& pts) {
+// ---- FeatureDEM ------------------------------------------------------------------------------------
+FeatureDEM::FeatureDEM(flv_ctx* ctx, int image_width, int image_height, const double f_para[6])   // feature_dem.cpp:12-54
+    : ctx_(ctx), width(image_width), height(image_height) {
+  prm_.max_region_feature_num = (int)f_para[0];
+  prm_.min_region_feature_num = (int)f_para[1];
+  prm_.boundary_dis = (int)std::floor(f_para[2] / 2.0);
+  prm_.gftt_num = (int)f_para[3];
+  prm_.gftt_ql = f_para[4];
+  prm_.gftt_dis = (int)f_para[5];
+}
+int FeatureDEM::detect(int slot, std::vector<P2f>& newPts) {                                       // :215-266
   std::vector<float> out(2 * MAX_PTS); int n = 0;
-  int rc = flv_feature_detect(ctx_, fr.slot0, 1, &fprm_, out.data(), &n, FLV_MEM_HOST);
+  int rc = flv_feature_detect(ctx_, slot, 1, &prm_, out.data(), &n, FLV_MEM_HOST);
   if (rc) return rc;
-  pts.resize(n);
-  memcpy(pts.data(), out.data(), (size_t)n * 8);
+  newPts.resize(n);
+  memcpy(newPts.data(), out.data(), (size_t)n * 8);
   return FLV_OK;
 }
-int F2FTracking::feature_redetect(CameraFrame& fr, std::vector<P2f>& pts) {
+int FeatureDEM::redetect(int slot, const std::vector<Vec2>& existedPts, std::vector<P2f>& newPts, int& newPtscount) {   // :124-213
   std::vector<double> ex(2 * MAX_PTS, 0.0);
-  int ne = (int)std::min<size_t>(fr.landmarks.size(), MAX_PTS), n = 0;
-  for (int i = 0; i < ne; ++i) { ex[2 * i] = fr.landmarks[i].lm_2d_plane[0]; ex[2 * i + 1] = fr.landmarks[i].lm_2d_plane[1]; }
+  int ne = (int)std::min<size_t>(existedPts.size(), MAX_PTS), n = 0;
+  for (int i = 0; i < ne; ++i) { ex[2 * i] = existedPts[i][0]; ex[2 * i + 1] = existedPts[i][1]; }
   std::vector<float> out(2 * MAX_PTS);
-  int rc = flv_feature_redetect(ctx_, fr.slot0, 1, &fprm_, ex.data(), &ne, out.data(), &n, FLV_MEM_HOST);
+  int rc = flv_feature_redetect(ctx_, slot, 1, &prm_, ex.data(), &ne, out.data(), &n, FLV_MEM_HOST);
   if (rc) return rc;
-  pts.resize(n);
-  memcpy(pts.data(), out.data(), (size_t)n * 8);
+  newPts.resize(n);
+  memcpy(newPts.data(), out.data(), (size_t)n * 8);
+  newPtscount = n;
   return FLV_OK;
 }
 
@@ -164,7 +175,8 @@ int F2FTracking::image_feed(double time, const uint8_t* img0, const void* img1, 
       if (has_localmap_feedback) apply_localmap_feedback();
       SE3 imu_guess; bool has_imu_guess = false;
       if (has_imu) has_imu_guess = vimotion->viGetCorrFrameState(time, imu_guess);
-      const bool tracking_success = tracking(*last_frame, *curr_frame, imu_guess, has_imu_guess);
+      std::vector<P2f> lm2d_from, lm2d_to, outlier_tracking;
+      const bool tracking_success = lkorb_tracker->tracking(*last_frame, *curr_frame, imu_guess, has_imu_guess, lm2d_from, lm2d_to, outlier_tracking);
       if (!tracking_success) {
         continus_tracking_fail_cnt++;
         last_frame.swap(curr_frame);
@@ -173,27 +185,31 @@ int F2FTracking::image_feed(double time, const uint8_t* img0, const void* img1, 
       }
       continus_tracking_fail_cnt = 0;
       if (has_imu) vimotion->viVisionRPCompensation(curr_frame->frame_time, curr_frame->T_c_w);
-      if (!optimize_in_frame(*curr_frame)) {
+      if (!OptimizeInFrame::optimize(*curr_frame)) {
         continus_tracking_fail_cnt++;
         last_frame.swap(curr_frame);
         if (continus_tracking_fail_cnt >= 2) { vo_tracking_state = TrackingFail; continus_tracking_fail_cnt = 0; }
         break;
       }
-      if ((rc = cal_reprj_inlier_outlier(*curr_frame, 1.5))) return rc;
+      std::vector<Vec2> outlier_reproject;
+      double mean_reprojection_error = 0;
+      if ((rc = curr_frame->calReprjInlierOutlier(mean_reprojection_error, outlier_reproject, 1.5))) return rc;
+      curr_frame->reprojection_error = mean_reprojection_error;
       curr_frame->eraseReprjOutlier();
       if (has_imu)
         vimotion->viCorrectionFromVision(curr_frame->frame_time, curr_frame->T_c_w, last_frame->frame_time, last_frame->T_c_w,
                                          curr_frame->reprojection_error);
       std::vector<P2f> pts2d;
       const int orig_size = (int)curr_frame->landmarks.size();
-      if ((rc = feature_redetect(*curr_frame, pts2d))) return rc;
+      int newPtsCount = 0;
+      if ((rc = feature_dem->redetect(curr_frame->slot0, curr_frame->get2dPlaneVec(), pts2d, newPtsCount))) return rc;
       const bool add_as_inliers = orig_size < 60;
       for (const P2f& p : pts2d) {      // DEPTH_D435 / STEREO_RECT: pts2d_undistort = pts2d (:294-299); UNRECT: undistortPoints (:300-303)
         P2f u = p;
         if (cam_type == STEREO_UNRECT) undistort_point(d_camera.lens0, p.x, p.y, u.x, u.y);
         curr_frame->landmarks.push_back(make_landmark(Vec2{p.x, p.y}, Vec2{u.x, u.y}, curr_frame->T_c_w, add_as_inliers));
       }
-      if ((rc = depth_innovation(*curr_frame))) return rc;
+      if ((rc = curr_frame->depthInnovation(iir_ratio, range, enable_dummy))) return rc;
       curr_frame->eraseNoDepthPoint();
       pose_records.push_back(ID_POSE{curr_frame->frame_id, curr_frame->T_c_w});
       if (pose_records.size() >= 1000) pose_records.pop_front();
@@ -257,14 +273,14 @@ void F2FTracking::apply_localmap_feedback() {                       // f2f_track
 
 bool F2FTracking::init_frame() {                                   // f2f_tracking.cpp:402-453
   std::vector<P2f> pts2d;
-  if (feature_detect(*curr_frame, pts2d)) return false;
+  if (feature_dem->detect(curr_frame->slot0, pts2d)) return false;
   // DEPTH: undistorted = plane.  STEREO_RECT: cv::undistortPoints(K0, D0=0, R0=I, P0) is the identity map up to rounding
   for (const P2f& p : pts2d) {
     P2f u = p;
     if (cam_type == STEREO_UNRECT) undistort_point(d_camera.lens0, p.x, p.y, u.x, u.y);      // :425
     curr_frame->landmarks.push_back(make_landmark(Vec2{p.x, p.y}, Vec2{u.x, u.y}, curr_frame->T_c_w, true));
   }
-  if (depth_innovation(*curr_frame)) return false;
+  if (curr_frame->depthInnovation(iir_ratio, range, enable_dummy)) return false;
   curr_frame->eraseNoDepthPoint();
   if (curr_frame->validLMCount() > 30) {
     pose_records.push_back(ID_POSE{curr_frame->frame_id, curr_frame->T_c_w});
@@ -274,7 +290,12 @@ bool F2FTracking::init_frame() {                                   // f2f_tracki
   return false;
 }
 
-bool F2FTracking::tracking(CameraFrame& from, CameraFrame& to, const SE3& T_c_w_guess, bool use_guess) {   // lkorb_tracking.cpp:9-202
+// ---- LKORBTracking ---------------------------------------------------------------------------------
+bool LKORBTracking::tracking(CameraFrame& from, CameraFrame& to, SE3 T_c_w_guess, bool use_guess, std::vector<P2f>& lm2d_from,
+                             std::vector<P2f>& lm2d_to, std::vector<P2f>& outlier) {   // lkorb_tracking.cpp:9-202
+  flv_ctx* ctx_ = from.ctx;
+  const int cam_type = d_camera.cam_type;
+  lm2d_from.clear(); lm2d_to.clear(); outlier.clear();
   const int n = (int)std::min<size_t>(from.landmarks.size(), MAX_PTS);
   std::vector<P2f> from_plane(n), tracked_plane(n), from_und(n);
   std::vector<P3f> from_p3d(n);
@@ -331,9 +352,9 @@ bool F2FTracking::tracking(CameraFrame& from, CameraFrame& to, const SE3& T_c_w_
   // STEP2: F-matrix consistency; mask index i is applied to to.landmarks[i] (mirrored order, kept: :138-149)
   const int m = (int)from_und.size();
   std::vector<uint8_t> maskF(m, 0);
-  if (fmat_fn_) {
-    if (fmat_fn_(hook_user_, m, &from_und[0].x, &tracked_und[0].x, maskF.data())) return false;
-  } else if (host_ransac_) {
+  if (fmat_fn) {
+    if (fmat_fn(hook_user, m, &from_und[0].x, &tracked_und[0].x, maskF.data())) return false;
+  } else if (host_ransac) {
     double F[9];
     find_fundamental_ransac(from_und, tracked_und, 5.0, 0.99, maskF, F);
   } else {                                                       // K11 on the device (flv_fundamental_ransac)
@@ -362,12 +383,12 @@ bool F2FTracking::tracking(CameraFrame& from, CameraFrame& to, const SE3& T_c_w_
   const double K[4] = {d_camera.cam0_fx, d_camera.cam0_fy, d_camera.cam0_cx, d_camera.cam0_cy};
   Pose7 T = to7(use_guess ? T_c_w_guess : from.T_c_w);
   std::vector<int> inl;
-  if (pnp_fn_) {
+  if (pnp_fn) {
     inl.resize(p2d.size());
     int ninl = 0;
-    if (p2d.empty() || pnp_fn_(hook_user_, (int)p2d.size(), &p3d[0].x, &p2d[0].x, K, use_guess ? 1 : 0, T.data(), inl.data(), &ninl)) return false;
+    if (p2d.empty() || pnp_fn(hook_user, (int)p2d.size(), &p3d[0].x, &p2d[0].x, K, use_guess ? 1 : 0, T.data(), inl.data(), &ninl)) return false;
     inl.resize(ninl);
-  } else if (host_ransac_) {
+  } else if (host_ransac) {
     solve_pnp_ransac(p3d, p2d, K, T, 100, 3.0, 0.99, inl);
   } else {                                                       // K11 on the device (flv_pnp_ransac), prior = guess / last pose
     std::vector<float> x3(3 * MAX_PTS, 0.f), x2(2 * MAX_PTS, 0.f);
@@ -385,15 +406,23 @@ bool F2FTracking::tracking(CameraFrame& from, CameraFrame& to, const SE3& T_c_w_
   to.updateLMState(mask_pnp);
   to.T_c_w = from7(T.data());
   last_pnp_inliers = (int)inl.size();
+  for (const LandMarkInFrame& lm : to.landmarks) {           // debug lists (:190-200)
+    const P2f p{(float)lm.lm_2d_plane[0], (float)lm.lm_2d_plane[1]};
+    if (lm.is_tracking_inlier) lm2d_to.push_back(p); else outlier.push_back(p);
+  }
+  for (const LandMarkInFrame& lm : from.landmarks) lm2d_from.push_back(P2f{(float)lm.lm_2d_plane[0], (float)lm.lm_2d_plane[1]});
   return inl.size() >= 10;
 }
 
-bool F2FTracking::optimize_in_frame(CameraFrame& frame) {          // optimize_in_frame.cpp:10-90
+// ---- OptimizeInFrame -------------------------------------------------------------------------------
+bool OptimizeInFrame::optimize(CameraFrame& frame) {                // optimize_in_frame.cpp:10-90
+  flv_ctx* ctx_ = frame.ctx;
+  const DepthCamera& d_camera = frame.d_camera;
   std::vector<const LandMarkInFrame*> lms;
   for (const LandMarkInFrame& lm : frame.landmarks) if (lm.has_3d && lm.is_tracking_inlier) lms.push_back(&lm);
   const int n = (int)lms.size();
   if (n < 10) return false;
-  if (flv_ba_reserve(ctx_, 1, MAX_PTS, MAX_PTS)) return false;
+  if (flv_ba_reserve(ctx_, 1, MAX_PTS, MAX_PTS)) return false;         // no-op once reserved (F2FTracking::init does it)
   std::vector<double> pts(3 * MAX_PTS, 0.0), uv(2 * MAX_PTS, 0.0);
   std::vector<int> ep(MAX_PTS, 0), el(MAX_PTS, 0);
   std::vector<uint8_t> act(MAX_PTS, 0);
@@ -413,7 +442,10 @@ bool F2FTracking::optimize_in_frame(CameraFrame& frame) {          // optimize_i
   return true;
 }
 
-int F2FTracking::cal_reprj_inlier_outlier(CameraFrame& fr, double sh_over_med) {   // camera_frame.cpp:43-91
+int CameraFrame::calReprjInlierOutlier(double& mean_prjerr, std::vector<Vec2>& outlier, double sh_over_med) {   // camera_frame.cpp:43-91
+  CameraFrame& fr = *this;
+  flv_ctx* ctx_ = ctx;
+  outlier.clear();
   const int n = (int)std::min<size_t>(fr.landmarks.size(), MAX_PTS);
   std::vector<double> und(2 * MAX_PTS, 0.0), p3(3 * MAX_PTS, 0.0);
   for (int i = 0; i < n; ++i) {
@@ -426,12 +458,19 @@ int F2FTracking::cal_reprj_inlier_outlier(CameraFrame& fr, double sh_over_med) {
   double mean = 0;
   int rc = flv_reprojection_inliers(ctx_, 1, &n, &cam, T.data(), und.data(), p3.data(), sh_over_med, inl.data(), &mean, FLV_MEM_HOST);
   if (rc) return rc;
-  for (int i = 0; i < n; ++i) fr.landmarks[i].is_tracking_inlier = inl[i] != 0;
-  fr.reprojection_error = mean;
+  for (int i = 0; i < n; ++i) {
+    fr.landmarks[i].is_tracking_inlier = inl[i] != 0;
+    if (!inl[i]) outlier.push_back(fr.landmarks[i].lm_2d_plane);
+  }
+  mean_prjerr = mean;
   return FLV_OK;
 }
 
-int F2FTracking::depth_innovation(CameraFrame& fr) {              // camera_frame.cpp:271-330 (+ :93-131 for the stereo LK)
+int CameraFrame::depthInnovation(float iir_ratio, float range, bool enable_dummy) {   // camera_frame.cpp:271-330 (+ :93-131 for the stereo LK)
+  CameraFrame& fr = *this;
+  flv_ctx* ctx_ = ctx;
+  const int cam_type = d_camera.cam_type;
+  GlibcRand& rand_ = *rand_stream;
   const int n = (int)std::min<size_t>(fr.landmarks.size(), MAX_PTS);
   std::vector<double> plane(2 * MAX_PTS, 0.0), und(2 * MAX_PTS, 0.0), p3w(3 * MAX_PTS, 0.0), p3c(3 * MAX_PTS, 0.0),
       f2(2 * MAX_PTS, 0.0), fp(7 * MAX_PTS, 0.0), pt1(2 * MAX_PTS, 0.0);

@@ -1,4 +1,5 @@
-// Host-side frame-to-frame tracker with the reference's class surface:
+// Host-side frame-to-frame tracker with the reference's class surface (one class per reference class, same method names and
+// argument meaning; cv::Mat image arguments become a GPU context + pyramid slot):
 //   LandMark / LandMarkInFrame   src/processing/include/landmark.h:8-36, src/processing/landmark.cpp:3-44
 //   DepthCamera                  src/processing/include/depth_camera.h:6-77, depth_camera.cpp:92-150
 //   CameraFrame                  src/processing/include/camera_frame.h:44-78, camera_frame.cpp:8-529
@@ -56,13 +57,21 @@ class CameraFrame {
  public:
   int64_t frame_id = 0;
   double frame_time = 0;
-  int slot0 = 0, slot1 = 1;                       // pyramid slots of img0 / img1 in the tracker's flv_ctx
+  // img0 / img1 of the reference (cv::Mat members) live on the GPU: pyramid slots slot0 / slot1 of `ctx`
+  flv_ctx* ctx = nullptr;
+  int slot0 = 0, slot1 = 1;
+  GlibcRand* rand_stream = nullptr;               // the sequence's rand() stream (dummy depths, camera_frame.cpp:153,168,198,222)
   std::vector<uint16_t> d_img;                    // depth image (DEPTH_D435), host copy for the nearest-pixel lookups
   DepthCamera d_camera;
   std::vector<LandMarkInFrame> landmarks;
   SE3 T_c_w;
   double reprojection_error = 0;
   void clear();
+  // CameraFrame::calReprjInlierOutlier (camera_frame.cpp:43-91) on the GPU (flv_reprojection_inliers); `outlier` receives
+  // the pixel positions of the landmarks flagged as outliers (the reference's debug list)
+  int calReprjInlierOutlier(double& mean_prjerr, std::vector<Vec2>& outlier, double sh_over_med = 3.0);
+  // CameraFrame::depthInnovation (camera_frame.cpp:271-330, incl. the left->right LK of recover3DPts_c_FromStereo :93-131)
+  int depthInnovation(float iir_ratio, float range, bool dummy_depth);
   void eraseReprjOutlier();
   void eraseNoDepthPoint();
   int validLMCount() const;
@@ -71,10 +80,48 @@ class CameraFrame {
   void getKeyFrameInf(std::vector<int64_t>& lm_id, std::vector<Vec2>& lm_2d, std::vector<Vec3>& lm_3d) const;
 };
 
+// ---- FeatureDEM <- src/processing/include/feature_dem.h:35-50, feature_dem.cpp:12-266 ------------------------------------
+// cv::Mat arguments become (context, pyramid slot): the image is already on the GPU.
+class FeatureDEM {
+ public:
+  FeatureDEM(flv_ctx* ctx, int image_width, int image_height, const double f_para[6]);
+  int detect(int slot, std::vector<P2f>& newPts);
+  int redetect(int slot, const std::vector<Vec2>& existedPts, std::vector<P2f>& newPts, int& newPtscount);
+  const flv_feature_params& params() const { return prm_; }
+
+ private:
+  flv_ctx* ctx_;
+  int width, height;
+  flv_feature_params prm_{};
+};
+
 // RANSAC hooks (default = host stand-ins of ransac.h).  Return 0 on success.
 typedef int (*flv_fmat_fn)(void* user, int n, const float* from_xy, const float* to_xy, uint8_t* mask_out);
 typedef int (*flv_pnp_fn)(void* user, int n, const float* p3d, const float* p2d, const double* K4, int use_guess,
                           double* T_c_w_inout /*[qx qy qz qw tx ty tz]*/, int* inlier_idx_out, int* n_inliers_out);
+
+// ---- LKORBTracking <- src/processing/include/lkorb_tracking.h:8-21, lkorb_tracking.cpp:9-202 ----------------------------
+class LKORBTracking {
+  int width, height;
+
+ public:
+  DepthCamera d_camera;
+  LKORBTracking(int width_in, int height_in) : width(width_in), height(height_in) {}
+  // lm2d_from / lm2d_to: pixel positions of the PnP inliers in both frames, outlier: positions rejected on the way
+  // (the reference's debug lists, lkorb_tracking.cpp:190-200)
+  bool tracking(CameraFrame& from, CameraFrame& to, SE3 T_c_w_guess, bool use_guess, std::vector<P2f>& lm2d_from,
+                std::vector<P2f>& lm2d_to, std::vector<P2f>& outlier);
+  // the two OpenCV RANSAC calls: device kernels (default), host stand-ins, or caller hooks
+  flv_fmat_fn fmat_fn = nullptr; flv_pnp_fn pnp_fn = nullptr; void* hook_user = nullptr;
+  bool host_ransac = false;
+  int last_of_inliers = 0, last_f_inliers = 0, last_pnp_inliers = 0;   // "pnp|F|of" (:191)
+};
+
+// ---- OptimizeInFrame <- src/processing/include/optimize_in_frame.h:27-32, optimize_in_frame.cpp:10-90 --------------------
+class OptimizeInFrame {
+ public:
+  static bool optimize(CameraFrame& frame);
+};
 
 class F2FTracking {
  public:
@@ -88,20 +135,23 @@ class F2FTracking {
   void imu_feed(double time, const Vec3& acc, const Vec3& gyro, Quat& q_w_i, Vec3& pos_w_i, Vec3& vel_w_i);
   // img1: u8 right image (stereo) or u16 depth image (DEPTH_D435); rows tightly packed
   int image_feed(double time, const uint8_t* img0, const void* img1, bool& new_keyframe, bool& reset_cmd);
-  void set_ransac_hooks(flv_fmat_fn f, flv_pnp_fn p, void* user) { fmat_fn_ = f; pnp_fn_ = p; hook_user_ = user; }
+  void set_ransac_hooks(flv_fmat_fn f, flv_pnp_fn p, void* user) { if (lkorb_tracker) { lkorb_tracker->fmat_fn = f; lkorb_tracker->pnp_fn = p; lkorb_tracker->hook_user = user; } }
   // raw lens model of camera `cam` (K, D[14], R rectification); P stays the rectified projection given at init
   int set_lens(int cam, const double* K4, const double* D14, const double* R9) {
-    LensModel& m = cam == 0 ? d_camera.lens0 : d_camera.lens1;
-    m.fx = K4[0]; m.fy = K4[1]; m.cx = K4[2]; m.cy = K4[3];
-    for (int i = 0; i < 14; ++i) m.k[i] = D14[i];
-    for (int i = 0; i < 9; ++i) m.R[i] = R9[i];
+    for (DepthCamera* dc : {&d_camera, lkorb_tracker ? &lkorb_tracker->d_camera : (DepthCamera*)nullptr}) {
+      if (!dc) continue;
+      LensModel& m = cam == 0 ? dc->lens0 : dc->lens1;
+      m.fx = K4[0]; m.fy = K4[1]; m.cx = K4[2]; m.cy = K4[3];
+      for (int i = 0; i < 14; ++i) m.k[i] = D14[i];
+      for (int i = 0; i < 9; ++i) m.R[i] = R9[i];
+    }
     return 0;
   }
   // F2FTracking::correction_feed (f2f_tracking.cpp:40-44): the local map's CorrectionInf for a past keyframe; applied at the
   // start of the next tracked frame (:189-219).  The reference's nodelet never calls it (vo_tracking.cpp:373-385 unpacks the
   // message and drops it), so it is off unless the integrator wires it.
   void correction_feed(double time, const CorrectionInfStruct& corr) { (void)time; correction_inf = corr; has_localmap_feedback = true; }
-  void set_host_ransac(bool on) { host_ransac_ = on; }
+  void set_host_ransac(bool on) { if (lkorb_tracker) lkorb_tracker->host_ransac = on; }
   int set_equalize_hist(bool enable) { need_equal_hist = enable; return flv_set_equalize_hist(ctx_, enable ? 1 : 0); }
 
   std::shared_ptr<CameraFrame> curr_frame, last_frame;
@@ -111,13 +161,12 @@ class F2FTracking {
   VIMOTION* vimotion = nullptr;
   const char* last_error() const { return err_; }
   const SE3& last_keyframe_pose() const { return T_c_w_last_keyframe; }
-  // last tracking() counters "pnp|F|of" (lkorb_tracking.cpp:191)
-  int last_of_inliers = 0, last_f_inliers = 0, last_pnp_inliers = 0;
+  FeatureDEM* feature_dem = nullptr;               // the modules the reference allocates in init (f2f_tracking.cpp:16-19)
+  LKORBTracking* lkorb_tracker = nullptr;
 
  private:
   flv_ctx* ctx_ = nullptr;
   DepthCamera d_camera;
-  flv_feature_params fprm_{};
   float iir_ratio = 0.9f, range = 50.f;
   bool enable_dummy = false, need_equal_hist = false;
   int skip_n_imgs = 0, cam_type = DEPTH_D435;
@@ -130,19 +179,11 @@ class F2FTracking {
   bool has_localmap_feedback = false;
   CorrectionInfStruct correction_inf;
   void apply_localmap_feedback();
-  flv_fmat_fn fmat_fn_ = nullptr; flv_pnp_fn pnp_fn_ = nullptr; void* hook_user_ = nullptr;
-  bool host_ransac_ = false;                       // true: the host stand-ins of ransac.h instead of the device K11 kernels
   char err_[256] = {0};
   int slot_toggle = 0;
 
   LandMarkInFrame make_landmark(const Vec2& pt2d, const Vec2& pt2d_undist, const SE3& T_c_w, bool is_inlier);
   bool init_frame();
-  bool tracking(CameraFrame& from, CameraFrame& to, const SE3& T_c_w_guess, bool use_guess);   // LKORBTracking::tracking
-  bool optimize_in_frame(CameraFrame& frame);                                                   // OptimizeInFrame::optimize
-  int depth_innovation(CameraFrame& frame);                                                     // CameraFrame::depthInnovation
-  int cal_reprj_inlier_outlier(CameraFrame& frame, double sh_over_med);                         // CameraFrame::calReprjInlierOutlier
-  int feature_detect(CameraFrame& frame, std::vector<P2f>& pts);
-  int feature_redetect(CameraFrame& frame, std::vector<P2f>& pts);
 };
 
 }  // namespace flv

@@ -264,9 +264,10 @@ int flv_f2f_get_imu_bias(flv_f2f* f, double* acc_bias, double* gyro_bias) {
 }
 int flv_f2f_tracking_counts(flv_f2f* f, int* of, int* fi, int* pnp) {
   if (!f) return FLV_ERR_INVALID;
-  if (of) *of = f->impl.last_of_inliers;
-  if (fi) *fi = f->impl.last_f_inliers;
-  if (pnp) *pnp = f->impl.last_pnp_inliers;
+  if (!f->impl.lkorb_tracker) return FLV_ERR_INVALID;
+  if (of) *of = f->impl.lkorb_tracker->last_of_inliers;
+  if (fi) *fi = f->impl.lkorb_tracker->last_f_inliers;
+  if (pnp) *pnp = f->impl.lkorb_tracker->last_pnp_inliers;
   return FLV_OK;
 }
 
