@@ -18,6 +18,25 @@ class F2FConfig(C.Structure):          # flv_f2f_config
                 ("vi_para", C.c_double * 6), ("dc_para", C.c_double * 3), ("skip_first_n_imgs", C.c_int)]
 
 
+class F2FStereoConfig(C.Structure):    # flv_f2f_stereo_config (DepthCamera::setSteroCamInfo's arguments)
+    _fields_ = [("cam_type", C.c_int), ("img_w", C.c_int), ("img_h", C.c_int),
+                ("K0", C.c_double * 9), ("D0", C.c_double * 14), ("R0", C.c_double * 9), ("P0", C.c_double * 12),
+                ("K1", C.c_double * 9), ("D1", C.c_double * 14), ("R1", C.c_double * 9), ("P1", C.c_double * 12),
+                ("T_c0_c1", C.c_double * 7), ("T_i_c0", C.c_double * 7), ("feature_para", C.c_double * 6),
+                ("vi_para", C.c_double * 6), ("dc_para", C.c_double * 3), ("skip_first_n_imgs", C.c_int), ("need_equal_hist", C.c_int)]
+
+
+def stereo_config_for(seq):
+    """flv_f2f_stereo_config for a STEREO_UNRECT synthdata sequence: the matrices vo_tracking.cpp:222-262 passes to
+    DepthCamera::setSteroCamInfo (cv::stereoRectify output included)."""
+    _, _, equalize, _, m = config_for(seq)
+    c = seq.cfg
+    d = lambda vals, n: (C.c_double * n)(*([float(v) for v in np.asarray(vals).ravel()] + [0.0] * (n - np.asarray(vals).size)))
+    return F2FStereoConfig(2, c["w"], c["h"], d(m["K0"], 9), d(m["D0"], 14), d(m["R0"], 9), d(m["P0"], 12), d(m["K1"], 9), d(m["D1"], 14),
+                           d(m["R1"], 9), d(m["P1"], 12), d(seq.T_c0_c1.to7(), 7), d(seq.T_i_c0.to7(), 7), d(c["feature_para"], 6),
+                           d(c["vi_para"], 6), d(c["dc_para"], 3), 0, 1 if equalize else 0)
+
+
 def _p(a):
     return a.ctypes.data_as(C.c_void_p)
 

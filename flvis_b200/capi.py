@@ -18,7 +18,7 @@ SYMBOLS = [
     "flv_launch_count", "flv_level_info", "flv_num_levels", "flv_upload_images", "flv_build_pyramid",
     "flv_download_level", "flv_lk_track", "flv_select_tracked", "flv_gftt", "flv_download_eig", "flv_gftt_capacity",
     "flv_feature_detect", "flv_feature_redetect", "flv_ba_reserve", "flv_ba_optimize", "flv_gftt_keep_response",
-    "flv_ba_profile", "flv_set_ba_stream", "flv_feature_prepare", "flv_set_equalize_hist", "flv_fundamental_ransac", "flv_pnp_ransac", "flv_upload_color_images", "flv_depth_innovation", "flv_reprojection_inliers",
+    "flv_ba_profile", "flv_set_ba_stream", "flv_set_ba_cluster", "flv_feature_prepare", "flv_set_equalize_hist", "flv_fundamental_ransac", "flv_pnp_ransac", "flv_upload_color_images", "flv_depth_innovation", "flv_reprojection_inliers",
     "flv_ba_trace", "flv_ba_debug_edges",
 ]
 
@@ -89,6 +89,7 @@ def load_library(path=LIB_PATH):
     lib.flv_ba_debug_edges.argtypes = [vp, C.c_int, vp, vp, vp, vp, vp, vp, vp]
     lib.flv_ba_reserve.argtypes = [vp, C.c_int, C.c_int, C.c_int]
     lib.flv_set_ba_stream.argtypes = [vp, vp, C.c_int]
+    lib.flv_set_ba_cluster.argtypes = [vp, C.c_int, C.c_int]
     lib.flv_level_info.argtypes = [vp, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int),
                                    C.POINTER(C.c_size_t)]
     lib.flv_upload_images.argtypes = [vp, C.c_int, C.c_int, vp, C.c_size_t, C.c_size_t, C.c_int]
@@ -265,6 +266,9 @@ class Context:
 
     def set_ba_stream(self, cuda_stream_ptr, enable=True):
         self._chk(self.lib.flv_set_ba_stream(self.h, C.c_void_p(cuda_stream_ptr), 1 if enable else 0))
+
+    def set_ba_cluster(self, host_mode=4, device_mode=1):
+        self._chk(self.lib.flv_set_ba_cluster(self.h, host_mode, device_mode))
 
     def ba_profile(self, stream):
         out = np.zeros(16, np.int64)

@@ -30,6 +30,9 @@
 //           pose (exp map), chi2 block reduction
 // Algorithmic bytes: build 168E+392P+120L, Schur 144E+96L+288Pf^2+48Pf per trial.
 #include "ctx.h"
+#include <cooperative_groups.h>
+
+namespace cg = cooperative_groups;
 
 namespace {
 
@@ -203,13 +206,20 @@ constexpr int BA_MAX_CHUNKS = 128;
 constexpr int BA_CHUNK_PLANES = 18 + 3;       // Z = W Ld (6x3) per slot, Ld^T bl per landmark
 constexpr int BA_MAX_CAP = 1023;              // chunk-local positions are packed 10 bits each
 
-struct Sh {   // fixed-size shared state
+struct Sh {   // fixed-size shared state (one copy per CTA of the window's cluster)
   double red[BA_WARPS];
   double Hd[BA_MAX_FREE][21];
   double part[2 * BA_MAX_FREE][27];     // pose-pass partial sums
+  double Hdp[BA_MAX_FREE][27];          // this CTA's share of (Hpp, bp) over its own chunks; rank 0 sums the cluster's shares
   double bp[6 * BA_MAX_FREE];
   double x[6 * BA_MAX_FREE];
   double invd[6 * BA_MAX_FREE];
+  double poses[7 * BA_MAX_POSES];       // the window's poses: every CTA of the cluster keeps (and updates) its own identical copy
+  double pbk[7 * BA_MAX_POSES];         // backup of the poses for a rejected trial
+  double xchg[2][4];                    // cluster all-reduce exchange slots (double-buffered: one cluster barrier per reduction)
+  int rank, C;                          // rank in / size of the window's cluster
+  int c0, c1, l0, l1, s0, s1;           // this CTA's chunks and the landmark / slot (= CSR) ranges they cover
+  // ---- written by setup_active on rank 0 and copied to the other CTAs (contiguous: pidx .. capq) ----
   int pidx[BA_MAX_POSES];
   int pose_of[BA_MAX_FREE];
   int pcount[BA_MAX_POSES];
@@ -224,6 +234,30 @@ struct Sh {   // fixed-size shared state
   long long prof[16], tlast;  // cycle counters: 0 chi2, 1 build (pose pass), 2 schur (pair products), 3 cholesky, 4 substitution,
                               // 5 update, 6 setup, 7 -, 8 schur init + Dinv, 9 schur chunk staging, 10 build edge pass, 11 build landmark pass
 };
+
+// Cluster-wide reductions of up to 4 block-uniform values: every CTA publishes its share in its own shared memory, one cluster
+// barrier, then every CTA sums the shares in rank order through distributed shared memory -- identical result in all CTAs, so
+// the LM control flow stays uniform over the cluster.  Slots alternate (xpar), so a CTA that runs ahead into the next
+// reduction writes the other slot while a slower one still reads this one.
+template <int K, bool MAX>
+__device__ __forceinline__ void cluster_reduce(double (&v)[K], Sh& sh, int& xpar) {
+  if (sh.C == 1) return;
+  cg::cluster_group cl = cg::this_cluster();
+  double* slot = sh.xchg[xpar];
+  xpar ^= 1;
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int i = 0; i < K; ++i) slot[i] = v[i];
+  }
+  cl.sync();
+#pragma unroll
+  for (int i = 0; i < K; ++i) v[i] = 0;
+  for (int r = 0; r < sh.C; ++r) {
+    const double* rs = cl.map_shared_rank(slot, r);
+#pragma unroll
+    for (int i = 0; i < K; ++i) v[i] = MAX ? fmax(v[i], rs[i]) : v[i] + rs[i];
+  }
+}
 
 __device__ __forceinline__ void mark(Sh& sh, int slot) {
   if (threadIdx.x == 0) { const long long now = clock64(); sh.prof[slot] += now - sh.tlast; sh.tlast = now; }
@@ -278,24 +312,27 @@ __device__ void block_exclusive_scan(int* a, int n, Sh& sh) {
 // chi2 over the edge arrays (used outside the LM loop, where no slot tables are required to be valid)
 __device__ double robust_chi2_edges(const flv_ba_problem& pb, const Cam& cam, const double* poses, const double* lms,
                                     const int* ep, const int* el, const double* uv, const uint8_t* act, double delta,
-                                    double* red) {
+                                    Sh& sh, int& xpar) {
   double acc = 0;
   const double d2 = delta * delta;
-  for (int e = threadIdx.x; e < pb.n_edges; e += BA_THREADS) {
+  for (int e = threadIdx.x + sh.rank * BA_THREADS; e < pb.n_edges; e += sh.C * BA_THREADS) {
     if (!act[e]) continue;
     double r[2];
     edge_eval<false>(poses + 7 * ep[e], lms + 3 * el[e], uv + 2 * e, cam, r, nullptr, nullptr);
     const double c = r[0] * r[0] + r[1] * r[1];
     acc += (c <= d2) ? c : 2 * sqrt(c) * delta - d2;
   }
-  return block_sum(acc, red);
+  double v[1] = {block_sum(acc, sh.red)};
+  cluster_reduce<1, false>(v, sh, xpar);
+  return v[0];
 }
 
-// chi2 over the active slots (inside the LM loop): coalesced reads of the slot tables
-__device__ double robust_chi2(const Cam& cam, const double* poses, const double* lms, double delta, Ws& ws, Sh& sh) {
+// chi2 over this CTA's active slots (inside the LM loop): coalesced reads of the slot tables.  Returns the CTA's share;
+// callers reduce over the cluster.
+__device__ double robust_chi2_part(const Cam& cam, const double* poses, const double* lms, double delta, Ws& ws, Sh& sh) {
   double acc = 0;
   const double d2 = delta * delta;
-  for (int s = threadIdx.x; s < sh.nact; s += BA_THREADS) {
+  for (int s = sh.s0 + threadIdx.x; s < sh.s1; s += BA_THREADS) {
     const int pl = ws.slot_pl[s];
     const double2 q2 = CPL2(ws.uvs)[s];
     const double uv[2] = {q2.x, q2.y};
@@ -305,6 +342,11 @@ __device__ double robust_chi2(const Cam& cam, const double* poses, const double*
     acc += (c <= d2) ? c : 2 * sqrt(c) * delta - d2;
   }
   return block_sum(acc, sh.red);
+}
+__device__ double robust_chi2(const Cam& cam, const double* poses, const double* lms, double delta, Ws& ws, Sh& sh, int& xpar) {
+  double v[1] = {robust_chi2_part(cam, poses, lms, delta, ws, sh)};
+  cluster_reduce<1, false>(v, sh, xpar);
+  return v[0];
 }
 
 // Active sets + lookup tables (sparse_optimizer.cpp:168-272 semantics), built once per optimize() phase.
@@ -353,6 +395,15 @@ __device__ void setup_active(const flv_ba_problem& pb, const int* ep, const int*
   __syncthreads();
   block_exclusive_scan(ws.lstart, L, sh);
   block_exclusive_scan(ws.lw, L, sh);
+  // a cluster of C CTAs splits the chunks evenly: shrink the chunks so that their number is (about) a multiple of C
+  if (tid == 0 && sh.C > 1 && !pb.fix_landmarks) {
+    const int Wt = ws.lw[L];
+    int rounds = (Wt + sh.C * sh.capq - 1) / (sh.C * sh.capq);
+    rounds = rounds < 1 ? 1 : rounds;
+    const int cq = Wt / (sh.C * rounds) + 1;
+    if (cq < sh.capq) sh.capq = cq;
+  }
+  __syncthreads();
   // chunk of landmark l = lw[l] / capq: a landmark has <= P edges, so a chunk holds < capq + P = cap weight
   const int capq = pb.fix_landmarks ? 0x3fffffff : sh.capq;
   if (tid == 0) { sh.nch = L > 0 ? ws.lw[L - 1] / capq + 1 : 0; }
@@ -464,6 +515,32 @@ __device__ void setup_active(const flv_ba_problem& pb, const int* ep, const int*
   __syncthreads();
 }
 
+// setup runs on rank 0 of the window's cluster (it writes the global tables); the other CTAs copy the shared-memory part of its
+// result through distributed shared memory.  Then every CTA takes a contiguous run of chunks: all edges of a landmark lie in the
+// landmark's chunk, so a CTA's landmarks, slots and CSR entries are private to it in every pass.
+__device__ void setup_cluster(const flv_ba_problem& pb, const int* ep, const int* el, const double* uv,
+                              const uint8_t* act, int chunk_area_doubles, Ws& ws, Sh& sh) {
+  if (sh.rank == 0) setup_active(pb, ep, el, uv, act, chunk_area_doubles, ws, sh);
+  if (sh.C > 1) {
+    cg::cluster_group cl = cg::this_cluster();
+    cl.sync();
+    if (sh.rank != 0) {
+      const int* src = cl.map_shared_rank(sh.pidx, 0);
+      int* dst = sh.pidx;
+      const int nw = (int)((offsetof(Sh, capq) + sizeof(int) - offsetof(Sh, pidx)) / sizeof(int));
+      for (int i = threadIdx.x; i < nw; i += BA_THREADS) dst[i] = src[i];
+    }
+    cl.sync();
+  }
+  if (threadIdx.x == 0) {
+    const int nch = (sh.np > BA_MAX_FREE || sh.overflow) ? 0 : sh.nch;
+    sh.c0 = (nch * sh.rank) / sh.C; sh.c1 = (nch * (sh.rank + 1)) / sh.C;
+    sh.l0 = nch ? sh.chunk_lb[sh.c0] : 0; sh.l1 = nch ? sh.chunk_lb[sh.c1] : 0;
+    sh.s0 = nch ? sh.chunk_sb[sh.c0] : 0; sh.s1 = nch ? sh.chunk_sb[sh.c1] : 0;
+  }
+  __syncthreads();
+}
+
 // Linearisation.  Pass A: thread per slot (edge): residual, Jacobians, W = rho' B^T A, Bw = sqrt(rho') B,
 // g = -sqrt(rho') r and the edge's share of Hll / bl.  Pass B: thread per landmark sums the shares (pose order).
 // Pass C: warp per (free pose, part of its slot runs): Hpp diagonal block and bp.
@@ -474,7 +551,7 @@ __device__ void build_system(const flv_ba_problem& pb, const Cam& cam, const dou
   const double d2 = delta * delta;
   if (!pb.fix_landmarks) {
     mark(sh, 10);
-    for (int l = tid; l < L; l += BA_THREADS) {
+    for (int l = sh.l0 + tid; l < sh.l1; l += BA_THREADS) {
       const int j0 = ws.lstart[l], j1 = ws.lstart[l + 1];
       if (j0 == j1) continue;
       double H[6] = {0, 0, 0, 0, 0, 0}, b[3] = {0, 0, 0};
@@ -502,13 +579,13 @@ __device__ void build_system(const flv_ba_problem& pb, const Cam& cam, const dou
     mark(sh, 11);
   }
   // pose diagonal blocks: task = (free pose, split part); a part owns a contiguous range of chunks
-  const int np = sh.np, nch = sh.nch, P1 = P + 1;
+  const int np = sh.np, nch = sh.c1 - sh.c0, P1 = P + 1;       // this CTA's chunks
   int split = BA_WARPS / (np > 0 ? np : 1);               // (4 parts per pose measured slower than 1: 0.80 M vs 0.68 M cycles)
   split = split < 1 ? 1 : (split > 4 ? 4 : split);
   if (split > nch) split = nch > 0 ? nch : 1;
   for (int task = warp; task < np * split; task += BA_WARPS) {
     const int pi = task / split, part = task - pi * split, p = sh.pose_of[pi];
-    const int c0 = (nch * part) / split, c1 = (nch * (part + 1)) / split;
+    const int c0 = sh.c0 + (nch * part) / split, c1 = sh.c0 + (nch * (part + 1)) / split;
     double H[21], b[6];
 #pragma unroll
     for (int i = 0; i < 21; ++i) H[i] = 0;
@@ -549,7 +626,20 @@ __device__ void build_system(const flv_ba_problem& pb, const Cam& cam, const dou
     const int pi = i / 27, k = i - 27 * pi;
     double v = 0;
     for (int part = 0; part < split; ++part) v += sh.part[pi * split + part][k];
-    if (k < 21) sh.Hd[pi][k] = v; else sh.bp[6 * pi + k - 21] = v;
+    sh.Hdp[pi][k] = v;
+  }
+  // the pose blocks live on rank 0 (it owns the reduced system): sum the cluster's shares in rank order
+  if (sh.C > 1) cg::this_cluster().sync(); else __syncthreads();
+  if (sh.rank == 0) {
+    for (int i = tid; i < np * 27; i += BA_THREADS) {
+      const int pi = i / 27, k = i - 27 * pi;
+      double v = sh.Hdp[pi][k];
+      if (sh.C > 1) {
+        cg::cluster_group cl = cg::this_cluster();
+        for (int r = 1; r < sh.C; ++r) v += cl.map_shared_rank(&sh.Hdp[pi][k], r)[0];
+      }
+      if (k < 21) sh.Hd[pi][k] = v; else sh.bp[6 * pi + k - 21] = v;
+    }
   }
   __syncthreads();
 }
@@ -564,17 +654,20 @@ __device__ void solve_system(const flv_ba_problem& pb, const Cam& cam, const dou
   const int np = sh.np, n = 6 * np, ME = ws.ME, ML = ws.ML;
   const int nblk = np * (np + 1) / 2;
   // reduced system starts as the pose blocks (+ lambda); the chunks subtract W Dinv W^T from it
+  // (in a cluster every CTA accumulates the products of its own chunks into its own S / y; rank 0 adds them up below)
   for (int i = tid; i < n * ld; i += BA_THREADS) S[i] = 0;
   __syncthreads();
-  for (int i = tid; i < np * 36; i += BA_THREADS) {
-    const int pi = i / 36, k = i - 36 * pi, r = k / 6, c = k - 6 * r;
-    double v = sh.Hd[pi][r <= c ? sym21(r, c) : sym21(c, r)];
-    if (r == c) v += lambda;
-    S[(6 * pi + r) * ld + 6 * pi + c] = v;
+  if (sh.rank == 0) {
+    for (int i = tid; i < np * 36; i += BA_THREADS) {
+      const int pi = i / 36, k = i - 36 * pi, r = k / 6, c = k - 6 * r;
+      double v = sh.Hd[pi][r <= c ? sym21(r, c) : sym21(c, r)];
+      if (r == c) v += lambda;
+      S[(6 * pi + r) * ld + 6 * pi + c] = v;
+    }
   }
-  if (tid < n) y[tid] = sh.bp[tid];
+  if (tid < n) y[tid] = sh.rank == 0 ? sh.bp[tid] : 0.0;
   if (!pb.fix_landmarks) {
-    for (int l = tid; l < L; l += BA_THREADS) {
+    for (int l = sh.l0 + tid; l < sh.l1; l += BA_THREADS) {
       if (!ws.lmask[l]) continue;
       const double a = ws.Hll[l] + lambda, b = ws.Hll[ML + l], c = ws.Hll[2 * ML + l], d = ws.Hll[3 * ML + l] + lambda,
                    e = ws.Hll[4 * ML + l], f = ws.Hll[5 * ML + l] + lambda;
@@ -597,7 +690,7 @@ __device__ void solve_system(const flv_ba_problem& pb, const Cam& cam, const dou
     const int cap = sh.cap;
     double* Zc = chunk;                   // [18][cap]  Z = W Ld of the chunk's slots
     double* Vc = chunk + 18 * cap;        // [3][cap]   Ld^T bl of the chunk's landmarks
-    for (int ch = 0; ch < sh.nch; ++ch) {
+    for (int ch = sh.c0; ch < sh.c1; ++ch) {
       const int sb = sh.chunk_sb[ch], ns = sh.chunk_sb[ch + 1] - sb, lb = sh.chunk_lb[ch], nl = sh.chunk_lb[ch + 1] - lb;
       // member-list bounds of every pose pair for this chunk -> shared memory; tasks are drawn dynamically below
       for (int i = tid; i <= nblk; i += BA_THREADS) sh.task_bounds[i] = ws.poff[ch * nblk + i];
@@ -695,11 +788,29 @@ __device__ void solve_system(const flv_ba_problem& pb, const Cam& cam, const dou
     }
   }
   if (tid == 0) sh.fail = 0;
+  if (sh.C > 1) {
+    // reduced system = sum of the cluster's shares (lower triangle + right-hand side), added in rank order on rank 0
+    cg::cluster_group cl = cg::this_cluster();
+    cl.sync();
+    if (sh.rank == 0) {
+      for (int i = tid; i < n * ld + n; i += BA_THREADS) {
+        const int r = i / ld, c = i - r * ld;
+        if (i < n * ld && c > r) continue;                    // upper triangle is never read (y follows S: rows n.. are y)
+        double* dst = i < n * ld ? S + i : y + (i - n * ld);
+        double v = *dst;
+        for (int q = 1; q < sh.C; ++q) v += *cl.map_shared_rank(dst, q);
+        *dst = v;
+      }
+    }
+  }
   __syncthreads();
   mark(sh, 2);
+  if (sh.rank == 0) {
   // Right-looking Cholesky (LDL^T form) of the augmented matrix [S ; y^T] (row n = right-hand side): one barrier per
   // column, no square roots -- after step j column j holds A_ij = L_ij sqrt(d_j), the diagonal d_j = L_jj^2, and
   //   x_j = (y_j - sum_{k>j} A_kj x_k) / d_j.
+  // (re-spreading the threads over the live rows in every step measured slower: 1.25 M vs 0.93 M cycles per window -- the
+  // step is bound by its fixed latency, barrier + dependent shared-memory loads, not by the trailing update)
   int T = BA_THREADS / (n + 1);                   // threads per row (no shuffles here: any count works)
   T = T < 1 ? 1 : (T > 32 ? 32 : T);
   const int row = tid / T, t = tid - row * T;
@@ -745,6 +856,16 @@ __device__ void solve_system(const flv_ba_problem& pb, const Cam& cam, const dou
       if (lane == 0) sh.x[j] = xj;
     }
   }
+  }   // rank 0
+  if (sh.C > 1) {
+    // the increment of the poses (and the failure flag) go back to every CTA
+    cg::cluster_group cl = cg::this_cluster();
+    cl.sync();
+    if (sh.rank != 0) {
+      if (tid < n) sh.x[tid] = cl.map_shared_rank(sh.x, 0)[tid];
+      if (tid == 0) sh.fail = *cl.map_shared_rank(&sh.fail, 0);
+    }
+  }
   __syncthreads();
   mark(sh, 4);
 }
@@ -753,17 +874,18 @@ __device__ void solve_system(const flv_ba_problem& pb, const Cam& cam, const dou
 // Returns sum_j x_j (lambda x_j + b_j) (computeScale, optimization_algorithm_levenberg.cpp:168-175).
 __device__ double apply_update(const flv_ba_problem& pb, const Cam& cam, double delta, double lambda, double* poses, double* lms,
                                double* scratch, int scratch_doubles, Ws& ws, Sh& sh) {
-  const int P = pb.n_poses, L = pb.n_landmarks, tid = threadIdx.x, ME = ws.ME, ML = ws.ML;
+  const int P = pb.n_poses, tid = threadIdx.x, ML = ws.ML;
   double sc = 0;
-  for (int i = tid; i < 7 * P; i += BA_THREADS) ws.pbk[i] = poses[i];
+  for (int i = tid; i < 7 * P; i += BA_THREADS) sh.pbk[i] = poses[i];
   if (!pb.fix_landmarks) {
     // thread per landmark: c = bl - sum_edges W^T x_p with W recomputed per edge (poses are still the linearisation point:
     // they move after the barrier below; a thread only writes its own landmark), dX = Dinv c
     const double d2 = delta * delta;
-    const bool in_smem = 3 * sh.nact <= scratch_doubles;      // t_j = W_j^T x_p of every CSR entry fits the (idle) chunk area
+    const int jb = sh.s0, nown = sh.s1 - sh.s0;               // this CTA's CSR entries (= its slot range: same landmarks)
+    const bool in_smem = 3 * nown <= scratch_doubles;         // t_j = W_j^T x_p of every own CSR entry fits the (idle) chunk area
     if (in_smem) {
       // thread per CSR entry: no divergence over the landmarks' edge counts, coalesced luv / csr_p reads
-      for (int j = tid; j < sh.nact; j += BA_THREADS) {
+      for (int j = jb + tid; j < sh.s1; j += BA_THREADS) {
         const int p = ws.csr_p[j], pi = sh.pidx[p];
         double t0 = 0, t1 = 0, t2 = 0;
         if (pi >= 0) {
@@ -776,11 +898,11 @@ __device__ double apply_update(const flv_ba_problem& pb, const Cam& cam, double 
 #pragma unroll
           for (int i = 0; i < 6; ++i) { t0 += w[3 * i] * xp[i]; t1 += w[3 * i + 1] * xp[i]; t2 += w[3 * i + 2] * xp[i]; }
         }
-        scratch[j] = t0; scratch[sh.nact + j] = t1; scratch[2 * sh.nact + j] = t2;
+        scratch[j - jb] = t0; scratch[nown + j - jb] = t1; scratch[2 * nown + j - jb] = t2;
       }
       __syncthreads();
     }
-    for (int l = tid; l < L; l += BA_THREADS) {
+    for (int l = sh.l0 + tid; l < sh.l1; l += BA_THREADS) {
       double* X = lms + 3 * (size_t)l;
       const double X0[3] = {X[0], X[1], X[2]};
       ws.lbk[3 * (size_t)l] = X0[0]; ws.lbk[3 * (size_t)l + 1] = X0[1]; ws.lbk[3 * (size_t)l + 2] = X0[2];
@@ -789,7 +911,7 @@ __device__ double apply_update(const flv_ba_problem& pb, const Cam& cam, double 
       const double bl0 = ws.bl[l], bl1 = ws.bl[ML + l], bl2 = ws.bl[2 * ML + l];
       double c0 = bl0, c1 = bl1, c2 = bl2;
       if (in_smem) {
-        for (int j = j0; j < j1; ++j) { c0 -= scratch[j]; c1 -= scratch[sh.nact + j]; c2 -= scratch[2 * sh.nact + j]; }
+        for (int j = j0 - jb; j < j1 - jb; ++j) { c0 -= scratch[j]; c1 -= scratch[nown + j]; c2 -= scratch[2 * nown + j]; }
       } else
       for (int j = j0; j < j1; ++j) {
         const int p = ws.csr_p[j], pi = sh.pidx[p];
@@ -811,16 +933,16 @@ __device__ double apply_update(const flv_ba_problem& pb, const Cam& cam, double 
       X[0] += x0; X[1] += x1; X[2] += x2;
     }
   }
-  if (tid < 6 * sh.np) sc += sh.x[tid] * (lambda * sh.x[tid] + sh.bp[tid]);
+  if (sh.rank == 0 && tid < 6 * sh.np) sc += sh.x[tid] * (lambda * sh.x[tid] + sh.bp[tid]);
   __syncthreads();     // backups of poses complete before anyone overwrites
-  if (tid < sh.np) pose_oplus(poses + 7 * sh.pose_of[tid], sh.x + 6 * tid);
-  return block_sum(sc, sh.red);
+  if (tid < sh.np) pose_oplus(poses + 7 * sh.pose_of[tid], sh.x + 6 * tid);     // every CTA moves its own copy of the poses
+  return block_sum(sc, sh.red);      // this CTA's share
 }
 
-__device__ void restore_state(const flv_ba_problem& pb, double* poses, double* lms, Ws& ws) {
-  for (int i = threadIdx.x; i < 7 * pb.n_poses; i += BA_THREADS) poses[i] = ws.pbk[i];
+__device__ void restore_state(const flv_ba_problem& pb, double* poses, double* lms, Ws& ws, Sh& sh) {
+  for (int i = threadIdx.x; i < 7 * pb.n_poses; i += BA_THREADS) poses[i] = sh.pbk[i];
   if (!pb.fix_landmarks)
-    for (int i = threadIdx.x; i < 3 * pb.n_landmarks; i += BA_THREADS) lms[i] = ws.lbk[i];
+    for (int i = 3 * sh.l0 + threadIdx.x; i < 3 * sh.l1; i += BA_THREADS) lms[i] = ws.lbk[i];
   __syncthreads();
 }
 
@@ -853,10 +975,14 @@ __host__ __device__ inline WsLayout ws_layout(int MP, int ML, int ME) {
 __global__ void __launch_bounds__(BA_THREADS, 1) ba_kernel(BAArgs a) {
   extern __shared__ double dyn[];
   __shared__ Sh sh;
-  const int s = blockIdx.x, tid = threadIdx.x;
+  cg::cluster_group cluster = cg::this_cluster();
+  const int C = (int)cluster.num_blocks(), rank = (int)cluster.block_rank();     // C CTAs (1, 2 or 4) work on one window
+  const int s = blockIdx.x / C, tid = threadIdx.x;
+  int xpar = 0;
   const flv_ba_problem pb = a.problems[s];
   const Cam cam = {pb.fx, pb.fy, pb.cx, pb.cy};
-  double* poses = a.poses + (size_t)s * a.max_poses * 7;
+  double* poses_g = a.poses + (size_t)s * a.max_poses * 7;
+  double* poses = sh.poses;                         // the LM loop works on the shared-memory copy
   double* lms = a.lms + (size_t)s * a.max_lms * 3;
   const int* ep = a.ep + (size_t)s * a.max_edges;
   const int* el = a.el + (size_t)s * a.max_edges;
@@ -880,15 +1006,17 @@ __global__ void __launch_bounds__(BA_THREADS, 1) ba_kernel(BAArgs a) {
   st.iterations_run = 0; st.n_culled = 0; st.ok = 1; st.reserved = 0;
   st.chi2_initial = st.chi2_after1 = st.chi2_final = 0; st.lambda_final = 0;
   if (P < 1 || P > BA_MAX_POSES || E < 0) {
-    if (tid == 0) { st.ok = 0; st.reserved = 1; a.stats[s] = st; }
+    if (tid == 0 && rank == 0) { st.ok = 0; st.reserved = 1; a.stats[s] = st; }
     return;
   }
-  if (tid == 0) { for (int i = 0; i < 16; ++i) sh.prof[i] = 0; sh.tlast = clock64(); }
-  st.chi2_initial = robust_chi2_edges(pb, cam, poses, lms, ep, el, uv, act, delta, sh.red);
+  if (tid == 0) { for (int i = 0; i < 16; ++i) sh.prof[i] = 0; sh.tlast = clock64(); sh.rank = rank; sh.C = C; }
+  for (int i = tid; i < 7 * P; i += BA_THREADS) sh.poses[i] = poses_g[i];
+  __syncthreads();
+  st.chi2_initial = robust_chi2_edges(pb, cam, poses, lms, ep, el, uv, act, delta, sh, xpar);
   double lambda = 0;
   for (int phase = 0; phase < 2; ++phase) {
     const int iters = phase == 0 ? a.prm.iters1 : a.prm.iters2;
-    setup_active(pb, ep, el, uv, act, a.dyn_doubles, ws, sh);
+    setup_cluster(pb, ep, el, uv, act, a.dyn_doubles, ws, sh);
     mark(sh, 6);
     if (sh.np > BA_MAX_FREE) { st.ok = 0; st.reserved = 2; break; }
     if (sh.overflow) { st.ok = 0; st.reserved = sh.overflow == 1 ? 3 : 4; break; }
@@ -901,20 +1029,22 @@ __global__ void __launch_bounds__(BA_THREADS, 1) ba_kernel(BAArgs a) {
     for (int it = 0; it < iters; ++it) {
       // g2o recomputes activeRobustChi2 at the start of every iteration; the state only changes through accepted trials
       // (whose chi2 was just computed by the same code on the same state), so the value is carried over bit-identically
-      if (it == 0) currentChi = robust_chi2(cam, poses, lms, delta, ws, sh);
+      if (it == 0) currentChi = robust_chi2(cam, poses, lms, delta, ws, sh, xpar);
       mark(sh, 0);
       build_system(pb, cam, poses, lms, delta, ws, sh);
       mark(sh, 1);
       if (it == 0) {
         double md = 0;
-        if (tid < sh.np) {
+        if (rank == 0 && tid < sh.np) {
 #pragma unroll
           for (int i = 0; i < 6; ++i) md = fmax(md, fabs(sh.Hd[tid][sym21(i, i)]));
         }
         if (!pb.fix_landmarks)
-          for (int l = tid; l < pb.n_landmarks; l += BA_THREADS)
+          for (int l = sh.l0 + tid; l < sh.l1; l += BA_THREADS)
             if (ws.lmask[l]) md = fmax(md, fmax(fabs(ws.Hll[l]), fmax(fabs(ws.Hll[3 * ws.ML + l]), fabs(ws.Hll[5 * ws.ML + l]))));
-        lambda = 1e-5 * block_max(md, sh.red);
+        double mv[1] = {block_max(md, sh.red)};
+        cluster_reduce<1, true>(mv, sh, xpar);
+        lambda = 1e-5 * mv[0];
         ni = 2;
       }
       double rho = 0;
@@ -924,10 +1054,13 @@ __global__ void __launch_bounds__(BA_THREADS, 1) ba_kernel(BAArgs a) {
         const int ok2 = !sh.fail;
         double scale = 0, tempChi;
         if (ok2) {
-          scale = apply_update(pb, cam, delta, lambda, poses, lms, chunk, a.dyn_doubles - (n * ld + ((n + 8) & ~1)), ws, sh);
+          double sv[2];
+          sv[0] = apply_update(pb, cam, delta, lambda, poses, lms, chunk, a.dyn_doubles - (n * ld + ((n + 8) & ~1)), ws, sh);
           __syncthreads();
           mark(sh, 5);
-          tempChi = robust_chi2(cam, poses, lms, delta, ws, sh);
+          sv[1] = robust_chi2_part(cam, poses, lms, delta, ws, sh);
+          cluster_reduce<2, false>(sv, sh, xpar);       // one cluster barrier for both sums
+          scale = sv[0]; tempChi = sv[1];
           mark(sh, 0);
         } else {
           tempChi = 1.7976931348623157e308;
@@ -941,12 +1074,12 @@ __global__ void __launch_bounds__(BA_THREADS, 1) ba_kernel(BAArgs a) {
           currentChi = tempChi;
         } else {
           lambda *= ni; ni *= 2;
-          if (ok2) restore_state(pb, poses, lms, ws);
+          if (ok2) restore_state(pb, poses, lms, ws, sh);
           if (!isfinite(lambda)) break;
         }
         ++qmax;
       } while (rho < 0 && qmax < 10);
-      if (a.trace && tid == 0 && st.iterations_run < BA_TRACE_ITERS) {
+      if (a.trace && tid == 0 && rank == 0 && st.iterations_run < BA_TRACE_ITERS) {
         double* tr = a.trace + ((size_t)s * BA_TRACE_ITERS + st.iterations_run) * 4;
         tr[0] = currentChi; tr[1] = lambda; tr[2] = rho; tr[3] = (double)qmax;
       }
@@ -954,10 +1087,10 @@ __global__ void __launch_bounds__(BA_THREADS, 1) ba_kernel(BAArgs a) {
       if (qmax == 10 || rho == 0 || !isfinite(lambda)) break;
     }
     if (phase == 0) {
-      st.chi2_after1 = robust_chi2(cam, poses, lms, delta, ws, sh);
+      st.chi2_after1 = robust_chi2(cam, poses, lms, delta, ws, sh, xpar);
       // cull: un-robustified chi2 > threshold (vo_localmap.cpp:303-316, optimize_in_frame.cpp:67-74)
       int culled = 0, remaining = 0;
-      for (int sl = tid; sl < sh.nact; sl += BA_THREADS) {
+      for (int sl = sh.s0 + tid; sl < sh.s1; sl += BA_THREADS) {
         const int pl = ws.slot_pl[sl];
         const double2 q2 = CPL2(ws.uvs)[sl];
         const double uvv[2] = {q2.x, q2.y};
@@ -965,18 +1098,27 @@ __global__ void __launch_bounds__(BA_THREADS, 1) ba_kernel(BAArgs a) {
         edge_eval<false>(poses + 7 * (pl & 255), lms + 3 * (size_t)(pl >> 8), uvv, cam, r, nullptr, nullptr);
         if (r[0] * r[0] + r[1] * r[1] > a.prm.cull_chi2) { act[ws.slot_e[sl]] = 0; ++culled; } else ++remaining;
       }
-      st.n_culled = (int)(block_sum((double)culled, sh.red) + 0.5);
-      const int rem = (int)(block_sum((double)remaining, sh.red) + 0.5);
+      double cv[2];
+      cv[0] = block_sum((double)culled, sh.red);
+      cv[1] = block_sum((double)remaining, sh.red);
+      cluster_reduce<2, false>(cv, sh, xpar);           // (its barrier also publishes the cleared `active` flags to rank 0's next setup)
+      st.n_culled = (int)(cv[0] + 0.5);
+      const int rem = (int)(cv[1] + 0.5);
       __syncthreads();
       if (rem < a.prm.min_edges_after_cull) { st.ok = 0; break; }
     }
   }
-  st.chi2_final = robust_chi2_edges(pb, cam, poses, lms, ep, el, uv, act, delta, sh.red);
+  if (C > 1) cluster.sync();                            // every CTA's landmarks are in global memory before the final chi2 reads them
+  st.chi2_final = robust_chi2_edges(pb, cam, poses, lms, ep, el, uv, act, delta, sh, xpar);
   st.lambda_final = lambda;
-  if (tid == 0) {
-    a.stats[s] = st;
-    if (a.prof) for (int i = 0; i < 16; ++i) a.prof[16 * s + i] = sh.prof[i];
+  if (rank == 0) {
+    for (int i = tid; i < 7 * P; i += BA_THREADS) poses_g[i] = sh.poses[i];
+    if (tid == 0) {
+      a.stats[s] = st;
+      if (a.prof) for (int i = 0; i < 16; ++i) a.prof[16 * s + i] = sh.prof[i];
+    }
   }
+  if (C > 1) cluster.sync();                            // no CTA leaves while another may still read its shared memory
 }
 
 __global__ void ba_debug_edges_kernel(int n, const double* poses, const double* pts, const double* uv, Cam cam, double* out) {
@@ -1002,6 +1144,28 @@ int ba_dyn_doubles() {
   if (cudaFuncGetAttributes(&fa, ba_kernel) != cudaSuccess) return 0;
   const long avail = 232448L - (long)fa.sharedSizeBytes - 1024;   // 227 KB per block on sm_100
   return (int)(avail / 8);
+}
+
+// one cluster of C CTAs per window (C = 1: plain launch semantics, same kernel)
+cudaError_t launch_ba(const BAArgs& a, int n_streams, int C, size_t smem, cudaStream_t stream) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)(n_streams * C)); cfg.blockDim = dim3(BA_THREADS);
+  cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = (unsigned)C; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+  cfg.attrs = at; cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, ba_kernel, a);
+}
+
+// CTAs per window: FLV_BA_CLUSTER / flv_set_ba_cluster (1, 2 or 4; default 4) for windows that optimise landmarks, 1 for pose-only
+int ba_cluster_size(flv_ctx* ctx) {
+  if (ctx->ba_cluster <= 0) {
+    const char* e = getenv("FLV_BA_CLUSTER");
+    const int v = e ? atoi(e) : 4;
+    ctx->ba_cluster = (v == 1 || v == 2 || v == 4) ? v : 4;
+  }
+  return ctx->ba_cluster;
 }
 
 }  // namespace
@@ -1067,11 +1231,15 @@ int flv_ba_optimize(flv_ctx* ctx, int n_streams, const flv_ba_problem* problems,
   if (mem == FLV_MEM_DEVICE) {
     a.problems = problems; a.poses = poses; a.lms = landmarks; a.ep = edge_pose; a.el = edge_lm; a.uv = edge_uv;
     a.active = edge_active; a.stats = stats;
-    ba_kernel<<<n_streams, BA_THREADS, smem, stream>>>(a);
+    // device-resident problems cannot be inspected here: one CTA per window unless the caller asked for clusters
+    FLV_CUDA(ctx, launch_ba(a, n_streams, ctx->ba_cluster_device > 0 ? ctx->ba_cluster_device : 1, smem, stream));
     ctx->launches++;
     FLV_CUDA(ctx, cudaGetLastError());
     return FLV_OK;
   }
+  int C = 1;
+  for (int s = 0; s < n_streams; ++s)
+    if (!problems[s].fix_landmarks && problems[s].n_poses >= 3) C = ba_cluster_size(ctx);
   for (int s = 0; s < n_streams; ++s) {
     const flv_ba_problem& p = problems[s];
     if (p.n_poses < 1 || p.n_poses > MP || p.n_landmarks < 0 || p.n_landmarks > ML || p.n_edges < 0 || p.n_edges > ME)
@@ -1091,7 +1259,7 @@ int flv_ba_optimize(flv_ctx* ctx, int n_streams, const flv_ba_problem* problems,
   FLV_CUDA(ctx, cudaMemcpyAsync(d_prob, problems, S * sizeof(flv_ba_problem), cudaMemcpyHostToDevice, stream));
   a.problems = d_prob; a.poses = (double*)(ds + o_pose); a.lms = (double*)(ds + o_lm); a.uv = (const double*)(ds + o_uv);
   a.ep = (const int*)(ds + o_ep); a.el = (const int*)(ds + o_el); a.active = (uint8_t*)(ds + o_act); a.stats = d_stats;
-  ba_kernel<<<n_streams, BA_THREADS, smem, stream>>>(a);
+  FLV_CUDA(ctx, launch_ba(a, n_streams, C, smem, stream));
   ctx->launches++;
   FLV_CUDA(ctx, cudaGetLastError());
   FLV_CUDA(ctx, cudaMemcpyAsync(hs + o_pose, ds + o_pose, b_pose + b_lm, cudaMemcpyDeviceToHost, stream));
@@ -1103,6 +1271,16 @@ int flv_ba_optimize(flv_ctx* ctx, int n_streams, const flv_ba_problem* problems,
     if (stats[s].reserved)
       FLV_FAIL(ctx, FLV_ERR_UNSUPPORTED, "stream %d: %s", s,
                stats[s].reserved == 1 ? "pose count outside [1,32]" : stats[s].reserved == 2 ? "more than 24 free poses (reduced system > 144)" : stats[s].reserved == 3 ? "pose-pair list capacity exceeded" : "window too large for the shared-memory landmark chunks");
+  return FLV_OK;
+}
+
+/* CTAs (thread-block cluster size) per window: 1, 2 or 4.  host_mode_cluster applies to FLV_MEM_HOST calls whose problems
+ * optimise landmarks (default 4; pose-only problems always use 1); device_mode_cluster to FLV_MEM_DEVICE calls (default 1). */
+int flv_set_ba_cluster(flv_ctx* ctx, int host_mode_cluster, int device_mode_cluster) {
+  if (!ctx) return FLV_ERR_INVALID;
+  auto ok = [](int v) { return v == 1 || v == 2 || v == 4; };
+  if (!ok(host_mode_cluster) || !ok(device_mode_cluster)) FLV_FAIL(ctx, FLV_ERR_INVALID, "cluster size must be 1, 2 or 4");
+  ctx->ba_cluster = host_mode_cluster; ctx->ba_cluster_device = device_mode_cluster;
   return FLV_OK;
 }
 

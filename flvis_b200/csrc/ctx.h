@@ -37,6 +37,7 @@ struct flv_ctx {
   int equalize; int* d_hist;     // cv::equalizeHist on ingest (flv_set_equalize_hist)
   int attr_lk3, attr_lk4, attr_region;     // cudaFuncSetAttribute done for this context's device
   int ba_dyn;                              // cached dynamic shared memory of ba_kernel (doubles)
+  int ba_cluster, ba_cluster_device;       // CTAs per window for FLV_MEM_HOST / FLV_MEM_DEVICE solves (0 = default)
   int no_fused_ingest;           // FLV_NO_FUSED_INGEST=1: A/B switch for tests
   char err[512];
 

@@ -60,6 +60,39 @@ void CameraFrame::getKeyFrameInf(std::vector<int64_t>& lm_id, std::vector<Vec2>&
     if (lm.has_3d && lm.is_tracking_inlier) { lm_3d.push_back(lm.lm_3d_w); lm_2d.push_back(lm.lm_2d_undistort); lm_id.push_back(lm.lm_id); }
 }
 
+// ---- DepthCamera ---------------------------------------------------------------------------------
+void DepthCamera::setDepthCamInfo(int w_in, int h_in, double fx, double fy, double cx, double cy, double scale_factor, int cam_type_in) {
+  img_w = w_in; img_h = h_in;
+  cam0_fx = fx; cam0_fy = fy; cam0_cx = cx; cam0_cy = cy;
+  lens0 = LensModel();                                             // K0_rect = K, D0_rect = 0 (depth_camera.cpp:20-22)
+  lens0.fx = fx; lens0.fy = fy; lens0.cx = cx; lens0.cy = cy;
+  lens0.P[0] = fx; lens0.P[2] = cx; lens0.P[5] = fy; lens0.P[6] = cy;
+  for (int i = 0; i < 12; ++i) P0_[i] = lens0.P[i];
+  cam_scale_factor = scale_factor;
+  cam_type = cam_type_in;
+}
+void DepthCamera::setSteroCamInfo(int w_in, int h_in, const double* K0_in, const double* D0_in, int nD0, const double*, const double*,
+                                  const double* R0_in, const double* P0_in, const double* K1_in, const double* D1_in, int nD1,
+                                  const double*, const double*, const double* R1_in, const double* P1_in, const SE3& T_c0_c1_in,
+                                  int cam_type_in) {
+  img_w = w_in; img_h = h_in;
+  auto fill = [](LensModel& m, const double* K, const double* D, int nD, const double* R, const double* P) {
+    m = LensModel();
+    m.fx = K[0]; m.fy = K[4]; m.cx = K[2]; m.cy = K[5];
+    for (int i = 0; i < nD && i < 14; ++i) m.k[i] = D[i];
+    for (int i = 0; i < 9; ++i) m.R[i] = R[i];
+    for (int i = 0; i < 12; ++i) m.P[i] = P[i];
+  };
+  fill(lens0, K0_in, D0_in, nD0, R0_in, P0_in);
+  fill(lens1, K1_in, D1_in, nD1, R1_in, P1_in);
+  T_cam0_cam1 = T_c0_c1_in;
+  T_cam1_cam0 = T_cam0_cam1.inverse();
+  for (int i = 0; i < 12; ++i) { P0_[i] = P0_in[i]; P1_[i] = P1_in[i]; }
+  cam0_fx = P0_[0]; cam0_fy = P0_[5]; cam0_cx = P0_[2]; cam0_cy = P0_[6];     // depth_camera.cpp:73-82
+  cam1_fx = P1_[0]; cam1_fy = P1_[5]; cam1_cx = P1_[2]; cam1_cy = P1_[6];
+  cam_type = cam_type_in;
+}
+
 // ---- F2FTracking ---------------------------------------------------------------------------------
 F2FTracking::F2FTracking() {}
 F2FTracking::~F2FTracking() { delete vimotion; delete feature_dem; delete lkorb_tracker; if (ctx_) flv_destroy(ctx_); }

@@ -38,6 +38,16 @@ struct DepthCamera {
   double P0_[12] = {0}, P1_[12] = {0};                          // rectified projection matrices, row-major 3x4
   SE3 T_cam1_cam0;
   LensModel lens0, lens1;                                       // K0/D0/R0/P0, K1/D1/R1/P1 (STEREO_UNRECT: raw lens models)
+  // DepthCamera::setDepthCamInfo (depth_camera.cpp:6-25): pinhole D435 colour camera + depth scale; K0_rect = K, D0_rect = 0
+  void setDepthCamInfo(int w_in, int h_in, double fx, double fy, double cx, double cy, double scale_factor, int cam_type_in = DEPTH_D435);
+  // DepthCamera::setSteroCamInfo (depth_camera.cpp:27-90), cv::Mat arguments as row-major arrays: K 3x3, D up to 14 OpenCV
+  // coefficients (nD given), R 3x3, P 3x4.  K*_rect / D*_rect are accepted for signature parity (the reference stores them and
+  // never reads them on the hot path: K_rect is the 3x3 part of P, D_rect is zero).  cam0/cam1 intrinsics come from P0 / P1.
+  void setSteroCamInfo(int w_in, int h_in, const double* K0_in, const double* D0_in, int nD0, const double* K0_rect_in,
+                       const double* D0_rect_in, const double* R0_in, const double* P0_in, const double* K1_in, const double* D1_in,
+                       int nD1, const double* K1_rect_in, const double* D1_rect_in, const double* R1_in, const double* P1_in,
+                       const SE3& T_c0_c1_in, int cam_type_in);
+  SE3 T_cam0_cam1;
   Vec2 camera2pixel(const Vec3& p_c) const { return Vec2{cam0_fx * p_c[0] / p_c[2] + cam0_cx, cam0_fy * p_c[1] / p_c[2] + cam0_cy}; }
   static Vec3 world2cameraT_c_w(const Vec3& p_w, const SE3& T) { const Vec3 r = q_rot(T.q, p_w); return Vec3{r[0] + T.t[0], r[1] + T.t[1], r[2] + T.t[2]}; }
   static Vec3 camera2worldT_c_w(const Vec3& p_c, const SE3& T) { const SE3 Ti = T.inverse(); const Vec3 r = q_rot(Ti.q, p_c); return Vec3{r[0] + Ti.t[0], r[1] + Ti.t[1], r[2] + Ti.t[2]}; }

@@ -131,6 +131,31 @@ flv_f2f* flv_f2f_create(const flv_f2f_config* c, int device) {
   }
   return f;
 }
+static flv::DepthCamera stereo_camera(const flv_f2f_stereo_config* c) {
+  flv::DepthCamera dc;
+  const double zero4[4] = {0, 0, 0, 0};
+  const double Kr0[9] = {c->P0[0], c->P0[1], c->P0[2], c->P0[4], c->P0[5], c->P0[6], c->P0[8], c->P0[9], c->P0[10]};
+  const double Kr1[9] = {c->P1[0], c->P1[1], c->P1[2], c->P1[4], c->P1[5], c->P1[6], c->P1[8], c->P1[9], c->P1[10]};
+  dc.setSteroCamInfo(c->img_w, c->img_h, c->K0, c->D0, 14, Kr0, zero4, c->R0, c->P0, c->K1, c->D1, 14, Kr1, zero4, c->R1, c->P1,
+                     se3_from7(c->T_c0_c1), c->cam_type == 1 ? flv::STEREO_RECT : flv::STEREO_UNRECT);
+  return dc;
+}
+flv_f2f* flv_f2f_create_stereo(const flv_f2f_stereo_config* c, int device) {
+  if (!c || (c->cam_type != 1 && c->cam_type != 2) || c->D0[12] != 0 || c->D0[13] != 0 || c->D1[12] != 0 || c->D1[13] != 0) return nullptr;
+  flv_f2f* f = new (std::nothrow) flv_f2f();
+  if (!f) return nullptr;
+  f->impl.init(stereo_camera(c), se3_from7(c->T_i_c0), c->feature_para, c->vi_para, c->dc_para, c->skip_first_n_imgs,
+               c->need_equal_hist != 0, device);     // on failure the object stays so that the caller can read last_error
+  return f;
+}
+int flv_host_stereo_cam_info(const flv_f2f_stereo_config* c, double* cam0_4, double* cam1_4, double* T_cam1_cam0_7) {
+  if (!c || !cam0_4 || !cam1_4 || !T_cam1_cam0_7) return FLV_ERR_INVALID;
+  const flv::DepthCamera dc = stereo_camera(c);
+  cam0_4[0] = dc.cam0_fx; cam0_4[1] = dc.cam0_fy; cam0_4[2] = dc.cam0_cx; cam0_4[3] = dc.cam0_cy;
+  cam1_4[0] = dc.cam1_fx; cam1_4[1] = dc.cam1_fy; cam1_4[2] = dc.cam1_cx; cam1_4[3] = dc.cam1_cy;
+  se3_to7(dc.T_cam1_cam0, T_cam1_cam0_7);
+  return FLV_OK;
+}
 void flv_f2f_destroy(flv_f2f* f) { delete f; }
 int flv_f2f_set_lens(flv_f2f* f, int cam, const double* K4, const double* D14, const double* R9) {
   if (!f || (cam != 0 && cam != 1) || !K4 || !D14 || !R9) return FLV_ERR_INVALID;

@@ -241,6 +241,11 @@ int flv_pnp_ransac(flv_ctx* ctx, int n_streams, const int* n_pts, const float* p
  * FLVIS's separate local-map thread: the BA of keyframe k overlaps the tracking of the following frames.
  * enable=0 reverts to the context stream.  The caller orders the streams (events) as it needs. */
 int flv_set_ba_stream(flv_ctx* ctx, void* cuda_stream, int enable);
+/* Thread-block cluster size (CTAs per window: 1, 2 or 4) of flv_ba_optimize.  A window that optimises landmarks is split over
+ * the cluster by landmark chunks; the partial reduced camera systems are summed through distributed shared memory.
+ * host_mode_cluster: FLV_MEM_HOST calls (default 4, env FLV_BA_CLUSTER; pose-only problems always run on 1 CTA);
+ * device_mode_cluster: FLV_MEM_DEVICE calls (default 1: the problems cannot be inspected on the host). */
+int flv_set_ba_cluster(flv_ctx* ctx, int host_mode_cluster, int device_mode_cluster);
 
 /* Debug: SM cycle counters of the last flv_ba_optimize for `stream`:
  * out16 = {chi2, build pose pass, schur products, cholesky, substitution, update, setup, -, schur init, schur staging,

@@ -69,6 +69,23 @@ void flv_f2f_destroy(flv_f2f* f);
  * R9 = rectification rotation (row-major).  The rectified projection P0 / P1 comes from flv_f2f_config.  Call before the
  * first image_feed.  need_equal_hist (f2f_tracking.cpp:125-145): cv::equalizeHist of every ingested image, on the GPU. */
 int flv_f2f_set_lens(flv_f2f* f, int cam, const double* K4, const double* D14, const double* R9);
+/* DepthCamera::setSteroCamInfo (src/processing/depth_camera.cpp:27-90) followed by F2FTracking::init, with the matrices the
+ * tracking nodelet hands over (src/frontend/vo_tracking.cpp:198-214 D435 stereo, :245-262 EuRoC, :276-302 KITTI): row-major
+ * K 3x3, D (OpenCV order, 14 slots, unused = 0), R 3x3 and P 3x4 of cv::stereoRectify, T_c0_c1 = [qx qy qz qw tx ty tz].
+ * cam_type 1 = STEREO_RECT, 2 = STEREO_UNRECT.  need_equal_hist as in F2FTracking::init (EuRoC: 1). */
+typedef struct {
+  int cam_type, img_w, img_h;
+  double K0[9], D0[14], R0[9], P0[12];
+  double K1[9], D1[14], R1[9], P1[12];
+  double T_c0_c1[7];
+  double T_i_c0[7];
+  double feature_para[6], vi_para[6], dc_para[3];
+  int skip_first_n_imgs, need_equal_hist;
+} flv_f2f_stereo_config;
+flv_f2f* flv_f2f_create_stereo(const flv_f2f_stereo_config* cfg, int device);
+/* The DepthCamera fields setSteroCamInfo derives (no GPU needed): cam0 / cam1 = fx fy cx cy taken from P0 / P1
+ * (depth_camera.cpp:73-82), T_cam1_cam0 = T_c0_c1^-1 (:60-61). */
+int flv_host_stereo_cam_info(const flv_f2f_stereo_config* cfg, double* cam0_4, double* cam1_4, double* T_cam1_cam0_7);
 int flv_f2f_set_equalize_hist(flv_f2f* f, int enable);
 /* the two per-point OpenCV calls of the UNRECT path, exported for the parity tests (flvis_b200/host/undistort.h) */
 int flv_host_undistort_points(const double* K4, const double* D14, const double* R9, const double* P12, int n, const float* in_xy,

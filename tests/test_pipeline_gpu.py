@@ -392,3 +392,36 @@ def test_correction_feed_applies_local_map_feedback_like_the_reference(lib):
     clib.flv_localmap_destroy(lm)
     ctx.close()
     lib.flv_f2f_destroy(h)
+
+
+def test_create_stereo_equals_create_plus_set_lens(lib):
+    """flv_f2f_create_stereo (DepthCamera::setSteroCamInfo + F2FTracking::init, vo_tracking.cpp:245-268) builds the same tracker
+    as flv_f2f_create + flv_f2f_set_lens + flv_f2f_set_equalize_hist: identical frames on an EuRoC-shaped raw stereo sequence."""
+    from flvis_b200 import batch
+    from synthdata import sequences
+    from .seq_harness import SingleTrackers
+    seq = sequences.make_c1(14)
+    a = SingleTrackers(lib, [seq], hooks=False)
+    lib.flv_f2f_create_stereo.restype = C.c_void_p
+    lib.flv_f2f_create_stereo.argtypes = [C.POINTER(batch.F2FStereoConfig), C.c_int]
+    sc = batch.stereo_config_for(seq)
+    hb = lib.flv_f2f_create_stereo(C.byref(sc), 0)
+    assert hb and lib.flv_f2f_last_error(hb) == b""
+    n_checked = 0
+    for t_img, img0, img1, imu in seq.frames():
+        for (t, acc, gyro) in imu:
+            acc = np.ascontiguousarray(acc, np.float64); gyro = np.ascontiguousarray(gyro, np.float64)
+            a.imu_feed(0, t, acc, gyro)
+            assert lib.flv_f2f_imu_feed(hb, t, acc.ctypes.data_as(C.c_void_p), gyro.ctypes.data_as(C.c_void_p)) == 0
+        a.image_feed([t_img], [img0], [img1])
+        kf = C.c_int(0); rs = C.c_int(0)
+        assert lib.flv_f2f_image_feed(hb, float(t_img), np.ascontiguousarray(img0).ctypes.data_as(C.c_void_p),
+                                      np.ascontiguousarray(img1).ctypes.data_as(C.c_void_p), C.byref(kf), C.byref(rs)) == 0
+        fa = a.get_frame(0)
+        a.h.append(hb); fb = a.get_frame(1); a.h.pop()
+        assert fa[0] == fb[0]
+        for x, y in zip(fa[1:], fb[1:]):
+            assert np.array_equal(x, y)
+        n_checked += fa[0] > 0
+    assert n_checked >= 6
+    lib.flv_f2f_destroy(hb)
