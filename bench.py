@@ -31,6 +31,10 @@ import time
 
 import numpy as np
 
+# every stream group, the image-upload, read-back and local-map streams need their own hardware queue: with the default of
+# 8 connections streams alias and serialise behind one another (must be set before the CUDA context exists)
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
+
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 from flvis_b200 import sharding  # noqa: E402

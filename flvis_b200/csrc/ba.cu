@@ -54,6 +54,7 @@ struct BAArgs {
   long long* prof;   // [S][8] cycle counters or nullptr
   double* trace;     // [S][BA_TRACE_ITERS][4] per LM iteration: chi2 at the end, lambda, rho of the last trial, trials
   int dyn_doubles;   // dynamic shared memory of the launch, in doubles
+  int member_buf;    // ints of shared memory for TMA-staged pose-pair member lists (0 = read them from L2; see BA_MEMBER_BUF)
 };
 
 // ---- SE3 helpers (g2o SE3Quat semantics, quaternion stored x,y,z,w) ----------------------------
@@ -205,6 +206,10 @@ constexpr int BA_MAX_PAIRS = BA_MAX_FREE * (BA_MAX_FREE + 1) / 2;   // 300
 constexpr int BA_MAX_CHUNKS = 128;
 constexpr int BA_CHUNK_PLANES = 18 + 3;       // Z = W Ld (6x3) per slot, Ld^T bl per landmark
 constexpr int BA_MAX_CAP = 1023;              // chunk-local positions are packed 10 bits each
+// ints of shared memory for TMA-staged member lists (FLV_BA_TMA=1).  Off by default: measured on B200 (tools/ba_profile.py,
+// profiles/README.md) the staged lists are 4 % slower at W=10 / 4 CTAs (the L2 reads were already prefetched one round ahead)
+// and 13 % slower at W=20 / 1 CTA (the buffer shrinks the landmark chunks).
+constexpr int BA_MEMBER_BUF = 6144;
 
 struct Sh {   // fixed-size shared state (one copy per CTA of the window's cluster)
   double red[BA_WARPS];
@@ -214,10 +219,16 @@ struct Sh {   // fixed-size shared state (one copy per CTA of the window's clust
   double bp[6 * BA_MAX_FREE];
   double x[6 * BA_MAX_FREE];
   double invd[6 * BA_MAX_FREE];
+  double col1[6 * BA_MAX_FREE + 2];     // Cholesky: final entries of the odd column of a two-column step (written back a step later)
   double poses[7 * BA_MAX_POSES];       // the window's poses: every CTA of the cluster keeps (and updates) its own identical copy
   double pbk[7 * BA_MAX_POSES];         // backup of the poses for a rejected trial
+  unsigned long long mbar;              // mbarrier of the bulk (TMA) copies that stage a chunk's pose-pair member lists
   double xchg[2][4];                    // cluster all-reduce exchange slots (double-buffered: one cluster barrier per reduction)
   int rank, C;                          // rank in / size of the window's cluster
+  // per-CTA state of the member-list staging (NOT part of the range copied from rank 0 below)
+  int mb_chunk;                          // what the member staging buffer holds: chunk index, -2 = all chunks of this CTA, -1 = nothing
+  int m_base;                            // first (16-byte aligned) index of `pairs` held in the buffer
+  unsigned m_issued;                     // bulk copies issued so far (a thread waits until it has seen as many completions)
   int c0, c1, l0, l1, s0, s1;           // this CTA's chunks and the landmark / slot (= CSR) ranges they cover
   // ---- written by setup_active on rank 0 and copied to the other CTAs (contiguous: pidx .. capq) ----
   int pidx[BA_MAX_POSES];
@@ -230,7 +241,7 @@ struct Sh {   // fixed-size shared state (one copy per CTA of the window's clust
   int task_bounds[BA_MAX_PAIRS + 1];    // member-list bounds of the pose pairs for the chunk being processed
   unsigned short task_order[BA_MAX_PAIRS];   // pose pairs by decreasing member count: the order warps pick them up in
   int next_task;
-  int np, fail, nact, overflow, nch, cap, capq;
+  int np, fail, nact, overflow, nch, mb, cap, capq;     // mb: ints of the member-list staging buffer behind the chunk planes (0 = none)
   long long prof[16], tlast;  // cycle counters: 0 chi2, 1 build (pose pass), 2 schur (pair products), 3 cholesky, 4 substitution,
                               // 5 update, 6 setup, 7 -, 8 schur init + Dinv, 9 schur chunk staging, 10 build edge pass, 11 build landmark pass
 };
@@ -259,6 +270,31 @@ __device__ __forceinline__ void cluster_reduce(double (&v)[K], Sh& sh, int& xpar
   }
 }
 
+// ---- TMA bulk copy global -> shared memory, completion on an mbarrier (cp.async.bulk; SASS: UBLKCP + SYNCS) ----------------
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+// one thread: announce `bytes`, then start the copy (src, dst 16-byte aligned, bytes a multiple of 16)
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned bytes, unsigned long long* bar) {
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // earlier generic-proxy reads of dst are done (after a barrier)
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\n"
+      "bra WAIT_%=;\n"
+      "DONE_%=:\n"
+      "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+
 __device__ __forceinline__ void mark(Sh& sh, int slot) {
   if (threadIdx.x == 0) { const long long now = clock64(); sh.prof[slot] += now - sh.tlast; sh.tlast = now; }
 }
@@ -282,6 +318,20 @@ struct Ws {
   int *pairs;                               // packed members: pos_a | pos_b << 10 | lpos << 20 (chunk-local)
   int pair_cap, ME, ML;
 };
+
+// One thread: stage the member lists of chunks [ch0, ch1) (a contiguous run of `pairs`, widened to 16-byte granules) unless
+// the buffer already holds them (tag).  False if they do not fit.  Readers look at sh.mb_chunk / m_base / m_issued after the
+// next barrier.
+__device__ __noinline__ bool members_stage(int ch0, int ch1, int tag, int nblk, int* Mb, Ws& ws, Sh& sh) {
+  const int m0 = ws.poff[ch0 * nblk] & ~3, m1 = (ws.poff[ch1 * nblk] + 3) & ~3;
+  if (!(m1 > m0 && m1 - m0 <= sh.mb)) { if (sh.mb_chunk == tag) sh.mb_chunk = -1; return false; }
+  if (sh.mb_chunk != tag) {
+    bulk_g2s(Mb, ws.pairs + m0, (unsigned)(m1 - m0) * 4u, &sh.mbar);
+    sh.m_issued++;
+    sh.mb_chunk = tag; sh.m_base = m0;
+  }
+  return true;
+}
 
 __device__ __forceinline__ int sym21(int i, int j) {   // index into upper-triangular 6x6 (i<=j)
   return i * 6 - (i * (i - 1)) / 2 + (j - i);
@@ -354,7 +404,7 @@ __device__ double robust_chi2(const Cam& cam, const double* poses, const double*
 // edges fit the shared-memory staging area of the Schur pass; inside a chunk the edges of one pose are contiguous
 // and sorted by landmark, so both the per-landmark and the per-pose passes read the planes nearly sequentially.
 __device__ void setup_active(const flv_ba_problem& pb, const int* ep, const int* el, const double* uv,
-                             const uint8_t* act, int chunk_area_doubles, Ws& ws, Sh& sh) {
+                             const uint8_t* act, int chunk_area_doubles, int member_buf, Ws& ws, Sh& sh) {
   const int P = pb.n_poses, L = pb.n_landmarks, E = pb.n_edges, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   for (int i = tid; i < P * L; i += BA_THREADS) ws.tab[i] = -1;
   for (int i = tid; i < L; i += BA_THREADS) ws.lmask[i] = 0u;
@@ -380,9 +430,14 @@ __device__ void setup_active(const flv_ba_problem& pb, const int* ep, const int*
     // staging capacity of the Schur pass: what the reduced system leaves of the dynamic shared memory
     const int npc = np < BA_MAX_FREE ? np : BA_MAX_FREE;
     const int n = 6 * npc;
-    int cap = (chunk_area_doubles - (n * (n + 1) + n + 8)) / BA_CHUNK_PLANES;
+    // behind the chunk planes: staging buffer of the chunk's pose-pair member lists (bulk-copied while Z is computed), unless
+    // the reduced system leaves too little room
+    int mb = member_buf;
+    int cap = (chunk_area_doubles - (n * (n + 1) + n + 8) - mb / 2) / BA_CHUNK_PLANES;
+    if (cap < 256 || pb.fix_landmarks) { mb = 0; cap = (chunk_area_doubles - (n * (n + 1) + n + 8)) / BA_CHUNK_PLANES; }
     cap = cap > BA_MAX_CAP ? BA_MAX_CAP : cap;
-    sh.cap = cap; sh.capq = cap - P;
+    cap &= ~1;                                    // keeps the member buffer behind the planes 16-byte aligned
+    sh.mb = mb; sh.cap = cap; sh.capq = cap - P;
   }
   __syncthreads();
   if (sh.np > BA_MAX_FREE) return;
@@ -519,8 +574,8 @@ __device__ void setup_active(const flv_ba_problem& pb, const int* ep, const int*
 // result through distributed shared memory.  Then every CTA takes a contiguous run of chunks: all edges of a landmark lie in the
 // landmark's chunk, so a CTA's landmarks, slots and CSR entries are private to it in every pass.
 __device__ void setup_cluster(const flv_ba_problem& pb, const int* ep, const int* el, const double* uv,
-                              const uint8_t* act, int chunk_area_doubles, Ws& ws, Sh& sh) {
-  if (sh.rank == 0) setup_active(pb, ep, el, uv, act, chunk_area_doubles, ws, sh);
+                              const uint8_t* act, int chunk_area_doubles, int member_buf, Ws& ws, Sh& sh) {
+  if (sh.rank == 0) setup_active(pb, ep, el, uv, act, chunk_area_doubles, member_buf, ws, sh);
   if (sh.C > 1) {
     cg::cluster_group cl = cg::this_cluster();
     cl.sync();
@@ -533,6 +588,7 @@ __device__ void setup_cluster(const flv_ba_problem& pb, const int* ep, const int
     cl.sync();
   }
   if (threadIdx.x == 0) {
+    sh.mb_chunk = -1;                              // new member lists
     const int nch = (sh.np > BA_MAX_FREE || sh.overflow) ? 0 : sh.nch;
     sh.c0 = (nch * sh.rank) / sh.C; sh.c1 = (nch * (sh.rank + 1)) / sh.C;
     sh.l0 = nch ? sh.chunk_lb[sh.c0] : 0; sh.l1 = nch ? sh.chunk_lb[sh.c1] : 0;
@@ -649,11 +705,17 @@ __device__ void build_system(const flv_ba_problem& pb, const Cam& cam, const dou
 // landmarks); a warp owns a pose pair, two lanes share a member landmark (lane parity h owns columns 3h..3h+2 of the
 // 6x6 block), member lists hold chunk-local positions, so every operand of the inner loop is a shared-memory read.
 __device__ void solve_system(const flv_ba_problem& pb, const Cam& cam, const double* poses, const double* lms, double delta,
-                             double lambda, double* S, double* y, double* chunk, int ld, Ws& ws, Sh& sh) {
+                             double lambda, double* S, double* y, double* chunk, int ld, Ws& ws, Sh& sh, unsigned& mpar) {
   const int L = pb.n_landmarks, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int np = sh.np, n = 6 * np, ME = ws.ME, ML = ws.ML;
   const int nblk = np * (np + 1) / 2;
   // reduced system starts as the pose blocks (+ lambda); the chunks subtract W Dinv W^T from it
+  // pose-pair member lists -> shared memory by TMA bulk copy (members_stage): all chunks of this CTA at once if they fit (then
+  // they stay resident over the LM trials of the phase), else chunk by chunk, issued early so the copy overlaps the Z pass
+  int* Mb = reinterpret_cast<int*>(chunk + BA_CHUNK_PLANES * sh.cap);
+  if (!pb.fix_landmarks && sh.c0 < sh.c1 && tid == 0) {
+    if (!members_stage(sh.c0, sh.c1, -2, nblk, Mb, ws, sh)) members_stage(sh.c0, sh.c0 + 1, sh.c0, nblk, Mb, ws, sh);
+  }
   // (in a cluster every CTA accumulates the products of its own chunks into its own S / y; rank 0 adds them up below)
   for (int i = tid; i < n * ld; i += BA_THREADS) S[i] = 0;
   __syncthreads();
@@ -692,6 +754,7 @@ __device__ void solve_system(const flv_ba_problem& pb, const Cam& cam, const dou
     double* Vc = chunk + 18 * cap;        // [3][cap]   Ld^T bl of the chunk's landmarks
     for (int ch = sh.c0; ch < sh.c1; ++ch) {
       const int sb = sh.chunk_sb[ch], ns = sh.chunk_sb[ch + 1] - sb, lb = sh.chunk_lb[ch], nl = sh.chunk_lb[ch + 1] - lb;
+
       // member-list bounds of every pose pair for this chunk -> shared memory; tasks are drawn dynamically below
       for (int i = tid; i <= nblk; i += BA_THREADS) sh.task_bounds[i] = ws.poff[ch * nblk + i];
       if (tid == 0) sh.next_task = 0;
@@ -717,6 +780,9 @@ __device__ void solve_system(const flv_ba_problem& pb, const Cam& cam, const dou
         Vc[i] = v0; Vc[cap + i] = v1; Vc[2 * cap + i] = v2;
       }
       __syncthreads();
+      const bool staged = sh.mb_chunk == -2 || sh.mb_chunk == ch;
+      if (staged && mpar != sh.m_issued) { mbar_wait(&sh.mbar, mpar & 1u); ++mpar; }     // mpar counts the copies this thread has waited for
+      const int* members = staged ? Mb - sh.m_base : ws.pairs;
       mark(sh, 9);
       for (;;) {
         int tsk = 0;
@@ -732,10 +798,10 @@ __device__ void solve_system(const flv_ba_problem& pb, const Cam& cam, const dou
 #pragma unroll
         for (int i = 0; i < 36; ++i) acc[i] = 0;
         int k = i0 + lane;
-        int ent = k < i1 ? ws.pairs[k] : 0;
+        int ent = k < i1 ? members[k] : 0;
         for (; k < i1; k += 32) {
           const int cur = ent;
-          if (k + 32 < i1) ent = ws.pairs[k + 32];          // prefetch the next round's member
+          if (k + 32 < i1) ent = members[k + 32];           // prefetch the next round's member
           const int pa = cur & 1023, pbb = (cur >> 10) & 1023;
           double za[18];
 #pragma unroll
@@ -772,7 +838,7 @@ __device__ void solve_system(const flv_ba_problem& pb, const Cam& cam, const dou
           // right-hand side of pose a: y_a -= sum_l Z_al (Ld^T bl)_l
           double cf[6] = {0, 0, 0, 0, 0, 0};
           for (int k2 = i0 + lane; k2 < i1; k2 += 32) {
-            const int cur = ws.pairs[k2];
+            const int cur = members[k2];
             const int pa = cur & 1023, lp = cur >> 20;
             const double v0 = Vc[lp], v1 = Vc[cap + lp], v2 = Vc[2 * cap + lp];
 #pragma unroll
@@ -785,6 +851,7 @@ __device__ void solve_system(const flv_ba_problem& pb, const Cam& cam, const dou
       }
       __syncthreads();
       mark(sh, 2);
+      if (tid == 0 && sh.mb_chunk != -2 && ch + 1 < sh.c1) members_stage(ch + 1, ch + 2, ch + 1, nblk, Mb, ws, sh);   // (the buffer is free)
     }
   }
   if (tid == 0) sh.fail = 0;
@@ -806,33 +873,50 @@ __device__ void solve_system(const flv_ba_problem& pb, const Cam& cam, const dou
   __syncthreads();
   mark(sh, 2);
   if (sh.rank == 0) {
-  // Right-looking Cholesky (LDL^T form) of the augmented matrix [S ; y^T] (row n = right-hand side): one barrier per
-  // column, no square roots -- after step j column j holds A_ij = L_ij sqrt(d_j), the diagonal d_j = L_jj^2, and
-  //   x_j = (y_j - sum_{k>j} A_kj x_k) / d_j.
-  // (re-spreading the threads over the live rows in every step measured slower: 1.25 M vs 0.93 M cycles per window -- the
-  // step is bound by its fixed latency, barrier + dependent shared-memory loads, not by the trailing update)
+  // Right-looking Cholesky (LDL^T form) of the augmented matrix [S ; y^T] (row n = right-hand side), no square roots: after
+  // its step column j holds A_ij = L_ij sqrt(d_j), the diagonal d_j = L_jj^2, and x_j = (y_j - sum_{k>j} A_kj x_k) / d_j.
+  // TWO columns per barrier (n = 6 np is even): a step is bound by its fixed latency (barrier + dependent shared-memory loads:
+  // ~690 cycles per column measured with one column per barrier), not by the trailing update, so every thread redoes the tiny
+  // 2x2 pivot block and the column-(j+1) entries it needs instead of waiting for another barrier.  Same operations in the same
+  // order per element as the one-column form.  The final column-(j+1) entries are parked in col1 and written back one step
+  // later (other threads still read the raw column during the step).
+  // (re-spreading the threads over the live rows in every step measured slower: the integer division costs more than it saves)
   int T = BA_THREADS / (n + 1);                   // threads per row (no shuffles here: any count works)
   T = T < 1 ? 1 : (T > 32 ? 32 : T);
   const int row = tid / T, t = tid - row * T;
   bool bad = false;
   if (tid == 0) sh.invd[0] = 1.0 / S[0];
   __syncthreads();
-  for (int j = 0; j < n; ++j) {
-    const double d = S[j * ld + j];
-    if (!(d > 0)) { bad = true; break; }                     // same value in every thread: uniform exit
-    const double inv = sh.invd[j];                           // 1 / d_j, computed by the owner of d_j during step j-1
-    if (row > j && row <= n) {
-      double* Ai = row < n ? S + row * ld : y;
-      const double f = Ai[j] * inv;
-      const int kmax = row < n ? row : n - 1;
-      for (int k = j + 1 + t; k <= kmax; k += T) {
-        const double v = Ai[k] - f * S[k * ld + j];
+  double* Ai = row < n ? S + row * ld : y;        // (dereferenced for row <= n only)
+  const int kmax = row < n ? row : n - 1;
+  for (int j = 0; j < n; j += 2) {
+    if (j > 0 && t == 0 && row >= j && row <= n) Ai[j - 1] = sh.col1[row];     // column j-1, final since the previous step
+    const double d0 = S[j * ld + j];
+    const double inv0 = sh.invd[j];                          // 1 / d_j, computed by the owner of d_j during the previous step
+    const double a10 = S[(j + 1) * ld + j];
+    const double f10 = a10 * inv0;
+    const double d1 = S[(j + 1) * ld + j + 1] - f10 * a10;
+    if (!(d0 > 0) || !(d1 > 0)) { bad = true; break; }       // same values in every thread: uniform exit
+    const double inv1 = 1.0 / d1;
+    if (tid == 0) sh.invd[j + 1] = inv1;
+    if (row >= j + 2 && row <= n) {
+      const double fi0 = Ai[j] * inv0;
+      const double ai1 = Ai[j + 1] - fi0 * a10;
+      const double fi1 = ai1 * inv1;
+#pragma unroll 2
+      for (int k = j + 2 + t; k <= kmax; k += T) {
+        const double ak0 = S[k * ld + j];
+        const double ak1 = S[k * ld + j + 1] - (ak0 * inv0) * a10;
+        double v = Ai[k] - fi0 * ak0;
+        v = v - fi1 * ak1;
         Ai[k] = v;
-        if (k == j + 1 && row == j + 1) sh.invd[j + 1] = 1.0 / v;   // next pivot: its reciprocal leaves the critical path
+        if (k == j + 2 && row == j + 2) sh.invd[j + 2] = 1.0 / v;   // next pivot: its reciprocal leaves the critical path
       }
+      if (t == 0) sh.col1[row] = ai1;
     }
     __syncthreads();
   }
+  if (!bad && t == 0 && row == n) y[n - 1] = sh.col1[n];     // last odd column: only the right-hand side row is left
   if (bad && tid == 0) sh.fail = 1;
   __syncthreads();
   mark(sh, 3);
@@ -964,16 +1048,17 @@ __host__ __device__ inline WsLayout ws_layout(int MP, int ML, int ME) {
   o.luv = d; d += 2 * E;
   o.uvs = d; d += 2 * E;
   o.Hll = d; d += 6 * L; o.bl = d; d += 3 * L; o.Dinv = d; d += 6 * L; o.Dv = d; d += 3 * L; o.Ld = d; d += 6 * L;
+  d += d & 1;                                   // ints start 16-byte aligned (bulk copies of `pairs` need it)
   o.n_doubles = d;
   o.tab = i; i += P * L; o.lmask = i; i += L; o.slot_e = i; i += E; o.slot_pl = i; i += E; o.slot_lp = i; i += E; o.csr_p = i; i += E; o.csr_l = i; i += E;
   o.lw = i; i += L + 1; o.lstart = i; i += L + 1; o.cp_off = i; i += (size_t)BA_MAX_CHUNKS * (P + 1);
-  o.poff = i; i += poff_capacity(); o.pairs = i; i += pair_capacity(MP, ME);
+  o.poff = i; i += poff_capacity(); i = (i + 3) & ~(size_t)3; o.pairs = i; i += pair_capacity(MP, ME) + 8;
   o.n_ints = i;
   return o;
 }
 
 __global__ void __launch_bounds__(BA_THREADS, 1) ba_kernel(BAArgs a) {
-  extern __shared__ double dyn[];
+  extern __shared__ __align__(16) double dyn[];
   __shared__ Sh sh;
   cg::cluster_group cluster = cg::this_cluster();
   const int C = (int)cluster.num_blocks(), rank = (int)cluster.block_rank();     // C CTAs (1, 2 or 4) work on one window
@@ -1009,14 +1094,15 @@ __global__ void __launch_bounds__(BA_THREADS, 1) ba_kernel(BAArgs a) {
     if (tid == 0 && rank == 0) { st.ok = 0; st.reserved = 1; a.stats[s] = st; }
     return;
   }
-  if (tid == 0) { for (int i = 0; i < 16; ++i) sh.prof[i] = 0; sh.tlast = clock64(); sh.rank = rank; sh.C = C; }
+  if (tid == 0) { for (int i = 0; i < 16; ++i) sh.prof[i] = 0; sh.tlast = clock64(); sh.rank = rank; sh.C = C; mbar_init(&sh.mbar, 1); sh.m_issued = 0; sh.mb_chunk = -1; }
+  unsigned mpar = 0;                                // phase parity of sh.mbar (one completed bulk copy per staged chunk)
   for (int i = tid; i < 7 * P; i += BA_THREADS) sh.poses[i] = poses_g[i];
   __syncthreads();
   st.chi2_initial = robust_chi2_edges(pb, cam, poses, lms, ep, el, uv, act, delta, sh, xpar);
   double lambda = 0;
   for (int phase = 0; phase < 2; ++phase) {
     const int iters = phase == 0 ? a.prm.iters1 : a.prm.iters2;
-    setup_cluster(pb, ep, el, uv, act, a.dyn_doubles, ws, sh);
+    setup_cluster(pb, ep, el, uv, act, a.dyn_doubles, a.member_buf, ws, sh);
     mark(sh, 6);
     if (sh.np > BA_MAX_FREE) { st.ok = 0; st.reserved = 2; break; }
     if (sh.overflow) { st.ok = 0; st.reserved = sh.overflow == 1 ? 3 : 4; break; }
@@ -1050,12 +1136,12 @@ __global__ void __launch_bounds__(BA_THREADS, 1) ba_kernel(BAArgs a) {
       double rho = 0;
       int qmax = 0;
       do {
-        solve_system(pb, cam, poses, lms, delta, lambda, S, y, chunk, ld, ws, sh);
+        solve_system(pb, cam, poses, lms, delta, lambda, S, y, chunk, ld, ws, sh, mpar);
         const int ok2 = !sh.fail;
         double scale = 0, tempChi;
         if (ok2) {
           double sv[2];
-          sv[0] = apply_update(pb, cam, delta, lambda, poses, lms, chunk, a.dyn_doubles - (n * ld + ((n + 8) & ~1)), ws, sh);
+          sv[0] = apply_update(pb, cam, delta, lambda, poses, lms, chunk, BA_CHUNK_PLANES * sh.cap, ws, sh);   // (planes only: the member lists stay resident)
           __syncthreads();
           mark(sh, 5);
           sv[1] = robust_chi2_part(cam, poses, lms, delta, ws, sh);
@@ -1225,6 +1311,8 @@ int flv_ba_optimize(flv_ctx* ctx, int n_streams, const flv_ba_problem* problems,
   a.ws = (unsigned char*)ctx->ba_ws + stride * slot0; a.ws_stride = stride;
   if (!ctx->ba_dyn) ctx->ba_dyn = ba_dyn_doubles();
   a.dyn_doubles = ctx->ba_dyn;
+  if (ctx->ba_member_buf < 0) { const char* e = getenv("FLV_BA_TMA"); ctx->ba_member_buf = (e && atoi(e) > 0) ? BA_MEMBER_BUF : 0; }
+  a.member_buf = ctx->ba_member_buf;
   const size_t smem = (size_t)a.dyn_doubles * 8;
   const size_t S = n_streams;
   cudaStream_t stream = ctx->ba_stream_set ? ctx->ba_stream : ctx->stream;

@@ -61,6 +61,7 @@ int flv_create(flv_ctx** out, int device, int max_streams, int img_w, int img_h,
   memset(ctx, 0, sizeof(*ctx));
   *out = ctx;
   ctx->device = device; ctx->S = max_streams; ctx->w = img_w; ctx->h = img_h; ctx->max_pts = max_pts;
+  ctx->ba_member_buf = -1;
   FLV_CUDA(ctx, cudaSetDevice(device));
   build_geom(ctx->geom, img_w, img_h);
   ctx->no_fused_ingest = getenv("FLV_NO_FUSED_INGEST") ? atoi(getenv("FLV_NO_FUSED_INGEST")) : 0;

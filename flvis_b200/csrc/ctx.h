@@ -38,6 +38,7 @@ struct flv_ctx {
   int attr_lk3, attr_lk4, attr_region;     // cudaFuncSetAttribute done for this context's device
   int ba_dyn;                              // cached dynamic shared memory of ba_kernel (doubles)
   int ba_cluster, ba_cluster_device;       // CTAs per window for FLV_MEM_HOST / FLV_MEM_DEVICE solves (0 = default)
+  int ba_member_buf;                       // ints of shared memory for TMA-staged member lists (-1 = read FLV_BA_TMA, 0 = off)
   int no_fused_ingest;           // FLV_NO_FUSED_INGEST=1: A/B switch for tests
   char err[512];
 
