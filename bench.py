@@ -536,7 +536,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--streams", type=int, default=32)
-    ap.add_argument("--groups", type=int, default=2, help="stream groups per GPU (own CUDA stream + host thread each)")
+    ap.add_argument("--groups", type=int, default=4, help="stream groups per GPU (own CUDA stream + host thread each)")
     ap.add_argument("--reps", type=int, default=7, help="repetitions of the K-step timed region (median reported)")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")

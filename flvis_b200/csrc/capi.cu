@@ -114,6 +114,8 @@ void flv_destroy(flv_ctx* ctx) {
   if (ctx->d_stage) cudaFree(ctx->d_stage);
   if (ctx->img_stage_bytes) for (int i = 0; i < flv_ctx::IMG_RING; ++i) cudaFree(ctx->d_img_stage[i]);
   if (ctx->d_hist) cudaFree(ctx->d_hist);
+  if (ctx->d_lut) cudaFree(ctx->d_lut);
+  if (ctx->d_lk_tmaps) cudaFree(ctx->d_lk_tmaps);
   if (ctx->d_color_stage) cudaFree(ctx->d_color_stage);
   if (ctx->aux_stream) { cudaEventDestroy(ctx->ev_fork); cudaEventDestroy(ctx->ev_gftt); cudaStreamDestroy(ctx->aux_stream); }
   if (ctx->copy_stream) {
@@ -164,6 +166,10 @@ int flv_upload_images(flv_ctx* ctx, int slot, int n_streams, const uint8_t* imgs
       row_stride_bytes < (size_t)ctx->w)
     return FLV_ERR_INVALID;
   if (mem == FLV_MEM_DEVICE && !ctx->equalize) return flv_launch_unpack(ctx, slot, n_streams, imgs, row_stride_bytes, img_stride_bytes);
+  if (mem == FLV_MEM_DEVICE) {       // equalizeHist fused into the ingest: no landing area at all
+    const int rc = flv_launch_unpack_equalized(ctx, slot, n_streams, imgs, row_stride_bytes, img_stride_bytes);
+    if (rc != FLV_ERR_UNSUPPORTED) return rc;
+  }
   // host images: one (2D) H2D copy of all streams into a tight device landing area on the copy stream, then one unpack
   // launch on the compute stream.  The landing areas form a ring, so a caller that submits frame k+1 before it waits for
   // the results of frame k gets the copy of k+1 overlapped with the kernels of k.
@@ -207,11 +213,14 @@ int flv_upload_images(flv_ctx* ctx, int slot, int n_streams, const uint8_t* imgs
   }
   FLV_CUDA(ctx, cudaEventRecord(ctx->img_ready[ring], cs));
   FLV_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->img_ready[ring], 0));
-  if (ctx->equalize) {
-    const int rc0 = flv_launch_equalize(ctx, n_streams, st, w, w * h, st);          // in place (element-wise LUT)
-    if (rc0) return rc0;
+  int rc = ctx->equalize ? flv_launch_unpack_equalized(ctx, slot, n_streams, st, w, w * h) : FLV_ERR_UNSUPPORTED;
+  if (rc == FLV_ERR_UNSUPPORTED) {
+    if (ctx->equalize) {
+      const int rc0 = flv_launch_equalize(ctx, n_streams, st, w, w * h, st);          // in place (element-wise LUT)
+      if (rc0) return rc0;
+    }
+    rc = flv_launch_unpack(ctx, slot, n_streams, st, w, w * h);
   }
-  const int rc = flv_launch_unpack(ctx, slot, n_streams, st, w, w * h);
   if (rc) return rc;
   FLV_CUDA(ctx, cudaEventRecord(ctx->img_free[ring], ctx->stream));
   return FLV_OK;
@@ -251,8 +260,11 @@ int flv_upload_color_images(flv_ctx* ctx, int slot, int n_streams, const uint8_t
   FLV_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->img_free[ring], 0));
   int rc = flv_launch_gray(ctx, n_streams, d_src, row_stride_bytes, img_stride_bytes, channels, is_rgb ? 1 : 0, st);
   if (rc) return rc;
-  if (ctx->equalize && (rc = flv_launch_equalize(ctx, n_streams, st, w, w * h, st))) return rc;
-  rc = flv_launch_unpack(ctx, slot, n_streams, st, w, w * h);
+  rc = ctx->equalize ? flv_launch_unpack_equalized(ctx, slot, n_streams, st, w, w * h) : FLV_ERR_UNSUPPORTED;
+  if (rc == FLV_ERR_UNSUPPORTED) {
+    if (ctx->equalize && (rc = flv_launch_equalize(ctx, n_streams, st, w, w * h, st))) return rc;
+    rc = flv_launch_unpack(ctx, slot, n_streams, st, w, w * h);
+  }
   if (rc) return rc;
   FLV_CUDA(ctx, cudaEventRecord(ctx->img_free[ring], ctx->stream));
   return FLV_OK;

@@ -35,6 +35,8 @@ struct flv_ctx {
   int prep_valid, prep_slot, prep_streams, prep_ncorn, prep_dis; double prep_ql;
   void* d_color_stage; size_t color_stage_bytes;   // landing area of interleaved colour uploads
   int equalize; int* d_hist;     // cv::equalizeHist on ingest (flv_set_equalize_hist)
+  void* d_lut;                   // [S][256] equalisation LUTs of the fused ingest
+  void* d_lk_tmaps;                        // LK TMA variant: tensor maps of the pyramid levels of every image slot
   int attr_lk3, attr_lk4, attr_region;     // cudaFuncSetAttribute done for this context's device
   int ba_dyn;                              // cached dynamic shared memory of ba_kernel (doubles)
   int ba_cluster, ba_cluster_device;       // CTAs per window for FLV_MEM_HOST / FLV_MEM_DEVICE solves (0 = default)
@@ -113,6 +115,7 @@ int flv_launch_gray(flv_ctx* ctx, int n_streams, const uint8_t* d_src, size_t ro
                     uint8_t* d_dst_tight);
 int flv_launch_equalize(flv_ctx* ctx, int n_streams, const uint8_t* d_src, size_t row_stride, size_t img_stride, uint8_t* d_dst_tight);
 int flv_launch_unpack(flv_ctx* ctx, int slot, int n_streams, const uint8_t* d_src, size_t row_stride, size_t img_stride);
+int flv_launch_unpack_equalized(flv_ctx* ctx, int slot, int n_streams, const uint8_t* d_src, size_t row_stride, size_t img_stride);
 int flv_launch_lk(flv_ctx* ctx, int src_slot, int dst_slot, int n_streams, const int* d_npts,
                   const float* d_prev, const float* d_init, float* d_next, uint8_t* d_status,
                   float* d_err, int nlev_used, int max_iter, double eps2, double min_eig_thr);

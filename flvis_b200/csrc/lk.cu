@@ -286,7 +286,7 @@ int flv_launch_lk(flv_ctx* ctx, int src_slot, int dst_slot, int n_streams, const
   // default: v4 (lk_v4.cu: precomputed Scharr pyramid, packed register patch, DP2A blend); FLV_LK_VARIANT selects the
   // earlier kernels (1 = register template, 3/4 = v2 register budgets, 5 = shared-memory template) for A/B runs
   const int variant = getenv("FLV_LK_VARIANT") ? atoi(getenv("FLV_LK_VARIANT")) : 6;
-  if (variant == 6)
+  if (variant == 6 || variant == 7)     // 7 = v4 with the second image's patch staged by TMA (measured A/B, see lk_v4.cu)
     return flv_launch_lk_v4(ctx, src_slot, dst_slot, n_streams, d_npts, d_prev, d_init, d_next, d_status, d_err, nlev_used,
                             max_iter, eps2, min_eig_thr);
   if (variant == 5)

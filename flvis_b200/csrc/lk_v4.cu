@@ -13,7 +13,13 @@
 //     adjacent bytes, so one DP2A (16-bit weights x 8-bit pixels) does two multiplies: 2 DP2A per pixel instead of
 //     4 IMAD + load + shuffle.  The patch is only reloaded when the integer window origin moves.
 // Reference call sites: src/processing/lkorb_tracking.cpp:64-73, src/processing/camera_frame.cpp:124-128.
+//
+// FLV_LK_VARIANT=7 is the measured TMA A/B of the patch staging: the 32x32 u8 patch of the second image comes through a
+// cp.async.bulk.tensor.3d load (one tensor map per pyramid level: x, y, stream; box 32x32x1) into a per-warp shared-memory
+// tile (48 x 32: tile loads start on 16-byte boundaries) and is packed into the same registers from there; everything else is
+// identical.  Numbers: profiles/README.md.
 #include <stdlib.h>
+#include <cuda.h>
 #include "ctx.h"
 
 namespace {
@@ -175,6 +181,42 @@ __device__ __forceinline__ void load_patch(const uint8_t* __restrict__ img, int 
   for (int k = 0; k < 8; ++k) Q[k] = __shfl_down_sync(FULL, P[k], 1);
 }
 
+// TMA variant of the interior patch load: lane 0 issues one 3-D tile load, the warp waits on its mbarrier and packs its column
+// from the row-major shared-memory tile.  A tile load must start on a 16-byte boundary of the innermost dimension (any other
+// start coordinate faults with "illegal instruction": tools/tma_probe.cu), so the box is 48 x 32 x 1 bytes at column
+// ox & ~15 and the lane reads column (ox & 15) + lane of it.
+constexpr int TMA_BOX_W = 48;
+constexpr int TMA_TILE_BYTES = TMA_BOX_W * 32;
+__device__ __forceinline__ unsigned smem_addr(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void load_patch_tma(const CUtensorMap* tm, uint8_t* tile, unsigned long long* bar, unsigned& parity,
+                                               int ox, int oy, int s, int lane, unsigned (&P)[8], unsigned (&Q)[8]) {
+  __syncwarp();                                   // every lane is done with the previous tile
+  if (lane == 0) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"((unsigned)TMA_TILE_BYTES) : "memory");
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+                 ::"r"(smem_addr(tile)), "l"(tm), "r"(ox & ~15), "r"(oy), "r"(s), "r"(smem_addr(bar)) : "memory");
+  }
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "LKW_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra LKD_%=;\n"
+      "bra LKW_%=;\n"
+      "LKD_%=:\n"
+      "}\n" ::"r"(smem_addr(bar)), "r"(parity) : "memory");
+  parity ^= 1u;
+  const uint8_t* p = tile + (ox & 15) + lane;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const unsigned b0 = p[0], b1 = p[TMA_BOX_W], b2 = p[2 * TMA_BOX_W], b3 = p[3 * TMA_BOX_W];
+    P[k] = pack4(b0, b1, b2, b3);
+    p += 4 * TMA_BOX_W;
+  }
+#pragma unroll
+  for (int k = 0; k < 8; ++k) Q[k] = __shfl_down_sync(FULL, P[k], 1);
+}
+
 // bilinear blend of rows (y, y+1) x columns (lane, lane+1), y = 4k + j:  c + w00 J[y][x] + w01 J[y][x+1] + w10 J[y+1][x] + w11 J[y+1][x+1]
 // wv0 = w00 | w10 << 16 (own column), wv1 = w01 | w11 << 16 (right column)
 template <int J>
@@ -282,19 +324,33 @@ __device__ __forceinline__ void build_template(const uint8_t* __restrict__ I, co
   }
 }
 
+struct LKTmaps { CUtensorMap lv[FLV_MAX_LEVELS]; };      // second image, one map per level (TMA variant only)
+
+template <bool TMA>
 __global__ void __launch_bounds__(V4_WARPS * 32, 5)
 lk_track_kernel_v4(const uint8_t* __restrict__ pyrI, const unsigned* __restrict__ derivI, const uint8_t* __restrict__ pyrJ,
                    LKGeom g, const int* __restrict__ npts, const float* __restrict__ prev_xy,
                    const float* __restrict__ init_xy, float* __restrict__ next_xy, uint8_t* __restrict__ status,
                    float* __restrict__ err, int max_pts, int nlev_used, int max_iter, double eps2, double min_eig_thr,
-                   float err_scale) {
-  extern __shared__ int2 tmpl_all[];
+                   float err_scale, const LKTmaps* __restrict__ tmaps_g) {
+  extern __shared__ __align__(128) int2 tmpl_all[];
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
   const int s = blockIdx.y;
   const int pt = blockIdx.x * V4_WARPS + warp;
   if (pt >= npts[s]) return;
   int2* tmpl = tmpl_all + warp * TMPL_WORDS + lane;      // this lane's column of the template: tmpl[row*32]
+  // TMA variant: per-warp 1 KB tile + mbarrier behind the templates
+  uint8_t* tile = reinterpret_cast<uint8_t*>(tmpl_all + V4_WARPS * TMPL_WORDS) + warp * TMA_TILE_BYTES;
+  unsigned long long* bar = reinterpret_cast<unsigned long long*>(reinterpret_cast<uint8_t*>(tmpl_all + V4_WARPS * TMPL_WORDS) + V4_WARPS * TMA_TILE_BYTES) + warp;
+  unsigned parity = 0;
+  if (TMA) {
+    if (lane == 0) {
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_addr(bar)) : "memory");
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+  }
   const size_t pidx = (size_t)s * max_pts + pt;
   const uint8_t* Ibase = pyrI + (size_t)s * g.stream_stride;
   const unsigned* Dbase = derivI + (size_t)s * g.stream_stride;
@@ -311,12 +367,14 @@ lk_track_kernel_v4(const uint8_t* __restrict__ pyrI, const unsigned* __restrict_
   for (int level = nlev_used - 1; level >= 0; --level) {
     int w, h, pitch;
     unsigned long long off;
+    const CUtensorMap* tm;
     switch (level) {
       case 0: w = g.w[0]; h = g.h[0]; pitch = g.pitch[0]; off = g.off[0]; break;
       case 1: w = g.w[1]; h = g.h[1]; pitch = g.pitch[1]; off = g.off[1]; break;
       case 2: w = g.w[2]; h = g.h[2]; pitch = g.pitch[2]; off = g.off[2]; break;
       default: w = g.w[3]; h = g.h[3]; pitch = g.pitch[3]; off = g.off[3]; break;
     }
+    tm = TMA ? &tmaps_g->lv[level] : nullptr;               // descriptors live in global memory (written once per context)
     const uint8_t* I = Ibase + off;
     const unsigned* Dv = Dbase + off;
     const uint8_t* J = Jbase + off;
@@ -363,7 +421,11 @@ lk_track_kernel_v4(const uint8_t* __restrict__ pyrI, const unsigned* __restrict_
         break;
       }
       bilinear_weights(cx - (float)inx, cy - (float)iny, w00, w01, w10, w11);
-      if (inx != cox || iny != coy) { load_patch(J, pitch, w, h, inx, iny, lane, P, Q); cox = inx; coy = iny; }
+      if (inx != cox || iny != coy) {
+        if (TMA && inx >= 0 && inx + 32 <= w && iny >= 0 && iny + 32 <= h) load_patch_tma(tm, tile, bar, parity, inx, iny, s, lane, P, Q);
+        else load_patch(J, pitch, w, h, inx, iny, lane, P, Q);
+        cox = inx; coy = iny;
+      }
       int b1 = 0, b2 = 0;
       window_pass<false>(P, Q, (w00 & 0xffff) | (w10 << 16), (w01 & 0xffff) | (w11 << 16), tmpl, live, b1, b2);
       const float fb1 = __ll2float_rn(warp_sum_exact(b1)) * FLT_SCALE;
@@ -387,7 +449,11 @@ lk_track_kernel_v4(const uint8_t* __restrict__ pyrI, const unsigned* __restrict_
         st = 0;
       } else {
         bilinear_weights(qx - (float)inx, qy - (float)iny, w00, w01, w10, w11);
-        if (inx != cox || iny != coy) { load_patch(J, pitch, w, h, inx, iny, lane, P, Q); cox = inx; coy = iny; }
+        if (inx != cox || iny != coy) {
+          if (TMA && inx >= 0 && inx + 32 <= w && iny >= 0 && iny + 32 <= h) load_patch_tma(tm, tile, bar, parity, inx, iny, s, lane, P, Q);
+          else load_patch(J, pitch, w, h, inx, iny, lane, P, Q);
+          cox = inx; coy = iny;
+        }
         int e = 0, unused = 0;
         window_pass<true>(P, Q, (w00 & 0xffff) | (w10 << 16), (w01 & 0xffff) | (w11 << 16), tmpl, live, e, unused);
         er = __ll2float_rn(warp_sum_exact(e)) * err_scale;
@@ -403,6 +469,32 @@ lk_track_kernel_v4(const uint8_t* __restrict__ pyrI, const unsigned* __restrict_
 }
 
 }  // namespace
+
+// tensor maps of the second image's pyramid levels: u8 [S][h][w] with the level's row pitch / the slot's stream stride
+static int lk_make_tmaps(flv_ctx* ctx, int slot, LKTmaps& out) {
+  typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                               const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                               CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+  static EncodeFn encode = nullptr;
+  if (!encode) {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qr;
+    FLV_CUDA(ctx, cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qr));
+    if (!fn || qr != cudaDriverEntryPointSuccess) FLV_FAIL(ctx, FLV_ERR_CUDA, "cuTensorMapEncodeTiled not available");
+    encode = (EncodeFn)fn;
+  }
+  memset(&out, 0, sizeof(out));
+  for (int l = 0; l < ctx->geom.nlev; ++l) {
+    const cuuint64_t dims[3] = {(cuuint64_t)ctx->geom.lv[l].w, (cuuint64_t)ctx->geom.lv[l].h, (cuuint64_t)ctx->S};
+    const cuuint64_t strides[2] = {(cuuint64_t)ctx->geom.lv[l].pitch, (cuuint64_t)ctx->geom.stream_stride};
+    const cuuint32_t box[3] = {TMA_BOX_W, 32, 1}, estr[3] = {1, 1, 1};
+    const CUresult r = encode(&out.lv[l], CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, ctx->pyr[slot] + ctx->geom.lv[l].off, dims, strides, box,
+                              estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) FLV_FAIL(ctx, FLV_ERR_CUDA, "cuTensorMapEncodeTiled(level %d) failed: %d", l, (int)r);
+  }
+  return FLV_OK;
+}
 
 int flv_launch_lk_v4(flv_ctx* ctx, int src_slot, int dst_slot, int n_streams, const int* d_npts,
                      const float* d_prev, const float* d_init, float* d_next, uint8_t* d_status,
@@ -430,18 +522,37 @@ int flv_launch_lk_v4(flv_ctx* ctx, int src_slot, int dst_slot, int n_streams, co
     FLV_CUDA(ctx, cudaGetLastError());
     ctx->deriv_streams[src_slot] = n_streams;
   }
-  const size_t smem = (size_t)V4_WARPS * TMPL_WORDS * sizeof(int2);
+  const bool tma = getenv("FLV_LK_VARIANT") && atoi(getenv("FLV_LK_VARIANT")) == 7;
+  const size_t smem = (size_t)V4_WARPS * TMPL_WORDS * sizeof(int2) + (tma ? V4_WARPS * (TMA_TILE_BYTES + 8) : 0);
   if (!ctx->attr_lk4) {          // per context (= per device): function attributes do not carry across devices
-    FLV_CUDA(ctx, cudaFuncSetAttribute(lk_track_kernel_v4, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    FLV_CUDA(ctx, cudaFuncSetAttribute(lk_track_kernel_v4, cudaFuncAttributePreferredSharedMemoryCarveout,
+    FLV_CUDA(ctx, cudaFuncSetAttribute(lk_track_kernel_v4<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    FLV_CUDA(ctx, cudaFuncSetAttribute(lk_track_kernel_v4<false>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                       getenv("FLV_LK_CARVEOUT") ? atoi(getenv("FLV_LK_CARVEOUT")) : 75));
+    FLV_CUDA(ctx, cudaFuncSetAttribute(lk_track_kernel_v4<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)((size_t)V4_WARPS * TMPL_WORDS * sizeof(int2) + V4_WARPS * (TMA_TILE_BYTES + 8))));
+    FLV_CUDA(ctx, cudaFuncSetAttribute(lk_track_kernel_v4<true>, cudaFuncAttributePreferredSharedMemoryCarveout,
                                        getenv("FLV_LK_CARVEOUT") ? atoi(getenv("FLV_LK_CARVEOUT")) : 75));
     ctx->attr_lk4 = 1;
   }
   dim3 grid((ctx->max_pts + V4_WARPS - 1) / V4_WARPS, n_streams);
   const float err_scale = (float)(1.0 / (32 * WIN * WIN));
-  lk_track_kernel_v4<<<grid, V4_WARPS * 32, smem, ctx->stream>>>(
+  if (tma) {
+    if (!ctx->d_lk_tmaps) {      // one descriptor set per image slot, encoded once (the pyramids never move)
+      FLV_CUDA(ctx, cudaMalloc(&ctx->d_lk_tmaps, FLV_NUM_SLOTS * sizeof(LKTmaps)));
+      for (int sl = 0; sl < FLV_NUM_SLOTS; ++sl) {
+        LKTmaps maps;
+        int rc = lk_make_tmaps(ctx, sl, maps);
+        if (rc) return rc;
+        FLV_CUDA(ctx, cudaMemcpy((LKTmaps*)ctx->d_lk_tmaps + sl, &maps, sizeof(maps), cudaMemcpyHostToDevice));
+      }
+    }
+    lk_track_kernel_v4<true><<<grid, V4_WARPS * 32, smem, ctx->stream>>>(
+        ctx->pyr[src_slot], ctx->deriv[src_slot], ctx->pyr[dst_slot], g, d_npts, d_prev, d_init, d_next, d_status, d_err,
+        ctx->max_pts, nlev_used, max_iter, eps2, min_eig_thr, err_scale, (const LKTmaps*)ctx->d_lk_tmaps + dst_slot);
+  } else
+  lk_track_kernel_v4<false><<<grid, V4_WARPS * 32, smem, ctx->stream>>>(
       ctx->pyr[src_slot], ctx->deriv[src_slot], ctx->pyr[dst_slot], g, d_npts, d_prev, d_init, d_next, d_status, d_err,
-      ctx->max_pts, nlev_used, max_iter, eps2, min_eig_thr, err_scale);
+      ctx->max_pts, nlev_used, max_iter, eps2, min_eig_thr, err_scale, nullptr);
   ctx->launches++;
   FLV_CUDA(ctx, cudaGetLastError());
   return FLV_OK;

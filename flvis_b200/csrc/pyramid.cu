@@ -96,12 +96,25 @@ __device__ __forceinline__ unsigned hsum_pair(unsigned A, unsigned B, unsigned C
   return lo | (hi << 16);
 }
 
+// EQ: cv::equalizeHist is applied on the fly -- every source word goes through the stream's 256-entry LUT (lut_kernel, below)
+// held in shared memory, so the equalised image is never written to / re-read from a landing area.
+__device__ __forceinline__ unsigned lut4(const unsigned char* l, unsigned v) {
+  return (unsigned)l[v & 0xffu] | ((unsigned)l[(v >> 8) & 0xffu] << 8) | ((unsigned)l[(v >> 16) & 0xffu] << 16) | ((unsigned)l[v >> 24] << 24);
+}
+
+template <bool EQ>
 __global__ void __launch_bounds__(FUSED_WARPS * 32) ingest_l1_kernel(const uint8_t* __restrict__ src, size_t row_stride,
                                                                      size_t img_stride, uint8_t* __restrict__ slot_base,
                                                                      size_t stream_stride, size_t off0, int pitch0,
-                                                                     size_t off1, int pitch1, int w, int h, int ow, int oh) {
+                                                                     size_t off1, int pitch1, int w, int h, int ow, int oh,
+                                                                     const unsigned char* __restrict__ lut_g) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int s = blockIdx.z;
+  __shared__ unsigned char s_lut[256];
+  if (EQ) {
+    reinterpret_cast<unsigned short*>(s_lut)[threadIdx.x] = reinterpret_cast<const unsigned short*>(lut_g + (size_t)s * 256)[threadIdx.x];
+    __syncthreads();
+  }
   const int oy0 = (blockIdx.y * FUSED_WARPS + warp) * FUSED_ROWS;
   if (oy0 >= oh) return;
   const int X = blockIdx.x * 128 + 4 * lane;          // first input column of this lane's word
@@ -115,15 +128,16 @@ __global__ void __launch_bounds__(FUSED_WARPS * 32) ingest_l1_kernel(const uint8
     const int yr = y < 0 ? -y : (y >= h ? 2 * h - 2 - y : y);
     unsigned B = 0;
     if (act) B = *reinterpret_cast<const unsigned*>(img + (size_t)yr * row_stride + X);
+    if (EQ) B = lut4(s_lut, B);
     unsigned A = __shfl_up_sync(0xffffffffu, B, 1);
     unsigned C = __shfl_down_sync(0xffffffffu, B, 1);
     if (act) {
       if (lane == 0) {
         if (X == 0) A = __byte_perm(B, 0, 0x1244);     // columns -2,-1 -> 2,1 into bytes 2,3
-        else A = *reinterpret_cast<const unsigned*>(img + (size_t)yr * row_stride + X - 4);
+        else { A = *reinterpret_cast<const unsigned*>(img + (size_t)yr * row_stride + X - 4); if (EQ) A = lut4(s_lut, A); }
       }
       if (X + 4 >= w) C = (B >> 16) & 0xffu;            // column w -> w-2
-      else if (lane == 31) C = *reinterpret_cast<const unsigned*>(img + (size_t)yr * row_stride + X + 4);
+      else if (lane == 31) { C = *reinterpret_cast<const unsigned*>(img + (size_t)yr * row_stride + X + 4); if (EQ) C = lut4(s_lut, C); }
       if (y == yr && y >= y_lo && y < y_hi) *reinterpret_cast<unsigned*>(L0 + (size_t)y * pitch0 + X) = B;
     }
     return hsum_pair(A, B, C);
@@ -178,6 +192,29 @@ __global__ void __launch_bounds__(256) hist_kernel(const uint8_t* __restrict__ s
   if (sh[threadIdx.x]) atomicAdd(&hist[blockIdx.y * 256 + threadIdx.x], sh[threadIdx.x]);
 }
 
+// the LUT alone (one CTA per stream), for the fused ingest
+__global__ void __launch_bounds__(256) lut_kernel(const int* __restrict__ hist, int total, unsigned char* __restrict__ lut_g) {
+  __shared__ int sh[256];
+  __shared__ int s_i0;
+  const int t = threadIdx.x;
+  sh[t] = hist[blockIdx.x * 256 + t];
+  if (t == 0) s_i0 = 256;
+  __syncthreads();
+  if (sh[t]) atomicMin(&s_i0, t);
+  __syncthreads();
+  const int i0 = s_i0;
+  unsigned char o;
+  if (sh[i0] == total) o = (unsigned char)i0;
+  else {
+    const float scale = __fdiv_rn(255.f, (float)(total - sh[i0]));
+    int sum = 0;
+    for (int j = i0 + 1; j <= t; ++j) sum += sh[j];
+    const int v = t <= i0 ? 0 : __float2int_rn(__fmul_rn((float)sum, scale));
+    o = (unsigned char)(v > 255 ? 255 : v);
+  }
+  lut_g[blockIdx.x * 256 + t] = o;
+}
+
 __global__ void __launch_bounds__(256) equalize_apply_kernel(const uint8_t* __restrict__ src, size_t row_stride, size_t img_stride,
                                                              uint8_t* __restrict__ dst, int w, int h, const int* __restrict__ hist) {
   __shared__ int sh[256];
@@ -228,18 +265,46 @@ int flv_launch_equalize(flv_ctx* ctx, int n_streams, const uint8_t* d_src, size_
   return FLV_OK;
 }
 
+static bool fused_ingest_ok(const flv_ctx* ctx, const uint8_t* d_src, size_t row_stride, size_t img_stride) {
+  return ctx->geom.nlev > 1 && ctx->w % 4 == 0 && row_stride % 4 == 0 && img_stride % 4 == 0 &&
+         reinterpret_cast<size_t>(d_src) % 4 == 0 && !ctx->no_fused_ingest;
+}
+
+// cv::equalizeHist + ingest + first pyrDown without an equalised intermediate image: histogram -> LUT -> fused ingest that maps
+// every source word through the LUT.  Returns FLV_ERR_UNSUPPORTED when the fused ingest cannot run on this source (the caller
+// then equalises into a landing area and unpacks from there).
+int flv_launch_unpack_equalized(flv_ctx* ctx, int slot, int n_streams, const uint8_t* d_src, size_t row_stride, size_t img_stride) {
+  if (!fused_ingest_ok(ctx, d_src, row_stride, img_stride) || getenv("FLV_NO_FUSED_EQUALIZE")) return FLV_ERR_UNSUPPORTED;
+  if (!ctx->d_hist) FLV_CUDA(ctx, cudaMalloc(&ctx->d_hist, (size_t)ctx->S * 256 * sizeof(int)));
+  if (!ctx->d_lut) FLV_CUDA(ctx, cudaMalloc(&ctx->d_lut, (size_t)ctx->S * 256));
+  FLV_CUDA(ctx, cudaMemsetAsync(ctx->d_hist, 0, (size_t)n_streams * 256 * sizeof(int), ctx->stream));
+  dim3 hgrid((ctx->h + EQ_ROWS - 1) / EQ_ROWS, n_streams);
+  hist_kernel<<<hgrid, 256, 0, ctx->stream>>>(d_src, row_stride, img_stride, ctx->w, ctx->h, ctx->d_hist);
+  lut_kernel<<<n_streams, 256, 0, ctx->stream>>>(ctx->d_hist, ctx->w * ctx->h, (unsigned char*)ctx->d_lut);
+  const LevelGeom& L0 = ctx->geom.lv[0];
+  const LevelGeom& L1 = ctx->geom.lv[1];
+  ctx->deriv_streams[slot] = 0;
+  dim3 grid((ctx->w + 127) / 128, (L1.h + FUSED_ROWS * FUSED_WARPS - 1) / (FUSED_ROWS * FUSED_WARPS), n_streams);
+  ingest_l1_kernel<true><<<grid, FUSED_WARPS * 32, 0, ctx->stream>>>(d_src, row_stride, img_stride, ctx->pyr[slot],
+                                                                     ctx->geom.stream_stride, L0.off, L0.pitch, L1.off, L1.pitch,
+                                                                     ctx->w, ctx->h, L1.w, L1.h, (const unsigned char*)ctx->d_lut);
+  ctx->launches += 3;
+  FLV_CUDA(ctx, cudaGetLastError());
+  ctx->l1_valid[slot] = 1;
+  return FLV_OK;
+}
+
 int flv_launch_unpack(flv_ctx* ctx, int slot, int n_streams, const uint8_t* d_src, size_t row_stride,
                       size_t img_stride) {
   const LevelGeom& L0 = ctx->geom.lv[0];
   ctx->l1_valid[slot] = 0;
   ctx->deriv_streams[slot] = 0;
-  if (ctx->geom.nlev > 1 && ctx->w % 4 == 0 && row_stride % 4 == 0 && img_stride % 4 == 0 &&
-      reinterpret_cast<size_t>(d_src) % 4 == 0 && !ctx->no_fused_ingest) {
+  if (fused_ingest_ok(ctx, d_src, row_stride, img_stride)) {
     const LevelGeom& L1 = ctx->geom.lv[1];
     dim3 grid((ctx->w + 127) / 128, (L1.h + FUSED_ROWS * FUSED_WARPS - 1) / (FUSED_ROWS * FUSED_WARPS), n_streams);
-    ingest_l1_kernel<<<grid, FUSED_WARPS * 32, 0, ctx->stream>>>(d_src, row_stride, img_stride, ctx->pyr[slot],
+    ingest_l1_kernel<false><<<grid, FUSED_WARPS * 32, 0, ctx->stream>>>(d_src, row_stride, img_stride, ctx->pyr[slot],
                                                                  ctx->geom.stream_stride, L0.off, L0.pitch, L1.off, L1.pitch,
-                                                                 ctx->w, ctx->h, L1.w, L1.h);
+                                                                 ctx->w, ctx->h, L1.w, L1.h, nullptr);
     ctx->launches++;
     FLV_CUDA(ctx, cudaGetLastError());
     ctx->l1_valid[slot] = 1;
