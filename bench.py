@@ -50,8 +50,10 @@ WORKLOADS = {   # BASELINE.json configs: image size, sensor, local-BA window
                  name="640x480 D435i depth + IMU 200 Hz, 8-KF local BA (configs[0]/[4])"),
 }
 PERIOD = 40                                       # frames per period of the synthetic rig trajectory
-LK_NCU_TRAFFIC = {"euroc": None}                  # dram bytes per launch from profiles/ (filled in when a capture exists)
-LK_WARP_INSTR_PER_POINT = 13900.0                 # profiles/r01_final_kernels_ncu_full.csv: 212.9 M warp instructions / (32 x 480) points
+# profiles/r02_step_kernels_ncu_full.csv (ncu --set full inside the bench step, 32 sequences x 420 landmarks in one launch):
+# lk_track_kernel_v4 dram__bytes_read 91.6 MB + write 4.5 MB, 204.3 M warp instructions
+LK_NCU_TRAFFIC_PER_SEQUENCE = {"euroc": (91.59e6 + 4.53e6) / 32}
+LK_WARP_INSTR_PER_POINT = 204.3e6 / (32 * 420.5)
 
 
 def pyramid_pixels(w, h):
@@ -183,6 +185,23 @@ def _issue_roofline(lk_us, S, n_pts, sm_mhz):
             "frac": instr / (lk_us * 1e-6) / peak, "source": "instructions per point from the ncu capture in profiles/, time from this run"}
 
 
+def _ba_roofline(t, peak):
+    """per LM iteration K7 build 168 E + 392 P + 120 L, K8 Schur 144 E + 96 L + 288 Pf^2 + 48 Pf, K10 update 160 E + 120 L + 56 P
+    bytes (one trial per iteration counted: a lower bound), against the wall time of the solver calls."""
+    n = t["solves"]
+    if not n or t["solve_ms"] <= 0:
+        return None
+    E, L, P, it = t["edges"] / n, t["landmarks"] / n, t["poses"] / n, t["lm_iterations"] / n
+    Pf = max(P - 1, 0)
+    per_iter = (168 * E + 392 * P + 120 * L) + (144 * E + 96 * L + 288 * Pf * Pf + 48 * Pf) + (160 * E + 120 * L + 56 * P)
+    alg = per_iter * it
+    gbs = alg * n / (t["solve_ms"] * 1e-3) / 1e9
+    return {"kernel": "ba_kernel (local map windows, cluster of 4 CTAs per window)", "bound": "hbm", "unit": "GB/s", "achieved": gbs, "peak": peak,
+            "frac": gbs / peak, "algorithmic_bytes_per_window": alg, "mean_edges": E, "mean_landmarks": L, "mean_poses": P, "mean_lm_iterations": it,
+            "note": "aggregate over the windows solved concurrently; a window's working set (< 1 MB) lives in L2 / shared memory, "
+                    "the kernel is latency-bound (barrier and dependent-load stalls, profiles/README.md), not HBM-bound"}
+
+
 # ------------------------------------------------------------------------------------------------
 def run_ours(args, wl, pools):
     import torch
@@ -291,7 +310,7 @@ def run_ours(args, wl, pools):
     if sampler:
         sampler.start()
     trk.set_profile(True)
-    dev_runs, e2e_runs, launches, ba_tot = [], [], 0, dict(keyframes=0, solves=0, launches=0, solve_ms=0.0, host_ms=0.0)
+    dev_runs, e2e_runs, launches, ba_tot = [], [], 0, dict(keyframes=0, solves=0, launches=0, solve_ms=0.0, host_ms=0.0, edges=0.0, landmarks=0.0, poses=0.0, lm_iterations=0.0)
     for r in range(args.reps):
         ms, nl, ba = region(trk, lmap, args.steps, "device")
         dev_runs.append(ms); launches = nl
@@ -389,13 +408,16 @@ def run_ours(args, wl, pools):
                            "windows it solved; the worker overlaps the tracker's kernels",
                    "window": wl["window"], "keyframes": ba_tot["keyframes"], "solves": ba_tot["solves"],
                    "windows_per_launch": ba_tot["solves"] / max(ba_tot["launches"], 1),
+                   "roofline": _ba_roofline(ba_tot, peak),
                    "keyframes_per_step": ba_tot["keyframes"] / (args.reps * args.steps)},
             "ate": {"vs_ground_truth_m_mean": float(np.mean(ates)) if ates else None, "vs_ground_truth_m_max": float(np.max(ates)) if ates else None,
                     "frames": args.steps, "note": "RMSE of the camera centres against the synthetic rig trajectory over the first timed "
                                                   "region; ATE against the reference path is asserted in tests/test_configs_gpu.py"},
             "single_stream": single,
             "roofline": {"kernel": "lk_track_kernel_v4 (frame->frame call)", "bound": "hbm", "achieved": achieved, "peak": peak,
-                         "unit": "GB/s", "frac": achieved / peak, "traffic": LK_NCU_TRAFFIC.get(args.workload),
+                         "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": (LK_NCU_TRAFFIC_PER_SEQUENCE[args.workload] * S / max(trk.groups, 1)) if args.workload in LK_NCU_TRAFFIC_PER_SEQUENCE else None,
+                         "traffic_note": "dram read + write of one ncu --set full capture (cold L2, 32 sequences per launch), scaled to this run's sequences per launch",
                          "peak_source": peak_src, "us_per_launch": lk_us, "us_per_launch_left_right": lk_lr_us,
                          "algorithmic_bytes_per_launch": alg,
                          "algorithmic_bytes_def": "SURVEY.md 8(d): (2 P(w,h) + 29 N) x S, P = pyramid pixels, N = mean tracked points per sequence",
@@ -410,11 +432,34 @@ def run_ours(args, wl, pools):
         }
         if cpu:
             out["cpu_baseline"] = cpu
-        print(json.dumps(out))
     trk.close(); lmap.close()
+    if out is not None:
+        if world == 1 and not args.no_others and args.workload == "euroc":
+            out["other_workloads"] = other_workloads(args, S)
+        print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()
     return out
+
+
+def other_workloads(args, S):
+    """BASELINE.json's other configurations (KITTI-shaped stereo, W=20; D435i depth + IMU, W=8) through the same bench, shortened
+    (2 repetitions of <= 10 steps, no CPU legs), each in its own process after this one released the GPU."""
+    res = {}
+    for name in ("kitti", "d435"):
+        cmd = [sys.executable, os.path.abspath(__file__), "--workload", name, "--reps", "2", "--steps", str(min(args.steps, 10)), "--warmup", "3",
+               "--streams", str(S), "--groups", str(args.groups), "--no-cpu", "--no-single", "--no-others"]
+        try:
+            r = subprocess.run(cmd, capture_output=True, text=True, timeout=300)
+            line = [l for l in r.stdout.splitlines() if l.startswith("{")][-1]
+            j = json.loads(line)
+            res[name] = {"workload": j["config"]["workload"], "value": j["value"], "e2e": j["e2e"]["value"], "unit": "frames/s",
+                         "ms_per_step": j["ms_per_step"], "steps": j["steps"], "repetitions": j["config"]["repetitions"],
+                         "ba_window": j["ba"]["window"], "ba_ms_per_kf": j["ba"]["ms_per_kf"], "keyframes_per_step": j["ba"]["keyframes_per_step"],
+                         "ate_vs_ground_truth_m_mean": j["ate"]["vs_ground_truth_m_mean"]}
+        except Exception as e:                      # a side measurement must not take the headline line down
+            res[name] = {"error": repr(e)[:200]}
+    return res
 
 
 # ------------------------------------------------------------------------------------------------
@@ -541,6 +586,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-single", action="store_true", help="skip the single-stream leg")
+    ap.add_argument("--no-others", action="store_true", help="skip the short kitti / d435 side measurements (N=1, euroc only)")
     ap.add_argument("--workload", default="euroc", choices=sorted(WORKLOADS), help="euroc = the headline (default)")
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]

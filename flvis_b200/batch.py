@@ -77,6 +77,7 @@ def _bind(lib):
     lib.flv_localmap_batch_destroy.argtypes = [vp]
     lib.flv_localmap_batch_wait.argtypes = [vp]
     lib.flv_localmap_batch_stats.argtypes = [vp] * 5
+    lib.flv_localmap_batch_problem_totals.argtypes = [vp, vp]
     lib.flv_localmap_batch_last_error.restype = C.c_char_p
     lib.flv_localmap_batch_last_error.argtypes = [vp]
     lib.flv_set_stream.argtypes = [vp, vp]
@@ -98,7 +99,10 @@ class LocalMapBatch:
     def stats(self):
         nk = C.c_longlong(); ns = C.c_longlong(); nl = C.c_longlong(); ms = (C.c_double * 2)()
         self.lib.flv_localmap_batch_stats(self.h, C.byref(nk), C.byref(ns), C.byref(nl), ms)
-        return dict(keyframes=nk.value, solves=ns.value, launches=nl.value, solve_ms=ms[0], host_ms=ms[1])
+        tot = (C.c_double * 4)()
+        self.lib.flv_localmap_batch_problem_totals(self.h, tot)
+        return dict(keyframes=nk.value, solves=ns.value, launches=nl.value, solve_ms=ms[0], host_ms=ms[1],
+                    edges=tot[0], landmarks=tot[1], poses=tot[2], lm_iterations=tot[3])
 
     def close(self):
         if self.h:

@@ -283,10 +283,11 @@ int flv_launch_lk(flv_ctx* ctx, int src_slot, int dst_slot, int n_streams, const
   dim3 grid((ctx->max_pts + WARPS - 1) / WARPS, n_streams);
   const float err_scale = (float)(1.0 / (32 * WIN * WIN));
   // two register budgets of the same kernel: 168 regs / 12 warps per SM (no spills) or 128 regs / 16 warps per SM
-  // default: v4 (lk_v4.cu: precomputed Scharr pyramid, packed register patch, DP2A blend); FLV_LK_VARIANT selects the
-  // earlier kernels (1 = register template, 3/4 = v2 register budgets, 5 = shared-memory template) for A/B runs
-  const int variant = getenv("FLV_LK_VARIANT") ? atoi(getenv("FLV_LK_VARIANT")) : 6;
-  if (variant == 6 || variant == 7)     // 7 = v4 with the second image's patch staged by TMA (measured A/B, see lk_v4.cu)
+  // default: v4 (lk_v4.cu: precomputed Scharr pyramid, packed register patch, DP2A blend) with the second image's patch staged
+  // by TMA (7; measured 325 vs 330 us against the plain loads of 6, bit-identical); FLV_LK_VARIANT selects the earlier kernels
+  // (1 = register template, 3/4 = v2 register budgets, 5 = shared-memory template, 6 = v4 without TMA) for A/B runs
+  const int variant = getenv("FLV_LK_VARIANT") ? atoi(getenv("FLV_LK_VARIANT")) : 7;
+  if (variant == 6 || variant == 7)
     return flv_launch_lk_v4(ctx, src_slot, dst_slot, n_streams, d_npts, d_prev, d_init, d_next, d_status, d_err, nlev_used,
                             max_iter, eps2, min_eig_thr);
   if (variant == 5)

@@ -14,7 +14,7 @@
 //     4 IMAD + load + shuffle.  The patch is only reloaded when the integer window origin moves.
 // Reference call sites: src/processing/lkorb_tracking.cpp:64-73, src/processing/camera_frame.cpp:124-128.
 //
-// FLV_LK_VARIANT=7 is the measured TMA A/B of the patch staging: the 32x32 u8 patch of the second image comes through a
+// FLV_LK_VARIANT=7 (the default since it measured faster; 6 = plain loads) is the TMA form of the patch staging: the 32x32 u8 patch of the second image comes through a
 // cp.async.bulk.tensor.3d load (one tensor map per pyramid level: x, y, stream; box 32x32x1) into a per-warp shared-memory
 // tile (48 x 32: tile loads start on 16-byte boundaries) and is packed into the same registers from there; everything else is
 // identical.  Numbers: profiles/README.md.
@@ -522,7 +522,7 @@ int flv_launch_lk_v4(flv_ctx* ctx, int src_slot, int dst_slot, int n_streams, co
     FLV_CUDA(ctx, cudaGetLastError());
     ctx->deriv_streams[src_slot] = n_streams;
   }
-  const bool tma = getenv("FLV_LK_VARIANT") && atoi(getenv("FLV_LK_VARIANT")) == 7;
+  const bool tma = !(getenv("FLV_LK_VARIANT") && atoi(getenv("FLV_LK_VARIANT")) == 6);      // default: TMA patch staging
   const size_t smem = (size_t)V4_WARPS * TMPL_WORDS * sizeof(int2) + (tma ? V4_WARPS * (TMA_TILE_BYTES + 8) : 0);
   if (!ctx->attr_lk4) {          // per context (= per device): function attributes do not carry across devices
     FLV_CUDA(ctx, cudaFuncSetAttribute(lk_track_kernel_v4<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -93,6 +93,7 @@ struct LmShard {
   bool stop = false, busy = false, failed = false, started = false;
   long long n_keyframes = 0, n_solves = 0, n_launches = 0;
   double solve_ms = 0, host_ms = 0;            // solver calls / graph editing + packing on the worker thread
+  double sum_edges = 0, sum_lms = 0, sum_poses = 0, sum_iters = 0;   // problem sizes / LM iterations of the solved windows
   int rP = 0, rL = 0, rE = 0;
   std::unique_ptr<Helpers> helpers;
   std::vector<double> poses, lms, uv; std::vector<int> ep, el; std::vector<uint8_t> act;
@@ -159,6 +160,7 @@ bool LmShard::process(std::vector<KfMsg>& batch) {
     }
     solve_ms += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
     n_solves += (long long)n; n_launches++;
+    for (size_t j = 0; j < n; ++j) { sum_edges += pb[j].n_edges; sum_lms += pb[j].n_landmarks; sum_poses += pb[j].n_poses; sum_iters += st[j].iterations_run; }
     std::vector<flv::CorrectionInfStruct> outs(n);
     helpers->parallel_for((int)n, [&](int jj) {
       const size_t j = (size_t)jj;
@@ -338,6 +340,17 @@ int flv_localmap_batch_stats(flv_localmap_batch* b, long long* n_keyframes, long
   if (n_solves) *n_solves = ns;
   if (n_launches) *n_launches = nl;
   if (solve_ms) { solve_ms[0] = ms; solve_ms[1] = hms; }   // solve_ms is double[2]: {solver calls, graph editing + packing}, summed over shards
+  return FLV_OK;
+}
+
+int flv_localmap_batch_problem_totals(flv_localmap_batch* b, double* totals4) {
+  if (!b || !totals4) return FLV_ERR_INVALID;
+  for (int i = 0; i < 4; ++i) totals4[i] = 0;
+  for (auto& shp : b->shards) {
+    LmShard* sh = shp.get();
+    std::lock_guard<std::mutex> lk(sh->mu);
+    totals4[0] += sh->sum_edges; totals4[1] += sh->sum_lms; totals4[2] += sh->sum_poses; totals4[3] += sh->sum_iters;
+  }
   return FLV_OK;
 }
 

@@ -147,6 +147,8 @@ int flv_localmap_batch_submit(flv_localmap_batch* b, int n_kf, const int* stream
 int flv_localmap_batch_wait(flv_localmap_batch* b);
 /* solve_ms2 = {wall ms inside the solver calls, wall ms of graph editing + array packing on the worker thread} */
 int flv_localmap_batch_stats(flv_localmap_batch* b, long long* n_keyframes, long long* n_solves, long long* n_launches, double* solve_ms2);
+/* totals over all windows solved so far: {edges, landmarks, poses, LM iterations} (for the BA roofline: SURVEY.md 8(d) bytes) */
+int flv_localmap_batch_problem_totals(flv_localmap_batch* b, double* totals4);
 int flv_localmap_batch_result(flv_localmap_batch* b, int stream, int64_t* out_frame_id, double* out_T_c_w, int* out_lm_count,
                               int64_t* out_lm_id, double* out_lm_3d, int lm_cap, int* out_outlier_count, int64_t* out_outlier_id,
                               int outlier_cap);
