@@ -90,7 +90,7 @@ class LocalMapBatch:
         self.lib = _bind(lib or capi.load_library())
         self.h = self.lib.flv_localmap_batch_create(device, n_streams, window, *[float(v) for v in K])
         if not self.h:
-            raise capi.FlvError("flv_localmap_batch_create failed (window must be 3..25)")
+            raise capi.FlvError("flv_localmap_batch_create failed (window must be 3..100)")
 
     def wait(self):
         if self.lib.flv_localmap_batch_wait(self.h) != 0:

@@ -30,6 +30,7 @@
 //           pose (exp map), chi2 block reduction
 // Algorithmic bytes: build 168E+392P+120L, Schur 144E+96L+288Pf^2+48Pf per trial.
 #include "ctx.h"
+#include "ba_math.h"
 #include <cooperative_groups.h>
 
 namespace cg = cooperative_groups;
@@ -55,123 +56,8 @@ struct BAArgs {
   double* trace;     // [S][BA_TRACE_ITERS][4] per LM iteration: chi2 at the end, lambda, rho of the last trial, trials
   int dyn_doubles;   // dynamic shared memory of the launch, in doubles
   int member_buf;    // ints of shared memory for TMA-staged pose-pair member lists (0 = read them from L2; see BA_MEMBER_BUF)
+  int ws_poses;      // pose capacity the workspace layout was computed for (min(max_poses, BA_MAX_POSES))
 };
-
-// ---- SE3 helpers (g2o SE3Quat semantics, quaternion stored x,y,z,w) ----------------------------
-__device__ __forceinline__ void q_rotate(const double* q, const double* v, double* o) {
-  double ux = q[1] * v[2] - q[2] * v[1], uy = q[2] * v[0] - q[0] * v[2], uz = q[0] * v[1] - q[1] * v[0];
-  ux += ux; uy += uy; uz += uz;
-  o[0] = v[0] + q[3] * ux + (q[1] * uz - q[2] * uy);
-  o[1] = v[1] + q[3] * uy + (q[2] * ux - q[0] * uz);
-  o[2] = v[2] + q[3] * uz + (q[0] * uy - q[1] * ux);
-}
-__device__ __forceinline__ void q_to_R(const double* q, double* R) {
-  double tx = 2 * q[0], ty = 2 * q[1], tz = 2 * q[2];
-  double twx = tx * q[3], twy = ty * q[3], twz = tz * q[3];
-  double txx = tx * q[0], txy = ty * q[0], txz = tz * q[0];
-  double tyy = ty * q[1], tyz = tz * q[1], tzz = tz * q[2];
-  R[0] = 1 - (tyy + tzz); R[1] = txy - twz; R[2] = txz + twy;
-  R[3] = txy + twz; R[4] = 1 - (txx + tzz); R[5] = tyz - twx;
-  R[6] = txz - twy; R[7] = tyz + twx; R[8] = 1 - (txx + tyy);
-}
-__device__ void R_to_q(const double* m, double* q) {
-  double t = m[0] + m[4] + m[8];
-  if (t > 0) {
-    t = sqrt(t + 1.0);
-    q[3] = 0.5 * t; t = 0.5 / t;
-    q[0] = (m[7] - m[5]) * t; q[1] = (m[2] - m[6]) * t; q[2] = (m[3] - m[1]) * t;
-  } else {
-    int i = 0;
-    if (m[4] > m[0]) i = 1;
-    if (m[8] > m[4 * i]) i = 2;
-    int j = (i + 1) % 3, k = (j + 1) % 3;
-    t = sqrt(m[4 * i] - m[4 * j] - m[4 * k] + 1.0);
-    double qq[3];
-    qq[i] = 0.5 * t; t = 0.5 / t;
-    q[3] = (m[3 * k + j] - m[3 * j + k]) * t;
-    qq[j] = (m[3 * j + i] + m[3 * i + j]) * t;
-    qq[k] = (m[3 * k + i] + m[3 * i + k]) * t;
-    q[0] = qq[0]; q[1] = qq[1]; q[2] = qq[2];
-  }
-}
-__device__ void pose_oplus(double* pose, const double* u) {   // pose <- exp(u) * pose  (se3quat.h:218-260, :99-105)
-  const double wx = u[0], wy = u[1], wz = u[2];
-  const double theta = sqrt(wx * wx + wy * wy + wz * wz);
-  const double O[9] = {0, -wz, wy, wz, 0, -wx, -wy, wx, 0};
-  double O2[9];
-#pragma unroll
-  for (int r = 0; r < 3; ++r)
-#pragma unroll
-    for (int c = 0; c < 3; ++c) O2[3 * r + c] = O[3 * r] * O[c] + O[3 * r + 1] * O[3 + c] + O[3 * r + 2] * O[6 + c];
-  double a, b, d;
-  if (theta < 0.00001) { a = 1.0; b = 0.5; d = 1.0 / 6.0; }
-  else { a = sin(theta) / theta; b = (1 - cos(theta)) / (theta * theta); d = (theta - sin(theta)) / (theta * theta * theta); }
-  double R[9], V[9];
-#pragma unroll
-  for (int i = 0; i < 9; ++i) {
-    const double id = (i == 0 || i == 4 || i == 8) ? 1.0 : 0.0;
-    R[i] = id + a * O[i] + b * O2[i];
-    V[i] = id + b * O[i] + d * O2[i];
-  }
-  double qe[4], te[3], rt[3];
-  R_to_q(R, qe);
-#pragma unroll
-  for (int r = 0; r < 3; ++r) te[r] = V[3 * r] * u[3] + V[3 * r + 1] * u[4] + V[3 * r + 2] * u[5];
-  q_rotate(qe, pose + 4, rt);
-  const double* b4 = pose;
-  double x = qe[3] * b4[0] + qe[0] * b4[3] + qe[1] * b4[2] - qe[2] * b4[1];
-  double y = qe[3] * b4[1] + qe[1] * b4[3] + qe[2] * b4[0] - qe[0] * b4[2];
-  double z = qe[3] * b4[2] + qe[2] * b4[3] + qe[0] * b4[1] - qe[1] * b4[0];
-  double w = qe[3] * b4[3] - qe[0] * b4[0] - qe[1] * b4[1] - qe[2] * b4[2];
-  if (w < 0) { x = -x; y = -y; z = -z; w = -w; }
-  const double nn = sqrt(x * x + y * y + z * z + w * w);
-  pose[0] = x / nn; pose[1] = y / nn; pose[2] = z / nn; pose[3] = w / nn;
-  pose[4] = te[0] + rt[0]; pose[5] = te[1] + rt[1]; pose[6] = te[2] + rt[2];
-}
-
-struct Cam { double fx, fy, cx, cy; };
-
-// residual r (2), optional A = d r / d point (2x3), B = d r / d pose (2x6).  One fp64 division per edge:
-// the reference's x/z, y/z, 1/z, x*y/z^2 ... are evaluated with iz = 1/z (differences ~1 ulp, tolerance-checked).
-template <bool JAC>
-__device__ __forceinline__ void edge_eval(const double* pose, const double* X, const double* uv, const Cam& c,
-                                          double* r, double* A, double* B) {
-  double Xc[3];
-  q_rotate(pose, X, Xc);
-  const double x = Xc[0] + pose[4], y = Xc[1] + pose[5], z = Xc[2] + pose[6];
-  const double iz = 1.0 / z;
-  const double xz = x * iz, yz = y * iz;
-  r[0] = uv[0] - (xz * c.fx + c.cx);
-  r[1] = uv[1] - (yz * c.fy + c.cy);
-  if (JAC) {
-    double R[9];
-    q_to_R(pose, R);
-    const double t02 = -xz * c.fx, t12 = -yz * c.fy, miz = -iz;
-#pragma unroll
-    for (int k = 0; k < 3; ++k) {
-      A[k] = miz * (c.fx * R[k] + t02 * R[6 + k]);
-      A[3 + k] = miz * (c.fy * R[3 + k] + t12 * R[6 + k]);
-    }
-    B[0] = xz * yz * c.fx; B[1] = -(1 + xz * xz) * c.fx; B[2] = yz * c.fx;
-    B[3] = miz * c.fx; B[4] = 0; B[5] = xz * iz * c.fx;
-    B[6] = (1 + yz * yz) * c.fy; B[7] = -xz * yz * c.fy; B[8] = -xz * c.fy;
-    B[9] = 0; B[10] = miz * c.fy; B[11] = yz * iz * c.fy;
-  }
-}
-
-// W = rho' B^T A of one edge (6x3, w[3 i + j]): recomputed where it is needed instead of being stored -- every pass of this
-// kernel waits on memory, not on the fp64 pipe, and 150 flops cost less than nine 16-byte round trips per edge
-__device__ __forceinline__ void edge_W(const double* pose, const double* X, const double* uv, const Cam& cam, double delta,
-                                       double d2, double* w) {
-  double r[2], A[6], B[12];
-  edge_eval<true>(pose, X, uv, cam, r, A, B);
-  const double c = r[0] * r[0] + r[1] * r[1];
-  const double rho1 = (c <= d2) ? 1.0 : delta / sqrt(c);
-#pragma unroll
-  for (int i = 0; i < 6; ++i)
-#pragma unroll
-    for (int j = 0; j < 3; ++j) w[3 * i + j] = rho1 * (B[i] * A[j] + B[6 + i] * A[3 + j]);
-}
 
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
@@ -1076,7 +962,7 @@ __global__ void __launch_bounds__(BA_THREADS, 1) ba_kernel(BAArgs a) {
   const int P = pb.n_poses, E = pb.n_edges;
   Ws ws;
   {
-    const WsLayout lo = ws_layout(a.max_poses, a.max_lms, a.max_edges);
+    const WsLayout lo = ws_layout(a.ws_poses, a.max_lms, a.max_edges);
     double* d = (double*)(a.ws + (size_t)s * a.ws_stride);
     int* ib = (int*)(d + lo.n_doubles);
     ws.pbk = d + lo.pbk; ws.lbk = d + lo.lbk; ws.luv = d + lo.luv;
@@ -1084,7 +970,7 @@ __global__ void __launch_bounds__(BA_THREADS, 1) ba_kernel(BAArgs a) {
     ws.tab = ib + lo.tab; ws.lmask = (unsigned*)(ib + lo.lmask); ws.slot_e = ib + lo.slot_e; ws.slot_pl = ib + lo.slot_pl; ws.slot_lp = ib + lo.slot_lp; ws.csr_p = ib + lo.csr_p; ws.csr_l = ib + lo.csr_l;
     ws.lw = ib + lo.lw; ws.lstart = ib + lo.lstart; ws.cp_off = ib + lo.cp_off; ws.poff = ib + lo.poff;
     ws.pairs = ib + lo.pairs;
-    ws.pair_cap = (int)pair_capacity(a.max_poses, a.max_edges); ws.ME = a.max_edges; ws.ML = a.max_lms;
+    ws.pair_cap = (int)pair_capacity(a.ws_poses, a.max_edges); ws.ME = a.max_edges; ws.ML = a.max_lms;
   }
   const double delta = a.prm.huber_delta;
   flv_ba_stats st;
@@ -1256,6 +1142,13 @@ int ba_cluster_size(flv_ctx* ctx) {
 
 }  // namespace
 
+// large windows (26 .. 100 poses): ba_big.cu
+size_t flv_ba_big_ws_bytes(int max_poses, int max_lms, int max_edges);
+int flv_ba_big_max_poses();
+cudaError_t flv_ba_big_launch(int n_streams, const flv_ba_problem* d_problems, const flv_ba_params* prm, double* d_poses, double* d_lms,
+                              const int* d_ep, const int* d_el, const double* d_uv, uint8_t* d_act, flv_ba_stats* d_stats, int max_poses,
+                              int max_lms, int max_edges, unsigned char* d_ws, double* d_trace, cudaStream_t stream);
+
 int flv_ba_free(flv_ctx* ctx) {
   if (ctx->ba_ws) cudaFree(ctx->ba_ws);
   ctx->ba_ws = nullptr; ctx->ba_ws_bytes = 0;
@@ -1266,9 +1159,8 @@ extern "C" {
 
 int flv_ba_reserve(flv_ctx* ctx, int max_poses, int max_landmarks, int max_edges) {
   if (!ctx || max_poses < 1 || max_landmarks < 1 || max_edges < 1) return FLV_ERR_INVALID;
-  if (max_poses > BA_MAX_POSES)
-    FLV_FAIL(ctx, FLV_ERR_UNSUPPORTED, "window of %d poses: this build supports <= %d (<= %d free poses)", max_poses,
-             BA_MAX_POSES, BA_MAX_FREE);
+  if (max_poses > flv_ba_big_max_poses())
+    FLV_FAIL(ctx, FLV_ERR_UNSUPPORTED, "window of %d poses: this build supports <= %d", max_poses, flv_ba_big_max_poses());
   // already large enough: nothing to do (the host tracker reserves per frame; a realloc would synchronise the device)
   if (ctx->ba_ws && max_poses <= ctx->ba_max_poses && max_landmarks <= ctx->ba_max_lms && max_edges <= ctx->ba_max_edges) return FLV_OK;
   if (ctx->ba_ws) {                        // grow: keep the union of the old and new capacities
@@ -1278,7 +1170,11 @@ int flv_ba_reserve(flv_ctx* ctx, int max_poses, int max_landmarks, int max_edges
     FLV_CUDA(ctx, cudaDeviceSynchronize());
   }
   flv_ba_free(ctx);
-  size_t stride = ws_stride_bytes(max_poses, max_landmarks, max_edges);
+  // windows with more than BA_MAX_FREE + 1 poses run on the global-memory solver (ba_big.cu): its workspace also holds the
+  // reduced camera system; the per-stream stride is the larger of the two layouts
+  size_t stride = ws_stride_bytes(max_poses < BA_MAX_POSES ? max_poses : BA_MAX_POSES, max_landmarks, max_edges);
+  if (max_poses > BA_MAX_FREE + 1) { const size_t b = flv_ba_big_ws_bytes(max_poses, max_landmarks, max_edges); stride = b > stride ? b : stride; }
+  ctx->ba_ws_stride = stride;
   // tail: device copies of problems / stats / staging are carved after the per-stream blocks
   size_t total = stride * ctx->S + (size_t)ctx->S * (sizeof(flv_ba_problem) + sizeof(flv_ba_stats) + 128 + BA_TRACE_ITERS * 32) + 512;
   FLV_CUDA(ctx, cudaMalloc(&ctx->ba_ws, total));
@@ -1298,7 +1194,7 @@ int flv_ba_optimize(flv_ctx* ctx, int n_streams, const flv_ba_problem* problems,
     return FLV_ERR_INVALID;
   if (!ctx->ba_ws) FLV_FAIL(ctx, FLV_ERR_INVALID, "flv_ba_reserve has not been called");
   const int MP = ctx->ba_max_poses, ML = ctx->ba_max_lms, ME = ctx->ba_max_edges;
-  const size_t stride = ws_stride_bytes(MP, ML, ME);
+  const size_t stride = ctx->ba_ws_stride;
   unsigned char* tail = (unsigned char*)ctx->ba_ws + stride * ctx->S;
   const int slot0 = prm->ws_slot0;
   if (slot0 < 0 || slot0 + n_streams > ctx->S) FLV_FAIL(ctx, FLV_ERR_INVALID, "ws_slot0 %d + %d streams exceeds %d slots", slot0, n_streams, ctx->S);
@@ -1309,6 +1205,9 @@ int flv_ba_optimize(flv_ctx* ctx, int n_streams, const flv_ba_problem* problems,
   a.trace = (double*)(tail + (size_t)ctx->S * (sizeof(flv_ba_problem) + sizeof(flv_ba_stats) + 128)) + (size_t)BA_TRACE_ITERS * 4 * slot0;
   a.prm = *prm; a.max_poses = MP; a.max_lms = ML; a.max_edges = ME;
   a.ws = (unsigned char*)ctx->ba_ws + stride * slot0; a.ws_stride = stride;
+  // ba_kernel's own layout is computed for min(MP, BA_MAX_POSES) poses (reserve does the same)
+  const int MPk = MP < BA_MAX_POSES ? MP : BA_MAX_POSES;
+  a.ws_poses = MPk;
   if (!ctx->ba_dyn) ctx->ba_dyn = ba_dyn_doubles();
   a.dyn_doubles = ctx->ba_dyn;
   if (ctx->ba_member_buf < 0) { const char* e = getenv("FLV_BA_TMA"); ctx->ba_member_buf = (e && atoi(e) > 0) ? BA_MEMBER_BUF : 0; }
@@ -1319,6 +1218,12 @@ int flv_ba_optimize(flv_ctx* ctx, int n_streams, const flv_ba_problem* problems,
   if (mem == FLV_MEM_DEVICE) {
     a.problems = problems; a.poses = poses; a.lms = landmarks; a.ep = edge_pose; a.el = edge_lm; a.uv = edge_uv;
     a.active = edge_active; a.stats = stats;
+    if (MP > BA_MAX_FREE + 1) {       // reserved for large windows: the global-memory solver takes any size
+      FLV_CUDA(ctx, flv_ba_big_launch(n_streams, problems, prm, poses, landmarks, edge_pose, edge_lm, edge_uv, edge_active, stats, MP, ML, ME,
+                                      a.ws, a.trace, stream));
+      ctx->launches++;
+      return FLV_OK;
+    }
     // device-resident problems cannot be inspected here: one CTA per window unless the caller asked for clusters
     FLV_CUDA(ctx, launch_ba(a, n_streams, ctx->ba_cluster_device > 0 ? ctx->ba_cluster_device : 1, smem, stream));
     ctx->launches++;
@@ -1326,8 +1231,11 @@ int flv_ba_optimize(flv_ctx* ctx, int n_streams, const flv_ba_problem* problems,
     return FLV_OK;
   }
   int C = 1;
-  for (int s = 0; s < n_streams; ++s)
+  bool big = false;
+  for (int s = 0; s < n_streams; ++s) {
     if (!problems[s].fix_landmarks && problems[s].n_poses >= 3) C = ba_cluster_size(ctx);
+    if (problems[s].n_poses > BA_MAX_FREE + 1) big = true;       // (a fixed pose may not exist: be conservative)
+  }
   for (int s = 0; s < n_streams; ++s) {
     const flv_ba_problem& p = problems[s];
     if (p.n_poses < 1 || p.n_poses > MP || p.n_landmarks < 0 || p.n_landmarks > ML || p.n_edges < 0 || p.n_edges > ME)
@@ -1347,7 +1255,10 @@ int flv_ba_optimize(flv_ctx* ctx, int n_streams, const flv_ba_problem* problems,
   FLV_CUDA(ctx, cudaMemcpyAsync(d_prob, problems, S * sizeof(flv_ba_problem), cudaMemcpyHostToDevice, stream));
   a.problems = d_prob; a.poses = (double*)(ds + o_pose); a.lms = (double*)(ds + o_lm); a.uv = (const double*)(ds + o_uv);
   a.ep = (const int*)(ds + o_ep); a.el = (const int*)(ds + o_el); a.active = (uint8_t*)(ds + o_act); a.stats = d_stats;
-  FLV_CUDA(ctx, launch_ba(a, n_streams, C, smem, stream));
+  if (big)
+    FLV_CUDA(ctx, flv_ba_big_launch(n_streams, a.problems, prm, a.poses, a.lms, a.ep, a.el, a.uv, a.active, a.stats, MP, ML, ME, a.ws, a.trace, stream));
+  else
+    FLV_CUDA(ctx, launch_ba(a, n_streams, C, smem, stream));
   ctx->launches++;
   FLV_CUDA(ctx, cudaGetLastError());
   FLV_CUDA(ctx, cudaMemcpyAsync(hs + o_pose, ds + o_pose, b_pose + b_lm, cudaMemcpyDeviceToHost, stream));
@@ -1382,7 +1293,7 @@ int flv_set_ba_stream(flv_ctx* ctx, void* cuda_stream, int enable) {
 /* debug: cycle counters of the last flv_ba_optimize for `stream` (8 values, see Sh::prof) */
 int flv_ba_profile(flv_ctx* ctx, int stream, long long* out16) {
   if (!ctx || !ctx->ba_ws || !out16 || stream < 0 || stream >= ctx->S) return FLV_ERR_INVALID;
-  const size_t stride = ws_stride_bytes(ctx->ba_max_poses, ctx->ba_max_lms, ctx->ba_max_edges);
+  const size_t stride = ctx->ba_ws_stride;
   unsigned char* tail = (unsigned char*)ctx->ba_ws + stride * ctx->S;
   long long* d = (long long*)(tail + (size_t)ctx->S * (sizeof(flv_ba_problem) + sizeof(flv_ba_stats)));
   FLV_CUDA(ctx, cudaDeviceSynchronize());
@@ -1394,7 +1305,7 @@ int flv_ba_profile(flv_ctx* ctx, int stream, long long* out16) {
  * lambda after it, rho of its last trial, trials}; returns the rows written (<= cap_iters, <= 32). */
 int flv_ba_trace(flv_ctx* ctx, int stream, double* out, int cap_iters, int iterations_run) {
   if (!ctx || !ctx->ba_ws || !out || stream < 0 || stream >= ctx->S || cap_iters < 0) return FLV_ERR_INVALID;
-  const size_t stride = ws_stride_bytes(ctx->ba_max_poses, ctx->ba_max_lms, ctx->ba_max_edges);
+  const size_t stride = ctx->ba_ws_stride;
   unsigned char* tail = (unsigned char*)ctx->ba_ws + stride * ctx->S;
   const double* d = (const double*)(tail + (size_t)ctx->S * (sizeof(flv_ba_problem) + sizeof(flv_ba_stats) + 128)) + (size_t)BA_TRACE_ITERS * 4 * stream;
   int n = iterations_run < BA_TRACE_ITERS ? iterations_run : BA_TRACE_ITERS;

@@ -84,6 +84,7 @@ struct flv_ctx {
   cudaStream_t ba_stream;         // optional separate stream for flv_ba_optimize (local-map thread analogue)
   int ba_stream_set;
   size_t ba_ws_bytes;
+  size_t ba_ws_stride;            // bytes of workspace per stream slot (max of the ba.cu and ba_big.cu layouts)
 };
 
 #define FLV_CUDA(ctx, call)                                                            \

@@ -10,9 +10,9 @@ struct flv_localmap { flv::LocalMap impl; flv_localmap(flv_ctx* c, int w, double
 extern "C" {
 
 flv_localmap* flv_localmap_create(flv_ctx* ctx, int window_size, double fx, double fy, double cx, double cy) {
-  // reference clamps window_size to [3,100] (vo_localmap.cpp:441-447); the solver keeps the reduced camera system in
-  // shared memory: 24 free poses + the fixed one
-  if (!ctx || window_size < 3 || window_size > 25) return nullptr;
+  // reference clamps window_size to [3,100] (vo_localmap.cpp:441-447); windows of more than 25 poses run on the global-memory
+  // solver (csrc/ba_big.cu)
+  if (!ctx || window_size < 3 || window_size > 100) return nullptr;
   return new (std::nothrow) flv_localmap(ctx, window_size, fx, fy, cx, cy);
 }
 void flv_localmap_destroy(flv_localmap* lm) { delete lm; }

@@ -253,7 +253,7 @@ void destroy_shard(LmShard* b) {
 extern "C" {
 
 flv_localmap_batch* flv_localmap_batch_create(int device, int n_streams, int window_size, double fx, double fy, double cx, double cy) {
-  if (n_streams < 1 || window_size < 3 || window_size > 25) return nullptr;
+  if (n_streams < 1 || window_size < 3 || window_size > 100) return nullptr;
   flv_localmap_batch* b = new (std::nothrow) flv_localmap_batch();
   if (!b) return nullptr;
   b->S = n_streams;

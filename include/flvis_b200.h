@@ -184,12 +184,22 @@ typedef struct {
  *   into the stream's pose / landmark arrays), edge_uv [s][max_edges][2],
  *   edge_active [s][max_edges] (in: 0 = already culled; out: 0 for edges culled by this call).
  * Vertex ordering inside the solver follows g2o: poses by index, landmarks by index, edges in
- * array order (the host keeps them in g2o id / insertion order). */
+ * array order (the host keeps them in g2o id / insertion order).
+ * Window sizes: up to 100 poses (the reference's limit, vo_localmap.cpp:441-447).  Windows of <= 25 poses run on the
+ * shared-memory solver (one cluster of 1/2/4 CTAs per window); a call that contains a larger window -- or, for FLV_MEM_DEVICE
+ * calls, a context reserved for more than 25 poses -- runs on the global-memory solver (one cluster of 8 CTAs per window). */
 int flv_ba_reserve(flv_ctx* ctx, int max_poses, int max_landmarks, int max_edges);
 int flv_ba_optimize(flv_ctx* ctx, int n_streams, const flv_ba_problem* problems,
                     const flv_ba_params* prm, double* poses, double* landmarks,
                     const int* edge_pose, const int* edge_lm, const double* edge_uv,
                     uint8_t* edge_active, flv_ba_stats* stats, flv_memspace mem);
+
+/* TEST AID, no GPU involved: the large-window solver's driver and phase code (csrc/ba_big.cu) executed sequentially on the host
+ * over host arrays of ONE window, `emulated_threads` (32..2048, multiple of 32) playing the kernel's threads one after the
+ * other.  Lets the CPU suite compare the arithmetic with the oracle; the product never calls it. */
+int flv_ba_big_emulate_host(const flv_ba_problem* problem, const flv_ba_params* prm, double* poses, double* landmarks,
+                            const int* edge_pose, const int* edge_lm, const double* edge_uv, uint8_t* edge_active,
+                            flv_ba_stats* stats, int emulated_threads);
 
 /* ---- per-landmark geometry (K6) -------------------------------------------------------------------
  * flv_depth_innovation replaces CameraFrame::depthInnovation (src/processing/camera_frame.cpp:271-330) and the

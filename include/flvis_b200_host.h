@@ -19,8 +19,9 @@ void flv_localmap_reset(flv_localmap* lm);      /* KFMSG_CMD_RESET_LM, vo_localm
 /* One KeyFrame message (msg/KeyFrame.msg without the images): lm_2d[n][2] undistorted px, lm_3d[n][3] world,
  * T_c_w = [qx qy qz qw tx ty tz].  Returns 1 when a solve ran and the CorrectionInf outputs were written
  * (msg/CorrectionInf.msg), 0 when the window is still filling, <0 on error (buffers too small = FLV_ERR_OVERFLOW, a due solve
- * that failed = FLV_ERR_CUDA with flv_last_error(ctx) set).  window_size: 3..25 (the reference allows up to 100,
- * vo_localmap.cpp:441-447; the reduced camera system of this solver lives in shared memory: 24 free poses). */
+ * that failed = FLV_ERR_CUDA with flv_last_error(ctx) set).  window_size: 3..100 like the reference
+ * (vo_localmap.cpp:441-447): up to 25 poses the reduced camera system lives in shared memory (csrc/ba.cu), larger windows run
+ * on the global-memory solver (csrc/ba_big.cu). */
 int flv_localmap_add_keyframe(flv_localmap* lm, int64_t frame_id, int n, const int64_t* lm_id, const double* lm_2d,
                               const double* lm_3d, const double* T_c_w, int64_t* out_frame_id, double* out_T_c_w,
                               int* out_lm_count, int64_t* out_lm_id, double* out_lm_3d, int lm_cap,

@@ -50,6 +50,19 @@ def test_local_ba_matches_oracle_small_and_euroc_sized():
     ctx.close()
 
 
+def test_large_windows_30_and_60_poses_global_memory_solver():
+    """Windows beyond the shared-memory solver's 25 poses (the reference allows up to 100, vo_localmap.cpp:441-447) run on
+    ba_big.cu: one cluster of 8 CTAs per window, reduced camera system in global memory.  Same bars as the small windows."""
+    probs = [ba_problems.make_problem(window=30, n_landmarks=500, obs_per_frame=120, seed=5),
+             ba_problems.make_problem(window=60, n_landmarks=1200, obs_per_frame=150, seed=6)]
+    batch = ba_batch.Batch(probs)
+    ctx = capi.Context(len(probs), 752, 480)
+    prm = capi.BAParams(12, 8, 1.0, 3.0, 0)
+    poses, lms, active, stats = ba_batch.solve_batch_host(ctx, batch, prm)
+    _check(batch, poses, lms, active, stats, prm)
+    ctx.close()
+
+
 def test_kitti_sized_window_20():
     probs = [ba_problems.make_problem(window=20, n_landmarks=2000, obs_per_frame=480, seed=11, w=1241, h=376,
                                    K=(718.856, 718.856, 607.1928, 185.2157))]

@@ -21,7 +21,7 @@ def test_oracle_localmap_runs_and_slides():
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("window,n_kf", [(5, 12), (10, 16)])
+@pytest.mark.parametrize("window,n_kf", [(5, 12), (10, 16), (30, 34)])     # 30: the large-window solver (ba_big.cu)
 def test_localmap_matches_oracle_keyframe_by_keyframe(window, n_kf):
     from flvis_b200 import capi
     K = (458.654, 457.296, 367.215, 248.375)
