@@ -19,7 +19,7 @@ SYMBOLS = [
     "flv_download_level", "flv_lk_track", "flv_select_tracked", "flv_gftt", "flv_download_eig", "flv_gftt_capacity",
     "flv_feature_detect", "flv_feature_redetect", "flv_ba_reserve", "flv_ba_optimize", "flv_gftt_keep_response",
     "flv_ba_profile", "flv_set_ba_stream", "flv_set_ba_cluster", "flv_feature_prepare", "flv_set_equalize_hist", "flv_fundamental_ransac", "flv_pnp_ransac", "flv_upload_color_images", "flv_depth_innovation", "flv_reprojection_inliers",
-    "flv_ba_trace", "flv_ba_debug_edges", "flv_ba_big_emulate_host",
+    "flv_ba_trace", "flv_ba_debug_edges", "flv_ba_big_emulate_host", "flv_get_flags",
 ]
 
 

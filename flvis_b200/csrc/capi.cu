@@ -64,6 +64,12 @@ int flv_create(flv_ctx** out, int device, int max_streams, int img_w, int img_h,
   ctx->ba_member_buf = -1;
   FLV_CUDA(ctx, cudaSetDevice(device));
   build_geom(ctx->geom, img_w, img_h);
+  {   // cv::buildOpticalFlowPyramid would build a further level for this size: LK would silently lose its coarsest level
+    const LevelGeom& top = ctx->geom.lv[ctx->geom.nlev - 1];
+    if (ctx->geom.nlev == FLV_MAX_LEVELS && (top.w + 1) / 2 > 31 && (top.h + 1) / 2 > 31)
+      FLV_FAIL(ctx, FLV_ERR_UNSUPPORTED, "%dx%d images need more than %d pyramid levels (31x31 window); this build supports %d", img_w,
+               img_h, FLV_MAX_LEVELS, FLV_MAX_LEVELS);
+  }
   ctx->no_fused_ingest = getenv("FLV_NO_FUSED_INGEST") ? atoi(getenv("FLV_NO_FUSED_INGEST")) : 0;
   FLV_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
   ctx->own_stream = true;
@@ -416,6 +422,22 @@ static int check_flags(flv_ctx* ctx, int n_streams) {
                "4=region kept 8=sort depth 16=max_pts)", s, f);
     }
   return FLV_OK;
+}
+
+/* FLV_MEM_DEVICE callers never synchronise inside the library, so the per-stream overflow flags of the Shi-Tomasi / FeatureDEM
+ * kernels stay on the device until somebody asks: copies them to flags_out[n_streams] (host), clears them, synchronises the
+ * context's stream.  Returns FLV_ERR_OVERFLOW if any flag was set. */
+int flv_get_flags(flv_ctx* ctx, int n_streams, int* flags_out) {
+  if (!ctx || n_streams < 1 || n_streams > ctx->S) return FLV_ERR_INVALID;
+  int rc = flv_stage_reserve(ctx, (size_t)n_streams * 4);
+  if (rc) return rc;
+  int* hf = (int*)ctx->h_stage;
+  FLV_CUDA(ctx, cudaMemcpyAsync(hf, ctx->d_flags, (size_t)n_streams * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  FLV_CUDA(ctx, cudaMemsetAsync(ctx->d_flags, 0, (size_t)n_streams * 4, ctx->stream));
+  FLV_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  int any = 0;
+  for (int s = 0; s < n_streams; ++s) { if (flags_out) flags_out[s] = hf[s]; any |= hf[s]; }
+  return any ? FLV_ERR_OVERFLOW : FLV_OK;
 }
 
 int flv_gftt(flv_ctx* ctx, int slot, int n_streams, int max_corners, double quality,

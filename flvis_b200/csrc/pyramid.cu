@@ -290,7 +290,7 @@ int flv_launch_unpack_equalized(flv_ctx* ctx, int slot, int n_streams, const uin
                                                                      ctx->w, ctx->h, L1.w, L1.h, (const unsigned char*)ctx->d_lut);
   ctx->launches += 3;
   FLV_CUDA(ctx, cudaGetLastError());
-  ctx->l1_valid[slot] = 1;
+  ctx->l1_valid[slot] = n_streams;        // streams whose level 1 came out of the fused ingest
   return FLV_OK;
 }
 
@@ -307,7 +307,7 @@ int flv_launch_unpack(flv_ctx* ctx, int slot, int n_streams, const uint8_t* d_sr
                                                                  ctx->w, ctx->h, L1.w, L1.h, nullptr);
     ctx->launches++;
     FLV_CUDA(ctx, cudaGetLastError());
-    ctx->l1_valid[slot] = 1;
+    ctx->l1_valid[slot] = n_streams;        // streams whose level 1 came out of the fused ingest
     return FLV_OK;
   }
   const bool vec = (ctx->w % 16 == 0) && (row_stride % 16 == 0) && (img_stride % 16 == 0) &&
@@ -329,7 +329,7 @@ int flv_launch_unpack(flv_ctx* ctx, int slot, int n_streams, const uint8_t* d_sr
 int flv_launch_pyramid(flv_ctx* ctx, int slot, int n_streams) {
   const PyrGeom& g = ctx->geom;
   ctx->deriv_streams[slot] = 0;
-  const int first = ctx->l1_valid[slot] ? 2 : 1;      // level 1 already built by the fused ingest kernel
+  const int first = ctx->l1_valid[slot] >= n_streams ? 2 : 1;      // level 1 already built by the fused ingest kernel (for all of these streams)
   ctx->l1_valid[slot] = 0;
   for (int l = first; l < g.nlev; ++l) {
     const LevelGeom& a = g.lv[l - 1];

@@ -119,6 +119,10 @@ int flv_gftt_keep_response(flv_ctx* ctx, int enable);
 int flv_download_eig(flv_ctx* ctx, int stream, float* out, flv_memspace mem);
 /* Capacity of the corner output (max value of max_corners). */
 int flv_gftt_capacity(flv_ctx* ctx);
+/* Device-mode callers: read (into flags_out[n_streams], may be NULL) and clear the per-stream capacity-overflow flags of the
+ * Shi-Tomasi / FeatureDEM kernels (1 = candidates, 2 = accepted corners, 4 = region kept, 8 = sort depth, 16 = max_pts).  Host-mode
+ * calls check them on their own.  Synchronises the context's stream; returns FLV_ERR_OVERFLOW if any flag was set. */
+int flv_get_flags(flv_ctx* ctx, int n_streams, int* flags_out);
 
 /* ---- FeatureDEM region selection (K5) ------------------------------------------------------
  * Replaces FeatureDEM::detect (src/processing/feature_dem.cpp:215-266) and

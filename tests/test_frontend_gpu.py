@@ -51,11 +51,13 @@ def test_lk_bit_exact_vs_oracle_and_golden(name):
     ctx.close()
 
 
+@pytest.mark.parametrize("variant", ["6", "7"])
 @pytest.mark.parametrize("name", cases.lk_cases())
-def test_lk_v4_packed_patch_all_cases(name, monkeypatch):
+def test_lk_v4_packed_patch_all_cases(name, variant, monkeypatch):
     """LK v4 (precomputed Scharr pyramid + packed register patch + DP2A blend) on every golden case, incl. border points
-    and a second call that reuses the cached derivative pyramid."""
-    monkeypatch.setenv("FLV_LK_VARIANT", "6")
+    and a second call that reuses the cached derivative pyramid.  Variant 7 (the default) stages the second image's patch
+    with TMA tile loads, variant 6 with plain loads: same bits."""
+    monkeypatch.setenv("FLV_LK_VARIANT", variant)
     g, I, J = cases.load_lk(name)
     h, w = I.shape
     ctx = _ctx(1, w, h)
@@ -77,7 +79,7 @@ def test_lk_v4_packed_patch_all_cases(name, monkeypatch):
     ctx.close()
 
 
-@pytest.mark.parametrize("variant", ["1", "3", "4", "5", "6"])
+@pytest.mark.parametrize("variant", ["1", "3", "4", "5", "6", "7"])
 def test_lk_kernel_variants_bit_exact(variant, monkeypatch):
     """All register-budget / shared-memory variants of the tracker obey the same arithmetic contract."""
     monkeypatch.setenv("FLV_LK_VARIANT", variant)

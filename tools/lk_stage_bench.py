@@ -44,7 +44,7 @@ for _ in range(15):
     e0.record(); run(); e1.record(); torch.cuda.synchronize()
     ts.append(e0.elapsed_time(e1) * 1e3)
 res = np.concatenate([d_next.cpu().numpy().view(np.uint32).ravel(), d_st.cpu().numpy().ravel().astype(np.uint32)])
-tag = os.environ.get("FLV_LK_VARIANT", "6")
+tag = os.environ.get("FLV_LK_VARIANT", "7")
 out = os.environ.get("FLV_LK_CHECK")
 same = None
 if out:
