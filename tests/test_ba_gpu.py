@@ -100,7 +100,8 @@ def test_zero_noise_known_answer_and_determinism():
 
 def test_unsupported_window_is_reported():
     ctx = capi.Context(1, 752, 480)
-    rc = ctx.lib.flv_ba_reserve(ctx.h, 40, 100, 100)
+    assert ctx.lib.flv_ba_reserve(ctx.h, 100, 100, 100) == 0             # the reference's largest window (vo_localmap.cpp:441-447)
+    rc = ctx.lib.flv_ba_reserve(ctx.h, 101, 100, 100)
     assert rc == -4 and b"supports" in ctx.lib.flv_last_error(ctx.h)
     ctx.close()
 

@@ -113,6 +113,43 @@ def test_pnp_ransac_vs_cv2():
     ctx.close()
 
 
+def test_pnp_ransac_with_a_poor_prior():
+    """The reference calls solvePnPRansac with useExtrinsicGuess only when the IMU supplies a pose (lkorb_tracking.cpp:170-177);
+    otherwise OpenCV starts from its own minimal solutions.  K11 always refines hypotheses from the prior it is given (the IMU guess
+    or the previous frame's pose), so a prior that is far off -- 6 degrees and 30 cm here, a previous-frame pose under fast
+    motion -- must still lead to the right model."""
+    from flvis_b200 import capi
+    rng = np.random.default_rng(7)
+    ns = [400, 150]
+    S = len(ns)
+    ctx = capi.Context(S, 752, 480, 512)
+    P3 = np.zeros((S, 512, 3), np.float32); P2 = np.zeros((S, 512, 2), np.float32)
+    Tin = np.zeros((S, 7)); Tin[:, 3] = 1
+    gts = []
+    for s, n in enumerate(ns):
+        X, R, t, u1, u2, bad = _scene(rng, n, 0.2)
+        P3[s, :n] = X[:n]; P2[s, :n] = u2[:n]
+        axis = rng.normal(0, 1, 3); axis /= np.linalg.norm(axis)
+        Rp, _ = cv2.Rodrigues(axis * np.deg2rad(6.0))
+        d = rng.normal(0, 1, 3); d *= 0.30 / np.linalg.norm(d)
+        Tin[s] = np.r_[_R2q(Rp @ R), t + d]
+        gts.append((R, t, bad[:n]))
+    To, mask, ni = ctx.pnp_ransac(P3, P2, np.array(ns, np.int32), np.tile(K4, (S, 1)), Tin, 3.0)
+    for s, n in enumerate(ns):
+        R, t, bad = gts[s]
+        m = mask[s, :n]
+        Rg = _q2R(To[s, :4])
+        terr = np.linalg.norm(To[s, 4:] - t); rerr = np.linalg.norm(cv2.Rodrigues(Rg @ R.T)[0])
+        ok, rvec, tvec, inl = cv2.solvePnPRansac(P3[s, :n].astype(np.float64), P2[s, :n].astype(np.float64), K, np.zeros(4), None, None,
+                                                 False, 100, 3.0, 0.99, flags=cv2.SOLVEPNP_ITERATIVE)
+        Rc, _ = cv2.Rodrigues(rvec)
+        terr_c = np.linalg.norm(tvec.ravel() - t); rerr_c = np.linalg.norm(cv2.Rodrigues(Rc @ R.T)[0])
+        assert terr <= 1.5 * terr_c + 0.01 and rerr <= 1.5 * rerr_c + 1e-3, (s, terr, terr_c, rerr, rerr_c)
+        good = ~bad
+        assert m[good].mean() > 0.95 and m[bad].mean() < 0.1
+    ctx.close()
+
+
 def _R2q(R):
     w = np.sqrt(max(0.0, 1 + R[0, 0] + R[1, 1] + R[2, 2])) / 2
     x = (R[2, 1] - R[1, 2]) / (4 * w); y = (R[0, 2] - R[2, 0]) / (4 * w); z = (R[1, 0] - R[0, 1]) / (4 * w)
