@@ -478,7 +478,7 @@ int feed_begin(flv_f2f_batch* b, const double* t, const uint8_t* img0, const voi
   const TrkBufs& q = b->d.b;
   mark();                                                                 // 1: frame -> frame LK
   if (any_track) {
-    B_RC(b, flv_lk_track(ctx, prev0, cur0, S, q.n_lk, q.lk_prev, q.lk_init, q.lk_next, q.lk_st, q.lk_err, &lk_f2f, FLV_MEM_DEVICE));
+    B_RC(b, flv_lk_track(ctx, prev0, cur0, S, q.n_lk, q.lk_prev, q.lk_init, q.lk_next, q.lk_st, /*err: unused by the reference (lkorb_tracking.cpp:36)*/ nullptr, &lk_f2f, FLV_MEM_DEVICE));
     mark();                                                               // 2: keep rule + F RANSAC
     B_RC(b, flv_trk_stage_keep(ctx, b->d, S));
     if (b->fmat_fn) { if (int rc = run_fmat_hooks(b)) return rc; }
@@ -519,7 +519,7 @@ int feed_begin(flv_f2f_batch* b, const double* t, const uint8_t* img0, const voi
   if (any_track || any_init) {
     if (b->stereo) {
       B_CUDA(b, cudaStreamWaitEvent(cs, b->ev_right, 0));
-      B_RC(b, flv_lk_track(ctx, cur0, cur1, S, q.n_r, q.r_prev, q.r_init, q.r_next, q.r_st, q.r_err, &lk_lr, FLV_MEM_DEVICE));
+      B_RC(b, flv_lk_track(ctx, cur0, cur1, S, q.n_r, q.r_prev, q.r_init, q.r_next, q.r_st, /*err unused (camera_frame.cpp:124-128)*/ nullptr, &lk_lr, FLV_MEM_DEVICE));
       B_RC(b, flv_trk_stage_pt1(ctx, b->d, S));
     }
     mark();                                                               // 8: depth innovation + finish

@@ -304,7 +304,7 @@ int flv_download_level(flv_ctx* ctx, int slot, int stream, int level, uint8_t* o
 int flv_lk_track(flv_ctx* ctx, int src_slot, int dst_slot, int n_streams, const int* n_pts,
                  const float* prev_xy, const float* init_xy, float* next_xy, uint8_t* status,
                  float* err, const flv_lk_params* prm, flv_memspace mem) {
-  if (!ctx || !prm || !n_pts || !prev_xy || !init_xy || !next_xy || !status || !err ||
+  if (!ctx || !prm || !n_pts || !prev_xy || !init_xy || !next_xy || !status || (!err && mem != FLV_MEM_DEVICE) ||
       src_slot < 0 || src_slot >= FLV_NUM_SLOTS || dst_slot < 0 || dst_slot >= FLV_NUM_SLOTS ||
       n_streams < 1 || n_streams > ctx->S)
     return FLV_ERR_INVALID;

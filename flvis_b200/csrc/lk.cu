@@ -287,6 +287,7 @@ int flv_launch_lk(flv_ctx* ctx, int src_slot, int dst_slot, int n_streams, const
   // by TMA (7; measured 325 vs 330 us against the plain loads of 6, bit-identical); FLV_LK_VARIANT selects the earlier kernels
   // (1 = register template, 3/4 = v2 register budgets, 5 = shared-memory template, 6 = v4 without TMA) for A/B runs
   const int variant = getenv("FLV_LK_VARIANT") ? atoi(getenv("FLV_LK_VARIANT")) : 7;
+  if (!d_err && variant != 6 && variant != 7) FLV_FAIL(ctx, FLV_ERR_UNSUPPORTED, "err = NULL needs the default LK kernel");
   if (variant == 6 || variant == 7)
     return flv_launch_lk_v4(ctx, src_slot, dst_slot, n_streams, d_npts, d_prev, d_init, d_next, d_status, d_err, nlev_used,
                             max_iter, eps2, min_eig_thr);

@@ -442,7 +442,7 @@ lk_track_kernel_v4(const uint8_t* __restrict__ pyrI, const unsigned* __restrict_
       }
       pdx = dx; pdy = dy;
     }
-    if (level == 0 && st) {
+    if (level == 0 && st && err != nullptr) {            // (the reference never reads `err`: callers may pass NULL and save the pass)
       const float qx = nx - half, qy = ny - half;
       const int inx = (int)floorf(qx), iny = (int)floorf(qy);
       if (inx < -WIN || inx >= w || iny < -WIN || iny >= h) {
@@ -464,7 +464,7 @@ lk_track_kernel_v4(const uint8_t* __restrict__ pyrI, const unsigned* __restrict_
     next_xy[2 * pidx] = nx;
     next_xy[2 * pidx + 1] = ny;
     status[pidx] = (uint8_t)st;
-    err[pidx] = er;
+    if (err != nullptr) err[pidx] = er;
   }
 }
 

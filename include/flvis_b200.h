@@ -86,7 +86,8 @@ int flv_download_level(flv_ctx* ctx, int slot, int stream, int level, uint8_t* o
  * maxLevel, TermCriteria(COUNT+EPS, 30, 1e-3), OPTFLOW_USE_INITIAL_FLOW) at
  * src/processing/lkorb_tracking.cpp:64-73 (maxLevel 10) and src/processing/camera_frame.cpp:124-128
  * (maxLevel 5).  Pyramids of both slots must have been built.  init_xy is the initial flow
- * (USE_INITIAL_FLOW); next_xy may alias init_xy.  win must be 31. */
+ * (USE_INITIAL_FLOW); next_xy may alias init_xy.  win must be 31.  FLV_MEM_DEVICE callers that do not need OpenCV's `err`
+ * output (the reference never reads it) may pass err = NULL: the kernel then skips the final error pass. */
 typedef struct {
   int win;          /* 31 */
   int max_level;    /* levels used = min(max_level, built levels-1)+1 */
