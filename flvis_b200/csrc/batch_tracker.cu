@@ -21,6 +21,7 @@
 #include "../host/glibc_rand.h"
 #include "../host/sophus_lite.h"
 #include "../host/vi_motion.h"
+#include "../host/nvtx_range.h"
 
 namespace {
 
@@ -446,8 +447,13 @@ int feed_begin(flv_f2f_batch* b, const double* t, const uint8_t* img0, const voi
   cudaStream_t cs = ctx->stream;
   const auto tp1 = std::chrono::steady_clock::now();
   int mark_i = 0;
+  static const char* const kStage[flv_f2f_batch::NSTAGE] = {
+      "flv: ingest + pyramids", "flv: LK frame->frame", "flv: keep rule + F RANSAC", "flv: PnP RANSAC", "flv: pose-only BA",
+      "flv: reprojection cull", "flv: FeatureDEM redetect", "flv: LK left->right", "flv: depth innovation + finish"};
+  flv::NvtxStages nvtx;                                   // NVTX range per stage (closed on every exit path)
   auto mark = [&]() {                                     // stage boundary: an event when profiling, a counter always
     if (mark_i > flv_f2f_batch::NSTAGE) return;
+    if (mark_i < flv_f2f_batch::NSTAGE) nvtx.next(kStage[mark_i]); else nvtx.close();
     if (b->profile) cudaEventRecord(b->ev_stage[mark_i], cs);
     ++mark_i;
   };

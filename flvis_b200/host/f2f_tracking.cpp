@@ -1,4 +1,5 @@
 #include "f2f_tracking.h"
+#include "nvtx_range.h"
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
@@ -172,6 +173,8 @@ int FeatureDEM::redetect(int slot, const std::vector<Vec2>& existedPts, std::vec
 
 int F2FTracking::image_feed(double time, const uint8_t* img0, const void* img1, bool& new_keyframe, bool& reset_cmd) {   // :59-400
   new_keyframe = false; reset_cmd = false;
+  NvtxStages nvtx;                                   // NVTX range per step of the reference's image_feed
+  nvtx.next("flv: ingest + pyramids");
   frameCount++;
   last_frame.swap(curr_frame);
   curr_frame->clear();
@@ -205,6 +208,7 @@ int F2FTracking::image_feed(double time, const uint8_t* img0, const void* img1, 
     }
     case Tracking: {
       // STEP1: local-map feedback (:189-219); only ever set through correction_feed, which the reference's nodelet never calls
+      nvtx.next("flv: STEP1-3 LKORBTracking::tracking (LK, F RANSAC, PnP RANSAC)");
       if (has_localmap_feedback) apply_localmap_feedback();
       SE3 imu_guess; bool has_imu_guess = false;
       if (has_imu) has_imu_guess = vimotion->viGetCorrFrameState(time, imu_guess);
@@ -217,6 +221,7 @@ int F2FTracking::image_feed(double time, const uint8_t* img0, const void* img1, 
         break;
       }
       continus_tracking_fail_cnt = 0;
+      nvtx.next("flv: STEP4 OptimizeInFrame (pose-only BA)");
       if (has_imu) vimotion->viVisionRPCompensation(curr_frame->frame_time, curr_frame->T_c_w);
       if (!OptimizeInFrame::optimize(*curr_frame)) {
         continus_tracking_fail_cnt++;
@@ -224,6 +229,7 @@ int F2FTracking::image_feed(double time, const uint8_t* img0, const void* img1, 
         if (continus_tracking_fail_cnt >= 2) { vo_tracking_state = TrackingFail; continus_tracking_fail_cnt = 0; }
         break;
       }
+      nvtx.next("flv: STEP5 reprojection cull");
       std::vector<Vec2> outlier_reproject;
       double mean_reprojection_error = 0;
       if ((rc = curr_frame->calReprjInlierOutlier(mean_reprojection_error, outlier_reproject, 1.5))) return rc;
@@ -232,6 +238,7 @@ int F2FTracking::image_feed(double time, const uint8_t* img0, const void* img1, 
       if (has_imu)
         vimotion->viCorrectionFromVision(curr_frame->frame_time, curr_frame->T_c_w, last_frame->frame_time, last_frame->T_c_w,
                                          curr_frame->reprojection_error);
+      nvtx.next("flv: STEP6 FeatureDEM redetect");
       std::vector<P2f> pts2d;
       const int orig_size = (int)curr_frame->landmarks.size();
       int newPtsCount = 0;
@@ -242,6 +249,7 @@ int F2FTracking::image_feed(double time, const uint8_t* img0, const void* img1, 
         if (cam_type == STEREO_UNRECT) undistort_point(d_camera.lens0, p.x, p.y, u.x, u.y);
         curr_frame->landmarks.push_back(make_landmark(Vec2{p.x, p.y}, Vec2{u.x, u.y}, curr_frame->T_c_w, add_as_inliers));
       }
+      nvtx.next("flv: STEP7 depth innovation (left->right LK, triangulation)");
       if ((rc = curr_frame->depthInnovation(iir_ratio, range, enable_dummy))) return rc;
       curr_frame->eraseNoDepthPoint();
       pose_records.push_back(ID_POSE{curr_frame->frame_id, curr_frame->T_c_w});

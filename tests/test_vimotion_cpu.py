@@ -92,11 +92,14 @@ def test_vimotion_is_safe_under_concurrent_imu_and_vision_threads(lib):
     stop = threading.Event()
 
     def feeder():
+        import time
         q2 = np.zeros(4); p2 = np.zeros(3); v2 = np.zeros(3)
         for i in range(60, len(t)):
             a = np.ascontiguousarray(acc[i]); g = np.ascontiguousarray(gyro[i])
             lib.flv_vimotion_imu_feed(h, float(t[i]), vp(a), vp(g), vp(q2), vp(p2), vp(v2))
             now[0] = i
+            if i % 25 == 0:
+                time.sleep(0.0005)          # paced like a sensor: the vision thread gets its turns whatever the machine load
         stop.set()
 
     th = threading.Thread(target=feeder)
