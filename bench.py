@@ -50,10 +50,10 @@ WORKLOADS = {   # BASELINE.json configs: image size, sensor, local-BA window
                  name="640x480 D435i depth + IMU 200 Hz, 8-KF local BA (configs[0]/[4])"),
 }
 PERIOD = 40                                       # frames per period of the synthetic rig trajectory
-# profiles/r02_step_kernels_ncu_full.csv (ncu --set full inside the bench step, 32 sequences x 420 landmarks in one launch):
-# lk_track_kernel_v4 dram__bytes_read 91.6 MB + write 4.5 MB, 204.3 M warp instructions
-LK_NCU_TRAFFIC_PER_SEQUENCE = {"euroc": (91.59e6 + 4.53e6) / 32}
-LK_WARP_INSTR_PER_POINT = 204.3e6 / (32 * 420.5)
+# profiles/r02_final_step_kernels_ncu_full.csv (ncu --set full inside the bench step, 32 sequences x 420 landmarks in one launch,
+# frame->frame call of lk_track_kernel_v4<TMA>): dram__bytes_read 91.6 MB + write 3.8 MB, 192.6 M warp instructions
+LK_NCU_TRAFFIC_PER_SEQUENCE = {"euroc": (91.63e6 + 3.82e6) / 32}
+LK_WARP_INSTR_PER_POINT = 192.6e6 / (32 * 420.5)
 
 
 def pyramid_pixels(w, h):
