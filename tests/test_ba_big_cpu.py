@@ -58,3 +58,18 @@ def test_big_window_solver_small_window_and_pose_only():
     ref = ba_ref.optimize(d, 12, 8, 1.0, 3.0, 0)
     assert st.iterations_run == ref.iterations_run and np.array_equal(act, d.active)
     assert np.abs(poses - d.poses).max() <= 1e-6 and np.abs(lms - d.lms).max() <= 1e-5
+
+
+def test_big_window_solver_at_the_reference_limit_of_100_poses():
+    """The reference's largest window (vo_localmap.cpp:441-447): 99 free poses, reduced camera system 594 x 594."""
+    lib = capi.load_library()
+    prm = capi.BAParams(12, 8, 1.0, 3.0, 0, 0)
+    p = ba_problems.make_problem(window=100, n_landmarks=1500, obs_per_frame=70, seed=9)
+    assert len(p.poses) == 100
+    poses, lms, act, st = _emulate(lib, p, 256, prm)
+    d = oracle_data(p)
+    ref = ba_ref.optimize(d, 12, 8, 1.0, 3.0, 0)
+    assert st.ok == ref.ok == 1 and st.iterations_run == ref.iterations_run and st.n_culled == ref.n_culled
+    assert np.array_equal(act, d.active)
+    assert abs(st.chi2_final - ref.chi2_final) <= 1e-7 * ref.chi2_final
+    assert np.abs(poses - d.poses).max() <= 1e-6 and np.abs(lms - d.lms).max() <= 1e-5
