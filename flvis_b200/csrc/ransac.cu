@@ -209,14 +209,15 @@ __device__ void f_from_vec(double* Fn /*unit 9-vector, destroyed*/, const NormT&
   mat3_mul(TbT, tmp, F);
 }
 
-__device__ __forceinline__ double f_error(const double* F, double x1, double y1, double x2, double y2) {
+// inlier test of the symmetric epipolar distance, max(e1, e2) <= thr2, without the two fp64 divisions of f_error:
+// d^2 / (la^2 + lb^2) <= thr2  <=>  d^2 <= thr2 (la^2 + lb^2).  The scoring loops run this 256 x n times per sequence.
+__device__ __forceinline__ bool f_inlier(const double* F, double x1, double y1, double x2, double y2, double thr2) {
   double la = F[0] * x1 + F[1] * y1 + F[2], lb = F[3] * x1 + F[4] * y1 + F[5], lc = F[6] * x1 + F[7] * y1 + F[8];
   const double d2 = x2 * la + y2 * lb + lc;
-  const double e2 = d2 * d2 / (la * la + lb * lb + 1e-300);
+  const bool ok2 = d2 * d2 <= thr2 * (la * la + lb * lb + 1e-300);
   la = F[0] * x2 + F[3] * y2 + F[6]; lb = F[1] * x2 + F[4] * y2 + F[7]; lc = F[2] * x2 + F[5] * y2 + F[8];
   const double d1 = x1 * la + y1 * lb + lc;
-  const double e1 = d1 * d1 / (la * la + lb * lb + 1e-300);
-  return fmax(e1, e2);
+  return ok2 && d1 * d1 <= thr2 * (la * la + lb * lb + 1e-300);
 }
 
 __global__ void __launch_bounds__(RS_THREADS) fmat_ransac_kernel(const int* __restrict__ npts, const float* __restrict__ from_xy,
@@ -272,7 +273,7 @@ __global__ void __launch_bounds__(RS_THREADS) fmat_ransac_kernel(const int* __re
     double Fh[9];
     for (int k = 0; k < 9; ++k) Fh[k] = sF[h][k];
     int c = 0;
-    for (int i = lane; i < n; i += 32) c += f_error(Fh, A[2 * i], A[2 * i + 1], B[2 * i], B[2 * i + 1]) <= thr2;
+    for (int i = lane; i < n; i += 32) c += f_inlier(Fh, A[2 * i], A[2 * i + 1], B[2 * i], B[2 * i + 1], thr2);
     c = __reduce_add_sync(FULL, c);
     if (lane == 0) score[h] = c;
   }
@@ -288,7 +289,7 @@ __global__ void __launch_bounds__(RS_THREADS) fmat_ransac_kernel(const int* __re
   for (int k = 0; k < 9; ++k) Fb[k] = sF[best][k];
   const int cnt = score[best];
   for (int i = tid; i < max_pts; i += RS_THREADS)
-    mask[i] = (i < n && f_error(Fb, A[2 * i], A[2 * i + 1], B[2 * i], B[2 * i + 1]) <= thr2) ? 1 : 0;
+    mask[i] = (i < n && f_inlier(Fb, A[2 * i], A[2 * i + 1], B[2 * i], B[2 * i + 1], thr2)) ? 1 : 0;
   if (tid == 0) n_inl[s] = cnt >= 8 ? cnt : 0;
   if (cnt < 8) {
     __syncthreads();
@@ -299,7 +300,7 @@ __global__ void __launch_bounds__(RS_THREADS) fmat_ransac_kernel(const int* __re
   // ---- least-squares refit on the inliers (block-parallel normalisation + Gram matrix) ---------------------------------
   double acc[6] = {0, 0, 0, 0, 0, 0};     // sums of ax, ay, bx, by
   for (int i = tid; i < n; i += RS_THREADS)
-    if (f_error(Fb, A[2 * i], A[2 * i + 1], B[2 * i], B[2 * i + 1]) <= thr2) { acc[0] += A[2 * i]; acc[1] += A[2 * i + 1]; acc[2] += B[2 * i]; acc[3] += B[2 * i + 1]; }
+    if (f_inlier(Fb, A[2 * i], A[2 * i + 1], B[2 * i], B[2 * i + 1], thr2)) { acc[0] += A[2 * i]; acc[1] += A[2 * i + 1]; acc[2] += B[2 * i]; acc[3] += B[2 * i + 1]; }
   for (int k = 0; k < 4; ++k) { double v = acc[k]; for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o); if (lane == 0) red[warp][k] = v; }
   __syncthreads();
   NormT T;
@@ -308,7 +309,7 @@ __global__ void __launch_bounds__(RS_THREADS) fmat_ransac_kernel(const int* __re
   __syncthreads();
   acc[0] = acc[1] = 0;
   for (int i = tid; i < n; i += RS_THREADS)
-    if (f_error(Fb, A[2 * i], A[2 * i + 1], B[2 * i], B[2 * i + 1]) <= thr2) {
+    if (f_inlier(Fb, A[2 * i], A[2 * i + 1], B[2 * i], B[2 * i + 1], thr2)) {
       const double ax = A[2 * i] - T.cax, ay = A[2 * i + 1] - T.cay, bx = B[2 * i] - T.cbx, by = B[2 * i + 1] - T.cby;
       acc[0] += sqrt(ax * ax + ay * ay); acc[1] += sqrt(bx * bx + by * by);
     }
@@ -344,7 +345,7 @@ __global__ void __launch_bounds__(RS_THREADS) fmat_ransac_kernel(const int* __re
   double Fr[9];
   for (int k = 0; k < 9; ++k) Fr[k] = sF[0][k];
   int c2 = 0;
-  for (int i = tid; i < n; i += RS_THREADS) c2 += f_error(Fr, A[2 * i], A[2 * i + 1], B[2 * i], B[2 * i + 1]) <= thr2;
+  for (int i = tid; i < n; i += RS_THREADS) c2 += f_inlier(Fr, A[2 * i], A[2 * i + 1], B[2 * i], B[2 * i + 1], thr2);
   c2 = __reduce_add_sync(FULL, c2);
   if (lane == 0) score[warp] = c2;
   __syncthreads();
@@ -352,7 +353,7 @@ __global__ void __launch_bounds__(RS_THREADS) fmat_ransac_kernel(const int* __re
   for (int w = 0; w < RS_WARPS; ++w) tot += score[w];
   const bool take = tot >= cnt;
   if (take)
-    for (int i = tid; i < n; i += RS_THREADS) mask[i] = f_error(Fr, A[2 * i], A[2 * i + 1], B[2 * i], B[2 * i + 1]) <= thr2 ? 1 : 0;
+    for (int i = tid; i < n; i += RS_THREADS) mask[i] = f_inlier(Fr, A[2 * i], A[2 * i + 1], B[2 * i], B[2 * i + 1], thr2) ? 1 : 0;
   if (tid == 0) {
     n_inl[s] = take ? tot : cnt;
     for (int k = 0; k < 9; ++k) F_out[9 * s + k] = take ? Fr[k] : Fb[k];
@@ -467,8 +468,9 @@ __device__ __forceinline__ bool pnp_inlier(const double* T, const double* K, con
   q_rot(T, X, Xc);
   const double z = Xc[2] + T[6];
   if (z < 1e-6) return false;
-  const double ex = uv[0] - ((Xc[0] + T[4]) / z * K[0] + K[2]), ey = uv[1] - ((Xc[1] + T[5]) / z * K[1] + K[3]);
-  return ex * ex + ey * ey <= thr2;
+  // (u - (fx x / z + cx))^2 + (v - (fy y / z + cy))^2 <= thr2, multiplied through by z^2 > 0: no fp64 division
+  const double ex = (uv[0] - K[2]) * z - (Xc[0] + T[4]) * K[0], ey = (uv[1] - K[3]) * z - (Xc[1] + T[5]) * K[1];
+  return ex * ex + ey * ey <= thr2 * (z * z);
 }
 
 __global__ void __launch_bounds__(RS_THREADS) pnp_ransac_kernel(const int* __restrict__ npts, const float* __restrict__ p3d,
