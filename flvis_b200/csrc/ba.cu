@@ -1093,6 +1093,216 @@ __global__ void __launch_bounds__(BA_THREADS, 1) ba_kernel(BAArgs a) {
   if (C > 1) cluster.sync();                            // no CTA leaves while another may still read its shared memory
 }
 
+
+// ---- pose-only BA (OptimizeInFrame::optimize, src/processing/optimize_in_frame.cpp:10-90): one pose, all landmarks fixed --------
+// The general kernel spends most of a 0.16 ms pose-only solve in its set-up passes (slot tables, CSR, chunking) that a problem
+// with ONE 6x6 system does not need.  This kernel runs the same LM control flow (ba_kernel above / optimization_algorithm_
+// levenberg.cpp:58-175) on one CTA per sequence with a thread per edge: residual + pose Jacobian -> block-reduced H (21) and
+// b (6) -> LDL^T of the damped 6x6 -> exp-map update -> robust chi2; cull of chi2 > threshold between the two optimize() calls.
+constexpr int PO_THREADS = 512;
+constexpr int PO_WARPS = PO_THREADS / 32;
+
+struct PoSh {
+  double part[PO_WARPS][28];
+  double H[21], b[6], x[6], pose[7], pbk[7];
+  double red[PO_WARPS];
+  int fail;
+};
+
+__device__ double po_block_sum(double v, double* red) {
+  v = warp_sum(v);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  double t = 0;
+#pragma unroll
+  for (int i = 0; i < PO_WARPS; ++i) t += red[i];
+  return t;
+}
+
+__device__ double po_chi2(const flv_ba_problem& pb, const Cam& cam, const double* pose, const double* lms, const int* el, const double* uv,
+                          const uint8_t* act, double delta, double* red) {
+  double acc = 0;
+  const double d2 = delta * delta;
+  for (int e = threadIdx.x; e < pb.n_edges; e += PO_THREADS) {
+    if (!act[e]) continue;
+    double r[2];
+    edge_eval<false>(pose, lms + 3 * (size_t)el[e], uv + 2 * (size_t)e, cam, r, nullptr, nullptr);
+    const double c = r[0] * r[0] + r[1] * r[1];
+    acc += (c <= d2) ? c : 2 * sqrt(c) * delta - d2;
+  }
+  return po_block_sum(acc, red);
+}
+
+__global__ void __launch_bounds__(PO_THREADS, 1) ba_pose_only_kernel(BAArgs a) {
+  __shared__ PoSh sh;
+  const int s = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const flv_ba_problem pb = a.problems[s];
+  const Cam cam = {pb.fx, pb.fy, pb.cx, pb.cy};
+  double* pose_g = a.poses + (size_t)s * a.max_poses * 7;
+  const double* lms = a.lms + (size_t)s * a.max_lms * 3;
+  const int* el = a.el + (size_t)s * a.max_edges;
+  const double* uv = a.uv + (size_t)s * a.max_edges * 2;
+  uint8_t* act = a.active + (size_t)s * a.max_edges;
+  const double delta = a.prm.huber_delta, d2 = delta * delta;
+  flv_ba_stats st;
+  st.iterations_run = 0; st.n_culled = 0; st.ok = 1; st.reserved = 0;
+  st.chi2_initial = st.chi2_after1 = st.chi2_final = 0; st.lambda_final = 0;
+  if (pb.n_poses != 1 || !pb.fix_landmarks || pb.n_edges < 0) {            // not a pose-only problem: this context cannot solve it
+    if (tid == 0) { st.ok = 0; st.reserved = 5; a.stats[s] = st; }
+    return;
+  }
+  if (tid < 7) sh.pose[tid] = pose_g[tid];
+  __syncthreads();
+  const double* pose = sh.pose;
+  st.chi2_initial = po_chi2(pb, cam, pose, lms, el, uv, act, delta, sh.red);
+  double lambda = 0;
+  for (int phase = 0; phase < 2; ++phase) {
+    const int iters = phase == 0 ? a.prm.iters1 : a.prm.iters2;
+    // the pose is optimised iff it is not the fixed vertex and has at least one active edge (sparse_optimizer.cpp:168-272)
+    int cnt = 0;
+    for (int e = tid; e < pb.n_edges; e += PO_THREADS) cnt += act[e] ? 1 : 0;
+    const int nact = (int)(po_block_sum((double)cnt, sh.red) + 0.5);
+    const bool free_pose = pb.fixed_pose != 0 && nact > 0;
+    double ni = 2, currentChi = 0;
+    for (int it = 0; it < iters; ++it) {
+      if (it == 0) currentChi = po_chi2(pb, cam, pose, lms, el, uv, act, delta, sh.red);
+      // linearisation: H = sum rho' B^T B, b = -sum rho' B^T r (as sqrt(rho') B and -sqrt(rho') r, like ba_kernel's pose pass)
+      double H[21], b[6];
+#pragma unroll
+      for (int i = 0; i < 21; ++i) H[i] = 0;
+#pragma unroll
+      for (int i = 0; i < 6; ++i) b[i] = 0;
+      if (free_pose)
+        for (int e = tid; e < pb.n_edges; e += PO_THREADS) {
+          if (!act[e]) continue;
+          double r[2], A[6], B[12];
+          edge_eval<true>(pose, lms + 3 * (size_t)el[e], uv + 2 * (size_t)e, cam, r, A, B);
+          const double c = r[0] * r[0] + r[1] * r[1];
+          const double sr = (c <= d2) ? 1.0 : sqrt(delta / sqrt(c));
+#pragma unroll
+          for (int i = 0; i < 12; ++i) B[i] *= sr;
+          const double g0 = -sr * r[0], g1 = -sr * r[1];
+          int k2 = 0;
+#pragma unroll
+          for (int i = 0; i < 6; ++i) {
+            b[i] += B[i] * g0 + B[6 + i] * g1;
+#pragma unroll
+            for (int j = i; j < 6; ++j) H[k2++] += B[i] * B[j] + B[6 + i] * B[6 + j];
+          }
+        }
+      __syncthreads();
+#pragma unroll
+      for (int i = 0; i < 21; ++i) { const double v = warp_sum(H[i]); if (lane == 0) sh.part[warp][i] = v; }
+#pragma unroll
+      for (int i = 0; i < 6; ++i) { const double v = warp_sum(b[i]); if (lane == 0) sh.part[warp][21 + i] = v; }
+      __syncthreads();
+      if (tid < 27) {
+        double v = 0;
+        for (int w = 0; w < PO_WARPS; ++w) v += sh.part[w][tid];
+        if (tid < 21) sh.H[tid] = v; else sh.b[tid - 21] = v;
+      }
+      __syncthreads();
+      if (it == 0) {
+        double md = 0;
+        if (free_pose) for (int i = 0; i < 6; ++i) md = fmax(md, fabs(sh.H[sym21(i, i)]));
+        lambda = 1e-5 * md; ni = 2;
+      }
+      double rho = 0;
+      int qmax = 0;
+      do {
+        // (H + lambda I) x = b by LDL^T without pivoting (every thread redundantly on registers: 6x6)
+        bool ok2 = true;
+        double scale = 0, tempChi = 1.7976931348623157e308;
+        if (free_pose) {
+          double M[6][6], y[6], d[6];
+#pragma unroll
+          for (int i = 0; i < 6; ++i) {
+#pragma unroll
+            for (int j = 0; j <= i; ++j) M[i][j] = sh.H[sym21(j, i)] + (i == j ? lambda : 0.0);
+            y[i] = sh.b[i];
+          }
+#pragma unroll
+          for (int j = 0; j < 6; ++j) {
+            double dj = M[j][j];
+#pragma unroll
+            for (int k = 0; k < j; ++k) dj -= M[j][k] * M[j][k] * d[k];
+            if (!(dj > 0)) ok2 = false;
+            d[j] = dj;
+#pragma unroll
+            for (int i = j + 1; i < 6; ++i) {
+              double v = M[i][j];
+#pragma unroll
+              for (int k = 0; k < j; ++k) v -= M[i][k] * M[j][k] * d[k];
+              M[i][j] = v / dj;
+            }
+          }
+          if (ok2) {
+#pragma unroll
+            for (int i = 0; i < 6; ++i) {
+#pragma unroll
+              for (int k = 0; k < i; ++k) y[i] -= M[i][k] * y[k];
+            }
+#pragma unroll
+            for (int i = 0; i < 6; ++i) y[i] /= d[i];
+#pragma unroll
+            for (int i = 5; i >= 0; --i) {
+#pragma unroll
+              for (int k = i + 1; k < 6; ++k) y[i] -= M[k][i] * y[k];
+            }
+#pragma unroll
+            for (int i = 0; i < 6; ++i) scale += y[i] * (lambda * y[i] + sh.b[i]);
+            __syncthreads();                                   // everyone has read H / b / pose
+            if (tid < 7) sh.pbk[tid] = sh.pose[tid];
+            if (tid < 6) sh.x[tid] = y[tid];
+            __syncthreads();
+            if (tid == 0) pose_oplus(sh.pose, sh.x);
+            __syncthreads();
+          }
+        }
+        if (ok2) tempChi = po_chi2(pb, cam, pose, lms, el, uv, act, delta, sh.red);
+        rho = (currentChi - tempChi) / (scale + 1e-3);
+        if (rho > 0 && isfinite(tempChi)) {
+          double alpha = 1. - (2 * rho - 1) * (2 * rho - 1) * (2 * rho - 1);
+          alpha = fmin(alpha, 2. / 3.);
+          lambda *= fmax(1. / 3., alpha);
+          ni = 2;
+          currentChi = tempChi;
+        } else {
+          lambda *= ni; ni *= 2;
+          if (ok2 && free_pose) { __syncthreads(); if (tid < 7) sh.pose[tid] = sh.pbk[tid]; __syncthreads(); }
+          if (!isfinite(lambda)) break;
+        }
+        ++qmax;
+      } while (rho < 0 && qmax < 10);
+      if (a.trace && tid == 0 && st.iterations_run < BA_TRACE_ITERS) {
+        double* tr = a.trace + ((size_t)s * BA_TRACE_ITERS + st.iterations_run) * 4;
+        tr[0] = currentChi; tr[1] = lambda; tr[2] = rho; tr[3] = (double)qmax;
+      }
+      ++st.iterations_run;
+      if (qmax == 10 || rho == 0 || !isfinite(lambda)) break;
+    }
+    if (phase == 0) {
+      st.chi2_after1 = po_chi2(pb, cam, pose, lms, el, uv, act, delta, sh.red);
+      int culled = 0, remaining = 0;
+      for (int e = tid; e < pb.n_edges; e += PO_THREADS) {
+        if (!act[e]) continue;
+        double r[2];
+        edge_eval<false>(pose, lms + 3 * (size_t)el[e], uv + 2 * (size_t)e, cam, r, nullptr, nullptr);
+        if (r[0] * r[0] + r[1] * r[1] > a.prm.cull_chi2) { act[e] = 0; ++culled; } else ++remaining;
+      }
+      st.n_culled = (int)(po_block_sum((double)culled, sh.red) + 0.5);
+      const int rem = (int)(po_block_sum((double)remaining, sh.red) + 0.5);
+      __syncthreads();
+      if (rem < a.prm.min_edges_after_cull) { st.ok = 0; break; }
+    }
+  }
+  st.chi2_final = po_chi2(pb, cam, pose, lms, el, uv, act, delta, sh.red);
+  st.lambda_final = lambda;
+  if (tid < 7) pose_g[tid] = sh.pose[tid];
+  if (tid == 0) a.stats[s] = st;
+}
+
 __global__ void ba_debug_edges_kernel(int n, const double* poses, const double* pts, const double* uv, Cam cam, double* out) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
@@ -1128,6 +1338,13 @@ cudaError_t launch_ba(const BAArgs& a, int n_streams, int C, size_t smem, cudaSt
   at[0].val.clusterDim.x = (unsigned)C; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
   cfg.attrs = at; cfg.numAttrs = 1;
   return cudaLaunchKernelEx(&cfg, ba_kernel, a);
+}
+
+// pose-only problems (one pose, fixed landmarks) run on ba_pose_only_kernel unless FLV_BA_POSE_ONLY_FAST=0 (A/B switch)
+bool pose_only_fast() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("FLV_BA_POSE_ONLY_FAST"); v = (e && atoi(e) == 0) ? 0 : 1; }
+  return v == 1;
 }
 
 // CTAs per window: FLV_BA_CLUSTER / flv_set_ba_cluster (1, 2 or 4; default 4) for windows that optimise landmarks, 1 for pose-only
@@ -1218,6 +1435,12 @@ int flv_ba_optimize(flv_ctx* ctx, int n_streams, const flv_ba_problem* problems,
   if (mem == FLV_MEM_DEVICE) {
     a.problems = problems; a.poses = poses; a.lms = landmarks; a.ep = edge_pose; a.el = edge_lm; a.uv = edge_uv;
     a.active = edge_active; a.stats = stats;
+    if (MP == 1 && pose_only_fast()) {       // a context reserved for one pose (the trackers' OptimizeInFrame): pose-only kernel;
+      ba_pose_only_kernel<<<n_streams, PO_THREADS, 0, stream>>>(a);     // a problem that is not pose-only comes back with reserved = 5
+      ctx->launches++;
+      FLV_CUDA(ctx, cudaGetLastError());
+      return FLV_OK;
+    }
     if (MP > BA_MAX_FREE + 1) {       // reserved for large windows: the global-memory solver takes any size
       FLV_CUDA(ctx, flv_ba_big_launch(n_streams, problems, prm, poses, landmarks, edge_pose, edge_lm, edge_uv, edge_active, stats, MP, ML, ME,
                                       a.ws, a.trace, stream));
@@ -1231,10 +1454,11 @@ int flv_ba_optimize(flv_ctx* ctx, int n_streams, const flv_ba_problem* problems,
     return FLV_OK;
   }
   int C = 1;
-  bool big = false;
+  bool big = false, pose_only = pose_only_fast();
   for (int s = 0; s < n_streams; ++s) {
     if (!problems[s].fix_landmarks && problems[s].n_poses >= 3) C = ba_cluster_size(ctx);
     if (problems[s].n_poses > BA_MAX_FREE + 1) big = true;       // (a fixed pose may not exist: be conservative)
+    if (problems[s].n_poses != 1 || !problems[s].fix_landmarks) pose_only = false;
   }
   for (int s = 0; s < n_streams; ++s) {
     const flv_ba_problem& p = problems[s];
@@ -1255,7 +1479,9 @@ int flv_ba_optimize(flv_ctx* ctx, int n_streams, const flv_ba_problem* problems,
   FLV_CUDA(ctx, cudaMemcpyAsync(d_prob, problems, S * sizeof(flv_ba_problem), cudaMemcpyHostToDevice, stream));
   a.problems = d_prob; a.poses = (double*)(ds + o_pose); a.lms = (double*)(ds + o_lm); a.uv = (const double*)(ds + o_uv);
   a.ep = (const int*)(ds + o_ep); a.el = (const int*)(ds + o_el); a.active = (uint8_t*)(ds + o_act); a.stats = d_stats;
-  if (big)
+  if (pose_only)
+    ba_pose_only_kernel<<<n_streams, PO_THREADS, 0, stream>>>(a);
+  else if (big)
     FLV_CUDA(ctx, flv_ba_big_launch(n_streams, a.problems, prm, a.poses, a.lms, a.ep, a.el, a.uv, a.active, a.stats, MP, ML, ME, a.ws, a.trace, stream));
   else
     FLV_CUDA(ctx, launch_ba(a, n_streams, C, smem, stream));
@@ -1269,7 +1495,7 @@ int flv_ba_optimize(flv_ctx* ctx, int n_streams, const flv_ba_problem* problems,
   for (int s = 0; s < n_streams; ++s)
     if (stats[s].reserved)
       FLV_FAIL(ctx, FLV_ERR_UNSUPPORTED, "stream %d: %s", s,
-               stats[s].reserved == 1 ? "pose count outside [1,32]" : stats[s].reserved == 2 ? "more than 24 free poses (reduced system > 144)" : stats[s].reserved == 3 ? "pose-pair list capacity exceeded" : "window too large for the shared-memory landmark chunks");
+               stats[s].reserved == 1 ? "pose count outside [1,32]" : stats[s].reserved == 2 ? "more than 24 free poses (reduced system > 144)" : stats[s].reserved == 3 ? "pose-pair list capacity exceeded" : stats[s].reserved == 5 ? "not a pose-only problem" : "window too large for the shared-memory landmark chunks");
   return FLV_OK;
 }
 
