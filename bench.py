@@ -444,10 +444,10 @@ def run_ours(args, wl, pools):
 
 def other_workloads(args, S):
     """BASELINE.json's other configurations (KITTI-shaped stereo, W=20; D435i depth + IMU, W=8) through the same bench, shortened
-    (2 repetitions of <= 10 steps, no CPU legs), each in its own process after this one released the GPU."""
+    (3 repetitions of <= 10 steps -- the median survives one slow repetition --, no CPU legs), each in its own process after this one released the GPU."""
     res = {}
     for name in ("kitti", "d435"):
-        cmd = [sys.executable, os.path.abspath(__file__), "--workload", name, "--reps", "2", "--steps", str(min(args.steps, 10)), "--warmup", "3",
+        cmd = [sys.executable, os.path.abspath(__file__), "--workload", name, "--reps", "3", "--steps", str(min(args.steps, 10)), "--warmup", "3",
                "--streams", str(S), "--groups", str(args.groups), "--no-cpu", "--no-single", "--no-others"]
         try:
             r = subprocess.run(cmd, capture_output=True, text=True, timeout=300)
