@@ -488,8 +488,8 @@ __device__ void setup_cluster(const flv_ba_problem& pb, const int* ep, const int
 // Pass C: warp per (free pose, part of its slot runs): Hpp diagonal block and bp.
 __device__ void build_system(const flv_ba_problem& pb, const Cam& cam, const double* poses, const double* lms,
                              double delta, Ws& ws, Sh& sh) {
-  const int P = pb.n_poses, L = pb.n_landmarks, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int ME = ws.ME, ML = ws.ML;
+  const int P = pb.n_poses, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int ML = ws.ML;
   const double d2 = delta * delta;
   if (!pb.fix_landmarks) {
     mark(sh, 10);
@@ -592,8 +592,8 @@ __device__ void build_system(const flv_ba_problem& pb, const Cam& cam, const dou
 // 6x6 block), member lists hold chunk-local positions, so every operand of the inner loop is a shared-memory read.
 __device__ void solve_system(const flv_ba_problem& pb, const Cam& cam, const double* poses, const double* lms, double delta,
                              double lambda, double* S, double* y, double* chunk, int ld, Ws& ws, Sh& sh, unsigned& mpar) {
-  const int L = pb.n_landmarks, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int np = sh.np, n = 6 * np, ME = ws.ME, ML = ws.ML;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int np = sh.np, n = 6 * np, ML = ws.ML;
   const int nblk = np * (np + 1) / 2;
   // reduced system starts as the pose blocks (+ lambda); the chunks subtract W Dinv W^T from it
   // pose-pair member lists -> shared memory by TMA bulk copy (members_stage): all chunks of this CTA at once if they fit (then
