@@ -210,6 +210,12 @@ def run_ours(args, wl, pools):
 
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    # host threads per rank that wait on the GPU most of the time: one per stream group, the local-map shards, this thread.
+    # CUDA's default is to spin while waiting; when the ranks of a node have more such threads than the node has cores, they
+    # sleep instead (cudaDeviceScheduleBlockingSync, set by the library for every context it creates)
+    waiting_threads = args.groups + 2 + 1
+    if world * waiting_threads > (os.cpu_count() or 1):
+        os.environ.setdefault("FLV_BLOCKING_SYNC", "1")
     if world > 1:
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")     # keep stdout to the one JSON line
         dist.init_process_group("nccl", init_method="env://", device_id=torch.device("cuda", local_rank))
@@ -393,7 +399,7 @@ def run_ours(args, wl, pools):
                                   "rewrites every pyramid",
                        "parallelism": f"sequences sharded {S}/GPU x {world} GPU, no collective in the frame loop; per-frame results of all ranks "
                                       "all-gathered (NCCL) once per timed region" + ("" if world > 1 else " when N > 1"),
-                       "per_rank_ms": per_rank_ms},
+                       "per_rank_ms": per_rank_ms, "host_wait": "blocking" if os.environ.get("FLV_BLOCKING_SYNC") == "1" else "spin"},
             "e2e": {"value": frames / (med_e * 1e-3), "unit": "frames/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "ms_per_step": med_e / args.steps, "value_min_max": [frames / (max(e2e_runs) * 1e-3), frames / (min(e2e_runs) * 1e-3)]},
             "gpu_launches": int(launches),

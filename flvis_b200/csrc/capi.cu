@@ -63,6 +63,12 @@ int flv_create(flv_ctx** out, int device, int max_streams, int img_w, int img_h,
   ctx->device = device; ctx->S = max_streams; ctx->w = img_w; ctx->h = img_h; ctx->max_pts = max_pts;
   ctx->ba_member_buf = -1;
   FLV_CUDA(ctx, cudaSetDevice(device));
+  // FLV_BLOCKING_SYNC=1: host threads that wait for the GPU sleep instead of spinning (cudaDeviceScheduleBlockingSync).  Every
+  // stream group, local-map shard and caller thread waits on the device most of the time; with several ranks per node that is
+  // more spinning threads than cores (bench.py sets it when ranks x threads exceed the core count).  Best effort.
+  if (const char* e = getenv("FLV_BLOCKING_SYNC")) {
+    if (atoi(e) > 0 && cudaSetDeviceFlags(cudaDeviceScheduleBlockingSync) != cudaSuccess) cudaGetLastError();
+  }
   build_geom(ctx->geom, img_w, img_h);
   {   // cv::buildOpticalFlowPyramid would build a further level for this size: LK would silently lose its coarsest level
     const LevelGeom& top = ctx->geom.lv[ctx->geom.nlev - 1];
