@@ -439,13 +439,13 @@ def run_ours(args, wl, pools):
         if cpu:
             out["cpu_baseline"] = cpu
     trk.close(); lmap.close()
+    if world > 1:
+        dist.destroy_process_group()              # the collective part is over: the side measurements below are rank 0's own
     if out is not None:
         out["roofline"]["isolated_launch"] = lk_isolated(f0, feeder.n_startup, W, H, load_peaks())
         if world == 1 and not args.no_others and args.workload == "euroc":
             out["other_workloads"] = other_workloads(args, S)
         print(json.dumps(out))
-    if world > 1:
-        dist.destroy_process_group()
     return out
 
 
